@@ -1,0 +1,1177 @@
+// gl_oracle.cpp -- CPU parity oracle (TEST INFRASTRUCTURE ONLY; see gl_oracle.h header comment).
+//
+// A deliberately plain restatement of the reference CPU algorithm. It follows the reference's
+// control flow (bit-reverse + radix-2 DIT NTT, per-column LDE, transpose + row bit-reversal,
+// recursive Merkle fill, coefficient-domain FRI fold + re-FFT) so that it is an independent
+// check of the GPU path, which uses different algorithms (four-step NTT, coset-wise LDE,
+// level-order Merkle build, value-domain leaf-local FRI fold).
+#include "gl_oracle.h"
+
+#include <algorithm>
+#include <cassert>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "gl_poseidon_constants.h"
+
+typedef unsigned __int128 u128;
+typedef uint64_t u64;
+
+namespace {
+
+// ------------------------------------------------------------------ field
+// field/src/goldilocks_field.rs:13-25,198
+const u64 P = 0xFFFFFFFF00000001ULL;
+const u64 EPS = 0xFFFFFFFFULL;
+// field/src/goldilocks_field.rs:80,87,76
+const u64 MULTIPLICATIVE_GROUP_GENERATOR = 14293326489335486720ULL;
+const u64 POWER_OF_TWO_GENERATOR = 7277203076849721926ULL;
+const uint32_t TWO_ADICITY = 32;
+
+// to_canonical_u64, goldilocks_field.rs:216-224
+inline u64 canon(u64 c) { return c >= P ? c - P : c; }
+
+// Add, goldilocks_field.rs:245-267
+inline u64 fadd(u64 a, u64 b) {
+    u64 sum = a + b;
+    bool over = sum < a;
+    u64 sum2 = sum + (over ? EPS : 0);
+    bool over2 = sum2 < sum;
+    if (over2) sum2 += EPS;
+    return sum2;
+}
+// Sub, goldilocks_field.rs:282-304
+inline u64 fsub(u64 a, u64 b) {
+    u64 diff = a - b;
+    bool under = a < b;
+    u64 diff2 = diff - (under ? EPS : 0);
+    bool under2 = diff2 > diff;
+    if (under2) diff2 -= EPS;
+    return diff2;
+}
+// reduce128, goldilocks_field.rs:401-415 (+ add_no_canonicalize_trashing_input :355-389)
+inline u64 reduce128(u128 x) {
+    u64 x_lo = (u64)x, x_hi = (u64)(x >> 64);
+    u64 x_hi_hi = x_hi >> 32;
+    u64 x_hi_lo = x_hi & EPS;
+    u64 t0 = x_lo - x_hi_hi;
+    if (x_lo < x_hi_hi) t0 -= EPS;
+    u64 t1 = x_hi_lo * EPS;
+    u64 res = t0 + t1;
+    if (res < t0) res += EPS;
+    return res;
+}
+// Mul, goldilocks_field.rs:313-320
+inline u64 fmul(u64 a, u64 b) { return reduce128((u128)a * (u128)b); }
+inline u64 fsqr(u64 a) { return fmul(a, a); }
+inline u64 fneg(u64 a) {
+    u64 c = canon(a);
+    return c == 0 ? 0 : P - c;
+}
+// exp_u64 (types.rs:359-376): square-and-multiply
+u64 fexp(u64 base, u64 e) {
+    u64 cur = base, prod = 1;
+    while (e) {
+        if (e & 1) prod = fmul(prod, cur);
+        cur = fsqr(cur);
+        e >>= 1;
+    }
+    return prod;
+}
+// try_inverse = a^(p-2) (goldilocks_field.rs:108-147; any addition chain gives the same value)
+u64 finv(u64 a) { return canon(a) == 0 ? 0 : fexp(a, P - 2); }
+// primitive_root_of_unity, types.rs:268-272
+u64 primitive_root_of_unity(uint32_t n_log) {
+    assert(n_log <= TWO_ADICITY);
+    u64 b = POWER_OF_TWO_GENERATOR;
+    for (uint32_t i = 0; i < TWO_ADICITY - n_log; i++) b = fsqr(b);
+    return b;
+}
+// inverse_2exp, types.rs:226-266 : for exp <= two_adicity, 2^-k = p - (p-1)/2^k
+u64 inverse_2exp(uint32_t k) {
+    if (k <= TWO_ADICITY) return P - ((P - 1) >> k);
+    return finv(fexp(2, k));
+}
+
+// ------------------------------------------------------------------ quadratic extension
+// goldilocks_extensions.rs:14-27 (W = 7), extension/quadratic.rs:180-193
+struct E2 {
+    u64 a, b;
+};
+inline E2 e2(u64 a, u64 b = 0) { return E2{a, b}; }
+inline E2 eadd(E2 x, E2 y) { return E2{fadd(x.a, y.a), fadd(x.b, y.b)}; }
+inline E2 esub(E2 x, E2 y) { return E2{fsub(x.a, y.a), fsub(x.b, y.b)}; }
+inline E2 emul(E2 x, E2 y) {
+    u64 c0 = fadd(fmul(x.a, y.a), fmul(7, fmul(x.b, y.b)));
+    u64 c1 = fadd(fmul(x.a, y.b), fmul(x.b, y.a));
+    return E2{c0, c1};
+}
+inline E2 escale(E2 x, u64 s) { return E2{fmul(x.a, s), fmul(x.b, s)}; }
+// try_inverse, extension/quadratic.rs:86-100: a^-1 = frob(a) / (a * frob(a)), frob = conjugation
+E2 einv(E2 x) {
+    u64 norm = fsub(fsqr(x.a), fmul(7, fsqr(x.b)));
+    u64 ninv = finv(norm);
+    return E2{fmul(x.a, ninv), fmul(fneg(x.b), ninv)};
+}
+inline bool eeq(E2 x, E2 y) { return canon(x.a) == canon(y.a) && canon(x.b) == canon(y.b); }
+E2 eexp(E2 base, u64 e) {
+    E2 cur = base, prod = e2(1);
+    while (e) {
+        if (e & 1) prod = emul(prod, cur);
+        cur = emul(cur, cur);
+        e >>= 1;
+    }
+    return prod;
+}
+
+// ------------------------------------------------------------------ bit reversal
+uint32_t log2_strict(size_t n) {
+    uint32_t l = 0;
+    while (((size_t)1 << l) < n) l++;
+    if (((size_t)1 << l) != n) {
+        fprintf(stderr, "oracle: Not a power of two: %zu\n", n);  // util/src/lib.rs:28
+        abort();
+    }
+    return l;
+}
+// reverse_bits, plonky2/src/util/mod.rs:33-41
+inline u64 reverse_bits(u64 x, uint32_t bits) {
+    u64 r = 0;
+    for (uint32_t i = 0; i < bits; i++) r |= ((x >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+// reverse_index_bits_in_place, util/src/lib.rs:185-234 (semantics: arr[i] <-> arr[bitrev(i)])
+void reverse_index_bits_in_place(u64* arr, size_t n, size_t w) {
+    uint32_t lg = log2_strict(n);
+    std::vector<u64> tmp(w);
+    for (size_t i = 0; i < n; i++) {
+        size_t j = reverse_bits(i, lg);
+        if (i < j) {
+            if (w == 1) {
+                std::swap(arr[i], arr[j]);
+            } else {
+                memcpy(tmp.data(), arr + i * w, w * 8);
+                memcpy(arr + i * w, arr + j * w, w * 8);
+                memcpy(arr + j * w, tmp.data(), w * 8);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ NTT
+// fft_root_table, field/src/fft.rs:14-33
+typedef std::vector<std::vector<u64>> RootTable;
+RootTable fft_root_table(size_t n) {
+    uint32_t lg_n = log2_strict(n);
+    std::vector<u64> bases;
+    u64 base = primitive_root_of_unity(lg_n);
+    bases.push_back(base);
+    for (uint32_t i = 1; i < lg_n; i++) {
+        base = fsqr(base);
+        bases.push_back(base);
+    }
+    RootTable t;
+    for (uint32_t lg_m = 1; lg_m <= lg_n; lg_m++) {
+        size_t half_m = (size_t)1 << (lg_m - 1);
+        u64 b = bases[lg_n - lg_m];
+        size_t cnt = std::max(half_m, (size_t)2);
+        std::vector<u64> row(cnt);
+        u64 cur = 1;
+        for (size_t i = 0; i < cnt; i++) {
+            row[i] = cur;
+            cur = fmul(cur, b);
+        }
+        t.push_back(std::move(row));
+    }
+    return t;
+}
+// fft_classic (+ scalar fft_classic_simd), field/src/fft.rs:95-202
+void fft_classic(u64* values, size_t n, uint32_t r, const RootTable& root_table) {
+    reverse_index_bits_in_place(values, n, 1);
+    uint32_t lg_n = log2_strict(n);
+    if (root_table.size() != lg_n) {
+        fprintf(stderr, "oracle: Expected root table of length %u, but it was %zu.\n", lg_n,
+                root_table.size());
+        abort();
+    }
+    if (r > 0) {
+        size_t mask = ~(((size_t)1 << r) - 1);
+        for (size_t i = 0; i < n; i++) values[i] = values[i & mask];
+    }
+    for (uint32_t lg_half_m = r; lg_half_m < lg_n; lg_half_m++) {
+        size_t m = (size_t)1 << (lg_half_m + 1);
+        size_t half_m = m / 2;
+        const std::vector<u64>& omega_table = root_table[lg_half_m];
+        for (size_t k = 0; k < n; k += m) {
+            for (size_t j = 0; j < half_m; j++) {
+                u64 omega = omega_table[j];
+                u64 t = fmul(omega, values[k + half_m + j]);
+                u64 u = values[k + j];
+                values[k + j] = fadd(u, t);
+                values[k + half_m + j] = fsub(u, t);
+            }
+        }
+    }
+}
+// fft_with_options, fft.rs:53-61
+void fft_with_options(u64* buf, size_t n, uint32_t zero_factor, const RootTable* rt) {
+    if (n == 1) return;
+    if (rt) {
+        fft_classic(buf, n, zero_factor, *rt);
+    } else {
+        RootTable t = fft_root_table(n);
+        fft_classic(buf, n, zero_factor, t);
+    }
+}
+// ifft_with_options, fft.rs:68-91
+void ifft_with_options(u64* buf, size_t n, const RootTable* rt) {
+    uint32_t lg_n = log2_strict(n);
+    u64 n_inv = inverse_2exp(lg_n);
+    fft_with_options(buf, n, 0, rt);
+    if (n == 1) return;
+    buf[0] = fmul(buf[0], n_inv);
+    buf[n / 2] = fmul(buf[n / 2], n_inv);
+    for (size_t i = 1; i < n / 2; i++) {
+        size_t j = n - i;
+        u64 ci = fmul(buf[j], n_inv);
+        u64 cj = fmul(buf[i], n_inv);
+        buf[i] = ci;
+        buf[j] = cj;
+    }
+}
+// coset_fft_with_options, polynomial/mod.rs:280-293
+void coset_fft_with_options(u64* buf, size_t n, u64 shift, uint32_t zero_factor, const RootTable* rt) {
+    u64 r = 1;
+    for (size_t i = 0; i < n; i++) {
+        buf[i] = fmul(r, buf[i]);
+        r = fmul(r, shift);
+    }
+    fft_with_options(buf, n, zero_factor, rt);
+}
+// coset_ifft, polynomial/mod.rs:63-73
+void coset_ifft(u64* buf, size_t n, u64 shift) {
+    ifft_with_options(buf, n, nullptr);
+    u64 sinv = finv(shift), r = 1;
+    for (size_t i = 0; i < n; i++) {
+        buf[i] = fmul(buf[i], r);
+        r = fmul(r, sinv);
+    }
+}
+
+// ------------------------------------------------------------------ Poseidon
+// constant_layer, poseidon.rs:630-641
+inline void constant_layer(u64 st[12], int round_ctr) {
+    for (int i = 0; i < 12; i++) st[i] = fadd(st[i], GL_POSEIDON_RC[i + 12 * round_ctr]);
+}
+// sbox_monomial, poseidon.rs:689-696
+inline u64 sbox(u64 x) {
+    u64 x2 = fsqr(x), x4 = fsqr(x2), x3 = fmul(x, x2);
+    return fmul(x3, x4);
+}
+// mds_row_shf + mds_layer, poseidon.rs:180-200,269-290
+inline void mds_layer(u64 st[12]) {
+    u64 out[12];
+    for (int r = 0; r < 12; r++) {
+        u128 res = 0;
+        for (int i = 0; i < 12; i++) res += (u128)st[(i + r) % 12] * (u128)GL_POSEIDON_MDS_CIRC[i];
+        res += (u128)st[r] * (u128)GL_POSEIDON_MDS_DIAG[r];
+        out[r] = reduce128(res);
+    }
+    memcpy(st, out, sizeof(out));
+}
+// full_rounds, poseidon.rs:741-749
+inline void full_rounds(u64 st[12], int* round_ctr) {
+    for (int k = 0; k < GL_POSEIDON_HALF_FULL_ROUNDS; k++) {
+        constant_layer(st, *round_ctr);
+        for (int i = 0; i < 12; i++) st[i] = sbox(st[i]);
+        mds_layer(st);
+        (*round_ctr)++;
+    }
+}
+// mds_partial_layer_init, poseidon.rs:413-441
+inline void mds_partial_layer_init(u64 st[12]) {
+    u64 result[12] = {0};
+    result[0] = st[0];
+    for (int r = 1; r < 12; r++)
+        for (int c = 1; c < 12; c++)
+            result[c] = fadd(result[c], fmul(st[r], GL_POSEIDON_FAST_INIT_MATRIX[(r - 1) * 11 + (c - 1)]));
+    memcpy(st, result, sizeof(result));
+}
+// mds_partial_layer_fast, poseidon.rs:514-542
+inline void mds_partial_layer_fast(u64 st[12], int r) {
+    // d = s0*(circ0+diag0) + sum_i w_hat[i]*s[i]; each product < 2^128, 12 of them < 2^132:
+    // accumulate the field value (the reference uses a u160 accumulator + reduce_u160).
+    u64 d = fmul(st[0], GL_POSEIDON_MDS_CIRC[0] + GL_POSEIDON_MDS_DIAG[0]);
+    for (int i = 1; i < 12; i++) d = fadd(d, fmul(st[i], GL_POSEIDON_FAST_W_HATS[r * 11 + i - 1]));
+    u64 result[12];
+    result[0] = d;
+    for (int i = 1; i < 12; i++)
+        result[i] = fadd(st[i], fmul(st[0], GL_POSEIDON_FAST_VS[r * 11 + i - 1]));  // multiply_accumulate
+    memcpy(st, result, sizeof(result));
+}
+// partial_rounds, poseidon.rs:751-764
+inline void partial_rounds(u64 st[12], int* round_ctr) {
+    for (int i = 0; i < 12; i++) st[i] = fadd(st[i], GL_POSEIDON_FAST_FIRST_RC[i]);
+    mds_partial_layer_init(st);
+    for (int i = 0; i < GL_POSEIDON_PARTIAL_ROUNDS; i++) {
+        st[0] = sbox(st[0]);
+        st[0] = fadd(st[0], GL_POSEIDON_FAST_RC[i]);
+        mds_partial_layer_fast(st, i);
+    }
+    *round_ctr += GL_POSEIDON_PARTIAL_ROUNDS;
+}
+// poseidon, poseidon.rs:766-777
+void poseidon(u64 st[12]) {
+    int round_ctr = 0;
+    full_rounds(st, &round_ctr);
+    partial_rounds(st, &round_ctr);
+    full_rounds(st, &round_ctr);
+    assert(round_ctr == GL_POSEIDON_ROUNDS);
+}
+// poseidon_naive, poseidon.rs:779-801
+void poseidon_naive(u64 st[12]) {
+    int round_ctr = 0;
+    full_rounds(st, &round_ctr);
+    for (int k = 0; k < GL_POSEIDON_PARTIAL_ROUNDS; k++) {
+        constant_layer(st, round_ctr);
+        st[0] = sbox(st[0]);
+        mds_layer(st);
+        round_ctr++;
+    }
+    full_rounds(st, &round_ctr);
+}
+
+struct Hash {
+    u64 e[4];
+};
+// hash_n_to_m_no_pad (num_outputs = 4), hashing.rs:118-145 (overwrite-mode sponge, rate 8)
+Hash hash_no_pad(const u64* in, size_t len) {
+    u64 st[12] = {0};
+    for (size_t off = 0; off < len; off += 8) {
+        size_t c = std::min((size_t)8, len - off);
+        for (size_t i = 0; i < c; i++) st[i] = in[off + i];
+        poseidon(st);
+    }
+    Hash h;
+    for (int i = 0; i < 4; i++) h.e[i] = canon(st[i]);
+    return h;
+}
+// hash_or_noop, plonk/config.rs:63-74
+Hash hash_or_noop(const u64* in, size_t len) {
+    if (len * 8 <= 32) {
+        Hash h = {{0, 0, 0, 0}};
+        for (size_t i = 0; i < len; i++) h.e[i] = canon(in[i]);
+        return h;
+    }
+    return hash_no_pad(in, len);
+}
+// compress / two_to_one, hashing.rs:97-114, poseidon.rs:884-886
+Hash two_to_one(const Hash& l, const Hash& r) {
+    u64 st[12] = {l.e[0], l.e[1], l.e[2], l.e[3], r.e[0], r.e[1], r.e[2], r.e[3], 0, 0, 0, 0};
+    poseidon(st);
+    Hash h;
+    for (int i = 0; i < 4; i++) h.e[i] = canon(st[i]);
+    return h;
+}
+inline bool heq(const Hash& a, const Hash& b) { return memcmp(a.e, b.e, 32) == 0; }
+
+// ------------------------------------------------------------------ Merkle tree
+// fill_subtree, merkle_tree.rs:86-113. digests_buf has 2*(n_leaves-1) hashes.
+Hash fill_subtree(Hash* digests_buf, size_t buf_len, const u64* leaves, size_t n_leaves, size_t W,
+                  int par_depth) {
+    assert(n_leaves == buf_len / 2 + 1);
+    if (buf_len == 0) return hash_or_noop(leaves, W);
+    size_t half = buf_len / 2;
+    Hash* left_buf = digests_buf;           // [0, half-1)
+    Hash* left_digest_mem = digests_buf + half - 1;
+    Hash* right_digest_mem = digests_buf + half;
+    Hash* right_buf = digests_buf + half + 1;
+    size_t sub_len = half - 1;
+    size_t nl = n_leaves / 2;
+    Hash ld, rd;
+    if (par_depth > 0) {  // rayon::join
+        std::thread t([&] { ld = fill_subtree(left_buf, sub_len, leaves, nl, W, par_depth - 1); });
+        rd = fill_subtree(right_buf, sub_len, leaves + nl * W, nl, W, par_depth - 1);
+        t.join();
+    } else {
+        ld = fill_subtree(left_buf, sub_len, leaves, nl, W, 0);
+        rd = fill_subtree(right_buf, sub_len, leaves + nl * W, nl, W, 0);
+    }
+    *left_digest_mem = ld;
+    *right_digest_mem = rd;
+    return two_to_one(ld, rd);
+}
+int ceil_log2(int x) {
+    int l = 0;
+    while ((1 << l) < x) l++;
+    return l;
+}
+// MerkleTree::new + fill_digests_buf, merkle_tree.rs:115-149,193-224
+int merkle_build(const u64* leaves, size_t N, size_t W, uint32_t cap_height, Hash* digests, Hash* cap,
+                 int nthreads) {
+    uint32_t lg = log2_strict(N);
+    if (cap_height > lg) {
+        fprintf(stderr, "oracle: cap_height=%u should be at most log2(leaves.len())=%u\n", cap_height, lg);
+        return 1;
+    }
+    size_t C = (size_t)1 << cap_height;
+    size_t num_digests = 2 * (N - C);
+    if (nthreads < 1) nthreads = 1;
+    if (num_digests == 0) {
+        for (size_t i = 0; i < N; i++) cap[i] = hash_or_noop(leaves + i * W, W);
+        return 0;
+    }
+    size_t sub_digests = num_digests >> cap_height;
+    size_t sub_leaves = N >> cap_height;
+    // one task per cap subtree (par_chunks), recursive join inside
+    int par_total = ceil_log2(nthreads);
+    int par_inside = std::max(0, par_total - (int)cap_height);
+    int outer = std::min<size_t>(C, (size_t)nthreads);
+    std::vector<std::thread> ths;
+    for (int t = 0; t < outer; t++) {
+        ths.emplace_back([=] {
+            for (size_t c = t; c < C; c += outer)
+                cap[c] = fill_subtree(digests + c * sub_digests, sub_digests, leaves + c * sub_leaves * W,
+                                      sub_leaves, W, par_inside);
+        });
+    }
+    for (auto& t : ths) t.join();
+    return 0;
+}
+// merkle_tree_prove, merkle_tree.rs:151-190
+void merkle_prove(size_t leaf_index, size_t leaves_len, uint32_t cap_height, const Hash* digests,
+                  Hash* out) {
+    uint32_t num_layers = log2_strict(leaves_len) - cap_height;
+    size_t digest_len = 2 * (leaves_len - ((size_t)1 << cap_height));
+    size_t tree_index = leaf_index >> num_layers;
+    size_t tree_len = digest_len >> cap_height;
+    const Hash* digest_tree = digests + tree_len * tree_index;
+    size_t pair_index = leaf_index & (((size_t)1 << num_layers) - 1);
+    for (uint32_t i = 0; i < num_layers; i++) {
+        size_t parity = pair_index & 1;
+        pair_index >>= 1;
+        size_t siblings_index = (pair_index << (i + 1)) + ((size_t)1 << i) - 1;
+        size_t sibling_index = 2 * siblings_index + (1 - parity);
+        out[i] = digest_tree[sibling_index];
+    }
+}
+// verify_merkle_proof_to_cap, merkle_proofs.rs:55-107 (single leaf)
+bool merkle_verify(const u64* leaf, size_t W, size_t leaf_index, const Hash* siblings, size_t n_sib,
+                   const Hash* cap) {
+    Hash cur = hash_or_noop(leaf, W);
+    for (size_t i = 0; i < n_sib; i++) {
+        size_t bit = leaf_index & 1;
+        leaf_index >>= 1;
+        cur = bit ? two_to_one(siblings[i], cur) : two_to_one(cur, siblings[i]);
+    }
+    return heq(cur, cap[leaf_index]);
+}
+
+template <class F>
+void parallel_for(size_t n, int nthreads, F f) {
+    if (nthreads <= 1 || n <= 1) {
+        for (size_t i = 0; i < n; i++) f(i);
+        return;
+    }
+    int T = (int)std::min<size_t>(n, nthreads);
+    std::vector<std::thread> ths;
+    for (int t = 0; t < T; t++)
+        ths.emplace_back([=] {
+            for (size_t i = t; i < n; i += T) f(i);
+        });
+    for (auto& t : ths) t.join();
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ PolynomialBatch
+struct glo_commit {
+    size_t B, W, n, N;
+    uint32_t degree_log, rate_bits, cap_height;
+    bool blinding;
+    std::vector<u64> coeffs;   // B x n column-major ("polynomials")
+    std::vector<u64> leaves;   // N x W row-major
+    std::vector<Hash> digests; // 2*(N-C)
+    std::vector<Hash> cap;     // C
+};
+
+namespace {
+const size_t SALT_SIZE = 4;  // oracle.rs:26
+
+// from_values / from_coeffs / lde_values, oracle.rs:57-139; transpose util/mod.rs:25-31
+glo_commit* commit_new(const u64* cols, size_t col_stride, size_t B, uint32_t log_n, uint32_t rate_bits,
+                       uint32_t cap_height, const u64* salt, bool is_coeffs, int nthreads) {
+    if (cap_height > log_n + rate_bits) {
+        fprintf(stderr, "oracle: cap_height=%u should be at most log2(leaves.len())=%u\n", cap_height,
+                log_n + rate_bits);  // merkle_tree.rs:195-200
+        return nullptr;
+    }
+    glo_commit* c = new glo_commit();
+    size_t n = (size_t)1 << log_n, N = n << rate_bits;
+    c->B = B;
+    c->n = n;
+    c->N = N;
+    c->degree_log = log_n;
+    c->rate_bits = rate_bits;
+    c->cap_height = cap_height;
+    c->blinding = salt != nullptr;
+    size_t W = B + (salt ? SALT_SIZE : 0);
+    c->W = W;
+    c->coeffs.resize(B * n);
+    // "IFFT": values.into_par_iter().map(|v| v.ifft())   (root table rebuilt per call: fft.rs:41)
+    RootTable rt_n = fft_root_table(n);
+    parallel_for(B, nthreads, [&](size_t b) {
+        u64* dst = c->coeffs.data() + b * n;
+        memcpy(dst, cols + b * col_stride, n * 8);
+        if (!is_coeffs) ifft_with_options(dst, n, &rt_n);
+        else
+            for (size_t i = 0; i < n; i++) dst[i] = canon(dst[i]);
+    });
+    for (auto& x : c->coeffs) x = canon(x);
+    // "FFT + blinding": lde_values
+    RootTable rt_N = fft_root_table(N);
+    std::vector<u64> lde(W * N);  // column-major Vec<Vec<F>>
+    parallel_for(B, nthreads, [&](size_t b) {
+        u64* dst = lde.data() + b * N;
+        memcpy(dst, c->coeffs.data() + b * n, n * 8);
+        memset(dst + n, 0, (N - n) * 8);  // p.lde(rate_bits): zero-pad
+        coset_fft_with_options(dst, N, MULTIPLICATIVE_GROUP_GENERATOR, rate_bits, &rt_N);
+    });
+    if (salt)
+        for (size_t s = 0; s < SALT_SIZE; s++) memcpy(lde.data() + (B + s) * N, salt + s * N, N * 8);
+    // "transpose LDEs": one row per LDE point
+    c->leaves.resize(N * W);
+    parallel_for(N, nthreads, [&](size_t i) {
+        u64* row = c->leaves.data() + i * W;
+        for (size_t b = 0; b < W; b++) row[b] = canon(lde[b * N + i]);
+    });
+    lde.clear();
+    lde.shrink_to_fit();
+    // reverse_index_bits_in_place(&mut leaves)
+    reverse_index_bits_in_place(c->leaves.data(), N, W);
+    // "build Merkle tree"
+    size_t C = (size_t)1 << cap_height;
+    c->digests.resize(2 * (N - C));
+    c->cap.resize(C);
+    merkle_build(c->leaves.data(), N, W, cap_height, c->digests.data(), c->cap.data(), nthreads);
+    return c;
+}
+}  // namespace
+
+// ------------------------------------------------------------------ Challenger
+struct glo_challenger {
+    u64 sponge_state[12];
+    std::vector<u64> input_buffer, output_buffer;
+};
+namespace {
+// duplexing, challenger.rs:129-144
+void duplexing(glo_challenger* ch) {
+    assert(ch->input_buffer.size() <= 8);
+    for (size_t i = 0; i < ch->input_buffer.size(); i++) ch->sponge_state[i] = ch->input_buffer[i];
+    ch->input_buffer.clear();
+    poseidon(ch->sponge_state);
+    ch->output_buffer.assign(ch->sponge_state, ch->sponge_state + 8);
+}
+// observe_element, challenger.rs:39-48
+void observe_element(glo_challenger* ch, u64 e) {
+    ch->output_buffer.clear();
+    ch->input_buffer.push_back(canon(e));
+    if (ch->input_buffer.size() == 8) duplexing(ch);
+}
+void observe_hash(glo_challenger* ch, const Hash& h) {
+    for (int i = 0; i < 4; i++) observe_element(ch, h.e[i]);
+}
+void observe_cap(glo_challenger* ch, const std::vector<Hash>& cap) {
+    for (auto& h : cap) observe_hash(ch, h);
+}
+// get_challenge, challenger.rs:82-92
+u64 get_challenge(glo_challenger* ch) {
+    if (!ch->input_buffer.empty() || ch->output_buffer.empty()) duplexing(ch);
+    u64 v = ch->output_buffer.back();
+    ch->output_buffer.pop_back();
+    return canon(v);
+}
+// get_extension_challenge, challenger.rs:109-116
+E2 get_extension_challenge(glo_challenger* ch) {
+    u64 a = get_challenge(ch);
+    u64 b = get_challenge(ch);
+    return E2{a, b};
+}
+void observe_ext(glo_challenger* ch, E2 x) {
+    observe_element(ch, x.a);
+    observe_element(ch, x.b);
+}
+
+// ------------------------------------------------------------------ FRI prover
+struct Tree {
+    size_t N, W;
+    uint32_t cap_height;
+    std::vector<u64> leaves;
+    std::vector<Hash> digests, cap;
+};
+
+void put_u64(std::vector<uint8_t>& out, u64 v) {
+    v = canon(v);
+    for (int i = 0; i < 8; i++) out.push_back((uint8_t)(v >> (8 * i)));  // write_field: LE canonical
+}
+void put_hash(std::vector<uint8_t>& out, const Hash& h) {
+    for (int i = 0; i < 4; i++) put_u64(out, h.e[i]);
+}
+
+// ext polynomial coset FFT: shift and roots are base-field, so it acts per component
+// (field/src/field_testing.rs:167-178)
+void ext_coset_fft(std::vector<E2>& v, u64 shift) {
+    size_t n = v.size();
+    std::vector<u64> a(n), b(n);
+    for (size_t i = 0; i < n; i++) {
+        a[i] = v[i].a;
+        b[i] = v[i].b;
+    }
+    coset_fft_with_options(a.data(), n, shift, 0, nullptr);
+    coset_fft_with_options(b.data(), n, shift, 0, nullptr);
+    for (size_t i = 0; i < n; i++) v[i] = E2{canon(a[i]), canon(b[i])};
+}
+}  // namespace
+
+extern "C" {
+
+uint64_t glo_canon(uint64_t a) { return canon(a); }
+uint64_t glo_add(uint64_t a, uint64_t b) { return canon(fadd(a, b)); }
+uint64_t glo_sub(uint64_t a, uint64_t b) { return canon(fsub(a, b)); }
+uint64_t glo_mul(uint64_t a, uint64_t b) { return canon(fmul(a, b)); }
+uint64_t glo_neg(uint64_t a) { return fneg(a); }
+uint64_t glo_inv(uint64_t a) { return canon(finv(a)); }
+uint64_t glo_exp(uint64_t a, uint64_t e) { return canon(fexp(a, e)); }
+uint64_t glo_primitive_root_of_unity(uint32_t k) { return canon(primitive_root_of_unity(k)); }
+uint64_t glo_inverse_2exp(uint32_t k) { return canon(inverse_2exp(k)); }
+uint64_t glo_coset_shift(void) { return MULTIPLICATIVE_GROUP_GENERATOR; }
+void glo_ext2_mul(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]) {
+    E2 r = emul(E2{a[0], a[1]}, E2{b[0], b[1]});
+    out[0] = canon(r.a);
+    out[1] = canon(r.b);
+}
+void glo_ext2_inv(const uint64_t a[2], uint64_t out[2]) {
+    E2 r = einv(E2{a[0], a[1]});
+    out[0] = canon(r.a);
+    out[1] = canon(r.b);
+}
+
+uint64_t glo_reverse_bits(uint64_t x, uint32_t bits) { return reverse_bits(x, bits); }
+void glo_reverse_index_bits_in_place(uint64_t* arr, size_t n, size_t w) { reverse_index_bits_in_place(arr, n, w); }
+
+void glo_fft(uint64_t* buf, uint32_t log_n, uint32_t zf) {
+    size_t n = (size_t)1 << log_n;
+    fft_with_options(buf, n, zf, nullptr);
+    for (size_t i = 0; i < n; i++) buf[i] = canon(buf[i]);
+}
+void glo_ifft(uint64_t* buf, uint32_t log_n) {
+    size_t n = (size_t)1 << log_n;
+    ifft_with_options(buf, n, nullptr);
+    for (size_t i = 0; i < n; i++) buf[i] = canon(buf[i]);
+}
+void glo_coset_fft(uint64_t* buf, uint32_t log_n, uint64_t shift, uint32_t zf) {
+    size_t n = (size_t)1 << log_n;
+    coset_fft_with_options(buf, n, shift, zf, nullptr);
+    for (size_t i = 0; i < n; i++) buf[i] = canon(buf[i]);
+}
+void glo_coset_ifft(uint64_t* buf, uint32_t log_n, uint64_t shift) {
+    size_t n = (size_t)1 << log_n;
+    coset_ifft(buf, n, shift);
+    for (size_t i = 0; i < n; i++) buf[i] = canon(buf[i]);
+}
+// evaluate_naive on the coset, field/src/fft.rs:251-282 / polynomial/mod.rs:476-516
+void glo_naive_coset_eval(const uint64_t* coeffs, uint32_t log_n, uint64_t shift, uint64_t* out) {
+    size_t n = (size_t)1 << log_n;
+    u64 w = primitive_root_of_unity(log_n);
+    u64 x = shift;
+    for (size_t i = 0; i < n; i++) {
+        u64 acc = 0;
+        for (size_t k = n; k-- > 0;) acc = fadd(fmul(acc, x), coeffs[k]);
+        out[i] = canon(acc);
+        x = fmul(x, w);
+    }
+}
+
+void glo_poseidon(uint64_t st[12]) {
+    poseidon(st);
+    for (int i = 0; i < 12; i++) st[i] = canon(st[i]);
+}
+void glo_poseidon_naive(uint64_t st[12]) {
+    poseidon_naive(st);
+    for (int i = 0; i < 12; i++) st[i] = canon(st[i]);
+}
+void glo_hash_no_pad(const uint64_t* in, size_t len, uint64_t out[4]) {
+    Hash h = hash_no_pad(in, len);
+    memcpy(out, h.e, 32);
+}
+void glo_hash_or_noop(const uint64_t* in, size_t len, uint64_t out[4]) {
+    Hash h = hash_or_noop(in, len);
+    memcpy(out, h.e, 32);
+}
+void glo_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]) {
+    Hash a, b;
+    memcpy(a.e, l, 32);
+    memcpy(b.e, r, 32);
+    Hash h = two_to_one(a, b);
+    memcpy(out, h.e, 32);
+}
+void glo_hash_many(const uint64_t* in, size_t n_items, size_t W, uint64_t* out, int nthreads) {
+    int T = std::max(1, nthreads);
+    std::vector<std::thread> ths;
+    for (int t = 0; t < T; t++)
+        ths.emplace_back([=] {
+            size_t lo = n_items * t / T, hi = n_items * (t + 1) / T;
+            for (size_t i = lo; i < hi; i++) {
+                Hash h = hash_or_noop(in + i * W, W);
+                memcpy(out + 4 * i, h.e, 32);
+            }
+        });
+    for (auto& t : ths) t.join();
+}
+
+int glo_merkle_build(const uint64_t* leaves, size_t N, size_t W, uint32_t cap_height, uint64_t* digests,
+                     uint64_t* cap, int nthreads) {
+    return merkle_build(leaves, N, W, cap_height, (Hash*)digests, (Hash*)cap, nthreads);
+}
+void glo_merkle_prove(size_t leaf_index, size_t N, uint32_t cap_height, const uint64_t* digests,
+                      uint64_t* siblings) {
+    merkle_prove(leaf_index, N, cap_height, (const Hash*)digests, (Hash*)siblings);
+}
+int glo_merkle_verify(const uint64_t* leaf, size_t W, size_t leaf_index, const uint64_t* siblings,
+                      size_t n_siblings, const uint64_t* cap, uint32_t cap_height) {
+    (void)cap_height;
+    return merkle_verify(leaf, W, leaf_index, (const Hash*)siblings, n_siblings, (const Hash*)cap) ? 1 : 0;
+}
+
+glo_commit* glo_commit_new(const uint64_t* cols, size_t col_stride, size_t B, uint32_t log_n,
+                           uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, int is_coeffs,
+                           int nthreads) {
+    return commit_new(cols, col_stride, B, log_n, rate_bits, cap_height, salt, is_coeffs != 0, nthreads);
+}
+void glo_commit_free(glo_commit* c) { delete c; }
+size_t glo_commit_leaf_width(const glo_commit* c) { return c->W; }
+const uint64_t* glo_commit_coeffs(const glo_commit* c) { return c->coeffs.data(); }
+const uint64_t* glo_commit_leaves(const glo_commit* c) { return c->leaves.data(); }
+const uint64_t* glo_commit_digests(const glo_commit* c) { return (const u64*)c->digests.data(); }
+const uint64_t* glo_commit_cap(const glo_commit* c) { return (const u64*)c->cap.data(); }
+// get_lde_values, oracle.rs:142-147
+void glo_commit_get_lde_values(const glo_commit* c, size_t index, size_t step, uint64_t* out) {
+    size_t idx = reverse_bits(index * step, c->degree_log + c->rate_bits);
+    memcpy(out, c->leaves.data() + idx * c->W, c->B * 8);
+}
+
+glo_challenger* glo_challenger_new(void) {
+    glo_challenger* ch = new glo_challenger();
+    memset(ch->sponge_state, 0, sizeof(ch->sponge_state));
+    return ch;
+}
+glo_challenger* glo_challenger_clone(const glo_challenger* c) { return new glo_challenger(*c); }
+void glo_challenger_free(glo_challenger* c) { delete c; }
+void glo_challenger_observe(glo_challenger* c, const uint64_t* e, size_t n) {
+    for (size_t i = 0; i < n; i++) observe_element(c, e[i]);
+}
+uint64_t glo_challenger_get_challenge(glo_challenger* c) { return get_challenge(c); }
+size_t glo_challenger_state(const glo_challenger* c, uint64_t state[12], uint64_t inbuf[8]) {
+    for (int i = 0; i < 12; i++) state[i] = canon(c->sponge_state[i]);
+    for (size_t i = 0; i < c->input_buffer.size(); i++) inbuf[i] = c->input_buffer[i];
+    return c->input_buffer.size();
+}
+
+void glo_free(void* p) { free(p); }
+
+void glo_eval_poly_base_at_ext(const uint64_t* coeffs, size_t n, const uint64_t z[2], uint64_t out[2]) {
+    E2 zz{z[0], z[1]}, acc = e2(0);
+    for (size_t k = n; k-- > 0;) acc = eadd(emul(acc, zz), e2(coeffs[k]));
+    out[0] = canon(acc.a);
+    out[1] = canon(acc.b);
+}
+
+// prove_openings (oracle.rs:176-237) -> fri_proof (prover.rs:24-70)
+int glo_prove_openings(const glo_commit* const* oracles, size_t n_oracles, const glo_fri_batch* batches,
+                       size_t n_batches, glo_challenger* ch, const glo_fri_params* params, uint8_t** out,
+                       size_t* out_len, uint64_t* tap_final_poly, uint64_t* tap_betas,
+                       uint64_t* tap_pow_witness, uint64_t* tap_query_indices) {
+    if (n_oracles == 0) return 1;
+    size_t n = oracles[0]->n;
+    uint32_t rate_bits = params->rate_bits;
+    // alpha = challenger.get_extension_challenge()                     oracle.rs:186
+    E2 alpha = get_extension_challenge(ch);
+    u64 alpha_count = 0;  // ReducingFactor.count
+    std::vector<E2> final_poly;  // PolynomialCoeffs::empty()
+    for (size_t bi = 0; bi < n_batches; bi++) {
+        const glo_fri_batch& batch = batches[bi];
+        E2 point{batch.point[0], batch.point[1]};
+        // composition_poly = alpha.reduce_polys_base(polys_coeff)     reducing.rs:83-95
+        std::vector<E2> comp(n, e2(0));
+        E2 base_power = e2(1);
+        for (size_t j = 0; j < batch.num_polys; j++) {
+            const glo_commit* oc = oracles[batch.oracle_index[j]];
+            if (oc->n != n) return 2;
+            const u64* poly = oc->coeffs.data() + (size_t)batch.poly_index[j] * n;
+            alpha_count++;
+            for (size_t k = 0; k < n; k++) comp[k] = eadd(comp[k], escale(base_power, poly[k]));
+            base_power = emul(base_power, alpha);
+        }
+        // quotient = composition_poly.divide_by_linear(point)         division.rs:75-88
+        std::vector<E2> bs(n);
+        E2 acc = e2(0);
+        for (size_t k = n; k-- > 0;) {
+            acc = eadd(emul(acc, point), comp[k]);
+            bs[n - 1 - k] = acc;  // scan over reversed coefficients
+        }
+        bs.pop_back();
+        std::reverse(bs.begin(), bs.end());
+        bs.push_back(e2(0));  // pad back to power of two             oracle.rs:210
+        // alpha.shift_poly(&mut final_poly); final_poly += quotient   reducing.rs:102-106
+        E2 sh = eexp(alpha, alpha_count);
+        alpha_count = 0;
+        if (final_poly.empty()) {
+            final_poly = bs;
+        } else {
+            for (size_t k = 0; k < n; k++) final_poly[k] = eadd(emul(final_poly[k], sh), bs[k]);
+        }
+    }
+    if (tap_final_poly)
+        for (size_t k = 0; k < n; k++) {
+            tap_final_poly[2 * k] = canon(final_poly[k].a);
+            tap_final_poly[2 * k + 1] = canon(final_poly[k].b);
+        }
+    // lde_final_poly = final_poly.lde(rate_bits); values = coset_fft(coset_shift)   oracle.rs:215-220
+    size_t N = n << rate_bits;
+    std::vector<E2> coeffs(N, e2(0));
+    for (size_t k = 0; k < n; k++) coeffs[k] = final_poly[k];
+    std::vector<E2> values = coeffs;
+    ext_coset_fft(values, MULTIPLICATIVE_GROUP_GENERATOR);
+
+    // ---- fri_committed_trees, prover.rs:84-150
+    std::vector<Tree> trees;
+    u64 shift = MULTIPLICATIVE_GROUP_GENERATOR;
+    for (uint32_t round = 0; round < params->num_reductions; round++) {
+        uint32_t arity_bits = params->reduction_arity_bits[round];
+        size_t arity = (size_t)1 << arity_bits;
+        // reverse_index_bits_in_place(&mut values.values); chunks(arity).map(flatten)
+        std::vector<u64> flat(values.size() * 2);
+        for (size_t i = 0; i < values.size(); i++) {
+            flat[2 * i] = canon(values[i].a);
+            flat[2 * i + 1] = canon(values[i].b);
+        }
+        reverse_index_bits_in_place(flat.data(), values.size(), 2);
+        Tree t;
+        t.N = values.size() / arity;
+        t.W = 2 * arity;
+        t.cap_height = params->cap_height;
+        if (t.cap_height > log2_strict(t.N)) return 3;
+        size_t C = (size_t)1 << t.cap_height;
+        t.leaves = std::move(flat);
+        t.digests.resize(2 * (t.N - C));
+        t.cap.resize(C);
+        merkle_build(t.leaves.data(), t.N, t.W, t.cap_height, t.digests.data(), t.cap.data(), 8);
+        observe_cap(ch, t.cap);
+        trees.push_back(std::move(t));
+        E2 beta = get_extension_challenge(ch);
+        if (tap_betas) {
+            tap_betas[2 * round] = beta.a;
+            tap_betas[2 * round + 1] = beta.b;
+        }
+        // coeffs = chunks_exact(arity).map(|chunk| reduce_with_powers(chunk, beta))   plonk_common.rs:118-130
+        std::vector<E2> folded(coeffs.size() / arity);
+        for (size_t j = 0; j < folded.size(); j++) {
+            E2 sum = e2(0);
+            for (size_t i = arity; i-- > 0;) sum = eadd(emul(sum, beta), coeffs[arity * j + i]);
+            folded[j] = sum;
+        }
+        coeffs = std::move(folded);
+        shift = fexp(shift, arity);
+        values = coeffs;
+        ext_coset_fft(values, shift);
+    }
+    // truncate; observe final coefficients                             prover.rs:134-147
+    coeffs.resize(coeffs.size() >> rate_bits);
+    for (auto& c : coeffs) observe_ext(ch, c);
+
+    // ---- fri_proof_of_work, prover.rs:153-202 (smallest qualifying nonce)
+    uint32_t min_leading_zeros = params->proof_of_work_bits + (64 - 64);
+    u64 inter[12];
+    memcpy(inter, ch->sponge_state, sizeof(inter));
+    size_t witness_input_pos = ch->input_buffer.size();
+    for (size_t i = 0; i < witness_input_pos; i++) inter[i] = ch->input_buffer[i];
+    u64 pow_witness = 0;
+    for (u64 cand = 0;; cand++) {
+        u64 st[12];
+        memcpy(st, inter, sizeof(st));
+        st[witness_input_pos] = cand;
+        poseidon(st);
+        u64 resp = canon(st[7]);  // squeeze().last()
+        uint32_t lz = resp == 0 ? 64 : (uint32_t)__builtin_clzll(resp);
+        if (lz >= min_leading_zeros) {
+            pow_witness = cand;
+            break;
+        }
+        if (cand == P - 1) return 4;
+    }
+    observe_element(ch, pow_witness);
+    u64 pow_response = get_challenge(ch);
+    {
+        uint32_t lz = pow_response == 0 ? 64 : (uint32_t)__builtin_clzll(pow_response);
+        if (lz < min_leading_zeros) return 5;
+    }
+    if (tap_pow_witness) *tap_pow_witness = pow_witness;
+
+    // ---- serialise: write_fri_proof, serialization/mod.rs:1595-1609
+    std::vector<uint8_t> buf;
+    for (auto& t : trees)
+        for (auto& h : t.cap) put_hash(buf, h);
+    // fri_prover_query_rounds, prover.rs:204-258
+    for (uint32_t q = 0; q < params->num_query_rounds; q++) {
+        u64 rand = get_challenge(ch);
+        size_t x_index = (size_t)(rand % N);
+        if (tap_query_indices) tap_query_indices[q] = x_index;
+        for (size_t o = 0; o < n_oracles; o++) {
+            const glo_commit* oc = oracles[o];
+            const u64* leaf = oc->leaves.data() + x_index * oc->W;
+            for (size_t i = 0; i < oc->W; i++) put_u64(buf, leaf[i]);
+            size_t len = log2_strict(oc->N) - oc->cap_height;
+            std::vector<Hash> sib(len);
+            merkle_prove(x_index, oc->N, oc->cap_height, oc->digests.data(), sib.data());
+            buf.push_back((uint8_t)len);
+            for (auto& h : sib) put_hash(buf, h);
+        }
+        for (size_t i = 0; i < trees.size(); i++) {
+            uint32_t arity_bits = params->reduction_arity_bits[i];
+            const Tree& t = trees[i];
+            size_t idx = x_index >> arity_bits;
+            const u64* leaf = t.leaves.data() + idx * t.W;
+            for (size_t k = 0; k < t.W; k++) put_u64(buf, leaf[k]);
+            size_t len = log2_strict(t.N) - t.cap_height;
+            std::vector<Hash> sib(len);
+            merkle_prove(idx, t.N, t.cap_height, t.digests.data(), sib.data());
+            buf.push_back((uint8_t)len);
+            for (auto& h : sib) put_hash(buf, h);
+            x_index >>= arity_bits;
+        }
+    }
+    for (auto& c : coeffs) {
+        put_u64(buf, c.a);
+        put_u64(buf, c.b);
+    }
+    put_u64(buf, pow_witness);
+    *out = (uint8_t*)malloc(buf.size());
+    memcpy(*out, buf.data(), buf.size());
+    *out_len = buf.size();
+    return 0;
+}
+
+// verify_fri_proof, fri/verifier.rs:62-241 with challenges from challenges.rs:28-75
+int glo_verify_fri_proof(const uint64_t* const* initial_caps, const size_t* oracle_num_polys,
+                         const size_t* oracle_leaf_width, size_t n_oracles, const glo_fri_batch* batches,
+                         size_t n_batches, const uint64_t* opened_values, uint32_t degree_bits,
+                         glo_challenger* ch, const glo_fri_params* params, const uint8_t* proof,
+                         size_t proof_len) {
+    (void)oracle_num_polys;
+    size_t pos = 0;
+    bool overrun = false;
+    auto get_u64 = [&]() -> u64 {
+        if (pos + 8 > proof_len) {
+            overrun = true;
+            return 0;
+        }
+        u64 v = 0;
+        for (int i = 0; i < 8; i++) v |= (u64)proof[pos + i] << (8 * i);
+        pos += 8;
+        return v;
+    };
+    auto get_hash = [&]() {
+        Hash h;
+        for (int i = 0; i < 4; i++) h.e[i] = get_u64();
+        return h;
+    };
+    uint32_t log_N = degree_bits + params->rate_bits;
+    size_t N = (size_t)1 << log_N;
+    size_t C = (size_t)1 << params->cap_height;
+    uint32_t R = params->num_reductions;
+    // ---- parse
+    std::vector<std::vector<Hash>> caps(R, std::vector<Hash>(C));
+    for (uint32_t r = 0; r < R; r++)
+        for (size_t c = 0; c < C; c++) caps[r][c] = get_hash();
+    struct Query {
+        std::vector<std::vector<u64>> init_leaf;
+        std::vector<std::vector<Hash>> init_sib;
+        std::vector<std::vector<E2>> evals;
+        std::vector<std::vector<Hash>> step_sib;
+    };
+    std::vector<Query> queries(params->num_query_rounds);
+    for (auto& q : queries) {
+        for (size_t o = 0; o < n_oracles; o++) {
+            std::vector<u64> leaf(oracle_leaf_width[o]);
+            for (auto& x : leaf) x = get_u64();
+            if (pos >= proof_len) return 10;
+            size_t len = proof[pos++];
+            std::vector<Hash> sib(len);
+            for (auto& h : sib) h = get_hash();
+            q.init_leaf.push_back(leaf);
+            q.init_sib.push_back(sib);
+        }
+        for (uint32_t r = 0; r < R; r++) {
+            size_t arity = (size_t)1 << params->reduction_arity_bits[r];
+            std::vector<E2> ev(arity);
+            for (auto& e : ev) {
+                e.a = get_u64();
+                e.b = get_u64();
+            }
+            if (pos >= proof_len) return 10;
+            size_t len = proof[pos++];
+            std::vector<Hash> sib(len);
+            for (auto& h : sib) h = get_hash();
+            q.evals.push_back(ev);
+            q.step_sib.push_back(sib);
+        }
+    }
+    uint32_t final_bits = degree_bits;
+    for (uint32_t r = 0; r < R; r++) final_bits -= params->reduction_arity_bits[r];
+    std::vector<E2> final_poly((size_t)1 << final_bits);
+    for (auto& c : final_poly) {
+        c.a = get_u64();
+        c.b = get_u64();
+    }
+    u64 pow_witness = get_u64();
+    if (overrun || pos != proof_len) return 10;
+
+    // ---- fri_challenges, challenges.rs:28-75
+    E2 fri_alpha = get_extension_challenge(ch);
+    std::vector<E2> betas;
+    for (uint32_t r = 0; r < R; r++) {
+        observe_cap(ch, caps[r]);
+        betas.push_back(get_extension_challenge(ch));
+    }
+    for (auto& c : final_poly) observe_ext(ch, c);
+    observe_element(ch, pow_witness);
+    u64 pow_response = get_challenge(ch);
+    std::vector<size_t> indices;
+    for (uint32_t q = 0; q < params->num_query_rounds; q++) indices.push_back((size_t)(get_challenge(ch) % N));
+
+    // ---- PoW, verifier.rs:49-60
+    {
+        uint32_t lz = pow_response == 0 ? 64 : (uint32_t)__builtin_clzll(pow_response);
+        if (lz < params->proof_of_work_bits) return 11;
+    }
+    // ---- PrecomputedReducedOpenings::from_os_and_alpha, verifier.rs:251-261
+    std::vector<E2> reduced_openings;
+    {
+        size_t off = 0;
+        for (size_t b = 0; b < n_batches; b++) {
+            E2 acc = e2(0);
+            for (size_t j = batches[b].num_polys; j-- > 0;)
+                acc = eadd(emul(acc, fri_alpha),
+                           E2{opened_values[2 * (off + j)], opened_values[2 * (off + j) + 1]});
+            off += batches[b].num_polys;
+            reduced_openings.push_back(acc);
+        }
+    }
+    u64 omega_N = primitive_root_of_unity(log_N);
+    for (size_t qi = 0; qi < queries.size(); qi++) {
+        const Query& q = queries[qi];
+        size_t x_index = indices[qi];
+        // fri_verify_initial_proof, verifier.rs:111-121
+        for (size_t o = 0; o < n_oracles; o++) {
+            if (q.init_sib[o].size() != log_N - params->cap_height) return 12;
+            if (!merkle_verify(q.init_leaf[o].data(), q.init_leaf[o].size(), x_index, q.init_sib[o].data(),
+                               q.init_sib[o].size(), (const Hash*)initial_caps[o]))
+                return 13;
+        }
+        u64 subgroup_x = fmul(MULTIPLICATIVE_GROUP_GENERATOR, fexp(omega_N, reverse_bits(x_index, log_N)));
+        // fri_combine_initial, verifier.rs:123-166
+        E2 sum = e2(0);
+        {
+            u64 count = 0;
+            for (size_t b = 0; b < n_batches; b++) {
+                E2 point{batches[b].point[0], batches[b].point[1]};
+                E2 red = e2(0);
+                for (size_t j = batches[b].num_polys; j-- > 0;) {
+                    u64 ev = q.init_leaf[batches[b].oracle_index[j]][batches[b].poly_index[j]];
+                    red = eadd(emul(red, fri_alpha), e2(ev));
+                    count++;
+                }
+                E2 numerator = esub(red, reduced_openings[b]);
+                E2 denominator = esub(e2(subgroup_x), point);
+                sum = emul(eexp(fri_alpha, count), sum);  // alpha.shift(sum)
+                count = 0;
+                sum = eadd(sum, emul(numerator, einv(denominator)));
+            }
+        }
+        E2 old_eval = sum;
+        for (uint32_t r = 0; r < R; r++) {
+            uint32_t arity_bits = params->reduction_arity_bits[r];
+            size_t arity = (size_t)1 << arity_bits;
+            const std::vector<E2>& evals = q.evals[r];
+            size_t coset_index = x_index >> arity_bits;
+            size_t within = x_index & (arity - 1);
+            if (!eeq(evals[within], old_eval)) return 14;
+            // compute_evaluation, verifier.rs:22-47 (Lagrange interpolation at beta)
+            {
+                u64 g = primitive_root_of_unity(arity_bits);
+                std::vector<E2> ev = evals;
+                {  // reverse_index_bits_in_place(&mut evals)
+                    std::vector<u64> flat(2 * arity);
+                    for (size_t i = 0; i < arity; i++) {
+                        flat[2 * i] = ev[i].a;
+                        flat[2 * i + 1] = ev[i].b;
+                    }
+                    reverse_index_bits_in_place(flat.data(), arity, 2);
+                    for (size_t i = 0; i < arity; i++) ev[i] = E2{flat[2 * i], flat[2 * i + 1]};
+                }
+                size_t rev_within = reverse_bits(within, arity_bits);
+                u64 coset_start = fmul(subgroup_x, fexp(g, arity - rev_within));
+                std::vector<E2> xs(arity);
+                u64 y = 1;
+                for (size_t i = 0; i < arity; i++) {
+                    xs[i] = e2(fmul(coset_start, y));
+                    y = fmul(y, g);
+                }
+                E2 beta = betas[r];
+                // interpolate, field/src/interpolation.rs:31-66
+                E2 result;
+                bool hit = false;
+                for (size_t i = 0; i < arity; i++)
+                    if (eeq(xs[i], beta)) {
+                        result = ev[i];
+                        hit = true;
+                    }
+                if (!hit) {
+                    E2 l_x = e2(1);
+                    for (size_t i = 0; i < arity; i++) l_x = emul(l_x, esub(beta, xs[i]));
+                    E2 s = e2(0);
+                    for (size_t i = 0; i < arity; i++) {
+                        E2 w = e2(1);
+                        for (size_t j = 0; j < arity; j++)
+                            if (j != i) w = emul(w, esub(xs[i], xs[j]));
+                        E2 wi = einv(w);
+                        s = eadd(s, emul(emul(wi, einv(esub(beta, xs[i]))), ev[i]));
+                    }
+                    result = emul(l_x, s);
+                }
+                old_eval = result;
+            }
+            // verify_merkle_proof_to_cap(flatten(evals), coset_index, cap_i, proof)
+            std::vector<u64> flat(2 * arity);
+            for (size_t i = 0; i < arity; i++) {
+                flat[2 * i] = evals[i].a;
+                flat[2 * i + 1] = evals[i].b;
+            }
+            if (!merkle_verify(flat.data(), flat.size(), coset_index, q.step_sib[r].data(),
+                               q.step_sib[r].size(), caps[r].data()))
+                return 15;
+            for (uint32_t k = 0; k < arity_bits; k++) subgroup_x = fsqr(subgroup_x);
+            x_index = coset_index;
+        }
+        // final_poly.eval(subgroup_x) == old_eval
+        E2 acc = e2(0);
+        for (size_t k = final_poly.size(); k-- > 0;) acc = eadd(escale(acc, subgroup_x), final_poly[k]);
+        if (!eeq(acc, old_eval)) return 16;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,163 @@
+/*
+ * gl_oracle.h -- CPU parity ORACLE for the plonky2 prover hot path (TEST INFRASTRUCTURE ONLY).
+ *
+ * This is a plain, literal C++ restatement of the reference's CPU algorithm
+ * (0xPolygonZero/plonky2 @ 5d9da5a) for: Goldilocks field arithmetic, radix-2 NTT/iNTT,
+ * coset-LDE, Poseidon-12 sponge, Merkle tree (reference digest layout), Fiat-Shamir
+ * challenger and the FRI prover (commit phase, proof-of-work, query openings).
+ * Every function cites the reference file:line it follows.
+ *
+ * USE: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library, and only as the checker / CPU baseline. The product
+ * (plonky2_b200/, libplonky2_b200.so) never links, imports or calls it.
+ *
+ * PINNING STATUS: the reference is Rust (nightly) and cannot be built in this image
+ * (no cargo/rustc), so there is no oracle/_ref. The oracle is pinned against every stored
+ * vector the reference's own tests hold for this path:
+ *   - Poseidon-12 permutation: the 4 known-answer vectors of
+ *     plonky2/src/hash/poseidon_goldilocks.rs:466-487 (tests/golden/poseidon_kat.json),
+ *     and fast-partial-rounds == naive form (poseidon.rs:944-957);
+ *   - bit-reversal: the 256-entry golden table of plonky2/src/util/mod.rs:64-84.
+ * For NTT / LDE / Merkle caps / FRI proofs the reference stores NO golden data
+ * (SURVEY.md section 4): for those outputs parity is UNPINNED by stored data and rests on
+ * the reference tests' own definitions, restated in tests/ (NTT == naive O(n^2) evaluation,
+ * field/src/fft.rs:215-282; coset FFT == naive coset evaluation, polynomial/mod.rs:476-516;
+ * every Merkle proof verifies against the cap, merkle_tree.rs:269-311; FRI proofs pass the
+ * restated verifier, fri/verifier.rs:62-241).
+ *
+ * All u64 outputs are CANONICAL (< p). Inputs may be any u64 (non-canonical allowed), exactly
+ * like the reference's GoldilocksField(pub u64) (field/src/goldilocks_field.rs:23-25).
+ */
+#ifndef GL_ORACLE_H
+#define GL_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- field (field/src/goldilocks_field.rs:198-320,392-449; types.rs:226-272,429-443) ---- */
+uint64_t glo_canon(uint64_t a);
+uint64_t glo_add(uint64_t a, uint64_t b);
+uint64_t glo_sub(uint64_t a, uint64_t b);
+uint64_t glo_mul(uint64_t a, uint64_t b);
+uint64_t glo_neg(uint64_t a);
+uint64_t glo_inv(uint64_t a);                      /* 0 -> 0 (reference returns None) */
+uint64_t glo_exp(uint64_t a, uint64_t e);
+uint64_t glo_primitive_root_of_unity(uint32_t log_n);
+uint64_t glo_inverse_2exp(uint32_t k);
+uint64_t glo_coset_shift(void);                    /* MULTIPLICATIVE_GROUP_GENERATOR */
+/* quadratic extension F[X]/(X^2-7): (field/src/extension/quadratic.rs:86-100,180-193) */
+void glo_ext2_mul(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]);
+void glo_ext2_inv(const uint64_t a[2], uint64_t out[2]);
+
+/* ---- bit reversal (util/src/lib.rs:53-101,185-234; plonky2/src/util/mod.rs:33-41) ---- */
+uint64_t glo_reverse_bits(uint64_t x, uint32_t bits);
+void glo_reverse_index_bits_in_place(uint64_t* arr, size_t n, size_t elem_words);
+
+/* ---- NTT (field/src/fft.rs:14-33,53-91,165-202; polynomial/mod.rs:58-88,199-201,280-293) ---- */
+/* in place, natural order in and out. zero_factor = r: top (1 - 2^-r) of the input is zero. */
+void glo_fft(uint64_t* buf, uint32_t log_n, uint32_t zero_factor);
+void glo_ifft(uint64_t* buf, uint32_t log_n);
+void glo_coset_fft(uint64_t* buf, uint32_t log_n, uint64_t shift, uint32_t zero_factor);
+void glo_coset_ifft(uint64_t* buf, uint32_t log_n, uint64_t shift);
+/* naive O(n^2) evaluation on shift*<omega_n>, the reference tests' definition (fft.rs:251-282) */
+void glo_naive_coset_eval(const uint64_t* coeffs, uint32_t log_n, uint64_t shift, uint64_t* out);
+
+/* ---- Poseidon-12 (plonky2/src/hash/poseidon.rs:630-641,689-801; hashing.rs:97-145;
+ *      plonk/config.rs:63-74) ---- */
+void glo_poseidon(uint64_t st[12]);        /* fast-partial-rounds form, poseidon.rs:766-777 */
+void glo_poseidon_naive(uint64_t st[12]);  /* textbook form, poseidon.rs:779-801 */
+void glo_hash_no_pad(const uint64_t* in, size_t len, uint64_t out[4]);
+void glo_hash_or_noop(const uint64_t* in, size_t len, uint64_t out[4]);
+void glo_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]);
+/* batched convenience for the CPU baseline: n_items inputs of W words, row-major */
+void glo_hash_many(const uint64_t* in, size_t n_items, size_t W, uint64_t* out, int nthreads);
+
+/* ---- Merkle tree (plonky2/src/hash/merkle_tree.rs:86-224, merkle_proofs.rs:55-107) ---- */
+/* leaves: row-major N x W. digests: 4*2*(N - C) words in the reference layout. cap: 4*C. */
+int glo_merkle_build(const uint64_t* leaves, size_t N, size_t W, uint32_t cap_height,
+                     uint64_t* digests, uint64_t* cap, int nthreads);
+/* siblings: 4*(log N - cap_height) words, bottom-up */
+void glo_merkle_prove(size_t leaf_index, size_t N, uint32_t cap_height, const uint64_t* digests,
+                      uint64_t* siblings);
+int glo_merkle_verify(const uint64_t* leaf, size_t W, size_t leaf_index, const uint64_t* siblings,
+                      size_t n_siblings, const uint64_t* cap, uint32_t cap_height);
+
+/* ---- PolynomialBatch (plonky2/src/fri/oracle.rs:57-147) ---- */
+typedef struct glo_commit glo_commit;
+/* cols: B columns of n words, column b at cols + b*col_stride. salt: NULL or 4 columns of N
+ * words (blinding; the reference draws them from OsRng, oracle.rs:133-137). */
+glo_commit* glo_commit_new(const uint64_t* cols, size_t col_stride, size_t B, uint32_t log_n,
+                           uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt,
+                           int is_coeffs, int nthreads);
+void glo_commit_free(glo_commit*);
+size_t glo_commit_leaf_width(const glo_commit*);
+const uint64_t* glo_commit_coeffs(const glo_commit*);   /* B x n, column-major */
+const uint64_t* glo_commit_leaves(const glo_commit*);   /* N x W, row-major, leaf j = LDE row bitrev(j) */
+const uint64_t* glo_commit_digests(const glo_commit*);  /* 8*(N-C) words */
+const uint64_t* glo_commit_cap(const glo_commit*);      /* 4*C words */
+/* get_lde_values(index, step) (oracle.rs:142-147): writes B words */
+void glo_commit_get_lde_values(const glo_commit*, size_t index, size_t step, uint64_t* out);
+
+/* ---- Challenger (plonky2/src/iop/challenger.rs:30-153) ---- */
+typedef struct glo_challenger glo_challenger;
+glo_challenger* glo_challenger_new(void);
+glo_challenger* glo_challenger_clone(const glo_challenger*);
+void glo_challenger_free(glo_challenger*);
+void glo_challenger_observe(glo_challenger*, const uint64_t* elems, size_t n);
+uint64_t glo_challenger_get_challenge(glo_challenger*);
+/* debugging / PoW: copies sponge state (12) and returns input_buffer length */
+size_t glo_challenger_state(const glo_challenger*, uint64_t state[12], uint64_t inbuf[8]);
+
+/* ---- FRI prover (plonky2/src/fri/oracle.rs:176-237, prover.rs:24-258) ---- */
+typedef struct {
+    uint32_t rate_bits;
+    uint32_t cap_height;
+    uint32_t proof_of_work_bits;
+    uint32_t num_query_rounds;
+    uint32_t num_reductions;
+    uint32_t reduction_arity_bits[32];
+} glo_fri_params;
+
+/* One opening batch: a point in F_{p^2} and a list of (oracle_index, polynomial_index). */
+typedef struct {
+    uint64_t point[2];
+    size_t num_polys;
+    const uint32_t* oracle_index;
+    const uint32_t* poly_index;
+} glo_fri_batch;
+
+/* prove_openings: returns the proof serialised exactly like the reference's write_fri_proof
+ * (plonky2/src/util/serialization/mod.rs:1595-1609): caps, query rounds (initial leaf + u8 len +
+ * siblings per oracle; evals + u8 len + siblings per step), final poly, pow witness; canonical
+ * little-endian u64s. *out is malloc'ed (free with glo_free). PoW = SMALLEST qualifying nonce
+ * (sequential `find`, maybe_rayon/src/lib.rs:254-259). Returns 0 on success. */
+int glo_prove_openings(const glo_commit* const* oracles, size_t n_oracles,
+                       const glo_fri_batch* batches, size_t n_batches, glo_challenger* challenger,
+                       const glo_fri_params* params, uint8_t** out, size_t* out_len,
+                       /* optional taps for stage-by-stage parity (may be NULL): */
+                       uint64_t* tap_final_poly /* 2*n words */, uint64_t* tap_betas /* 2*num_reductions */,
+                       uint64_t* tap_pow_witness, uint64_t* tap_query_indices);
+void glo_free(void*);
+
+/* Restated FRI verifier (plonky2/src/fri/verifier.rs:62-241, challenges.rs:28-75): checks a
+ * serialised proof against the initial caps and the claimed openings. challenger must be in the
+ * same state prove_openings started from. opened_values: for each batch, for each polynomial,
+ * the F_{p^2} value f(point) (2 words each), concatenated in batch order.
+ * Returns 0 if the proof verifies, a positive code naming the failed check otherwise. */
+int glo_verify_fri_proof(const uint64_t* const* initial_caps, const size_t* oracle_num_polys,
+                         const size_t* oracle_leaf_width, size_t n_oracles,
+                         const glo_fri_batch* batches, size_t n_batches,
+                         const uint64_t* opened_values, uint32_t degree_bits,
+                         glo_challenger* challenger, const glo_fri_params* params,
+                         const uint8_t* proof, size_t proof_len);
+
+/* polynomial evaluation helper for the verifier test: f(z) for base coeffs, z in F_{p^2} */
+void glo_eval_poly_base_at_ext(const uint64_t* coeffs, size_t n, const uint64_t z[2], uint64_t out[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,222 @@
+"""Pin the CPU oracle against every stored vector / definitional check the reference's own tests hold
+for the hot path. CPU only.
+
+Reference tests mirrored here:
+  * Poseidon KATs + fast==naive      plonky2/src/hash/poseidon_goldilocks.rs:455-495, poseidon.rs:926-957
+  * bit-reversal golden table         plonky2/src/util/mod.rs:60-126
+  * prime-field edge arithmetic       field/src/prime_field_testing.rs:7-17,69-183
+  * fft_and_ifft vs naive evaluation  field/src/fft.rs:215-282
+  * coset fft/ifft vs naive           field/src/polynomial/mod.rs:476-516
+  * Merkle proofs for every leaf      plonky2/src/hash/merkle_tree.rs:253-311
+  * digest layout == commit_single    plonky2/src/hash/batch_merkle_tree.rs:185-228
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import EDGE, P, synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_poseidon_known_answer_vectors(oracle):
+    kat = json.load(open(os.path.join(GOLD, "poseidon_kat.json")))
+    assert len(kat["vectors"]) == 4
+    for v in kat["vectors"]:
+        inp = [int(x) for x in v["input"]]
+        exp = [int(x) for x in v["output"]]
+        assert oracle.poseidon(inp).tolist() == exp
+        assert oracle.poseidon(inp, naive=True).tolist() == exp
+
+
+def test_poseidon_fast_equals_naive(oracle):
+    xs = synth(0x77, (200, 12), canonical=False)
+    for row in xs:
+        assert oracle.poseidon(row).tolist() == oracle.poseidon(row, naive=True).tolist()
+
+
+def test_bit_reversal_golden_table(oracle):
+    table = json.load(open(os.path.join(GOLD, "bitrev256.json")))["table"]
+    arr = np.arange(256, dtype=np.uint64)
+    oracle.lib().glo_reverse_index_bits_in_place(oracle.ptr(arr), 256, 1)
+    assert arr.tolist() == table
+    assert oracle.lib().glo_reverse_bits(0b1000000000, 10) == 1
+    assert oracle.lib().glo_reverse_bits(0b01011, 5) == 0b11010
+    arr4 = np.array([10, 20, 30, 40], dtype=np.uint64)
+    oracle.lib().glo_reverse_index_bits_in_place(oracle.ptr(arr4), 4, 1)
+    assert arr4.tolist() == [10, 30, 20, 40]
+
+
+def test_prime_field_edge_arithmetic(oracle):
+    L = oracle.lib()
+    ins = [int(x) for x in json.load(open(os.path.join(GOLD, "field_edge_inputs.json")))["inputs"]]
+    ins = ins[::3] + EDGE
+    for a in ins:
+        assert L.glo_neg(a) == (-a) % P
+        assert L.glo_canon(a) == a % P
+        for b in ins:
+            assert L.glo_add(a, b) == (a + b) % P
+            assert L.glo_sub(a, b) == (a - b) % P
+            assert L.glo_mul(a, b) == (a * b) % P
+    for a in ins:
+        if a % P:
+            assert L.glo_mul(L.glo_inv(a), a) == 1
+
+
+def test_field_constants(oracle):
+    L = oracle.lib()
+    # SURVEY appendix A items 2-4
+    assert L.glo_primitive_root_of_unity(6) == 8
+    assert L.glo_primitive_root_of_unity(1) == P - 1
+    assert L.glo_primitive_root_of_unity(20) == 1971462654193939361
+    assert L.glo_primitive_root_of_unity(23) == 5936499541590631774
+    assert L.glo_coset_shift() == 14293326489335486720
+    for k in range(0, 33):
+        assert L.glo_mul(L.glo_inverse_2exp(k), pow(2, k, P)) == 1
+    w32 = L.glo_primitive_root_of_unity(32)
+    assert pow(w32, 1 << 32, P) == 1 and pow(w32, 1 << 31, P) == P - 1
+
+
+def test_ext2(oracle):
+    xs = synth(0x99, (20, 4), canonical=False)
+    for a0, a1, b0, b1 in xs.tolist():
+        out = np.zeros(2, dtype=np.uint64)
+        oracle.lib().glo_ext2_mul(oracle.ptr(np.array([a0, a1], dtype=np.uint64)),
+                                  oracle.ptr(np.array([b0, b1], dtype=np.uint64)), oracle.ptr(out))
+        assert out.tolist() == [(a0 * b0 + 7 * a1 * b1) % P, (a0 * b1 + a1 * b0) % P]
+        inv = np.zeros(2, dtype=np.uint64)
+        oracle.lib().glo_ext2_inv(oracle.ptr(np.array([a0, a1], dtype=np.uint64)), oracle.ptr(inv))
+        i0, i1 = inv.tolist()
+        assert [(a0 * i0 + 7 * a1 * i1) % P, (a0 * i1 + a1 * i0) % P] == [1, 0]
+
+
+def test_fft_and_ifft_match_naive(oracle):
+    # field/src/fft.rs:215-249: degree 200 padded to 256, deterministic coefficients i*1337 % 100
+    degree, padded = 200, 256
+    coeffs = np.array([(i * 1337) % 100 for i in range(degree)] + [0] * (padded - degree), dtype=np.uint64)
+    naive = oracle.naive_coset_eval(coeffs, 1)
+    points = oracle.fft(coeffs)
+    assert points.tolist() == naive.tolist()
+    assert oracle.ifft(points).tolist() == coeffs.tolist()
+    for r in range(4):
+        # zero_factor only valid when the top (1 - 2^-r) is zero: extend by zeros like the reference
+        ext = np.concatenate([coeffs, np.zeros(padded * ((1 << r) - 1), dtype=np.uint64)])
+        assert oracle.fft(ext, zero_factor=r).tolist() == oracle.fft(ext).tolist()
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 5, 8])
+def test_coset_fft_matches_naive(oracle, log_n):
+    n = 1 << log_n
+    coeffs = synth(0x31 + log_n, (n,))
+    shift = int(synth(0x41, (1,))[0]) or 3
+    got = oracle.coset_fft(coeffs, shift)
+    assert got.tolist() == oracle.naive_coset_eval(coeffs, shift).tolist()
+    assert oracle.coset_ifft(got, shift).tolist() == coeffs.tolist()
+    # pure-python definition as a third opinion
+    w = oracle.lib().glo_primitive_root_of_unity(log_n)
+    exp = [sum(int(c) * pow(shift * pow(w, i, P) % P, k, P) for k, c in enumerate(coeffs)) % P for i in range(n)]
+    assert got.tolist() == exp
+
+
+def test_sponge_semantics(oracle):
+    # hash_or_noop no-op threshold (config.rs:63-74) and overwrite-mode partial chunk (hashing.rs:118-141)
+    for w in range(0, 5):
+        x = synth(0x51, (w,), canonical=False)
+        exp = [int(v) % P for v in x] + [0] * (4 - w)
+        assert oracle.hash_or_noop(x).tolist() == exp
+    x = synth(0x52, (12,))
+    st = np.zeros(12, dtype=np.uint64)
+    st[:8] = x[:8]
+    st = oracle.poseidon(st)
+    st[:4] = x[8:]  # partial chunk overwrites only its own length; lanes 4.. keep previous output
+    st = oracle.poseidon(st)
+    assert oracle.hash_no_pad(x).tolist() == st[:4].tolist()
+    assert oracle.hash_or_noop(x).tolist() == st[:4].tolist()
+    l, r = synth(0x53, (4,)), synth(0x54, (4,))
+    st = oracle.poseidon(np.concatenate([l, r, np.zeros(4, dtype=np.uint64)]))
+    assert oracle.two_to_one(l, r).tolist() == st[:4].tolist()
+
+
+@pytest.mark.parametrize("cap_height", [0, 1, 3, 8])
+def test_merkle_every_proof_verifies(oracle, cap_height):
+    # merkle_tree.rs:269-311: 256 leaves x 7
+    leaves = synth(0x61, (256, 7))
+    digests, cap = oracle.merkle_build(leaves, cap_height)
+    for i in range(256):
+        sib = oracle.merkle_prove(i, 256, cap_height, digests)
+        assert len(sib) == 8 - cap_height
+        assert oracle.merkle_verify(leaves[i], i, sib, cap, cap_height)
+    bad = leaves[3].copy()
+    bad[0] ^= np.uint64(1)
+    assert not oracle.merkle_verify(bad, 3, oracle.merkle_prove(3, 256, cap_height, digests), cap, cap_height)
+
+
+def test_merkle_cap_too_big(oracle):
+    with pytest.raises(ValueError):
+        oracle.merkle_build(synth(1, (8, 5)), 4)
+
+
+def test_merkle_digest_layout(oracle):
+    # batch_merkle_tree.rs:185-228 (commit_single): explicit layout for 4 leaves, cap_height 0
+    leaves = synth(0x62, (4, 9))
+    digests, cap = oracle.merkle_build(leaves, 0)
+    h = [oracle.hash_or_noop(l) for l in leaves]
+    h01, h23 = oracle.two_to_one(h[0], h[1]), oracle.two_to_one(h[2], h[3])
+    root = oracle.two_to_one(h01, h23)
+    assert digests.tolist() == [x.tolist() for x in (h[0], h[1], h01, h23, h[2], h[3])]
+    assert cap.tolist() == [root.tolist()]
+    # closed form of SURVEY row a12 vs the recursive fill, 64 leaves, cap_height 2
+    leaves = synth(0x63, (64, 5))
+    digests, cap = oracle.merkle_build(leaves, 2)
+    sub = 2 * (16 - 1)
+    for c in range(4):
+        layer = [oracle.hash_or_noop(l) for l in leaves[16 * c:16 * (c + 1)]]
+        i = 0
+        while len(layer) > 1:
+            for q, node in enumerate(layer):
+                pos = 2 * (((q >> 1) << (i + 1)) + (1 << i) - 1) + (q & 1)
+                assert digests[c * sub + pos].tolist() == node.tolist()
+            layer = [oracle.two_to_one(layer[2 * k], layer[2 * k + 1]) for k in range(len(layer) // 2)]
+            i += 1
+        assert cap[c].tolist() == layer[0].tolist()
+
+
+def test_commit_matches_definition(oracle):
+    # from_values == ifft -> lde -> coset_fft -> transpose -> bit-reverse rows -> MerkleTree (oracle.rs:57-112)
+    B, log_n, r, hc = 5, 4, 2, 1
+    n, N = 1 << log_n, 1 << (log_n + r)
+    vals = synth(0x71, (B, n))
+    c = oracle.Commit(vals, r, hc)
+    coeffs = np.stack([oracle.ifft(v) for v in vals])
+    assert c.coeffs.tolist() == coeffs.tolist()
+    g = oracle.lib().glo_coset_shift()
+    lde = np.stack([oracle.naive_coset_eval(np.concatenate([co, np.zeros(N - n, dtype=np.uint64)]), g)
+                    for co in coeffs])
+    leaves = c.leaves
+    for j in range(N):
+        i = oracle.lib().glo_reverse_bits(j, log_n + r)
+        assert leaves[j].tolist() == lde[:, i].tolist()
+    d, cap = oracle.merkle_build(leaves, hc)
+    assert c.cap.tolist() == cap.tolist() and c.digests.tolist() == d.tolist()
+    assert c.get_lde_values(3, 2).tolist() == lde[:, 6].tolist()
+    # original values are the LDE's restriction? (values = P on <w_n>, LDE on g<w_N>: check via coeffs instead)
+    c2 = oracle.Commit(coeffs, r, hc, is_coeffs=True)
+    assert c2.cap.tolist() == c.cap.tolist()
+
+
+def test_challenger_semantics(oracle):
+    # challenger.rs:82-92,129-144: pop from the back; partial input flush overwrites only its length
+    ch = oracle.Challenger()
+    xs = synth(0x81, (11,))
+    ch.observe_elements(xs)
+    st = np.zeros(12, dtype=np.uint64)
+    st[:8] = xs[:8]
+    st = oracle.poseidon(st)
+    st[:3] = xs[8:]
+    st = oracle.poseidon(st)
+    got = ch.get_n_challenges(8)
+    assert got == st[:8][::-1].tolist()
+    nxt = oracle.poseidon(st)
+    assert ch.get_challenge() == int(nxt[7])
