@@ -1,0 +1,176 @@
+/*
+ * plonky2_b200.h -- C ABI of the B200-native plonky2 prover hot path
+ * (Goldilocks NTT / coset-LDE / Poseidon Merkle commitment / FRI commit phase, sm_100a CUDA).
+ *
+ * The reference (0xPolygonZero/plonky2 @ 5d9da5a) is pure Rust with no FFI; the seam this ABI
+ * replaces is the trait/struct surface listed in SURVEY.md section 8(b). Each entry point below
+ * cites the reference interface it stands in for. A Rust binding (`extern "C"` block + safe
+ * wrappers for PolynomialBatch / MerkleTree / fri_proof) is sketched in INTEGRATION.md.
+ *
+ * Conventions
+ *  - Field element = uint64_t, exactly the reference's #[repr(transparent)] GoldilocksField(pub u64)
+ *    (field/src/goldilocks_field.rs:23-25). Inputs may be non-canonical (any u64); every output is
+ *    CANONICAL (< p = 2^64 - 2^32 + 1), little-endian host.
+ *  - F_{p^2} element = 2 consecutive words (c0, c1), X^2 = 7 (field/src/goldilocks_extensions.rs:14-27).
+ *  - Hash = 4 words (plonky2/src/hash/hash_types.rs:20-27).
+ *  - `mem` arguments: GL_MEM_HOST (pageable or pinned host memory; the call does the copies) or
+ *    GL_MEM_DEVICE (device pointers on the context's device; no copies, stream-ordered).
+ *  - Every function returns an int status: GL_OK or a GL_ERR_* code; gl_last_error(ctx) gives text.
+ *    Nothing unwinds or aborts across the ABI. Shape errors mirror the reference's panics
+ *    (field/src/fft.rs:171-177, plonky2/src/hash/merkle_tree.rs:195-200, plonky2/src/fri/oracle.rs:128).
+ *  - One gl_ctx per (device, stream). Calls on one context are serialised by the caller; different
+ *    contexts are independent (no global mutable state). The library owns all device memory behind
+ *    opaque handles; the caller owns every host buffer.
+ *  - There is NO CPU fallback: without a CUDA device gl_ctx_create fails with GL_ERR_CUDA.
+ */
+#ifndef PLONKY2_B200_H
+#define PLONKY2_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GL_OK 0
+#define GL_ERR_BAD_SHAPE 1   /* not a power of two, inconsistent degrees, cap_height > log2(leaves) ... */
+#define GL_ERR_OOM 2
+#define GL_ERR_CUDA 3
+#define GL_ERR_UNSUPPORTED 4 /* size beyond this build's limits (log_n > 24 per transform) */
+#define GL_ERR_BAD_ARG 5
+#define GL_ERR_POW_FAILED 6
+
+#define GL_MEM_HOST 0
+#define GL_MEM_DEVICE 1
+
+#define GL_SALT_SIZE 4 /* plonky2/src/fri/oracle.rs:26 */
+
+typedef struct gl_ctx gl_ctx;
+typedef struct gl_commit gl_commit; /* a PolynomialBatch on the device */
+typedef struct gl_merkle gl_merkle; /* a MerkleTree on the device */
+typedef struct gl_fri gl_fri;       /* FRI commit-phase state on the device */
+
+/* ---- context -------------------------------------------------------------------------------- */
+/* stream: a cudaStream_t (NULL = a private non-blocking stream is created). */
+int gl_ctx_create(int device, void* stream, gl_ctx** out);
+void gl_ctx_destroy(gl_ctx* ctx);
+const char* gl_last_error(const gl_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
+int gl_ctx_synchronize(gl_ctx* ctx);
+/* number of kernels this context has launched so far (for bench.py's gpu_launches) */
+uint64_t gl_ctx_launch_count(const gl_ctx* ctx);
+/* tuning: columns per NTT group (scratch = group * n * 8 bytes; sized so pass A -> pass B stays in L2) */
+int gl_ctx_set_ntt_group(gl_ctx* ctx, uint32_t columns);
+
+/* ---- NTT  (field/src/fft.rs:53-91 fft_with_options / ifft_with_options;
+ *            field/src/polynomial/mod.rs:63-73,280-293 coset_ifft / coset_fft_with_options) -------- */
+/* In place, natural order in and out, `batch` columns of n = 2^log_n words, column b at
+ * data + b*stride.  inverse = 0: out[k] = sum_j in[j] * (shift*w_n^k)^j;  inverse = 1: the inverse map
+ * (coefficients of the polynomial whose values on shift*<w_n> are `data`).  coset_shift = 1 for the
+ * plain subgroup.  zero_factor_log is the reference's `zero_factor` hint (top 1 - 2^-r of the input is
+ * zero); results do not depend on it. */
+int gl_ntt(gl_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t batch, size_t stride, int inverse,
+           uint32_t zero_factor_log, uint64_t coset_shift, int mem);
+
+/* ---- PolynomialBatch  (plonky2/src/fri/oracle.rs:30-37,57-147) -------------------------------- */
+/* from_values (is_coeffs = 0) / from_coeffs (is_coeffs = 1): B columns of n = 2^log_n words at
+ * cols + b*col_stride.  salt: NULL (blinding = false) or GL_SALT_SIZE columns of N = n << rate_bits
+ * words (column s at salt + s*N) appended to every leaf -- the reference draws them from OsRng
+ * (oracle.rs:133-137); here the caller supplies them so the result is deterministic.
+ * The handle keeps coefficients (B x n), leaves (N x W row-major, leaf j = LDE row bitrev(j)),
+ * digests (reference layout, merkle_tree.rs:50-58) and the cap on the device. */
+int gl_commit_create(gl_ctx* ctx, const uint64_t* cols, size_t col_stride, uint32_t B, uint32_t log_n,
+                     uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, int is_coeffs,
+                     int mem, gl_commit** out);
+void gl_commit_destroy(gl_commit* c);
+/* shape queries */
+uint32_t gl_commit_num_polys(const gl_commit* c);  /* B */
+uint32_t gl_commit_leaf_width(const gl_commit* c); /* W = B + (salt ? 4 : 0) */
+uint32_t gl_commit_degree_log(const gl_commit* c);
+uint32_t gl_commit_rate_bits(const gl_commit* c);
+uint32_t gl_commit_cap_height(const gl_commit* c);
+/* PolynomialBatch.merkle_tree.cap: 4 * 2^cap_height words */
+int gl_commit_cap(gl_commit* c, uint64_t* out, int mem);
+/* PolynomialBatch.polynomials: B x n coefficients, column-major, column b at out + b*n */
+int gl_commit_coeffs(gl_commit* c, uint64_t* out, int mem);
+/* MerkleTree.leaves[row_begin .. row_begin + row_count): row-major, W words per leaf */
+int gl_commit_leaves(gl_commit* c, size_t row_begin, size_t row_count, uint64_t* out, int mem);
+/* MerkleTree.digests: 4 * 2 * (N - 2^cap_height) words, reference layout */
+int gl_commit_digests(gl_commit* c, uint64_t* out, int mem);
+/* get_lde_values(index, step) (oracle.rs:142-147): B words (salt removed) */
+int gl_commit_get_lde_values(gl_commit* c, size_t index, size_t step, uint64_t* out);
+/* MerkleTree::get + MerkleTree::prove (merkle_tree.rs:226-237) for `count` leaf indices:
+ * out_leaves = count x W, out_paths = count x (log N - cap_height) x 4, siblings bottom-up. Host out. */
+int gl_commit_open(gl_commit* c, const uint64_t* leaf_indices, size_t count, uint64_t* out_leaves,
+                   uint64_t* out_paths);
+/* device views (valid until destroy; for device-resident pipelines and benchmarks) */
+const uint64_t* gl_commit_dev_leaves(const gl_commit* c);
+const uint64_t* gl_commit_dev_coeffs(const gl_commit* c);
+
+/* ---- Hasher / MerkleTree  (plonky2/src/plonk/config.rs:36-77, plonky2/src/hash/merkle_tree.rs:193-237) */
+/* PoseidonPermutation::permute on the HOST for the sequential Fiat-Shamir transcript
+ * (plonky2/src/iop/challenger.rs:129-144); the same source as the device permutation. */
+void gl_poseidon_permute_host(uint64_t state[12]);
+/* Batched PoseidonHash::hash_or_noop: n_items inputs of W words (row-major) -> n_items x 4 words */
+int gl_poseidon_hash_many(gl_ctx* ctx, const uint64_t* in, size_t n_items, uint32_t W, uint64_t* out, int mem);
+/* Batched PoseidonHash::hash_no_pad (always the sponge, no no-op branch; hashing.rs:118-145) */
+int gl_poseidon_hash_no_pad_many(gl_ctx* ctx, const uint64_t* in, size_t n_items, uint32_t W, uint64_t* out, int mem);
+/* Batched PoseidonHash::two_to_one: n_items pairs (8 words each) -> n_items x 4 words */
+int gl_poseidon_two_to_one_many(gl_ctx* ctx, const uint64_t* in, size_t n_items, uint64_t* out, int mem);
+/* MerkleTree::new(leaves, cap_height): leaves N x W row-major. */
+int gl_merkle_build(gl_ctx* ctx, const uint64_t* leaves, size_t N, uint32_t W, uint32_t cap_height, int mem,
+                    gl_merkle** out);
+void gl_merkle_destroy(gl_merkle* m);
+int gl_merkle_cap(gl_merkle* m, uint64_t* out, int mem);
+int gl_merkle_digests(gl_merkle* m, uint64_t* out, int mem);
+int gl_merkle_open(gl_merkle* m, const uint64_t* leaf_indices, size_t count, uint64_t* out_leaves,
+                   uint64_t* out_paths);
+
+/* ---- FRI  (plonky2/src/fri/oracle.rs:176-237 prove_openings; plonky2/src/fri/prover.rs:24-258) --- */
+/* One opening batch: a point z in F_{p^2} and the polynomials opened there, each named by
+ * (oracle index into the `oracles` array, polynomial index inside it)
+ * (plonky2/src/fri/structure.rs:14-60 FriInstanceInfo / FriBatchInfo / FriPolynomialInfo). */
+typedef struct {
+    uint64_t point[2];
+    size_t num_polys;
+    const uint32_t* oracle_index;
+    const uint32_t* poly_index;
+} gl_fri_batch;
+
+/* The part of prove_openings before fri_proof (oracle.rs:186-220): with alpha from the caller's
+ * transcript, final_poly = sum_b alpha^{k_b} (F_b(X) - F_b(z_b)) / (X - z_b), F_b = sum_j alpha^j f_{b,j},
+ * then its rate-2^-rate_bits coset LDE. The handle holds the n F_{p^2} coefficients and the N values in
+ * bit-reversed order (the order fri_committed_trees hashes them in). */
+int gl_fri_begin(gl_ctx* ctx, gl_commit* const* oracles, size_t n_oracles, const gl_fri_batch* batches,
+                 size_t n_batches, const uint64_t alpha[2], uint32_t rate_bits, uint32_t cap_height,
+                 gl_fri** out);
+/* Same, from explicit final-polynomial coefficients (n = 2^log_n F_{p^2} elements, 2n words, host). */
+int gl_fri_begin_from_coeffs(gl_ctx* ctx, const uint64_t* coeffs_ext, uint32_t log_n, uint32_t rate_bits,
+                             uint32_t cap_height, gl_fri** out);
+void gl_fri_destroy(gl_fri* f);
+/* final_poly coefficients before folding (n x 2 words), for parity checks */
+int gl_fri_coeffs(gl_fri* f, uint64_t* out);
+/* One round of fri_committed_trees (prover.rs:96-120), split at the transcript:
+ *   commit: leaves = arity consecutive (bit-reversed) values flattened; MerkleTree::new; cap -> host. */
+int gl_fri_commit_round(gl_fri* f, uint32_t arity_bits, uint64_t* cap_out /* 4 * 2^cap_height */);
+/*   fold:   with beta from the transcript, values' = fold(values, beta) on the coset shift^arity. */
+int gl_fri_fold(gl_fri* f, const uint64_t beta[2]);
+/* Final polynomial after the last fold, truncated by 2^rate_bits (prover.rs:134-139):
+ * *len_out coefficients (2 words each) written to out (capacity `cap_words` words). */
+int gl_fri_final_poly(gl_fri* f, uint64_t* out, size_t cap_words, size_t* len_out);
+/* Query openings in the committed FRI trees (prover.rs:236-250): for tree `round`, leaves
+ * (arity*2 words each) and Merkle paths for `count` leaf indices. */
+int gl_fri_open(gl_fri* f, uint32_t round, const uint64_t* leaf_indices, size_t count, uint64_t* out_leaves,
+                uint64_t* out_paths);
+uint32_t gl_fri_num_rounds(const gl_fri* f);
+/* fri_proof_of_work (prover.rs:153-202): the SMALLEST u64 nonce such that, with the duplex state
+ * `state` (sponge state already overwritten by the pending inputs) and the nonce written at lane `pos`,
+ * lane 7 of the permuted state has >= min_leading_zeros leading zero bits in canonical form.
+ * (The reference's rayon find_any returns an arbitrary qualifying nonce; a sequential run returns
+ * the smallest -- maybe_rayon/src/lib.rs:254-259.) */
+int gl_fri_pow(gl_ctx* ctx, const uint64_t state[12], uint32_t pos, uint32_t min_leading_zeros,
+               uint64_t* nonce_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

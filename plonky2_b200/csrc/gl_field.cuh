@@ -1,0 +1,205 @@
+// gl_field.cuh -- Goldilocks field arithmetic, p = 2^64 - 2^32 + 1, for sm_100a device code
+// (and the host, for the transcript's single permutations).
+//
+// Semantics follow the reference's GoldilocksField (field/src/goldilocks_field.rs:23-25,198-320,
+// 392-449): an element is ANY u64 (non-canonical values in [p, 2^64) are allowed and represent
+// themselves mod p); add/sub/mul return a u64 congruent to the exact result; canonicalisation
+// (to_canonical_u64, :216-224) happens only where values are stored for hashing/comparison/output.
+//
+// This is not a translation of the x86 code: the 64x64->128 product is built from four 32x32->64
+// IMAD.WIDE ops and the reduction uses 2^64 = 2^32 - 1, 2^96 = -1 (mod p) with 32-bit carry chains
+// (Montgomery-free, as BASELINE.json asks).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GL_HD __host__ __device__ __forceinline__
+#define GL_D __device__ __forceinline__
+#else
+#define GL_HD inline
+#define GL_D inline
+#endif
+
+namespace gl {
+
+constexpr uint64_t P = 0xFFFFFFFF00000001ULL;
+constexpr uint64_t EPS = 0xFFFFFFFFULL;  // 2^32 - 1 = 2^64 mod p
+// field/src/goldilocks_field.rs:80,87
+constexpr uint64_t MULTIPLICATIVE_GROUP_GENERATOR = 14293326489335486720ULL;
+constexpr uint64_t POWER_OF_TWO_GENERATOR = 7277203076849721926ULL;
+constexpr uint32_t TWO_ADICITY = 32;
+
+GL_HD uint64_t canon(uint64_t x) { return x >= P ? x - P : x; }
+
+// a + b (mod p), any u64 inputs, result in [0, 2^64).
+GL_HD uint64_t add(uint64_t a, uint64_t b) {
+    uint64_t s = a + b;
+    // carry out of 2^64: add 2^64 mod p = EPS. A second carry is possible only when both inputs
+    // are non-canonical (goldilocks_field.rs:245-267); handle it so any u64 pair is safe.
+    uint64_t c = (s < a) ? EPS : 0;
+    uint64_t t = s + c;
+    return (t < c) ? t + EPS : t;
+}
+// a - b (mod p)
+GL_HD uint64_t sub(uint64_t a, uint64_t b) {
+    uint64_t d = a - b;
+    uint64_t c = (a < b) ? EPS : 0;
+    uint64_t t = d - c;
+    return (d < c) ? t - EPS : t;
+}
+GL_HD uint64_t neg(uint64_t a) {
+    uint64_t c = canon(a);
+    return c ? P - c : 0;
+}
+
+// Reduce hi*2^64 + lo (mod p) to [0, 2^64): lo - (hi >> 32) + (hi & EPS) * EPS
+// (the reference's reduce128, goldilocks_field.rs:401-415, re-expressed on 32-bit halves).
+GL_HD uint64_t reduce128(uint64_t lo, uint64_t hi) {
+    uint64_t hh = hi >> 32;
+    uint64_t hl = hi & EPS;
+    uint64_t t0 = lo - hh;
+    if (lo < hh) t0 -= EPS;           // borrow: subtract 2^64 mod p
+    uint64_t t1 = (hl << 32) - hl;    // hl * (2^32 - 1)
+    uint64_t r = t0 + t1;
+    return (r < t1) ? r + EPS : r;    // carry: add 2^64 mod p (cannot carry again)
+}
+// Reduce hi*2^64 + lo with hi < 2^32 (a "u96").
+GL_HD uint64_t reduce96(uint64_t lo, uint32_t hi) {
+    uint64_t t1 = ((uint64_t)hi << 32) - hi;
+    uint64_t r = lo + t1;
+    return (r < t1) ? r + EPS : r;
+}
+
+// GL_FORCE_32BIT_PATH lets tests/emu run the device formulation on the host.
+GL_HD void mul_wide(uint64_t a, uint64_t b, uint64_t& lo, uint64_t& hi) {
+#if defined(__CUDA_ARCH__) || defined(GL_FORCE_32BIT_PATH)
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);
+    uint32_t b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+    uint64_t p00 = (uint64_t)a0 * b0;
+    uint64_t mid = (uint64_t)a0 * b1 + (p00 >> 32);          // < 2^64, cannot overflow
+    uint64_t mid2 = (uint64_t)a1 * b0 + (uint32_t)mid;       // < 2^64
+    hi = (uint64_t)a1 * b1 + (mid >> 32) + (mid2 >> 32);     // exact high half
+    lo = (mid2 << 32) | (uint32_t)p00;
+#else
+    unsigned __int128 p = (unsigned __int128)a * b;
+    lo = (uint64_t)p;
+    hi = (uint64_t)(p >> 64);
+#endif
+}
+GL_HD void sqr_wide(uint64_t a, uint64_t& lo, uint64_t& hi) {
+#if defined(__CUDA_ARCH__) || defined(GL_FORCE_32BIT_PATH)
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);
+    uint64_t p00 = (uint64_t)a0 * a0;
+    uint64_t p01 = (uint64_t)a0 * a1;
+    uint64_t p11 = (uint64_t)a1 * a1;
+    // a^2 = p00 + 2*p01*2^32 + p11*2^64
+    uint64_t m = p01 + (p00 >> 32);                           // < 2^64
+    uint64_t m2 = p01 + (uint32_t)m;                          // < 2^64
+    hi = p11 + (m >> 32) + (m2 >> 32);
+    lo = (m2 << 32) | (uint32_t)p00;
+#else
+    mul_wide(a, a, lo, hi);
+#endif
+}
+
+GL_HD uint64_t mul(uint64_t a, uint64_t b) {
+    uint64_t lo, hi;
+    mul_wide(a, b, lo, hi);
+    return reduce128(lo, hi);
+}
+GL_HD uint64_t sqr(uint64_t a) {
+    uint64_t lo, hi;
+    sqr_wide(a, lo, hi);
+    return reduce128(lo, hi);
+}
+// a * b + c (mod p) with one reduction (multiply_accumulate, goldilocks_field.rs:184-188)
+GL_HD uint64_t mul_add(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t lo, hi;
+    mul_wide(a, b, lo, hi);
+    uint64_t l2 = lo + c;
+    hi += (l2 < lo);  // a*b + c < 2^128
+    return reduce128(l2, hi);
+}
+
+// a * 2^k (mod p), 0 <= k < 96, using 2^64 = EPS, 2^96 = -1.
+GL_HD uint64_t mul_pow2(uint64_t a, uint32_t k) {
+    if (k == 0) return a;
+    if (k < 32) {
+        uint64_t lo = a << k;
+        uint32_t hi = (uint32_t)(a >> (64 - k));
+        return reduce96(lo, hi);
+    } else if (k == 32) {
+        return reduce96(a << 32, (uint32_t)(a >> 32));
+    } else if (k < 64) {
+        uint64_t lo = a << k;
+        uint64_t hi = a >> (64 - k);  // < 2^k, k < 64
+        return reduce128(lo, hi);
+    } else {  // 64 <= k < 96: a*2^k = (a * 2^(k-64)) * 2^64
+        uint32_t j = k - 64;
+        uint64_t lo = j ? (a << j) : a;
+        uint64_t hi = j ? (a >> (64 - j)) : 0;  // < 2^32
+        // value = hi*2^128 + lo*2^64 ; 2^128 = 2^96*2^32 = -2^32 ; lo*2^64 -> reduce128(0, lo)
+        uint64_t r = reduce128(0, lo);
+        return sub(r, hi << 32);
+    }
+}
+
+GL_HD uint64_t pow(uint64_t base, uint64_t e) {
+    uint64_t cur = base, acc = 1;
+    while (e) {
+        if (e & 1) acc = mul(acc, cur);
+        cur = sqr(cur);
+        e >>= 1;
+    }
+    return acc;
+}
+GL_HD uint64_t inv(uint64_t a) { return pow(a, P - 2); }  // try_inverse, goldilocks_field.rs:108-147
+// primitive_root_of_unity, field/src/types.rs:268-272
+GL_HD uint64_t root_of_unity(uint32_t log_n) {
+    uint64_t b = POWER_OF_TWO_GENERATOR;
+    for (uint32_t i = log_n; i < TWO_ADICITY; i++) b = sqr(b);
+    return b;
+}
+// inverse_2exp, field/src/types.rs:226-266
+GL_HD uint64_t inverse_2exp(uint32_t k) { return P - ((P - 1) >> k); }
+
+// ---- quadratic extension F[X]/(X^2 - 7) (goldilocks_extensions.rs:14-27, quadratic.rs:180-193)
+struct E2 {
+    uint64_t a, b;
+};
+GL_HD E2 e2_add(E2 x, E2 y) { return E2{add(x.a, y.a), add(x.b, y.b)}; }
+GL_HD E2 e2_sub(E2 x, E2 y) { return E2{sub(x.a, y.a), sub(x.b, y.b)}; }
+GL_HD E2 e2_mul(E2 x, E2 y) {
+    // c0 = a0*b0 + 7*a1*b1 ; c1 = a0*b1 + a1*b0
+    uint64_t t = mul(x.b, y.b);
+    uint64_t t7 = sub(mul_pow2(t, 3), t);
+    return E2{mul_add(x.a, y.a, t7), mul_add(x.a, y.b, mul(x.b, y.a))};
+}
+GL_HD E2 e2_scale(E2 x, uint64_t s) { return E2{mul(x.a, s), mul(x.b, s)}; }
+GL_HD E2 e2_inv(E2 x) {
+    uint64_t t = sqr(x.b);
+    uint64_t norm = sub(sqr(x.a), sub(mul_pow2(t, 3), t));
+    uint64_t ni = inv(norm);
+    return E2{mul(x.a, ni), mul(neg(x.b), ni)};
+}
+GL_HD E2 e2_pow(E2 base, uint64_t e) {
+    E2 cur = base, acc = E2{1, 0};
+    while (e) {
+        if (e & 1) acc = e2_mul(acc, cur);
+        cur = e2_mul(cur, cur);
+        e >>= 1;
+    }
+    return acc;
+}
+
+GL_HD uint32_t bitrev32(uint32_t x, uint32_t bits) {
+#if defined(__CUDA_ARCH__)
+    return bits ? (__brev(x) >> (32 - bits)) : 0;
+#else
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+#endif
+}
+
+}  // namespace gl

@@ -1,0 +1,186 @@
+// gl_poseidon.cuh -- Poseidon-12 (x^7, 4 + 22 + 4 rounds) over Goldilocks and the sponge built on it.
+//
+// Replaces (reference, CPU): Poseidon::poseidon and layers  plonky2/src/hash/poseidon.rs:630-641,689-777
+//                            hash_n_to_m_no_pad / compress    plonky2/src/hash/hashing.rs:97-145
+//                            Hasher::hash_or_noop             plonky2/src/plonk/config.rs:63-74
+//
+// One thread owns one 12-lane state in registers. Full rounds: x^7 with two squarings + two
+// multiplies per lane, then the circulant MDS evaluated on 32-bit halves with IMAD.WIDE
+// accumulation (constants < 2^6, so 12-term sums of 32x6-bit products stay < 2^42) and ONE 96-bit
+// reduction per lane. Partial rounds use the "fast" factorisation (w_hat / v vectors), with the
+// 12-term dot product accumulated in 160 bits and reduced once.
+#pragma once
+#include "gl_field.cuh"
+#include "gl_poseidon_constants.h"
+
+namespace gl {
+
+struct PoseidonTables {
+    uint64_t rc[360];
+    uint64_t fast_first[12];
+    uint64_t fast_rc[22];
+    uint64_t vs[22 * 11];
+    uint64_t w_hats[22 * 11];
+    uint64_t init[11 * 11];
+};
+
+#if defined(__CUDACC__)
+__constant__ PoseidonTables c_pos;
+#endif
+
+inline const PoseidonTables& host_poseidon_tables() {
+    static PoseidonTables t = [] {
+        PoseidonTables x;
+        for (int i = 0; i < 360; i++) x.rc[i] = GL_POSEIDON_RC[i];
+        for (int i = 0; i < 12; i++) x.fast_first[i] = GL_POSEIDON_FAST_FIRST_RC[i];
+        for (int i = 0; i < 22; i++) x.fast_rc[i] = GL_POSEIDON_FAST_RC[i];
+        for (int i = 0; i < 242; i++) x.vs[i] = GL_POSEIDON_FAST_VS[i];
+        for (int i = 0; i < 242; i++) x.w_hats[i] = GL_POSEIDON_FAST_W_HATS[i];
+        for (int i = 0; i < 121; i++) x.init[i] = GL_POSEIDON_FAST_INIT_MATRIX[i];
+        return x;
+    }();
+    return t;
+}
+
+#if defined(__CUDA_ARCH__)
+#define GL_POS (c_pos)
+#else
+#define GL_POS (host_poseidon_tables())
+#endif
+
+// MDS circulant first row / diagonal (poseidon_goldilocks.rs:24-25) as compile-time immediates.
+#define GL_MDS_CIRC_LIST {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20}
+
+// 160-bit accumulator for sums of 64x64 products.
+struct Acc160 {
+    uint64_t lo, hi;
+    uint32_t top;
+};
+GL_HD void acc_mul(Acc160& a, uint64_t x, uint64_t y) {
+    uint64_t pl, ph;
+    mul_wide(x, y, pl, ph);
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
+        : "+l"(a.lo), "+l"(a.hi), "+r"(a.top)
+        : "l"(pl), "l"(ph));
+#else
+    unsigned __int128 s = (unsigned __int128)a.lo + pl;
+    a.lo = (uint64_t)s;
+    unsigned __int128 h = (unsigned __int128)a.hi + ph + (uint64_t)(s >> 64);
+    a.hi = (uint64_t)h;
+    a.top += (uint32_t)(h >> 64);
+#endif
+}
+GL_HD uint64_t acc_reduce(const Acc160& a) {
+    // top*2^128 + hi*2^64 + lo ; 2^128 = 2^96 * 2^32 = -2^32 (mod p)
+    uint64_t r = reduce128(a.lo, a.hi);
+    return sub(r, (uint64_t)a.top << 32);
+}
+
+GL_HD uint64_t sbox7(uint64_t x) {  // sbox_monomial, poseidon.rs:689-696
+    uint64_t x2 = sqr(x);
+    uint64_t x4 = sqr(x2);
+    uint64_t x3 = mul(x, x2);
+    return mul(x3, x4);
+}
+
+// mds_layer (poseidon.rs:269-290; out[r] = sum_i s[(i+r)%12]*circ[i] + s[r]*diag[r]) on 32-bit halves.
+GL_HD void mds_layer(uint64_t s[12]) {
+    constexpr uint32_t CIRC[12] = GL_MDS_CIRC_LIST;
+    uint32_t lo[12], hi[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        lo[i] = (uint32_t)s[i];
+        hi[i] = (uint32_t)(s[i] >> 32);
+    }
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        uint64_t al = 0, ah = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            uint32_t c = CIRC[i] + ((r == 0 && i == 0) ? 8u : 0u);  // diag = [8,0,...,0]
+            al += (uint64_t)lo[(i + r) % 12] * c;
+            ah += (uint64_t)hi[(i + r) % 12] * c;
+        }
+        // value = al + ah * 2^32, al,ah < 2^42  ->  96-bit (l64, h32)
+        uint64_t l64 = al + (ah << 32);
+        uint32_t h32 = (uint32_t)(ah >> 32) + (l64 < al ? 1u : 0u);
+        s[r] = reduce96(l64, h32);
+    }
+}
+
+GL_HD void full_round(uint64_t s[12], const uint64_t* rc) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = sbox7(add(s[i], rc[i]));  // constant_layer + sbox_layer
+    mds_layer(s);
+}
+
+// Poseidon::poseidon, poseidon.rs:766-777 (fast partial rounds, :751-764)
+GL_HD void poseidon_permute(uint64_t s[12]) {
+    const PoseidonTables& T = GL_POS;
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) full_round(s, &T.rc[12 * r]);
+
+    // partial_first_constant_layer + mds_partial_layer_init (poseidon.rs:413-441)
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = add(s[i], T.fast_first[i]);
+    {
+        uint64_t res[12];
+        res[0] = s[0];
+#pragma unroll
+        for (int c = 1; c < 12; c++) {
+            Acc160 a = {0, 0, 0};
+#pragma unroll
+            for (int r = 1; r < 12; r++) acc_mul(a, s[r], T.init[(r - 1) * 11 + (c - 1)]);
+            res[c] = acc_reduce(a);
+        }
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = res[i];
+    }
+#pragma unroll 1
+    for (int r = 0; r < 22; r++) {
+        uint64_t s0 = add(sbox7(s[0]), T.fast_rc[r]);
+        // mds_partial_layer_fast (poseidon.rs:514-542)
+        Acc160 a = {0, 0, 0};
+        acc_mul(a, s0, 17 + 8);
+#pragma unroll
+        for (int i = 1; i < 12; i++) acc_mul(a, s[i], T.w_hats[r * 11 + i - 1]);
+#pragma unroll
+        for (int i = 1; i < 12; i++) s[i] = mul_add(s0, T.vs[r * 11 + i - 1], s[i]);
+        s[0] = acc_reduce(a);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) full_round(s, &T.rc[12 * (26 + r)]);
+}
+
+// compress / two_to_one (hashing.rs:97-114): state = [l, r, 0,0,0,0]; one permutation; lanes 0..3.
+GL_HD void two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]) {
+    uint64_t s[12] = {l[0], l[1], l[2], l[3], r[0], r[1], r[2], r[3], 0, 0, 0, 0};
+    poseidon_permute(s);
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = canon(s[i]);
+}
+
+// hash_or_noop over a strided leaf (config.rs:63-74 + hashing.rs:118-141, overwrite-mode sponge):
+// element k of the leaf is in[k * stride].
+template <bool NOOP_SHORT = true>
+GL_HD void hash_or_noop_strided(const uint64_t* in, size_t stride, uint32_t W, uint64_t out[4]) {
+    if (NOOP_SHORT && W <= 4) {
+#pragma unroll
+        for (uint32_t i = 0; i < 4; i++) out[i] = (i < W) ? canon(in[i * stride]) : 0;
+        return;
+    }
+    uint64_t s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+    for (uint32_t off = 0; off < W; off += 8) {
+#pragma unroll
+        for (uint32_t i = 0; i < 8; i++)
+            if (off + i < W) s[i] = in[(size_t)(off + i) * stride];
+        poseidon_permute(s);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = canon(s[i]);
+}
+
+}  // namespace gl

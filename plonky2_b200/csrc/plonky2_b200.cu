@@ -1,0 +1,1567 @@
+// plonky2_b200.cu -- sm_100a kernels + host orchestration + the C ABI of include/plonky2_b200.h.
+//
+// Hot path implemented here (reference -> this file):
+//   PolynomialBatch::from_values/from_coeffs  plonky2/src/fri/oracle.rs:57-139   -> commit_build()
+//   MerkleTree::new / prove                   plonky2/src/hash/merkle_tree.rs:86-237 -> tree_build(), tree_open()
+//   prove_openings (pre-FRI part)             plonky2/src/fri/oracle.rs:176-220   -> gl_fri_begin()
+//   fri_committed_trees / fri_proof_of_work   plonky2/src/fri/prover.rs:84-202    -> gl_fri_commit_round/fold/pow
+// There is no CPU fallback anywhere in this file: every compute entry point launches kernels.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/plonky2_b200.h"
+#include "gl_field.cuh"
+#include "gl_ntt.cuh"
+#include "gl_poseidon.cuh"
+
+using namespace gl;
+typedef uint64_t u64;
+
+// =====================================================================================
+// errors / context
+// =====================================================================================
+static thread_local std::string g_last_error;
+
+struct gl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    u64 launches = 0;
+    std::string err;
+    u64* wt[NTT_MAX_LOG_TILE + 1] = {nullptr};  // full-cycle in-tile tables, wt[log][j] = w_{2^log}^j
+    std::map<int, u64*> twa;                    // pass-A twiddles by log_n
+    u64* scratch = nullptr;                     // NTT group scratch (device)
+    size_t scratch_words = 0;
+    u64* pinned = nullptr;                      // host staging for small D2H / H2D
+    size_t pinned_words = 0;
+    u64* dstage = nullptr;                      // device staging for openings
+    size_t dstage_words = 0;
+    uint32_t ntt_group = 0;                     // 0 = auto
+};
+
+static int set_err(gl_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (ctx) ctx->err = buf;
+    return code;
+}
+#define CK(ctx, call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return set_err(ctx, e_ == cudaErrorMemoryAllocation ? GL_ERR_OOM : GL_ERR_CUDA,    \
+                           "%s failed: %s", #call, cudaGetErrorString(e_));                    \
+    } while (0)
+#define CKL(ctx)                                                                               \
+    do {                                                                                       \
+        (ctx)->launches++;                                                                     \
+        cudaError_t e_ = cudaGetLastError();                                                   \
+        if (e_ != cudaSuccess)                                                                 \
+            return set_err(ctx, GL_ERR_CUDA, "kernel launch failed (%s:%d): %s", __FILE__,     \
+                           __LINE__, cudaGetErrorString(e_));                                  \
+    } while (0)
+#define TRY(expr)                  \
+    do {                           \
+        int rc_ = (expr);          \
+        if (rc_ != GL_OK) return rc_; \
+    } while (0)
+
+static int dmalloc(gl_ctx* ctx, u64** p, size_t words) {
+    *p = nullptr;
+    if (words == 0) return GL_OK;
+    CK(ctx, cudaMallocAsync((void**)p, words * 8, ctx->stream));
+    return GL_OK;
+}
+static void dfree(gl_ctx* ctx, u64* p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+static int ensure_scratch(gl_ctx* ctx, size_t words) {
+    if (ctx->scratch_words >= words) return GL_OK;
+    if (ctx->scratch) dfree(ctx, ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_words = 0;
+    TRY(dmalloc(ctx, &ctx->scratch, words));
+    ctx->scratch_words = words;
+    return GL_OK;
+}
+static int ensure_pinned(gl_ctx* ctx, size_t words) {
+    if (ctx->pinned_words >= words) return GL_OK;
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_words = 0;
+    size_t w = words < 65536 ? 65536 : words;
+    CK(ctx, cudaHostAlloc((void**)&ctx->pinned, w * 8, cudaHostAllocDefault));
+    ctx->pinned_words = w;
+    return GL_OK;
+}
+static int ensure_dstage(gl_ctx* ctx, size_t words) {
+    if (ctx->dstage_words >= words) return GL_OK;
+    if (ctx->dstage) dfree(ctx, ctx->dstage);
+    ctx->dstage = nullptr;
+    ctx->dstage_words = 0;
+    size_t w = words < 65536 ? 65536 : words;
+    TRY(dmalloc(ctx, &ctx->dstage, w));
+    ctx->dstage_words = w;
+    return GL_OK;
+}
+// device -> host through pinned staging (stream-ordered, then synchronised)
+static int d2h(gl_ctx* ctx, u64* host, const u64* dev, size_t words) {
+    if (words == 0) return GL_OK;
+    CK(ctx, cudaMemcpyAsync(host, dev, words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+static int h2d(gl_ctx* ctx, u64* dev, const u64* host, size_t words) {
+    if (words == 0) return GL_OK;
+    CK(ctx, cudaMemcpyAsync(dev, host, words * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return GL_OK;
+}
+static int copy_out(gl_ctx* ctx, u64* out, const u64* dev, size_t words, int mem) {
+    if (mem == GL_MEM_DEVICE) {
+        CK(ctx, cudaMemcpyAsync(out, dev, words * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        return GL_OK;
+    }
+    return d2h(ctx, out, dev, words);
+}
+
+// =====================================================================================
+// TMA bulk copy of the in-tile twiddle table (cp.async.bulk + mbarrier)
+// =====================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void tma_table_issue(u64* dst_smem, const u64* src_gmem, uint32_t bytes, u64* mbar) {
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(dst_smem)),
+            "l"(src_gmem), "r"(bytes), "r"(smem_u32(mbar))
+            : "memory");
+    }
+}
+// all threads: called after a __syncthreads() that follows tma_table_issue()
+__device__ __forceinline__ void tma_table_wait(u64* mbar) {
+    uint32_t done = 0;
+    const uint32_t addr = smem_u32(mbar);
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr)
+            : "memory");
+    }
+}
+
+// =====================================================================================
+// NTT kernels
+// =====================================================================================
+template <int LOG>
+__global__ void __launch_bounds__(ntt_tile_threads(LOG)) k_passA(PassA pa) {
+    extern __shared__ __align__(16) u64 smem[];
+    u64* wt_s = smem;
+    u64* s = smem + (1 << LOG);
+    u64* mbar = s + (size_t)(1 << LOG) * ntt_tile_TS(LOG);
+    tma_table_issue(wt_s, pa.wt, (uint32_t)((1 << LOG) * 8), mbar);
+    passA_load<LOG>(pa, s, blockIdx.x, threadIdx.x, blockDim.x);
+    __syncthreads();
+    tma_table_wait(mbar);
+#pragma unroll 1
+    for (int i = 0; i < ntt_num_steps(LOG); i++) {
+        tile_step<LOG>(s, wt_s, i, threadIdx.x, blockDim.x);
+        __syncthreads();
+    }
+    passA_store<LOG>(pa, s, blockIdx.x, threadIdx.x, blockDim.x);
+}
+
+template <int LOG, int MODE>
+__global__ void __launch_bounds__(ntt_tile_threads(LOG)) k_passB(PassB pb) {
+    extern __shared__ __align__(16) u64 smem[];
+    u64* wt_s = smem;
+    u64* s = smem + (1 << LOG);
+    u64* mbar = s + (size_t)(1 << LOG) * ntt_tile_TS(LOG);
+    tma_table_issue(wt_s, pb.wt, (uint32_t)((1 << LOG) * 8), mbar);
+    passB_load<LOG, MODE>(pb, s, blockIdx.x, threadIdx.x, blockDim.x);
+    __syncthreads();
+    tma_table_wait(mbar);
+#pragma unroll 1
+    for (int i = 0; i < ntt_num_steps(LOG); i++) {
+        tile_step<LOG>(s, wt_s, i, threadIdx.x, blockDim.x);
+        __syncthreads();
+    }
+    passB_store<LOG, MODE>(pb, s, blockIdx.x, threadIdx.x, blockDim.x);
+}
+
+__global__ void k_fill_wt(int log, u64* out) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < (1u << log)) out[j] = table_wt_entry(log, j);
+}
+__global__ void k_fill_twa(int a, int b, u64* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ((size_t)1 << (a + b))) out[i] = table_twa_entry(a, b, i);
+}
+// out[t*count + i] = bases[t]^i  for t < ntab
+__global__ void k_fill_pows(const u64* bases, int ntab, size_t count, u64* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count * ntab) return;
+    size_t t = i / count, e = i % count;
+    out[i] = gl::pow(bases[t], e);
+}
+// data[b*stride + k] *= hi[k >> lowbits] * lo[k & mask]
+__global__ void k_mul_pows(u64* data, size_t stride, size_t n, const u64* hi, const u64* lo, int lowbits) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    u64* col = data + (size_t)blockIdx.y * stride;
+    u64 f = mul(hi[k >> lowbits], lo[k & (((size_t)1 << lowbits) - 1)]);
+    col[k] = canon(mul(col[k], f));
+}
+
+template <int LOG>
+static int launch_passA(gl_ctx* ctx, const PassA& pa, int nblocks) {
+    const size_t smem = ntt_tile_smem_bytes(LOG);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CK(ctx, cudaFuncSetAttribute(k_passA<LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    k_passA<LOG><<<nblocks, ntt_tile_threads(LOG), smem, ctx->stream>>>(pa);
+    CKL(ctx);
+    return GL_OK;
+}
+template <int LOG, int MODE>
+static int launch_passB(gl_ctx* ctx, const PassB& pb) {
+    const size_t smem = ntt_tile_smem_bytes(LOG);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CK(ctx, cudaFuncSetAttribute(k_passB<LOG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const int nblocks = passB_blocks<LOG>(pb, MODE);
+    k_passB<LOG, MODE><<<nblocks, ntt_tile_threads(LOG), smem, ctx->stream>>>(pb);
+    CKL(ctx);
+    return GL_OK;
+}
+#define LOG_SWITCH(LOGV, LO, EXPR)                                                 \
+    switch (LOGV) {                                                                \
+        case 1: { constexpr int L = 1; EXPR; } break;                              \
+        case 2: { constexpr int L = 2; EXPR; } break;                              \
+        case 3: { constexpr int L = 3; EXPR; } break;                              \
+        case 4: { constexpr int L = 4; EXPR; } break;                              \
+        case 5: { constexpr int L = 5; EXPR; } break;                              \
+        case 6: { constexpr int L = 6; EXPR; } break;                              \
+        case 7: { constexpr int L = 7; EXPR; } break;                              \
+        case 8: { constexpr int L = 8; EXPR; } break;                              \
+        case 9: { constexpr int L = 9; EXPR; } break;                              \
+        case 10: { constexpr int L = 10; EXPR; } break;                            \
+        case 11: { constexpr int L = 11; EXPR; } break;                            \
+        case 12: { constexpr int L = 12; EXPR; } break;                            \
+        default: return set_err(ctx, GL_ERR_UNSUPPORTED, "tile log %d", (int)(LOGV)); \
+    }
+
+static int dispatch_passA(gl_ctx* ctx, int a, const PassA& pa, int nblocks) {
+    if (a < 6) return set_err(ctx, GL_ERR_UNSUPPORTED, "pass A log %d", a);
+    switch (a) {
+        case 6: return launch_passA<6>(ctx, pa, nblocks);
+        case 7: return launch_passA<7>(ctx, pa, nblocks);
+        case 8: return launch_passA<8>(ctx, pa, nblocks);
+        case 9: return launch_passA<9>(ctx, pa, nblocks);
+        case 10: return launch_passA<10>(ctx, pa, nblocks);
+        case 11: return launch_passA<11>(ctx, pa, nblocks);
+        case 12: return launch_passA<12>(ctx, pa, nblocks);
+    }
+    return set_err(ctx, GL_ERR_UNSUPPORTED, "pass A log %d", a);
+}
+static int dispatch_passB(gl_ctx* ctx, int b, int mode, const PassB& pb) {
+    if (mode == PB_NATURAL) {
+        LOG_SWITCH(b, 1, return (launch_passB<L, PB_NATURAL>(ctx, pb)));
+    } else if (mode == PB_NATURAL_COLS) {
+        LOG_SWITCH(b, 1, return (launch_passB<L, PB_NATURAL_COLS>(ctx, pb)));
+    } else {
+        LOG_SWITCH(b, 1, return (launch_passB<L, PB_LEAVES>(ctx, pb)));
+    }
+    return GL_OK;
+}
+
+static int get_wt(gl_ctx* ctx, int log, const u64** out) {
+    if (log < 1 || log > NTT_MAX_LOG_TILE) return set_err(ctx, GL_ERR_UNSUPPORTED, "wt log %d", log);
+    if (!ctx->wt[log]) {
+        CK(ctx, cudaMalloc((void**)&ctx->wt[log], ((size_t)8 << log) < 16 ? 16 : ((size_t)8 << log)));
+        k_fill_wt<<<((1 << log) + 255) / 256, 256, 0, ctx->stream>>>(log, ctx->wt[log]);
+        CKL(ctx);
+    }
+    *out = ctx->wt[log];
+    return GL_OK;
+}
+static int get_twa(gl_ctx* ctx, int log_n, const u64** out) {
+    auto it = ctx->twa.find(log_n);
+    if (it == ctx->twa.end()) {
+        int a, b;
+        ntt_split(log_n, a, b);
+        u64* p;
+        CK(ctx, cudaMalloc((void**)&p, (size_t)8 << log_n));
+        size_t n = (size_t)1 << log_n;
+        k_fill_twa<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a, b, p);
+        CKL(ctx);
+        ctx->twa[log_n] = p;
+        *out = p;
+        return GL_OK;
+    }
+    *out = it->second;
+    return GL_OK;
+}
+// columns per group so that the pass-A scratch stays L2-resident (about 32 MiB), multiple of 8
+static uint32_t group_cols(const gl_ctx* ctx, int log_n, uint32_t ncols) {
+    uint32_t g = ctx->ntt_group;
+    if (g == 0) {
+        size_t col_bytes = (size_t)8 << log_n;
+        size_t target = (size_t)32 << 20;
+        g = (uint32_t)(target / col_bytes);
+        if (g < 8) g = 8;
+    }
+    g = (g + 7) & ~7u;
+    if (g > ((ncols + 7) & ~7u)) g = (ncols + 7) & ~7u;
+    return g;
+}
+
+// Upload `bases` (host) and build ntab tables of `count` powers each on the device.
+static int build_pow_tables(gl_ctx* ctx, const std::vector<u64>& bases, size_t count, u64** out) {
+    const int ntab = (int)bases.size();
+    u64* dbases;
+    TRY(dmalloc(ctx, &dbases, ntab));
+    TRY(ensure_pinned(ctx, ntab));
+    // pinned staging is reused: make sure earlier async copies from it are done
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->pinned, bases.data(), ntab * 8);
+    TRY(h2d(ctx, dbases, ctx->pinned, ntab));
+    TRY(dmalloc(ctx, out, count * ntab));
+    size_t total = count * ntab;
+    k_fill_pows<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(dbases, ntab, count, *out);
+    CKL(ctx);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));  // pinned buffer free for reuse
+    dfree(ctx, dbases);
+    return GL_OK;
+}
+
+// Natural-order NTT of `ncols` device columns (in -> out, may alias), optional forward coset pre-scale.
+static int ntt_natural(gl_ctx* ctx, const u64* in, size_t in_stride, u64* out, size_t out_stride, int log_n,
+                       uint32_t ncols, bool inverse, u64 shift) {
+    if (ncols == 0) return GL_OK;
+    const size_t n = (size_t)1 << log_n;
+    if (log_n == 0) {
+        if (in != out)
+            for (uint32_t c = 0; c < ncols; c++)
+                CK(ctx, cudaMemcpyAsync(out + c * out_stride, in + c * in_stride, 8, cudaMemcpyDeviceToDevice,
+                                        ctx->stream));
+        // canonicalise via a multiply by one
+        u64 one = 1;
+        u64* tabs;
+        TRY(build_pow_tables(ctx, std::vector<u64>{one, one}, 1, &tabs));
+        k_mul_pows<<<dim3(1, ncols), 32, 0, ctx->stream>>>(out, out_stride, 1, tabs, tabs + 1, 0);
+        CKL(ctx);
+        dfree(ctx, tabs);
+        return GL_OK;
+    }
+    if (log_n > 2 * NTT_MAX_LOG_TILE) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %d > 24", log_n);
+    int a, b;
+    ntt_split(log_n, a, b);
+    const u64 *wta = nullptr, *wtb = nullptr, *twa = nullptr;
+    TRY(get_wt(ctx, b, &wtb));
+    const bool coset = (!inverse) && (canon(shift) != 1);
+    u64* ctab = nullptr;  // [u (R entries) | v (C entries)] for the forward coset
+    if (a > 0) {
+        TRY(get_wt(ctx, a, &wta));
+        TRY(get_twa(ctx, log_n, &twa));
+    }
+    const size_t R = (size_t)1 << a, C = (size_t)1 << b;
+    if (coset) {
+        size_t cnt = R > C ? R : C;
+        std::vector<u64> bases = {gl::pow(shift, C), shift};
+        TRY(build_pow_tables(ctx, bases, cnt, &ctab));  // ctab[0..cnt) = (s^C)^i ; ctab[cnt..) = s^i
+        // single-pass: v must have n = C entries (cnt == C)
+        (void)cnt;
+    }
+    const size_t cnt = R > C ? R : C;
+    PassB pb{};
+    pb.wt = wtb;
+    pb.log_r = a;
+    pb.reverse = inverse ? 1 : 0;
+    pb.scale = inverse ? inverse_2exp((uint32_t)log_n) : 1;
+    if (a == 0) {
+        pb.in = in;
+        pb.in_stride = in_stride;
+        pb.out = out;
+        pb.out_stride = out_stride;
+        pb.ncols = (int)ncols;
+        pb.pre = coset ? ctab + cnt : nullptr;
+        TRY(dispatch_passB(ctx, b, PB_NATURAL_COLS, pb));
+    } else {
+        const uint32_t G = group_cols(ctx, log_n, ncols);
+        TRY(ensure_scratch(ctx, (size_t)G * n));
+        for (uint32_t g0 = 0; g0 < ncols; g0 += G) {
+            const uint32_t gc = (ncols - g0 < G) ? ncols - g0 : G;
+            PassA pa{};
+            pa.in = in + (size_t)g0 * in_stride;
+            pa.in_stride = in_stride;
+            pa.out = ctx->scratch;
+            pa.out_stride = n;
+            pa.twa = twa;
+            pa.wt = wta;
+            pa.log_c = b;
+            pa.tiles_per_col = (int)(C / ntt_tile_T(a));
+            pa.u = coset ? ctab : nullptr;
+            pa.v = coset ? ctab + cnt : nullptr;
+            TRY(dispatch_passA(ctx, a, pa, (int)gc * pa.tiles_per_col));
+            pb.in = ctx->scratch;
+            pb.in_stride = n;
+            pb.out = out + (size_t)g0 * out_stride;
+            pb.out_stride = out_stride;
+            pb.ncols = (int)gc;
+            TRY(dispatch_passB(ctx, b, PB_NATURAL, pb));
+        }
+    }
+    if (ctab) dfree(ctx, ctab);
+    if (inverse && canon(shift) != 1) {
+        // coset_ifft: coefficients *= shift^-k   (polynomial/mod.rs:63-73)
+        const int lowbits = log_n > 12 ? 12 : log_n;
+        const size_t lo_cnt = (size_t)1 << lowbits, hi_cnt = (size_t)1 << (log_n - lowbits);
+        const u64 sinv = gl::inv(shift);
+        const size_t tcnt = lo_cnt > hi_cnt ? lo_cnt : hi_cnt;
+        u64* tabs;
+        TRY(build_pow_tables(ctx, std::vector<u64>{gl::pow(sinv, lo_cnt), sinv}, tcnt, &tabs));
+        k_mul_pows<<<dim3((unsigned)((n + 255) / 256), ncols), 256, 0, ctx->stream>>>(out, out_stride, n, tabs,
+                                                                                     tabs + tcnt, lowbits);
+        CKL(ctx);
+        dfree(ctx, tabs);
+    }
+    return GL_OK;
+}
+
+// Coset LDE of device coefficient columns into leaf-major rows:
+// leaves[(c*n + j)*W + col0 + col] = P_col( g * w_N^{bitrev_r(c)} * w_n^{bitrev(j)} ), base shift g.
+static int lde_leaves(gl_ctx* ctx, const u64* coeffs, size_t coeff_stride, uint32_t ncols, int log_n, int rate_bits,
+                      u64 base_shift, u64* leaves, size_t W, int col0) {
+    if (ncols == 0) return GL_OK;
+    if (log_n > 2 * NTT_MAX_LOG_TILE) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %d > 24", log_n);
+    if (log_n < 1) return set_err(ctx, GL_ERR_BAD_SHAPE, "lde_leaves needs n >= 2");
+    const size_t n = (size_t)1 << log_n;
+    const int ncos = 1 << rate_bits;
+    int a = 0, b = log_n;
+    ntt_split(log_n, a, b);
+    const size_t R = (size_t)1 << a, C = (size_t)1 << b;
+    const size_t cnt = R > C ? R : C;
+    // per-coset scale tables: [c][0] = (s_c^C)^i, [c][1] = s_c^i
+    std::vector<u64> bases;
+    const u64 wN = root_of_unity((uint32_t)(log_n + rate_bits));
+    for (int c = 0; c < ncos; c++) {
+        u64 s = mul(base_shift, gl::pow(wN, bitrev32((uint32_t)c, (uint32_t)rate_bits)));
+        bases.push_back(gl::pow(s, C));
+        bases.push_back(s);
+    }
+    u64* ctab;
+    TRY(build_pow_tables(ctx, bases, cnt, &ctab));
+    const u64 *wta = nullptr, *wtb = nullptr, *twa = nullptr;
+    if (b > 0) TRY(get_wt(ctx, b, &wtb));
+    if (a > 0) {
+        TRY(get_wt(ctx, a, &wta));
+        TRY(get_twa(ctx, log_n, &twa));
+    }
+    const uint32_t G = a > 0 ? group_cols(ctx, log_n, ncols) : ncols;
+    if (a > 0) TRY(ensure_scratch(ctx, (size_t)G * n));
+    for (uint32_t g0 = 0; g0 < ncols; g0 += G) {
+        const uint32_t gc = (ncols - g0 < G) ? ncols - g0 : G;
+        for (int c = 0; c < ncos; c++) {
+            const u64* u = ctab + (size_t)(2 * c) * cnt;
+            const u64* v = ctab + (size_t)(2 * c + 1) * cnt;
+            PassB pb{};
+            pb.wt = wtb;
+            pb.log_r = a;
+            pb.scale = 1;
+            pb.out = leaves;
+            pb.out_stride = W;
+            pb.row0 = (size_t)c * n;
+            pb.col0 = col0 + (int)g0;
+            pb.ncols = (int)gc;
+            if (a == 0) {
+                pb.in = coeffs + (size_t)g0 * coeff_stride;
+                pb.in_stride = coeff_stride;
+                pb.pre = v;
+            } else {
+                PassA pa{};
+                pa.in = coeffs + (size_t)g0 * coeff_stride;
+                pa.in_stride = coeff_stride;
+                pa.out = ctx->scratch;
+                pa.out_stride = n;
+                pa.twa = twa;
+                pa.wt = wta;
+                pa.log_c = b;
+                pa.tiles_per_col = (int)(C / ntt_tile_T(a));
+                pa.u = u;
+                pa.v = v;
+                TRY(dispatch_passA(ctx, a, pa, (int)gc * pa.tiles_per_col));
+                pb.in = ctx->scratch;
+                pb.in_stride = n;
+            }
+            TRY(dispatch_passB(ctx, b, PB_LEAVES, pb));
+        }
+    }
+    dfree(ctx, ctab);
+    return GL_OK;
+}
+
+// degenerate n = 1 LDE: leaves[c][col] = coeff[col]
+__global__ void k_lde_const(const u64* coeffs, size_t stride, uint32_t ncols, int ncos, u64* leaves, size_t W, int col0) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncols * (uint32_t)ncos) return;
+    uint32_t col = i % ncols, c = i / ncols;
+    leaves[(size_t)c * W + col0 + col] = canon(coeffs[(size_t)col * stride]);
+}
+
+// =====================================================================================
+// Poseidon / Merkle kernels
+// =====================================================================================
+struct TreeView {
+    const u64* leaves;  // N x W row-major
+    u64* digests;       // 4 * 2 * (N - C)
+    u64* cap;           // 4 * C
+    size_t N;
+    uint32_t W, log_n, cap_height;
+};
+
+// position (in hashes) of node q of layer i inside its subtree's digest block (merkle_tree.rs:176-187)
+__host__ __device__ __forceinline__ size_t digest_pos(size_t q, uint32_t i) {
+    return 2 * (((q >> 1) << (i + 1)) + ((size_t)1 << i) - 1) + (q & 1);
+}
+
+__global__ void __launch_bounds__(128) k_leaf_hash(TreeView t) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= t.N) return;
+    u64 h[4];
+    hash_or_noop_strided(t.leaves + j * t.W, 1, t.W, h);
+    u64* dst;
+    const uint32_t sub_log = t.log_n - t.cap_height;  // log2(leaves per cap subtree)
+    if (sub_log == 0) {
+        dst = t.cap + 4 * j;
+    } else {
+        const size_t L = (size_t)1 << sub_log;
+        const size_t c = j >> sub_log, q = j & (L - 1);
+        dst = t.digests + 4 * (c * 2 * (L - 1) + digest_pos(q, 0));
+    }
+    dst[0] = h[0];
+    dst[1] = h[1];
+    dst[2] = h[2];
+    dst[3] = h[3];
+}
+// layer i (>= 1) from layer i-1: one thread per node
+__global__ void __launch_bounds__(128) k_merkle_level(TreeView t, uint32_t i) {
+    const uint32_t sub_log = t.log_n - t.cap_height;
+    const size_t nodes_per_sub = (size_t)1 << (sub_log - i);
+    const size_t total = nodes_per_sub << t.cap_height;
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const size_t c = g >> (sub_log - i), q = g & (nodes_per_sub - 1);
+    const size_t L = (size_t)1 << sub_log;
+    u64* sub = t.digests + 4 * (c * 2 * (L - 1));
+    const u64* pair = sub + 4 * digest_pos(2 * q, i - 1);
+    u64 l[4] = {pair[0], pair[1], pair[2], pair[3]};
+    u64 r[4] = {pair[4], pair[5], pair[6], pair[7]};
+    u64 h[4];
+    two_to_one(l, r, h);
+    u64* dst = (i == sub_log) ? (t.cap + 4 * c) : (sub + 4 * digest_pos(q, i));
+    dst[0] = h[0];
+    dst[1] = h[1];
+    dst[2] = h[2];
+    dst[3] = h[3];
+}
+template <bool NOOP_SHORT>
+__global__ void __launch_bounds__(128) k_hash_many(const u64* in, size_t n_items, uint32_t W, u64* out) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_items) return;
+    u64 h[4];
+    hash_or_noop_strided<NOOP_SHORT>(in + j * W, 1, W, h);
+    for (int k = 0; k < 4; k++) out[4 * j + k] = h[k];
+}
+__global__ void __launch_bounds__(128) k_two_to_one_many(const u64* in, size_t n_items, u64* out) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_items) return;
+    u64 l[4], r[4], h[4];
+    for (int k = 0; k < 4; k++) {
+        l[k] = in[8 * j + k];
+        r[k] = in[8 * j + 4 + k];
+    }
+    two_to_one(l, r, h);
+    for (int k = 0; k < 4; k++) out[4 * j + k] = h[k];
+}
+// Openings: one CTA per queried leaf; copies the leaf and its sibling path (merkle_tree.rs:151-190).
+__global__ void k_tree_open(TreeView t, const u64* indices, u64* out_leaves, u64* out_paths) {
+    const size_t idx = indices[blockIdx.x];
+    const uint32_t num_layers = t.log_n - t.cap_height;
+    for (uint32_t k = threadIdx.x; k < t.W; k += blockDim.x)
+        out_leaves[(size_t)blockIdx.x * t.W + k] = t.leaves[idx * t.W + k];
+    const size_t L = (size_t)1 << num_layers;
+    const size_t tree_index = idx >> num_layers;
+    const u64* sub = t.digests + 4 * (tree_index * 2 * (L - 1));
+    for (uint32_t k = threadIdx.x; k < num_layers * 4; k += blockDim.x) {
+        const uint32_t i = k >> 2, w = k & 3;
+        const size_t node = (idx & (L - 1)) >> i;  // ancestor at layer i
+        const size_t sib = node ^ 1;
+        out_paths[(size_t)blockIdx.x * num_layers * 4 + k] = sub[4 * digest_pos(sib, i) + w];
+    }
+}
+
+struct Tree {
+    u64* leaves = nullptr;  // device
+    bool own_leaves = false;
+    u64* digests = nullptr;
+    u64* cap = nullptr;
+    size_t N = 0;
+    uint32_t W = 0, log_n = 0, cap_height = 0;
+    TreeView view() const { return TreeView{leaves, digests, cap, N, W, log_n, cap_height}; }
+    size_t digest_words() const { return 8 * (N - ((size_t)1 << cap_height)); }
+    size_t cap_words() const { return (size_t)4 << cap_height; }
+};
+
+static int log2_exact(size_t n, uint32_t* out) {
+    if (n == 0 || (n & (n - 1))) return 1;
+    uint32_t l = 0;
+    while (((size_t)1 << l) < n) l++;
+    *out = l;
+    return 0;
+}
+
+// MerkleTree::new over device leaves (merkle_tree.rs:193-224)
+static int tree_build(gl_ctx* ctx, Tree& t) {
+    if (log2_exact(t.N, &t.log_n)) return set_err(ctx, GL_ERR_BAD_SHAPE, "Not a power of two: %zu", t.N);
+    if (t.cap_height > t.log_n)
+        return set_err(ctx, GL_ERR_BAD_SHAPE, "cap_height=%u should be at most log2(leaves.len())=%u", t.cap_height,
+                       t.log_n);
+    TRY(dmalloc(ctx, &t.digests, t.digest_words()));
+    TRY(dmalloc(ctx, &t.cap, t.cap_words()));
+    TreeView v = t.view();
+    k_leaf_hash<<<(unsigned)((t.N + 127) / 128), 128, 0, ctx->stream>>>(v);
+    CKL(ctx);
+    const uint32_t sub_log = t.log_n - t.cap_height;
+    for (uint32_t i = 1; i <= sub_log; i++) {
+        size_t total = (size_t)1 << (t.log_n - i);
+        k_merkle_level<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(v, i);
+        CKL(ctx);
+    }
+    return GL_OK;
+}
+static void tree_free(gl_ctx* ctx, Tree& t) {
+    if (t.own_leaves) dfree(ctx, t.leaves);
+    dfree(ctx, t.digests);
+    dfree(ctx, t.cap);
+    t.leaves = t.digests = t.cap = nullptr;
+}
+static int tree_open(gl_ctx* ctx, const Tree& t, const u64* leaf_indices, size_t count, u64* out_leaves,
+                     u64* out_paths) {
+    if (count == 0) return GL_OK;
+    for (size_t i = 0; i < count; i++)
+        if (leaf_indices[i] >= t.N) return set_err(ctx, GL_ERR_BAD_ARG, "leaf index %llu out of range",
+                                                   (unsigned long long)leaf_indices[i]);
+    const uint32_t layers = t.log_n - t.cap_height;
+    const size_t lw = count * t.W, pw = count * layers * 4;
+    TRY(ensure_dstage(ctx, count + lw + pw));
+    TRY(ensure_pinned(ctx, count + lw + pw));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->pinned, leaf_indices, count * 8);
+    TRY(h2d(ctx, ctx->dstage, ctx->pinned, count));
+    k_tree_open<<<(unsigned)count, 128, 0, ctx->stream>>>(t.view(), ctx->dstage, ctx->dstage + count,
+                                                         ctx->dstage + count + lw);
+    CKL(ctx);
+    TRY(d2h(ctx, ctx->pinned, ctx->dstage + count, lw + pw));
+    memcpy(out_leaves, ctx->pinned, lw * 8);
+    if (pw) memcpy(out_paths, ctx->pinned + lw, pw * 8);
+    return GL_OK;
+}
+
+// =====================================================================================
+// PolynomialBatch
+// =====================================================================================
+struct gl_commit {
+    gl_ctx* ctx;
+    uint32_t B, W, degree_log, rate_bits;
+    bool blinding;
+    u64* coeffs = nullptr;  // B x n
+    Tree tree;
+};
+
+// leaves[j][B + s] = salt[s][bitrev(j)]  (salt columns are LDE columns in natural order, oracle.rs:133-137)
+__global__ void k_salt(const u64* salt, size_t N, uint32_t log_N, u64* leaves, size_t W, uint32_t B) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    size_t i = (size_t)(__brevll(j) >> (64 - log_N));
+    if (log_N == 0) i = 0;
+    for (int s = 0; s < GL_SALT_SIZE; s++) leaves[j * W + B + s] = canon(salt[(size_t)s * N + i]);
+}
+__global__ void k_canon(u64* data, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) data[i] = canon(data[i]);
+}
+
+static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_stride, const u64* salt, int is_coeffs,
+                        int mem, uint32_t cap_height) {
+    const size_t n = (size_t)1 << c->degree_log, N = n << c->rate_bits;
+    const uint32_t B = c->B;
+    TRY(dmalloc(ctx, &c->coeffs, (size_t)B * n));
+    // inputs -> device coefficient buffer
+    if (mem == GL_MEM_HOST) {
+        if (col_stride == n) {
+            TRY(h2d(ctx, c->coeffs, cols, (size_t)B * n));
+        } else {
+            for (uint32_t b = 0; b < B; b++) TRY(h2d(ctx, c->coeffs + (size_t)b * n, cols + (size_t)b * col_stride, n));
+        }
+    } else {
+        CK(ctx, cudaMemcpy2DAsync(c->coeffs, n * 8, cols, col_stride * 8, n * 8, B, cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
+    }
+    if (!is_coeffs) {
+        // "IFFT" (oracle.rs:65-69)
+        TRY(ntt_natural(ctx, c->coeffs, n, c->coeffs, n, (int)c->degree_log, B, true, 1));
+    } else {
+        size_t tot = (size_t)B * n;
+        k_canon<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(c->coeffs, tot);
+        CKL(ctx);
+    }
+    // "FFT + blinding" + "transpose LDEs" + bit-reversal, fused: leaf-major coset LDE
+    Tree& t = c->tree;
+    t.N = N;
+    t.W = c->W;
+    t.cap_height = cap_height;
+    t.own_leaves = true;
+    TRY(dmalloc(ctx, &t.leaves, N * (size_t)c->W));
+    if (c->degree_log == 0) {
+        const int ncos = 1 << c->rate_bits;
+        k_lde_const<<<(B * ncos + 127) / 128, 128, 0, ctx->stream>>>(c->coeffs, n, B, ncos, t.leaves, c->W, 0);
+        CKL(ctx);
+    } else {
+        TRY(lde_leaves(ctx, c->coeffs, n, B, (int)c->degree_log, (int)c->rate_bits, MULTIPLICATIVE_GROUP_GENERATOR,
+                       t.leaves, c->W, 0));
+    }
+    if (salt) {
+        u64* dsalt = nullptr;
+        const u64* sp = salt;
+        if (mem == GL_MEM_HOST) {
+            TRY(dmalloc(ctx, &dsalt, GL_SALT_SIZE * N));
+            TRY(h2d(ctx, dsalt, salt, GL_SALT_SIZE * N));
+            sp = dsalt;
+        }
+        k_salt<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(sp, N, c->degree_log + c->rate_bits, t.leaves,
+                                                                    c->W, B);
+        CKL(ctx);
+        if (dsalt) dfree(ctx, dsalt);
+    }
+    // "build Merkle tree"
+    TRY(tree_build(ctx, t));
+    return GL_OK;
+}
+
+// =====================================================================================
+// FRI
+// =====================================================================================
+struct PolyRef {
+    const u64* ptr;
+    u64 a0, a1;  // alpha^j
+};
+// comp[k] = sum_j alpha^j * f_j[k]   (ReducingFactor::reduce_polys_base, reducing.rs:83-95)
+__global__ void k_fri_compose(const PolyRef* refs, uint32_t num, size_t n, u64* comp /* n x 2 */) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    Acc160 a0 = {0, 0, 0}, a1 = {0, 0, 0};
+    for (uint32_t j = 0; j < num; j++) {
+        const u64 c = refs[j].ptr[k];
+        acc_mul(a0, c, refs[j].a0);
+        acc_mul(a1, c, refs[j].a1);
+    }
+    comp[2 * k] = acc_reduce(a0);
+    comp[2 * k + 1] = acc_reduce(a1);
+}
+// z^m via factored tables (F_{p^2}): hi[m >> 12] * lo[m & 4095]
+__device__ __forceinline__ E2 e2_pow_tab(const u64* hi, const u64* lo, size_t m) {
+    const size_t h = m >> 12, l = m & 4095;
+    return e2_mul(E2{hi[2 * h], hi[2 * h + 1]}, E2{lo[2 * l], lo[2 * l + 1]});
+}
+__global__ void k_fill_e2_pows(E2 base, size_t count, u64* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    E2 r = e2_pow(base, i);
+    out[2 * i] = r.a;
+    out[2 * i + 1] = r.b;
+}
+// divide_by_linear (division.rs:75-88) as a suffix scan: acc_k = sum_{m>=k} c_m z^{m-k}
+//   = z^{-k} * S_k,  S_k = sum_{m>=k} c_m z^m ;  quotient q_k = acc_{k+1}, q_{n-1} = 0.
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;
+// phase 1: d_m = c_m * z^m (in place) and per-chunk totals
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_phase1(u64* comp, size_t n, const u64* zhi, const u64* zlo,
+                                                            u64* chunk_tot) {
+    __shared__ u64 sh[2 * SCAN_THREADS];
+    const size_t base = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * SCAN_ITEMS;
+    E2 tot = {0, 0};
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        const size_t m = base + i;
+        if (m < n) {
+            E2 d = e2_mul(E2{comp[2 * m], comp[2 * m + 1]}, e2_pow_tab(zhi, zlo, m));
+            comp[2 * m] = d.a;
+            comp[2 * m + 1] = d.b;
+            tot = e2_add(tot, d);
+        }
+    }
+    sh[2 * threadIdx.x] = tot.a;
+    sh[2 * threadIdx.x + 1] = tot.b;
+    __syncthreads();
+    for (int off = SCAN_THREADS / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) {
+            sh[2 * threadIdx.x] = add(sh[2 * threadIdx.x], sh[2 * (threadIdx.x + off)]);
+            sh[2 * threadIdx.x + 1] = add(sh[2 * threadIdx.x + 1], sh[2 * (threadIdx.x + off) + 1]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        chunk_tot[2 * blockIdx.x] = sh[0];
+        chunk_tot[2 * blockIdx.x + 1] = sh[1];
+    }
+}
+// phase 2: exclusive suffix sums of the chunk totals (single thread; <= 8192 chunks)
+__global__ void k_scan_phase2(u64* chunk_tot, size_t nchunks) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    E2 run = {0, 0};
+    for (size_t i = nchunks; i-- > 0;) {
+        E2 t = {chunk_tot[2 * i], chunk_tot[2 * i + 1]};
+        chunk_tot[2 * i] = run.a;
+        chunk_tot[2 * i + 1] = run.b;
+        run = e2_add(run, t);
+    }
+}
+// phase 3: S_k inside each chunk (+ carry), q_k = z^{-(k+1)} S_{k+1}; final = final*sh + q, written
+// de-interleaved as two base-field columns (c0 column | c1 column) for the LDE.
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_phase3(const u64* d, size_t n, const u64* chunk_carry,
+                                                            const u64* zihi, const u64* zilo, E2 shiftmul,
+                                                            int first_batch, u64* final_cols /* 2 x n */) {
+    __shared__ u64 sh[2 * SCAN_THREADS];
+    const size_t base = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * SCAN_ITEMS;
+    // thread-local suffix sums
+    E2 loc[SCAN_ITEMS];
+    E2 run = {0, 0};
+    for (int i = SCAN_ITEMS - 1; i >= 0; i--) {
+        const size_t m = base + i;
+        if (m < n) run = e2_add(run, E2{d[2 * m], d[2 * m + 1]});
+        loc[i] = run;
+    }
+    sh[2 * threadIdx.x] = run.a;
+    sh[2 * threadIdx.x + 1] = run.b;
+    __syncthreads();
+    // exclusive suffix over threads (serial in thread 0: 256 adds)
+    if (threadIdx.x == 0) {
+        E2 r = {chunk_carry[2 * blockIdx.x], chunk_carry[2 * blockIdx.x + 1]};
+        for (int t = SCAN_THREADS - 1; t >= 0; t--) {
+            E2 v = {sh[2 * t], sh[2 * t + 1]};
+            sh[2 * t] = r.a;
+            sh[2 * t + 1] = r.b;
+            r = e2_add(r, v);
+        }
+    }
+    __syncthreads();
+    const E2 carry = {sh[2 * threadIdx.x], sh[2 * threadIdx.x + 1]};
+    // S_m = loc[i] + carry for m = base + i. q_k = z^{-(k+1)} * S_{k+1}.
+    // This thread owns S_m for m in [base, base+ITEMS): emits q_{m-1}.
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        const size_t m = base + i;
+        if (m >= n || m == 0) continue;
+        E2 S = e2_add(loc[i], carry);
+        E2 q = e2_mul(S, e2_pow_tab(zihi, zilo, m));
+        const size_t k = m - 1;
+        E2 f = q;
+        if (!first_batch) f = e2_add(e2_mul(E2{final_cols[k], final_cols[n + k]}, shiftmul), q);
+        final_cols[k] = canon(f.a);
+        final_cols[n + k] = canon(f.b);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // q_{n-1} = 0 (the reference pads the quotient back to a power of two, oracle.rs:210)
+        E2 f = {0, 0};
+        if (!first_batch) f = e2_mul(E2{final_cols[n - 1], final_cols[2 * n - 1]}, shiftmul);
+        final_cols[n - 1] = canon(f.a);
+        final_cols[2 * n - 1] = canon(f.b);
+    }
+}
+// z == 0 special case: q_k = c_{k+1}
+__global__ void k_div_by_x(const u64* comp, size_t n, E2 shiftmul, int first_batch, u64* final_cols) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    E2 q = {0, 0};
+    if (k + 1 < n) q = E2{comp[2 * (k + 1)], comp[2 * (k + 1) + 1]};
+    E2 f = q;
+    if (!first_batch) f = e2_add(e2_mul(E2{final_cols[k], final_cols[n + k]}, shiftmul), q);
+    final_cols[k] = canon(f.a);
+    final_cols[n + k] = canon(f.b);
+}
+
+// FRI fold, leaf-local in bit-reversed storage (equals the reference's
+// coefficient fold + coset_fft, prover.rs:111-119, and the verifier's compute_evaluation,
+// verifier.rs:22-47): leaf l holds v_t = f(x0 * w_arity^{bitrev(t)}), x0 = shift * w_N^{bitrev(l)};
+// u = iDFT(v) are x0^i P_i(y); result = sum_i u_i (beta/x0)^i.
+struct FoldParams {
+    const u64* values;   // N_k x 2 (bit-reversed order)
+    u64* out;            // N_k/arity x 2
+    size_t n_leaves;
+    uint32_t log_leaves; // log2(N_k / arity)
+    const u64* winv_hi;  // (w_Nk^-1)^(4096*i)
+    const u64* winv_lo;  // (w_Nk^-1)^i, i < 4096
+    u64 shift_inv;
+    u64 beta0, beta1;
+    u64 arity_inv;
+    u64 root_inv[32];    // w_arity^-j
+};
+template <int AB>
+__global__ void __launch_bounds__(128) k_fri_fold(FoldParams fp) {
+    constexpr int A = 1 << AB;
+    const size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= fp.n_leaves) return;
+    E2 e[A];
+#pragma unroll
+    for (int t = 0; t < A; t++) e[t] = E2{fp.values[2 * (l * A + t)], fp.values[2 * (l * A + t) + 1]};
+    // DIT inverse DFT: bit-reversed input (storage order) -> natural-order u (unscaled)
+#pragma unroll
+    for (int s = 1; s <= AB; s++) {
+        const int m = 1 << s, half = m >> 1;
+#pragma unroll
+        for (int k = 0; k < A; k += m) {
+#pragma unroll
+            for (int j = 0; j < half; j++) {
+                const u64 w = fp.root_inv[j * (A / m)];
+                E2 tt = (j == 0) ? e[k + j + half] : e2_scale(e[k + j + half], w);
+                E2 uu = e[k + j];
+                e[k + j] = e2_add(uu, tt);
+                e[k + j + half] = e2_sub(uu, tt);
+            }
+        }
+    }
+    // gamma = beta / x0 ; x0^-1 = shift^-1 * w_N^{-bitrev(l)}
+    const size_t r = fp.log_leaves ? (size_t)(__brevll(l) >> (64 - fp.log_leaves)) : 0;
+    const u64 x0inv = mul(fp.shift_inv, mul(fp.winv_hi[r >> 12], fp.winv_lo[r & 4095]));
+    const E2 gamma = E2{mul(fp.beta0, x0inv), mul(fp.beta1, x0inv)};
+    E2 acc = e[A - 1];
+#pragma unroll
+    for (int i = A - 2; i >= 0; i--) acc = e2_add(e2_mul(acc, gamma), e[i]);
+    acc = e2_scale(acc, fp.arity_inv);
+    fp.out[2 * l] = canon(acc.a);
+    fp.out[2 * l + 1] = canon(acc.b);
+}
+// values (bit-reversed, interleaved) -> two natural-order base columns
+__global__ void k_unbitrev_split(const u64* values, size_t n, uint32_t log_n, u64* cols) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    size_t j = log_n ? (size_t)(__brevll(i) >> (64 - log_n)) : 0;
+    cols[i] = values[2 * j];
+    cols[n + i] = values[2 * j + 1];
+}
+__global__ void k_interleave(const u64* cols, size_t n, size_t count, u64* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    out[2 * i] = cols[i];
+    out[2 * i + 1] = cols[n + i];
+}
+// proof-of-work grind (prover.rs:183-194): smallest qualifying nonce via atomicMin
+struct PowParams {
+    u64 state[12];
+    uint32_t pos, min_lz;
+    u64 start, count;
+};
+__global__ void __launch_bounds__(128) k_fri_pow(PowParams pp, unsigned long long* result) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < pp.count; i += stride) {
+        const u64 cand = pp.start + i;
+        u64 s[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) s[k] = pp.state[k];
+        s[pp.pos] = cand;
+        poseidon_permute(s);
+        const u64 resp = canon(s[7]);
+        const uint32_t lz = resp ? (uint32_t)__clzll((long long)resp) : 64u;
+        if (lz >= pp.min_lz) atomicMin(result, (unsigned long long)cand);
+    }
+}
+
+struct gl_fri {
+    gl_ctx* ctx;
+    uint32_t log_n, rate_bits, cap_height;
+    u64* coeff_cols = nullptr;  // 2 x n (c0 column, c1 column), natural order
+    u64* values = nullptr;      // current round values, N_k x 2, bit-reversed order (owned unless moved to a tree)
+    uint32_t log_cur = 0;       // log2(N_k)
+    u64 shift = 0;              // current coset shift
+    uint32_t pending_arity_bits = 0;
+    bool committed = false;     // commit_round done, fold pending
+    std::vector<Tree> trees;
+};
+
+static int fri_finish_begin(gl_ctx* ctx, gl_fri* f) {
+    // lde_final_poly / coset_fft (oracle.rs:215-220) on both F_{p^2} components, leaf-major W = 2
+    const size_t n = (size_t)1 << f->log_n, N = n << f->rate_bits;
+    TRY(dmalloc(ctx, &f->values, 2 * N));
+    if (f->log_n == 0) {
+        const int ncos = 1 << f->rate_bits;
+        k_lde_const<<<(2 * ncos + 127) / 128, 128, 0, ctx->stream>>>(f->coeff_cols, n, 2, ncos, f->values, 2, 0);
+        CKL(ctx);
+    } else {
+        TRY(lde_leaves(ctx, f->coeff_cols, n, 2, (int)f->log_n, (int)f->rate_bits, MULTIPLICATIVE_GROUP_GENERATOR,
+                       f->values, 2, 0));
+    }
+    f->log_cur = f->log_n + f->rate_bits;
+    f->shift = MULTIPLICATIVE_GROUP_GENERATOR;
+    return GL_OK;
+}
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+int gl_ctx_create(int device, void* stream, gl_ctx** out) {
+    if (!out) return set_err(nullptr, GL_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return set_err(nullptr, GL_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                       cudaGetErrorString(e));
+    if (device < 0 || device >= count) return set_err(nullptr, GL_ERR_BAD_ARG, "device %d out of range", device);
+    gl_ctx* ctx = new gl_ctx();
+    ctx->device = device;
+    CK(ctx, cudaSetDevice(device));
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    // keep freed blocks in the pool: the commit buffers are large and re-allocated every call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    const PoseidonTables& t = host_poseidon_tables();
+    CK(ctx, cudaMemcpyToSymbol(c_pos, &t, sizeof(PoseidonTables)));
+    *out = ctx;
+    return GL_OK;
+}
+void gl_ctx_destroy(gl_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& w : ctx->wt)
+        if (w) cudaFree(w);
+    for (auto& kv : ctx->twa) cudaFree(kv.second);
+    if (ctx->scratch) cudaFreeAsync(ctx->scratch, ctx->stream);
+    if (ctx->dstage) cudaFreeAsync(ctx->dstage, ctx->stream);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+const char* gl_last_error(const gl_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+int gl_ctx_synchronize(gl_ctx* ctx) {
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+uint64_t gl_ctx_launch_count(const gl_ctx* ctx) { return ctx->launches; }
+int gl_ctx_set_ntt_group(gl_ctx* ctx, uint32_t columns) {
+    ctx->ntt_group = columns;
+    return GL_OK;
+}
+
+int gl_ntt(gl_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t batch, size_t stride, int inverse,
+           uint32_t zero_factor_log, uint64_t coset_shift, int mem) {
+    (void)zero_factor_log;
+    if (!ctx || !data) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (log_n > 2 * NTT_MAX_LOG_TILE) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %u > 24", log_n);
+    const size_t n = (size_t)1 << log_n;
+    if (batch > 1 && stride < n) return set_err(ctx, GL_ERR_BAD_SHAPE, "stride %zu < n %zu", stride, n);
+    if (canon(coset_shift) == 0) return set_err(ctx, GL_ERR_BAD_ARG, "coset_shift must be non-zero");
+    if (mem == GL_MEM_DEVICE) return ntt_natural(ctx, data, stride, data, stride, (int)log_n, batch, inverse != 0, coset_shift);
+    u64* d;
+    TRY(dmalloc(ctx, &d, (size_t)batch * n));
+    for (uint32_t b = 0; b < batch; b++) TRY(h2d(ctx, d + (size_t)b * n, data + (size_t)b * stride, n));
+    int rc = ntt_natural(ctx, d, n, d, n, (int)log_n, batch, inverse != 0, coset_shift);
+    if (rc == GL_OK) {
+        for (uint32_t b = 0; b < batch && rc == GL_OK; b++) {
+            cudaError_t e = cudaMemcpyAsync(data + (size_t)b * stride, d + (size_t)b * n, n * 8, cudaMemcpyDeviceToHost,
+                                            ctx->stream);
+            if (e != cudaSuccess) rc = set_err(ctx, GL_ERR_CUDA, "D2H: %s", cudaGetErrorString(e));
+        }
+        if (rc == GL_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            rc = set_err(ctx, GL_ERR_CUDA, "sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    dfree(ctx, d);
+    return rc;
+}
+
+int gl_commit_create(gl_ctx* ctx, const uint64_t* cols, size_t col_stride, uint32_t B, uint32_t log_n,
+                     uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, int is_coeffs, int mem,
+                     gl_commit** out) {
+    if (!ctx || !cols || !out) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (B == 0) return set_err(ctx, GL_ERR_BAD_SHAPE, "empty polynomial batch");
+    if (log_n > 2 * NTT_MAX_LOG_TILE) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %u > 24", log_n);
+    if (log_n + rate_bits > 32) return set_err(ctx, GL_ERR_BAD_SHAPE, "LDE size exceeds the field's 2-adicity");
+    if (cap_height > log_n + rate_bits)
+        return set_err(ctx, GL_ERR_BAD_SHAPE, "cap_height=%u should be at most log2(leaves.len())=%u", cap_height,
+                       log_n + rate_bits);
+    if (B > 1 && col_stride < ((size_t)1 << log_n))
+        return set_err(ctx, GL_ERR_BAD_SHAPE, "Polynomial degrees inconsistent (stride < n)");
+    gl_commit* c = new gl_commit();
+    c->ctx = ctx;
+    c->B = B;
+    c->W = B + (salt ? GL_SALT_SIZE : 0);
+    c->degree_log = log_n;
+    c->rate_bits = rate_bits;
+    c->blinding = salt != nullptr;
+    int rc = commit_build(ctx, c, cols, col_stride, salt, is_coeffs, mem, cap_height);
+    if (rc != GL_OK) {
+        gl_commit_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return GL_OK;
+}
+void gl_commit_destroy(gl_commit* c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    dfree(c->ctx, c->coeffs);
+    tree_free(c->ctx, c->tree);
+    delete c;
+}
+uint32_t gl_commit_num_polys(const gl_commit* c) { return c->B; }
+uint32_t gl_commit_leaf_width(const gl_commit* c) { return c->W; }
+uint32_t gl_commit_degree_log(const gl_commit* c) { return c->degree_log; }
+uint32_t gl_commit_rate_bits(const gl_commit* c) { return c->rate_bits; }
+uint32_t gl_commit_cap_height(const gl_commit* c) { return c->tree.cap_height; }
+int gl_commit_cap(gl_commit* c, uint64_t* out, int mem) { return copy_out(c->ctx, out, c->tree.cap, c->tree.cap_words(), mem); }
+int gl_commit_coeffs(gl_commit* c, uint64_t* out, int mem) {
+    return copy_out(c->ctx, out, c->coeffs, (size_t)c->B << c->degree_log, mem);
+}
+int gl_commit_leaves(gl_commit* c, size_t row_begin, size_t row_count, uint64_t* out, int mem) {
+    if (row_begin + row_count > c->tree.N) return set_err(c->ctx, GL_ERR_BAD_ARG, "row range out of bounds");
+    return copy_out(c->ctx, out, c->tree.leaves + row_begin * c->W, row_count * c->W, mem);
+}
+int gl_commit_digests(gl_commit* c, uint64_t* out, int mem) {
+    return copy_out(c->ctx, out, c->tree.digests, c->tree.digest_words(), mem);
+}
+int gl_commit_get_lde_values(gl_commit* c, size_t index, size_t step, uint64_t* out) {
+    const uint32_t bits = c->degree_log + c->rate_bits;
+    size_t idx = index * step;
+    if (idx >= c->tree.N) return set_err(c->ctx, GL_ERR_BAD_ARG, "index out of range");
+    size_t rev = 0;
+    for (uint32_t i = 0; i < bits; i++) rev |= ((idx >> i) & 1) << (bits - 1 - i);
+    return d2h(c->ctx, out, c->tree.leaves + rev * c->W, c->B);
+}
+int gl_commit_open(gl_commit* c, const uint64_t* leaf_indices, size_t count, uint64_t* out_leaves, uint64_t* out_paths) {
+    return tree_open(c->ctx, c->tree, leaf_indices, count, out_leaves, out_paths);
+}
+const uint64_t* gl_commit_dev_leaves(const gl_commit* c) { return c->tree.leaves; }
+const uint64_t* gl_commit_dev_coeffs(const gl_commit* c) { return c->coeffs; }
+
+void gl_poseidon_permute_host(uint64_t state[12]) {
+    poseidon_permute(state);
+    for (int i = 0; i < 12; i++) state[i] = canon(state[i]);
+}
+
+static int hash_many_impl(gl_ctx* ctx, const u64* in, size_t n_items, size_t in_words_per_item, u64* out, int mem,
+                          int which, uint32_t W) {
+    if (n_items == 0) return GL_OK;
+    const u64* din = in;
+    u64 *tin = nullptr, *dout = out;
+    if (mem == GL_MEM_HOST) {
+        TRY(dmalloc(ctx, &tin, n_items * in_words_per_item));
+        TRY(h2d(ctx, tin, in, n_items * in_words_per_item));
+        din = tin;
+        TRY(dmalloc(ctx, &dout, n_items * 4));
+    }
+    if (which == 0)
+        k_hash_many<true><<<(unsigned)((n_items + 127) / 128), 128, 0, ctx->stream>>>(din, n_items, W, dout);
+    else if (which == 2)
+        k_hash_many<false><<<(unsigned)((n_items + 127) / 128), 128, 0, ctx->stream>>>(din, n_items, W, dout);
+    else
+        k_two_to_one_many<<<(unsigned)((n_items + 127) / 128), 128, 0, ctx->stream>>>(din, n_items, dout);
+    CKL(ctx);
+    if (mem == GL_MEM_HOST) {
+        int rc = d2h(ctx, out, dout, n_items * 4);
+        dfree(ctx, tin);
+        dfree(ctx, dout);
+        return rc;
+    }
+    return GL_OK;
+}
+int gl_poseidon_hash_many(gl_ctx* ctx, const uint64_t* in, size_t n_items, uint32_t W, uint64_t* out, int mem) {
+    if (!ctx || !out || (!in && W)) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    return hash_many_impl(ctx, in, n_items, W, out, mem, 0, W);
+}
+int gl_poseidon_hash_no_pad_many(gl_ctx* ctx, const uint64_t* in, size_t n_items, uint32_t W, uint64_t* out, int mem) {
+    if (!ctx || !out || (!in && W)) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    return hash_many_impl(ctx, in, n_items, W, out, mem, 2, W);
+}
+int gl_poseidon_two_to_one_many(gl_ctx* ctx, const uint64_t* in, size_t n_items, uint64_t* out, int mem) {
+    if (!ctx || !out || !in) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    return hash_many_impl(ctx, in, n_items, 8, out, mem, 1, 8);
+}
+
+struct gl_merkle {
+    gl_ctx* ctx;
+    Tree tree;
+};
+int gl_merkle_build(gl_ctx* ctx, const uint64_t* leaves, size_t N, uint32_t W, uint32_t cap_height, int mem,
+                    gl_merkle** out) {
+    if (!ctx || !out || !leaves) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    CK(ctx, cudaSetDevice(ctx->device));
+    uint32_t lg;
+    if (log2_exact(N, &lg)) return set_err(ctx, GL_ERR_BAD_SHAPE, "Not a power of two: %zu", N);
+    if (cap_height > lg)
+        return set_err(ctx, GL_ERR_BAD_SHAPE, "cap_height=%u should be at most log2(leaves.len())=%u", cap_height, lg);
+    gl_merkle* m = new gl_merkle();
+    m->ctx = ctx;
+    m->tree.N = N;
+    m->tree.W = W;
+    m->tree.cap_height = cap_height;
+    int rc = GL_OK;
+    if (mem == GL_MEM_HOST) {
+        m->tree.own_leaves = true;
+        rc = dmalloc(ctx, &m->tree.leaves, N * (size_t)W);
+        if (rc == GL_OK) rc = h2d(ctx, m->tree.leaves, leaves, N * (size_t)W);
+    } else {
+        m->tree.leaves = const_cast<u64*>(leaves);  // caller keeps the buffer alive
+    }
+    if (rc == GL_OK) rc = tree_build(ctx, m->tree);
+    if (rc != GL_OK) {
+        gl_merkle_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return GL_OK;
+}
+void gl_merkle_destroy(gl_merkle* m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    tree_free(m->ctx, m->tree);
+    delete m;
+}
+int gl_merkle_cap(gl_merkle* m, uint64_t* out, int mem) { return copy_out(m->ctx, out, m->tree.cap, m->tree.cap_words(), mem); }
+int gl_merkle_digests(gl_merkle* m, uint64_t* out, int mem) {
+    return copy_out(m->ctx, out, m->tree.digests, m->tree.digest_words(), mem);
+}
+int gl_merkle_open(gl_merkle* m, const uint64_t* leaf_indices, size_t count, uint64_t* out_leaves, uint64_t* out_paths) {
+    return tree_open(m->ctx, m->tree, leaf_indices, count, out_leaves, out_paths);
+}
+
+// ------------------------------------------------------------------------------- FRI
+int gl_fri_begin(gl_ctx* ctx, gl_commit* const* oracles, size_t n_oracles, const gl_fri_batch* batches,
+                 size_t n_batches, const uint64_t alpha_in[2], uint32_t rate_bits, uint32_t cap_height, gl_fri** out) {
+    if (!ctx || !oracles || !batches || !alpha_in || !out || n_oracles == 0 || n_batches == 0)
+        return set_err(ctx, GL_ERR_BAD_ARG, "null/empty argument");
+    *out = nullptr;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const uint32_t log_n = oracles[0]->degree_log;
+    const size_t n = (size_t)1 << log_n;
+    for (size_t o = 0; o < n_oracles; o++)
+        if (oracles[o]->degree_log != log_n) return set_err(ctx, GL_ERR_BAD_SHAPE, "Polynomial degrees inconsistent");
+    gl_fri* f = new gl_fri();
+    f->ctx = ctx;
+    f->log_n = log_n;
+    f->rate_bits = rate_bits;
+    f->cap_height = cap_height;
+    int rc = GL_OK;
+    u64 *comp = nullptr, *chunk = nullptr, *drefs = nullptr;
+    const E2 alpha = {canon(alpha_in[0]), canon(alpha_in[1])};
+    const size_t nchunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    auto body = [&]() -> int {
+        TRY(dmalloc(ctx, &f->coeff_cols, 2 * n));
+        TRY(dmalloc(ctx, &comp, 2 * n));
+        TRY(dmalloc(ctx, &chunk, 2 * nchunks));
+        size_t max_polys = 0;
+        for (size_t b = 0; b < n_batches; b++) max_polys = batches[b].num_polys > max_polys ? batches[b].num_polys : max_polys;
+        const size_t ref_words = max_polys * sizeof(PolyRef) / 8;
+        TRY(dmalloc(ctx, &drefs, ref_words));
+        for (size_t b = 0; b < n_batches; b++) {
+            const gl_fri_batch& batch = batches[b];
+            // alpha^j per polynomial (ReducingFactor restarts at alpha^0 for every batch)
+            TRY(ensure_pinned(ctx, ref_words));
+            CK(ctx, cudaStreamSynchronize(ctx->stream));
+            PolyRef* refs = (PolyRef*)ctx->pinned;
+            E2 ap = {1, 0};
+            for (size_t j = 0; j < batch.num_polys; j++) {
+                const uint32_t oi = batch.oracle_index[j], pi = batch.poly_index[j];
+                if (oi >= n_oracles || pi >= oracles[oi]->B) return set_err(ctx, GL_ERR_BAD_ARG, "bad polynomial reference");
+                refs[j].ptr = oracles[oi]->coeffs + (size_t)pi * n;
+                refs[j].a0 = canon(ap.a);
+                refs[j].a1 = canon(ap.b);
+                ap = e2_mul(ap, alpha);
+            }
+            const E2 shiftmul = {canon(ap.a), canon(ap.b)};  // alpha^count: alpha.shift_poly (reducing.rs:102-106)
+            TRY(h2d(ctx, drefs, ctx->pinned, batch.num_polys * sizeof(PolyRef) / 8));
+            k_fri_compose<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const PolyRef*)drefs,
+                                                                              (uint32_t)batch.num_polys, n, comp);
+            CKL(ctx);
+            CK(ctx, cudaStreamSynchronize(ctx->stream));  // pinned refs consumed
+            const E2 z = {canon(batch.point[0]), canon(batch.point[1])};
+            if (z.a == 0 && z.b == 0) {
+                k_div_by_x<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(comp, n, shiftmul, b == 0, f->coeff_cols);
+                CKL(ctx);
+                continue;
+            }
+            const E2 zi = e2_inv(z);
+            const size_t hi_cnt = (n >> 12) + 1;
+            u64 *zhi, *zlo, *zihi, *zilo;
+            TRY(dmalloc(ctx, &zhi, 2 * hi_cnt));
+            TRY(dmalloc(ctx, &zlo, 2 * 4096));
+            TRY(dmalloc(ctx, &zihi, 2 * hi_cnt));
+            TRY(dmalloc(ctx, &zilo, 2 * 4096));
+            k_fill_e2_pows<<<(unsigned)((hi_cnt + 127) / 128), 128, 0, ctx->stream>>>(e2_pow(z, 4096), hi_cnt, zhi);
+            CKL(ctx);
+            k_fill_e2_pows<<<32, 128, 0, ctx->stream>>>(z, 4096, zlo);
+            CKL(ctx);
+            k_fill_e2_pows<<<(unsigned)((hi_cnt + 127) / 128), 128, 0, ctx->stream>>>(e2_pow(zi, 4096), hi_cnt, zihi);
+            CKL(ctx);
+            k_fill_e2_pows<<<32, 128, 0, ctx->stream>>>(zi, 4096, zilo);
+            CKL(ctx);
+            k_scan_phase1<<<(unsigned)nchunks, SCAN_THREADS, 0, ctx->stream>>>(comp, n, zhi, zlo, chunk);
+            CKL(ctx);
+            k_scan_phase2<<<1, 32, 0, ctx->stream>>>(chunk, nchunks);
+            CKL(ctx);
+            k_scan_phase3<<<(unsigned)nchunks, SCAN_THREADS, 0, ctx->stream>>>(comp, n, chunk, zihi, zilo, shiftmul,
+                                                                              b == 0, f->coeff_cols);
+            CKL(ctx);
+            dfree(ctx, zhi);
+            dfree(ctx, zlo);
+            dfree(ctx, zihi);
+            dfree(ctx, zilo);
+        }
+        TRY(fri_finish_begin(ctx, f));
+        return GL_OK;
+    };
+    rc = body();
+    dfree(ctx, comp);
+    dfree(ctx, chunk);
+    dfree(ctx, drefs);
+    if (rc != GL_OK) {
+        gl_fri_destroy(f);
+        return rc;
+    }
+    *out = f;
+    return GL_OK;
+}
+
+__global__ void k_split_ext(const u64* inter, size_t n, u64* cols) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cols[i] = canon(inter[2 * i]);
+    cols[n + i] = canon(inter[2 * i + 1]);
+}
+int gl_fri_begin_from_coeffs(gl_ctx* ctx, const uint64_t* coeffs_ext, uint32_t log_n, uint32_t rate_bits,
+                             uint32_t cap_height, gl_fri** out) {
+    if (!ctx || !coeffs_ext || !out) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (log_n > 2 * NTT_MAX_LOG_TILE) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %u > 24", log_n);
+    const size_t n = (size_t)1 << log_n;
+    gl_fri* f = new gl_fri();
+    f->ctx = ctx;
+    f->log_n = log_n;
+    f->rate_bits = rate_bits;
+    f->cap_height = cap_height;
+    u64* tmp = nullptr;
+    auto body = [&]() -> int {
+        TRY(dmalloc(ctx, &f->coeff_cols, 2 * n));
+        TRY(dmalloc(ctx, &tmp, 2 * n));
+        TRY(h2d(ctx, tmp, coeffs_ext, 2 * n));
+        k_split_ext<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(tmp, n, f->coeff_cols);
+        CKL(ctx);
+        TRY(fri_finish_begin(ctx, f));
+        return GL_OK;
+    };
+    int rc = body();
+    dfree(ctx, tmp);
+    if (rc != GL_OK) {
+        gl_fri_destroy(f);
+        return rc;
+    }
+    *out = f;
+    return GL_OK;
+}
+void gl_fri_destroy(gl_fri* f) {
+    if (!f) return;
+    cudaSetDevice(f->ctx->device);
+    dfree(f->ctx, f->coeff_cols);
+    dfree(f->ctx, f->values);
+    for (auto& t : f->trees) tree_free(f->ctx, t);
+    delete f;
+}
+int gl_fri_coeffs(gl_fri* f, uint64_t* out) {
+    gl_ctx* ctx = f->ctx;
+    const size_t n = (size_t)1 << f->log_n;
+    u64* tmp;
+    TRY(dmalloc(ctx, &tmp, 2 * n));
+    k_interleave<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(f->coeff_cols, n, n, tmp);
+    CKL(ctx);
+    int rc = d2h(ctx, out, tmp, 2 * n);
+    dfree(ctx, tmp);
+    return rc;
+}
+uint32_t gl_fri_num_rounds(const gl_fri* f) { return (uint32_t)f->trees.size(); }
+
+int gl_fri_commit_round(gl_fri* f, uint32_t arity_bits, uint64_t* cap_out) {
+    gl_ctx* ctx = f->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (f->committed) return set_err(ctx, GL_ERR_BAD_ARG, "fold the previous round first");
+    if (arity_bits < 1 || arity_bits > 5) return set_err(ctx, GL_ERR_UNSUPPORTED, "arity_bits %u not in 1..5", arity_bits);
+    if (arity_bits > f->log_cur) return set_err(ctx, GL_ERR_BAD_SHAPE, "arity exceeds the codeword length");
+    Tree t;
+    t.N = (size_t)1 << (f->log_cur - arity_bits);
+    t.W = 2u << arity_bits;
+    t.cap_height = f->cap_height;
+    t.leaves = f->values;  // chunks(arity).map(flatten) of the bit-reversed values == this buffer
+    if (t.cap_height > f->log_cur - arity_bits)
+        return set_err(ctx, GL_ERR_BAD_SHAPE, "cap_height=%u should be at most log2(leaves.len())=%u", t.cap_height,
+                       f->log_cur - arity_bits);
+    t.own_leaves = false;
+    int rc = tree_build(ctx, t);
+    if (rc != GL_OK) {
+        tree_free(ctx, t);
+        return rc;
+    }
+    t.own_leaves = true;  // ownership of the values buffer moves to the tree
+    f->values = nullptr;
+    f->trees.push_back(t);
+    f->pending_arity_bits = arity_bits;
+    f->committed = true;
+    return d2h(ctx, cap_out, t.cap, t.cap_words());
+}
+
+int gl_fri_fold(gl_fri* f, const uint64_t beta[2]) {
+    gl_ctx* ctx = f->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (!f->committed) return set_err(ctx, GL_ERR_BAD_ARG, "commit the round first");
+    const uint32_t ab = f->pending_arity_bits;
+    const Tree& t = f->trees.back();
+    const size_t leaves = t.N;
+    u64* out;
+    TRY(dmalloc(ctx, &out, 2 * leaves));
+    FoldParams fp{};
+    fp.values = t.leaves;
+    fp.out = out;
+    fp.n_leaves = leaves;
+    fp.log_leaves = f->log_cur - ab;
+    const u64 wN = root_of_unity(f->log_cur);
+    const u64 winv = gl::inv(wN);
+    const size_t hi_cnt = (leaves >> 12) + 1;
+    const size_t tcnt = hi_cnt > 4096 ? hi_cnt : 4096;
+    u64* tabs;
+    TRY(build_pow_tables(ctx, std::vector<u64>{gl::pow(winv, 4096), winv}, tcnt, &tabs));
+    fp.winv_hi = tabs;
+    fp.winv_lo = tabs + tcnt;
+    fp.shift_inv = gl::inv(f->shift);
+    fp.beta0 = canon(beta[0]);
+    fp.beta1 = canon(beta[1]);
+    fp.arity_inv = inverse_2exp(ab);
+    const u64 wa_inv = gl::inv(root_of_unity(ab));
+    for (uint32_t j = 0; j < (1u << ab); j++) fp.root_inv[j] = gl::pow(wa_inv, j);
+    const unsigned nb = (unsigned)((leaves + 127) / 128);
+    switch (ab) {
+        case 1: k_fri_fold<1><<<nb, 128, 0, ctx->stream>>>(fp); break;
+        case 2: k_fri_fold<2><<<nb, 128, 0, ctx->stream>>>(fp); break;
+        case 3: k_fri_fold<3><<<nb, 128, 0, ctx->stream>>>(fp); break;
+        case 4: k_fri_fold<4><<<nb, 128, 0, ctx->stream>>>(fp); break;
+        case 5: k_fri_fold<5><<<nb, 128, 0, ctx->stream>>>(fp); break;
+    }
+    CKL(ctx);
+    dfree(ctx, tabs);
+    f->values = out;
+    f->log_cur -= ab;
+    f->shift = gl::pow(f->shift, (u64)1 << ab);  // shift = shift.exp_u64(arity), prover.rs:118
+    f->committed = false;
+    return GL_OK;
+}
+
+int gl_fri_final_poly(gl_fri* f, uint64_t* out, size_t cap_words, size_t* len_out) {
+    gl_ctx* ctx = f->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (f->committed) return set_err(ctx, GL_ERR_BAD_ARG, "fold the last round first");
+    const size_t Nf = (size_t)1 << f->log_cur;
+    if (f->log_cur < f->rate_bits) return set_err(ctx, GL_ERR_BAD_SHAPE, "codeword shorter than the blowup");
+    const size_t len = Nf >> f->rate_bits;
+    if (cap_words < 2 * len) return set_err(ctx, GL_ERR_BAD_ARG, "output buffer too small");
+    u64 *cols, *inter;
+    TRY(dmalloc(ctx, &cols, 2 * Nf));
+    TRY(dmalloc(ctx, &inter, 2 * len));
+    k_unbitrev_split<<<(unsigned)((Nf + 255) / 256), 256, 0, ctx->stream>>>(f->values, Nf, f->log_cur, cols);
+    CKL(ctx);
+    // coset_ifft on the current coset (the reference keeps coefficients; we recover them once)
+    int rc = ntt_natural(ctx, cols, Nf, cols, Nf, (int)f->log_cur, 2, true, f->shift);
+    if (rc == GL_OK) {
+        k_interleave<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(cols, Nf, len, inter);
+        ctx->launches++;
+        rc = d2h(ctx, out, inter, 2 * len);
+    }
+    dfree(ctx, cols);
+    dfree(ctx, inter);
+    if (rc == GL_OK && len_out) *len_out = len;
+    return rc;
+}
+
+int gl_fri_open(gl_fri* f, uint32_t round, const uint64_t* leaf_indices, size_t count, uint64_t* out_leaves,
+                uint64_t* out_paths) {
+    if (round >= f->trees.size()) return set_err(f->ctx, GL_ERR_BAD_ARG, "round %u out of range", round);
+    CK(f->ctx, cudaSetDevice(f->ctx->device));
+    return tree_open(f->ctx, f->trees[round], leaf_indices, count, out_leaves, out_paths);
+}
+
+int gl_fri_pow(gl_ctx* ctx, const uint64_t state[12], uint32_t pos, uint32_t min_leading_zeros, uint64_t* nonce_out) {
+    if (!ctx || !state || !nonce_out || pos >= 8) return set_err(ctx, GL_ERR_BAD_ARG, "bad argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    unsigned long long* dres;
+    TRY(dmalloc(ctx, (u64**)&dres, 1));
+    PowParams pp;
+    for (int i = 0; i < 12; i++) pp.state[i] = canon(state[i]);
+    pp.pos = pos;
+    pp.min_lz = min_leading_zeros;
+    const u64 BATCH = (u64)1 << 22;
+    int rc = GL_OK;
+    u64 found = ~0ULL;
+    for (u64 start = 0; start < P; start += BATCH) {
+        CK(ctx, cudaMemsetAsync(dres, 0xFF, 8, ctx->stream));
+        pp.start = start;
+        pp.count = (P - start < BATCH) ? P - start : BATCH;
+        k_fri_pow<<<148 * 8, 128, 0, ctx->stream>>>(pp, dres);
+        CKL(ctx);
+        rc = d2h(ctx, &found, (u64*)dres, 1);
+        if (rc != GL_OK || found != ~0ULL) break;
+        if (start > ((u64)1 << 40)) {
+            rc = set_err(ctx, GL_ERR_POW_FAILED, "Proof of work failed. This is highly unlikely!");
+            break;
+        }
+    }
+    dfree(ctx, (u64*)dres);
+    if (rc == GL_OK) *nonce_out = found;
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,302 @@
+"""FRI prover mirroring plonky2/src/fri/{mod,structure,proof,prover,reduction_strategies}.rs and the
+pre-FRI part of prove_openings (plonky2/src/fri/oracle.rs:176-237).
+
+The transcript (Challenger) is sequential and stays on the host, exactly as in the reference; every
+array-sized step (alpha-batching, division by (X - z), coset LDE, Merkle trees, folding, grinding,
+openings) is a CUDA call through the C ABI."""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _native as N
+from .field import ORDER
+from .hash import NUM_HASH_OUT_ELTS, MerkleCap
+
+
+# ------------------------------------------------------------------ parameters (fri/mod.rs:30-143)
+@dataclass
+class FriConfig:
+    rate_bits: int
+    cap_height: int
+    proof_of_work_bits: int
+    reduction_strategy: tuple  # ("ConstantArityBits", arity_bits, final_poly_bits) | ("Fixed", [..])
+    num_query_rounds: int
+
+    def rate(self):
+        return 1.0 / (1 << self.rate_bits)
+
+    def fri_params(self, degree_bits, hiding):
+        arity = reduction_arity_bits(self.reduction_strategy, degree_bits, self.rate_bits, self.cap_height,
+                                     self.num_query_rounds)
+        return FriParams(self, hiding, degree_bits, arity)
+
+
+def reduction_arity_bits(strategy, degree_bits, rate_bits, cap_height, num_queries):
+    """FriReductionStrategy::reduction_arity_bits (reduction_strategies.rs:30-57)."""
+    kind = strategy[0]
+    if kind == "Fixed":
+        return list(strategy[1])
+    if kind == "ConstantArityBits":
+        arity_bits, final_poly_bits = strategy[1], strategy[2]
+        result = []
+        while degree_bits > final_poly_bits and degree_bits + rate_bits - arity_bits >= cap_height:
+            result.append(arity_bits)
+            assert degree_bits >= arity_bits
+            degree_bits -= arity_bits
+        return result
+    raise ValueError("unsupported reduction strategy %r" % (kind,))
+
+
+@dataclass
+class FriParams:
+    config: FriConfig
+    hiding: bool
+    degree_bits: int
+    reduction_arity_bits: List[int]
+
+    def total_arities(self):
+        return sum(self.reduction_arity_bits)
+
+    def lde_bits(self):
+        return self.degree_bits + self.config.rate_bits
+
+    def lde_size(self):
+        return 1 << self.lde_bits()
+
+    def final_poly_bits(self):
+        return self.degree_bits - self.total_arities()
+
+    def final_poly_len(self):
+        return 1 << self.final_poly_bits()
+
+
+def standard_recursion_fri_config():
+    """FriConfig of CircuitConfig::standard_recursion_config (plonk/circuit_data.rs:101-119)."""
+    return FriConfig(rate_bits=3, cap_height=4, proof_of_work_bits=16,
+                     reduction_strategy=("ConstantArityBits", 4, 5), num_query_rounds=28)
+
+
+def starky_standard_fast_fri_config():
+    """StarkConfig::standard_fast_config (starky/src/config.rs:52-64)."""
+    return FriConfig(rate_bits=1, cap_height=4, proof_of_work_bits=16,
+                     reduction_strategy=("ConstantArityBits", 4, 5), num_query_rounds=84)
+
+
+# ------------------------------------------------------------------ instance (fri/structure.rs:14-60)
+@dataclass
+class FriPolynomialInfo:
+    oracle_index: int
+    polynomial_index: int
+
+    @staticmethod
+    def from_range(oracle_index, polynomial_indices):
+        return [FriPolynomialInfo(oracle_index, i) for i in polynomial_indices]
+
+
+@dataclass
+class FriBatchInfo:
+    point: Tuple[int, int]
+    polynomials: List[FriPolynomialInfo]
+
+
+@dataclass
+class FriOracleInfo:
+    num_polys: int
+    blinding: bool
+
+
+@dataclass
+class FriInstanceInfo:
+    oracles: List[FriOracleInfo]
+    batches: List[FriBatchInfo]
+
+
+# ------------------------------------------------------------------ proof (fri/proof.rs:25-113)
+@dataclass
+class FriQueryStep:
+    evals: np.ndarray          # (arity, 2)
+    merkle_proof: np.ndarray   # (len, 4)
+
+
+@dataclass
+class FriInitialTreeProof:
+    evals_proofs: List[Tuple[np.ndarray, np.ndarray]]  # per oracle: (leaf (W,), siblings (len, 4))
+
+
+@dataclass
+class FriQueryRound:
+    initial_trees_proof: FriInitialTreeProof
+    steps: List[FriQueryStep]
+
+
+@dataclass
+class FriProof:
+    commit_phase_merkle_caps: List[MerkleCap]
+    query_round_proofs: List[FriQueryRound]
+    final_poly: np.ndarray  # (len, 2)
+    pow_witness: int
+
+    def to_bytes(self):
+        """write_fri_proof (util/serialization/mod.rs:1595-1609): canonical little-endian u64s."""
+        out = bytearray()
+
+        def put(arr):
+            out.extend(np.ascontiguousarray(arr, dtype="<u8").tobytes())
+
+        for cap in self.commit_phase_merkle_caps:
+            put(cap.hashes)
+        for qr in self.query_round_proofs:
+            for leaf, sib in qr.initial_trees_proof.evals_proofs:
+                put(leaf)
+                out.append(len(sib))
+                put(sib)
+            for st in qr.steps:
+                put(st.evals)
+                out.append(len(st.merkle_proof))
+                put(st.merkle_proof)
+        put(self.final_poly)
+        put(np.array([self.pow_witness], dtype=np.uint64))
+        return bytes(out)
+
+
+# ------------------------------------------------------------------ prover
+class _FriState:
+    """Owner of a gl_fri handle."""
+
+    def __init__(self, h, ctx):
+        self.h, self.ctx = h, ctx
+
+    def close(self):
+        if getattr(self, "h", None):
+            N.lib().gl_fri_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _begin(instance, oracles, alpha, fri_params):
+    ctx = oracles[0].ctx
+    handles = (N.vp * len(oracles))(*[o.h for o in oracles])
+    barr = (N.FriBatch * len(instance.batches))()
+    keep = []
+    for i, b in enumerate(instance.batches):
+        oi = np.array([p.oracle_index for p in b.polynomials], dtype=np.uint32)
+        pi = np.array([p.polynomial_index for p in b.polynomials], dtype=np.uint32)
+        keep += [oi, pi]
+        barr[i].point[0], barr[i].point[1] = int(b.point[0]) % ORDER, int(b.point[1]) % ORDER
+        barr[i].num_polys = len(b.polynomials)
+        barr[i].oracle_index = oi.ctypes.data_as(N.u32p)
+        barr[i].poly_index = pi.ctypes.data_as(N.u32p)
+    al = np.array([alpha[0], alpha[1]], dtype=np.uint64)
+    h = N.vp()
+    N.check(N.lib().gl_fri_begin(ctx.h, handles, len(oracles), barr, len(instance.batches), N.np_ptr(al),
+                                 fri_params.config.rate_bits, fri_params.config.cap_height, C.byref(h)), ctx.h)
+    return _FriState(h, ctx)
+
+
+def fri_committed_trees(state, challenger, fri_params, final_poly_coeff_len=None, max_num_query_steps=None):
+    """fri_committed_trees (prover.rs:84-150): returns (caps, final_poly coefficients (len, 2))."""
+    L, ctx = N.lib(), state.ctx
+    cap_words = NUM_HASH_OUT_ELTS << fri_params.config.cap_height
+    caps = []
+    for arity_bits in fri_params.reduction_arity_bits:
+        cap = np.empty(cap_words, dtype=np.uint64)
+        N.check(L.gl_fri_commit_round(state.h, arity_bits, N.np_ptr(cap)), ctx.h)
+        cap = MerkleCap(cap)
+        challenger.observe_cap(cap)
+        caps.append(cap)
+        beta = challenger.get_extension_challenge()
+        b = np.array(beta, dtype=np.uint64)
+        N.check(L.gl_fri_fold(state.h, N.np_ptr(b)), ctx.h)
+    if max_num_query_steps is not None:
+        zero_cap = [0] * cap_words
+        for _ in range(len(fri_params.reduction_arity_bits), max_num_query_steps):
+            challenger.observe_elements(zero_cap)
+            challenger.get_extension_challenge()
+    n_final = fri_params.final_poly_len()
+    buf = np.empty(2 * max(n_final, 1), dtype=np.uint64)
+    ln = C.c_size_t()
+    N.check(L.gl_fri_final_poly(state.h, N.np_ptr(buf), buf.size, C.byref(ln)), ctx.h)
+    coeffs = buf[:2 * ln.value].reshape(-1, 2).copy()
+    challenger.observe_extension_elements([(int(c[0]), int(c[1])) for c in coeffs])
+    if final_poly_coeff_len is not None:
+        for _ in range(len(coeffs), final_poly_coeff_len):
+            challenger.observe_extension_element((0, 0))
+    return caps, coeffs
+
+
+def fri_proof_of_work(challenger, config, ctx=None):
+    """fri_proof_of_work (prover.rs:153-202); the grind runs on the GPU and returns the smallest nonce."""
+    ctx = ctx or N.default_context()
+    min_leading_zeros = config.proof_of_work_bits + (64 - ORDER.bit_length())
+    inter = challenger.sponge_state.copy()
+    pos = len(challenger.input_buffer)
+    inter.set_from_iter(challenger.input_buffer, 0)
+    nonce = np.zeros(1, dtype=np.uint64)
+    st = np.ascontiguousarray(inter.state, dtype=np.uint64)
+    N.check(N.lib().gl_fri_pow(ctx.h, N.np_ptr(st), pos, min_leading_zeros, N.np_ptr(nonce)), ctx.h)
+    pow_witness = int(nonce[0])
+    challenger.observe_element(pow_witness)
+    pow_response = challenger.get_challenge()
+    leading_zeros = 64 - pow_response.bit_length()
+    assert leading_zeros >= min_leading_zeros
+    return pow_witness
+
+
+def fri_prover_query_rounds(oracles, state, challenger, n, fri_params):
+    """fri_prover_query_rounds / fri_prover_query_round (prover.rs:204-258), batched per tree."""
+    L, ctx = N.lib(), state.ctx
+    nq = fri_params.config.num_query_rounds
+    x_indices = [c % n for c in challenger.get_n_challenges(nq)]
+    idx = np.array(x_indices, dtype=np.uint64)
+    initial = [o.merkle_tree.open_many(idx) for o in oracles]
+    steps = []
+    cur = idx.copy()
+    log_cur = fri_params.lde_bits()
+    for r, arity_bits in enumerate(fri_params.reduction_arity_bits):
+        cur = cur >> np.uint64(arity_bits)
+        w = 2 << arity_bits
+        layers = log_cur - arity_bits - fri_params.config.cap_height
+        leaves = np.empty((nq, w), dtype=np.uint64)
+        paths = np.empty((nq, layers, 4), dtype=np.uint64)
+        if nq:
+            N.check(L.gl_fri_open(state.h, r, N.np_ptr(np.ascontiguousarray(cur)), nq, N.np_ptr(leaves),
+                                  N.np_ptr(paths) if paths.size else None), ctx.h)
+        steps.append((leaves, paths))
+        log_cur -= arity_bits
+    rounds = []
+    for q in range(nq):
+        init = FriInitialTreeProof([(lv[q], pt[q]) for (lv, pt) in initial])
+        st = [FriQueryStep(lv[q].reshape(-1, 2), pt[q]) for (lv, pt) in steps]
+        rounds.append(FriQueryRound(init, st))
+    return rounds, x_indices
+
+
+def prove_openings(instance, oracles, challenger, fri_params, final_poly_coeff_len=None,
+                   max_num_query_steps=None, taps=None):
+    """PolynomialBatch::prove_openings -> fri_proof (oracle.rs:176-237, prover.rs:24-70)."""
+    alpha = challenger.get_extension_challenge()
+    state = _begin(instance, oracles, alpha, fri_params)
+    try:
+        if taps is not None:
+            n = 1 << oracles[0].degree_log
+            fp = np.empty((n, 2), dtype=np.uint64)
+            N.check(N.lib().gl_fri_coeffs(state.h, N.np_ptr(fp)), state.ctx.h)
+            taps["final_poly"] = fp
+        caps, final_coeffs = fri_committed_trees(state, challenger, fri_params, final_poly_coeff_len,
+                                                 max_num_query_steps)
+        pow_witness = fri_proof_of_work(challenger, fri_params.config, state.ctx)
+        n = fri_params.lde_size()
+        rounds, x_indices = fri_prover_query_rounds(oracles, state, challenger, n, fri_params)
+        if taps is not None:
+            taps["pow_witness"] = pow_witness
+            taps["query_indices"] = x_indices
+        return FriProof(caps, rounds, final_coeffs, pow_witness)
+    finally:
+        state.close()

@@ -1,0 +1,340 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): every call goes through the C ABI
+(libplonky2_b200.so) and is compared bit-for-bit with the CPU oracle on the same seeded inputs,
+plus size-independent properties at larger sizes. /root/reference is never read here."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import EDGE, P, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import plonky2_b200 as p
+
+    p.default_context()  # fails loudly if the CUDA extension is missing
+    return p
+
+
+# ----------------------------------------------------------------------------- NTT
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 4, 5, 7, 8, 10, 12, 13, 14, 16])
+def test_fft_ifft_match_oracle(pb, oracle, log_n):
+    n = 1 << log_n
+    x = synth(0x01 + log_n, (3, n), canonical=False)
+    got = pb.fft(x)
+    for b in range(3):
+        assert np.array_equal(got[b], oracle.fft(x[b])), (log_n, b)
+    goti = pb.ifft(x)
+    for b in range(3):
+        assert np.array_equal(goti[b], oracle.ifft(x[b]))
+    assert np.array_equal(pb.ifft(got), x % np.uint64(P))  # round trip returns the (canonical) input
+
+
+def test_fft_reference_test_vector(pb, oracle):
+    # field/src/fft.rs:215-249: deterministic i*1337 % 100, degree 200 padded to 256, zero_factor 0..3
+    coeffs = np.array([(i * 1337) % 100 for i in range(200)] + [0] * 56, dtype=np.uint64)
+    pts = pb.fft(coeffs)
+    assert np.array_equal(pts, oracle.naive_coset_eval(coeffs, 1))
+    assert np.array_equal(pb.ifft(pts), coeffs)
+    for r in range(4):
+        ext = pb.lde(coeffs, r)
+        assert np.array_equal(pb.fft_with_options(ext, zero_factor=r), pb.fft(ext))
+        assert np.array_equal(pb.fft(ext), oracle.fft(ext))
+
+
+def test_edge_values_and_single_column(pb, oracle):
+    x = np.array((EDGE * 6)[:64], dtype=np.uint64)
+    assert np.array_equal(pb.fft(x), oracle.fft(x))
+    assert np.array_equal(pb.ifft(x), oracle.ifft(x))
+
+
+@pytest.mark.parametrize("log_n", [1, 4, 9, 13])
+def test_coset_fft_and_ifft(pb, oracle, log_n):
+    n = 1 << log_n
+    x = synth(0x21 + log_n, (2, n))
+    shift = int(synth(0x22, (1,))[0]) | 1
+    got = pb.coset_fft(x, shift)
+    for b in range(2):
+        assert np.array_equal(got[b], oracle.coset_fft(x[b], shift))
+    back = pb.coset_ifft(got, shift)
+    assert np.array_equal(back, x)
+    for b in range(2):
+        assert np.array_equal(pb.coset_ifft(x, shift)[b], oracle.coset_ifft(x[b], shift))
+
+
+def test_cfg1_2pow16_roundtrip(pb, oracle):
+    # BASELINE.json configs[0]: 2^16-point forward + inverse NTT, single column, bit-exact vs CPU reference
+    x = synth(0x01, (1 << 16,))
+    y = pb.fft(x)
+    assert np.array_equal(y, oracle.fft(x))
+    assert np.array_equal(pb.ifft(y), x)
+    assert np.array_equal(pb.ifft(x), oracle.ifft(x))
+
+
+def test_ntt_linearity_large(pb):
+    # size-independent property at 2^20 x 4 columns: NTT(a + c*b) = NTT(a) + c*NTT(b)
+    n = 1 << 20
+    a, b = synth(0x31, (2, n)), synth(0x32, (2, n))
+    c = 0x1234567
+    P_ = int(P)
+    comb = ((a.astype(object) + c * b.astype(object)) % P_).astype(np.uint64)
+    fa, fb, fc = pb.fft(a), pb.fft(b), pb.fft(comb)
+    want = ((fa.astype(object) + c * fb.astype(object)) % P_).astype(np.uint64)
+    assert np.array_equal(fc, want)
+    assert np.array_equal(pb.ifft(fa), a)
+
+
+def test_ntt_shape_errors(pb):
+    with pytest.raises(ValueError):
+        pb.fft(np.zeros(12, dtype=np.uint64))
+
+
+# ----------------------------------------------------------------------------- Poseidon / Merkle
+def test_poseidon_kats_on_device(pb):
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "poseidon_kat.json")))
+    for v in kat["vectors"]:
+        inp = np.array([int(x) for x in v["input"]], dtype=np.uint64)
+        exp = [int(x) for x in v["output"]]
+        # hash_no_pad over 8 + 4 lanes exposes lanes 0..3 only; use two_to_one/compress + sponge identities
+        # and check the full state through the sponge: absorb 8 lanes with capacity lanes = 0 is not the KAT
+        # input in general, so check the device permutation through the PoW kernel's sibling: hash_many on a
+        # 12-word leaf equals permute(permute([x0..x7,0,0,0,0]) overwritten by x8..x11).
+        got = pb.PoseidonHash.hash_no_pad(inp)
+        st = np.zeros(12, dtype=np.uint64)
+        st[:8] = inp[:8]
+        pb._native.lib().gl_poseidon_permute_host(pb._native.np_ptr(st))
+        st[:4] = inp[8:]
+        pb._native.lib().gl_poseidon_permute_host(pb._native.np_ptr(st))
+        assert got.tolist() == st[:4].tolist()
+        # the all-zero KAT is directly visible: compress(0, 0) = permute(0)[0..4]
+        if not any(int(x) for x in v["input"]):
+            z = np.zeros(4, dtype=np.uint64)
+            assert pb.PoseidonHash.two_to_one(z, z).tolist() == exp[:4]
+
+
+@pytest.mark.parametrize("W", [0, 1, 3, 4, 5, 7, 8, 9, 12, 16, 17, 33, 135])
+def test_hash_many_matches_oracle(pb, oracle, W):
+    rows = synth(0x41 + W, (257, W), canonical=False) if W else np.zeros((5, 0), dtype=np.uint64)
+    got = pb.PoseidonHash.hash_many(rows)
+    want = oracle.hash_many(rows) if W else np.zeros((5, 4), dtype=np.uint64)
+    assert np.array_equal(got, want)
+    if W:
+        g2 = pb.PoseidonHash.hash_no_pad_many(rows[:9])
+        for i in range(9):
+            assert np.array_equal(g2[i], oracle.hash_no_pad(rows[i]))
+
+
+def test_hash_extreme_inputs(pb, oracle):
+    rows = np.array([(EDGE * 3)[i:i + 12] for i in range(12)], dtype=np.uint64)
+    assert np.array_equal(pb.PoseidonHash.hash_many(rows), oracle.hash_many(rows))
+    rows = np.full((4, 20), 2**64 - 1, dtype=np.uint64)
+    assert np.array_equal(pb.PoseidonHash.hash_many(rows), oracle.hash_many(rows))
+
+
+def test_two_to_one(pb, oracle):
+    pairs = synth(0x51, (100, 8), canonical=False)
+    got = pb.PoseidonHash.two_to_one_many(pairs)
+    for i in range(100):
+        assert np.array_equal(got[i], oracle.two_to_one(pairs[i, :4], pairs[i, 4:]))
+
+
+@pytest.mark.parametrize("log_n,W,cap_height", [(8, 7, 0), (8, 7, 1), (8, 7, 8), (0, 5, 0), (3, 2, 3),
+                                                (10, 12, 4), (11, 135, 4), (6, 4, 2), (12, 32, 4)])
+def test_merkle_tree_matches_oracle(pb, oracle, log_n, W, cap_height):
+    N = 1 << log_n
+    leaves = synth(0x61 + log_n, (N, W))
+    t = pb.MerkleTree(leaves, cap_height)
+    d, cap = oracle.merkle_build(leaves, cap_height)
+    assert np.array_equal(t.cap.hashes, cap)
+    assert np.array_equal(t.digests, d)
+    idx = sorted(set([0, N - 1, N // 2, N // 3]))
+    lv, paths = t.open_many(idx)
+    for k, i in enumerate(idx):
+        assert np.array_equal(lv[k], leaves[i])
+        assert np.array_equal(paths[k], oracle.merkle_prove(i, N, cap_height, d))
+        assert oracle.merkle_verify(lv[k], i, paths[k], cap, cap_height)
+
+
+def test_merkle_every_leaf_proof_verifies(pb, oracle):
+    # merkle_tree.rs:269-311 (random 256 x 7 leaves, every proof against the cap)
+    leaves = synth(0x71, (256, 7))
+    for cap_height in (1, 8):
+        t = pb.MerkleTree(leaves, cap_height)
+        lv, paths = t.open_many(np.arange(256))
+        cap = t.cap.hashes
+        for i in range(256):
+            assert oracle.merkle_verify(lv[i], i, paths[i], cap, cap_height)
+    pb.verify_merkle_proof_to_cap(leaves[5], 5, t.cap, t.prove(5))
+    with pytest.raises(ValueError):
+        pb.verify_merkle_proof_to_cap(leaves[6], 5, t.cap, t.prove(5))
+
+
+def test_merkle_cap_too_big(pb):
+    with pytest.raises(ValueError) as e:
+        pb.MerkleTree(synth(1, (8, 5)), 4)
+    assert "should be at most log2(leaves.len())" in str(e.value)
+    with pytest.raises(ValueError):
+        pb.MerkleTree(synth(1, (12, 5)), 1)
+
+
+def test_merkle_large_cap_property(pb, oracle):
+    # 2^18 leaves x 12 (config 3 shape, reduced): cap equals the fold of the digest array's top pairs and a
+    # sample of proofs verifies; full 2^23 is covered by bench.py's checks.
+    N, W, h = 1 << 18, 12, 4
+    leaves = synth(0x03, (N, W))
+    t = pb.MerkleTree(leaves, h)
+    d, cap = oracle.merkle_build(leaves, h)
+    assert np.array_equal(t.cap.hashes, cap)
+    lv, paths = t.open_many([1, 77777, N - 2])
+    for k, i in enumerate([1, 77777, N - 2]):
+        assert oracle.merkle_verify(lv[k], i, paths[k], cap, h)
+
+
+# ----------------------------------------------------------------------------- PolynomialBatch
+@pytest.mark.parametrize("B,log_n,r,h", [(5, 4, 2, 1), (3, 0, 3, 0), (1, 1, 1, 2), (9, 6, 3, 4), (135, 10, 3, 4),
+                                         (20, 13, 3, 4), (16, 14, 1, 4), (2, 12, 0, 0), (17, 9, 2, 11)])
+def test_from_values_matches_oracle(pb, oracle, B, log_n, r, h):
+    n = 1 << log_n
+    vals = synth(0x02 + B, (B, n), canonical=(B % 2 == 0))
+    c = pb.PolynomialBatch.from_values(vals, r, False, h)
+    o = oracle.Commit(vals, r, h)
+    assert np.array_equal(c.polynomials, o.coeffs)
+    assert np.array_equal(c.merkle_tree.cap.hashes, o.cap)
+    assert np.array_equal(c.merkle_tree.leaves, o.leaves)
+    assert np.array_equal(c.merkle_tree.digests, o.digests)
+    N = n << r
+    for (idx, step) in [(0, 1), (N // 2 - 1 if N > 1 else 0, 2 if N > 1 else 1), (N - 1, 1)]:
+        assert np.array_equal(c.get_lde_values(idx, step), o.get_lde_values(idx, step))
+    lv, paths = c.merkle_tree.open_many([0, N - 1])
+    assert np.array_equal(lv[1], o.leaves[N - 1])
+    if N > (1 << h):
+        assert np.array_equal(paths[1], oracle.merkle_prove(N - 1, N, h, o.digests))
+    c.close()
+
+
+def test_from_coeffs_and_blinding(pb, oracle):
+    B, log_n, r, h = 6, 7, 3, 2
+    n, N = 1 << log_n, 1 << (log_n + r)
+    co = synth(0x81, (B, n))
+    salt = synth(0x82, (4, N))
+    c = pb.PolynomialBatch.from_coeffs(co, r, True, h, salt=salt)
+    o = oracle.Commit(co, r, h, salt=salt, is_coeffs=True)
+    assert c.leaf_width == B + 4
+    assert np.array_equal(c.merkle_tree.leaves, o.leaves)
+    assert np.array_equal(c.merkle_tree.cap.hashes, o.cap)
+    assert np.array_equal(c.get_lde_values(3, 1), o.get_lde_values(3, 1))  # salt stripped
+    # OsRng-salted commitment: different caps, same unsalted LDE values
+    c2 = pb.PolynomialBatch.from_coeffs(co, r, True, h)
+    assert not np.array_equal(c2.merkle_tree.cap.hashes, o.cap)
+    assert np.array_equal(c2.get_lde_values(3, 1), o.get_lde_values(3, 1))
+
+
+def test_commit_shape_errors(pb):
+    with pytest.raises(ValueError):
+        pb.PolynomialBatch.from_values(np.zeros((2, 12), dtype=np.uint64), 1, False, 0)
+    with pytest.raises(ValueError) as e:
+        pb.PolynomialBatch.from_values(np.zeros((2, 8), dtype=np.uint64), 1, False, 5)
+    assert "cap_height" in str(e.value)
+
+
+def test_commit_lde_restricts_to_values(pb):
+    # property at a larger size (B=8, n=2^16, r=3): LDE at rate 1 extends the same polynomial: the coeffs'
+    # forward NTT returns the committed values, and the commitment of coeffs equals the commitment of values.
+    B, log_n = 8, 16
+    vals = synth(0x83, (B, 1 << log_n))
+    c = pb.PolynomialBatch.from_values(vals, 3, False, 4)
+    co = c.polynomials
+    assert np.array_equal(pb.fft(co), vals)
+    c2 = pb.PolynomialBatch.from_coeffs(co, 3, False, 4)
+    assert np.array_equal(c2.merkle_tree.cap.hashes, c.merkle_tree.cap.hashes)
+
+
+# ----------------------------------------------------------------------------- FRI
+def _instance(pb, oracles_B, zeta, gzeta, z_polys):
+    inst_batches = []
+    all_polys = [pb.FriPolynomialInfo(o, i) for o, B in enumerate(oracles_B) for i in range(B)]
+    inst_batches.append(pb.FriBatchInfo(zeta, all_polys))
+    inst_batches.append(pb.FriBatchInfo(gzeta, [pb.FriPolynomialInfo(*p) for p in z_polys]))
+    return pb.FriInstanceInfo([pb.FriOracleInfo(B, False) for B in oracles_B], inst_batches)
+
+
+def _opened_values(oracle, ocommits, batches):
+    vals = []
+    for point, polys in batches:
+        for (oi, pi) in polys:
+            vals.append(oracle.eval_poly_base_at_ext(ocommits[oi].coeffs[pi], point))
+    return np.array(vals, dtype=np.uint64)
+
+
+@pytest.mark.parametrize("log_n,Bs,arity,pow_bits,nq", [(5, [3, 2], [1], 3, 4), (8, [4, 6, 2], [2, 2], 5, 6),
+                                                       (10, [7, 9, 4, 3], [4], 8, 9),
+                                                       (12, [20, 33, 20, 16], [4, 4], 16, 28),
+                                                       (9, [5], [3, 1, 2], 4, 5), (7, [2, 2], [5], 2, 3)])
+def test_prove_openings_bit_exact_and_verifies(pb, oracle, log_n, Bs, arity, pow_bits, nq):
+    r, h = 3, (4 if log_n >= 8 else 1)
+    n = 1 << log_n
+    vals = [synth(0x04 + i, (B, n)) for i, B in enumerate(Bs)]
+    commits = [pb.PolynomialBatch.from_values(v, r, False, h) for v in vals]
+    ocommits = [oracle.Commit(v, r, h) for v in vals]
+    zeta = (int(synth(0xA1, (1,))[0]), int(synth(0xA2, (1,))[0]))
+    gz = pb.field.ext_mul(zeta, (pb.field.primitive_root_of_unity(log_n), 0))
+    z_polys = [(len(Bs) - 1, i) for i in range(min(2, Bs[-1]))]
+    inst = _instance(pb, Bs, zeta, gz, z_polys)
+    obatches = [(b.point, [(p.oracle_index, p.polynomial_index) for p in b.polynomials]) for b in inst.batches]
+    cfg = pb.FriConfig(r, h, pow_bits, ("Fixed", arity), nq)
+    params = pb.FriParams(cfg, False, log_n, arity)
+    oparams = oracle.make_params(r, h, pow_bits, nq, arity)
+
+    # a transcript prefix both sides share
+    ch, och = pb.Challenger(), oracle.Challenger()
+    for c in commits:
+        ch.observe_cap(c.merkle_tree.cap)
+    for o in ocommits:
+        och.observe_cap(o.cap)
+    och_verify = och.clone()
+
+    taps = {}
+    proof = pb.prove_openings(inst, commits, ch, params, taps=taps)
+    oproof, otaps = oracle.prove_openings(ocommits, obatches, och, oparams, taps=True)
+    assert np.array_equal(taps["final_poly"], otaps["final_poly"])
+    assert taps["pow_witness"] == otaps["pow_witness"]
+    assert list(taps["query_indices"]) == otaps["query_indices"].tolist()
+    assert proof.to_bytes() == oproof                      # bit-exact FRI proof bytes
+    assert ch.get_challenge() == och.get_challenge()       # transcripts stay in sync
+    # and the proof passes the restated verifier (fri/verifier.rs:62-241)
+    opened = _opened_values(oracle, ocommits, obatches)
+    rc = oracle.verify_fri_proof([o.cap for o in ocommits], Bs, [o.W for o in ocommits], obatches, opened,
+                                 log_n, och_verify, oparams, proof.to_bytes())
+    assert rc == 0
+    # a corrupted proof must be rejected
+    bad = bytearray(proof.to_bytes())
+    bad[-9] ^= 1
+    rc2 = oracle.verify_fri_proof([o.cap for o in ocommits], Bs, [o.W for o in ocommits], obatches, opened,
+                                  log_n, oracle.Challenger(), oparams, bytes(bad))
+    assert rc2 != 0
+
+
+def test_fri_pow_smallest_nonce(pb, oracle):
+    ctx = pb.default_context()
+    st = synth(0xB1, (12,))
+    for pos, bits in [(0, 0), (3, 7), (7, 10)]:
+        nonce = np.zeros(1, dtype=np.uint64)
+        pb._native.check(pb._native.lib().gl_fri_pow(ctx.h, pb._native.np_ptr(st), pos, bits,
+                                                     pb._native.np_ptr(nonce)), ctx.h)
+        # brute force on the oracle
+        want = None
+        for cand in range(1 << 14):
+            s = st.copy()
+            s[pos] = cand
+            if (64 - int(oracle.poseidon(s)[7]).bit_length()) >= bits:
+                want = cand
+                break
+        assert int(nonce[0]) == want
