@@ -1,0 +1,376 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native plonky2 prover hot path.
+
+A "step" = one pass of the hot path over one batch of synthetic input: PolynomialBatch::from_values
+(plonky2/src/fri/oracle.rs:57-112) = iNTT of every column -> rate-2^-r coset LDE -> Poseidon Merkle
+commitment of the LDE rows.  Workload at N=1 = BASELINE.json configs[1]: 234 columns x 2^20 values,
+rate_bits 3, cap_height 4 (2^23 leaves of 234 elements).  Metric = Goldilocks field-elements/s
+(LDE output elements committed per second = B*N / t), whole job.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+N > 1: the SAME commitment is row-block sharded over the ranks (strong scaling): rank g builds leaf rows
+[g*N/G, (g+1)*N/G) on its own coset and the ranks all-gather their Merkle-cap entries over NCCL.
+Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement").
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "goldilocks_field_elements_per_s_ntt_lde_merkle"
+UNIT = "elements/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_config(args, world):
+    n, N = 1 << args.log_n, 1 << (args.log_n + args.rate_bits)
+    name = "from_values: %d columns x 2^%d values, rate_bits=%d, cap_height=%d (2^%d leaves x %d)" % (
+        args.cols, args.log_n, args.rate_bits, args.cap_height, args.log_n + args.rate_bits, args.cols)
+    if (args.cols, args.log_n, args.rate_bits, args.cap_height) == (234, 20, 3, 4):
+        name = "BASELINE configs[1]: " + name
+    return {
+        "workload": name,
+        "columns": args.cols, "log_n": args.log_n, "rate_bits": args.rate_bits, "cap_height": args.cap_height,
+        "lde_elements": args.cols * N,
+        "l2": "inputs %.2f GB + leaves %.2f GB per step, far larger than the 126 MB L2 (no flush needed)" % (
+            args.cols * n * 8 / 1e9, args.cols * N * 8 / 1e9),
+        "parallelism": "row-block (coset) sharding x%d, NCCL all-gather of cap entries" % world if world > 1
+        else "single GPU",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the CPU path (oracle port; the Rust reference cannot be built in this image)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(args, cores, target_cpu_seconds=20.0):
+    """Bounded sample of the same workload for the CPU arm: same columns/rate/cap, fewer rows."""
+    # ~1.3 us of CPU per Poseidon permutation; perms per leaf = ceil(W/8) + 1
+    perms_per_leaf = (args.cols + 7) // 8 + 1
+    log_n = args.log_n
+    while log_n > 10 and (1 << (log_n + args.rate_bits)) * perms_per_leaf * 1.3e-6 > target_cpu_seconds * max(1, cores) / 4:
+        log_n -= 1
+    return log_n
+
+
+def run_cpu_once(args, log_n_s, cores, seed):
+    import oracle_lib
+
+    from conftest import synth
+
+    vals = synth(seed, (args.cols, 1 << log_n_s))
+    t0 = time.perf_counter()
+    c = oracle_lib.Commit(vals, args.rate_bits, args.cap_height, nthreads=cores)
+    dt = time.perf_counter() - t0
+    cap = c.cap
+    del c
+    return dt, cap
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    import oracle_lib
+
+    cores = oracle_lib.nproc()
+    log_n_s = cpu_sample(args, cores)
+    for w in range(args.warmup):
+        run_cpu_once(args, min(log_n_s, 12), cores, 100 + w)
+    times = []
+    for k in range(args.steps):
+        dt, _ = run_cpu_once(args, log_n_s, cores, 200 + k)
+        times.append(dt)
+    elems = args.cols * (1 << (log_n_s + args.rate_bits))
+    total = sum(times)
+    value = elems * len(times) / total
+    sample = "same columns/rate/cap, n=2^%d rows per step (bounded sample of n=2^%d)" % (log_n_s, args.log_n)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic", "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "C++ restatement of the reference CPU algorithm (oracle/); the Rust reference "
+                                 "needs nightly cargo, absent from this image"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(",") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if sm:
+            busy = sorted(sm)[len(sm) // 2:]  # samples under load are the upper half when idle ones exist
+            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def gpu_arm(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from plonky2_b200 import _native as N
+
+    L = N.lib()
+    stream = torch.cuda.Stream(device=dev)
+    ctx = N.Context(local_rank, stream=stream.cuda_stream)
+    ctx.set_profiling(True)
+    B, log_n, r, h = args.cols, args.log_n, args.rate_bits, args.cap_height
+    n, NN = 1 << log_n, 1 << (log_n + r)
+    cap_local_words = (4 << h) // world
+    peak, peak_src = load_peaks()
+
+    with torch.cuda.stream(stream):
+        g = torch.Generator(device=dev)
+        g.manual_seed(0x02)
+        vals = torch.randint(0, 2**63 - 1, (B, n), dtype=torch.int64, device=dev, generator=g)  # canonical (< p)
+        cap_local = torch.empty(cap_local_words, dtype=torch.int64, device=dev)
+        cap_full = torch.empty(cap_local_words * world, dtype=torch.int64, device=dev)
+
+        def step_device():
+            hnd = N.vp()
+            N.check(L.gl_commit_create_sharded(ctx.h, C.c_void_p(vals.data_ptr()), n, B, log_n, r, h, None, 0,
+                                               N.MEM_DEVICE, rank, world, C.byref(hnd)), ctx.h)
+            N.check(L.gl_commit_cap(hnd, C.c_void_p(cap_local.data_ptr()), N.MEM_DEVICE), ctx.h)
+            if world > 1:
+                dist.all_gather_into_tensor(cap_full, cap_local)
+            else:
+                cap_full.copy_(cap_local)
+            L.gl_commit_destroy(hnd)
+
+        def sync_all():
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize(dev)
+
+        for _ in range(max(args.warmup, 3)):
+            step_device()
+        sync_all()
+        ctx.reset_phases()
+        launches0 = ctx.launch_count
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        e1.record(stream)
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        launches = ctx.launch_count - launches0
+        clocks = sampler.stop() if sampler else None
+        phases = ctx.phase_ms()
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.item())
+        cap_dev = cap_full.cpu().numpy().view(np.uint64).reshape(-1, 4).copy()
+
+        # ---- end to end through the C ABI with HOST buffers (pinned): H2D of the columns + D2H of the cap
+        host_vals = torch.empty((B, n), dtype=torch.int64, pin_memory=True)
+        host_vals.copy_(vals)
+        torch.cuda.synchronize(dev)
+        host_cap = np.empty(cap_local_words, dtype=np.uint64)
+
+        def step_e2e():
+            hnd = N.vp()
+            N.check(L.gl_commit_create_sharded(ctx.h, C.c_void_p(host_vals.data_ptr()), n, B, log_n, r, h, None, 0,
+                                               N.MEM_HOST, rank, world, C.byref(hnd)), ctx.h)
+            N.check(L.gl_commit_cap(hnd, N.np_ptr(host_cap), N.MEM_HOST), ctx.h)  # synchronises
+            if world > 1:
+                cap_local.copy_(torch.from_numpy(host_cap.view(np.int64)))
+                dist.all_gather_into_tensor(cap_full, cap_local)
+            L.gl_commit_destroy(hnd)
+
+        step_e2e()
+        sync_all()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ke = max(1, min(args.steps, 3))
+        e2.record(stream)
+        for _ in range(ke):
+            step_e2e()
+        e3.record(stream)
+        sync_all()
+        t2 = torch.tensor([e2.elapsed_time(e3)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t2.item()) / ke
+        assert np.array_equal(host_cap.reshape(-1, 4), cap_dev[rank * (len(cap_dev) // world):(rank + 1) * (len(cap_dev) // world)])
+
+        # ---- bare batched NTT roofline (the north star's "2^20-point NTT"): 64 columns, working set 512 MiB
+        ntt = None
+        if rank == 0 and not args.no_ntt:
+            cols_ntt = args.ntt_cols
+            buf = vals[:cols_ntt].clone() if cols_ntt <= B else torch.randint(0, 2**63 - 1, (cols_ntt, n), dtype=torch.int64, device=dev)
+            for _ in range(3):
+                N.check(L.gl_ntt(ctx.h, C.c_void_p(buf.data_ptr()), log_n, cols_ntt, n, 0, 0, 1, N.MEM_DEVICE), ctx.h)
+            torch.cuda.synchronize(dev)
+            l0 = ctx.launch_count
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            a.record(stream)
+            for _ in range(reps):
+                N.check(L.gl_ntt(ctx.h, C.c_void_p(buf.data_ptr()), log_n, cols_ntt, n, 0, 0, 1, N.MEM_DEVICE), ctx.h)
+            b.record(stream)
+            torch.cuda.synchronize(dev)
+            ms_ntt = a.elapsed_time(b) / reps
+            alg = 16.0 * n * cols_ntt
+            ntt = {"workload": "forward NTT, %d columns x 2^%d, in place, device resident" % (cols_ntt, log_n),
+                   "ms": ms_ntt, "elements_per_s": cols_ntt * n / (ms_ntt * 1e-3),
+                   "algorithmic_bytes": alg, "achieved": alg / (ms_ntt * 1e-3) / 1e9, "unit": "GB/s",
+                   "peak": peak, "frac": alg / (ms_ntt * 1e-3) / 1e9 / peak,
+                   "launches_per_call": (ctx.launch_count - l0) // reps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    steps = args.steps
+    ms_step = ms_max / steps
+    value = B * NN / (ms_step * 1e-3)
+    N_loc = NN // world
+    # dominant kernel = the Poseidon leaf hash (k_leaf_hash): algorithmic bytes = leaves read + digests written
+    leaf_ms, leaf_cnt = phases["leaf_hash"]
+    leaf_avg = leaf_ms / max(1, leaf_cnt)
+    leaf_bytes = 8.0 * N_loc * B + 32.0 * N_loc
+    perms = N_loc * ((B + 7) // 8 if B > 4 else 0)
+    roof = {
+        "kernel": "k_leaf_hash (Poseidon sponge over each LDE row)", "bound": "hbm",
+        "achieved": leaf_bytes / (leaf_avg * 1e-3) / 1e9 if leaf_avg else None, "peak": peak, "unit": "GB/s",
+        "frac": (leaf_bytes / (leaf_avg * 1e-3) / 1e9 / peak) if leaf_avg else None,
+        "traffic": None, "peak_source": peak_src, "avg_ms": leaf_avg, "launches": leaf_cnt,
+        "algorithmic_bytes": leaf_bytes,
+        "permutations_per_s": perms / (leaf_avg * 1e-3) if leaf_avg else None,
+        "note": "integer-issue bound (x^7 S-boxes + MDS in IMAD/IADD3), not HBM bound: see DESIGN.md",
+    }
+    lde_ms = (phases["intt"][0] + phases["lde"][0]) / steps
+    lde_bytes = 8.0 * n * B * (2 + (1 << r) / world)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic", "config": workload_config(args, world),
+        "clocks": clocks,
+        "e2e": {"value": B * NN / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": B * n * 8, "d2h_bytes_per_step": cap_local_words * 8,
+                "note": "host (pinned) columns -> gl_commit_create -> cap on host; leaves/digests stay on the "
+                        "device behind the handle (fetched on demand by gl_commit_leaves/_open)"},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "phases_ms_per_step": {k: v[0] / steps for k, v in phases.items()},
+        "roofline_lde": {"kernels": "k_passA + k_passB (iNTT + 2^r coset NTTs, leaf-major stores)", "bound": "hbm",
+                         "algorithmic_bytes": lde_bytes, "ms": lde_ms,
+                         "achieved": lde_bytes / (lde_ms * 1e-3) / 1e9 if lde_ms else None, "peak": peak,
+                         "unit": "GB/s", "frac": lde_bytes / (lde_ms * 1e-3) / 1e9 / peak if lde_ms else None},
+        "roofline_ntt": ntt,
+        "cap0": [int(x) for x in cap_dev[0]],
+    }
+    # ---- CPU baseline (bounded sample, rank 0, N=1 only)
+    if world == 1 and not args.no_cpu:
+        import oracle_lib
+
+        cores = oracle_lib.nproc()
+        log_n_s = cpu_sample(args, cores)
+        run_cpu_once(args, min(log_n_s, 12), cores, 1)
+        dt, _ = run_cpu_once(args, log_n_s, cores, 2)
+        line["cpu_baseline"] = {
+            "value": B * (1 << (log_n_s + r)) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "same columns/rate/cap, n=2^%d rows (bounded sample of n=2^%d), %.2f s" % (log_n_s, log_n, dt)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cols", type=int, default=234)
+    ap.add_argument("--log-n", type=int, default=20)
+    ap.add_argument("--rate-bits", type=int, default=3)
+    ap.add_argument("--cap-height", type=int, default=4)
+    ap.add_argument("--ntt-cols", type=int, default=64)
+    ap.add_argument("--no-ntt", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    gpu_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -60,6 +60,17 @@ int gl_ctx_synchronize(gl_ctx* ctx);
 uint64_t gl_ctx_launch_count(const gl_ctx* ctx);
 /* tuning: columns per NTT group (scratch = group * n * 8 bytes; sized so pass A -> pass B stays in L2) */
 int gl_ctx_set_ntt_group(gl_ctx* ctx, uint32_t columns);
+/* Optional CUDA-event phase timing on the context's stream (the analogue of the reference's TimingTree
+ * scopes "IFFT" / "FFT + blinding" / "build Merkle tree", plonky2/src/fri/oracle.rs:65-103). */
+#define GL_PHASE_INTT 0          /* from_values' iNTT of all columns */
+#define GL_PHASE_LDE 1           /* coset LDE into leaf-major rows (passes A + B, all cosets) */
+#define GL_PHASE_LEAF_HASH 2     /* the Poseidon leaf-hash kernel */
+#define GL_PHASE_MERKLE_LEVELS 3 /* all two_to_one levels up to the cap */
+#define GL_NUM_PHASES 4
+int gl_ctx_set_profiling(gl_ctx* ctx, int on);
+/* accumulated milliseconds and number of scopes of `phase` since the last reset (synchronises) */
+int gl_ctx_phase_ms(gl_ctx* ctx, int phase, double* ms, uint64_t* count);
+int gl_ctx_reset_phases(gl_ctx* ctx);
 
 /* ---- NTT  (field/src/fft.rs:53-91 fft_with_options / ifft_with_options;
  *            field/src/polynomial/mod.rs:63-73,280-293 coset_ifft / coset_fft_with_options) -------- */
@@ -81,6 +92,15 @@ int gl_ntt(gl_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t batch, size_t s
 int gl_commit_create(gl_ctx* ctx, const uint64_t* cols, size_t col_stride, uint32_t B, uint32_t log_n,
                      uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, int is_coeffs,
                      int mem, gl_commit** out);
+/* Row-block sharded variant (one shard per GPU): shard g of G = 2^s <= 2^cap_height
+ * builds leaf rows [g*N/G, (g+1)*N/G) -- all columns on the coset (g*w_N^{bitrev_s(g)})<w_{N/G}> -- their
+ * digests and cap entries [g*C/G, (g+1)*C/G). Concatenating the shards' leaves / digests / caps in shard
+ * order gives exactly the single-device commitment; only the C/G cap entries need to be exchanged
+ * (one all-gather). Accessors of a sharded handle return the LOCAL rows / digests / cap entries. */
+int gl_commit_create_sharded(gl_ctx* ctx, const uint64_t* cols, size_t col_stride, uint32_t B, uint32_t log_n,
+                             uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, int is_coeffs,
+                             int mem, uint32_t shard_index, uint32_t num_shards, gl_commit** out);
+int gl_commit_shard(const gl_commit* c, uint32_t* shard_index, uint32_t* num_shards);
 void gl_commit_destroy(gl_commit* c);
 /* shape queries */
 uint32_t gl_commit_num_polys(const gl_commit* c);  /* B */

@@ -38,7 +38,7 @@ inline u64 canon(u64 c) { return c >= P ? c - P : c; }
 inline u64 fadd(u64 a, u64 b) {
     u64 sum = a + b;
     bool over = sum < a;
-    u64 sum2 = sum + (over ? EPS : 0);
+    u64 sum2 = sum + ((0 - (u64)over) & EPS);
     bool over2 = sum2 < sum;
     if (over2) sum2 += EPS;
     return sum2;
@@ -47,7 +47,7 @@ inline u64 fadd(u64 a, u64 b) {
 inline u64 fsub(u64 a, u64 b) {
     u64 diff = a - b;
     bool under = a < b;
-    u64 diff2 = diff - (under ? EPS : 0);
+    u64 diff2 = diff - ((0 - (u64)under) & EPS);
     bool under2 = diff2 > diff;
     if (under2) diff2 -= EPS;
     return diff2;
@@ -61,7 +61,8 @@ inline u64 reduce128(u128 x) {
     if (x_lo < x_hi_hi) t0 -= EPS;
     u64 t1 = x_hi_lo * EPS;
     u64 res = t0 + t1;
-    if (res < t0) res += EPS;
+    // add_no_canonicalize_trashing_input (:355-389): branch-free "+= EPS * carry" (the carry is ~50% likely)
+    res += (0 - (u64)(res < t0)) & EPS;
     return res;
 }
 // Mul, goldilocks_field.rs:313-320
@@ -271,16 +272,26 @@ inline u64 sbox(u64 x) {
     u64 x2 = fsqr(x), x4 = fsqr(x2), x3 = fmul(x, x2);
     return fmul(x3, x4);
 }
-// mds_row_shf + mds_layer, poseidon.rs:180-200,269-290
+// mds_row_shf + mds_layer, poseidon.rs:180-200,269-290 -- evaluated like the reference's Goldilocks
+// override (poseidon_goldilocks.rs:217-248) on the low/high 32-bit halves of the state so that the
+// 12-term sums of (32-bit x 6-bit) products fit in u64 and one reduction per lane suffices.
 inline void mds_layer(u64 st[12]) {
-    u64 out[12];
-    for (int r = 0; r < 12; r++) {
-        u128 res = 0;
-        for (int i = 0; i < 12; i++) res += (u128)st[(i + r) % 12] * (u128)GL_POSEIDON_MDS_CIRC[i];
-        res += (u128)st[r] * (u128)GL_POSEIDON_MDS_DIAG[r];
-        out[r] = reduce128(res);
+    u64 lo[24], hi[24];
+    for (int i = 0; i < 12; i++) {
+        lo[i] = lo[i + 12] = st[i] & EPS;
+        hi[i] = hi[i + 12] = st[i] >> 32;
     }
-    memcpy(st, out, sizeof(out));
+    for (int r = 0; r < 12; r++) {
+        u64 al = 0, ah = 0;
+        for (int i = 0; i < 12; i++) {
+            al += lo[i + r] * GL_POSEIDON_MDS_CIRC[i];
+            ah += hi[i + r] * GL_POSEIDON_MDS_CIRC[i];
+        }
+        al += lo[r] * GL_POSEIDON_MDS_DIAG[r];
+        ah += hi[r] * GL_POSEIDON_MDS_DIAG[r];
+        u128 sum = (u128)al + ((u128)ah << 32);
+        st[r] = reduce128(sum);
+    }
 }
 // full_rounds, poseidon.rs:741-749
 inline void full_rounds(u64 st[12], int* round_ctr) {

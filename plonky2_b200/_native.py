@@ -20,7 +20,8 @@ vp = C.c_void_p
 
 EXPORTS = [
     "gl_ctx_create", "gl_ctx_destroy", "gl_last_error", "gl_ctx_synchronize", "gl_ctx_launch_count",
-    "gl_ctx_set_ntt_group", "gl_ntt", "gl_commit_create", "gl_commit_destroy", "gl_commit_num_polys",
+    "gl_ctx_set_ntt_group", "gl_ctx_set_profiling", "gl_ctx_phase_ms", "gl_ctx_reset_phases", "gl_ntt",
+    "gl_commit_create", "gl_commit_create_sharded", "gl_commit_shard", "gl_commit_destroy", "gl_commit_num_polys",
     "gl_commit_leaf_width", "gl_commit_degree_log", "gl_commit_rate_bits", "gl_commit_cap_height",
     "gl_commit_cap", "gl_commit_coeffs", "gl_commit_leaves", "gl_commit_digests", "gl_commit_get_lde_values",
     "gl_commit_open", "gl_commit_dev_leaves", "gl_commit_dev_coeffs", "gl_poseidon_permute_host",
@@ -68,6 +69,12 @@ def lib():
     L.gl_ntt.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_size_t, C.c_int, C.c_uint32, C.c_uint64, C.c_int]
     L.gl_commit_create.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp,
                                    C.c_int, C.c_int, C.POINTER(vp)]
+    L.gl_commit_create_sharded.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp,
+                                           C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+    L.gl_commit_shard.argtypes = [vp, u32p, u32p]
+    L.gl_ctx_set_profiling.argtypes = [vp, C.c_int]
+    L.gl_ctx_phase_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.gl_ctx_reset_phases.argtypes = [vp]
     L.gl_commit_destroy.argtypes = [vp]
     L.gl_commit_destroy.restype = None
     for n in ("gl_commit_num_polys", "gl_commit_leaf_width", "gl_commit_degree_log", "gl_commit_rate_bits",
@@ -147,6 +154,23 @@ class Context:
 
     def set_ntt_group(self, columns):
         check(lib().gl_ctx_set_ntt_group(self.h, int(columns)), self.h)
+
+    PHASES = {"intt": 0, "lde": 1, "leaf_hash": 2, "merkle_levels": 3}
+
+    def set_profiling(self, on):
+        check(lib().gl_ctx_set_profiling(self.h, int(bool(on))), self.h)
+
+    def reset_phases(self):
+        check(lib().gl_ctx_reset_phases(self.h), self.h)
+
+    def phase_ms(self):
+        """{phase: (accumulated ms, scopes)} from CUDA events on this context's stream."""
+        out = {}
+        for name, pid in self.PHASES.items():
+            ms, cnt = C.c_double(), C.c_uint64()
+            check(lib().gl_ctx_phase_ms(self.h, pid, C.byref(ms), C.byref(cnt)), self.h)
+            out[name] = (ms.value, cnt.value)
+        return out
 
     def close(self):
         if getattr(self, "h", None):

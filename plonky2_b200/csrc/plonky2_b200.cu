@@ -43,6 +43,32 @@ struct gl_ctx {
     u64* dstage = nullptr;                      // device staging for openings
     size_t dstage_words = 0;
     uint32_t ntt_group = 0;                     // 0 = auto
+    // optional CUDA-event phase timing (bench.py's roofline numbers come from here)
+    bool prof_on = false;
+    struct Pending {
+        int phase;
+        cudaEvent_t a, b;
+    };
+    std::vector<Pending> prof_pending;
+    double prof_ms[GL_NUM_PHASES] = {0};
+    u64 prof_count[GL_NUM_PHASES] = {0};
+};
+
+struct PhaseScope {
+    gl_ctx* ctx;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int phase;
+    PhaseScope(gl_ctx* c, int ph) : ctx(c), phase(ph) {
+        if (!ctx->prof_on) return;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~PhaseScope() {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->prof_pending.push_back({phase, a, b});
+    }
 };
 
 static int set_err(gl_ctx* ctx, int code, const char* fmt, ...) {
@@ -653,8 +679,12 @@ static int tree_build(gl_ctx* ctx, Tree& t) {
     TRY(dmalloc(ctx, &t.digests, t.digest_words()));
     TRY(dmalloc(ctx, &t.cap, t.cap_words()));
     TreeView v = t.view();
-    k_leaf_hash<<<(unsigned)((t.N + 127) / 128), 128, 0, ctx->stream>>>(v);
-    CKL(ctx);
+    {
+        PhaseScope ps(ctx, GL_PHASE_LEAF_HASH);
+        k_leaf_hash<<<(unsigned)((t.N + 127) / 128), 128, 0, ctx->stream>>>(v);
+        CKL(ctx);
+    }
+    PhaseScope ps2(ctx, GL_PHASE_MERKLE_LEVELS);
     const uint32_t sub_log = t.log_n - t.cap_height;
     for (uint32_t i = 1; i <= sub_log; i++) {
         size_t total = (size_t)1 << (t.log_n - i);
@@ -697,18 +727,30 @@ static int tree_open(gl_ctx* ctx, const Tree& t, const u64* leaf_indices, size_t
 struct gl_commit {
     gl_ctx* ctx;
     uint32_t B, W, degree_log, rate_bits;
+    uint32_t shard_index = 0, shard_log = 0;  // this handle holds leaf rows [g*N/G, (g+1)*N/G)
     bool blinding;
     u64* coeffs = nullptr;  // B x n
     Tree tree;
 };
 
 // leaves[j][B + s] = salt[s][bitrev(j)]  (salt columns are LDE columns in natural order, oracle.rs:133-137)
-__global__ void k_salt(const u64* salt, size_t N, uint32_t log_N, u64* leaves, size_t W, uint32_t B) {
+__global__ void k_salt(const u64* salt, size_t N, uint32_t log_N, size_t row0, size_t rows, u64* leaves, size_t W,
+                       uint32_t B) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
-    size_t i = (size_t)(__brevll(j) >> (64 - log_N));
+    if (j >= rows) return;
+    size_t i = (size_t)(__brevll(row0 + j) >> (64 - log_N));
     if (log_N == 0) i = 0;
     for (int s = 0; s < GL_SALT_SIZE; s++) leaves[j * W + B + s] = canon(salt[(size_t)s * N + i]);
+}
+// Restriction of a degree-<n polynomial to a coset of size M < n (x^M = sM on it):
+// a'[k0] = sum_{k1 < n/M} a[k0 + M*k1] * sM^k1     ("fold coefficients mod X^M - s^M")
+__global__ void k_fold_coeffs(const u64* coeffs, size_t stride, size_t n, size_t M, u64 sM, u64* out) {
+    size_t k0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k0 >= M) return;
+    const u64* col = coeffs + (size_t)blockIdx.y * stride;
+    u64 acc = 0;
+    for (size_t k1 = n / M; k1-- > 0;) acc = mul_add(acc, sM, col[k0 + M * k1]);
+    out[(size_t)blockIdx.y * M + k0] = acc;
 }
 __global__ void k_canon(u64* data, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -733,6 +775,7 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
     }
     if (!is_coeffs) {
         // "IFFT" (oracle.rs:65-69)
+        PhaseScope ps(ctx, GL_PHASE_INTT);
         TRY(ntt_natural(ctx, c->coeffs, n, c->coeffs, n, (int)c->degree_log, B, true, 1));
     } else {
         size_t tot = (size_t)B * n;
@@ -740,19 +783,47 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
         CKL(ctx);
     }
     // "FFT + blinding" + "transpose LDEs" + bit-reversal, fused: leaf-major coset LDE
+    // Row-block sharding: shard g of G = 2^s owns leaves [g*N/G, (g+1)*N/G), i.e. the
+    // LDE points i = g' (mod G), g' = bitrev_s(g): the coset (g * w_N^{g'}) <w_{N/G}> in bit-reversed order.
+    const uint32_t sl = c->shard_log;
+    const size_t Nloc = N >> sl;
+    const uint32_t gprime = bitrev32(c->shard_index, sl);
+    const u64 sg = mul(MULTIPLICATIVE_GROUP_GENERATOR,
+                       gl::pow(root_of_unity(c->degree_log + c->rate_bits), gprime));
     Tree& t = c->tree;
-    t.N = N;
+    t.N = Nloc;
     t.W = c->W;
-    t.cap_height = cap_height;
+    t.cap_height = cap_height - sl;
     t.own_leaves = true;
-    TRY(dmalloc(ctx, &t.leaves, N * (size_t)c->W));
-    if (c->degree_log == 0) {
-        const int ncos = 1 << c->rate_bits;
-        k_lde_const<<<(B * ncos + 127) / 128, 128, 0, ctx->stream>>>(c->coeffs, n, B, ncos, t.leaves, c->W, 0);
-        CKL(ctx);
-    } else {
-        TRY(lde_leaves(ctx, c->coeffs, n, B, (int)c->degree_log, (int)c->rate_bits, MULTIPLICATIVE_GROUP_GENERATOR,
-                       t.leaves, c->W, 0));
+    TRY(dmalloc(ctx, &t.leaves, Nloc * (size_t)c->W));
+    {
+        PhaseScope ps(ctx, GL_PHASE_LDE);
+        if (sl <= c->rate_bits) {
+            const uint32_t rloc = c->rate_bits - sl;
+            if (c->degree_log == 0) {
+                const int ncos = 1 << rloc;
+                k_lde_const<<<(B * ncos + 127) / 128, 128, 0, ctx->stream>>>(c->coeffs, n, B, ncos, t.leaves, c->W, 0);
+                CKL(ctx);
+            } else {
+                TRY(lde_leaves(ctx, c->coeffs, n, B, (int)c->degree_log, (int)rloc, sg, t.leaves, c->W, 0));
+            }
+        } else {
+            // fewer than n points per shard: restrict the polynomials to the sub-coset first
+            const uint32_t logM = c->degree_log + c->rate_bits - sl;
+            const size_t M = (size_t)1 << logM;
+            u64* folded;
+            TRY(dmalloc(ctx, &folded, (size_t)B * M));
+            k_fold_coeffs<<<dim3((unsigned)((M + 127) / 128), B), 128, 0, ctx->stream>>>(c->coeffs, n, n, M,
+                                                                                       gl::pow(sg, M), folded);
+            CKL(ctx);
+            if (logM == 0) {
+                k_lde_const<<<(B + 127) / 128, 128, 0, ctx->stream>>>(folded, 1, B, 1, t.leaves, c->W, 0);
+                CKL(ctx);
+            } else {
+                TRY(lde_leaves(ctx, folded, M, B, (int)logM, 0, sg, t.leaves, c->W, 0));
+            }
+            dfree(ctx, folded);
+        }
     }
     if (salt) {
         u64* dsalt = nullptr;
@@ -762,8 +833,9 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
             TRY(h2d(ctx, dsalt, salt, GL_SALT_SIZE * N));
             sp = dsalt;
         }
-        k_salt<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(sp, N, c->degree_log + c->rate_bits, t.leaves,
-                                                                    c->W, B);
+        k_salt<<<(unsigned)((Nloc + 255) / 256), 256, 0, ctx->stream>>>(sp, N, c->degree_log + c->rate_bits,
+                                                                       (size_t)c->shard_index * Nloc, Nloc, t.leaves,
+                                                                       c->W, B);
         CKL(ctx);
         if (dsalt) dfree(ctx, dsalt);
     }
@@ -1084,6 +1156,36 @@ int gl_ctx_set_ntt_group(gl_ctx* ctx, uint32_t columns) {
     ctx->ntt_group = columns;
     return GL_OK;
 }
+int gl_ctx_set_profiling(gl_ctx* ctx, int on) {
+    ctx->prof_on = on != 0;
+    return GL_OK;
+}
+int gl_ctx_phase_ms(gl_ctx* ctx, int phase, double* ms, uint64_t* count) {
+    if (phase < 0 || phase >= GL_NUM_PHASES) return set_err(ctx, GL_ERR_BAD_ARG, "bad phase");
+    if (!ctx->prof_pending.empty()) {
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        for (auto& p : ctx->prof_pending) {
+            float t = 0;
+            cudaEventElapsedTime(&t, p.a, p.b);
+            ctx->prof_ms[p.phase] += t;
+            ctx->prof_count[p.phase]++;
+            cudaEventDestroy(p.a);
+            cudaEventDestroy(p.b);
+        }
+        ctx->prof_pending.clear();
+    }
+    if (ms) *ms = ctx->prof_ms[phase];
+    if (count) *count = ctx->prof_count[phase];
+    return GL_OK;
+}
+int gl_ctx_reset_phases(gl_ctx* ctx) {
+    TRY(gl_ctx_phase_ms(ctx, 0, nullptr, nullptr));
+    for (int i = 0; i < GL_NUM_PHASES; i++) {
+        ctx->prof_ms[i] = 0;
+        ctx->prof_count[i] = 0;
+    }
+    return GL_OK;
+}
 
 int gl_ntt(gl_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t batch, size_t stride, int inverse,
            uint32_t zero_factor_log, uint64_t coset_shift, int mem) {
@@ -1115,7 +1217,19 @@ int gl_ntt(gl_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t batch, size_t s
 int gl_commit_create(gl_ctx* ctx, const uint64_t* cols, size_t col_stride, uint32_t B, uint32_t log_n,
                      uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, int is_coeffs, int mem,
                      gl_commit** out) {
+    return gl_commit_create_sharded(ctx, cols, col_stride, B, log_n, rate_bits, cap_height, salt, is_coeffs, mem, 0, 1,
+                                    out);
+}
+int gl_commit_create_sharded(gl_ctx* ctx, const uint64_t* cols, size_t col_stride, uint32_t B, uint32_t log_n,
+                             uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, int is_coeffs, int mem,
+                             uint32_t shard_index, uint32_t num_shards, gl_commit** out) {
     if (!ctx || !cols || !out) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
+    uint32_t shard_log = 0;
+    if (log2_exact(num_shards, &shard_log) || shard_index >= num_shards)
+        return set_err(ctx, GL_ERR_BAD_ARG, "bad shard %u of %u (power of two required)", shard_index, num_shards);
+    if (shard_log > cap_height)
+        return set_err(ctx, GL_ERR_BAD_SHAPE, "num_shards=%u exceeds the cap size 2^%u: shards must own whole cap subtrees",
+                       num_shards, cap_height);
     *out = nullptr;
     CK(ctx, cudaSetDevice(ctx->device));
     if (B == 0) return set_err(ctx, GL_ERR_BAD_SHAPE, "empty polynomial batch");
@@ -1133,6 +1247,8 @@ int gl_commit_create(gl_ctx* ctx, const uint64_t* cols, size_t col_stride, uint3
     c->degree_log = log_n;
     c->rate_bits = rate_bits;
     c->blinding = salt != nullptr;
+    c->shard_index = shard_index;
+    c->shard_log = shard_log;
     int rc = commit_build(ctx, c, cols, col_stride, salt, is_coeffs, mem, cap_height);
     if (rc != GL_OK) {
         gl_commit_destroy(c);
@@ -1152,7 +1268,7 @@ uint32_t gl_commit_num_polys(const gl_commit* c) { return c->B; }
 uint32_t gl_commit_leaf_width(const gl_commit* c) { return c->W; }
 uint32_t gl_commit_degree_log(const gl_commit* c) { return c->degree_log; }
 uint32_t gl_commit_rate_bits(const gl_commit* c) { return c->rate_bits; }
-uint32_t gl_commit_cap_height(const gl_commit* c) { return c->tree.cap_height; }
+uint32_t gl_commit_cap_height(const gl_commit* c) { return c->tree.cap_height + c->shard_log; }
 int gl_commit_cap(gl_commit* c, uint64_t* out, int mem) { return copy_out(c->ctx, out, c->tree.cap, c->tree.cap_words(), mem); }
 int gl_commit_coeffs(gl_commit* c, uint64_t* out, int mem) {
     return copy_out(c->ctx, out, c->coeffs, (size_t)c->B << c->degree_log, mem);
@@ -1167,10 +1283,17 @@ int gl_commit_digests(gl_commit* c, uint64_t* out, int mem) {
 int gl_commit_get_lde_values(gl_commit* c, size_t index, size_t step, uint64_t* out) {
     const uint32_t bits = c->degree_log + c->rate_bits;
     size_t idx = index * step;
-    if (idx >= c->tree.N) return set_err(c->ctx, GL_ERR_BAD_ARG, "index out of range");
+    if (idx >= ((size_t)1 << bits)) return set_err(c->ctx, GL_ERR_BAD_ARG, "index out of range");
     size_t rev = 0;
     for (uint32_t i = 0; i < bits; i++) rev |= ((idx >> i) & 1) << (bits - 1 - i);
-    return d2h(c->ctx, out, c->tree.leaves + rev * c->W, c->B);
+    const size_t row0 = (size_t)c->shard_index * c->tree.N;
+    if (rev < row0 || rev >= row0 + c->tree.N) return set_err(c->ctx, GL_ERR_BAD_ARG, "LDE row held by another shard");
+    return d2h(c->ctx, out, c->tree.leaves + (rev - row0) * c->W, c->B);
+}
+int gl_commit_shard(const gl_commit* c, uint32_t* shard_index, uint32_t* num_shards) {
+    if (shard_index) *shard_index = c->shard_index;
+    if (num_shards) *num_shards = 1u << c->shard_log;
+    return GL_OK;
 }
 int gl_commit_open(gl_commit* c, const uint64_t* leaf_indices, size_t count, uint64_t* out_leaves, uint64_t* out_paths) {
     return tree_open(c->ctx, c->tree, leaf_indices, count, out_leaves, out_paths);

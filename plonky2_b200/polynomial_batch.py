@@ -20,14 +20,15 @@ class _DeviceMerkleTree:
 
     @property
     def cap(self):
+        """The Merkle cap (for a sharded batch: this shard's cap entries; see distributed.gather_cap)."""
         b = self._b
-        out = np.empty((1 << b.cap_height, 4), dtype=np.uint64)
+        out = np.empty(((1 << b.cap_height) // b.num_shards, 4), dtype=np.uint64)
         N.check(N.lib().gl_commit_cap(b.h, N.np_ptr(out), N.MEM_HOST), b.ctx.h)
         return MerkleCap(out)
 
     @property
     def leaves(self):
-        return self.get_rows(0, self._b.lde_size)
+        return self.get_rows(0, self._b.local_rows)
 
     def get_rows(self, begin, count):
         b = self._b
@@ -39,7 +40,7 @@ class _DeviceMerkleTree:
     @property
     def digests(self):
         b = self._b
-        out = np.empty((2 * (b.lde_size - (1 << b.cap_height)), 4), dtype=np.uint64)
+        out = np.empty((2 * (b.local_rows - (1 << b.cap_height) // b.num_shards), 4), dtype=np.uint64)
         if out.size:
             N.check(N.lib().gl_commit_digests(b.h, N.np_ptr(out), N.MEM_HOST), b.ctx.h)
         return out
@@ -50,7 +51,7 @@ class _DeviceMerkleTree:
     def open_many(self, indices):
         b = self._b
         idx = np.ascontiguousarray(indices, dtype=np.uint64)
-        layers = b.degree_log + b.rate_bits - b.cap_height
+        layers = b.degree_log + b.rate_bits - b.cap_height  # local rows and local cap shrink together
         leaves = np.empty((len(idx), b.leaf_width), dtype=np.uint64)
         paths = np.empty((len(idx), layers, 4), dtype=np.uint64)
         if len(idx):
@@ -65,16 +66,18 @@ class _DeviceMerkleTree:
 class PolynomialBatch:
     """PolynomialBatch<F, PoseidonGoldilocksConfig, 2> (oracle.rs:30-37)."""
 
-    def __init__(self, handle, ctx, num_polys, degree_log, rate_bits, cap_height, blinding):
+    def __init__(self, handle, ctx, num_polys, degree_log, rate_bits, cap_height, blinding, shard=(0, 1)):
         self.h, self.ctx = handle, ctx
+        self.shard_index, self.num_shards = shard
         self.num_polys, self.degree_log, self.rate_bits = num_polys, degree_log, rate_bits
         self.cap_height, self.blinding = cap_height, blinding
         self.leaf_width = num_polys + (SALT_SIZE if blinding else 0)
         self.lde_size = 1 << (degree_log + rate_bits)
+        self.local_rows = self.lde_size // self.num_shards  # leaf rows [shard*local_rows, (shard+1)*local_rows)
         self.merkle_tree = _DeviceMerkleTree(self)
 
     @classmethod
-    def _create(cls, cols, rate_bits, blinding, cap_height, is_coeffs, salt, ctx):
+    def _create(cls, cols, rate_bits, blinding, cap_height, is_coeffs, salt, ctx, shard=(0, 1)):
         ctx = ctx or N.default_context()
         cols = np.ascontiguousarray(cols, dtype=np.uint64)
         if cols.ndim != 2 or cols.shape[0] == 0:
@@ -95,21 +98,23 @@ class PolynomialBatch:
                 raise N.ShapeError("salt must be (4, n << rate_bits)")
             sp = N.np_ptr(salt)
         h = N.vp()
-        N.check(N.lib().gl_commit_create(ctx.h, N.np_ptr(cols), n, B, log_n, rate_bits, cap_height, sp,
-                                         int(is_coeffs), N.MEM_HOST, C.byref(h)), ctx.h)
-        return cls(h, ctx, B, log_n, rate_bits, cap_height, bool(blinding))
+        N.check(N.lib().gl_commit_create_sharded(ctx.h, N.np_ptr(cols), n, B, log_n, rate_bits, cap_height, sp,
+                                                 int(is_coeffs), N.MEM_HOST, int(shard[0]), int(shard[1]),
+                                                 C.byref(h)), ctx.h)
+        return cls(h, ctx, B, log_n, rate_bits, cap_height, bool(blinding), (int(shard[0]), int(shard[1])))
 
     @classmethod
     def from_values(cls, values, rate_bits, blinding, cap_height, timing=None, fft_root_table=None, *,
-                    salt=None, ctx=None):
-        """from_values (oracle.rs:57-79). `timing`/`fft_root_table` are accepted for signature parity."""
-        return cls._create(values, rate_bits, blinding, cap_height, False, salt, ctx)
+                    salt=None, ctx=None, shard=(0, 1)):
+        """from_values (oracle.rs:57-79). `timing`/`fft_root_table` are accepted for signature parity.
+        shard=(g, G): build only leaf rows [g*N/G, (g+1)*N/G) on this device (multi-GPU row-block sharding)."""
+        return cls._create(values, rate_bits, blinding, cap_height, False, salt, ctx, shard)
 
     @classmethod
     def from_coeffs(cls, polynomials, rate_bits, blinding, cap_height, timing=None, fft_root_table=None, *,
-                    salt=None, ctx=None):
+                    salt=None, ctx=None, shard=(0, 1)):
         """from_coeffs (oracle.rs:82-112)."""
-        return cls._create(polynomials, rate_bits, blinding, cap_height, True, salt, ctx)
+        return cls._create(polynomials, rate_bits, blinding, cap_height, True, salt, ctx, shard)
 
     @property
     def polynomials(self):

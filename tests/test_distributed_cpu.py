@@ -1,0 +1,80 @@
+"""world_size-2 gloo test of the multi-GPU host logic (plonky2_b200/distributed.py) on CPU: each rank
+owns one row block of the commitment (its leaves/cap come from the oracle here, since there is no GPU),
+the ranks all-gather their cap entries, and every rank must end with the single-device cap."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+
+    import oracle_lib
+    from conftest import synth
+    from plonky2_b200 import distributed as D
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, log_n, r, h = 5, 6, 2, 3
+        N = 1 << (log_n + r)
+        vals = synth(0x55, (B, 1 << log_n))
+        full = oracle_lib.Commit(vals, r, h, nthreads=1)
+        lo, hi = D.shard_row_range(N, rank, world)
+        clo, chi = D.shard_cap_range(h, rank, world)
+        # this rank's shard: its own leaves reduced to its own cap entries
+        _, local_cap = oracle_lib.merkle_build(full.leaves[lo:hi], h - int(np.log2(world)), nthreads=1)
+        assert np.array_equal(local_cap, full.cap[clo:chi])
+        cap = D.gather_cap(local_cap)
+        ok = np.array_equal(cap.hashes, full.cap)
+        owner = D.owner_of_leaf(N - 1, N, world)
+        q.put((rank, bool(ok), owner))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cap_all_gather_two_ranks():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] for r in res)
+    assert all(r[2] == (1, 127) for r in res)
+
+
+def test_shard_ranges():
+    from plonky2_b200 import distributed as D
+
+    assert D.shard_row_range(1 << 10, 3, 8) == (384, 512)
+    assert D.shard_cap_range(4, 3, 8) == (6, 8)
+    with pytest.raises(ValueError):
+        D.shard_cap_range(2, 0, 8)
+    assert D.owner_of_leaf(700, 1024, 4) == (2, 188)
+    # single process: gather_cap is the identity
+    cap = np.arange(16, dtype=np.uint64).reshape(4, 4)
+    assert np.array_equal(D.gather_cap(cap).hashes, cap)

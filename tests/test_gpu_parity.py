@@ -338,3 +338,37 @@ def test_fri_pow_smallest_nonce(pb, oracle):
                 want = cand
                 break
         assert int(nonce[0]) == want
+
+
+# ----------------------------------------------------------------------------- row-block sharding
+@pytest.mark.parametrize("B,log_n,r,h,G", [(9, 8, 3, 4, 2), (9, 8, 3, 4, 8), (5, 10, 1, 4, 8), (5, 10, 1, 4, 16),
+                                           (3, 13, 1, 3, 4), (4, 2, 1, 3, 8), (6, 6, 0, 2, 4)])
+def test_sharded_commit_concatenates_to_single_device_commit(pb, oracle, B, log_n, r, h, G):
+    # every shard is built on this one GPU; concatenated shards must equal the single-device commitment
+    n, N = 1 << log_n, 1 << (log_n + r)
+    vals = synth(0x05 + G, (B, n))
+    salt = synth(0x06, (4, N)) if B == 9 else None
+    o = oracle.Commit(vals, r, h, salt=salt)
+    leaves, digests, caps = [], [], []
+    for g in range(G):
+        c = pb.PolynomialBatch.from_values(vals, r, salt is not None, h, salt=salt, shard=(g, G))
+        assert np.array_equal(c.polynomials, o.coeffs)
+        leaves.append(c.merkle_tree.leaves)
+        digests.append(c.merkle_tree.digests)
+        caps.append(c.merkle_tree.cap.hashes)
+        # a local opening verifies against the local cap with the local index
+        lv, paths = c.merkle_tree.open_many([0, c.local_rows - 1])
+        assert oracle.merkle_verify(lv[1], c.local_rows - 1, paths[1], caps[-1], h - int(np.log2(G)))
+        # and is the global opening of leaf g*rows + local
+        gi = g * c.local_rows + c.local_rows - 1
+        assert np.array_equal(lv[1], o.leaves[gi])
+        assert np.array_equal(paths[1], oracle.merkle_prove(gi, N, h, o.digests))
+        c.close()
+    assert np.array_equal(np.concatenate(leaves), o.leaves)
+    assert np.array_equal(np.concatenate(caps), o.cap)
+    assert np.array_equal(np.concatenate(digests), o.digests)
+
+
+def test_sharding_rejects_more_shards_than_cap_entries(pb):
+    with pytest.raises(ValueError):
+        pb.PolynomialBatch.from_values(synth(1, (2, 16)), 1, False, 1, shard=(0, 4))
