@@ -31,21 +31,86 @@ constexpr uint32_t TWO_ADICITY = 32;
 
 GL_HD uint64_t canon(uint64_t x) { return x >= P ? x - P : x; }
 
+#if defined(__CUDA_ARCH__)
+// ---- device formulations: 32-bit carry chains in PTX (ptxas spreads them over IADD3.X / IMAD.X) ----
+__device__ __forceinline__ uint32_t lo32(uint64_t v) { return (uint32_t)v; }
+__device__ __forceinline__ uint32_t hi32(uint64_t v) { return (uint32_t)(v >> 32); }
+__device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+#endif
+
 // a + b (mod p), any u64 inputs, result in [0, 2^64).
 GL_HD uint64_t add(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r0, r1;
+    asm("{\n\t.reg .u32 c, m;\n\t"
+        "add.cc.u32 %0, %2, %4;\n\t"
+        "addc.cc.u32 %1, %3, %5;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "neg.s32 m, c;\n\t"          // carry: += 2^64 mod p = 2^32 - 1
+        "add.cc.u32 %0, %0, m;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "addc.u32 c, 0, 0;\n\t"      // second carry: only if both inputs are non-canonical
+        "neg.s32 m, c;\n\t"
+        "add.cc.u32 %0, %0, m;\n\t"
+        "addc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+    return pack64(r0, r1);
+#else
     uint64_t s = a + b;
     // carry out of 2^64: add 2^64 mod p = EPS. A second carry is possible only when both inputs
     // are non-canonical (goldilocks_field.rs:245-267); handle it so any u64 pair is safe.
     uint64_t c = (s < a) ? EPS : 0;
     uint64_t t = s + c;
     return (t < c) ? t + EPS : t;
+#endif
+}
+// a + b (mod p) when b is CANONICAL (b < p): a single carry fix-up suffices
+// (Field64::add_canonical_u64, goldilocks_field.rs:200-205).
+GL_HD uint64_t add_canonical(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r0, r1;
+    asm("{\n\t.reg .u32 c, m;\n\t"
+        "add.cc.u32 %0, %2, %4;\n\t"
+        "addc.cc.u32 %1, %3, %5;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "neg.s32 m, c;\n\t"
+        "add.cc.u32 %0, %0, m;\n\t"
+        "addc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+    return pack64(r0, r1);
+#else
+    uint64_t s = a + b;
+    return (s < a) ? s + EPS : s;
+#endif
 }
 // a - b (mod p)
 GL_HD uint64_t sub(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r0, r1;
+    asm("{\n\t.reg .u32 m;\n\t"
+        "sub.cc.u32 %0, %2, %4;\n\t"
+        "subc.cc.u32 %1, %3, %5;\n\t"
+        "subc.u32 m, 0, 0;\n\t"      // 0xFFFFFFFF on borrow: -= 2^64 mod p
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"      // second borrow: only if b is non-canonical and a tiny
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+    return pack64(r0, r1);
+#else
     uint64_t d = a - b;
     uint64_t c = (a < b) ? EPS : 0;
     uint64_t t = d - c;
     return (d < c) ? t - EPS : t;
+#endif
 }
 GL_HD uint64_t neg(uint64_t a) {
     uint64_t c = canon(a);
@@ -55,6 +120,27 @@ GL_HD uint64_t neg(uint64_t a) {
 // Reduce hi*2^64 + lo (mod p) to [0, 2^64): lo - (hi >> 32) + (hi & EPS) * EPS
 // (the reference's reduce128, goldilocks_field.rs:401-415, re-expressed on 32-bit halves).
 GL_HD uint64_t reduce128(uint64_t lo, uint64_t hi) {
+#if defined(__CUDA_ARCH__)
+    // x = lo - hh (borrow b), r = x + hl*EPS (carry c); true value = r_wrapped + (c - b)*2^64, and
+    // 2^64 = EPS (mod p): apply the signed fix-up (c - b)*EPS in one 64-bit add (it cannot wrap).
+    uint32_t r0, r1;
+    asm("{\n\t.reg .u32 t0, t1, nb, d, f0, f1;\n\t"
+        "sub.cc.u32 t0, 0, %4;\n\t"        // t = hl * (2^32 - 1) = (hl << 32) - hl
+        "subc.u32 t1, %4, 0;\n\t"
+        "sub.cc.u32 %0, %2, %5;\n\t"       // x = lo - hh
+        "subc.cc.u32 %1, %3, 0;\n\t"
+        "subc.u32 nb, 0, 0;\n\t"           // -b
+        "add.cc.u32 %0, %0, t0;\n\t"       // r = x + t
+        "addc.cc.u32 %1, %1, t1;\n\t"
+        "addc.u32 d, nb, 0;\n\t"           // d = c - b in {-1, 0, 1}
+        "neg.s32 f0, d;\n\t"               // d*EPS = (d >> 31 : -d)
+        "shr.s32 f1, d, 31;\n\t"
+        "add.cc.u32 %0, %0, f0;\n\t"
+        "addc.u32 %1, %1, f1;\n\t}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(lo32(lo)), "r"(hi32(lo)), "r"(lo32(hi)), "r"(hi32(hi)));
+    return pack64(r0, r1);
+#else
     uint64_t hh = hi >> 32;
     uint64_t hl = hi & EPS;
     uint64_t t0 = lo - hh;
@@ -62,17 +148,38 @@ GL_HD uint64_t reduce128(uint64_t lo, uint64_t hi) {
     uint64_t t1 = (hl << 32) - hl;    // hl * (2^32 - 1)
     uint64_t r = t0 + t1;
     return (r < t1) ? r + EPS : r;    // carry: add 2^64 mod p (cannot carry again)
+#endif
 }
 // Reduce hi*2^64 + lo with hi < 2^32 (a "u96").
 GL_HD uint64_t reduce96(uint64_t lo, uint32_t hi) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r0, r1;
+    asm("{\n\t.reg .u32 t0, t1, c, m;\n\t"
+        "sub.cc.u32 t0, 0, %4;\n\t"
+        "subc.u32 t1, %4, 0;\n\t"
+        "add.cc.u32 %0, %2, t0;\n\t"
+        "addc.cc.u32 %1, %3, t1;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "neg.s32 m, c;\n\t"
+        "add.cc.u32 %0, %0, m;\n\t"
+        "addc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(lo32(lo)), "r"(hi32(lo)), "r"(hi));
+    return pack64(r0, r1);
+#else
     uint64_t t1 = ((uint64_t)hi << 32) - hi;
     uint64_t r = lo + t1;
     return (r < t1) ? r + EPS : r;
+#endif
 }
 
 // GL_FORCE_32BIT_PATH lets tests/emu run the device formulation on the host.
 GL_HD void mul_wide(uint64_t a, uint64_t b, uint64_t& lo, uint64_t& hi) {
-#if defined(__CUDA_ARCH__) || defined(GL_FORCE_32BIT_PATH)
+#if defined(__CUDA_ARCH__)
+    // ptxas turns this pair into 4 IMAD.WIDE.U32 (one with carry-out, one with carry-in) + 3 adds
+    lo = a * b;
+    hi = __umul64hi(a, b);
+#elif defined(GL_FORCE_32BIT_PATH)
     uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);
     uint32_t b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
     uint64_t p00 = (uint64_t)a0 * b0;
@@ -87,7 +194,9 @@ GL_HD void mul_wide(uint64_t a, uint64_t b, uint64_t& lo, uint64_t& hi) {
 #endif
 }
 GL_HD void sqr_wide(uint64_t a, uint64_t& lo, uint64_t& hi) {
-#if defined(__CUDA_ARCH__) || defined(GL_FORCE_32BIT_PATH)
+#if defined(__CUDA_ARCH__)
+    mul_wide(a, a, lo, hi);
+#elif defined(GL_FORCE_32BIT_PATH)
     uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);
     uint64_t p00 = (uint64_t)a0 * a0;
     uint64_t p01 = (uint64_t)a0 * a1;
@@ -116,9 +225,17 @@ GL_HD uint64_t sqr(uint64_t a) {
 GL_HD uint64_t mul_add(uint64_t a, uint64_t b, uint64_t c) {
     uint64_t lo, hi;
     mul_wide(a, b, lo, hi);
+#if defined(__CUDA_ARCH__)
+    uint32_t l0, l1, h0, h1;  // a*b + c < 2^128
+    asm("add.cc.u32 %0, %4, %6;\n\taddc.cc.u32 %1, %5, %7;\n\taddc.cc.u32 %2, %8, 0;\n\taddc.u32 %3, %9, 0;"
+        : "=&r"(l0), "=&r"(l1), "=&r"(h0), "=&r"(h1)
+        : "r"(lo32(lo)), "r"(hi32(lo)), "r"(lo32(c)), "r"(hi32(c)), "r"(lo32(hi)), "r"(hi32(hi)));
+    return reduce128(pack64(l0, l1), pack64(h0, h1));
+#else
     uint64_t l2 = lo + c;
     hi += (l2 < lo);  // a*b + c < 2^128
     return reduce128(l2, hi);
+#endif
 }
 
 // a * 2^k (mod p), 0 <= k < 96, using 2^64 = EPS, 2^96 = -1.

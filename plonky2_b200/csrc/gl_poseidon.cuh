@@ -111,7 +111,7 @@ GL_HD void mds_layer(uint64_t s[12]) {
 
 GL_HD void full_round(uint64_t s[12], const uint64_t* rc) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = sbox7(add(s[i], rc[i]));  // constant_layer + sbox_layer
+    for (int i = 0; i < 12; i++) s[i] = sbox7(add_canonical(s[i], rc[i]));  // constant_layer + sbox_layer
     mds_layer(s);
 }
 
@@ -123,7 +123,7 @@ GL_HD void poseidon_permute(uint64_t s[12]) {
 
     // partial_first_constant_layer + mds_partial_layer_init (poseidon.rs:413-441)
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = add(s[i], T.fast_first[i]);
+    for (int i = 0; i < 12; i++) s[i] = add_canonical(s[i], T.fast_first[i]);
     {
         uint64_t res[12];
         res[0] = s[0];
@@ -139,7 +139,7 @@ GL_HD void poseidon_permute(uint64_t s[12]) {
     }
 #pragma unroll 1
     for (int r = 0; r < 22; r++) {
-        uint64_t s0 = add(sbox7(s[0]), T.fast_rc[r]);
+        uint64_t s0 = add_canonical(sbox7(s[0]), T.fast_rc[r]);
         // mds_partial_layer_fast (poseidon.rs:514-542)
         Acc160 a = {0, 0, 0};
         acc_mul(a, s0, 17 + 8);
