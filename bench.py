@@ -64,12 +64,13 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------
 # reference arm: the CPU path (oracle port; the Rust reference cannot be built in this image)
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(args, cores, target_cpu_seconds=20.0):
+def cpu_sample(args, cores, target_cpu_seconds=8.0):
     """Bounded sample of the same workload for the CPU arm: same columns/rate/cap, fewer rows."""
-    # ~1.3 us of CPU per Poseidon permutation; perms per leaf = ceil(W/8) + 1
+    # ~5 us of CPU per Poseidon permutation in the port; perms per leaf = ceil(W/8) + 1. Size the sample
+    # for roughly target_cpu_seconds of wall time on `cores` threads (the transposes/NTTs add ~30%).
     perms_per_leaf = (args.cols + 7) // 8 + 1
     log_n = args.log_n
-    while log_n > 10 and (1 << (log_n + args.rate_bits)) * perms_per_leaf * 1.3e-6 > target_cpu_seconds * max(1, cores) / 4:
+    while log_n > 10 and (1 << (log_n + args.rate_bits)) * perms_per_leaf * 6.5e-6 / max(1, cores) > target_cpu_seconds:
         log_n -= 1
     return log_n
 

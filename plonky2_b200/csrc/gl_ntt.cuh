@@ -34,6 +34,11 @@ GL_HD constexpr int ntt_tile_threads(int log) {
     int n = ((1 << log) * ntt_tile_T(log)) / 16;
     return n < 32 ? 32 : (n > 1024 ? 1024 : n);
 }
+// resident CTAs per SM the kernels are compiled for (register cap = 65536 / (threads * blocks))
+GL_HD constexpr int ntt_tile_min_blocks(int log) {
+    int b = 1024 / ntt_tile_threads(log);
+    return b < 1 ? 1 : (b > 8 ? 8 : b);
+}
 GL_HD constexpr size_t ntt_tile_smem_bytes(int log) {
     // data tile + full-cycle twiddle table + mbarrier slot
     return ((size_t)(1 << log) * ntt_tile_TS(log) + (size_t)(1 << log)) * 8 + 16;

@@ -115,27 +115,26 @@ GL_HD void full_round(uint64_t s[12], const uint64_t* rc) {
     mds_layer(s);
 }
 
-// Poseidon::poseidon, poseidon.rs:766-777 (fast partial rounds, :751-764)
-GL_HD void poseidon_permute(uint64_t s[12]) {
+// partial_rounds, poseidon.rs:751-764 (fast form). Kept compact on purpose: the init matrix runs as a
+// rolled loop over output lanes (results staged in a small local array) and the 22 rounds as a rolled
+// loop, so that the whole permutation stays close to the instruction-cache size (the fully unrolled
+// form is ~9k instructions and stalls on instruction fetch).
+GL_HD void poseidon_partial_rounds(uint64_t s[12]) {
     const PoseidonTables& T = GL_POS;
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) full_round(s, &T.rc[12 * r]);
-
     // partial_first_constant_layer + mds_partial_layer_init (poseidon.rs:413-441)
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = add_canonical(s[i], T.fast_first[i]);
     {
-        uint64_t res[12];
-        res[0] = s[0];
-#pragma unroll
-        for (int c = 1; c < 12; c++) {
+        uint64_t res[11];
+#pragma unroll 1
+        for (int c = 0; c < 11; c++) {
             Acc160 a = {0, 0, 0};
 #pragma unroll
-            for (int r = 1; r < 12; r++) acc_mul(a, s[r], T.init[(r - 1) * 11 + (c - 1)]);
+            for (int r = 1; r < 12; r++) acc_mul(a, s[r], T.init[(r - 1) * 11 + c]);
             res[c] = acc_reduce(a);
         }
 #pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = res[i];
+        for (int i = 1; i < 12; i++) s[i] = res[i - 1];
     }
 #pragma unroll 1
     for (int r = 0; r < 22; r++) {
@@ -149,8 +148,17 @@ GL_HD void poseidon_permute(uint64_t s[12]) {
         for (int i = 1; i < 12; i++) s[i] = mul_add(s0, T.vs[r * 11 + i - 1], s[i]);
         s[0] = acc_reduce(a);
     }
+}
+
+// Poseidon::poseidon, poseidon.rs:766-777. One rolled loop over the 8 full rounds (a single copy of
+// the round body in the instruction stream), with the partial rounds run after the 4th.
+GL_HD void poseidon_permute(uint64_t s[12]) {
+    const PoseidonTables& T = GL_POS;
 #pragma unroll 1
-    for (int r = 0; r < 4; r++) full_round(s, &T.rc[12 * (26 + r)]);
+    for (int r = 0; r < 8; r++) {
+        full_round(s, &T.rc[12 * (r < 4 ? r : r + 22)]);
+        if (r == 3) poseidon_partial_rounds(s);
+    }
 }
 
 // compress / two_to_one (hashing.rs:97-114): state = [l, r, 0,0,0,0]; one permutation; lanes 0..3.

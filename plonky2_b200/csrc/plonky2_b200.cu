@@ -199,7 +199,7 @@ __device__ __forceinline__ void tma_table_wait(u64* mbar) {
 // NTT kernels
 // =====================================================================================
 template <int LOG>
-__global__ void __launch_bounds__(ntt_tile_threads(LOG)) k_passA(PassA pa) {
+__global__ void __launch_bounds__(ntt_tile_threads(LOG), ntt_tile_min_blocks(LOG)) k_passA(PassA pa) {
     extern __shared__ __align__(16) u64 smem[];
     u64* wt_s = smem;
     u64* s = smem + (1 << LOG);
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(ntt_tile_threads(LOG)) k_passA(PassA pa) {
 }
 
 template <int LOG, int MODE>
-__global__ void __launch_bounds__(ntt_tile_threads(LOG)) k_passB(PassB pb) {
+__global__ void __launch_bounds__(ntt_tile_threads(LOG), ntt_tile_min_blocks(LOG)) k_passB(PassB pb) {
     extern __shared__ __align__(16) u64 smem[];
     u64* wt_s = smem;
     u64* s = smem + (1 << LOG);
@@ -264,6 +264,8 @@ static int launch_passA(gl_ctx* ctx, const PassA& pa, int nblocks) {
     static bool attr_done = false;
     if (!attr_done) {
         CK(ctx, cudaFuncSetAttribute(k_passA<LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(ctx, cudaFuncSetAttribute(k_passA<LOG>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     k_passA<LOG><<<nblocks, ntt_tile_threads(LOG), smem, ctx->stream>>>(pa);
@@ -276,6 +278,8 @@ static int launch_passB(gl_ctx* ctx, const PassB& pb) {
     static bool attr_done = false;
     if (!attr_done) {
         CK(ctx, cudaFuncSetAttribute(k_passB<LOG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(ctx, cudaFuncSetAttribute(k_passB<LOG, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     const int nblocks = passB_blocks<LOG>(pb, MODE);

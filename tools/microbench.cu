@@ -96,6 +96,34 @@ __global__ void __launch_bounds__(128) k_poseidon(uint64_t* out, uint64_t a, int
     for (int r = 0; r < reps; r++) poseidon_permute(s);
     out[blockIdx.x * blockDim.x + threadIdx.x] = s[0];
 }
+// variant: big CTA, all warps kept in the same round by a barrier (instruction-cache locality)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_poseidon_sync(uint64_t* out, uint64_t a, int reps) {
+    uint64_t s[12];
+    for (int i = 0; i < 12; i++) s[i] = a * (threadIdx.x + blockIdx.x * 131 + i + 1);
+    const PoseidonTables& T = c_pos;
+    for (int r = 0; r < reps; r++) {
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) { full_round(s, &T.rc[12 * k]); __syncthreads(); }
+        poseidon_partial_rounds(s);
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) { full_round(s, &T.rc[12 * (26 + k)]); __syncthreads(); }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s[0];
+}
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_poseidon_plain(uint64_t* out, uint64_t a, int reps) {
+    uint64_t s[12];
+    for (int i = 0; i < 12; i++) s[i] = a * (threadIdx.x + blockIdx.x * 131 + i + 1);
+    for (int r = 0; r < reps; r++) poseidon_permute(s);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s[0];
+}
+__global__ void __launch_bounds__(128) k_partial(uint64_t* out, uint64_t a, int reps) {
+    uint64_t s[12];
+    for (int i = 0; i < 12; i++) s[i] = a * (threadIdx.x + blockIdx.x * 131 + i + 1);
+    for (int r = 0; r < reps; r++) poseidon_partial_rounds(s);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s[0];
+}
 __global__ void __launch_bounds__(128) k_fullround(uint64_t* out, uint64_t a, int reps) {
     uint64_t s[12];
     for (int i = 0; i < 12; i++) s[i] = a * (threadIdx.x + blockIdx.x * 131 + i + 1);
@@ -152,6 +180,18 @@ int main() {
     double perms = (double)pb * pt * reps;
     double ms = timeit([&] { k_poseidon<<<pb, pt>>>(out, 3, reps); });
     printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "poseidon_permute", ms, perms / ms / 1e3);
+    ms = timeit([&] { k_partial<<<pb, pt>>>(out, 3, reps); });
+    printf("%-26s %8.3f ms  %8.2f M partial-blocks/s\n", "partial rounds (22+init)", ms, perms / ms / 1e3);
+    ms = timeit([&] { k_poseidon_plain<256><<<pb / 2, 256>>>(out, 3, reps); });
+    printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "poseidon plain CTA=256", ms, perms / ms / 1e3);
+    ms = timeit([&] { k_poseidon_plain<512><<<pb / 4, 512>>>(out, 3, reps); });
+    printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "poseidon plain CTA=512", ms, perms / ms / 1e3);
+    ms = timeit([&] { k_poseidon_sync<256><<<pb / 2, 256>>>(out, 3, reps); });
+    printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "poseidon sync CTA=256", ms, perms / ms / 1e3);
+    ms = timeit([&] { k_poseidon_sync<512><<<pb / 4, 512>>>(out, 3, reps); });
+    printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "poseidon sync CTA=512", ms, perms / ms / 1e3);
+    ms = timeit([&] { k_poseidon_sync<768><<<pb / 6, 768>>>(out, 3, reps); });
+    printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "poseidon sync CTA=768", ms, perms * (pb / 6 * 6) / pb / ms / 1e3);
     ms = timeit([&] { k_fullround<<<pb, pt>>>(out, 3, reps * 8); });
     printf("%-26s %8.3f ms  %8.2f M full-rounds/s (x8 per perm => %.2f Mperm/s if only full rounds)\n", "full_round", ms,
            perms * 8 / ms / 1e3, perms / ms / 1e3);
