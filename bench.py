@@ -64,7 +64,7 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------
 # reference arm: the CPU path (oracle port; the Rust reference cannot be built in this image)
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(args, cores, target_cpu_seconds=8.0):
+def cpu_sample(args, cores, target_cpu_seconds=3.0):
     """Bounded sample of the same workload for the CPU arm: same columns/rate/cap, fewer rows."""
     # ~5 us of CPU per Poseidon permutation in the port; perms per leaf = ceil(W/8) + 1. Size the sample
     # for roughly target_cpu_seconds of wall time on `cores` threads (the transposes/NTTs add ~30%).

@@ -553,16 +553,17 @@ glo_commit* commit_new(const u64* cols, size_t col_stride, size_t B, uint32_t lo
     });
     if (salt)
         for (size_t s = 0; s < SALT_SIZE; s++) memcpy(lde.data() + (B + s) * N, salt + s * N, N * 8);
-    // "transpose LDEs": one row per LDE point
+    // "transpose LDEs" + reverse_index_bits_in_place(&mut leaves) (oracle.rs:97-98): the reference transposes
+    // into one Vec per LDE point and then permutes the Vec headers; writing row i straight to position
+    // bitrev(i) is the same permutation without moving W-word rows twice.
     c->leaves.resize(N * W);
+    const uint32_t lgN = log_n + rate_bits;
     parallel_for(N, nthreads, [&](size_t i) {
-        u64* row = c->leaves.data() + i * W;
+        u64* row = c->leaves.data() + (size_t)reverse_bits(i, lgN) * W;
         for (size_t b = 0; b < W; b++) row[b] = canon(lde[b * N + i]);
     });
     lde.clear();
     lde.shrink_to_fit();
-    // reverse_index_bits_in_place(&mut leaves)
-    reverse_index_bits_in_place(c->leaves.data(), N, W);
     // "build Merkle tree"
     size_t C = (size_t)1 << cap_height;
     c->digests.resize(2 * (N - C));

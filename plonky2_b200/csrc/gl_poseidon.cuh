@@ -22,6 +22,7 @@ struct PoseidonTables {
     uint64_t vs[22 * 11];
     uint64_t w_hats[22 * 11];
     uint64_t init[11 * 11];
+    uint64_t zeros[12];  // "no constants" block for the last round's folded constant layer
 };
 
 #if defined(__CUDACC__)
@@ -37,6 +38,7 @@ inline const PoseidonTables& host_poseidon_tables() {
         for (int i = 0; i < 242; i++) x.vs[i] = GL_POSEIDON_FAST_VS[i];
         for (int i = 0; i < 242; i++) x.w_hats[i] = GL_POSEIDON_FAST_W_HATS[i];
         for (int i = 0; i < 121; i++) x.init[i] = GL_POSEIDON_FAST_INIT_MATRIX[i];
+        for (int i = 0; i < 12; i++) x.zeros[i] = 0;
         return x;
     }();
     return t;
@@ -84,8 +86,10 @@ GL_HD uint64_t sbox7(uint64_t x) {  // sbox_monomial, poseidon.rs:689-696
     return mul(x3, x4);
 }
 
-// mds_layer (poseidon.rs:269-290; out[r] = sum_i s[(i+r)%12]*circ[i] + s[r]*diag[r]) on 32-bit halves.
-GL_HD void mds_layer(uint64_t s[12]) {
+// mds_layer (poseidon.rs:269-290; out[r] = sum_i s[(i+r)%12]*circ[i] + s[r]*diag[r]) on 32-bit halves,
+// FUSED with the constant layer that follows it (poseidon.rs:630-641): the accumulators start from the
+// next round's constants `nrc` (canonical u64s), so the constant addition costs nothing.
+GL_HD void mds_layer_add(uint64_t s[12], const uint64_t* nrc) {
     constexpr uint32_t CIRC[12] = GL_MDS_CIRC_LIST;
     uint32_t lo[12], hi[12];
 #pragma unroll
@@ -95,35 +99,52 @@ GL_HD void mds_layer(uint64_t s[12]) {
     }
 #pragma unroll
     for (int r = 0; r < 12; r++) {
-        uint64_t al = 0, ah = 0;
+        const uint64_t c = nrc[r];
+        uint64_t al = (uint32_t)c, ah = c >> 32;
 #pragma unroll
         for (int i = 0; i < 12; i++) {
-            uint32_t c = CIRC[i] + ((r == 0 && i == 0) ? 8u : 0u);  // diag = [8,0,...,0]
-            al += (uint64_t)lo[(i + r) % 12] * c;
-            ah += (uint64_t)hi[(i + r) % 12] * c;
+            uint32_t m = CIRC[i] + ((r == 0 && i == 0) ? 8u : 0u);  // diag = [8,0,...,0]
+            al += (uint64_t)lo[(i + r) % 12] * m;
+            ah += (uint64_t)hi[(i + r) % 12] * m;
         }
         // value = al + ah * 2^32, al,ah < 2^42  ->  96-bit (l64, h32)
+#if defined(__CUDA_ARCH__)
+        uint32_t r1, r2;
+        asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;"
+            : "=r"(r1), "=r"(r2)
+            : "r"(hi32(al)), "r"(lo32(ah)), "r"(hi32(ah)));
+        s[r] = reduce96(pack64(lo32(al), r1), r2);
+#else
         uint64_t l64 = al + (ah << 32);
         uint32_t h32 = (uint32_t)(ah >> 32) + (l64 < al ? 1u : 0u);
         s[r] = reduce96(l64, h32);
+#endif
     }
 }
+GL_HD void mds_layer(uint64_t s[12]) { mds_layer_add(s, GL_POS.zeros); }
 
+// One full round WITHOUT its own constant layer (already folded into the previous MDS / added by the
+// caller) but WITH the next round's: sbox_layer, then mds_layer + next constants.
+GL_HD void full_round_fused(uint64_t s[12], const uint64_t* next_rc) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
+    mds_layer_add(s, next_rc);
+}
+// Plain full round (constant_layer, sbox_layer, mds_layer; poseidon.rs:741-749) -- used by tools/microbench.
 GL_HD void full_round(uint64_t s[12], const uint64_t* rc) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = sbox7(add_canonical(s[i], rc[i]));  // constant_layer + sbox_layer
-    mds_layer(s);
+    for (int i = 0; i < 12; i++) s[i] = add_canonical(s[i], rc[i]);
+    full_round_fused(s, GL_POS.zeros);
 }
 
-// partial_rounds, poseidon.rs:751-764 (fast form). Kept compact on purpose: the init matrix runs as a
-// rolled loop over output lanes (results staged in a small local array) and the 22 rounds as a rolled
-// loop, so that the whole permutation stays close to the instruction-cache size (the fully unrolled
-// form is ~9k instructions and stalls on instruction fetch).
-GL_HD void poseidon_partial_rounds(uint64_t s[12]) {
+// partial_rounds, poseidon.rs:751-764 (fast form), minus partial_first_constant_layer which the caller
+// folds into the preceding MDS. Kept compact on purpose: the init matrix runs as a rolled loop over output
+// lanes (results staged in a small local array) and the 22 rounds as a rolled loop, so that the whole
+// permutation stays close to the instruction-cache size (the fully unrolled form is ~9k instructions and
+// stalls on instruction fetch).
+GL_HD void poseidon_partial_rounds_noconst(uint64_t s[12]) {
     const PoseidonTables& T = GL_POS;
-    // partial_first_constant_layer + mds_partial_layer_init (poseidon.rs:413-441)
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = add_canonical(s[i], T.fast_first[i]);
+    // mds_partial_layer_init (poseidon.rs:413-441)
     {
         uint64_t res[11];
 #pragma unroll 1
@@ -149,29 +170,53 @@ GL_HD void poseidon_partial_rounds(uint64_t s[12]) {
         s[0] = acc_reduce(a);
     }
 }
-
-// Poseidon::poseidon, poseidon.rs:766-777. One rolled loop over the 8 full rounds (a single copy of
-// the round body in the instruction stream), with the partial rounds run after the 4th.
-GL_HD void poseidon_permute(uint64_t s[12]) {
-    const PoseidonTables& T = GL_POS;
-#pragma unroll 1
-    for (int r = 0; r < 8; r++) {
-        full_round(s, &T.rc[12 * (r < 4 ? r : r + 22)]);
-        if (r == 3) poseidon_partial_rounds(s);
-    }
+GL_HD void poseidon_partial_rounds(uint64_t s[12]) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = add_canonical(s[i], GL_POS.fast_first[i]);
+    poseidon_partial_rounds_noconst(s);
 }
 
+// Poseidon::poseidon, poseidon.rs:766-777. One rolled loop over the 8 full rounds (a single copy of the
+// round body in the instruction stream); every constant layer except the first of each half is folded into
+// the preceding MDS. SYNC (device only): a CTA barrier per full round keeps all warps of the CTA in the same
+// round body, which improves instruction-cache locality (+10 % in tools/microbench); all threads of the CTA
+// must then call this the same number of times.
+template <bool SYNC = false>
+GL_HD void poseidon_permute_t(uint64_t s[12]) {
+    const PoseidonTables& T = GL_POS;
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = add_canonical(s[i], T.rc[i]);
+#pragma unroll 1
+    for (int r = 0; r < 8; r++) {
+        // constants that follow this round's MDS: next full round's, or the partial rounds' first layer,
+        // or nothing (after the partial rounds the 5th full round's constants are added explicitly)
+        const uint64_t* nrc = (r < 3) ? &T.rc[12 * (r + 1)] : (r == 3) ? T.fast_first
+                            : (r < 7) ? &T.rc[12 * (r + 23)] : T.zeros;
+        full_round_fused(s, nrc);
+#if defined(__CUDA_ARCH__)
+        if (SYNC) __syncthreads();
+#endif
+        if (r == 3) {
+            poseidon_partial_rounds_noconst(s);
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = add_canonical(s[i], T.rc[12 * 26 + i]);
+        }
+    }
+}
+GL_HD void poseidon_permute(uint64_t s[12]) { poseidon_permute_t<false>(s); }
+
 // compress / two_to_one (hashing.rs:97-114): state = [l, r, 0,0,0,0]; one permutation; lanes 0..3.
+template <bool SYNC = false>
 GL_HD void two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]) {
     uint64_t s[12] = {l[0], l[1], l[2], l[3], r[0], r[1], r[2], r[3], 0, 0, 0, 0};
-    poseidon_permute(s);
+    poseidon_permute_t<SYNC>(s);
 #pragma unroll
     for (int i = 0; i < 4; i++) out[i] = canon(s[i]);
 }
 
 // hash_or_noop over a strided leaf (config.rs:63-74 + hashing.rs:118-141, overwrite-mode sponge):
 // element k of the leaf is in[k * stride].
-template <bool NOOP_SHORT = true>
+template <bool NOOP_SHORT = true, bool SYNC = false>
 GL_HD void hash_or_noop_strided(const uint64_t* in, size_t stride, uint32_t W, uint64_t out[4]) {
     if (NOOP_SHORT && W <= 4) {
 #pragma unroll
@@ -185,7 +230,7 @@ GL_HD void hash_or_noop_strided(const uint64_t* in, size_t stride, uint32_t W, u
 #pragma unroll
         for (uint32_t i = 0; i < 8; i++)
             if (off + i < W) s[i] = in[(size_t)(off + i) * stride];
-        poseidon_permute(s);
+        poseidon_permute_t<SYNC>(s);
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) out[i] = canon(s[i]);

@@ -578,11 +578,14 @@ __host__ __device__ __forceinline__ size_t digest_pos(size_t q, uint32_t i) {
     return 2 * (((q >> 1) << (i + 1)) + ((size_t)1 << i) - 1) + (q & 1);
 }
 
-__global__ void __launch_bounds__(128) k_leaf_hash(TreeView t) {
+constexpr int HASH_CTA = 256;  // CTA size of the barrier-synchronised Poseidon kernels
+__global__ void __launch_bounds__(HASH_CTA) k_leaf_hash(TreeView t) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= t.N) return;
+    const bool live = j < t.N;
+    if (!live) j = t.N - 1;  // keep the whole CTA in the per-round barriers; the result is discarded
     u64 h[4];
-    hash_or_noop_strided(t.leaves + j * t.W, 1, t.W, h);
+    hash_or_noop_strided<true, true>(t.leaves + j * t.W, 1, t.W, h);
+    if (!live) return;
     u64* dst;
     const uint32_t sub_log = t.log_n - t.cap_height;  // log2(leaves per cap subtree)
     if (sub_log == 0) {
@@ -598,12 +601,13 @@ __global__ void __launch_bounds__(128) k_leaf_hash(TreeView t) {
     dst[3] = h[3];
 }
 // layer i (>= 1) from layer i-1: one thread per node
-__global__ void __launch_bounds__(128) k_merkle_level(TreeView t, uint32_t i) {
+__global__ void __launch_bounds__(HASH_CTA) k_merkle_level(TreeView t, uint32_t i) {
     const uint32_t sub_log = t.log_n - t.cap_height;
     const size_t nodes_per_sub = (size_t)1 << (sub_log - i);
     const size_t total = nodes_per_sub << t.cap_height;
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total) return;
+    const bool live = g < total;
+    if (!live) g = total - 1;
     const size_t c = g >> (sub_log - i), q = g & (nodes_per_sub - 1);
     const size_t L = (size_t)1 << sub_log;
     u64* sub = t.digests + 4 * (c * 2 * (L - 1));
@@ -611,7 +615,8 @@ __global__ void __launch_bounds__(128) k_merkle_level(TreeView t, uint32_t i) {
     u64 l[4] = {pair[0], pair[1], pair[2], pair[3]};
     u64 r[4] = {pair[4], pair[5], pair[6], pair[7]};
     u64 h[4];
-    two_to_one(l, r, h);
+    two_to_one<true>(l, r, h);
+    if (!live) return;
     u64* dst = (i == sub_log) ? (t.cap + 4 * c) : (sub + 4 * digest_pos(q, i));
     dst[0] = h[0];
     dst[1] = h[1];
@@ -685,14 +690,14 @@ static int tree_build(gl_ctx* ctx, Tree& t) {
     TreeView v = t.view();
     {
         PhaseScope ps(ctx, GL_PHASE_LEAF_HASH);
-        k_leaf_hash<<<(unsigned)((t.N + 127) / 128), 128, 0, ctx->stream>>>(v);
+        k_leaf_hash<<<(unsigned)((t.N + HASH_CTA - 1) / HASH_CTA), HASH_CTA, 0, ctx->stream>>>(v);
         CKL(ctx);
     }
     PhaseScope ps2(ctx, GL_PHASE_MERKLE_LEVELS);
     const uint32_t sub_log = t.log_n - t.cap_height;
     for (uint32_t i = 1; i <= sub_log; i++) {
         size_t total = (size_t)1 << (t.log_n - i);
-        k_merkle_level<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(v, i);
+        k_merkle_level<<<(unsigned)((total + HASH_CTA - 1) / HASH_CTA), HASH_CTA, 0, ctx->stream>>>(v, i);
         CKL(ctx);
     }
     return GL_OK;

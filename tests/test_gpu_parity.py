@@ -372,3 +372,56 @@ def test_sharded_commit_concatenates_to_single_device_commit(pb, oracle, B, log_
 def test_sharding_rejects_more_shards_than_cap_entries(pb):
     with pytest.raises(ValueError):
         pb.PolynomialBatch.from_values(synth(1, (2, 16)), 1, False, 1, shard=(0, 4))
+
+
+# ----------------------------------------------------------------------------- large shapes (BASELINE configs)
+@pytest.mark.parametrize("log_n", [17, 20, 22, 23, 24])
+def test_large_ntt_against_oracle_and_roundtrip(pb, oracle, log_n):
+    # exercises every tile size up to 2^12 x 2^12 (log_n = 24 is the per-transform maximum of this build)
+    n = 1 << log_n
+    x = synth(0x100 + log_n, (n,))
+    y = pb.fft(x)
+    assert np.array_equal(y, oracle.fft(x))
+    assert np.array_equal(pb.ifft(y), x)
+
+
+def test_ntt_rejects_sizes_beyond_the_build_limit(pb):
+    with pytest.raises(pb.NativeError):
+        pb.fft(np.zeros(1 << 25, dtype=np.uint64))
+
+
+def test_cfg3_merkle_2pow23_leaves_width12(pb, oracle):
+    # BASELINE.json configs[2]: Poseidon Merkle commitment of 2^23 leaves x width 12, cap bit-exact vs CPU
+    N, W, h = 1 << 23, 12, 4
+    leaves = synth(0x03, (N, W))
+    t = pb.MerkleTree(leaves, h)
+    d, cap = oracle.merkle_build(leaves, h)
+    assert np.array_equal(t.cap.hashes, cap)
+    idx = [0, 12345, N - 1]
+    lv, paths = t.open_many(idx)
+    for k, i in enumerate(idx):
+        assert np.array_equal(paths[k], oracle.merkle_prove(i, N, h, d))
+        assert oracle.merkle_verify(lv[k], i, paths[k], cap, h)
+    t.close()
+
+
+def test_cfg5_shape_reduced_starky_commit_and_fri(pb, oracle):
+    # starky standard_fast_config shape (rate_bits 1, cap 4, arity-16 rounds) at n = 2^16, 8 columns:
+    # commitment vs oracle, then the FRI commit phase + proof bytes vs oracle.
+    B, log_n, r, h = 8, 16, 1, 4
+    vals = synth(0x05, (B, 1 << log_n))
+    c = pb.PolynomialBatch.from_values(vals, r, False, h)
+    o = oracle.Commit(vals, r, h)
+    assert np.array_equal(c.merkle_tree.cap.hashes, o.cap)
+    cfg = pb.starky_standard_fast_fri_config()
+    params = cfg.fri_params(log_n, False)
+    assert params.reduction_arity_bits == [4, 4, 4]
+    zeta = (123456789, 987654321)
+    inst = _instance(pb, [B], zeta, pb.field.ext_mul(zeta, (pb.field.primitive_root_of_unity(log_n), 0)), [(0, 0)])
+    obatches = [(b.point, [(p.oracle_index, p.polynomial_index) for p in b.polynomials]) for b in inst.batches]
+    ch, och = pb.Challenger(), oracle.Challenger()
+    ch.observe_cap(c.merkle_tree.cap)
+    och.observe_cap(o.cap)
+    proof = pb.prove_openings(inst, [c], ch, params)
+    oproof = oracle.prove_openings([o], obatches, och, oracle.make_params(r, h, 16, 84, [4, 4, 4]))
+    assert proof.to_bytes() == oproof

@@ -101,14 +101,7 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_poseidon_sync(uint64_t* out, uint64_t a, int reps) {
     uint64_t s[12];
     for (int i = 0; i < 12; i++) s[i] = a * (threadIdx.x + blockIdx.x * 131 + i + 1);
-    const PoseidonTables& T = c_pos;
-    for (int r = 0; r < reps; r++) {
-#pragma unroll 1
-        for (int k = 0; k < 4; k++) { full_round(s, &T.rc[12 * k]); __syncthreads(); }
-        poseidon_partial_rounds(s);
-#pragma unroll 1
-        for (int k = 0; k < 4; k++) { full_round(s, &T.rc[12 * (26 + k)]); __syncthreads(); }
-    }
+    for (int r = 0; r < reps; r++) poseidon_permute_t<true>(s);
     out[blockIdx.x * blockDim.x + threadIdx.x] = s[0];
 }
 template <int THREADS>
