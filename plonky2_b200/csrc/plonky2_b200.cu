@@ -13,6 +13,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/plonky2_b200.h"
@@ -36,6 +37,8 @@ struct gl_ctx {
     std::string err;
     u64* wt[NTT_MAX_LOG_TILE + 1] = {nullptr};  // full-cycle in-tile tables, wt[log][j] = w_{2^log}^j
     std::map<int, u64*> twa;                    // pass-A twiddles by log_n
+    std::map<std::tuple<int, int, u64>, u64*> coset_tabs;  // LDE coset scale tables by (log_n, rate_bits, shift)
+    cudaStream_t copy_stream = nullptr;         // H2D of column chunks, overlapped with the NTTs of earlier chunks
     u64* scratch = nullptr;                     // NTT group scratch (device)
     size_t scratch_words = 0;
     u64* pinned = nullptr;                      // host staging for small D2H / H2D
@@ -495,16 +498,29 @@ static int lde_leaves(gl_ctx* ctx, const u64* coeffs, size_t coeff_stride, uint3
     ntt_split(log_n, a, b);
     const size_t R = (size_t)1 << a, C = (size_t)1 << b;
     const size_t cnt = R > C ? R : C;
-    // per-coset scale tables: [c][0] = (s_c^C)^i, [c][1] = s_c^i
-    std::vector<u64> bases;
-    const u64 wN = root_of_unity((uint32_t)(log_n + rate_bits));
-    for (int c = 0; c < ncos; c++) {
-        u64 s = mul(base_shift, gl::pow(wN, bitrev32((uint32_t)c, (uint32_t)rate_bits)));
-        bases.push_back(gl::pow(s, C));
-        bases.push_back(s);
-    }
+    // per-coset scale tables: [c][0] = (s_c^C)^i, [c][1] = s_c^i  (cached per context)
     u64* ctab;
-    TRY(build_pow_tables(ctx, bases, cnt, &ctab));
+    {
+        auto key = std::make_tuple(log_n, rate_bits, canon(base_shift));
+        auto it = ctx->coset_tabs.find(key);
+        if (it == ctx->coset_tabs.end()) {
+            std::vector<u64> bases;
+            const u64 wN = root_of_unity((uint32_t)(log_n + rate_bits));
+            for (int c = 0; c < ncos; c++) {
+                u64 s = mul(base_shift, gl::pow(wN, bitrev32((uint32_t)c, (uint32_t)rate_bits)));
+                bases.push_back(gl::pow(s, C));
+                bases.push_back(s);
+            }
+            TRY(build_pow_tables(ctx, bases, cnt, &ctab));
+            if (ctx->coset_tabs.size() > 64) {  // bound the cache
+                for (auto& kv : ctx->coset_tabs) dfree(ctx, kv.second);
+                ctx->coset_tabs.clear();
+            }
+            ctx->coset_tabs[key] = ctab;
+        } else {
+            ctab = it->second;
+        }
+    }
     const u64 *wta = nullptr, *wtb = nullptr, *twa = nullptr;
     if (b > 0) TRY(get_wt(ctx, b, &wtb));
     if (a > 0) {
@@ -550,7 +566,6 @@ static int lde_leaves(gl_ctx* ctx, const u64* coeffs, size_t coeff_stride, uint3
             TRY(dispatch_passB(ctx, b, PB_LEAVES, pb));
         }
     }
-    dfree(ctx, ctab);
     return GL_OK;
 }
 
@@ -771,27 +786,6 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
     const size_t n = (size_t)1 << c->degree_log, N = n << c->rate_bits;
     const uint32_t B = c->B;
     TRY(dmalloc(ctx, &c->coeffs, (size_t)B * n));
-    // inputs -> device coefficient buffer
-    if (mem == GL_MEM_HOST) {
-        if (col_stride == n) {
-            TRY(h2d(ctx, c->coeffs, cols, (size_t)B * n));
-        } else {
-            for (uint32_t b = 0; b < B; b++) TRY(h2d(ctx, c->coeffs + (size_t)b * n, cols + (size_t)b * col_stride, n));
-        }
-    } else {
-        CK(ctx, cudaMemcpy2DAsync(c->coeffs, n * 8, cols, col_stride * 8, n * 8, B, cudaMemcpyDeviceToDevice,
-                                  ctx->stream));
-    }
-    if (!is_coeffs) {
-        // "IFFT" (oracle.rs:65-69)
-        PhaseScope ps(ctx, GL_PHASE_INTT);
-        TRY(ntt_natural(ctx, c->coeffs, n, c->coeffs, n, (int)c->degree_log, B, true, 1));
-    } else {
-        size_t tot = (size_t)B * n;
-        k_canon<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(c->coeffs, tot);
-        CKL(ctx);
-    }
-    // "FFT + blinding" + "transpose LDEs" + bit-reversal, fused: leaf-major coset LDE
     // Row-block sharding: shard g of G = 2^s owns leaves [g*N/G, (g+1)*N/G), i.e. the
     // LDE points i = g' (mod G), g' = bitrev_s(g): the coset (g * w_N^{g'}) <w_{N/G}> in bit-reversed order.
     const uint32_t sl = c->shard_log;
@@ -805,35 +799,94 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
     t.cap_height = cap_height - sl;
     t.own_leaves = true;
     TRY(dmalloc(ctx, &t.leaves, Nloc * (size_t)c->W));
-    {
-        PhaseScope ps(ctx, GL_PHASE_LDE);
-        if (sl <= c->rate_bits) {
-            const uint32_t rloc = c->rate_bits - sl;
-            if (c->degree_log == 0) {
-                const int ncos = 1 << rloc;
-                k_lde_const<<<(B * ncos + 127) / 128, 128, 0, ctx->stream>>>(c->coeffs, n, B, ncos, t.leaves, c->W, 0);
-                CKL(ctx);
+
+    // Column chunks flow through  H2D copy -> iNTT ("IFFT", oracle.rs:65-69) -> leaf-major coset LDE
+    // ("FFT + blinding" + "transpose LDEs" + bit-reversal, fused); the copy of chunk k+1 (separate stream)
+    // overlaps the transforms of chunk k.
+    const uint32_t CH = 16;
+    const bool overlap = (mem == GL_MEM_HOST) && B > CH;
+    std::vector<cudaEvent_t> evs;
+    if (overlap) {
+        if (!ctx->copy_stream) CK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        cudaEvent_t ready;
+        CK(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        CK(ctx, cudaEventRecord(ready, ctx->stream));  // the stream-ordered allocations above
+        CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
+        cudaEventDestroy(ready);
+        for (uint32_t g0 = 0; g0 < B; g0 += CH) {
+            const uint32_t gc = (B - g0 < CH) ? B - g0 : CH;
+            if (col_stride == n) {
+                CK(ctx, cudaMemcpyAsync(c->coeffs + (size_t)g0 * n, cols + (size_t)g0 * n, (size_t)gc * n * 8,
+                                        cudaMemcpyHostToDevice, ctx->copy_stream));
             } else {
-                TRY(lde_leaves(ctx, c->coeffs, n, B, (int)c->degree_log, (int)rloc, sg, t.leaves, c->W, 0));
+                CK(ctx, cudaMemcpy2DAsync(c->coeffs + (size_t)g0 * n, n * 8, cols + (size_t)g0 * col_stride,
+                                          col_stride * 8, n * 8, gc, cudaMemcpyHostToDevice, ctx->copy_stream));
             }
-        } else {
-            // fewer than n points per shard: restrict the polynomials to the sub-coset first
-            const uint32_t logM = c->degree_log + c->rate_bits - sl;
-            const size_t M = (size_t)1 << logM;
-            u64* folded;
-            TRY(dmalloc(ctx, &folded, (size_t)B * M));
-            k_fold_coeffs<<<dim3((unsigned)((M + 127) / 128), B), 128, 0, ctx->stream>>>(c->coeffs, n, n, M,
-                                                                                       gl::pow(sg, M), folded);
-            CKL(ctx);
-            if (logM == 0) {
-                k_lde_const<<<(B + 127) / 128, 128, 0, ctx->stream>>>(folded, 1, B, 1, t.leaves, c->W, 0);
-                CKL(ctx);
-            } else {
-                TRY(lde_leaves(ctx, folded, M, B, (int)logM, 0, sg, t.leaves, c->W, 0));
-            }
-            dfree(ctx, folded);
+            cudaEvent_t e;
+            CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            CK(ctx, cudaEventRecord(e, ctx->copy_stream));
+            evs.push_back(e);
         }
+    } else if (mem == GL_MEM_HOST) {
+        if (col_stride == n) {
+            TRY(h2d(ctx, c->coeffs, cols, (size_t)B * n));
+        } else {
+            for (uint32_t b = 0; b < B; b++) TRY(h2d(ctx, c->coeffs + (size_t)b * n, cols + (size_t)b * col_stride, n));
+        }
+    } else {
+        CK(ctx, cudaMemcpy2DAsync(c->coeffs, n * 8, cols, col_stride * 8, n * 8, B, cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
     }
+    const uint32_t step = overlap ? CH : B;
+    int rc_loop = GL_OK;
+    for (uint32_t g0 = 0, k = 0; g0 < B && rc_loop == GL_OK; g0 += step, k++) {
+        const uint32_t gc = (B - g0 < step) ? B - g0 : step;
+        u64* cg = c->coeffs + (size_t)g0 * n;
+        if (overlap) cudaStreamWaitEvent(ctx->stream, evs[k], 0);
+        auto chunk = [&]() -> int {
+            if (!is_coeffs) {
+                PhaseScope ps(ctx, GL_PHASE_INTT);
+                TRY(ntt_natural(ctx, cg, n, cg, n, (int)c->degree_log, gc, true, 1));
+            } else {
+                size_t tot = (size_t)gc * n;
+                k_canon<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(cg, tot);
+                CKL(ctx);
+            }
+            PhaseScope ps(ctx, GL_PHASE_LDE);
+            if (sl <= c->rate_bits) {
+                const uint32_t rloc = c->rate_bits - sl;
+                if (c->degree_log == 0) {
+                    const int ncos = 1 << rloc;
+                    k_lde_const<<<(gc * ncos + 127) / 128, 128, 0, ctx->stream>>>(cg, n, gc, ncos, t.leaves, c->W, (int)g0);
+                    CKL(ctx);
+                } else {
+                    TRY(lde_leaves(ctx, cg, n, gc, (int)c->degree_log, (int)rloc, sg, t.leaves, c->W, (int)g0));
+                }
+            } else {
+                // fewer than n points per shard: restrict the polynomials to the sub-coset first
+                const uint32_t logM = c->degree_log + c->rate_bits - sl;
+                const size_t M = (size_t)1 << logM;
+                u64* folded;
+                TRY(dmalloc(ctx, &folded, (size_t)gc * M));
+                k_fold_coeffs<<<dim3((unsigned)((M + 127) / 128), gc), 128, 0, ctx->stream>>>(cg, n, n, M, gl::pow(sg, M),
+                                                                                            folded);
+                CKL(ctx);
+                int rc2 = GL_OK;
+                if (logM == 0) {
+                    k_lde_const<<<(gc + 127) / 128, 128, 0, ctx->stream>>>(folded, 1, gc, 1, t.leaves, c->W, (int)g0);
+                    ctx->launches++;
+                } else {
+                    rc2 = lde_leaves(ctx, folded, M, gc, (int)logM, 0, sg, t.leaves, c->W, (int)g0);
+                }
+                dfree(ctx, folded);
+                TRY(rc2);
+            }
+            return GL_OK;
+        };
+        rc_loop = chunk();
+    }
+    for (auto e : evs) cudaEventDestroy(e);
+    TRY(rc_loop);
     if (salt) {
         u64* dsalt = nullptr;
         const u64* sp = salt;
@@ -1148,6 +1201,8 @@ void gl_ctx_destroy(gl_ctx* ctx) {
     for (auto& w : ctx->wt)
         if (w) cudaFree(w);
     for (auto& kv : ctx->twa) cudaFree(kv.second);
+    for (auto& kv : ctx->coset_tabs) cudaFreeAsync(kv.second, ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->scratch) cudaFreeAsync(ctx->scratch, ctx->stream);
     if (ctx->dstage) cudaFreeAsync(ctx->dstage, ctx->stream);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
