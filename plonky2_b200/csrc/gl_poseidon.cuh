@@ -23,6 +23,12 @@ struct PoseidonTables {
     uint64_t w_hats[22 * 11];
     uint64_t init[11 * 11];
     uint64_t zeros[12];  // "no constants" block for the last round's folded constant layer
+    // MDS first row (poseidon_goldilocks.rs:24) read from the constant bank ON PURPOSE: as literals the
+    // compiler strength-reduces x2 / x16 / x18 ... into shift+add sequences on the (bottleneck) ALU pipe;
+    // as constant-bank operands every term is one IMAD.WIDE.U32 on the FMA pipe.
+    uint32_t mds_circ[12];
+    uint32_t mds_00;  // circ[0] + diag[0]
+    uint32_t pad_;
 };
 
 #if defined(__CUDACC__)
@@ -39,6 +45,9 @@ inline const PoseidonTables& host_poseidon_tables() {
         for (int i = 0; i < 242; i++) x.w_hats[i] = GL_POSEIDON_FAST_W_HATS[i];
         for (int i = 0; i < 121; i++) x.init[i] = GL_POSEIDON_FAST_INIT_MATRIX[i];
         for (int i = 0; i < 12; i++) x.zeros[i] = 0;
+        for (int i = 0; i < 12; i++) x.mds_circ[i] = (uint32_t)GL_POSEIDON_MDS_CIRC[i];
+        x.mds_00 = (uint32_t)(GL_POSEIDON_MDS_CIRC[0] + GL_POSEIDON_MDS_DIAG[0]);
+        x.pad_ = 0;
         return x;
     }();
     return t;
@@ -90,7 +99,7 @@ GL_HD uint64_t sbox7(uint64_t x) {  // sbox_monomial, poseidon.rs:689-696
 // FUSED with the constant layer that follows it (poseidon.rs:630-641): the accumulators start from the
 // next round's constants `nrc` (canonical u64s), so the constant addition costs nothing.
 GL_HD void mds_layer_add(uint64_t s[12], const uint64_t* nrc) {
-    constexpr uint32_t CIRC[12] = GL_MDS_CIRC_LIST;
+    const PoseidonTables& T = GL_POS;
     uint32_t lo[12], hi[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) {
@@ -103,9 +112,15 @@ GL_HD void mds_layer_add(uint64_t s[12], const uint64_t* nrc) {
         uint64_t al = (uint32_t)c, ah = c >> 32;
 #pragma unroll
         for (int i = 0; i < 12; i++) {
-            uint32_t m = CIRC[i] + ((r == 0 && i == 0) ? 8u : 0u);  // diag = [8,0,...,0]
+            const uint32_t m = (r == 0 && i == 0) ? T.mds_00 : T.mds_circ[i];  // diag = [8,0,...,0]
+#if defined(__CUDA_ARCH__)
+            // explicit mad.wide: the C form makes nvcc emit an extra (zero) high-word add per term
+            asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(al) : "r"(lo[(i + r) % 12]), "r"(m));
+            asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(ah) : "r"(hi[(i + r) % 12]), "r"(m));
+#else
             al += (uint64_t)lo[(i + r) % 12] * m;
             ah += (uint64_t)hi[(i + r) % 12] * m;
+#endif
         }
         // value = al + ah * 2^32, al,ah < 2^42  ->  96-bit (l64, h32)
 #if defined(__CUDA_ARCH__)
@@ -162,7 +177,7 @@ GL_HD void poseidon_partial_rounds_noconst(uint64_t s[12]) {
         uint64_t s0 = add_canonical(sbox7(s[0]), T.fast_rc[r]);
         // mds_partial_layer_fast (poseidon.rs:514-542)
         Acc160 a = {0, 0, 0};
-        acc_mul(a, s0, 17 + 8);
+        acc_mul(a, s0, T.mds_00);
 #pragma unroll
         for (int i = 1; i < 12; i++) acc_mul(a, s[i], T.w_hats[r * 11 + i - 1]);
 #pragma unroll

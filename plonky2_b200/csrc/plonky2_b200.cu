@@ -38,6 +38,7 @@ struct gl_ctx {
     u64* wt[NTT_MAX_LOG_TILE + 1] = {nullptr};  // full-cycle in-tile tables, wt[log][j] = w_{2^log}^j
     std::map<int, u64*> twa;                    // pass-A twiddles by log_n
     std::map<std::tuple<int, int, u64>, u64*> coset_tabs;  // LDE coset scale tables by (log_n, rate_bits, shift)
+    std::map<int, u64*> fold_tabs;              // FRI fold tables (w_N^-1 powers, hi | lo) by log N
     cudaStream_t copy_stream = nullptr;         // H2D of column chunks, overlapped with the NTTs of earlier chunks
     u64* scratch = nullptr;                     // NTT group scratch (device)
     size_t scratch_words = 0;
@@ -593,7 +594,7 @@ __host__ __device__ __forceinline__ size_t digest_pos(size_t q, uint32_t i) {
     return 2 * (((q >> 1) << (i + 1)) + ((size_t)1 << i) - 1) + (q & 1);
 }
 
-constexpr int HASH_CTA = 256;  // CTA size of the barrier-synchronised Poseidon kernels
+constexpr int HASH_CTA = 512;  // CTA size of the barrier-synchronised Poseidon kernels
 __global__ void __launch_bounds__(HASH_CTA) k_leaf_hash(TreeView t) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = j < t.N;
@@ -705,14 +706,17 @@ static int tree_build(gl_ctx* ctx, Tree& t) {
     TreeView v = t.view();
     {
         PhaseScope ps(ctx, GL_PHASE_LEAF_HASH);
-        k_leaf_hash<<<(unsigned)((t.N + HASH_CTA - 1) / HASH_CTA), HASH_CTA, 0, ctx->stream>>>(v);
+        // big CTAs (barrier-synchronised rounds) for big trees; small CTAs to spread small trees over the SMs
+        const int cta = t.N >= (size_t)148 * HASH_CTA * 4 ? HASH_CTA : 128;
+        k_leaf_hash<<<(unsigned)((t.N + cta - 1) / cta), cta, 0, ctx->stream>>>(v);
         CKL(ctx);
     }
     PhaseScope ps2(ctx, GL_PHASE_MERKLE_LEVELS);
     const uint32_t sub_log = t.log_n - t.cap_height;
     for (uint32_t i = 1; i <= sub_log; i++) {
         size_t total = (size_t)1 << (t.log_n - i);
-        k_merkle_level<<<(unsigned)((total + HASH_CTA - 1) / HASH_CTA), HASH_CTA, 0, ctx->stream>>>(v, i);
+        const int cta = total >= (size_t)148 * HASH_CTA * 4 ? HASH_CTA : 128;
+        k_merkle_level<<<(unsigned)((total + cta - 1) / cta), cta, 0, ctx->stream>>>(v, i);
         CKL(ctx);
     }
     return GL_OK;
@@ -1202,6 +1206,7 @@ void gl_ctx_destroy(gl_ctx* ctx) {
         if (w) cudaFree(w);
     for (auto& kv : ctx->twa) cudaFree(kv.second);
     for (auto& kv : ctx->coset_tabs) cudaFreeAsync(kv.second, ctx->stream);
+    for (auto& kv : ctx->fold_tabs) cudaFreeAsync(kv.second, ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->scratch) cudaFreeAsync(ctx->scratch, ctx->stream);
     if (ctx->dstage) cudaFreeAsync(ctx->dstage, ctx->stream);
@@ -1659,10 +1664,18 @@ int gl_fri_fold(gl_fri* f, const uint64_t beta[2]) {
     fp.log_leaves = f->log_cur - ab;
     const u64 wN = root_of_unity(f->log_cur);
     const u64 winv = gl::inv(wN);
-    const size_t hi_cnt = (leaves >> 12) + 1;
+    const size_t hi_cnt = ((size_t)1 << (f->log_cur > 12 ? f->log_cur - 12 : 0)) + 1;  // covers any arity
     const size_t tcnt = hi_cnt > 4096 ? hi_cnt : 4096;
     u64* tabs;
-    TRY(build_pow_tables(ctx, std::vector<u64>{gl::pow(winv, 4096), winv}, tcnt, &tabs));
+    {
+        auto it = ctx->fold_tabs.find((int)f->log_cur);
+        if (it == ctx->fold_tabs.end()) {
+            TRY(build_pow_tables(ctx, std::vector<u64>{gl::pow(winv, 4096), winv}, tcnt, &tabs));
+            ctx->fold_tabs[(int)f->log_cur] = tabs;
+        } else {
+            tabs = it->second;
+        }
+    }
     fp.winv_hi = tabs;
     fp.winv_lo = tabs + tcnt;
     fp.shift_inv = gl::inv(f->shift);
@@ -1680,7 +1693,6 @@ int gl_fri_fold(gl_fri* f, const uint64_t beta[2]) {
         case 5: k_fri_fold<5><<<nb, 128, 0, ctx->stream>>>(fp); break;
     }
     CKL(ctx);
-    dfree(ctx, tabs);
     f->values = out;
     f->log_cur -= ab;
     f->shift = gl::pow(f->shift, (u64)1 << ab);  // shift = shift.exp_u64(arity), prover.rs:118
@@ -1730,14 +1742,18 @@ int gl_fri_pow(gl_ctx* ctx, const uint64_t state[12], uint32_t pos, uint32_t min
     for (int i = 0; i < 12; i++) pp.state[i] = canon(state[i]);
     pp.pos = pos;
     pp.min_lz = min_leading_zeros;
-    const u64 BATCH = (u64)1 << 22;
+    // batches grow geometrically from ~2x the expected number of tries so that an easy grind costs one
+    // small launch; candidates are scanned in increasing order, so the first hit batch holds the minimum.
+    u64 batch = (u64)2 << (min_leading_zeros < 24 ? min_leading_zeros : 24);
+    if (batch < 4096) batch = 4096;
     int rc = GL_OK;
     u64 found = ~0ULL;
-    for (u64 start = 0; start < P; start += BATCH) {
+    for (u64 start = 0; start < P; start += batch, batch = batch < ((u64)1 << 24) ? batch * 4 : batch) {
         CK(ctx, cudaMemsetAsync(dres, 0xFF, 8, ctx->stream));
         pp.start = start;
-        pp.count = (P - start < BATCH) ? P - start : BATCH;
-        k_fri_pow<<<148 * 8, 128, 0, ctx->stream>>>(pp, dres);
+        pp.count = (P - start < batch) ? P - start : batch;
+        const unsigned nb = (unsigned)((pp.count + 127) / 128 < 148 * 8 ? (pp.count + 127) / 128 : 148 * 8);
+        k_fri_pow<<<nb, 128, 0, ctx->stream>>>(pp, dres);
         CKL(ctx);
         rc = d2h(ctx, &found, (u64*)dres, 1);
         if (rc != GL_OK || found != ~0ULL) break;
