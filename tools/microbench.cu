@@ -46,6 +46,18 @@ __global__ void k_add64(uint64_t* out, uint64_t a) {
     for (int i = 0; i < ILP; i++) s += acc[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+__global__ void k_dfma(uint64_t* out, double a) {
+    double acc[ILP];
+    for (int i = 0; i < ILP; i++) acc[i] = threadIdx.x + i;
+    double x = a + threadIdx.x;
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++) acc[i] = fma(acc[i], x, 1.0 + i);
+    }
+    double s = 0;
+    for (int i = 0; i < ILP; i++) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (uint64_t)s;
+}
 __global__ void k_modmul(uint64_t* out, uint64_t a) {
     uint64_t acc[ILP];
     for (int i = 0; i < ILP; i++) acc[i] = a * (threadIdx.x + i + 1);
@@ -165,6 +177,7 @@ int main() {
     rep("IMAD.WIDE.U32 (64b acc)", timeit([&] { k_imad_wide<<<blocks, threads>>>(out, 3, 5); }), nops);
     rep("IMAD 32-bit", timeit([&] { k_imad32<<<blocks, threads>>>(out, 3, 5); }), nops);
     rep("add64 (+xor)", timeit([&] { k_add64<<<blocks, threads>>>(out, 3); }), nops);
+    rep("DFMA (fp64 pipe)", timeit([&] { k_dfma<<<blocks, threads>>>(out, 1.0000001); }), nops);
     rep("gl::mul", timeit([&] { k_modmul<<<blocks, threads>>>(out, 3); }), nops);
     rep("gl::sqr", timeit([&] { k_modsqr<<<blocks, threads>>>(out, 3); }), nops);
     rep("gl::add", timeit([&] { k_modadd<<<blocks, threads>>>(out, 3); }), nops);
