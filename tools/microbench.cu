@@ -116,6 +116,13 @@ __global__ void __launch_bounds__(THREADS) k_poseidon_sync(uint64_t* out, uint64
     for (int r = 0; r < reps; r++) poseidon_permute_t<true>(s);
     out[blockIdx.x * blockDim.x + threadIdx.x] = s[0];
 }
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_poseidon_sync_occ(uint64_t* out, uint64_t a, int reps) {
+    uint64_t s[12];
+    for (int i = 0; i < 12; i++) s[i] = a * (threadIdx.x + blockIdx.x * 131 + i + 1);
+    for (int r = 0; r < reps; r++) poseidon_permute_t<true>(s);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s[0];
+}
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_poseidon_plain(uint64_t* out, uint64_t a, int reps) {
     uint64_t s[12];
@@ -198,6 +205,14 @@ int main() {
     printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "poseidon sync CTA=512", ms, perms / ms / 1e3);
     ms = timeit([&] { k_poseidon_sync<768><<<pb / 6, 768>>>(out, 3, reps); });
     printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "poseidon sync CTA=768", ms, perms * (pb / 6 * 6) / pb / ms / 1e3);
+    ms = timeit([&] { k_poseidon_sync_occ<256, 4><<<pb / 2, 256>>>(out, 3, reps); });
+    printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "sync CTA=256 minb=4 (64r)", ms, perms / ms / 1e3);
+    ms = timeit([&] { k_poseidon_sync_occ<512, 2><<<pb / 4, 512>>>(out, 3, reps); });
+    printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "sync CTA=512 minb=2 (64r)", ms, perms / ms / 1e3);
+    ms = timeit([&] { k_poseidon_sync_occ<256, 3><<<pb / 2, 256>>>(out, 3, reps); });
+    printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "sync CTA=256 minb=3 (80r)", ms, perms / ms / 1e3);
+    ms = timeit([&] { k_poseidon_sync_occ<128, 5><<<pb, 128>>>(out, 3, reps); });
+    printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "sync CTA=128 minb=5 (96r)", ms, perms / ms / 1e3);
     ms = timeit([&] { k_fullround<<<pb, pt>>>(out, 3, reps * 8); });
     printf("%-26s %8.3f ms  %8.2f M full-rounds/s (x8 per perm => %.2f Mperm/s if only full rounds)\n", "full_round", ms,
            perms * 8 / ms / 1e3, perms / ms / 1e3);
