@@ -304,11 +304,18 @@ def gpu_arm(args, rank, local_rank, world):
     leaf_avg = leaf_ms / max(1, leaf_cnt)
     leaf_bytes = 8.0 * N_loc * B + 32.0 * N_loc
     perms = N_loc * ((B + 7) // 8 if B > 4 else 0)
+    traffic, traffic_note = None, None
+    try:  # DRAM bytes per launch from the committed ncu --set full capture (scaled by the algorithmic bytes)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["k_leaf_hash"]
+        traffic = tr["dram_bytes_per_algorithmic_byte"] * leaf_bytes
+        traffic_note = "ncu dram read+write per algorithmic byte x this launch's algorithmic bytes; " + tr["source"]
+    except Exception:
+        pass
     roof = {
         "kernel": "k_leaf_hash (Poseidon sponge over each LDE row)", "bound": "hbm",
         "achieved": leaf_bytes / (leaf_avg * 1e-3) / 1e9 if leaf_avg else None, "peak": peak, "unit": "GB/s",
         "frac": (leaf_bytes / (leaf_avg * 1e-3) / 1e9 / peak) if leaf_avg else None,
-        "traffic": None, "peak_source": peak_src, "avg_ms": leaf_avg, "launches": leaf_cnt,
+        "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "avg_ms": leaf_avg, "launches": leaf_cnt,
         "algorithmic_bytes": leaf_bytes,
         "permutations_per_s": perms / (leaf_avg * 1e-3) if leaf_avg else None,
         "note": "integer-issue bound (x^7 S-boxes + MDS in IMAD/IADD3), not HBM bound: see DESIGN.md",
