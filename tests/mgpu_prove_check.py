@@ -1,0 +1,63 @@
+"""Multi-GPU end-to-end check (run under torchrun, one rank per GPU):
+sharded commitments -> NCCL all-gather of caps -> prove_openings with routed initial-tree openings.
+Rank 0 compares caps and the proof bytes with the CPU oracle. Launched by tests/test_gpu_parity.py when the
+box has >= 2 GPUs, or by hand:  gpurun --gpus 2 -- python -m torch.distributed.run --nproc-per-node 2 ... this file
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import plonky2_b200 as pb
+from conftest import synth
+from plonky2_b200 import distributed as D
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = pb.default_context(local)
+    log_n, r, h = 10, 3, 4
+    Bs = [7, 5, 3]
+    vals = [synth(0x60 + i, (B, 1 << log_n)) for i, B in enumerate(Bs)]
+    commits = [pb.PolynomialBatch.from_values(v, r, False, h, ctx=ctx, shard=(rank, world)) for v in vals]
+    dev = torch.device("cuda", local)
+    caps = [D.gather_cap(c.merkle_tree.cap, device=dev) for c in commits]
+    ch = pb.Challenger()
+    for cap in caps:
+        ch.observe_cap(cap)
+    zeta = (1234567, 7654321)
+    gz = pb.field.ext_mul(zeta, (pb.field.primitive_root_of_unity(log_n), 0))
+    allp = [pb.FriPolynomialInfo(o, i) for o, B in enumerate(Bs) for i in range(B)]
+    inst = pb.FriInstanceInfo([pb.FriOracleInfo(B, False) for B in Bs],
+                              [pb.FriBatchInfo(zeta, allp), pb.FriBatchInfo(gz, [pb.FriPolynomialInfo(2, 0)])])
+    params = pb.FriParams(pb.FriConfig(r, h, 8, ("Fixed", [4, 2]), 12), False, log_n, [4, 2])
+    proof = D.prove_openings_sharded(inst, commits, ch, params)
+    ok = True
+    if rank == 0:
+        import oracle_lib
+
+        ocommits = [oracle_lib.Commit(v, r, h) for v in vals]
+        for cap, o in zip(caps, ocommits):
+            ok &= bool(np.array_equal(cap.hashes, o.cap))
+        och = oracle_lib.Challenger()
+        for o in ocommits:
+            och.observe_cap(o.cap)
+        obatches = [(b.point, [(p.oracle_index, p.polynomial_index) for p in b.polynomials]) for b in inst.batches]
+        oproof = oracle_lib.prove_openings(ocommits, obatches, och, oracle_lib.make_params(r, h, 8, 12, [4, 2]))
+        ok &= proof.to_bytes() == oproof
+        print("MGPU_PROVE_CHECK", "OK" if ok else "FAILED", "world", world, flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -78,3 +78,25 @@ def test_shard_ranges():
     # single process: gather_cap is the identity
     cap = np.arange(16, dtype=np.uint64).reshape(4, 4)
     assert np.array_equal(D.gather_cap(cap).hashes, cap)
+
+
+def test_open_sharded_routing_single_process():
+    """Routing logic of open_sharded with a fake local batch (no GPU): owned indices are opened locally with
+    the local index; an index owned by another shard makes the single-process call fail loudly."""
+    from plonky2_b200 import distributed as D
+
+    class FakeTree:
+        def open_many(self, idx):
+            idx = list(idx)
+            return (np.array([[100 + i, 7] for i in idx], dtype=np.uint64).reshape(len(idx), 2),
+                    np.zeros((len(idx), 3, 4), dtype=np.uint64))
+
+    class FakeBatch:
+        num_shards, shard_index, lde_size, leaf_width = 2, 1, 64, 2
+        degree_log, rate_bits, cap_height = 5, 1, 3
+        merkle_tree = FakeTree()
+
+    lv, pt = D.open_sharded(FakeBatch(), [32, 63])   # both owned by shard 1 -> local 0 and 31
+    assert lv[:, 0].tolist() == [100, 131] and pt.shape == (2, 3, 4)
+    with pytest.raises(RuntimeError):
+        D.open_sharded(FakeBatch(), [5])             # owned by shard 0, nobody serves it here

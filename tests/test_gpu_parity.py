@@ -425,3 +425,20 @@ def test_cfg5_shape_reduced_starky_commit_and_fri(pb, oracle):
     proof = pb.prove_openings(inst, [c], ch, params)
     oproof = oracle.prove_openings([o], obatches, och, oracle.make_params(r, h, 16, 84, [4, 4, 4]))
     assert proof.to_bytes() == oproof
+
+
+def test_multi_gpu_sharded_prove(pb):
+    """Needs >= 2 GPUs (skipped on the single-GPU test box): torchrun, one rank per GPU, NCCL cap all-gather,
+    routed openings; rank 0 checks caps and proof bytes against the CPU oracle."""
+    import subprocess
+    import sys
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_prove_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MGPU_PROVE_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
