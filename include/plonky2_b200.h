@@ -122,6 +122,10 @@ int gl_commit_get_lde_values(gl_commit* c, size_t index, size_t step, uint64_t* 
  * out_leaves = count x W, out_paths = count x (log N - cap_height) x 4, siblings bottom-up. Host out. */
 int gl_commit_open(gl_commit* c, const uint64_t* leaf_indices, size_t count, uint64_t* out_leaves,
                    uint64_t* out_paths);
+/* eval_commitment of OpeningSet::new (plonky2/src/plonk/proof.rs:313-351): every polynomial of the batch
+ * evaluated at one point z of F_{p^2}: out = B x 2 words (host). First "next" row of SURVEY section 8(f):
+ * it keeps the coefficient D2H off the prover's critical path. */
+int gl_commit_eval_ext(gl_commit* c, const uint64_t point[2], uint64_t* out);
 /* device views (valid until destroy; for device-resident pipelines and benchmarks) */
 const uint64_t* gl_commit_dev_leaves(const gl_commit* c);
 const uint64_t* gl_commit_dev_coeffs(const gl_commit* c);

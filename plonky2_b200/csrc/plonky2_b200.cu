@@ -1115,6 +1115,41 @@ __global__ void k_interleave(const u64* cols, size_t n, size_t count, u64* out) 
     out[2 * i] = cols[i];
     out[2 * i + 1] = cols[n + i];
 }
+// ---- openings at a point (OpeningSet::new's eval_commitment, plonk/proof.rs:313-351) ----
+// zt[k] = z^k (F_{p^2}) for k < n, from factored tables
+__global__ void k_e2_pow_table(const u64* zhi, const u64* zlo, size_t n, u64* zt) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    E2 v = e2_pow_tab(zhi, zlo, k);
+    zt[2 * k] = canon(v.a);
+    zt[2 * k + 1] = canon(v.b);
+}
+// out[b] = sum_k coeffs[b][k] * z^k : one CTA per polynomial, 160-bit lazy accumulators, one reduction per thread
+__global__ void __launch_bounds__(256) k_eval_ext(const u64* coeffs, size_t stride, size_t n, const u64* zt, u64* out) {
+    __shared__ u64 sh[2 * 256];
+    const u64* col = coeffs + (size_t)blockIdx.x * stride;
+    Acc160 a0 = {0, 0, 0}, a1 = {0, 0, 0};
+    for (size_t k = threadIdx.x; k < n; k += blockDim.x) {
+        const u64 c = col[k];
+        acc_mul(a0, c, zt[2 * k]);
+        acc_mul(a1, c, zt[2 * k + 1]);
+    }
+    sh[2 * threadIdx.x] = acc_reduce(a0);
+    sh[2 * threadIdx.x + 1] = acc_reduce(a1);
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) {
+            sh[2 * threadIdx.x] = add(sh[2 * threadIdx.x], sh[2 * (threadIdx.x + off)]);
+            sh[2 * threadIdx.x + 1] = add(sh[2 * threadIdx.x + 1], sh[2 * (threadIdx.x + off) + 1]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[2 * blockIdx.x] = canon(sh[0]);
+        out[2 * blockIdx.x + 1] = canon(sh[1]);
+    }
+}
+
 // proof-of-work grind (prover.rs:183-194): smallest qualifying nonce via atomicMin
 struct PowParams {
     u64 state[12];
@@ -1367,6 +1402,36 @@ int gl_commit_shard(const gl_commit* c, uint32_t* shard_index, uint32_t* num_sha
 }
 int gl_commit_open(gl_commit* c, const uint64_t* leaf_indices, size_t count, uint64_t* out_leaves, uint64_t* out_paths) {
     return tree_open(c->ctx, c->tree, leaf_indices, count, out_leaves, out_paths);
+}
+int gl_commit_eval_ext(gl_commit* c, const uint64_t point[2], uint64_t* out) {
+    gl_ctx* ctx = c->ctx;
+    if (!point || !out) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)1 << c->degree_log;
+    const E2 z = {canon(point[0]), canon(point[1])};
+    const size_t hi_cnt = (n >> 12) + 1;
+    u64 *zhi = nullptr, *zlo = nullptr, *zt = nullptr, *dout = nullptr;
+    auto body = [&]() -> int {
+        TRY(dmalloc(ctx, &zhi, 2 * hi_cnt));
+        TRY(dmalloc(ctx, &zlo, 2 * 4096));
+        TRY(dmalloc(ctx, &zt, 2 * n));
+        TRY(dmalloc(ctx, &dout, 2 * (size_t)c->B));
+        k_fill_e2_pows<<<(unsigned)((hi_cnt + 127) / 128), 128, 0, ctx->stream>>>(e2_pow(z, 4096), hi_cnt, zhi);
+        CKL(ctx);
+        k_fill_e2_pows<<<32, 128, 0, ctx->stream>>>(z, 4096, zlo);
+        CKL(ctx);
+        k_e2_pow_table<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(zhi, zlo, n, zt);
+        CKL(ctx);
+        k_eval_ext<<<c->B, 256, 0, ctx->stream>>>(c->coeffs, n, n, zt, dout);
+        CKL(ctx);
+        return d2h(ctx, out, dout, 2 * (size_t)c->B);
+    };
+    int rc = body();
+    dfree(ctx, zhi);
+    dfree(ctx, zlo);
+    dfree(ctx, zt);
+    dfree(ctx, dout);
+    return rc;
 }
 const uint64_t* gl_commit_dev_leaves(const gl_commit* c) { return c->tree.leaves; }
 const uint64_t* gl_commit_dev_coeffs(const gl_commit* c) { return c->coeffs; }

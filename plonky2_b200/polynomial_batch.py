@@ -128,6 +128,14 @@ class PolynomialBatch:
         N.check(N.lib().gl_commit_get_lde_values(self.h, index, step, N.np_ptr(out)), self.ctx.h)
         return out
 
+    def eval_commitment(self, z):
+        """eval_commitment of OpeningSet::new (plonk/proof.rs:313-351): every polynomial at z in F_{p^2};
+        returns (num_polys, 2)."""
+        pt = np.array([int(z[0]), int(z[1])], dtype=np.uint64)
+        out = np.empty((self.num_polys, 2), dtype=np.uint64)
+        N.check(N.lib().gl_commit_eval_ext(self.h, N.np_ptr(pt), N.np_ptr(out)), self.ctx.h)
+        return out
+
     @staticmethod
     def prove_openings(instance, oracles, challenger, fri_params, final_poly_coeff_len=None,
                        max_num_query_steps=None, timing=None):

@@ -442,3 +442,15 @@ def test_multi_gpu_sharded_prove(pb):
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_prove_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MGPU_PROVE_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("B,log_n", [(3, 0), (5, 1), (7, 9), (20, 13), (4, 16)])
+def test_eval_commitment_at_extension_point(pb, oracle, B, log_n):
+    # OpeningSet::new's eval_commitment (plonk/proof.rs:313-351) vs Horner evaluation on the CPU
+    vals = synth(0xE0 + B, (B, 1 << log_n))
+    c = pb.PolynomialBatch.from_values(vals, 1, False, 0)
+    coeffs = c.polynomials
+    for z in [(0, 0), (1, 0), (5, 7), (int(synth(0xE1, (1,))[0]), int(synth(0xE2, (1,))[0]))]:
+        got = c.eval_commitment(z)
+        for b in range(B):
+            assert tuple(int(x) for x in got[b]) == oracle.eval_poly_base_at_ext(coeffs[b], z)
