@@ -130,6 +130,16 @@ int gl_commit_eval_ext(gl_commit* c, const uint64_t point[2], uint64_t* out);
 const uint64_t* gl_commit_dev_leaves(const gl_commit* c);
 const uint64_t* gl_commit_dev_coeffs(const gl_commit* c);
 
+/* ---- "next" rows ------------------------------------------------------------------ */
+/* wires_permutation_partial_products_and_zs (plonky2/src/plonk/prover.rs:387-449, util/partial_products.rs:13-37):
+ * wires, sigmas = num_routed columns of n = 2^log_n values (column-major); k_is = num_routed host words;
+ * out = (ceil(num_routed/degree)) columns of n values: the partial products, then Z LAST (the function's
+ * return order). Produces the second commitment's input on the device. Fails with GL_ERR_BAD_ARG
+ * ("Tried to invert zero") where the reference's batch_multiplicative_inverse panics. */
+int gl_partial_products_and_zs(gl_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, const uint64_t* k_is,
+                               uint32_t log_n, uint32_t num_routed, uint64_t beta, uint64_t gamma, uint32_t degree,
+                               uint64_t* out, int mem);
+
 /* ---- Hasher / MerkleTree  (plonky2/src/plonk/config.rs:36-77, plonky2/src/hash/merkle_tree.rs:193-237) */
 /* PoseidonPermutation::permute on the HOST for the sequential Fiat-Shamir transcript
  * (plonky2/src/iop/challenger.rs:129-144); the same source as the device permutation. */

@@ -794,6 +794,43 @@ size_t glo_challenger_state(const glo_challenger* c, uint64_t state[12], uint64_
 
 void glo_free(void* p) { free(p); }
 
+// wires_permutation_partial_products_and_zs, plonk/prover.rs:387-449
+int glo_partial_products_and_zs(const uint64_t* wires, const uint64_t* sigmas, const uint64_t* k_is, uint32_t log_n,
+                                uint32_t num_routed, uint64_t beta, uint64_t gamma, uint32_t degree, uint64_t* out) {
+    const size_t n = (size_t)1 << log_n;
+    const size_t num_chunks = (num_routed + degree - 1) / degree;  // quotient_chunk_products length
+    const size_t num_prods = num_chunks - 1;                        // num_partial_products, partial_products.rs:40-47
+    // subgroup = two_adic_subgroup(degree_bits)
+    const u64 w = primitive_root_of_unity(log_n);
+    u64 x = 1, z_x = 1;
+    std::vector<u64> q(num_routed), chunkp(num_chunks);
+    for (size_t i = 0; i < n; i++) {
+        for (uint32_t j = 0; j < num_routed; j++) {
+            u64 wire = wires[(size_t)j * n + i];
+            u64 num = fadd(fadd(wire, fmul(beta, fmul(k_is[j], x))), gamma);
+            u64 den = fadd(fadd(wire, fmul(beta, sigmas[(size_t)j * n + i])), gamma);
+            if (canon(den) == 0) return 1;
+            q[j] = fmul(num, finv(den));
+        }
+        // quotient_chunk_products, partial_products.rs:13-24
+        for (size_t m = 0; m < num_chunks; m++) {
+            u64 p = 1;
+            for (size_t j = m * degree; j < std::min<size_t>((m + 1) * degree, num_routed); j++) p = fmul(p, q[j]);
+            chunkp[m] = p;
+        }
+        // partial_products_and_z_gx, partial_products.rs:28-37, then swap(z_x, last)
+        u64 acc = z_x;
+        for (size_t m = 0; m < num_chunks; m++) {
+            acc = fmul(acc, chunkp[m]);
+            if (m < num_prods) out[m * n + i] = canon(acc);
+        }
+        out[num_prods * n + i] = canon(z_x);  // the last slot holds Z(x), not Z(gx)
+        z_x = acc;
+        x = fmul(x, w);
+    }
+    return 0;
+}
+
 void glo_eval_poly_base_at_ext(const uint64_t* coeffs, size_t n, const uint64_t z[2], uint64_t out[2]) {
     E2 zz{z[0], z[1]}, acc = e2(0);
     for (size_t k = n; k-- > 0;) acc = eadd(emul(acc, zz), e2(coeffs[k]));

@@ -154,6 +154,16 @@ int glo_verify_fri_proof(const uint64_t* const* initial_caps, const size_t* orac
                          glo_challenger* challenger, const glo_fri_params* params,
                          const uint8_t* proof, size_t proof_len);
 
+/* ---- "next" row: wires_permutation_partial_products_and_zs
+ *      (plonky2/src/plonk/prover.rs:387-449, util/partial_products.rs:13-37) ----
+ * wires, sigmas: num_routed columns of n values, column-major (wire_values[col][row]; sigma polynomial values).
+ * out: (num_prods + 1) columns of n values, column-major, partial products first and Z LAST (the function's
+ * return order; the prover then moves Z to the front, prover.rs:227-232). Returns 0, or 1 on a zero denominator
+ * (the reference's batch_multiplicative_inverse panics). */
+int glo_partial_products_and_zs(const uint64_t* wires, const uint64_t* sigmas, const uint64_t* k_is,
+                                uint32_t log_n, uint32_t num_routed, uint64_t beta, uint64_t gamma,
+                                uint32_t degree, uint64_t* out);
+
 /* polynomial evaluation helper for the verifier test: f(z) for base coeffs, z in F_{p^2} */
 void glo_eval_poly_base_at_ext(const uint64_t* coeffs, size_t n, const uint64_t z[2], uint64_t out[2]);
 

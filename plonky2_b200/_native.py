@@ -24,7 +24,7 @@ EXPORTS = [
     "gl_commit_create", "gl_commit_create_sharded", "gl_commit_shard", "gl_commit_destroy", "gl_commit_num_polys",
     "gl_commit_leaf_width", "gl_commit_degree_log", "gl_commit_rate_bits", "gl_commit_cap_height",
     "gl_commit_cap", "gl_commit_coeffs", "gl_commit_leaves", "gl_commit_digests", "gl_commit_get_lde_values",
-    "gl_commit_open", "gl_commit_eval_ext", "gl_commit_dev_leaves", "gl_commit_dev_coeffs", "gl_poseidon_permute_host",
+    "gl_commit_open", "gl_commit_eval_ext", "gl_commit_dev_leaves", "gl_commit_dev_coeffs", "gl_partial_products_and_zs", "gl_poseidon_permute_host",
     "gl_poseidon_hash_many", "gl_poseidon_hash_no_pad_many", "gl_poseidon_two_to_one_many", "gl_merkle_build", "gl_merkle_destroy",
     "gl_merkle_cap", "gl_merkle_digests", "gl_merkle_open", "gl_fri_begin", "gl_fri_begin_from_coeffs",
     "gl_fri_destroy", "gl_fri_coeffs", "gl_fri_commit_round", "gl_fri_fold", "gl_fri_final_poly",
@@ -92,6 +92,8 @@ def lib():
     L.gl_commit_dev_leaves.restype = vp
     L.gl_commit_dev_coeffs.argtypes = [vp]
     L.gl_commit_dev_coeffs.restype = vp
+    L.gl_partial_products_and_zs.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64,
+                                             C.c_uint32, vp, C.c_int]
     L.gl_poseidon_permute_host.argtypes = [vp]
     L.gl_poseidon_permute_host.restype = None
     L.gl_poseidon_hash_many.argtypes = [vp, vp, C.c_size_t, C.c_uint32, vp, C.c_int]

@@ -1150,6 +1150,108 @@ __global__ void __launch_bounds__(256) k_eval_ext(const u64* coeffs, size_t stri
     }
 }
 
+// ---- Z and partial products (wires_permutation_partial_products_and_zs, plonk/prover.rs:387-449;
+//      SURVEY 8(f) row 3). Per (row i, chunk m): c = prod_{j in chunk} (w + beta*k_j*x_i + gamma) /
+//      (w + beta*sigma + gamma); then ONE running product over the row-major sequence (i, m).
+struct PPParams {
+    const u64 *wires, *sigmas, *k_is;
+    size_t n;
+    uint32_t log_n, num_routed, degree, num_chunks;
+    u64 beta, gamma, omega;
+    u64* seq;            // n * num_chunks chunk products, row-major
+    unsigned int* flag;  // set when a denominator is zero
+};
+__global__ void __launch_bounds__(128) k_pp_chunks(PPParams p) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.n * p.num_chunks) return;
+    const size_t m = g / p.n, i = g % p.n;  // consecutive threads -> consecutive rows: coalesced column reads
+    const u64 bx = mul(p.beta, gl::pow(p.omega, i));
+    u64 num = 1, den = 1;
+    const uint32_t j1 = min((uint32_t)((m + 1) * p.degree), p.num_routed);
+    for (uint32_t j = (uint32_t)(m * p.degree); j < j1; j++) {
+        const u64 w = p.wires[(size_t)j * p.n + i];
+        const u64 wg = add(w, p.gamma);
+        num = mul(num, add(wg, mul(bx, p.k_is[j])));
+        den = mul(den, add(wg, mul(p.beta, p.sigmas[(size_t)j * p.n + i])));
+    }
+    if (canon(den) == 0) atomicOr(p.flag, 1u);
+    p.seq[i * p.num_chunks + m] = mul(num, gl::inv(den));
+}
+// multiplicative inclusive prefix scan, 3 phases
+__global__ void __launch_bounds__(SCAN_THREADS) k_mscan_phase1(const u64* seq, size_t L, u64* chunk_tot) {
+    __shared__ u64 sh[SCAN_THREADS];
+    const size_t base = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * SCAN_ITEMS;
+    u64 t = 1;
+    for (int k = 0; k < SCAN_ITEMS; k++)
+        if (base + k < L) t = mul(t, seq[base + k]);
+    sh[threadIdx.x] = t;
+    __syncthreads();
+    for (int off = SCAN_THREADS / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] = mul(sh[threadIdx.x], sh[threadIdx.x + off]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) chunk_tot[blockIdx.x] = sh[0];
+}
+// exclusive prefix products of the chunk totals, one CTA: each thread owns a contiguous run
+__global__ void __launch_bounds__(1024) k_mscan_phase2(u64* chunk_tot, size_t nchunks) {
+    __shared__ u64 sh[1024];
+    const size_t per = (nchunks + 1023) / 1024;
+    const size_t lo = (size_t)threadIdx.x * per, hi = lo + per < nchunks ? lo + per : nchunks;
+    u64 t = 1;
+    for (size_t k = lo; k < hi; k++) t = mul(t, chunk_tot[k]);
+    sh[threadIdx.x] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {  // 1024 sequential multiplies
+        u64 run = 1;
+        for (int k = 0; k < 1024; k++) {
+            u64 v = sh[k];
+            sh[k] = run;
+            run = mul(run, v);
+        }
+    }
+    __syncthreads();
+    u64 run = sh[threadIdx.x];
+    for (size_t k = lo; k < hi; k++) {
+        u64 v = chunk_tot[k];
+        chunk_tot[k] = run;
+        run = mul(run, v);
+    }
+}
+// phase 3: inclusive products inside each chunk; scatter to the output columns:
+// acc(i, m) -> partial product column m (m < M-1) at row i, or Z at row i+1 (m == M-1); Z(0) = 1.
+__global__ void __launch_bounds__(SCAN_THREADS) k_mscan_phase3(const u64* seq, size_t L, const u64* chunk_carry, size_t n,
+                                                             uint32_t M, u64* out) {
+    __shared__ u64 sh[SCAN_THREADS];
+    const size_t base = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * SCAN_ITEMS;
+    u64 loc[SCAN_ITEMS];
+    u64 run = 1;
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < L) run = mul(run, seq[base + k]);
+        loc[k] = run;
+    }
+    sh[threadIdx.x] = run;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 r = chunk_carry[blockIdx.x];
+        for (int t = 0; t < SCAN_THREADS; t++) {
+            u64 v = sh[t];
+            sh[t] = r;
+            r = mul(r, v);
+        }
+    }
+    __syncthreads();
+    const u64 carry = sh[threadIdx.x];
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const size_t t = base + k;
+        if (t >= L) break;
+        const u64 acc = canon(mul(carry, loc[k]));
+        const size_t i = t / M, m = t % M;
+        if (m + 1 < M) out[m * n + i] = acc;
+        else if (i + 1 < n) out[(size_t)(M - 1) * n + i + 1] = acc;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[(size_t)(M - 1) * n] = 1;
+}
+
 // proof-of-work grind (prover.rs:183-194): smallest qualifying nonce via atomicMin
 struct PowParams {
     u64 state[12];
@@ -1435,6 +1537,62 @@ int gl_commit_eval_ext(gl_commit* c, const uint64_t point[2], uint64_t* out) {
 }
 const uint64_t* gl_commit_dev_leaves(const gl_commit* c) { return c->tree.leaves; }
 const uint64_t* gl_commit_dev_coeffs(const gl_commit* c) { return c->coeffs; }
+
+int gl_partial_products_and_zs(gl_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, const uint64_t* k_is,
+                               uint32_t log_n, uint32_t num_routed, uint64_t beta, uint64_t gamma, uint32_t degree,
+                               uint64_t* out, int mem) {
+    if (!ctx || !wires || !sigmas || !k_is || !out) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
+    if (degree < 2 || num_routed == 0 || log_n > 26) return set_err(ctx, GL_ERR_BAD_SHAPE, "bad partial-product shape");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)1 << log_n;
+    const uint32_t M = (num_routed + degree - 1) / degree;
+    const size_t L = n * M, nchunks = (L + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    u64 *dw = nullptr, *ds = nullptr, *dk = nullptr, *seq = nullptr, *tot = nullptr, *dout = nullptr, *dflag = nullptr;
+    auto body = [&]() -> int {
+        const u64 *pw = wires, *ps = sigmas;
+        if (mem == GL_MEM_HOST) {
+            TRY(dmalloc(ctx, &dw, (size_t)num_routed * n));
+            TRY(dmalloc(ctx, &ds, (size_t)num_routed * n));
+            TRY(h2d(ctx, dw, wires, (size_t)num_routed * n));
+            TRY(h2d(ctx, ds, sigmas, (size_t)num_routed * n));
+            pw = dw;
+            ps = ds;
+            TRY(dmalloc(ctx, &dout, (size_t)M * n));
+        } else {
+            dout = out;
+        }
+        TRY(dmalloc(ctx, &dk, num_routed));
+        TRY(h2d(ctx, dk, k_is, num_routed));  // k_is is a small host array in both modes
+        TRY(dmalloc(ctx, &seq, L));
+        TRY(dmalloc(ctx, &tot, nchunks));
+        TRY(dmalloc(ctx, &dflag, 1));
+        CK(ctx, cudaMemsetAsync(dflag, 0, 8, ctx->stream));
+        PPParams pp{pw, ps, dk, n, log_n, num_routed, degree, M, canon(beta), canon(gamma), root_of_unity(log_n), seq,
+                    (unsigned int*)dflag};
+        k_pp_chunks<<<(unsigned)((L + 127) / 128), 128, 0, ctx->stream>>>(pp);
+        CKL(ctx);
+        k_mscan_phase1<<<(unsigned)nchunks, SCAN_THREADS, 0, ctx->stream>>>(seq, L, tot);
+        CKL(ctx);
+        k_mscan_phase2<<<1, 1024, 0, ctx->stream>>>(tot, nchunks);
+        CKL(ctx);
+        k_mscan_phase3<<<(unsigned)nchunks, SCAN_THREADS, 0, ctx->stream>>>(seq, L, tot, n, M, dout);
+        CKL(ctx);
+        u64 flag = 0;
+        TRY(d2h(ctx, &flag, dflag, 1));
+        if (flag & 0xFFFFFFFFu) return set_err(ctx, GL_ERR_BAD_ARG, "Tried to invert zero");
+        if (mem == GL_MEM_HOST) TRY(d2h(ctx, out, dout, (size_t)M * n));
+        return GL_OK;
+    };
+    int rc = body();
+    dfree(ctx, dw);
+    dfree(ctx, ds);
+    dfree(ctx, dk);
+    dfree(ctx, seq);
+    dfree(ctx, tot);
+    dfree(ctx, dflag);
+    if (mem == GL_MEM_HOST) dfree(ctx, dout);
+    return rc;
+}
 
 void gl_poseidon_permute_host(uint64_t state[12]) {
     poseidon_permute(state);

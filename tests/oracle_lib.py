@@ -121,6 +121,8 @@ def lib():
                                        C.c_size_t, C.POINTER(FriBatch), C.c_size_t, u64p, C.c_uint32,
                                        C.c_void_p, C.POINTER(FriParams), C.POINTER(C.c_uint8), C.c_size_t]
     L.glo_eval_poly_base_at_ext.argtypes = [u64p, C.c_size_t, u64p, u64p]
+    L.glo_partial_products_and_zs.restype = C.c_int
+    L.glo_partial_products_and_zs.argtypes = [u64p, u64p, u64p, C.c_uint32, C.c_uint32, u64, u64, C.c_uint32, u64p]
     _lib = L
     return L
 
@@ -400,3 +402,18 @@ def eval_poly_base_at_ext(coeffs, z):
     out = np.zeros(2, dtype=np.uint64)
     lib().glo_eval_poly_base_at_ext(ptr(coeffs), len(coeffs), ptr(zz), ptr(out))
     return (int(out[0]), int(out[1]))
+
+
+def partial_products_and_zs(wires, sigmas, k_is, beta, gamma, degree):
+    """wires, sigmas: (num_routed, n). Returns (num_prods + 1, n): partial products then Z."""
+    wires = np.ascontiguousarray(wires, dtype=np.uint64)
+    sigmas = np.ascontiguousarray(sigmas, dtype=np.uint64)
+    k_is = np.ascontiguousarray(k_is, dtype=np.uint64)
+    R, n = wires.shape
+    chunks = (R + degree - 1) // degree
+    out = np.zeros((chunks, n), dtype=np.uint64)
+    rc = lib().glo_partial_products_and_zs(ptr(wires), ptr(sigmas), ptr(k_is), int(np.log2(n)), R, int(beta),
+                                           int(gamma), degree, ptr(out))
+    if rc != 0:
+        raise ZeroDivisionError("Tried to invert zero")
+    return out

@@ -454,3 +454,30 @@ def test_eval_commitment_at_extension_point(pb, oracle, B, log_n):
         got = c.eval_commitment(z)
         for b in range(B):
             assert tuple(int(x) for x in got[b]) == oracle.eval_poly_base_at_ext(coeffs[b], z)
+
+
+@pytest.mark.parametrize("R,log_n,deg", [(13, 4, 4), (80, 10, 8), (80, 14, 8), (5, 0, 2), (9, 12, 3)])
+def test_partial_products_and_zs(pb, oracle, R, log_n, deg):
+    # wires_permutation_partial_products_and_zs (plonk/prover.rs:387-449) vs the oracle restatement
+    from plonky2_b200.prover import wires_permutation_partial_products_and_zs as gpu_pp
+
+    n = 1 << log_n
+    w, sg, k = synth(0xF0 + R, (R, n)), synth(0xF1 + R, (R, n)), synth(0xF2, (R,))
+    beta, gamma = int(synth(0xF3, (1,))[0]), int(synth(0xF4, (1,))[0])
+    got = gpu_pp(w, sg, k, beta, gamma, deg)
+    want = oracle.partial_products_and_zs(w, sg, k, beta, gamma, deg)
+    assert np.array_equal(got, want)
+    # a valid permutation (sigma = identity: s_sigma = k_j * x) makes every quotient 1: Z == 1 everywhere
+    wn = pb.field.primitive_root_of_unity(log_n)
+    xs = np.array([pow(wn, i, P) for i in range(n)], dtype=object)
+    ident = np.array([[int(k[j]) * int(x) % P for x in xs] for j in range(R)], dtype=np.uint64) if n <= 1024 else None
+    if ident is not None:
+        one = gpu_pp(w, ident, k, beta, gamma, deg)
+        assert np.all(one == 1)
+    # zero denominator -> the reference panics ("Tried to invert zero")
+    if n >= 2:
+        sg2 = sg.copy()
+        # choose sigma so that w + beta*sigma + gamma == 0 at (row 1, col 0)
+        sg2[0, 1] = (-(int(w[0, 1]) + gamma)) * pow(beta, P - 2, P) % P
+        with pytest.raises(ZeroDivisionError):
+            gpu_pp(w, sg2, k, beta, gamma, deg)
