@@ -481,3 +481,90 @@ def test_partial_products_and_zs(pb, oracle, R, log_n, deg):
         sg2[0, 1] = (-(int(w[0, 1]) + gamma)) * pow(beta, P - 2, P) % P
         with pytest.raises(ZeroDivisionError):
             gpu_pp(w, sg2, k, beta, gamma, deg)
+
+
+# ----------------------------------------------------------------------------- GL_MEM_DEVICE entry points
+def test_device_memory_entry_points(pb, oracle):
+    """The same ABI with device pointers (what a device-resident pipeline / bench.py uses): NTT with a column
+    stride larger than n, commit from device columns, cap/leaves/coeffs to device buffers, Merkle and hashing
+    on device leaves."""
+    import ctypes as C
+
+    import torch
+
+    N_ = pb._native
+    L, ctx = N_.lib(), pb.default_context()
+    dev = torch.device("cuda", 0)
+
+    def to_dev(a):
+        return torch.from_numpy(a.view(np.int64).copy()).to(dev)
+
+    def to_np(t):
+        return t.cpu().numpy().view(np.uint64)
+
+    # --- gl_ntt, stride > n, forward then inverse with a coset
+    B, log_n, stride = 5, 13, (1 << 13) + 24
+    x = synth(0xD1, (B, stride))
+    d = to_dev(x)
+    N_.check(L.gl_ntt(ctx.h, C.c_void_p(d.data_ptr()), log_n, B, stride, 0, 0, 7, N_.MEM_DEVICE), ctx.h)
+    ctx.synchronize()
+    got = to_np(d)
+    for b in range(B):
+        assert np.array_equal(got[b, :1 << log_n], oracle.coset_fft(x[b, :1 << log_n], 7))
+        assert np.array_equal(got[b, 1 << log_n:], x[b, 1 << log_n:])  # padding untouched
+    N_.check(L.gl_ntt(ctx.h, C.c_void_p(d.data_ptr()), log_n, B, stride, 1, 0, 7, N_.MEM_DEVICE), ctx.h)
+    ctx.synchronize()
+    assert np.array_equal(to_np(d)[:, :1 << log_n], x[:, :1 << log_n])
+
+    # --- gl_commit_create from device columns; outputs into device buffers
+    B, log_n, r, h = 11, 9, 2, 3
+    n, NN = 1 << log_n, 1 << (log_n + r)
+    vals = synth(0xD2, (B, n))
+    dv = to_dev(vals)
+    hnd = N_.vp()
+    N_.check(L.gl_commit_create(ctx.h, C.c_void_p(dv.data_ptr()), n, B, log_n, r, h, None, 0, N_.MEM_DEVICE,
+                                C.byref(hnd)), ctx.h)
+    o = oracle.Commit(vals, r, h)
+    cap = torch.empty(4 << h, dtype=torch.int64, device=dev)
+    leaves = torch.empty(NN * B, dtype=torch.int64, device=dev)
+    coeffs = torch.empty(B * n, dtype=torch.int64, device=dev)
+    digs = torch.empty(8 * (NN - (1 << h)), dtype=torch.int64, device=dev)
+    N_.check(L.gl_commit_cap(hnd, C.c_void_p(cap.data_ptr()), N_.MEM_DEVICE), ctx.h)
+    N_.check(L.gl_commit_leaves(hnd, 0, NN, C.c_void_p(leaves.data_ptr()), N_.MEM_DEVICE), ctx.h)
+    N_.check(L.gl_commit_coeffs(hnd, C.c_void_p(coeffs.data_ptr()), N_.MEM_DEVICE), ctx.h)
+    N_.check(L.gl_commit_digests(hnd, C.c_void_p(digs.data_ptr()), N_.MEM_DEVICE), ctx.h)
+    ctx.synchronize()
+    assert np.array_equal(to_np(cap).reshape(-1, 4), o.cap)
+    assert np.array_equal(to_np(leaves).reshape(NN, B), o.leaves)
+    assert np.array_equal(to_np(coeffs).reshape(B, n), o.coeffs)
+    assert np.array_equal(to_np(digs).reshape(-1, 4), o.digests)
+    assert L.gl_commit_num_polys(hnd) == B and L.gl_commit_leaf_width(hnd) == B
+    assert L.gl_commit_degree_log(hnd) == log_n and L.gl_commit_rate_bits(hnd) == r and L.gl_commit_cap_height(hnd) == h
+
+    # --- MerkleTree::new and hashing directly on the device leaves
+    mh = N_.vp()
+    N_.check(L.gl_merkle_build(ctx.h, C.c_void_p(leaves.data_ptr()), NN, B, h, N_.MEM_DEVICE, C.byref(mh)), ctx.h)
+    cap2 = np.empty((1 << h, 4), dtype=np.uint64)
+    N_.check(L.gl_merkle_cap(mh, N_.np_ptr(cap2), N_.MEM_HOST), ctx.h)
+    assert np.array_equal(cap2, o.cap)
+    hashes = torch.empty(NN * 4, dtype=torch.int64, device=dev)
+    N_.check(L.gl_poseidon_hash_many(ctx.h, C.c_void_p(leaves.data_ptr()), NN, B, C.c_void_p(hashes.data_ptr()),
+                                     N_.MEM_DEVICE), ctx.h)
+    ctx.synchronize()
+    assert np.array_equal(to_np(hashes).reshape(NN, 4), oracle.hash_many(o.leaves))
+    L.gl_merkle_destroy(mh)
+    L.gl_commit_destroy(hnd)
+
+
+def test_profiling_phases_and_launch_count(pb):
+    ctx = pb.Context(0)
+    ctx.set_profiling(True)
+    l0 = ctx.launch_count
+    c = pb.PolynomialBatch.from_values(synth(0xD5, (9, 1 << 12)), 3, False, 4, ctx=ctx)
+    ph = ctx.phase_ms()
+    assert ctx.launch_count > l0
+    assert ph["leaf_hash"][1] == 1 and ph["leaf_hash"][0] > 0 and ph["lde"][1] >= 1 and ph["intt"][1] >= 1
+    ctx.reset_phases()
+    assert ctx.phase_ms()["leaf_hash"] == (0.0, 0)
+    c.close()
+    ctx.close()
