@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -40,6 +41,7 @@ struct gl_ctx {
     std::map<std::tuple<int, int, u64>, u64*> coset_tabs;  // LDE coset scale tables by (log_n, rate_bits, shift)
     std::map<int, u64*> fold_tabs;              // FRI fold tables (w_N^-1 powers, hi | lo) by log N
     cudaStream_t copy_stream = nullptr;         // H2D of column chunks, overlapped with the NTTs of earlier chunks
+    std::set<const void*> smem_attr_done;       // kernels whose dynamic-smem attributes are set on THIS device
     u64* scratch = nullptr;                     // NTT group scratch (device)
     size_t scratch_words = 0;
     u64* pinned = nullptr;                      // host staging for small D2H / H2D
@@ -265,12 +267,12 @@ __global__ void k_mul_pows(u64* data, size_t stride, size_t n, const u64* hi, co
 template <int LOG>
 static int launch_passA(gl_ctx* ctx, const PassA& pa, int nblocks) {
     const size_t smem = ntt_tile_smem_bytes(LOG);
-    static bool attr_done = false;
-    if (!attr_done) {
+    const void* fn = (const void*)k_passA<LOG>;
+    if (!ctx->smem_attr_done.count(fn)) {  // function attributes are per device: track them per context
         CK(ctx, cudaFuncSetAttribute(k_passA<LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(ctx, cudaFuncSetAttribute(k_passA<LOG>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
-        attr_done = true;
+        ctx->smem_attr_done.insert(fn);
     }
     k_passA<LOG><<<nblocks, ntt_tile_threads(LOG), smem, ctx->stream>>>(pa);
     CKL(ctx);
@@ -279,12 +281,12 @@ static int launch_passA(gl_ctx* ctx, const PassA& pa, int nblocks) {
 template <int LOG, int MODE>
 static int launch_passB(gl_ctx* ctx, const PassB& pb) {
     const size_t smem = ntt_tile_smem_bytes(LOG);
-    static bool attr_done = false;
-    if (!attr_done) {
+    const void* fn = (const void*)k_passB<LOG, MODE>;
+    if (!ctx->smem_attr_done.count(fn)) {
         CK(ctx, cudaFuncSetAttribute(k_passB<LOG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(ctx, cudaFuncSetAttribute(k_passB<LOG, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
-        attr_done = true;
+        ctx->smem_attr_done.insert(fn);
     }
     const int nblocks = passB_blocks<LOG>(pb, MODE);
     k_passB<LOG, MODE><<<nblocks, ntt_tile_threads(LOG), smem, ctx->stream>>>(pb);

@@ -135,3 +135,22 @@ def test_fri_proof_serialisation_layout():
     assert len(b) == 8 * (8 + 3 + 8 + 4 + 4 + 2 + 1) + 2
     assert b[:8] == (0).to_bytes(8, "little") and b[-8:] == (77).to_bytes(8, "little")
     assert b[8 * 8 + 3 * 8] == 2
+
+
+def test_cpp_host_layer_compiles_and_fails_loudly_without_gpu(native, oracle):
+    """include/plonky2_b200.hpp (the C++ mirror of the reference's Rust interface) builds against the C ABI;
+    without a GPU the program must abort with the library's "no CPU fallback" error, not compute anything."""
+    import subprocess
+
+    import torch
+
+    exe = "/tmp/gl_host_parity_cpu"
+    subprocess.check_call(["g++", "-std=c++17", "-O0", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "host_parity.cpp"),
+                           "-L" + os.path.join(ROOT, "plonky2_b200"), "-lplonky2_b200",
+                           "-L" + os.path.join(ROOT, "oracle"), "-lgl_oracle",
+                           "-Wl,-rpath," + os.path.join(ROOT, "plonky2_b200"), "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu test")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr

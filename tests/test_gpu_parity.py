@@ -568,3 +568,19 @@ def test_profiling_phases_and_launch_count(pb):
     assert ctx.phase_ms()["leaf_hash"] == (0.0, 0)
     c.close()
     ctx.close()
+
+
+def test_cpp_host_layer_parity(pb):
+    """The compiled-language host layer (include/plonky2_b200.hpp, mirroring the reference's Rust interface)
+    driven by tests/cpp/host_parity.cpp: NTT vs naive evaluation, commitment vs oracle, shape errors,
+    byte-identical FriProof accepted by the restated verifier."""
+    import subprocess
+
+    exe = "/tmp/gl_host_parity"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "host_parity.cpp"),
+                           "-L" + os.path.join(ROOT, "plonky2_b200"), "-lplonky2_b200",
+                           "-L" + os.path.join(ROOT, "oracle"), "-lgl_oracle",
+                           "-Wl,-rpath," + os.path.join(ROOT, "plonky2_b200"), "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "CPP HOST PARITY OK" in r.stdout, r.stdout + r.stderr

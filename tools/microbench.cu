@@ -123,6 +123,34 @@ __global__ void __launch_bounds__(THREADS, MINB) k_poseidon_sync_occ(uint64_t* o
     for (int r = 0; r < reps; r++) poseidon_permute_t<true>(s);
     out[blockIdx.x * blockDim.x + threadIdx.x] = s[0];
 }
+// two independent permutations per thread, interleaved round by round (more ILP, pipe diversity inside a warp)
+GL_D void poseidon_permute_x2(uint64_t a[12], uint64_t b[12]) {
+    const PoseidonTables& T = c_pos;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { a[i] = add_canonical(a[i], T.rc[i]); b[i] = add_canonical(b[i], T.rc[i]); }
+#pragma unroll 1
+    for (int r = 0; r < 8; r++) {
+        const uint64_t* nrc = (r < 3) ? &T.rc[12 * (r + 1)] : (r == 3) ? T.fast_first : (r < 7) ? &T.rc[12 * (r + 23)] : T.zeros;
+#pragma unroll
+        for (int i = 0; i < 12; i++) { a[i] = sbox7(a[i]); b[i] = sbox7(b[i]); }
+        mds_layer_add(a, nrc);
+        mds_layer_add(b, nrc);
+        __syncthreads();
+        if (r == 3) {
+            poseidon_partial_rounds_noconst(a);
+            poseidon_partial_rounds_noconst(b);
+#pragma unroll
+            for (int i = 0; i < 12; i++) { a[i] = add_canonical(a[i], T.rc[12 * 26 + i]); b[i] = add_canonical(b[i], T.rc[12 * 26 + i]); }
+        }
+    }
+}
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_poseidon_x2(uint64_t* out, uint64_t a0, int reps) {
+    uint64_t a[12], b[12];
+    for (int i = 0; i < 12; i++) { a[i] = a0 * (threadIdx.x + blockIdx.x * 131 + i + 1); b[i] = a[i] ^ 0x5555; }
+    for (int r = 0; r < reps; r++) poseidon_permute_x2(a, b);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a[0] ^ b[0];
+}
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_poseidon_plain(uint64_t* out, uint64_t a, int reps) {
     uint64_t s[12];
@@ -213,6 +241,12 @@ int main() {
     printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "sync CTA=256 minb=3 (80r)", ms, perms / ms / 1e3);
     ms = timeit([&] { k_poseidon_sync_occ<128, 5><<<pb, 128>>>(out, 3, reps); });
     printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "sync CTA=128 minb=5 (96r)", ms, perms / ms / 1e3);
+    ms = timeit([&] { k_poseidon_x2<128, 3><<<pb / 2, 128>>>(out, 3, reps); });
+    printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "x2 CTA=128 minb=3", ms, perms / ms / 1e3);
+    ms = timeit([&] { k_poseidon_x2<128, 2><<<pb / 2, 128>>>(out, 3, reps); });
+    printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "x2 CTA=128 minb=2", ms, perms / ms / 1e3);
+    ms = timeit([&] { k_poseidon_x2<64, 4><<<pb, 64>>>(out, 3, reps); });
+    printf("%-26s %8.3f ms  %8.2f Mperm/s\n", "x2 CTA=64 minb=4", ms, perms / ms / 1e3);
     ms = timeit([&] { k_fullround<<<pb, pt>>>(out, 3, reps * 8); });
     printf("%-26s %8.3f ms  %8.2f M full-rounds/s (x8 per perm => %.2f Mperm/s if only full rounds)\n", "full_round", ms,
            perms * 8 / ms / 1e3, perms / ms / 1e3);
