@@ -64,15 +64,16 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------
 # reference arm: the CPU path (oracle port; the Rust reference cannot be built in this image)
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(args, cores, target_cpu_seconds=3.0):
-    """Bounded sample of the same workload for the CPU arm: same columns/rate/cap, fewer rows."""
-    # ~5 us of CPU per Poseidon permutation in the port; perms per leaf = ceil(W/8) + 1. Size the sample
-    # for roughly target_cpu_seconds of wall time on `cores` threads (the transposes/NTTs add ~30%).
-    perms_per_leaf = (args.cols + 7) // 8 + 1
-    log_n = args.log_n
-    while log_n > 10 and (1 << (log_n + args.rate_bits)) * perms_per_leaf * 6.5e-6 / max(1, cores) > target_cpu_seconds:
-        log_n -= 1
-    return log_n
+def cpu_sample(args, cores, target_seconds=3.0):
+    """Bounded sample of the same workload for the CPU arm: same columns/rate/cap, fewer rows. Calibrated by
+    timing a small sample and scaling linearly in n so that one step takes about `target_seconds`."""
+    import math
+
+    base = min(12, args.log_n)
+    run_cpu_once(args, base, cores, 7)          # warm-up (thread pool, page faults)
+    dt, _ = run_cpu_once(args, base, cores, 8)
+    grow = int(math.floor(math.log2(max(target_seconds / max(dt, 1e-4), 1.0))))
+    return max(base, min(args.log_n, base + grow))
 
 
 def run_cpu_once(args, log_n_s, cores, seed):
@@ -434,7 +435,17 @@ def recursion_shape(ctx_device, reps=5):
     t0 = time.perf_counter()
     oproof = cpu_once()
     cpu_ms = (time.perf_counter() - t0) * 1e3
-    return {"workload": "recursion-shaped synthetic proof, n=2^14, standard_recursion_config "
+    # the same sequence through the compiled C++ host layer (include/plonky2_b200.hpp): no Python in the loop
+    cpp = None
+    try:
+        exe = os.path.join(tempfile.gettempdir(), "gl_prove_latency")
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                               os.path.join(ROOT, "tools", "prove_latency.cpp"), "-L" + os.path.join(ROOT, "plonky2_b200"),
+                               "-lplonky2_b200", "-Wl,-rpath," + os.path.join(ROOT, "plonky2_b200")])
+        cpp = json.loads(subprocess.run([exe, "7"], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1])
+    except Exception as e:
+        cpp = {"error": repr(e)}
+    return {"cpp_host": cpp,"workload": "recursion-shaped synthetic proof, n=2^14, standard_recursion_config "
                         "(3 commitments of 135/20/16 polys + prove_openings over 255 polys, arity 16 x3, PoW 16, 28 queries)",
             "gpu_ms_per_proof_median": float(np.median(ts)) * 1e3, "gpu_ms_per_proof_min": min(ts) * 1e3,
             "cpu_port_ms_per_proof": cpu_ms, "cpu_cores": cores, "proof_bytes": len(proof_bytes),

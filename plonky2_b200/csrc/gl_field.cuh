@@ -6,9 +6,10 @@
 // themselves mod p); add/sub/mul return a u64 congruent to the exact result; canonicalisation
 // (to_canonical_u64, :216-224) happens only where values are stored for hashing/comparison/output.
 //
-// This is not a translation of the x86 code: the 64x64->128 product is built from four 32x32->64
-// IMAD.WIDE ops and the reduction uses 2^64 = 2^32 - 1, 2^96 = -1 (mod p) with 32-bit carry chains
-// (Montgomery-free, as BASELINE.json asks).
+// This is not a translation of the x86 code: on the device the 64x64->128 product is four IMAD.WIDE.U32
+// (ptxas' carry-in/carry-out forms) and the reduction uses 2^64 = 2^32 - 1, 2^96 = -1 (mod p) with 32-bit
+// carry chains written in PTX (Montgomery-free, as BASELINE.json asks): reduce128 is 12 instructions, a
+// general add 10, a modmul 19 (measured 1.04 T modmul/s on B200, tools/microbench.cu).
 #pragma once
 #include <stdint.h>
 

@@ -44,12 +44,6 @@ GL_HD constexpr size_t ntt_tile_smem_bytes(int log) {
     return ((size_t)(1 << log) * ntt_tile_TS(log) + (size_t)(1 << log)) * 8 + 16;
 }
 
-// multiply by 2^K, K a compile-time constant in [0, 96)
-template <int K>
-GL_HD uint64_t mul_pow2_c(uint64_t a) {
-    return mul_pow2(a, (uint32_t)K);
-}
-
 // 2^M-point DIF DFT in registers, natural in, bit-reversed out, w_{2^M} = 2^(192 / 2^M).
 template <int M>
 GL_HD void dft_regs(uint64_t* r) {
@@ -100,7 +94,6 @@ GL_HD void radix_step(uint64_t* s, const uint64_t* wt, int sbit, int tid, int nt
 
 // Number of radix steps and the M of step i for a 2^LOG transform: 4,4,...,rem.
 GL_HD constexpr int ntt_num_steps(int log) { return (log + 3) / 4; }
-GL_HD constexpr int ntt_step_M(int log, int i) { return (i < log / 4) ? 4 : (log % 4); }
 
 // ---------------------------------------------------------------- pass descriptors
 struct PassA {

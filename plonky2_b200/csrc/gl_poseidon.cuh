@@ -4,11 +4,13 @@
 //                            hash_n_to_m_no_pad / compress    plonky2/src/hash/hashing.rs:97-145
 //                            Hasher::hash_or_noop             plonky2/src/plonk/config.rs:63-74
 //
-// One thread owns one 12-lane state in registers. Full rounds: x^7 with two squarings + two
-// multiplies per lane, then the circulant MDS evaluated on 32-bit halves with IMAD.WIDE
-// accumulation (constants < 2^6, so 12-term sums of 32x6-bit products stay < 2^42) and ONE 96-bit
-// reduction per lane. Partial rounds use the "fast" factorisation (w_hat / v vectors), with the
-// 12-term dot product accumulated in 160 bits and reduced once.
+// One thread owns one 12-lane state in registers. Full rounds: x^7 with two squarings + two multiplies per
+// lane, then the circulant MDS evaluated on 32-bit halves (constants < 2^6, so 13-term sums of 32x6-bit
+// products stay < 2^42): on the device these sums run as DFMAs on the otherwise idle FP64 pipe (exact), on
+// the host as integer multiply-adds; ONE 96-bit reduction per lane, and the next round's constants are folded
+// into the accumulators. Partial rounds use the "fast" factorisation (w_hat / v vectors), with the 12-term
+// dot product accumulated in 160 bits and reduced once. The rounds are rolled loops (one copy of each round
+// body) so the permutation fits the instruction cache.
 #pragma once
 #include "gl_field.cuh"
 #include "gl_poseidon_constants.h"
@@ -69,9 +71,6 @@ inline const PoseidonTables& host_poseidon_tables() {
 #else
 #define GL_POS (host_poseidon_tables())
 #endif
-
-// MDS circulant first row / diagonal (poseidon_goldilocks.rs:24-25) as compile-time immediates.
-#define GL_MDS_CIRC_LIST {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20}
 
 // 160-bit accumulator for sums of 64x64 products.
 struct Acc160 {
