@@ -321,6 +321,19 @@ def gpu_arm(args, rank, local_rank, world):
         "permutations_per_s": perms / (leaf_avg * 1e-3) if leaf_avg else None,
         "note": "integer-issue bound (x^7 S-boxes + MDS in IMAD/IADD3), not HBM bound: see DESIGN.md",
     }
+    # integer-issue roofline (what actually bounds these kernels): thread-instructions/s vs 128 lanes/clk/SM
+    issue = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+        peak_issue = 148 * 128 * sm_clk * 1e6
+        ipp = tr["k_leaf_hash"]["thread_instructions_per_permutation"]
+        ach = ipp * roof["permutations_per_s"]
+        issue = {"kernel": "k_leaf_hash", "bound": "integer issue (4 warp-instructions/clk/SM)",
+                 "achieved": ach, "peak": peak_issue, "unit": "thread-instructions/s", "frac": ach / peak_issue,
+                 "thread_instructions_per_permutation": ipp, "source": tr["k_leaf_hash"]["instr_source"]}
+    except Exception:
+        pass
     lde_ms = (phases["intt"][0] + phases["lde"][0]) / steps
     lde_bytes = 8.0 * n * B * (2 + (1 << r) / world)
     line = {
@@ -334,6 +347,7 @@ def gpu_arm(args, rank, local_rank, world):
                         "device behind the handle (fetched on demand by gl_commit_leaves/_open)"},
         "gpu_launches": int(launches),
         "roofline": roof,
+        "roofline_issue": issue,
         "phases_ms_per_step": {k: v[0] / steps for k, v in phases.items()},
         "roofline_lde": {"kernels": "k_passA + k_passB (iNTT + 2^r coset NTTs, leaf-major stores)", "bound": "hbm",
                          "algorithmic_bytes": lde_bytes, "ms": lde_ms,
