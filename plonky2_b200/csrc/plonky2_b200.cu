@@ -6,6 +6,7 @@
 //   prove_openings (pre-FRI part)             plonky2/src/fri/oracle.rs:176-220   -> gl_fri_begin()
 //   fri_committed_trees / fri_proof_of_work   plonky2/src/fri/prover.rs:84-202    -> gl_fri_commit_round/fold/pow
 // There is no CPU fallback anywhere in this file: every compute entry point launches kernels.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -642,6 +643,41 @@ __global__ void __launch_bounds__(HASH_CTA, HASH_MINB) k_merkle_level(TreeView t
     dst[2] = h[2];
     dst[3] = h[3];
 }
+// Upper levels in ONE persistent cooperative launch: when a level has fewer nodes than the resident thread
+// capacity, per-level launches are latency-bound; here the resident CTAs walk the levels i0..sub_log with a
+// grid-wide barrier between levels (every level reads what the previous one wrote).
+__global__ void __launch_bounds__(HASH_CTA, HASH_MINB) k_merkle_upper(TreeView t, uint32_t i0) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const uint32_t sub_log = t.log_n - t.cap_height;
+    const size_t L = (size_t)1 << sub_log;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    for (uint32_t i = i0; i <= sub_log; i++) {
+        const size_t nodes_per_sub = (size_t)1 << (sub_log - i);
+        const size_t total = nodes_per_sub << t.cap_height;
+        // uniform trip count per CTA (the permutation contains CTA barriers)
+        const size_t first = (size_t)blockIdx.x * blockDim.x;
+        for (size_t base = first; base < total; base += nthreads) {
+            size_t g = base + threadIdx.x;
+            const bool live = g < total;
+            if (!live) g = total - 1;
+            const size_t c = g >> (sub_log - i), q = g & (nodes_per_sub - 1);
+            u64* sub = t.digests + 4 * (c * 2 * (L - 1));
+            const u64* pair = sub + 4 * digest_pos(2 * q, i - 1);
+            u64 l[4] = {pair[0], pair[1], pair[2], pair[3]};
+            u64 r[4] = {pair[4], pair[5], pair[6], pair[7]};
+            u64 h[4];
+            two_to_one<true>(l, r, h);
+            if (live) {
+                u64* dst = (i == sub_log) ? (t.cap + 4 * c) : (sub + 4 * digest_pos(q, i));
+                dst[0] = h[0];
+                dst[1] = h[1];
+                dst[2] = h[2];
+                dst[3] = h[3];
+            }
+        }
+        grid.sync();
+    }
+}
 template <bool NOOP_SHORT>
 __global__ void __launch_bounds__(128) k_hash_many(const u64* in, size_t n_items, uint32_t W, u64* out) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -716,8 +752,26 @@ static int tree_build(gl_ctx* ctx, Tree& t) {
     }
     PhaseScope ps2(ctx, GL_PHASE_MERKLE_LEVELS);
     const uint32_t sub_log = t.log_n - t.cap_height;
+    // resident capacity of the persistent upper-level kernel (cooperative launch needs co-residency)
+    static int coop_blocks_per_sm = -1, coop_sms = 0, coop_ok = 0;
+    if (coop_blocks_per_sm < 0) {
+        cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, ctx->device);
+        cudaDeviceGetAttribute(&coop_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks_per_sm, k_merkle_upper, HASH_CTA, 0) != cudaSuccess)
+            coop_blocks_per_sm = 0;
+    }
+    const size_t coop_threads = coop_ok ? (size_t)coop_blocks_per_sm * coop_sms * HASH_CTA : 0;
     for (uint32_t i = 1; i <= sub_log; i++) {
         size_t total = (size_t)1 << (t.log_n - i);
+        if (coop_threads && total <= coop_threads && i < sub_log) {
+            // this and all higher levels fit the resident grid: one persistent launch finishes the tree
+            unsigned nb = (unsigned)((total + HASH_CTA - 1) / HASH_CTA);
+            uint32_t i0 = i;
+            void* args[] = {(void*)&v, (void*)&i0};
+            CK(ctx, cudaLaunchCooperativeKernel((void*)k_merkle_upper, dim3(nb), dim3(HASH_CTA), args, 0, ctx->stream));
+            ctx->launches++;
+            break;
+        }
         const int cta = HASH_CTA;
         k_merkle_level<<<(unsigned)((total + cta - 1) / cta), cta, 0, ctx->stream>>>(v, i);
         CKL(ctx);
