@@ -186,6 +186,8 @@ def gpu_arm(args, rank, local_rank, world):
     stream = torch.cuda.Stream(device=dev)
     ctx = N.Context(local_rank, stream=stream.cuda_stream)
     ctx.set_profiling(True)
+    if args.ntt_group:
+        ctx.set_ntt_group(args.ntt_group)
     B, log_n, r, h = args.cols, args.log_n, args.rate_bits, args.cap_height
     n, NN = 1 << log_n, 1 << (log_n + r)
     cap_local_words = (4 << h) // world
@@ -479,6 +481,7 @@ def main():
     ap.add_argument("--cap-height", type=int, default=4)
     ap.add_argument("--ntt-cols", type=int, default=64)
     ap.add_argument("--no-ntt", action="store_true")
+    ap.add_argument("--ntt-group", type=int, default=0, help="columns per NTT group (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the recursion-shaped prove() timing")
     args = ap.parse_args()

@@ -60,6 +60,8 @@ int gl_ctx_synchronize(gl_ctx* ctx);
 uint64_t gl_ctx_launch_count(const gl_ctx* ctx);
 /* tuning: columns per NTT group (scratch = group * n * 8 bytes; sized so pass A -> pass B stays in L2) */
 int gl_ctx_set_ntt_group(gl_ctx* ctx, uint32_t columns);
+/* tuning: log2 of the contiguous (pass B) transform size for two-pass NTTs; 0 = balanced split */
+int gl_ctx_set_ntt_split(gl_ctx* ctx, int log_contiguous);
 /* Optional CUDA-event phase timing on the context's stream (the analogue of the reference's TimingTree
  * scopes "IFFT" / "FFT + blinding" / "build Merkle tree", plonky2/src/fri/oracle.rs:65-103). */
 #define GL_PHASE_INTT 0          /* from_values' iNTT of all columns */

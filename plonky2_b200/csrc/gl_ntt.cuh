@@ -241,12 +241,15 @@ GL_HD void tile_step(uint64_t* s, const uint64_t* wt, int i, int tid, int nthrea
 
 // ---------------------------------------------------------------- plan + table entries
 // n = 2^log_n = R*C with R = 2^a (pass A, absent when a == 0) and C = 2^b (pass B).
-GL_HD void ntt_split(int log_n, int& a, int& b) {
+GL_HD void ntt_split(int log_n, int& a, int& b, int force_b = 0) {
     if (log_n <= NTT_MAX_LOG_TILE) {
         a = 0;
         b = log_n;
     } else {
         b = (log_n + 1) / 2;
+        // tuning override (gl_ctx_set_ntt_split): any b with 6 <= a, b <= 12
+        if (force_b >= 6 && force_b <= NTT_MAX_LOG_TILE && log_n - force_b >= 6 && log_n - force_b <= NTT_MAX_LOG_TILE)
+            b = force_b;
         a = log_n - b;
     }
 }

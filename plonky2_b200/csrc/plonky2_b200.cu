@@ -50,6 +50,7 @@ struct gl_ctx {
     u64* dstage = nullptr;                      // device staging for openings
     size_t dstage_words = 0;
     uint32_t ntt_group = 0;                     // 0 = auto
+    int ntt_force_b = 0;                        // 0 = balanced split; else log2 of the contiguous pass size
     // optional CUDA-event phase timing (bench.py's roofline numbers come from here)
     bool prof_on = false;
     struct Pending {
@@ -349,7 +350,7 @@ static int get_twa(gl_ctx* ctx, int log_n, const u64** out) {
     auto it = ctx->twa.find(log_n);
     if (it == ctx->twa.end()) {
         int a, b;
-        ntt_split(log_n, a, b);
+        ntt_split(log_n, a, b, ctx->ntt_force_b);
         u64* p;
         CK(ctx, cudaMalloc((void**)&p, (size_t)8 << log_n));
         size_t n = (size_t)1 << log_n;
@@ -362,12 +363,15 @@ static int get_twa(gl_ctx* ctx, int log_n, const u64** out) {
     *out = it->second;
     return GL_OK;
 }
-// columns per group so that the pass-A scratch stays L2-resident (about 32 MiB), multiple of 8
+// Columns per two-pass group (scratch = group * n * 8 bytes, multiple of 8 columns). Measured on B200
+// (tools/ntt_sweep.py): the passes are integer-issue bound, so keeping the intermediate L2-resident buys nothing,
+// while larger launches amortise wave quantisation (1024-CTA launches fill 3.46 waves of 296 resident CTAs):
+// 64 x 2^20 NTT 1.65 ms at 8 columns/group -> 1.46 ms at 64. Default: as many columns as fit 1 GiB of scratch.
 static uint32_t group_cols(const gl_ctx* ctx, int log_n, uint32_t ncols) {
     uint32_t g = ctx->ntt_group;
     if (g == 0) {
         size_t col_bytes = (size_t)8 << log_n;
-        size_t target = (size_t)32 << 20;
+        size_t target = (size_t)1 << 30;
         g = (uint32_t)(target / col_bytes);
         if (g < 8) g = 8;
     }
@@ -416,7 +420,7 @@ static int ntt_natural(gl_ctx* ctx, const u64* in, size_t in_stride, u64* out, s
     }
     if (log_n > 2 * NTT_MAX_LOG_TILE) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %d > 24", log_n);
     int a, b;
-    ntt_split(log_n, a, b);
+    ntt_split(log_n, a, b, ctx->ntt_force_b);
     const u64 *wta = nullptr, *wtb = nullptr, *twa = nullptr;
     TRY(get_wt(ctx, b, &wtb));
     const bool coset = (!inverse) && (canon(shift) != 1);
@@ -499,7 +503,7 @@ static int lde_leaves(gl_ctx* ctx, const u64* coeffs, size_t coeff_stride, uint3
     const size_t n = (size_t)1 << log_n;
     const int ncos = 1 << rate_bits;
     int a = 0, b = log_n;
-    ntt_split(log_n, a, b);
+    ntt_split(log_n, a, b, ctx->ntt_force_b);
     const size_t R = (size_t)1 << a, C = (size_t)1 << b;
     const size_t cnt = R > C ? R : C;
     // per-coset scale tables: [c][0] = (s_c^C)^i, [c][1] = s_c^i  (cached per context)
@@ -864,7 +868,7 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
     // Column chunks flow through  H2D copy -> iNTT ("IFFT", oracle.rs:65-69) -> leaf-major coset LDE
     // ("FFT + blinding" + "transpose LDEs" + bit-reversal, fused); the copy of chunk k+1 (separate stream)
     // overlaps the transforms of chunk k.
-    const uint32_t CH = 16;
+    const uint32_t CH = 32;  // 32 columns: launches big enough for full waves, first-chunk H2D exposure ~5 ms at n = 2^20
     const bool overlap = (mem == GL_MEM_HOST) && B > CH;
     std::vector<cudaEvent_t> evs;
     if (overlap) {
@@ -1417,6 +1421,15 @@ int gl_ctx_synchronize(gl_ctx* ctx) {
 uint64_t gl_ctx_launch_count(const gl_ctx* ctx) { return ctx->launches; }
 int gl_ctx_set_ntt_group(gl_ctx* ctx, uint32_t columns) {
     ctx->ntt_group = columns;
+    return GL_OK;
+}
+int gl_ctx_set_ntt_split(gl_ctx* ctx, int log_contiguous) {
+    // the pass-A twiddle table depends on the split: drop cached tables
+    for (auto& kv : ctx->twa) cudaFree(kv.second);
+    ctx->twa.clear();
+    for (auto& kv : ctx->coset_tabs) cudaFreeAsync(kv.second, ctx->stream);
+    ctx->coset_tabs.clear();
+    ctx->ntt_force_b = log_contiguous;
     return GL_OK;
 }
 int gl_ctx_set_profiling(gl_ctx* ctx, int on) {
