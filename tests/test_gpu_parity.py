@@ -277,7 +277,8 @@ def _opened_values(oracle, ocommits, batches):
 @pytest.mark.parametrize("log_n,Bs,arity,pow_bits,nq", [(5, [3, 2], [1], 3, 4), (8, [4, 6, 2], [2, 2], 5, 6),
                                                        (10, [7, 9, 4, 3], [4], 8, 9),
                                                        (12, [20, 33, 20, 16], [4, 4], 16, 28),
-                                                       (9, [5], [3, 1, 2], 4, 5), (7, [2, 2], [5], 2, 3)])
+                                                       (9, [5], [3, 1, 2], 4, 5), (7, [2, 2], [5], 2, 3),
+                                                       (6, [3], [], 2, 3), (4, [1], [1, 1, 1], 0, 2)])
 def test_prove_openings_bit_exact_and_verifies(pb, oracle, log_n, Bs, arity, pow_bits, nq):
     r, h = 3, (4 if log_n >= 8 else 1)
     n = 1 << log_n
