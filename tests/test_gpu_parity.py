@@ -585,3 +585,31 @@ def test_cpp_host_layer_parity(pb):
                            "-Wl,-rpath," + os.path.join(ROOT, "plonky2_b200"), "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "CPP HOST PARITY OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_randomised_shapes_against_oracle(pb, oracle):
+    """Seeded sweep over random (columns, degree, rate, cap, salt, coeffs/values, non-canonical inputs) shapes:
+    commitment (coefficients, cap, a leaf block, an opening) bit-exact vs the oracle."""
+    rng = np.random.RandomState(20260922)
+    for case in range(40):
+        log_n = int(rng.randint(0, 12))
+        r = int(rng.randint(0, 4))
+        B = int(rng.randint(1, 40))
+        h = int(rng.randint(0, min(log_n + r, 5) + 1))
+        blinding = bool(rng.randint(0, 4) == 0)
+        is_coeffs = bool(rng.randint(0, 2))
+        n, N = 1 << log_n, 1 << (log_n + r)
+        vals = synth(1000 + case, (B, n), canonical=bool(rng.randint(0, 2)))
+        salt = synth(2000 + case, (4, N)) if blinding else None
+        mk = pb.PolynomialBatch.from_coeffs if is_coeffs else pb.PolynomialBatch.from_values
+        c = mk(vals, r, blinding, h, salt=salt)
+        o = oracle.Commit(vals, r, h, salt=salt, is_coeffs=is_coeffs)
+        tag = (case, B, log_n, r, h, blinding, is_coeffs)
+        assert np.array_equal(c.polynomials, o.coeffs), tag
+        assert np.array_equal(c.merkle_tree.cap.hashes, o.cap), tag
+        lo = int(rng.randint(0, N))
+        cnt = min(N - lo, 7)
+        assert np.array_equal(c.merkle_tree.get_rows(lo, cnt), o.leaves[lo:lo + cnt]), tag
+        lv, pt = c.merkle_tree.open_many([lo])
+        assert np.array_equal(pt[0], oracle.merkle_prove(lo, N, h, o.digests)), tag
+        c.close()
