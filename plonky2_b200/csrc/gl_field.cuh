@@ -252,13 +252,19 @@ GL_HD uint64_t mul_pow2(uint64_t a, uint32_t k) {
         uint64_t lo = a << k;
         uint64_t hi = a >> (64 - k);  // < 2^k, k < 64
         return reduce128(lo, hi);
-    } else {  // 64 <= k < 96: a*2^k = (a * 2^(k-64)) * 2^64
+    } else {
+        // 64 <= k < 96, k = 64 + j: with (v2:v1:v0) = a << j (96 bits, v2 < 2^31),
+        // a*2^k = v0*2^64 + v1*2^96 + v2*2^128 = v0*(2^32 - 1) - v1 - v2*2^32   (2^96 = -1, 2^128 = -2^32)
+        //       = (v0 << 32) - ((v2 << 32) + v0 + v1):  one modular subtraction; the subtrahend is < 2^63 < p,
+        // so a single borrow fix-up is exact.
         uint32_t j = k - 64;
-        uint64_t lo = j ? (a << j) : a;
-        uint64_t hi = j ? (a >> (64 - j)) : 0;  // < 2^32
-        // value = hi*2^128 + lo*2^64 ; 2^128 = 2^96*2^32 = -2^32 ; lo*2^64 -> reduce128(0, lo)
-        uint64_t r = reduce128(0, lo);
-        return sub(r, hi << 32);
+        uint64_t sh = j ? (a << j) : a;
+        uint32_t v0 = (uint32_t)sh, v1 = (uint32_t)(sh >> 32);
+        uint32_t v2 = j ? (uint32_t)(a >> (64 - j)) : 0u;
+        uint64_t A = (uint64_t)v0 << 32;
+        uint64_t B = ((uint64_t)v2 << 32) + v0 + v1;
+        uint64_t d = A - B;
+        return (A < B) ? d - EPS : d;
     }
 }
 
