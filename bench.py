@@ -56,7 +56,8 @@ def workload_config(args, world):
         "lde_elements": args.cols * N,
         "l2": "inputs %.2f GB + leaves %.2f GB per step, far larger than the 126 MB L2 (no flush needed)" % (
             args.cols * n * 8 / 1e9, args.cols * N * 8 / 1e9),
-        "parallelism": "row-block (coset) sharding x%d, NCCL all-gather of cap entries" % world if world > 1
+        "parallelism": (("column-sharded iNTT + NCCL all-gather of coefficients, then " if world >= 4 else "") +
+                        "row-block (coset) sharded LDE + Merkle x%d + NCCL all-gather of cap entries" % world) if world > 1
         else "single GPU",
     }
 
@@ -200,10 +201,21 @@ def gpu_arm(args, rank, local_rank, world):
         cap_local = torch.empty(cap_local_words, dtype=torch.int64, device=dev)
         cap_full = torch.empty(cap_local_words * world, dtype=torch.int64, device=dev)
 
+        committer = None
+        if world >= 4:  # at 2 ranks the replicated iNTT with chunk-overlapped H2D has the better end-to-end time
+            from plonky2_b200.distributed import ColumnShardedCommitter
+
+            committer = ColumnShardedCommitter(ctx, B, log_n, r, h, rank, world, dev)
+            my_cols = vals[committer.b0:committer.b1]
+
         def step_device():
-            hnd = N.vp()
-            N.check(L.gl_commit_create_sharded(ctx.h, C.c_void_p(vals.data_ptr()), n, B, log_n, r, h, None, 0,
-                                               N.MEM_DEVICE, rank, world, C.byref(hnd)), ctx.h)
+            if committer is not None:
+                # column-sharded iNTT -> NCCL all-gather of coefficients -> row-block sharded LDE + Merkle
+                hnd = committer.commit(my_cols, from_host=False)
+            else:
+                hnd = N.vp()
+                N.check(L.gl_commit_create_sharded(ctx.h, C.c_void_p(vals.data_ptr()), n, B, log_n, r, h, None, 0,
+                                                   N.MEM_DEVICE, rank, world, C.byref(hnd)), ctx.h)
             N.check(L.gl_commit_cap(hnd, C.c_void_p(cap_local.data_ptr()), N.MEM_DEVICE), ctx.h)
             if world > 1:
                 dist.all_gather_into_tensor(cap_full, cap_local)
@@ -246,9 +258,12 @@ def gpu_arm(args, rank, local_rank, world):
         host_cap = np.empty(cap_local_words, dtype=np.uint64)
 
         def step_e2e():
-            hnd = N.vp()
-            N.check(L.gl_commit_create_sharded(ctx.h, C.c_void_p(host_vals.data_ptr()), n, B, log_n, r, h, None, 0,
-                                               N.MEM_HOST, rank, world, C.byref(hnd)), ctx.h)
+            if committer is not None:
+                hnd = committer.commit(host_vals[committer.b0:committer.b1], from_host=True)  # H2D of 1/G of the columns
+            else:
+                hnd = N.vp()
+                N.check(L.gl_commit_create_sharded(ctx.h, C.c_void_p(host_vals.data_ptr()), n, B, log_n, r, h, None, 0,
+                                                   N.MEM_HOST, rank, world, C.byref(hnd)), ctx.h)
             N.check(L.gl_commit_cap(hnd, N.np_ptr(host_cap), N.MEM_HOST), ctx.h)  # synchronises
             if world > 1:
                 cap_local.copy_(torch.from_numpy(host_cap.view(np.int64)))
@@ -344,7 +359,8 @@ def gpu_arm(args, rank, local_rank, world):
         "dtype": "u64", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks,
         "e2e": {"value": B * NN / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": B * n * 8, "d2h_bytes_per_step": cap_local_words * 8,
+                "h2d_bytes_per_step": (B * n * 8 * world) if world < 4 else ((B + world - 1) // world) * n * 8 * world,
+                "d2h_bytes_per_step": cap_local_words * 8,
                 "note": "host (pinned) columns -> gl_commit_create -> cap on host; leaves/digests stay on the "
                         "device behind the handle (fetched on demand by gl_commit_leaves/_open)"},
         "gpu_launches": int(launches),

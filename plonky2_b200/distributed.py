@@ -109,3 +109,56 @@ def prove_openings_sharded(instance, oracles, challenger, fri_params, group=None
         return F.FriProof(caps, rounds, final_coeffs, pow_witness)
     finally:
         state.close()
+
+
+def column_slice(num_polys, rank, world):
+    """Columns [b0, b1) whose iNTT rank `rank` computes; slices are equal-sized (the last ones may be padded)."""
+    per = (num_polys + world - 1) // world
+    b0 = min(rank * per, num_polys)
+    return b0, min(b0 + per, num_polys), per
+
+
+class ColumnShardedCommitter:
+    """from_values over G ranks with BOTH axes of SURVEY.md section 8e: each rank uploads and inverse-transforms
+    only its own slice of the columns (the reference's rayon axis, oracle.rs:65-69), the ranks all-gather the
+    coefficients over NVLink (NCCL; the optional second collective of section 8e), then every rank extends all
+    columns on its own row block / coset and hashes its own leaves (gl_commit_create_sharded, is_coeffs=1).
+    Compared with replicating the iNTT this cuts the per-rank H2D and iNTT work by G; the commitment is bit-identical.
+
+    Buffers (device slice, gathered coefficients) are torch tensors allocated once and reused across calls."""
+
+    def __init__(self, ctx, num_polys, log_n, rate_bits, cap_height, rank, world, device, group=None):
+        import torch
+
+        self.ctx, self.B, self.log_n, self.r, self.h = ctx, num_polys, log_n, rate_bits, cap_height
+        self.rank, self.world, self.group, self.device = rank, world, group, device
+        self.n = 1 << log_n
+        self.b0, self.b1, self.per = column_slice(num_polys, rank, world)
+        self.slice = torch.zeros((self.per, self.n), dtype=torch.int64, device=device)   # padded columns stay 0
+        self.coeffs = torch.empty((self.per * world, self.n), dtype=torch.int64, device=device)
+
+    def commit(self, values, from_host):
+        """values: torch int64 tensor holding THIS RANK'S columns [b0, b1) x n (pinned host if from_host, else on
+        the device). Returns the gl_commit handle (row-block shard `rank` of `world`)."""
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _native as N
+
+        L = N.lib()
+        cnt = self.b1 - self.b0
+        if cnt:
+            self.slice[:cnt].copy_(values[:cnt], non_blocking=True)   # H2D of 1/G of the trace (or D2D)
+            N.check(L.gl_ntt(self.ctx.h, C.c_void_p(self.slice.data_ptr()), self.log_n, cnt, self.n, 1, 0, 1,
+                             N.MEM_DEVICE), self.ctx.h)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.coeffs, self.slice, group=self.group)
+            src = self.coeffs
+        else:
+            src = self.slice
+        h = N.vp()
+        N.check(L.gl_commit_create_sharded(self.ctx.h, C.c_void_p(src.data_ptr()), self.n, self.B, self.log_n, self.r,
+                                           self.h, None, 1, N.MEM_DEVICE, self.rank, self.world, C.byref(h)), self.ctx.h)
+        return h

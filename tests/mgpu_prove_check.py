@@ -41,6 +41,23 @@ def main():
     params = pb.FriParams(pb.FriConfig(r, h, 8, ("Fixed", [4, 2]), 12), False, log_n, [4, 2])
     proof = D.prove_openings_sharded(inst, commits, ch, params)
     ok = True
+    # column-sharded iNTT + all-gather of coefficients + row-block sharded LDE/Merkle (ColumnShardedCommitter)
+    import ctypes as C
+    from plonky2_b200 import _native as N_
+    Bc, lg = 11, 12
+    vals_c = synth(0x77, (Bc, 1 << lg))
+    # torch copies / NCCL and the library must share ONE stream: make the context on a torch stream
+    tstream = torch.cuda.Stream(device=dev)
+    ctx2 = pb.Context(local, stream=tstream.cuda_stream)
+    with torch.cuda.stream(tstream):
+        cm = D.ColumnShardedCommitter(ctx2, Bc, lg, 2, 3, rank, world, dev)
+        mine = torch.from_numpy(np.ascontiguousarray(vals_c[cm.b0:cm.b1]).view(np.int64).copy()).pin_memory()
+        hnd = cm.commit(mine, from_host=True)
+        lcap = np.empty(((1 << 3) // world, 4), dtype=np.uint64)
+        N_.check(N_.lib().gl_commit_cap(hnd, N_.np_ptr(lcap), N_.MEM_HOST), ctx2.h)
+        N_.lib().gl_commit_destroy(hnd)
+    torch.cuda.synchronize(dev)
+    full_cap_c = D.gather_cap(lcap, device=dev)
     if rank == 0:
         import oracle_lib
 
@@ -53,6 +70,7 @@ def main():
         obatches = [(b.point, [(p.oracle_index, p.polynomial_index) for p in b.polynomials]) for b in inst.batches]
         oproof = oracle_lib.prove_openings(ocommits, obatches, och, oracle_lib.make_params(r, h, 8, 12, [4, 2]))
         ok &= proof.to_bytes() == oproof
+        ok &= bool(np.array_equal(full_cap_c.hashes, oracle_lib.Commit(vals_c, 2, 3).cap))
         print("MGPU_PROVE_CHECK", "OK" if ok else "FAILED", "world", world, flush=True)
     dist.barrier()
     dist.destroy_process_group()
