@@ -8,8 +8,8 @@
 //
 // This is not a translation of the x86 code: on the device the 64x64->128 product is four IMAD.WIDE.U32
 // (ptxas' carry-in/carry-out forms) and the reduction uses 2^64 = 2^32 - 1, 2^96 = -1 (mod p) with 32-bit
-// carry chains written in PTX (Montgomery-free, as BASELINE.json asks): reduce128 is 12 instructions, a
-// general add 10, a modmul 19 (measured 1.04 T modmul/s on B200, tools/microbench.cu).
+// carry chains written in PTX (Montgomery-free, as BASELINE.json asks): reduce128 is 11 instructions, a
+// general add 10, a modmul 4 IMAD.WIDE + 14 (tools/microbench.cu; tools/variants ranks the formulations).
 #pragma once
 #include <stdint.h>
 
@@ -121,7 +121,7 @@ GL_HD uint64_t neg(uint64_t a) {
 // Reduce hi*2^64 + lo (mod p) to [0, 2^64): lo - (hi >> 32) + (hi & EPS) * EPS
 // (the reference's reduce128, goldilocks_field.rs:401-415, re-expressed on 32-bit halves).
 GL_HD uint64_t reduce128(uint64_t lo, uint64_t hi) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(GL_REDUCE_V1)
     // x = lo - hh (borrow b), r = x + hl*EPS (carry c); true value = r_wrapped + (c - b)*2^64, and
     // 2^64 = EPS (mod p): apply the signed fix-up (c - b)*EPS in one 64-bit add (it cannot wrap).
     uint32_t r0, r1;
@@ -134,6 +134,28 @@ GL_HD uint64_t reduce128(uint64_t lo, uint64_t hi) {
         "add.cc.u32 %0, %0, t0;\n\t"       // r = x + t
         "addc.cc.u32 %1, %1, t1;\n\t"
         "addc.u32 d, nb, 0;\n\t"           // d = c - b in {-1, 0, 1}
+        "neg.s32 f0, d;\n\t"               // d*EPS = (d >> 31 : -d)
+        "shr.s32 f1, d, 31;\n\t"
+        "add.cc.u32 %0, %0, f0;\n\t"
+        "addc.u32 %1, %1, f1;\n\t}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(lo32(lo)), "r"(hi32(lo)), "r"(lo32(hi)), "r"(hi32(hi)));
+    return pack64(r0, r1);
+#elif defined(__CUDA_ARCH__)
+    // value = lo + hl*2^32 - (hl + hh)   (2^64 = 2^32 - 1, 2^96 = -1):  A = lo + (hl << 32) only touches the high
+    // word (carry ca), s = hl + hh is 33 bits, r = A - s (borrow b); true value = r_wrapped + (ca - b)*2^64 and
+    // 2^64 = EPS (mod p): apply the signed fix-up d*EPS, d = ca - b in {-1, 0, 1}, in one 64-bit add. It cannot
+    // wrap: d = 1 means A >= 2^64 so r_wrapped < 2^64 - 2^32 + ... (r = A - 2^64 - s + [0] <= 2^64 - 2^32 - 1);
+    // d = -1 means A < s < 2^33 so r_wrapped = 2^64 + A - s >= 2^64 - 2^33 > EPS.
+    uint32_t r0, r1;
+    asm("{\n\t.reg .u32 s0, s1, a1, ca, d, f0, f1;\n\t"
+        "add.cc.u32 s0, %4, %5;\n\t"       // s = hl + hh
+        "addc.u32 s1, 0, 0;\n\t"
+        "add.cc.u32 a1, %3, %4;\n\t"       // A = lo + (hl << 32)
+        "addc.u32 ca, 0, 0;\n\t"
+        "sub.cc.u32 %0, %2, s0;\n\t"       // r = A - s
+        "subc.cc.u32 %1, a1, s1;\n\t"
+        "subc.u32 d, ca, 0;\n\t"           // d = ca - b
         "neg.s32 f0, d;\n\t"               // d*EPS = (d >> 31 : -d)
         "shr.s32 f1, d, 31;\n\t"
         "add.cc.u32 %0, %0, f0;\n\t"
@@ -177,9 +199,12 @@ GL_HD uint64_t reduce96(uint64_t lo, uint32_t hi) {
 // GL_FORCE_32BIT_PATH lets tests/emu run the device formulation on the host.
 GL_HD void mul_wide(uint64_t a, uint64_t b, uint64_t& lo, uint64_t& hi) {
 #if defined(__CUDA_ARCH__)
-    // ptxas turns this pair into 4 IMAD.WIDE.U32 (one with carry-out, one with carry-in) + 3 adds
-    lo = a * b;
-    hi = __umul64hi(a, b);
+    // One 128-bit product: 4 IMAD.WIDE.U32 (one with carry-out, one with carry-in) + 3 adds/moves. Written as
+    // `lo = a * b; hi = __umul64hi(a, b)` the two halves are lowered separately and ptxas does NOT merge them:
+    // 5 IMAD.WIDE + 2 IMAD + 4 adds (cuobjdump), i.e. +50 % on the FMA-heavy pipe that bounds these kernels.
+    const unsigned __int128 p = (unsigned __int128)a * b;
+    lo = (uint64_t)p;
+    hi = (uint64_t)(p >> 64);
 #elif defined(GL_FORCE_32BIT_PATH)
     uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);
     uint32_t b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
@@ -195,7 +220,29 @@ GL_HD void mul_wide(uint64_t a, uint64_t b, uint64_t& lo, uint64_t& hi) {
 #endif
 }
 GL_HD void sqr_wide(uint64_t a, uint64_t& lo, uint64_t& hi) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(GL_SQR_3WIDE)
+    // Variant: a^2 = a0^2 + 2*a0*a1*2^32 + a1^2*2^64 with THREE IMAD.WIDE.U32 and the cross term added twice on
+    // the ALU pipe. Measured on B200 (tools/variants): 909 vs 953 M perm/s for the generic 4-IMAD.WIDE product --
+    // after the mul_wide fix both integer pipes run at ~65 % and the extra ALU work costs more than it saves.
+    uint32_t r0, r1, r2, r3;
+    asm("{\n\t.reg .u64 z, c, w;\n\t.reg .u32 z1, c0, c1, w0, w1;\n\t"
+        "mul.wide.u32 z, %4, %4;\n\t"
+        "mul.wide.u32 c, %4, %5;\n\t"
+        "mul.wide.u32 w, %5, %5;\n\t"
+        "mov.b64 {%0, z1}, z;\n\t"
+        "mov.b64 {c0, c1}, c;\n\t"
+        "mov.b64 {w0, w1}, w;\n\t"
+        "add.cc.u32 %1, z1, c0;\n\t"
+        "addc.cc.u32 %2, w0, c1;\n\t"
+        "addc.u32 %3, w1, 0;\n\t"
+        "add.cc.u32 %1, %1, c0;\n\t"
+        "addc.cc.u32 %2, %2, c1;\n\t"
+        "addc.u32 %3, %3, 0;\n\t}"
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
+        : "r"(lo32(a)), "r"(hi32(a)));
+    lo = pack64(r0, r1);
+    hi = pack64(r2, r3);
+#elif defined(__CUDA_ARCH__)
     mul_wide(a, a, lo, hi);
 #elif defined(GL_FORCE_32BIT_PATH)
     uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);

@@ -40,6 +40,10 @@ struct PoseidonTables {
     uint32_t mds_00;  // circ[0] + diag[0]
     uint32_t pad_;
     double mds_f64[13];  // the same constants as doubles ([12] = circ[0] + diag[0]) for the FP64-pipe variant
+    // constants that follow full round r's MDS (r = 0..7: rounds 1-3, partial first layer, rounds 27-29, none),
+    // pre-split into 32-bit halves AS DOUBLES ([2i] = low half of lane i, [2i+1] = high half): the FP64 MDS
+    // starts its accumulators from them straight out of the constant bank.
+    double nrc_f64[8][24];
 };
 
 #if defined(__CUDACC__)
@@ -61,6 +65,14 @@ inline const PoseidonTables& host_poseidon_tables() {
         x.pad_ = 0;
         for (int i = 0; i < 12; i++) x.mds_f64[i] = (double)GL_POSEIDON_MDS_CIRC[i];
         x.mds_f64[12] = (double)(GL_POSEIDON_MDS_CIRC[0] + GL_POSEIDON_MDS_DIAG[0]);
+        for (int r = 0; r < 8; r++) {
+            const uint64_t* src = (r < 3) ? &x.rc[12 * (r + 1)] : (r == 3) ? x.fast_first
+                                : (r < 7) ? &x.rc[12 * (r + 23)] : x.zeros;
+            for (int i = 0; i < 12; i++) {
+                x.nrc_f64[r][2 * i] = (double)(uint32_t)src[i];
+                x.nrc_f64[r][2 * i + 1] = (double)(uint32_t)(src[i] >> 32);
+            }
+        }
         return x;
     }();
     return t;
@@ -108,7 +120,9 @@ GL_HD uint64_t sbox7(uint64_t x) {  // sbox_monomial, poseidon.rs:689-696
 // mds_layer (poseidon.rs:269-290; out[r] = sum_i s[(i+r)%12]*circ[i] + s[r]*diag[r]) on 32-bit halves,
 // FUSED with the constant layer that follows it (poseidon.rs:630-641): the accumulators start from the
 // next round's constants `nrc` (canonical u64s), so the constant addition costs nothing.
-GL_HD void mds_layer_add(uint64_t s[12], const uint64_t* nrc) {
+// `nrcd` (device, optional): the same constants pre-split as doubles (PoseidonTables::nrc_f64[r]).
+GL_HD void mds_layer_add(uint64_t s[12], const uint64_t* nrc, const double* nrcd = nullptr) {
+    (void)nrcd;
     const PoseidonTables& T = GL_POS;
 #if defined(__CUDA_ARCH__) && defined(GL_MDS_FP64)
     // Variant: evaluate the 12x12 small-constant products on the FP64 pipe (idle otherwise). Every term is
@@ -119,14 +133,28 @@ GL_HD void mds_layer_add(uint64_t s[12], const uint64_t* nrc) {
         double dl[12], dh[12];
 #pragma unroll
         for (int i = 0; i < 12; i++) {
+#if defined(GL_MDS_I2F)
+            dl[i] = (double)(uint32_t)s[i];          // I2F.F64.U32 (XU pipe) instead of MOV + DADD
+            dh[i] = (double)(uint32_t)(s[i] >> 32);
+#else
             dl[i] = __hiloint2double(0x43300000, (int)(uint32_t)s[i]) - K52;
             dh[i] = __hiloint2double(0x43300000, (int)(uint32_t)(s[i] >> 32)) - K52;
+#endif
         }
 #pragma unroll
         for (int r = 0; r < 12; r++) {
-            const uint64_t c = nrc[r];
-            double al = __hiloint2double(0x43300000, (int)(uint32_t)c) - K52;
-            double ah = __hiloint2double(0x43300000, (int)(uint32_t)(c >> 32)) - K52;
+            double al, ah;
+#if !defined(GL_MDS_RC_CONVERT)
+            if (nrcd) {
+                al = nrcd[2 * r];
+                ah = nrcd[2 * r + 1];
+            } else
+#endif
+            {
+                const uint64_t c = nrc[r];
+                al = __hiloint2double(0x43300000, (int)(uint32_t)c) - K52;
+                ah = __hiloint2double(0x43300000, (int)(uint32_t)(c >> 32)) - K52;
+            }
 #pragma unroll
             for (int i = 0; i < 12; i++) {
                 const double m = (r == 0 && i == 0) ? T.mds_f64[12] : T.mds_f64[i];
@@ -184,10 +212,10 @@ GL_HD void mds_layer(uint64_t s[12]) { mds_layer_add(s, GL_POS.zeros); }
 
 // One full round WITHOUT its own constant layer (already folded into the previous MDS / added by the
 // caller) but WITH the next round's: sbox_layer, then mds_layer + next constants.
-GL_HD void full_round_fused(uint64_t s[12], const uint64_t* next_rc) {
+GL_HD void full_round_fused(uint64_t s[12], const uint64_t* next_rc, const double* next_rcd = nullptr) {
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
-    mds_layer_add(s, next_rc);
+    mds_layer_add(s, next_rc, next_rcd);
 }
 // Plain full round (constant_layer, sbox_layer, mds_layer; poseidon.rs:741-749) -- used by tools/microbench.
 GL_HD void full_round(uint64_t s[12], const uint64_t* rc) {
@@ -216,7 +244,11 @@ GL_HD void poseidon_partial_rounds_noconst(uint64_t s[12]) {
 #pragma unroll
         for (int i = 1; i < 12; i++) s[i] = res[i - 1];
     }
+#if defined(GL_PARTIAL_UNROLL2)
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
     for (int r = 0; r < 22; r++) {
         uint64_t s0 = add_canonical(sbox7(s[0]), T.fast_rc[r]);
         // mds_partial_layer_fast (poseidon.rs:514-542)
@@ -251,7 +283,7 @@ GL_HD void poseidon_permute_t(uint64_t s[12]) {
         // or nothing (after the partial rounds the 5th full round's constants are added explicitly)
         const uint64_t* nrc = (r < 3) ? &T.rc[12 * (r + 1)] : (r == 3) ? T.fast_first
                             : (r < 7) ? &T.rc[12 * (r + 23)] : T.zeros;
-        full_round_fused(s, nrc);
+        full_round_fused(s, nrc, T.nrc_f64[r]);
 #if defined(__CUDA_ARCH__)
         if (SYNC) __syncthreads();
 #endif
