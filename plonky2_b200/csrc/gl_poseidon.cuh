@@ -22,6 +22,16 @@
 #if !defined(GL_MDS_INT) && !defined(GL_MDS_FP64)
 #define GL_MDS_FP64 1
 #endif
+// The FP64 formulation is device code; tests/emu compiles it for the host too (-DGL_FP64_ON_HOST) to check its
+// exactness argument against the integer formulation without a GPU (IEEE doubles and fma behave identically).
+#if defined(GL_MDS_FP64) && (defined(__CUDA_ARCH__) || defined(GL_FP64_ON_HOST))
+#define GL_FP64_PATH 1
+#endif
+// Partial rounds: FP64-resident by default where the FP64 path exists (see poseidon_partial_rounds_f64);
+// -DGL_PARTIAL_FAST selects the integer "fast" factorisation (w_hat / v vectors) everywhere.
+#if defined(GL_FP64_PATH) && !defined(GL_PARTIAL_FAST)
+#define GL_PARTIAL_F64 1
+#endif
 
 namespace gl {
 
@@ -43,7 +53,14 @@ struct PoseidonTables {
     // constants that follow full round r's MDS (r = 0..7: rounds 1-3, partial first layer, rounds 27-29, none),
     // pre-split into 32-bit halves AS DOUBLES ([2i] = low half of lane i, [2i+1] = high half): the FP64 MDS
     // starts its accumulators from them straight out of the constant bank.
-    double nrc_f64[8][24];
+    // row 8: the ORIGINAL first partial-round constants (ALL_ROUND_CONSTANTS[48..59]) for the FP64-resident
+    // partial rounds, which run in the original (non-"fast") basis.
+    double nrc_f64[9][24];
+    // FP64-resident partial rounds: constants added after partial round r's MDS (= the next round's constant
+    // layer, ALL_ROUND_CONSTANTS[12*(5+r) + i]), split like nrc_f64, PLUS a bias (bl, bh) with
+    // bl + 2^32*bh = 2^18 * p = 0 (mod p) on every lane that is converted back to an integer after that
+    // round (lane 0 always; all lanes after the last one) so that the signed limbs become positive.
+    double prc_f64[22][24];
 };
 
 #if defined(__CUDACC__)
@@ -65,12 +82,22 @@ inline const PoseidonTables& host_poseidon_tables() {
         x.pad_ = 0;
         for (int i = 0; i < 12; i++) x.mds_f64[i] = (double)GL_POSEIDON_MDS_CIRC[i];
         x.mds_f64[12] = (double)(GL_POSEIDON_MDS_CIRC[0] + GL_POSEIDON_MDS_DIAG[0]);
-        for (int r = 0; r < 8; r++) {
+        for (int r = 0; r < 9; r++) {
             const uint64_t* src = (r < 3) ? &x.rc[12 * (r + 1)] : (r == 3) ? x.fast_first
-                                : (r < 7) ? &x.rc[12 * (r + 23)] : x.zeros;
+                                : (r < 7) ? &x.rc[12 * (r + 23)] : (r == 7) ? x.zeros : &x.rc[48];
             for (int i = 0; i < 12; i++) {
                 x.nrc_f64[r][2 * i] = (double)(uint32_t)src[i];
                 x.nrc_f64[r][2 * i + 1] = (double)(uint32_t)(src[i] >> 32);
+            }
+        }
+        // bias: bl = 2^50 + 2^18, bh = 2^50 - 2^19;  bl + 2^32*bh = 2^82 - 2^50 + 2^18 = 2^18 * p
+        const double bl = 1125899906842624.0 + 262144.0, bh = 1125899906842624.0 - 524288.0;
+        for (int r = 0; r < 22; r++) {
+            const uint64_t* src = &x.rc[12 * (5 + r)];
+            for (int i = 0; i < 12; i++) {
+                const bool biased = (i == 0) || (r == 21);
+                x.prc_f64[r][2 * i] = (double)(uint32_t)src[i] + (biased ? bl : 0.0);
+                x.prc_f64[r][2 * i + 1] = (double)(uint32_t)(src[i] >> 32) + (biased ? bh : 0.0);
             }
         }
         return x;
@@ -110,6 +137,58 @@ GL_HD uint64_t acc_reduce(const Acc160& a) {
     return sub(r, (uint64_t)a.top << 32);
 }
 
+#if !defined(GL_F64_TRACK)
+#define GL_F64_TRACK(x)  // tests/emu hooks the largest limb magnitude here
+#endif
+#if defined(GL_FP64_PATH)
+// ---- exact integer arithmetic on the FP64 pipe: every double below holds an integer of magnitude < 2^53 ----
+GL_HD double f64_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return fma(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+GL_HD double u32_to_f64(uint32_t x) {
+#if defined(__CUDA_ARCH__) && !defined(GL_MDS_I2F)
+    return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0;  // bits(2^52 + x) = 0x43300000:x
+#else
+    return (double)x;
+#endif
+}
+// al + 2^32 * ah (mod p) for NON-NEGATIVE integers al, ah < 2^52 held in doubles.
+GL_HD uint64_t f64_pair_to_u64(double al, double ah) {
+#if defined(__CUDA_ARCH__)
+    // bits(2^52 + v) = 0x43300000 | (v >> 32) : (v & 0xffffffff) for v < 2^52
+    const double bl = al + 4503599627370496.0, bh = ah + 4503599627370496.0;
+    const uint32_t al0 = (uint32_t)__double2loint(bl), al1 = (uint32_t)__double2hiint(bl) & 0xFFFFFu;
+    const uint32_t ah0 = (uint32_t)__double2loint(bh), ah1 = (uint32_t)__double2hiint(bh) & 0xFFFFFu;
+    uint32_t r1, r2;
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(r1), "=r"(r2) : "r"(al1), "r"(ah0), "r"(ah1));
+    return reduce96(pack64(al0, r1), r2);
+#else
+    const unsigned __int128 v = (unsigned __int128)(uint64_t)al + ((unsigned __int128)(uint64_t)ah << 32);
+    return reduce96((uint64_t)v, (uint32_t)(v >> 64));
+#endif
+}
+// v <- c + MDS * v for one limb vector (circulant first row mds_f64[0..11], +diag 8 on lane 0 = mds_f64[12]);
+// c[2*j] is lane j's constant (the caller offsets c by one for the high limbs).
+GL_HD void mds_f64_inplace(double v[12], const double* c) {
+    const PoseidonTables& T = GL_POS;
+    double n[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        double a = c[2 * j];
+#pragma unroll
+        for (int i = 0; i < 12; i++) a = f64_fma(v[(i + j) % 12], (j == 0 && i == 0) ? T.mds_f64[12] : T.mds_f64[i], a);
+        n[j] = a;
+        GL_F64_TRACK(a);
+    }
+#pragma unroll
+    for (int j = 0; j < 12; j++) v[j] = n[j];
+}
+#endif  // GL_FP64_PATH
+
 GL_HD uint64_t sbox7(uint64_t x) {  // sbox_monomial, poseidon.rs:689-696
     uint64_t x2 = sqr(x);
     uint64_t x4 = sqr(x2);
@@ -124,22 +203,15 @@ GL_HD uint64_t sbox7(uint64_t x) {  // sbox_monomial, poseidon.rs:689-696
 GL_HD void mds_layer_add(uint64_t s[12], const uint64_t* nrc, const double* nrcd = nullptr) {
     (void)nrcd;
     const PoseidonTables& T = GL_POS;
-#if defined(__CUDA_ARCH__) && defined(GL_MDS_FP64)
-    // Variant: evaluate the 12x12 small-constant products on the FP64 pipe (idle otherwise). Every term is
+#if defined(GL_FP64_PATH)
+    // Evaluate the 12x12 small-constant products on the FP64 pipe (idle otherwise). Every term is
     // (32-bit half) x (6-bit constant) and a 13-term sum stays < 2^42, so double arithmetic is EXACT.
-    // Conversions use the 2^52 trick: bits(2^52 + x) = 0x43300000:x for x < 2^32.
     {
-        const double K52 = 4503599627370496.0;  // 2^52
         double dl[12], dh[12];
 #pragma unroll
         for (int i = 0; i < 12; i++) {
-#if defined(GL_MDS_I2F)
-            dl[i] = (double)(uint32_t)s[i];          // I2F.F64.U32 (XU pipe) instead of MOV + DADD
-            dh[i] = (double)(uint32_t)(s[i] >> 32);
-#else
-            dl[i] = __hiloint2double(0x43300000, (int)(uint32_t)s[i]) - K52;
-            dh[i] = __hiloint2double(0x43300000, (int)(uint32_t)(s[i] >> 32)) - K52;
-#endif
+            dl[i] = u32_to_f64((uint32_t)s[i]);
+            dh[i] = u32_to_f64((uint32_t)(s[i] >> 32));
         }
 #pragma unroll
         for (int r = 0; r < 12; r++) {
@@ -152,22 +224,16 @@ GL_HD void mds_layer_add(uint64_t s[12], const uint64_t* nrc, const double* nrcd
 #endif
             {
                 const uint64_t c = nrc[r];
-                al = __hiloint2double(0x43300000, (int)(uint32_t)c) - K52;
-                ah = __hiloint2double(0x43300000, (int)(uint32_t)(c >> 32)) - K52;
+                al = u32_to_f64((uint32_t)c);
+                ah = u32_to_f64((uint32_t)(c >> 32));
             }
 #pragma unroll
             for (int i = 0; i < 12; i++) {
                 const double m = (r == 0 && i == 0) ? T.mds_f64[12] : T.mds_f64[i];
-                al = fma(dl[(i + r) % 12], m, al);
-                ah = fma(dh[(i + r) % 12], m, ah);
+                al = f64_fma(dl[(i + r) % 12], m, al);
+                ah = f64_fma(dh[(i + r) % 12], m, ah);
             }
-            // back to integers: bits(2^52 + v) = 0x43300000 | (v >> 32) : (v & 0xffffffff), v < 2^42
-            const double bl = al + K52, bh = ah + K52;
-            const uint32_t al0 = (uint32_t)__double2loint(bl), al1 = (uint32_t)__double2hiint(bl) & 0xFFFFFu;
-            const uint32_t ah0 = (uint32_t)__double2loint(bh), ah1 = (uint32_t)__double2hiint(bh) & 0xFFFFFu;
-            uint32_t r1, r2;
-            asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(r1), "=r"(r2) : "r"(al1), "r"(ah0), "r"(ah1));
-            s[r] = reduce96(pack64(al0, r1), r2);
+            s[r] = f64_pair_to_u64(al, ah);
         }
     }
 #else
@@ -261,6 +327,63 @@ GL_HD void poseidon_partial_rounds_noconst(uint64_t s[12]) {
         s[0] = acc_reduce(a);
     }
 }
+#if defined(GL_FP64_PATH)
+// partial_rounds (poseidon.rs:751-764) in the ORIGINAL basis (constant_layer, x^7 on lane 0, mds_layer -- the
+// reference's poseidon_naive form, poseidon.rs:779-801), with lanes 1..11 kept RESIDENT ON THE FP64 PIPE:
+// they pass through no non-linearity for 22 rounds, only through the small-constant circulant MDS, so each lane
+// is held as two doubles (L, H), value = L + 2^32*H (mod p), and a round is 288 DFMAs with the next round's
+// constants as accumulator seeds. Only lane 0 crosses to the integer pipes each round (x^7). Exactness: limbs
+// are integers; after a renormalisation |L|, |H| <= 2^31 + 2^18, one MDS multiplies magnitudes by <= 264
+// (+ constants < 2^32), so two rounds stay < 2^48.2 < 2^53; then each lane is renormalised ON THE FP64 PIPE
+// (round-to-multiple-of-2^32 via the 1.5*2^84 trick, 2^64 = 2^32 - 1) -- 9 FP64 ops per lane every other round.
+// Lane 0's limbs can be negative by < 2^48.2, so its constants carry a bias (bl, bh) = 0 (mod p) of 2^50
+// (PoseidonTables::prc_f64) and f64_pair_to_u64 sees non-negative integers < 2^51.
+// Versus the "fast" integer form (23 64x64 products + 12 reductions per round on the ALU/FMA-heavy pipes that
+// bound this kernel): no init matrix, ~80 integer instructions per round instead of ~520.
+// In: s after full round 4's MDS + first partial constant layer. Out: s after the last partial round's MDS +
+// the 5th full round's constant layer.
+GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
+    const PoseidonTables& T = GL_POS;
+    double L[12], H[12];
+#pragma unroll
+    for (int i = 1; i < 12; i++) {
+        L[i] = u32_to_f64((uint32_t)s[i]);
+        H[i] = u32_to_f64((uint32_t)(s[i] >> 32));
+    }
+    uint64_t s0 = s[0];
+#pragma unroll 1
+    for (int rp = 0; rp < 11; rp++) {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const double* c = T.prc_f64[2 * rp + q];
+            const uint64_t y = sbox7(s0);
+            L[0] = u32_to_f64((uint32_t)y);
+            H[0] = u32_to_f64((uint32_t)(y >> 32));
+            mds_f64_inplace(L, c);
+            mds_f64_inplace(H, c + 1);
+            s0 = f64_pair_to_u64(L[0], H[0]);
+        }
+        if (rp != 10) {
+            const double C84 = 29014219670751100192948224.0;  // 1.5 * 2^84: x + C84 is rounded to a multiple of 2^32
+            const double I32 = 2.3283064365386962890625e-10;  // 2^-32
+#pragma unroll
+            for (int i = 1; i < 12; i++) {
+                // H = Hlo + th (th multiple of 2^32, kH = th/2^32): 2^64*kH = (2^32 - 1)*kH moves kH into H, -kH into L
+                const double th = (H[i] + C84) - C84;
+                const double hlo = H[i] - th;
+                const double l2 = f64_fma(th, -I32, L[i]);
+                const double tl = (l2 + C84) - C84;  // L carry kL = tl/2^32 moves into H
+                L[i] = l2 - tl;
+                H[i] = f64_fma(tl, I32, f64_fma(th, I32, hlo));
+            }
+        }
+    }
+    s[0] = s0;
+#pragma unroll
+    for (int i = 1; i < 12; i++) s[i] = f64_pair_to_u64(L[i], H[i]);
+}
+#endif  // GL_FP64_PATH
+
 GL_HD void poseidon_partial_rounds(uint64_t s[12]) {
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = add_canonical(s[i], GL_POS.fast_first[i]);
@@ -281,16 +404,26 @@ GL_HD void poseidon_permute_t(uint64_t s[12]) {
     for (int r = 0; r < 8; r++) {
         // constants that follow this round's MDS: next full round's, or the partial rounds' first layer,
         // or nothing (after the partial rounds the 5th full round's constants are added explicitly)
+#if defined(GL_PARTIAL_F64)
+        const uint64_t* nrc = (r < 3) ? &T.rc[12 * (r + 1)] : (r == 3) ? &T.rc[48]
+                            : (r < 7) ? &T.rc[12 * (r + 23)] : T.zeros;
+        full_round_fused(s, nrc, T.nrc_f64[r == 3 ? 8 : r]);
+#else
         const uint64_t* nrc = (r < 3) ? &T.rc[12 * (r + 1)] : (r == 3) ? T.fast_first
                             : (r < 7) ? &T.rc[12 * (r + 23)] : T.zeros;
         full_round_fused(s, nrc, T.nrc_f64[r]);
+#endif
 #if defined(__CUDA_ARCH__)
         if (SYNC) __syncthreads();
 #endif
         if (r == 3) {
+#if defined(GL_PARTIAL_F64)
+            poseidon_partial_rounds_f64(s);  // ends with the 5th full round's constant layer folded in
+#else
             poseidon_partial_rounds_noconst(s);
 #pragma unroll
             for (int i = 0; i < 12; i++) s[i] = add_canonical(s[i], T.rc[12 * 26 + i]);
+#endif
         }
     }
 }
