@@ -61,6 +61,16 @@ struct PoseidonTables {
     // bl + 2^32*bh = 2^18 * p = 0 (mod p) on every lane that is converted back to an integer after that
     // round (lane 0 always; all lanes after the last one) so that the signed limbs become positive.
     double prc_f64[22][24];
+    // Two partial rounds as ONE linear step (poseidon_partial_rounds_f64): with x~ = (x0^7, x1..x11), the state
+    // after rounds A, B is  Q*x~ + z0*M[:,0] + k  where z0 = ((M*x~)_0 + cA_0)^7, Q = M*diag(0,1..1)*M and
+    // k = M*diag(0,1..1)*cA + cB (mod p). pq_f64 = Q (entries < 2^14.1, row sums <= 264^2), pm0_f64 = M[:,0],
+    // pk_f64[pair] = k split in 32-bit halves (+ bias where a lane is converted to an integer afterwards),
+    // pa_f64[pair] = cA_0 split (+ bias).
+    double pq_f64[12][12];
+    double pq2_f64[12][12];  // second copy of Q for the high limbs: keeps nvcc from caching 144 constants in registers
+    double pm0_f64[12];
+    double pk_f64[11][24];
+    double pa_f64[11][2];
 };
 
 #if defined(__CUDACC__)
@@ -100,6 +110,33 @@ inline const PoseidonTables& host_poseidon_tables() {
                 x.prc_f64[r][2 * i + 1] = (double)(uint32_t)(src[i] >> 32) + (biased ? bh : 0.0);
             }
         }
+        // pair tables
+        uint64_t M[12][12];
+        for (int i = 0; i < 12; i++)
+            for (int j = 0; j < 12; j++)
+                M[i][j] = GL_POSEIDON_MDS_CIRC[(j - i + 12) % 12] + ((i == 0 && j == 0) ? GL_POSEIDON_MDS_DIAG[0] : 0);
+        for (int i = 0; i < 12; i++) {
+            x.pm0_f64[i] = (double)M[i][0];
+            for (int j = 0; j < 12; j++) {
+                uint64_t q = 0;
+                for (int k = 1; k < 12; k++) q += M[i][k] * M[k][j];
+                x.pq_f64[i][j] = x.pq2_f64[i][j] = (double)q;
+            }
+        }
+        for (int pr = 0; pr < 11; pr++) {
+            const uint64_t* cA = &x.rc[12 * (5 + 2 * pr)];      // constants after round A = 2*pr
+            const uint64_t* cB = &x.rc[12 * (5 + 2 * pr + 1)];  // constants after round B = 2*pr + 1
+            x.pa_f64[pr][0] = (double)(uint32_t)cA[0] + bl;
+            x.pa_f64[pr][1] = (double)(uint32_t)(cA[0] >> 32) + bh;
+            for (int i = 0; i < 12; i++) {
+                unsigned __int128 k = cB[i];
+                for (int t = 1; t < 12; t++) k += (unsigned __int128)M[i][t] * cA[t];
+                const uint64_t kr = (uint64_t)(k % (unsigned __int128)0xFFFFFFFF00000001ULL);
+                const bool biased = (i == 0) || (pr == 10);
+                x.pk_f64[pr][2 * i] = (double)(uint32_t)kr + (biased ? bl : 0.0);
+                x.pk_f64[pr][2 * i + 1] = (double)(uint32_t)(kr >> 32) + (biased ? bh : 0.0);
+            }
+        }
         return x;
     }();
     return t;
@@ -135,6 +172,19 @@ GL_HD uint64_t acc_reduce(const Acc160& a) {
     // top*2^128 + hi*2^64 + lo ; 2^128 = 2^96 * 2^32 = -2^32 (mod p)
     uint64_t r = reduce128(a.lo, a.hi);
     return sub(r, (uint64_t)a.top << 32);
+}
+
+// Compile-time copies of the MDS matrix M[i][j] = circ[(j - i) mod 12] (+ diag on [0][0]) and of
+// Q = M * diag(0,1,...,1) * M (two partial rounds as one linear step), so that fully unrolled FP64 code gets
+// them as literal operands.
+GL_HD constexpr uint32_t mds_entry(int i, int j) {
+    constexpr uint32_t circ[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};  // poseidon_goldilocks.rs:24
+    return circ[(j - i + 12) % 12] + ((i == 0 && j == 0) ? 8u : 0u);                  // diag = [8, 0, ...]: :25
+}
+GL_HD constexpr double mds_pair_entry(int i, int j) {
+    uint32_t q = 0;
+    for (int k = 1; k < 12; k++) q += mds_entry(i, k) * mds_entry(k, j);
+    return (double)q;
 }
 
 #if !defined(GL_F64_TRACK)
@@ -229,7 +279,11 @@ GL_HD void mds_layer_add(uint64_t s[12], const uint64_t* nrc, const double* nrcd
             }
 #pragma unroll
             for (int i = 0; i < 12; i++) {
+#if !defined(GL_MDS_LITERAL)
                 const double m = (r == 0 && i == 0) ? T.mds_f64[12] : T.mds_f64[i];
+#else
+                const double m = (double)mds_entry(r, (i + r) % 12);  // literal: DFMA takes it as an immediate
+#endif
                 al = f64_fma(dl[(i + r) % 12], m, al);
                 ah = f64_fma(dh[(i + r) % 12], m, ah);
             }
@@ -342,7 +396,7 @@ GL_HD void poseidon_partial_rounds_noconst(uint64_t s[12]) {
 // bound this kernel): no init matrix, ~80 integer instructions per round instead of ~520.
 // In: s after full round 4's MDS + first partial constant layer. Out: s after the last partial round's MDS +
 // the 5th full round's constant layer.
-GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
+GL_HD void poseidon_partial_rounds_f64_v1(uint64_t s[12]) {
     const PoseidonTables& T = GL_POS;
     double L[12], H[12];
 #pragma unroll
@@ -373,6 +427,86 @@ GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
                 const double hlo = H[i] - th;
                 const double l2 = f64_fma(th, -I32, L[i]);
                 const double tl = (l2 + C84) - C84;  // L carry kL = tl/2^32 moves into H
+                L[i] = l2 - tl;
+                H[i] = f64_fma(tl, I32, f64_fma(th, I32, hlo));
+            }
+        }
+    }
+    s[0] = s0;
+#pragma unroll
+    for (int i = 1; i < 12; i++) s[i] = f64_pair_to_u64(L[i], H[i]);
+}
+// Same, two rounds per linear step: lanes 1..11 only see the MDS twice between renormalisations, and lane 0's
+// second S-box input needs just row 0 of the first MDS, so a PAIR of rounds is
+//     a  = (M x~)_0 + cA_0            (12 DFMAs per limb)        x~ = (x0^7, x1..x11)
+//     x' = Q x~ + a^7 * M[:,0] + k    (156 DFMAs per limb)       Q = M diag(0,1..1) M,  k = M diag(0,1..1) cA + cB
+// = 336 DFMAs instead of 576, with the same magnitude bound as two separate rounds (row sums of Q <= 264^2).
+// Q, M[:,0] are round-independent and read straight from the constant bank as DFMA operands.
+template <bool SYNC = false>
+GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
+    const PoseidonTables& T = GL_POS;
+    double L[12], H[12];
+#pragma unroll
+    for (int i = 1; i < 12; i++) {
+        L[i] = u32_to_f64((uint32_t)s[i]);
+        H[i] = u32_to_f64((uint32_t)(s[i] >> 32));
+    }
+    uint64_t s0 = s[0];
+#pragma unroll 1
+    for (int rp = 0; rp < 11; rp++) {
+        const uint64_t y = sbox7(s0);
+        L[0] = u32_to_f64((uint32_t)y);
+        H[0] = u32_to_f64((uint32_t)(y >> 32));
+        double aL = T.pa_f64[rp][0], aH = T.pa_f64[rp][1];
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            aL = f64_fma(L[j], (double)mds_entry(0, j), aL);
+            aH = f64_fma(H[j], (double)mds_entry(0, j), aH);
+        }
+        GL_F64_TRACK(aL);
+        GL_F64_TRACK(aH);
+        const uint64_t z = sbox7(f64_pair_to_u64(aL, aH));
+        const double zL = u32_to_f64((uint32_t)z), zH = u32_to_f64((uint32_t)(z >> 32));
+        const double* k = T.pk_f64[rp];
+        {
+            double n[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                double a = f64_fma(zL, (double)mds_entry(i, 0), k[2 * i]);
+#pragma unroll
+                for (int j = 0; j < 12; j++) a = f64_fma(L[j], mds_pair_entry(i, j), a);
+                n[i] = a;
+                GL_F64_TRACK(a);
+            }
+#pragma unroll
+            for (int i = 0; i < 12; i++) L[i] = n[i];
+        }
+        {
+            double n[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                double a = f64_fma(zH, (double)mds_entry(i, 0), k[2 * i + 1]);
+#pragma unroll
+                for (int j = 0; j < 12; j++) a = f64_fma(H[j], mds_pair_entry(i, j), a);
+                n[i] = a;
+                GL_F64_TRACK(a);
+            }
+#pragma unroll
+            for (int i = 0; i < 12; i++) H[i] = n[i];
+        }
+        s0 = f64_pair_to_u64(L[0], H[0]);
+#if defined(__CUDA_ARCH__) && defined(GL_PARTIAL_SYNC)
+        if (SYNC) __syncthreads();  // same instruction-cache argument as the per-full-round barrier
+#endif
+        if (rp != 10) {
+            const double C84 = 29014219670751100192948224.0;  // 1.5 * 2^84: x + C84 is rounded to a multiple of 2^32
+            const double I32 = 2.3283064365386962890625e-10;  // 2^-32
+#pragma unroll
+            for (int i = 1; i < 12; i++) {
+                const double th = (H[i] + C84) - C84;
+                const double hlo = H[i] - th;
+                const double l2 = f64_fma(th, -I32, L[i]);
+                const double tl = (l2 + C84) - C84;
                 L[i] = l2 - tl;
                 H[i] = f64_fma(tl, I32, f64_fma(th, I32, hlo));
             }
@@ -418,7 +552,11 @@ GL_HD void poseidon_permute_t(uint64_t s[12]) {
 #endif
         if (r == 3) {
 #if defined(GL_PARTIAL_F64)
-            poseidon_partial_rounds_f64(s);  // ends with the 5th full round's constant layer folded in
+#if defined(GL_PARTIAL_F64_V1)
+            poseidon_partial_rounds_f64_v1(s);
+#else
+            poseidon_partial_rounds_f64<SYNC>(s);  // ends with the 5th full round's constant layer folded in
+#endif
 #else
             poseidon_partial_rounds_noconst(s);
 #pragma unroll
