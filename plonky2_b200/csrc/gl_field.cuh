@@ -202,9 +202,34 @@ GL_HD void mul_wide(uint64_t a, uint64_t b, uint64_t& lo, uint64_t& hi) {
     // One 128-bit product: 4 IMAD.WIDE.U32 (one with carry-out, one with carry-in) + 3 adds/moves. Written as
     // `lo = a * b; hi = __umul64hi(a, b)` the two halves are lowered separately and ptxas does NOT merge them:
     // 5 IMAD.WIDE + 2 IMAD + 4 adds (cuobjdump), i.e. +50 % on the FMA-heavy pipe that bounds these kernels.
+#if defined(GL_MUL_EXPLICIT)
+    // Variant: four independent IMAD.WIDE.U32 and the column sums on the ALU pipe (3-input IADD3 chains), instead
+    // of ptxas' carry-in/carry-out IMAD.WIDE forms + IMAD.X + IMAD.MOV (all on the FMA-heavy pipe).
+    uint32_t r0, r1, r2, r3;
+    asm("{\n\t.reg .u64 z, x, y, w;\n\t.reg .u32 z1, x0, x1, y0, y1, w0, w1;\n\t"
+        "mul.wide.u32 z, %4, %6;\n\t"
+        "mul.wide.u32 x, %5, %6;\n\t"
+        "mul.wide.u32 y, %4, %7;\n\t"
+        "mul.wide.u32 w, %5, %7;\n\t"
+        "mov.b64 {%0, z1}, z;\n\t"
+        "mov.b64 {x0, x1}, x;\n\t"
+        "mov.b64 {y0, y1}, y;\n\t"
+        "mov.b64 {w0, w1}, w;\n\t"
+        "add.cc.u32 %1, z1, x0;\n\t"
+        "addc.cc.u32 %2, w0, x1;\n\t"
+        "addc.u32 %3, w1, 0;\n\t"
+        "add.cc.u32 %1, %1, y0;\n\t"
+        "addc.cc.u32 %2, %2, y1;\n\t"
+        "addc.u32 %3, %3, 0;\n\t}"
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
+        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+    lo = pack64(r0, r1);
+    hi = pack64(r2, r3);
+#else
     const unsigned __int128 p = (unsigned __int128)a * b;
     lo = (uint64_t)p;
     hi = (uint64_t)(p >> 64);
+#endif
 #elif defined(GL_FORCE_32BIT_PATH)
     uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);
     uint32_t b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);

@@ -56,6 +56,9 @@ struct PoseidonTables {
     // row 8: the ORIGINAL first partial-round constants (ALL_ROUND_CONSTANTS[48..59]) for the FP64-resident
     // partial rounds, which run in the original (non-"fast") basis.
     double nrc_f64[9][24];
+    // the same rows + the bias (bl2, bh2) = (2^42 + 2^10, 2^42 - 2^11) = 0 (mod p) on every lane, for MDS inputs
+    // that come from sbox7_f64 (signed low limbs, |L| < 2^33.6)
+    double nrcb_f64[9][24];
     // FP64-resident partial rounds: constants added after partial round r's MDS (= the next round's constant
     // layer, ALL_ROUND_CONSTANTS[12*(5+r) + i]), split like nrc_f64, PLUS a bias (bl, bh) with
     // bl + 2^32*bh = 2^18 * p = 0 (mod p) on every lane that is converted back to an integer after that
@@ -71,6 +74,7 @@ struct PoseidonTables {
     double pm0_f64[12];
     double pk_f64[11][24];
     double pa_f64[11][2];
+    double pkb_f64[11][24];  // pk_f64 with the bias on EVERY lane (variant GL_RENORM_INT: renormalise via integers)
 };
 
 #if defined(__CUDACC__)
@@ -98,6 +102,9 @@ inline const PoseidonTables& host_poseidon_tables() {
             for (int i = 0; i < 12; i++) {
                 x.nrc_f64[r][2 * i] = (double)(uint32_t)src[i];
                 x.nrc_f64[r][2 * i + 1] = (double)(uint32_t)(src[i] >> 32);
+                // bl2 + 2^32*bh2 = 2^10 + 2^42 + 2^74 - 2^43 = 2^74 - 2^42 + 2^10 = 2^10 * p
+                x.nrcb_f64[r][2 * i] = x.nrc_f64[r][2 * i] + (4398046511104.0 + 1024.0);
+                x.nrcb_f64[r][2 * i + 1] = x.nrc_f64[r][2 * i + 1] + (4398046511104.0 - 2048.0);
             }
         }
         // bias: bl = 2^50 + 2^18, bh = 2^50 - 2^19;  bl + 2^32*bh = 2^82 - 2^50 + 2^18 = 2^18 * p
@@ -135,6 +142,8 @@ inline const PoseidonTables& host_poseidon_tables() {
                 const bool biased = (i == 0) || (pr == 10);
                 x.pk_f64[pr][2 * i] = (double)(uint32_t)kr + (biased ? bl : 0.0);
                 x.pk_f64[pr][2 * i + 1] = (double)(uint32_t)(kr >> 32) + (biased ? bh : 0.0);
+                x.pkb_f64[pr][2 * i] = (double)(uint32_t)kr + bl;
+                x.pkb_f64[pr][2 * i + 1] = (double)(uint32_t)(kr >> 32) + bh;
             }
         }
         return x;
@@ -200,15 +209,21 @@ GL_HD double f64_fma(double a, double b, double c) {
 #endif
 }
 GL_HD double u32_to_f64(uint32_t x) {
-#if defined(__CUDA_ARCH__) && !defined(GL_MDS_I2F)
-    return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0;  // bits(2^52 + x) = 0x43300000:x
+#if defined(__CUDA_ARCH__) && defined(GL_CVT_MAGIC)
+    return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0;  // bits(2^52 + x) = 0x43300000:x (MOV + DADD)
 #else
-    return (double)x;
+    return (double)x;  // I2F.F64.U32 on the (idle) XU pipe: one instruction, exact
 #endif
 }
 // al + 2^32 * ah (mod p) for NON-NEGATIVE integers al, ah < 2^52 held in doubles.
 GL_HD uint64_t f64_pair_to_u64(double al, double ah) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(GL_CVT_MAGIC)
+    // F2I.U64.F64 (XU pipe, exact on integers) instead of the 2^52 magic add (FP64 pipe) + mask: fewer instructions
+    const uint64_t ul = __double2ull_rz(al), uh = __double2ull_rz(ah);
+    uint32_t r1, r2;
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(r1), "=r"(r2) : "r"(hi32(ul)), "r"(lo32(uh)), "r"(hi32(uh)));
+    return reduce96(pack64(lo32(ul), r1), r2);
+#elif defined(__CUDA_ARCH__)
     // bits(2^52 + v) = 0x43300000 | (v >> 32) : (v & 0xffffffff) for v < 2^52
     const double bl = al + 4503599627370496.0, bh = ah + 4503599627370496.0;
     const uint32_t al0 = (uint32_t)__double2loint(bl), al1 = (uint32_t)__double2hiint(bl) & 0xFFFFFu;
@@ -245,6 +260,36 @@ GL_HD uint64_t sbox7(uint64_t x) {  // sbox_monomial, poseidon.rs:689-696
     uint64_t x3 = mul(x, x2);
     return mul(x3, x4);
 }
+
+#if defined(GL_FP64_PATH)
+// x^7 handed to the FP64 MDS WITHOUT the last modular reduction: with x^3 * x^4 = (p3 p2 p1 p0) in 32-bit
+// words, 2^64 = 2^32 - 1 and 2^96 = -1 give  x^7 = (p0 - p2 - p3) + 2^32 * (p1 + p2)  (mod p), i.e. exactly a
+// (signed) limb pair (L, H), |L| < 2^33.6, 0 <= H < 2^33: three FP64 adds replace the 11-instruction integer
+// reduce128, and the MDS constants carry a bias = 0 (mod p) that makes its outputs positive again.
+GL_HD void sbox7_f64(uint64_t x, double& L, double& H) {
+    const uint64_t x2 = sqr(x);
+    const uint64_t x4 = sqr(x2);
+    const uint64_t x3 = mul(x, x2);
+    uint64_t lo, hi;
+    mul_wide(x3, x4, lo, hi);
+#if defined(__CUDA_ARCH__) && defined(GL_SBOX_INTLIMBS)
+    // Variant: form the two limbs on the ALU pipe (6 adds) and convert them with two 64-bit I2F (XU pipe)
+    uint32_t l0, l1, h0, h1;
+    asm("sub.cc.u32 %0, %4, %6;\n\tsubc.u32 %1, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, %7;\n\tsubc.u32 %1, %1, 0;\n\t"
+        "add.cc.u32 %2, %5, %6;\n\taddc.u32 %3, 0, 0;"
+        : "=&r"(l0), "=&r"(l1), "=&r"(h0), "=&r"(h1)
+        : "r"(lo32(lo)), "r"(hi32(lo)), "r"(lo32(hi)), "r"(hi32(hi)));
+    L = (double)(long long)pack64(l0, l1);
+    H = (double)(unsigned long long)pack64(h0, h1);
+#else
+    const double d0 = u32_to_f64((uint32_t)lo), d1 = u32_to_f64((uint32_t)(lo >> 32));
+    const double d2 = u32_to_f64((uint32_t)hi), d3 = u32_to_f64((uint32_t)(hi >> 32));
+    L = (d0 - d2) - d3;
+    H = d1 + d2;
+#endif
+}
+#endif
 
 // mds_layer (poseidon.rs:269-290; out[r] = sum_i s[(i+r)%12]*circ[i] + s[r]*diag[r]) on 32-bit halves,
 // FUSED with the constant layer that follows it (poseidon.rs:630-641): the accumulators start from the
@@ -337,6 +382,32 @@ GL_HD void full_round_fused(uint64_t s[12], const uint64_t* next_rc, const doubl
     for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
     mds_layer_add(s, next_rc, next_rcd);
 }
+#if defined(GL_FP64_PATH)
+// The same round with the S-box outputs going straight to the FP64 pipe (sbox7_f64); `rcb` = a row of
+// PoseidonTables::nrcb_f64 (next constants + bias).
+GL_HD void full_round_f64(uint64_t s[12], const double* rcb) {
+    double dl[12], dh[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) sbox7_f64(s[i], dl[i], dh[i]);
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        double al = rcb[2 * r], ah = rcb[2 * r + 1];
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+#if !defined(GL_MDS_LITERAL)
+            const double m = (r == 0 && i == 0) ? GL_POS.mds_f64[12] : GL_POS.mds_f64[i];
+#else
+            const double m = (double)mds_entry(r, (i + r) % 12);
+#endif
+            al = f64_fma(dl[(i + r) % 12], m, al);
+            ah = f64_fma(dh[(i + r) % 12], m, ah);
+        }
+        GL_F64_TRACK(al);
+        GL_F64_TRACK(ah);
+        s[r] = f64_pair_to_u64(al, ah);
+    }
+}
+#endif
 // Plain full round (constant_layer, sbox_layer, mds_layer; poseidon.rs:741-749) -- used by tools/microbench.
 GL_HD void full_round(uint64_t s[12], const uint64_t* rc) {
 #pragma unroll
@@ -454,9 +525,13 @@ GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
     uint64_t s0 = s[0];
 #pragma unroll 1
     for (int rp = 0; rp < 11; rp++) {
+#if defined(GL_SBOX_INT)
         const uint64_t y = sbox7(s0);
         L[0] = u32_to_f64((uint32_t)y);
         H[0] = u32_to_f64((uint32_t)(y >> 32));
+#else
+        sbox7_f64(s0, L[0], H[0]);  // signed low limb, |L[0]| < 2^33.6: covered by the 2^50 bias
+#endif
         double aL = T.pa_f64[rp][0], aH = T.pa_f64[rp][1];
 #pragma unroll
         for (int j = 0; j < 12; j++) {
@@ -465,9 +540,18 @@ GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
         }
         GL_F64_TRACK(aL);
         GL_F64_TRACK(aH);
+#if defined(GL_SBOX_INT)
         const uint64_t z = sbox7(f64_pair_to_u64(aL, aH));
         const double zL = u32_to_f64((uint32_t)z), zH = u32_to_f64((uint32_t)(z >> 32));
+#else
+        double zL, zH;
+        sbox7_f64(f64_pair_to_u64(aL, aH), zL, zH);
+#endif
+#if defined(GL_RENORM_INT)
+        const double* k = T.pkb_f64[rp];
+#else
         const double* k = T.pk_f64[rp];
+#endif
         {
             double n[12];
 #pragma unroll
@@ -498,6 +582,17 @@ GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
 #if defined(__CUDA_ARCH__) && defined(GL_PARTIAL_SYNC)
         if (SYNC) __syncthreads();  // same instruction-cache argument as the per-full-round barrier
 #endif
+#if defined(GL_RENORM_INT)
+        // Variant: renormalise through the integer pipes (2 FP64 + ~12 ALU + 2 XU per lane instead of 9 FP64)
+        if (rp != 10) {
+#pragma unroll
+            for (int i = 1; i < 12; i++) {
+                const uint64_t u = f64_pair_to_u64(L[i], H[i]);
+                L[i] = u32_to_f64((uint32_t)u);
+                H[i] = u32_to_f64((uint32_t)(u >> 32));
+            }
+        }
+#else
         if (rp != 10) {
             const double C84 = 29014219670751100192948224.0;  // 1.5 * 2^84: x + C84 is rounded to a multiple of 2^32
             const double I32 = 2.3283064365386962890625e-10;  // 2^-32
@@ -511,6 +606,7 @@ GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
                 H[i] = f64_fma(tl, I32, f64_fma(th, I32, hlo));
             }
         }
+#endif
     }
     s[0] = s0;
 #pragma unroll
@@ -541,7 +637,12 @@ GL_HD void poseidon_permute_t(uint64_t s[12]) {
 #if defined(GL_PARTIAL_F64)
         const uint64_t* nrc = (r < 3) ? &T.rc[12 * (r + 1)] : (r == 3) ? &T.rc[48]
                             : (r < 7) ? &T.rc[12 * (r + 23)] : T.zeros;
+#if defined(GL_SBOX_INT)
         full_round_fused(s, nrc, T.nrc_f64[r == 3 ? 8 : r]);
+#else
+        (void)nrc;
+        full_round_f64(s, T.nrcb_f64[r == 3 ? 8 : r]);
+#endif
 #else
         const uint64_t* nrc = (r < 3) ? &T.rc[12 * (r + 1)] : (r == 3) ? T.fast_first
                             : (r < 7) ? &T.rc[12 * (r + 23)] : T.zeros;
