@@ -336,7 +336,7 @@ def gpu_arm(args, rank, local_rank, world):
         "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "avg_ms": leaf_avg, "launches": leaf_cnt,
         "algorithmic_bytes": leaf_bytes,
         "permutations_per_s": perms / (leaf_avg * 1e-3) if leaf_avg else None,
-        "note": "integer-issue bound (x^7 S-boxes + MDS in IMAD/IADD3), not HBM bound: see DESIGN.md",
+        "note": "instruction-issue bound (x^7 S-boxes on the integer pipes, MDS / partial rounds on the FP64 pipe), not HBM bound: see DESIGN.md",
     }
     # integer-issue roofline (what actually bounds these kernels): thread-instructions/s vs 128 lanes/clk/SM
     issue = None
@@ -346,7 +346,7 @@ def gpu_arm(args, rank, local_rank, world):
         peak_issue = 148 * 128 * sm_clk * 1e6
         ipp = tr["k_leaf_hash"]["thread_instructions_per_permutation"]
         ach = ipp * roof["permutations_per_s"]
-        issue = {"kernel": "k_leaf_hash", "bound": "integer issue (4 warp-instructions/clk/SM)",
+        issue = {"kernel": "k_leaf_hash", "bound": "instruction issue (4 warp-instructions/clk/SM)",
                  "achieved": ach, "peak": peak_issue, "unit": "thread-instructions/s", "frac": ach / peak_issue,
                  "thread_instructions_per_permutation": ipp, "source": tr["k_leaf_hash"]["instr_source"]}
     except Exception:

@@ -4,21 +4,30 @@
 //                            hash_n_to_m_no_pad / compress    plonky2/src/hash/hashing.rs:97-145
 //                            Hasher::hash_or_noop             plonky2/src/plonk/config.rs:63-74
 //
-// One thread owns one 12-lane state in registers. Full rounds: x^7 with two squarings + two multiplies per
-// lane, then the circulant MDS evaluated on 32-bit halves (constants < 2^6, so 13-term sums of 32x6-bit
-// products stay < 2^42): on the device these sums run as DFMAs on the otherwise idle FP64 pipe (exact), on
-// the host as integer multiply-adds; ONE 96-bit reduction per lane, and the next round's constants are folded
-// into the accumulators. Partial rounds use the "fast" factorisation (w_hat / v vectors), with the 12-term
-// dot product accumulated in 160 bits and reduced once. The rounds are rolled loops (one copy of each round
-// body) so the permutation fits the instruction cache.
+// One thread owns one 12-lane state. The kernels built on this are bound by instruction issue on the integer
+// pipes (IMAD.WIDE alone costs ~5 issue cycles, tools/pipe_mix.cu), so everything that is linear with small
+// constants runs on the FP64 pipe instead, exactly (integers < 2^53 in doubles):
+//  * full rounds: x^7 = two squarings + two multiplies per lane on the integer pipes; the last 128-bit product is
+//    handed to the FP64 pipe unreduced (sbox7_f64: 2^64 = 2^32 - 1, 2^96 = -1 turn its four words into a signed
+//    limb pair with three FP64 adds), the circulant MDS is 288 DFMAs on two 32-bit-limb vectors with the NEXT
+//    round's constants as accumulator seeds, and one 96-bit reduction per lane brings the state back;
+//  * partial rounds: lanes 1..11 never leave the FP64 pipe for all 22 rounds and two rounds are one linear step
+//    (poseidon_partial_rounds_f64) -- the reference's "fast" w_hat / v factorisation (23 64x64 products per
+//    round) is only used on the host and under -DGL_PARTIAL_FAST;
+//  * u32 <-> f64 conversions are I2F / F2I on the XU pipe.
+// The rounds are rolled loops (one copy of each round body) so the permutation fits the instruction cache.
+// History on B200 (leaf hash of 234-wide rows, M permutations/s): 818 (integer fast form) -> 950 (single
+// 128-bit product) -> 1110 (FP64-resident partial rounds) -> 1300 (two rounds per step); profiles/r01_*.
 #pragma once
 #include "gl_field.cuh"
 #include "gl_poseidon_constants.h"
 
-// Evaluate the MDS layer's 6-bit-constant products on the (otherwise idle) FP64 pipe: DFMA issues at the
-// same 64 lanes/clk/SM as IMAD but on its own pipe, and every sum is < 2^42, so doubles are exact.
-// Measured on B200 (tools/microbench): full rounds 12.1 -> 15.3 G rounds/s, permutation +7 %.
-// Define GL_MDS_INT to force the integer (IMAD.WIDE) formulation.
+// Evaluate the MDS layer's 6-bit-constant products on the FP64 pipe: DFMA issues at the same 64 lanes/clk/SM as
+// IMAD on its own pipe (tools/pipe_mix.cu: a DFMA + IMAD stream runs at the speed of either alone), and every
+// sum is < 2^53, so doubles are exact. Define GL_MDS_INT to force the integer (IMAD.WIDE) formulation.
+// Other measured alternatives kept as switches: GL_PARTIAL_FAST, GL_SBOX_INT (reduce x^7 on the integer pipes),
+// GL_CVT_MAGIC (2^52 magic-number conversions on the FP64 pipe); gl_field.cuh: GL_SQR_3WIDE, GL_MUL_EXPLICIT,
+// GL_REDUCE_V1. tools/variants/ ranks them with one GPU call.
 #if !defined(GL_MDS_INT) && !defined(GL_MDS_FP64)
 #define GL_MDS_FP64 1
 #endif
@@ -59,22 +68,14 @@ struct PoseidonTables {
     // the same rows + the bias (bl2, bh2) = (2^42 + 2^10, 2^42 - 2^11) = 0 (mod p) on every lane, for MDS inputs
     // that come from sbox7_f64 (signed low limbs, |L| < 2^33.6)
     double nrcb_f64[9][24];
-    // FP64-resident partial rounds: constants added after partial round r's MDS (= the next round's constant
-    // layer, ALL_ROUND_CONSTANTS[12*(5+r) + i]), split like nrc_f64, PLUS a bias (bl, bh) with
-    // bl + 2^32*bh = 2^18 * p = 0 (mod p) on every lane that is converted back to an integer after that
-    // round (lane 0 always; all lanes after the last one) so that the signed limbs become positive.
-    double prc_f64[22][24];
-    // Two partial rounds as ONE linear step (poseidon_partial_rounds_f64): with x~ = (x0^7, x1..x11), the state
-    // after rounds A, B is  Q*x~ + z0*M[:,0] + k  where z0 = ((M*x~)_0 + cA_0)^7, Q = M*diag(0,1..1)*M and
-    // k = M*diag(0,1..1)*cA + cB (mod p). pq_f64 = Q (entries < 2^14.1, row sums <= 264^2), pm0_f64 = M[:,0],
-    // pk_f64[pair] = k split in 32-bit halves (+ bias where a lane is converted to an integer afterwards),
-    // pa_f64[pair] = cA_0 split (+ bias).
-    double pq_f64[12][12];
-    double pq2_f64[12][12];  // second copy of Q for the high limbs: keeps nvcc from caching 144 constants in registers
-    double pm0_f64[12];
+    // FP64-resident partial rounds, two rounds per linear step (poseidon_partial_rounds_f64): with cA / cB the
+    // constant layers that follow rounds A = 2*pair and B = 2*pair + 1 (ALL_ROUND_CONSTANTS[12*(5+r) + i]),
+    // pk_f64[pair] = k = M*diag(0,1..1)*cA + cB (mod p) and pa_f64[pair] = cA_0, split in 32-bit halves like
+    // nrc_f64, PLUS a bias (bl, bh) = (2^50 + 2^18, 2^50 - 2^19), bl + 2^32*bh = 2^18 * p = 0 (mod p), on every
+    // lane that is converted back to an integer afterwards (lane 0 always; all lanes after the last pair) so
+    // that signed limbs become positive.
     double pk_f64[11][24];
     double pa_f64[11][2];
-    double pkb_f64[11][24];  // pk_f64 with the bias on EVERY lane (variant GL_RENORM_INT: renormalise via integers)
 };
 
 #if defined(__CUDACC__)
@@ -109,27 +110,11 @@ inline const PoseidonTables& host_poseidon_tables() {
         }
         // bias: bl = 2^50 + 2^18, bh = 2^50 - 2^19;  bl + 2^32*bh = 2^82 - 2^50 + 2^18 = 2^18 * p
         const double bl = 1125899906842624.0 + 262144.0, bh = 1125899906842624.0 - 524288.0;
-        for (int r = 0; r < 22; r++) {
-            const uint64_t* src = &x.rc[12 * (5 + r)];
-            for (int i = 0; i < 12; i++) {
-                const bool biased = (i == 0) || (r == 21);
-                x.prc_f64[r][2 * i] = (double)(uint32_t)src[i] + (biased ? bl : 0.0);
-                x.prc_f64[r][2 * i + 1] = (double)(uint32_t)(src[i] >> 32) + (biased ? bh : 0.0);
-            }
-        }
         // pair tables
         uint64_t M[12][12];
         for (int i = 0; i < 12; i++)
             for (int j = 0; j < 12; j++)
                 M[i][j] = GL_POSEIDON_MDS_CIRC[(j - i + 12) % 12] + ((i == 0 && j == 0) ? GL_POSEIDON_MDS_DIAG[0] : 0);
-        for (int i = 0; i < 12; i++) {
-            x.pm0_f64[i] = (double)M[i][0];
-            for (int j = 0; j < 12; j++) {
-                uint64_t q = 0;
-                for (int k = 1; k < 12; k++) q += M[i][k] * M[k][j];
-                x.pq_f64[i][j] = x.pq2_f64[i][j] = (double)q;
-            }
-        }
         for (int pr = 0; pr < 11; pr++) {
             const uint64_t* cA = &x.rc[12 * (5 + 2 * pr)];      // constants after round A = 2*pr
             const uint64_t* cB = &x.rc[12 * (5 + 2 * pr + 1)];  // constants after round B = 2*pr + 1
@@ -142,8 +127,6 @@ inline const PoseidonTables& host_poseidon_tables() {
                 const bool biased = (i == 0) || (pr == 10);
                 x.pk_f64[pr][2 * i] = (double)(uint32_t)kr + (biased ? bl : 0.0);
                 x.pk_f64[pr][2 * i + 1] = (double)(uint32_t)(kr >> 32) + (biased ? bh : 0.0);
-                x.pkb_f64[pr][2 * i] = (double)(uint32_t)kr + bl;
-                x.pkb_f64[pr][2 * i + 1] = (double)(uint32_t)(kr >> 32) + bh;
             }
         }
         return x;
@@ -236,22 +219,6 @@ GL_HD uint64_t f64_pair_to_u64(double al, double ah) {
     return reduce96((uint64_t)v, (uint32_t)(v >> 64));
 #endif
 }
-// v <- c + MDS * v for one limb vector (circulant first row mds_f64[0..11], +diag 8 on lane 0 = mds_f64[12]);
-// c[2*j] is lane j's constant (the caller offsets c by one for the high limbs).
-GL_HD void mds_f64_inplace(double v[12], const double* c) {
-    const PoseidonTables& T = GL_POS;
-    double n[12];
-#pragma unroll
-    for (int j = 0; j < 12; j++) {
-        double a = c[2 * j];
-#pragma unroll
-        for (int i = 0; i < 12; i++) a = f64_fma(v[(i + j) % 12], (j == 0 && i == 0) ? T.mds_f64[12] : T.mds_f64[i], a);
-        n[j] = a;
-        GL_F64_TRACK(a);
-    }
-#pragma unroll
-    for (int j = 0; j < 12; j++) v[j] = n[j];
-}
 #endif  // GL_FP64_PATH
 
 GL_HD uint64_t sbox7(uint64_t x) {  // sbox_monomial, poseidon.rs:689-696
@@ -272,22 +239,10 @@ GL_HD void sbox7_f64(uint64_t x, double& L, double& H) {
     const uint64_t x3 = mul(x, x2);
     uint64_t lo, hi;
     mul_wide(x3, x4, lo, hi);
-#if defined(__CUDA_ARCH__) && defined(GL_SBOX_INTLIMBS)
-    // Variant: form the two limbs on the ALU pipe (6 adds) and convert them with two 64-bit I2F (XU pipe)
-    uint32_t l0, l1, h0, h1;
-    asm("sub.cc.u32 %0, %4, %6;\n\tsubc.u32 %1, 0, 0;\n\t"
-        "sub.cc.u32 %0, %0, %7;\n\tsubc.u32 %1, %1, 0;\n\t"
-        "add.cc.u32 %2, %5, %6;\n\taddc.u32 %3, 0, 0;"
-        : "=&r"(l0), "=&r"(l1), "=&r"(h0), "=&r"(h1)
-        : "r"(lo32(lo)), "r"(hi32(lo)), "r"(lo32(hi)), "r"(hi32(hi)));
-    L = (double)(long long)pack64(l0, l1);
-    H = (double)(unsigned long long)pack64(h0, h1);
-#else
     const double d0 = u32_to_f64((uint32_t)lo), d1 = u32_to_f64((uint32_t)(lo >> 32));
     const double d2 = u32_to_f64((uint32_t)hi), d3 = u32_to_f64((uint32_t)(hi >> 32));
     L = (d0 - d2) - d3;
     H = d1 + d2;
-#endif
 }
 #endif
 
@@ -311,24 +266,17 @@ GL_HD void mds_layer_add(uint64_t s[12], const uint64_t* nrc, const double* nrcd
 #pragma unroll
         for (int r = 0; r < 12; r++) {
             double al, ah;
-#if !defined(GL_MDS_RC_CONVERT)
             if (nrcd) {
                 al = nrcd[2 * r];
                 ah = nrcd[2 * r + 1];
-            } else
-#endif
-            {
+            } else {
                 const uint64_t c = nrc[r];
                 al = u32_to_f64((uint32_t)c);
                 ah = u32_to_f64((uint32_t)(c >> 32));
             }
 #pragma unroll
             for (int i = 0; i < 12; i++) {
-#if !defined(GL_MDS_LITERAL)
                 const double m = (r == 0 && i == 0) ? T.mds_f64[12] : T.mds_f64[i];
-#else
-                const double m = (double)mds_entry(r, (i + r) % 12);  // literal: DFMA takes it as an immediate
-#endif
                 al = f64_fma(dl[(i + r) % 12], m, al);
                 ah = f64_fma(dh[(i + r) % 12], m, ah);
             }
@@ -394,11 +342,7 @@ GL_HD void full_round_f64(uint64_t s[12], const double* rcb) {
         double al = rcb[2 * r], ah = rcb[2 * r + 1];
 #pragma unroll
         for (int i = 0; i < 12; i++) {
-#if !defined(GL_MDS_LITERAL)
             const double m = (r == 0 && i == 0) ? GL_POS.mds_f64[12] : GL_POS.mds_f64[i];
-#else
-            const double m = (double)mds_entry(r, (i + r) % 12);
-#endif
             al = f64_fma(dl[(i + r) % 12], m, al);
             ah = f64_fma(dh[(i + r) % 12], m, ah);
         }
@@ -435,11 +379,7 @@ GL_HD void poseidon_partial_rounds_noconst(uint64_t s[12]) {
 #pragma unroll
         for (int i = 1; i < 12; i++) s[i] = res[i - 1];
     }
-#if defined(GL_PARTIAL_UNROLL2)
-#pragma unroll 2
-#else
 #pragma unroll 1
-#endif
     for (int r = 0; r < 22; r++) {
         uint64_t s0 = add_canonical(sbox7(s[0]), T.fast_rc[r]);
         // mds_partial_layer_fast (poseidon.rs:514-542)
@@ -454,66 +394,26 @@ GL_HD void poseidon_partial_rounds_noconst(uint64_t s[12]) {
 }
 #if defined(GL_FP64_PATH)
 // partial_rounds (poseidon.rs:751-764) in the ORIGINAL basis (constant_layer, x^7 on lane 0, mds_layer -- the
-// reference's poseidon_naive form, poseidon.rs:779-801), with lanes 1..11 kept RESIDENT ON THE FP64 PIPE:
-// they pass through no non-linearity for 22 rounds, only through the small-constant circulant MDS, so each lane
-// is held as two doubles (L, H), value = L + 2^32*H (mod p), and a round is 288 DFMAs with the next round's
-// constants as accumulator seeds. Only lane 0 crosses to the integer pipes each round (x^7). Exactness: limbs
-// are integers; after a renormalisation |L|, |H| <= 2^31 + 2^18, one MDS multiplies magnitudes by <= 264
-// (+ constants < 2^32), so two rounds stay < 2^48.2 < 2^53; then each lane is renormalised ON THE FP64 PIPE
-// (round-to-multiple-of-2^32 via the 1.5*2^84 trick, 2^64 = 2^32 - 1) -- 9 FP64 ops per lane every other round.
-// Lane 0's limbs can be negative by < 2^48.2, so its constants carry a bias (bl, bh) = 0 (mod p) of 2^50
-// (PoseidonTables::prc_f64) and f64_pair_to_u64 sees non-negative integers < 2^51.
-// Versus the "fast" integer form (23 64x64 products + 12 reductions per round on the ALU/FMA-heavy pipes that
-// bound this kernel): no init matrix, ~80 integer instructions per round instead of ~520.
-// In: s after full round 4's MDS + first partial constant layer. Out: s after the last partial round's MDS +
-// the 5th full round's constant layer.
-GL_HD void poseidon_partial_rounds_f64_v1(uint64_t s[12]) {
-    const PoseidonTables& T = GL_POS;
-    double L[12], H[12];
-#pragma unroll
-    for (int i = 1; i < 12; i++) {
-        L[i] = u32_to_f64((uint32_t)s[i]);
-        H[i] = u32_to_f64((uint32_t)(s[i] >> 32));
-    }
-    uint64_t s0 = s[0];
-#pragma unroll 1
-    for (int rp = 0; rp < 11; rp++) {
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            const double* c = T.prc_f64[2 * rp + q];
-            const uint64_t y = sbox7(s0);
-            L[0] = u32_to_f64((uint32_t)y);
-            H[0] = u32_to_f64((uint32_t)(y >> 32));
-            mds_f64_inplace(L, c);
-            mds_f64_inplace(H, c + 1);
-            s0 = f64_pair_to_u64(L[0], H[0]);
-        }
-        if (rp != 10) {
-            const double C84 = 29014219670751100192948224.0;  // 1.5 * 2^84: x + C84 is rounded to a multiple of 2^32
-            const double I32 = 2.3283064365386962890625e-10;  // 2^-32
-#pragma unroll
-            for (int i = 1; i < 12; i++) {
-                // H = Hlo + th (th multiple of 2^32, kH = th/2^32): 2^64*kH = (2^32 - 1)*kH moves kH into H, -kH into L
-                const double th = (H[i] + C84) - C84;
-                const double hlo = H[i] - th;
-                const double l2 = f64_fma(th, -I32, L[i]);
-                const double tl = (l2 + C84) - C84;  // L carry kL = tl/2^32 moves into H
-                L[i] = l2 - tl;
-                H[i] = f64_fma(tl, I32, f64_fma(th, I32, hlo));
-            }
-        }
-    }
-    s[0] = s0;
-#pragma unroll
-    for (int i = 1; i < 12; i++) s[i] = f64_pair_to_u64(L[i], H[i]);
-}
-// Same, two rounds per linear step: lanes 1..11 only see the MDS twice between renormalisations, and lane 0's
-// second S-box input needs just row 0 of the first MDS, so a PAIR of rounds is
-//     a  = (M x~)_0 + cA_0            (12 DFMAs per limb)        x~ = (x0^7, x1..x11)
+// reference's poseidon_naive form, poseidon.rs:779-801), with lanes 1..11 kept RESIDENT ON THE FP64 PIPE: they
+// pass through no non-linearity for 22 rounds, only through the small-constant circulant MDS, so each lane is
+// held as two doubles (L, H), value = L + 2^32*H (mod p). Only lane 0 crosses to the integer pipes (x^7).
+// Two rounds are ONE linear step: lane 0's second S-box input needs just row 0 of the first MDS, so with
+// x~ = (x0^7, x1..x11) a PAIR of rounds is
+//     a  = (M x~)_0 + cA_0            (12 DFMAs per limb)
 //     x' = Q x~ + a^7 * M[:,0] + k    (156 DFMAs per limb)       Q = M diag(0,1..1) M,  k = M diag(0,1..1) cA + cB
-// = 336 DFMAs instead of 576, with the same magnitude bound as two separate rounds (row sums of Q <= 264^2).
-// Q, M[:,0] are round-independent and read straight from the constant bank as DFMA operands.
-template <bool SYNC = false>
+// = 336 DFMAs instead of 2 x 288; Q and M[:,0] are compile-time literals (DFMA immediates), k and cA_0 come
+// from PoseidonTables::pk_f64 / pa_f64.
+// Exactness: limbs are integers. After a renormalisation |L|, |H| <= 2^31 + 2^18; the row sums of Q are
+// <= 264^2, lane 0 enters with |L| < 2^33.6 (sbox7_f64), so a pair stays < 2^49 < 2^53; then lanes 1..11 are
+// renormalised ON THE FP64 PIPE (round to a multiple of 2^32 with the 1.5*2^84 trick; 2^64 = 2^32 - 1 moves the
+// carry of H into L) -- 9 FP64 ops per lane per pair. Limbs that are converted to integers (lane 0 twice per
+// pair, all lanes after the last pair) can be negative, so their constants carry a bias (bl, bh) = 0 (mod p) of
+// 2^50 and f64_pair_to_u64 sees non-negative integers < 2^51 (tests/emu/poseidon_f64_emu.cpp tracks the bound).
+// Versus the "fast" integer form (23 64x64 products + 12 reductions per round, all on the integer pipes that
+// bound this kernel): no init matrix, ~90 integer instructions per round instead of ~520; measured 950 -> 1300 M
+// permutations/s (profiles/r01_poseidon_variants*.txt).
+// In: s after full round 4's MDS + first partial constant layer (original constants). Out: s after the last
+// partial round's MDS + the 5th full round's constant layer.
 GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
     const PoseidonTables& T = GL_POS;
     double L[12], H[12];
@@ -547,11 +447,7 @@ GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
         double zL, zH;
         sbox7_f64(f64_pair_to_u64(aL, aH), zL, zH);
 #endif
-#if defined(GL_RENORM_INT)
-        const double* k = T.pkb_f64[rp];
-#else
         const double* k = T.pk_f64[rp];
-#endif
         {
             double n[12];
 #pragma unroll
@@ -579,20 +475,6 @@ GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
             for (int i = 0; i < 12; i++) H[i] = n[i];
         }
         s0 = f64_pair_to_u64(L[0], H[0]);
-#if defined(__CUDA_ARCH__) && defined(GL_PARTIAL_SYNC)
-        if (SYNC) __syncthreads();  // same instruction-cache argument as the per-full-round barrier
-#endif
-#if defined(GL_RENORM_INT)
-        // Variant: renormalise through the integer pipes (2 FP64 + ~12 ALU + 2 XU per lane instead of 9 FP64)
-        if (rp != 10) {
-#pragma unroll
-            for (int i = 1; i < 12; i++) {
-                const uint64_t u = f64_pair_to_u64(L[i], H[i]);
-                L[i] = u32_to_f64((uint32_t)u);
-                H[i] = u32_to_f64((uint32_t)(u >> 32));
-            }
-        }
-#else
         if (rp != 10) {
             const double C84 = 29014219670751100192948224.0;  // 1.5 * 2^84: x + C84 is rounded to a multiple of 2^32
             const double I32 = 2.3283064365386962890625e-10;  // 2^-32
@@ -606,7 +488,6 @@ GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
                 H[i] = f64_fma(tl, I32, f64_fma(th, I32, hlo));
             }
         }
-#endif
     }
     s[0] = s0;
 #pragma unroll
@@ -653,11 +534,7 @@ GL_HD void poseidon_permute_t(uint64_t s[12]) {
 #endif
         if (r == 3) {
 #if defined(GL_PARTIAL_F64)
-#if defined(GL_PARTIAL_F64_V1)
-            poseidon_partial_rounds_f64_v1(s);
-#else
-            poseidon_partial_rounds_f64<SYNC>(s);  // ends with the 5th full round's constant layer folded in
-#endif
+            poseidon_partial_rounds_f64(s);  // ends with the 5th full round's constant layer folded in
 #else
             poseidon_partial_rounds_noconst(s);
 #pragma unroll

@@ -13,11 +13,6 @@
 #endif
 extern "C" __global__ void __launch_bounds__(VB_THREADS, VB_MINB)
 k_leaf(const uint64_t* leaves, size_t N, uint32_t W, uint64_t* out) {
-#if defined(VB_STAGGER_NS)
-    // experiment: de-phase the CTAs that share an SM so that FP64-bound partial rounds of one CTA overlap the
-    // integer-bound full rounds of another
-    __nanosleep((blockIdx.x % 5) * VB_STAGGER_NS);
-#endif
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = j < N;
     if (!live) j = N - 1;
