@@ -139,6 +139,22 @@ def test_hash_extreme_inputs(pb, oracle):
     assert np.array_equal(pb.PoseidonHash.hash_many(rows), oracle.hash_many(rows))
 
 
+def test_hash_fp64_limb_stress(pb, oracle):
+    """Inputs that maximise the FP64-pipe limbs of the device Poseidon (both 32-bit halves of every word near
+    2^32, non-canonical words, sparse states): the exactness bound of gl_poseidon.cuh must hold on the GPU as it
+    does in tests/emu/poseidon_f64_emu.cpp."""
+    rng = np.random.default_rng(0xF64)
+    rows = rng.integers(0, 2**63, size=(4096, 16), dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    rows[0::4] |= np.uint64(0xFFFFFFF0FFFFFFF0)
+    rows[1::4] = np.uint64(2**64 - 1) - (rows[1::4] & np.uint64(7))
+    rows[2::4, 1:] = 0
+    assert np.array_equal(pb.PoseidonHash.hash_many(rows), oracle.hash_many(rows))
+    pairs = rows[:, :8].copy()
+    got = pb.PoseidonHash.two_to_one_many(pairs[:256])
+    for i in range(256):
+        assert np.array_equal(got[i], oracle.two_to_one(pairs[i, :4], pairs[i, 4:]))
+
+
 def test_two_to_one(pb, oracle):
     pairs = synth(0x51, (100, 8), canonical=False)
     got = pb.PoseidonHash.two_to_one_many(pairs)
