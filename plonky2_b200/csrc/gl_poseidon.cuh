@@ -68,6 +68,9 @@ struct PoseidonTables {
     // the same rows + the bias (bl2, bh2) = (2^42 + 2^10, 2^42 - 2^11) = 0 (mod p) on every lane, for MDS inputs
     // that come from sbox7_f64 (signed low limbs, |L| < 2^33.6)
     double nrcb_f64[9][24];
+    // nrcb_f64 in the SEED form of circ12_f64: [0..5] = (kL[r] + kL[r+6])/2, [6..11] = (kL[r] - kL[r+6])/2 for the
+    // low limbs kL, [12..23] the same for the high limbs.
+    double nrcs_f64[9][24];
     // FP64-resident partial rounds, two rounds per linear step (poseidon_partial_rounds_f64): with cA / cB the
     // constant layers that follow rounds A = 2*pair and B = 2*pair + 1 (ALL_ROUND_CONSTANTS[12*(5+r) + i]),
     // pk_f64[pair] = k = M*diag(0,1..1)*cA + cB (mod p) and pa_f64[pair] = cA_0, split in 32-bit halves like
@@ -76,6 +79,11 @@ struct PoseidonTables {
     // that signed limbs become positive.
     double pk_f64[11][24];
     double pa_f64[11][2];
+    // split-circulant form of the pair step (GL_MDS_SPLIT): x' = C*C*x~ + 8*x~0*C[:,0] + (a^7 - a)*M[:,0] + 8*a*e0 + k2
+    // with a = (M x~)_0 + cA_0 and k2 = M*cA + cB - 8*cA_0*e0 (mod p). pks_f64[pair] = k2 (+ bias as in pk_f64) in
+    // the seed form of circ12_f64; pan_f64[pair] = cA_0 split WITHOUT bias (the bias is added at the conversion).
+    double pks_f64[11][24];
+    double pan_f64[11][2];
 };
 
 #if defined(__CUDACC__)
@@ -107,6 +115,12 @@ inline const PoseidonTables& host_poseidon_tables() {
                 x.nrcb_f64[r][2 * i] = x.nrc_f64[r][2 * i] + (4398046511104.0 + 1024.0);
                 x.nrcb_f64[r][2 * i + 1] = x.nrc_f64[r][2 * i + 1] + (4398046511104.0 - 2048.0);
             }
+            for (int q = 0; q < 6; q++)
+                for (int l = 0; l < 2; l++) {  // limb: 0 = low, 1 = high
+                    const double k0 = x.nrcb_f64[r][2 * q + l], k6 = x.nrcb_f64[r][2 * (q + 6) + l];
+                    x.nrcs_f64[r][12 * l + q] = (k0 + k6) * 0.5;
+                    x.nrcs_f64[r][12 * l + 6 + q] = (k0 - k6) * 0.5;
+                }
         }
         // bias: bl = 2^50 + 2^18, bh = 2^50 - 2^19;  bl + 2^32*bh = 2^82 - 2^50 + 2^18 = 2^18 * p
         const double bl = 1125899906842624.0 + 262144.0, bh = 1125899906842624.0 - 524288.0;
@@ -128,6 +142,24 @@ inline const PoseidonTables& host_poseidon_tables() {
                 x.pk_f64[pr][2 * i] = (double)(uint32_t)kr + (biased ? bl : 0.0);
                 x.pk_f64[pr][2 * i + 1] = (double)(uint32_t)(kr >> 32) + (biased ? bh : 0.0);
             }
+            x.pan_f64[pr][0] = (double)(uint32_t)cA[0];
+            x.pan_f64[pr][1] = (double)(uint32_t)(cA[0] >> 32);
+            double k2[12][2];
+            for (int i = 0; i < 12; i++) {
+                unsigned __int128 k = cB[i];
+                for (int t = 0; t < 12; t++) k += (unsigned __int128)M[i][t] * cA[t];
+                const unsigned __int128 PP = (unsigned __int128)0xFFFFFFFF00000001ULL;
+                if (i == 0) k += 8 * (PP - cA[0] % PP);  // - 8*cA_0 on lane 0
+                const uint64_t kr = (uint64_t)(k % PP);
+                const bool biased = (i == 0) || (pr == 10);
+                k2[i][0] = (double)(uint32_t)kr + (biased ? bl : 0.0);
+                k2[i][1] = (double)(uint32_t)(kr >> 32) + (biased ? bh : 0.0);
+            }
+            for (int q = 0; q < 6; q++)
+                for (int l = 0; l < 2; l++) {
+                    x.pks_f64[pr][12 * l + q] = (k2[q][l] + k2[q + 6][l]) * 0.5;
+                    x.pks_f64[pr][12 * l + 6 + q] = (k2[q][l] - k2[q + 6][l]) * 0.5;
+                }
         }
         return x;
     }();
@@ -179,6 +211,30 @@ GL_HD constexpr double mds_pair_entry(int i, int j) {
     return (double)q;
 }
 
+// The circulant part C (first row circ) through x^12 - 1 = (x^6 - 1)(x^6 + 1): with v+- = v[0..5] +- v[6..11] and
+// c+- = (circ[0..5] +- circ[6..11]) / 2, out[r] +- out[r+6] are a cyclic / negacyclic length-6 correlation:
+//   S+[r] = sum_j v+[j] * c+[(j - r) mod 6],   S-[r] = sum_{j>=r} v-[j] * c-[j - r] - sum_{j<r} v-[j] * c-[j - r + 6],
+//   out[r] = S+[r] + S-[r],  out[r+6] = S+[r] - S-[r]
+// = 12 + 72 + 12 FP64 operations instead of 144 (the halves make some values multiples of 1/2: still exact).
+// MdsCirc is C itself, MdsCirc2 is C*C (two partial rounds in one step), entries < 2^14.4.
+struct MdsCirc {
+    static GL_HD constexpr double c(int d) {
+        constexpr double circ[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+        return circ[((d % 12) + 12) % 12];
+    }
+};
+struct MdsCirc2 {
+    static GL_HD constexpr double c(int d) {  // (C*C x)[r] = sum_l x[l] * c2[(l - r) mod 12],  c2 = circ (*) circ
+        double a = 0;
+        for (int t = 0; t < 12; t++) a += MdsCirc::c(t) * MdsCirc::c(d - t);
+        return a;
+    }
+};
+template <class K>
+GL_HD constexpr double circ_half_p(int k) { return (K::c(k) + K::c(k + 6)) * 0.5; }
+template <class K>
+GL_HD constexpr double circ_half_m(int k) { return (K::c(k) - K::c(k + 6)) * 0.5; }
+
 #if !defined(GL_F64_TRACK)
 #define GL_F64_TRACK(x)  // tests/emu hooks the largest limb magnitude here
 #endif
@@ -218,6 +274,30 @@ GL_HD uint64_t f64_pair_to_u64(double al, double ah) {
     const unsigned __int128 v = (unsigned __int128)(uint64_t)al + ((unsigned __int128)(uint64_t)ah << 32);
     return reduce96((uint64_t)v, (uint32_t)(v >> 64));
 #endif
+}
+// out = Circ(K) * v + k for one limb vector, the constants k given as SEEDS: seed[r] = (k[r] + k[r+6]) / 2,
+// seed[6 + r] = (k[r] - k[r+6]) / 2 (r < 6). See MdsCirc above.
+template <class K>
+GL_HD void circ12_f64(const double v[12], const double* seed, double out[12]) {
+    double vp[6], vm[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        vp[j] = v[j] + v[j + 6];
+        vm[j] = v[j] - v[j + 6];
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        double sp = seed[r], sm = seed[6 + r];
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            sp = f64_fma(vp[j], circ_half_p<K>((j - r + 6) % 6), sp);
+            sm = f64_fma(vm[j], j >= r ? circ_half_m<K>(j - r) : -circ_half_m<K>(j - r + 6), sm);
+        }
+        GL_F64_TRACK(sp);
+        GL_F64_TRACK(sm);
+        out[r] = sp + sm;
+        out[r + 6] = sp - sm;
+    }
 }
 #endif  // GL_FP64_PATH
 
@@ -333,10 +413,27 @@ GL_HD void full_round_fused(uint64_t s[12], const uint64_t* next_rc, const doubl
 #if defined(GL_FP64_PATH)
 // The same round with the S-box outputs going straight to the FP64 pipe (sbox7_f64); `rcb` = a row of
 // PoseidonTables::nrcb_f64 (next constants + bias).
-GL_HD void full_round_f64(uint64_t s[12], const double* rcb) {
+GL_HD void full_round_f64(uint64_t s[12], const double* rcb, const double* rcs) {
     double dl[12], dh[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) sbox7_f64(s[i], dl[i], dh[i]);
+#if !defined(GL_MDS_DIRECT)
+    (void)rcb;
+    double ol[12], oh[12];
+    circ12_f64<MdsCirc>(dl, rcs, ol);
+    ol[0] = f64_fma(dl[0], 8.0, ol[0]);  // + diag[0] * v[0]
+    circ12_f64<MdsCirc>(dh, rcs + 12, oh);
+    oh[0] = f64_fma(dh[0], 8.0, oh[0]);
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        GL_F64_TRACK(ol[r]);
+        GL_F64_TRACK(oh[r]);
+        s[r] = f64_pair_to_u64(ol[r], oh[r]);
+    }
+    return;
+#else
+    (void)rcs;
+#endif
 #pragma unroll
     for (int r = 0; r < 12; r++) {
         double al = rcb[2 * r], ah = rcb[2 * r + 1];
@@ -423,6 +520,68 @@ GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
         H[i] = u32_to_f64((uint32_t)(s[i] >> 32));
     }
     uint64_t s0 = s[0];
+#if !defined(GL_MDS_DIRECT)
+#pragma unroll 1
+    for (int rp = 0; rp < 11; rp++) {
+        sbox7_f64(s0, L[0], H[0]);  // x~0 = x0^7: signed low limb, |L[0]| < 2^33
+        // a = (M x~)_0 + cA_0 (no bias in the limbs; the bias (bl, bh) = 0 (mod p) is added for the conversion only)
+        double aL = T.pan_f64[rp][0], aH = T.pan_f64[rp][1];
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            aL = f64_fma(L[j], (double)mds_entry(0, j), aL);
+            aH = f64_fma(H[j], (double)mds_entry(0, j), aH);
+        }
+        double zL, zH;
+        sbox7_f64(f64_pair_to_u64(aL + (1125899906842624.0 + 262144.0), aH + (1125899906842624.0 - 524288.0)), zL, zH);
+        zL -= aL;  // z0 - a
+        zH -= aH;
+        const double* k = T.pks_f64[rp];
+        {
+            double n[12];
+            circ12_f64<MdsCirc2>(L, k, n);
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                n[i] = f64_fma(L[0], 8.0 * MdsCirc::c(12 - i), n[i]);        // 8 * x~0 * C[:,0]
+                n[i] = f64_fma(zL, (double)mds_entry(i, 0), n[i]);           // (a^7 - a) * M[:,0]
+            }
+            n[0] = f64_fma(aL, 8.0, n[0]);
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                L[i] = n[i];
+                GL_F64_TRACK(n[i]);
+            }
+        }
+        {
+            double n[12];
+            circ12_f64<MdsCirc2>(H, k + 12, n);
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                n[i] = f64_fma(H[0], 8.0 * MdsCirc::c(12 - i), n[i]);
+                n[i] = f64_fma(zH, (double)mds_entry(i, 0), n[i]);
+            }
+            n[0] = f64_fma(aH, 8.0, n[0]);
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                H[i] = n[i];
+                GL_F64_TRACK(n[i]);
+            }
+        }
+        s0 = f64_pair_to_u64(L[0], H[0]);
+        if (rp != 10) {
+            const double C84 = 29014219670751100192948224.0;  // 1.5 * 2^84: x + C84 is rounded to a multiple of 2^32
+            const double I32 = 2.3283064365386962890625e-10;  // 2^-32
+#pragma unroll
+            for (int i = 1; i < 12; i++) {
+                const double th = (H[i] + C84) - C84;
+                const double hlo = H[i] - th;
+                const double l2 = f64_fma(th, -I32, L[i]);
+                const double tl = (l2 + C84) - C84;
+                L[i] = l2 - tl;
+                H[i] = f64_fma(tl, I32, f64_fma(th, I32, hlo));
+            }
+        }
+    }
+#else
 #pragma unroll 1
     for (int rp = 0; rp < 11; rp++) {
 #if defined(GL_SBOX_INT)
@@ -489,6 +648,7 @@ GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
             }
         }
     }
+#endif  // GL_MDS_DIRECT
     s[0] = s0;
 #pragma unroll
     for (int i = 1; i < 12; i++) s[i] = f64_pair_to_u64(L[i], H[i]);
@@ -522,7 +682,7 @@ GL_HD void poseidon_permute_t(uint64_t s[12]) {
         full_round_fused(s, nrc, T.nrc_f64[r == 3 ? 8 : r]);
 #else
         (void)nrc;
-        full_round_f64(s, T.nrcb_f64[r == 3 ? 8 : r]);
+        full_round_f64(s, T.nrcb_f64[r == 3 ? 8 : r], T.nrcs_f64[r == 3 ? 8 : r]);
 #endif
 #else
         const uint64_t* nrc = (r < 3) ? &T.rc[12 * (r + 1)] : (r == 3) ? T.fast_first
