@@ -9,15 +9,16 @@
 // constants runs on the FP64 pipe instead, exactly (integers < 2^53 in doubles):
 //  * full rounds: x^7 = two squarings + two multiplies per lane on the integer pipes; the last 128-bit product is
 //    handed to the FP64 pipe unreduced (sbox7_f64: 2^64 = 2^32 - 1, 2^96 = -1 turn its four words into a signed
-//    limb pair with three FP64 adds), the circulant MDS is 288 DFMAs on two 32-bit-limb vectors with the NEXT
-//    round's constants as accumulator seeds, and one 96-bit reduction per lane brings the state back;
+//    limb pair with three FP64 adds), the circulant MDS runs on two 32-bit-limb vectors through x^12 - 1 =
+//    (x^6 - 1)(x^6 + 1) (circ12_f64: 96 FP64 operations per vector) with the NEXT round's constants as seeds, and one 96-bit reduction per lane brings the state back;
 //  * partial rounds: lanes 1..11 never leave the FP64 pipe for all 22 rounds and two rounds are one linear step
 //    (poseidon_partial_rounds_f64) -- the reference's "fast" w_hat / v factorisation (23 64x64 products per
 //    round) is only used on the host and under -DGL_PARTIAL_FAST;
 //  * u32 <-> f64 conversions are I2F / F2I on the XU pipe.
 // The rounds are rolled loops (one copy of each round body) so the permutation fits the instruction cache.
 // History on B200 (leaf hash of 234-wide rows, M permutations/s): 818 (integer fast form) -> 950 (single
-// 128-bit product) -> 1110 (FP64-resident partial rounds) -> 1300 (two rounds per step); profiles/r01_*.
+// 128-bit product) -> 1110 (FP64-resident partial rounds) -> 1300 (two rounds per step) -> 1459 (split circulant
+// MDS); profiles/r01_*.
 #pragma once
 #include "gl_field.cuh"
 #include "gl_poseidon_constants.h"
@@ -25,7 +26,7 @@
 // Evaluate the MDS layer's 6-bit-constant products on the FP64 pipe: DFMA issues at the same 64 lanes/clk/SM as
 // IMAD on its own pipe (tools/pipe_mix.cu: a DFMA + IMAD stream runs at the speed of either alone), and every
 // sum is < 2^53, so doubles are exact. Define GL_MDS_INT to force the integer (IMAD.WIDE) formulation.
-// Other measured alternatives kept as switches: GL_PARTIAL_FAST, GL_SBOX_INT (reduce x^7 on the integer pipes),
+// Other measured alternatives kept as switches: GL_PARTIAL_FAST (integer rounds everywhere),
 // GL_CVT_MAGIC (2^52 magic-number conversions on the FP64 pipe); gl_field.cuh: GL_SQR_3WIDE, GL_MUL_EXPLICIT,
 // GL_REDUCE_V1. tools/variants/ ranks them with one GPU call.
 #if !defined(GL_MDS_INT) && !defined(GL_MDS_FP64)
@@ -65,23 +66,17 @@ struct PoseidonTables {
     // row 8: the ORIGINAL first partial-round constants (ALL_ROUND_CONSTANTS[48..59]) for the FP64-resident
     // partial rounds, which run in the original (non-"fast") basis.
     double nrc_f64[9][24];
-    // the same rows + the bias (bl2, bh2) = (2^42 + 2^10, 2^42 - 2^11) = 0 (mod p) on every lane, for MDS inputs
-    // that come from sbox7_f64 (signed low limbs, |L| < 2^33.6)
-    double nrcb_f64[9][24];
-    // nrcb_f64 in the SEED form of circ12_f64: [0..5] = (kL[r] + kL[r+6])/2, [6..11] = (kL[r] - kL[r+6])/2 for the
-    // low limbs kL, [12..23] the same for the high limbs.
+    // the same rows + the bias (bl2, bh2) = (2^42 + 2^10, 2^42 - 2^11) = 0 (mod p) on every lane (the MDS inputs
+    // that come from sbox7_f64 have signed low limbs, |L| < 2^33), in the SEED form of circ12_f64:
+    // [0..5] = (kL[r] + kL[r+6])/2, [6..11] = (kL[r] - kL[r+6])/2 for the low limbs kL, [12..23] for the high limbs.
     double nrcs_f64[9][24];
     // FP64-resident partial rounds, two rounds per linear step (poseidon_partial_rounds_f64): with cA / cB the
     // constant layers that follow rounds A = 2*pair and B = 2*pair + 1 (ALL_ROUND_CONSTANTS[12*(5+r) + i]),
-    // pk_f64[pair] = k = M*diag(0,1..1)*cA + cB (mod p) and pa_f64[pair] = cA_0, split in 32-bit halves like
-    // nrc_f64, PLUS a bias (bl, bh) = (2^50 + 2^18, 2^50 - 2^19), bl + 2^32*bh = 2^18 * p = 0 (mod p), on every
-    // lane that is converted back to an integer afterwards (lane 0 always; all lanes after the last pair) so
-    // that signed limbs become positive.
-    double pk_f64[11][24];
-    double pa_f64[11][2];
-    // split-circulant form of the pair step (GL_MDS_SPLIT): x' = C*C*x~ + 8*x~0*C[:,0] + (a^7 - a)*M[:,0] + 8*a*e0 + k2
-    // with a = (M x~)_0 + cA_0 and k2 = M*cA + cB - 8*cA_0*e0 (mod p). pks_f64[pair] = k2 (+ bias as in pk_f64) in
-    // the seed form of circ12_f64; pan_f64[pair] = cA_0 split WITHOUT bias (the bias is added at the conversion).
+    // x' = C*C*x~ + 8*x~0*C[:,0] + (a^7 - a)*M[:,0] + 8*a*e0 + k2 with a = (M x~)_0 + cA_0 and
+    // k2 = M*cA + cB - 8*cA_0*e0 (mod p). pks_f64[pair] = k2 split in 32-bit halves PLUS a bias (bl, bh) =
+    // (2^50 + 2^18, 2^50 - 2^19), bl + 2^32*bh = 2^18 * p = 0 (mod p), on every lane that is converted back to an
+    // integer afterwards (lane 0 always; all lanes after the last pair), in the seed form of circ12_f64;
+    // pan_f64[pair] = cA_0 split WITHOUT bias (the bias is added at the conversion).
     double pks_f64[11][24];
     double pan_f64[11][2];
 };
@@ -111,13 +106,12 @@ inline const PoseidonTables& host_poseidon_tables() {
             for (int i = 0; i < 12; i++) {
                 x.nrc_f64[r][2 * i] = (double)(uint32_t)src[i];
                 x.nrc_f64[r][2 * i + 1] = (double)(uint32_t)(src[i] >> 32);
-                // bl2 + 2^32*bh2 = 2^10 + 2^42 + 2^74 - 2^43 = 2^74 - 2^42 + 2^10 = 2^10 * p
-                x.nrcb_f64[r][2 * i] = x.nrc_f64[r][2 * i] + (4398046511104.0 + 1024.0);
-                x.nrcb_f64[r][2 * i + 1] = x.nrc_f64[r][2 * i + 1] + (4398046511104.0 - 2048.0);
             }
+            // bl2 + 2^32*bh2 = 2^10 + 2^42 + 2^74 - 2^43 = 2^74 - 2^42 + 2^10 = 2^10 * p
+            const double b2[2] = {4398046511104.0 + 1024.0, 4398046511104.0 - 2048.0};
             for (int q = 0; q < 6; q++)
                 for (int l = 0; l < 2; l++) {  // limb: 0 = low, 1 = high
-                    const double k0 = x.nrcb_f64[r][2 * q + l], k6 = x.nrcb_f64[r][2 * (q + 6) + l];
+                    const double k0 = x.nrc_f64[r][2 * q + l] + b2[l], k6 = x.nrc_f64[r][2 * (q + 6) + l] + b2[l];
                     x.nrcs_f64[r][12 * l + q] = (k0 + k6) * 0.5;
                     x.nrcs_f64[r][12 * l + 6 + q] = (k0 - k6) * 0.5;
                 }
@@ -132,16 +126,6 @@ inline const PoseidonTables& host_poseidon_tables() {
         for (int pr = 0; pr < 11; pr++) {
             const uint64_t* cA = &x.rc[12 * (5 + 2 * pr)];      // constants after round A = 2*pr
             const uint64_t* cB = &x.rc[12 * (5 + 2 * pr + 1)];  // constants after round B = 2*pr + 1
-            x.pa_f64[pr][0] = (double)(uint32_t)cA[0] + bl;
-            x.pa_f64[pr][1] = (double)(uint32_t)(cA[0] >> 32) + bh;
-            for (int i = 0; i < 12; i++) {
-                unsigned __int128 k = cB[i];
-                for (int t = 1; t < 12; t++) k += (unsigned __int128)M[i][t] * cA[t];
-                const uint64_t kr = (uint64_t)(k % (unsigned __int128)0xFFFFFFFF00000001ULL);
-                const bool biased = (i == 0) || (pr == 10);
-                x.pk_f64[pr][2 * i] = (double)(uint32_t)kr + (biased ? bl : 0.0);
-                x.pk_f64[pr][2 * i + 1] = (double)(uint32_t)(kr >> 32) + (biased ? bh : 0.0);
-            }
             x.pan_f64[pr][0] = (double)(uint32_t)cA[0];
             x.pan_f64[pr][1] = (double)(uint32_t)(cA[0] >> 32);
             double k2[12][2];
@@ -198,17 +182,11 @@ GL_HD uint64_t acc_reduce(const Acc160& a) {
     return sub(r, (uint64_t)a.top << 32);
 }
 
-// Compile-time copies of the MDS matrix M[i][j] = circ[(j - i) mod 12] (+ diag on [0][0]) and of
-// Q = M * diag(0,1,...,1) * M (two partial rounds as one linear step), so that fully unrolled FP64 code gets
-// them as literal operands.
+// Compile-time copy of the MDS matrix M[i][j] = circ[(j - i) mod 12] (+ diag on [0][0]), so that fully unrolled
+// FP64 code gets its entries as literal operands (DFMA immediates).
 GL_HD constexpr uint32_t mds_entry(int i, int j) {
     constexpr uint32_t circ[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};  // poseidon_goldilocks.rs:24
     return circ[(j - i + 12) % 12] + ((i == 0 && j == 0) ? 8u : 0u);                  // diag = [8, 0, ...]: :25
-}
-GL_HD constexpr double mds_pair_entry(int i, int j) {
-    uint32_t q = 0;
-    for (int k = 1; k < 12; k++) q += mds_entry(i, k) * mds_entry(k, j);
-    return (double)q;
 }
 
 // The circulant part C (first row circ) through x^12 - 1 = (x^6 - 1)(x^6 + 1): with v+- = v[0..5] +- v[6..11] and
@@ -411,14 +389,12 @@ GL_HD void full_round_fused(uint64_t s[12], const uint64_t* next_rc, const doubl
     mds_layer_add(s, next_rc, next_rcd);
 }
 #if defined(GL_FP64_PATH)
-// The same round with the S-box outputs going straight to the FP64 pipe (sbox7_f64); `rcb` = a row of
-// PoseidonTables::nrcb_f64 (next constants + bias).
-GL_HD void full_round_f64(uint64_t s[12], const double* rcb, const double* rcs) {
+// The same round with the S-box outputs going straight to the FP64 pipe (sbox7_f64) and the split-circulant MDS;
+// `rcs` = a row of PoseidonTables::nrcs_f64 (next constants + bias, seed form).
+GL_HD void full_round_f64(uint64_t s[12], const double* rcs) {
     double dl[12], dh[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) sbox7_f64(s[i], dl[i], dh[i]);
-#if !defined(GL_MDS_DIRECT)
-    (void)rcb;
     double ol[12], oh[12];
     circ12_f64<MdsCirc>(dl, rcs, ol);
     ol[0] = f64_fma(dl[0], 8.0, ol[0]);  // + diag[0] * v[0]
@@ -429,23 +405,6 @@ GL_HD void full_round_f64(uint64_t s[12], const double* rcb, const double* rcs) 
         GL_F64_TRACK(ol[r]);
         GL_F64_TRACK(oh[r]);
         s[r] = f64_pair_to_u64(ol[r], oh[r]);
-    }
-    return;
-#else
-    (void)rcs;
-#endif
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        double al = rcb[2 * r], ah = rcb[2 * r + 1];
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            const double m = (r == 0 && i == 0) ? GL_POS.mds_f64[12] : GL_POS.mds_f64[i];
-            al = f64_fma(dl[(i + r) % 12], m, al);
-            ah = f64_fma(dh[(i + r) % 12], m, ah);
-        }
-        GL_F64_TRACK(al);
-        GL_F64_TRACK(ah);
-        s[r] = f64_pair_to_u64(al, ah);
     }
 }
 #endif
@@ -495,20 +454,22 @@ GL_HD void poseidon_partial_rounds_noconst(uint64_t s[12]) {
 // pass through no non-linearity for 22 rounds, only through the small-constant circulant MDS, so each lane is
 // held as two doubles (L, H), value = L + 2^32*H (mod p). Only lane 0 crosses to the integer pipes (x^7).
 // Two rounds are ONE linear step: lane 0's second S-box input needs just row 0 of the first MDS, so with
-// x~ = (x0^7, x1..x11) a PAIR of rounds is
-//     a  = (M x~)_0 + cA_0            (12 DFMAs per limb)
-//     x' = Q x~ + a^7 * M[:,0] + k    (156 DFMAs per limb)       Q = M diag(0,1..1) M,  k = M diag(0,1..1) cA + cB
-// = 336 DFMAs instead of 2 x 288; Q and M[:,0] are compile-time literals (DFMA immediates), k and cA_0 come
-// from PoseidonTables::pk_f64 / pa_f64.
+// x~ = (x0^7, x1..x11), M = C + 8*e0*e0^T (C circulant) a PAIR of rounds is
+//     a  = (M x~)_0 + cA_0                                                        (12 DFMAs per limb)
+//     x' = Q x~ + a^7 * M[:,0] + k,   Q = M diag(0,1..1) M,  k = M diag(0,1..1) cA + cB
+//        = C*C*x~ + 8*x~0*C[:,0] + (a^7 - a)*M[:,0] + 8*a*e0 + k2,   k2 = M*cA + cB - 8*cA_0*e0
+// so that the split-circulant form (circ12_f64) applies to C*C: 135 FP64 operations per limb instead of 2 x 144.
+// All matrix entries are compile-time literals (DFMA immediates); k2 and cA_0 come from PoseidonTables::pks_f64 /
+// pan_f64.
 // Exactness: limbs are integers. After a renormalisation |L|, |H| <= 2^31 + 2^18; the row sums of Q are
-// <= 264^2, lane 0 enters with |L| < 2^33.6 (sbox7_f64), so a pair stays < 2^49 < 2^53; then lanes 1..11 are
+// <= 264^2 (those of C*C are 256^2), lane 0 enters with |L| < 2^33 (sbox7_f64), so a pair stays < 2^49 < 2^53; then lanes 1..11 are
 // renormalised ON THE FP64 PIPE (round to a multiple of 2^32 with the 1.5*2^84 trick; 2^64 = 2^32 - 1 moves the
 // carry of H into L) -- 9 FP64 ops per lane per pair. Limbs that are converted to integers (lane 0 twice per
 // pair, all lanes after the last pair) can be negative, so their constants carry a bias (bl, bh) = 0 (mod p) of
 // 2^50 and f64_pair_to_u64 sees non-negative integers < 2^51 (tests/emu/poseidon_f64_emu.cpp tracks the bound).
 // Versus the "fast" integer form (23 64x64 products + 12 reductions per round, all on the integer pipes that
 // bound this kernel): no init matrix, ~90 integer instructions per round instead of ~520; measured 950 -> 1300 M
-// permutations/s (profiles/r01_poseidon_variants*.txt).
+// permutations/s, 1424 with the split circulant (profiles/r01_poseidon_variants.md).
 // In: s after full round 4's MDS + first partial constant layer (original constants). Out: s after the last
 // partial round's MDS + the 5th full round's constant layer.
 GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
@@ -520,7 +481,6 @@ GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
         H[i] = u32_to_f64((uint32_t)(s[i] >> 32));
     }
     uint64_t s0 = s[0];
-#if !defined(GL_MDS_DIRECT)
 #pragma unroll 1
     for (int rp = 0; rp < 11; rp++) {
         sbox7_f64(s0, L[0], H[0]);  // x~0 = x0^7: signed low limb, |L[0]| < 2^33
@@ -581,74 +541,6 @@ GL_HD void poseidon_partial_rounds_f64(uint64_t s[12]) {
             }
         }
     }
-#else
-#pragma unroll 1
-    for (int rp = 0; rp < 11; rp++) {
-#if defined(GL_SBOX_INT)
-        const uint64_t y = sbox7(s0);
-        L[0] = u32_to_f64((uint32_t)y);
-        H[0] = u32_to_f64((uint32_t)(y >> 32));
-#else
-        sbox7_f64(s0, L[0], H[0]);  // signed low limb, |L[0]| < 2^33.6: covered by the 2^50 bias
-#endif
-        double aL = T.pa_f64[rp][0], aH = T.pa_f64[rp][1];
-#pragma unroll
-        for (int j = 0; j < 12; j++) {
-            aL = f64_fma(L[j], (double)mds_entry(0, j), aL);
-            aH = f64_fma(H[j], (double)mds_entry(0, j), aH);
-        }
-        GL_F64_TRACK(aL);
-        GL_F64_TRACK(aH);
-#if defined(GL_SBOX_INT)
-        const uint64_t z = sbox7(f64_pair_to_u64(aL, aH));
-        const double zL = u32_to_f64((uint32_t)z), zH = u32_to_f64((uint32_t)(z >> 32));
-#else
-        double zL, zH;
-        sbox7_f64(f64_pair_to_u64(aL, aH), zL, zH);
-#endif
-        const double* k = T.pk_f64[rp];
-        {
-            double n[12];
-#pragma unroll
-            for (int i = 0; i < 12; i++) {
-                double a = f64_fma(zL, (double)mds_entry(i, 0), k[2 * i]);
-#pragma unroll
-                for (int j = 0; j < 12; j++) a = f64_fma(L[j], mds_pair_entry(i, j), a);
-                n[i] = a;
-                GL_F64_TRACK(a);
-            }
-#pragma unroll
-            for (int i = 0; i < 12; i++) L[i] = n[i];
-        }
-        {
-            double n[12];
-#pragma unroll
-            for (int i = 0; i < 12; i++) {
-                double a = f64_fma(zH, (double)mds_entry(i, 0), k[2 * i + 1]);
-#pragma unroll
-                for (int j = 0; j < 12; j++) a = f64_fma(H[j], mds_pair_entry(i, j), a);
-                n[i] = a;
-                GL_F64_TRACK(a);
-            }
-#pragma unroll
-            for (int i = 0; i < 12; i++) H[i] = n[i];
-        }
-        s0 = f64_pair_to_u64(L[0], H[0]);
-        if (rp != 10) {
-            const double C84 = 29014219670751100192948224.0;  // 1.5 * 2^84: x + C84 is rounded to a multiple of 2^32
-            const double I32 = 2.3283064365386962890625e-10;  // 2^-32
-#pragma unroll
-            for (int i = 1; i < 12; i++) {
-                const double th = (H[i] + C84) - C84;
-                const double hlo = H[i] - th;
-                const double l2 = f64_fma(th, -I32, L[i]);
-                const double tl = (l2 + C84) - C84;
-                L[i] = l2 - tl;
-                H[i] = f64_fma(tl, I32, f64_fma(th, I32, hlo));
-            }
-        }
-    }
-#endif  // GL_MDS_DIRECT
     s[0] = s0;
 #pragma unroll
     for (int i = 1; i < 12; i++) s[i] = f64_pair_to_u64(L[i], H[i]);
@@ -678,12 +570,8 @@ GL_HD void poseidon_permute_t(uint64_t s[12]) {
 #if defined(GL_PARTIAL_F64)
         const uint64_t* nrc = (r < 3) ? &T.rc[12 * (r + 1)] : (r == 3) ? &T.rc[48]
                             : (r < 7) ? &T.rc[12 * (r + 23)] : T.zeros;
-#if defined(GL_SBOX_INT)
-        full_round_fused(s, nrc, T.nrc_f64[r == 3 ? 8 : r]);
-#else
         (void)nrc;
-        full_round_f64(s, T.nrcb_f64[r == 3 ? 8 : r], T.nrcs_f64[r == 3 ? 8 : r]);
-#endif
+        full_round_f64(s, T.nrcs_f64[r == 3 ? 8 : r]);
 #else
         const uint64_t* nrc = (r < 3) ? &T.rc[12 * (r + 1)] : (r == 3) ? T.fast_first
                             : (r < 7) ? &T.rc[12 * (r + 23)] : T.zeros;

@@ -7,8 +7,6 @@ NV="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo"
 nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o out/variant_bench variant_bench.cu -lcuda
 v() { name=$1; shift; $NV -cubin -o out/$name.cubin leaf_kernel.cu "$@" & }
 v base
-v mdsdirect -DGL_MDS_DIRECT
-v sboxint -DGL_SBOX_INT
 v cvtmagic -DGL_CVT_MAGIC
 v pfast -DGL_PARTIAL_FAST
 v mdsint -DGL_MDS_INT
