@@ -100,3 +100,22 @@ def test_open_sharded_routing_single_process():
     assert lv[:, 0].tolist() == [100, 131] and pt.shape == (2, 3, 4)
     with pytest.raises(RuntimeError):
         D.open_sharded(FakeBatch(), [5])             # owned by shard 0, nobody serves it here
+
+
+@pytest.mark.parametrize("num_polys,world", [(234, 8), (234, 4), (64, 8), (5, 4), (3, 8), (16, 1)])
+def test_column_slices_tile_the_all_gathered_coefficient_buffer(num_polys, world):
+    """ColumnShardedCommitter's layout contract (column axis): equal-sized (padded) slices, in rank order,
+    so that all_gather_into_tensor of the per-rank (per, n) buffers IS the (world*per, n) coefficient matrix whose
+    first num_polys rows are the columns in order."""
+    from plonky2_b200 import distributed as D
+
+    per_all, covered = None, []
+    for rank in range(world):
+        b0, b1, per = D.column_slice(num_polys, rank, world)
+        per_all = per if per_all is None else per_all
+        assert per == per_all and 0 <= b0 <= b1 <= num_polys and b1 - b0 <= per
+        # a rank's real columns sit at the start of its padded slot: global row rank*per + k <-> column b0 + k
+        assert b0 == min(rank * per, num_polys)
+        covered += list(range(b0, b1))
+    assert covered == list(range(num_polys))
+    assert per_all * world >= num_polys
