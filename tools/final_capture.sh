@@ -1,7 +1,8 @@
 #!/bin/bash
-# Round-end evidence in ONE gpurun call (1 GPU): parity tests, the bench line, the ncu launch list of a bench step and
-# --set full captures of the dominant kernel and of the NTT passes. Outputs in gpurun_out/; tools/update_profiles.py
-# turns them into the tracked summaries under profiles/.
+# Round-end evidence in ONE gpurun call (1 GPU, about 200 s on the box): parity tests, the bench line, the ncu launch
+# list of a bench step and --set full captures of the dominant kernel and of the NTT passes, the microbenchmarks and
+# the Poseidon variant ranking. Outputs in gpurun_out/; `python tools/update_profiles.py prof_leaf_final.ncu-rep` turns
+# them into the tracked summaries under profiles/.
 mkdir -p gpurun_out
 (time timeout 300 python -m pytest tests -m gpu -x -q) > gpurun_out/pytest_gpu_final.log 2>&1
 tail -4 gpurun_out/pytest_gpu_final.log

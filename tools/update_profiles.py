@@ -1,4 +1,4 @@
-"""Regenerate the tracked profile summaries from a gpurun_out/ capture (run here after tools/profile.sh ran on the box).
+"""Regenerate the tracked profile summaries from a gpurun_out/ capture (run here after tools/final_capture.sh ran on the box).
 Reads gpurun_out/prof_leaf*.ncu-rep (ncu --set full of k_leaf_hash) and gpurun_out/launches.csv (launch list of a bench
 step) and writes profiles/r01_ncu_raw_k_leaf_hash.csv, profiles/r01_launches_bench_cfg2.csv, profiles/r01_traffic.json."""
 import csv
