@@ -1,18 +1,19 @@
 // Which B200 pipes share an issue port? Times pure and interleaved streams of DFMA (FP64), IMAD / IMAD.WIDE
-// (FMA-heavy), LOP3 (ALU) and I2F.F64 (XU), each with 8 independent chains per thread. If two classes share a port the
+// (FMA-heavy), LOP3 (ALU) and I2F.F64 (XU), each with 8 independent chains per thread (IMAD.HI streams were added
+// after the round-1 run: profiles/r01_pipe_mix.txt does not have them yet). If two classes share a port the
 // mixed stream takes the SUM of the pure times, otherwise about the MAX. Output feeds the cost model in DESIGN.md.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/pipe_mix tools/pipe_mix.cu
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
 constexpr int ILP = 8, ITERS = 2048;
-template <int D, int I, int W, int A, int X>
+template <int D, int I, int W, int A, int X, int HI = 0>
 __global__ void k_mix(uint64_t* out, double dx, uint32_t ix) {
     double d[ILP];
-    uint32_t a[ILP], m[ILP], xs[ILP];
+    uint32_t a[ILP], m[ILP], xs[ILP], hs[ILP];
     uint64_t w[ILP];
     for (int i = 0; i < ILP; i++) {
-        d[i] = threadIdx.x + i; a[i] = threadIdx.x * 3 + i; m[i] = threadIdx.x + 7 * i; w[i] = threadIdx.x + i; xs[i] = threadIdx.x + i;
+        d[i] = threadIdx.x + i; a[i] = threadIdx.x * 3 + i; m[i] = threadIdx.x + 7 * i; w[i] = threadIdx.x + i; xs[i] = threadIdx.x + i; hs[i] = 0x9E3779B9u * (threadIdx.x + i + 1);
     }
     double acc = 0;
     for (int it = 0; it < ITERS; it++) {
@@ -20,13 +21,14 @@ __global__ void k_mix(uint64_t* out, double dx, uint32_t ix) {
         for (int i = 0; i < ILP; i++) {
             if (D) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dx), "d"(1.0));
             if (I) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(m[i]) : "r"(ix), "r"(i + 1));
+            if (HI) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(hs[i]) : "r"(ix * 0x85EBCA6Bu), "r"(i + 7));
             if (W) asm volatile("{\n\t.reg .u32 t;\n\tcvt.u32.u64 t, %0;\n\tmad.wide.u32 %0, t, %1, %0;\n\t}" : "+l"(w[i]) : "r"(ix));
             if (A) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(ix), "r"(i + 5));
             if (X) asm volatile("{\n\t.reg .f64 t;\n\t.reg .u32 h;\n\tcvt.rn.f64.u32 t, %0;\n\tmov.b64 {%0, h}, t;\n\t}" : "+r"(xs[i]));
         }
     }
     uint64_t s = 0;
-    for (int i = 0; i < ILP; i++) s += (uint64_t)d[i] + a[i] + m[i] + w[i] + xs[i];
+    for (int i = 0; i < ILP; i++) s += (uint64_t)d[i] + a[i] + m[i] + w[i] + xs[i] + hs[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s + (uint64_t)acc;
 }
 template <typename F>
@@ -64,5 +66,10 @@ int main() {
     RUN(1, 0, 0, 0, 1, "DFMA+I2F");
     RUN(0, 1, 0, 0, 1, "IMAD+I2F");
     RUN(1, 1, 1, 1, 1, "all five");
+#define RUNH(D, I, W, A, X, name) rep(name, timeit([&] { k_mix<D, I, W, A, X, 1><<<blocks, threads>>>(out, 1.0000001, 3); }))
+    RUNH(0, 0, 0, 0, 0, "IMAD.HI");
+    RUNH(0, 1, 0, 0, 0, "IMAD.HI+IMAD");
+    RUNH(0, 0, 0, 1, 0, "IMAD.HI+LOP3");
+    RUNH(1, 0, 0, 0, 0, "IMAD.HI+DFMA");
     return 0;
 }
