@@ -39,6 +39,7 @@ extern "C" {
 #define GL_ERR_UNSUPPORTED 4 /* size beyond this build's limits (log_n > 24 per transform) */
 #define GL_ERR_BAD_ARG 5
 #define GL_ERR_POW_FAILED 6
+#define GL_ERR_DIV_ZERO 7    /* "Tried to invert zero" (field/src/types.rs batch_multiplicative_inverse panics) */
 
 #define GL_MEM_HOST 0
 #define GL_MEM_DEVICE 1
@@ -136,7 +137,7 @@ const uint64_t* gl_commit_dev_coeffs(const gl_commit* c);
 /* wires_permutation_partial_products_and_zs (plonky2/src/plonk/prover.rs:387-449, util/partial_products.rs:13-37):
  * wires, sigmas = num_routed columns of n = 2^log_n values (column-major); k_is = num_routed host words;
  * out = (ceil(num_routed/degree)) columns of n values: the partial products, then Z LAST (the function's
- * return order). Produces the second commitment's input on the device. Fails with GL_ERR_BAD_ARG
+ * return order). Produces the second commitment's input on the device. Fails with GL_ERR_DIV_ZERO
  * ("Tried to invert zero") where the reference's batch_multiplicative_inverse panics. */
 int gl_partial_products_and_zs(gl_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, const uint64_t* k_is,
                                uint32_t log_n, uint32_t num_routed, uint64_t beta, uint64_t gamma, uint32_t degree,
@@ -146,6 +147,9 @@ int gl_partial_products_and_zs(gl_ctx* ctx, const uint64_t* wires, const uint64_
 /* PoseidonPermutation::permute on the HOST for the sequential Fiat-Shamir transcript
  * (plonky2/src/iop/challenger.rs:129-144); the same source as the device permutation. */
 void gl_poseidon_permute_host(uint64_t state[12]);
+/* Batched PoseidonPermutation::permute (plonky2/src/hash/poseidon.rs:766-777, hashing.rs:62-94): n_items states of
+ * 12 words, permuted in place on the device; outputs canonical. */
+int gl_poseidon_permute_many(gl_ctx* ctx, uint64_t* states, size_t n_items, int mem);
 /* Batched PoseidonHash::hash_or_noop: n_items inputs of W words (row-major) -> n_items x 4 words */
 int gl_poseidon_hash_many(gl_ctx* ctx, const uint64_t* in, size_t n_items, uint32_t W, uint64_t* out, int mem);
 /* Batched PoseidonHash::hash_no_pad (always the sponge, no no-op branch; hashing.rs:118-145) */

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libplonky2_b200.so")
 
 GL_OK = 0
-GL_ERR_BAD_SHAPE, GL_ERR_OOM, GL_ERR_CUDA, GL_ERR_UNSUPPORTED, GL_ERR_BAD_ARG, GL_ERR_POW_FAILED = 1, 2, 3, 4, 5, 6
+GL_ERR_BAD_SHAPE, GL_ERR_OOM, GL_ERR_CUDA, GL_ERR_UNSUPPORTED, GL_ERR_BAD_ARG, GL_ERR_POW_FAILED, GL_ERR_DIV_ZERO = 1, 2, 3, 4, 5, 6, 7
 MEM_HOST, MEM_DEVICE = 0, 1
 
 u64p = C.POINTER(C.c_uint64)
@@ -25,7 +25,7 @@ EXPORTS = [
     "gl_commit_leaf_width", "gl_commit_degree_log", "gl_commit_rate_bits", "gl_commit_cap_height",
     "gl_commit_cap", "gl_commit_coeffs", "gl_commit_leaves", "gl_commit_digests", "gl_commit_get_lde_values",
     "gl_commit_open", "gl_commit_eval_ext", "gl_commit_dev_leaves", "gl_commit_dev_coeffs", "gl_partial_products_and_zs", "gl_poseidon_permute_host",
-    "gl_poseidon_hash_many", "gl_poseidon_hash_no_pad_many", "gl_poseidon_two_to_one_many", "gl_merkle_build", "gl_merkle_destroy",
+    "gl_poseidon_permute_many", "gl_poseidon_hash_many", "gl_poseidon_hash_no_pad_many", "gl_poseidon_two_to_one_many", "gl_merkle_build", "gl_merkle_destroy",
     "gl_merkle_cap", "gl_merkle_digests", "gl_merkle_open", "gl_fri_begin", "gl_fri_begin_from_coeffs",
     "gl_fri_destroy", "gl_fri_coeffs", "gl_fri_commit_round", "gl_fri_fold", "gl_fri_final_poly",
     "gl_fri_open", "gl_fri_num_rounds", "gl_fri_pow",
@@ -97,6 +97,7 @@ def lib():
                                              C.c_uint32, vp, C.c_int]
     L.gl_poseidon_permute_host.argtypes = [vp]
     L.gl_poseidon_permute_host.restype = None
+    L.gl_poseidon_permute_many.argtypes = [vp, vp, C.c_size_t, C.c_int]
     L.gl_poseidon_hash_many.argtypes = [vp, vp, C.c_size_t, C.c_uint32, vp, C.c_int]
     L.gl_poseidon_hash_no_pad_many.argtypes = [vp, vp, C.c_size_t, C.c_uint32, vp, C.c_int]
     L.gl_poseidon_two_to_one_many.argtypes = [vp, vp, C.c_size_t, vp, C.c_int]
@@ -132,6 +133,8 @@ def check(rc, ctx=None):
         raise ShapeError(msg)
     if rc == GL_ERR_OOM:
         raise MemoryError(msg)
+    if rc == GL_ERR_DIV_ZERO:
+        raise ZeroDivisionError(msg)
     raise NativeError("plonky2_b200 native error %d: %s" % (rc, msg))
 
 

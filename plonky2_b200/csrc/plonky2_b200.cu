@@ -51,6 +51,9 @@ struct gl_ctx {
     size_t dstage_words = 0;
     uint32_t ntt_group = 0;                     // 0 = auto
     int ntt_force_b = 0;                        // 0 = balanced split; else log2 of the contiguous pass size
+    int sm_count = 0;                           // queried once for ctx->device in gl_ctx_create
+    int coop_ok = 0;                            // cooperative launch supported on this device
+    int coop_blocks_per_sm = 0;                 // resident CTAs/SM of k_merkle_upper on this device
     // optional CUDA-event phase timing (bench.py's roofline numbers come from here)
     bool prof_on = false;
     struct Pending {
@@ -690,6 +693,17 @@ __global__ void __launch_bounds__(128) k_hash_many(const u64* in, size_t n_items
     hash_or_noop_strided<NOOP_SHORT>(in + j * W, 1, W, h);
     for (int k = 0; k < 4; k++) out[4 * j + k] = h[k];
 }
+// PoseidonPermutation::permute on n_items independent 12-lane states, in place (hashing.rs:62-94 permute)
+__global__ void __launch_bounds__(128) k_permute_many(u64* states, size_t n_items) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_items) return;
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = states[12 * j + k];
+    poseidon_permute(s);
+#pragma unroll
+    for (int k = 0; k < 12; k++) states[12 * j + k] = canon(s[k]);
+}
 __global__ void __launch_bounds__(128) k_two_to_one_many(const u64* in, size_t n_items, u64* out) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_items) return;
@@ -757,14 +771,8 @@ static int tree_build(gl_ctx* ctx, Tree& t) {
     PhaseScope ps2(ctx, GL_PHASE_MERKLE_LEVELS);
     const uint32_t sub_log = t.log_n - t.cap_height;
     // resident capacity of the persistent upper-level kernel (cooperative launch needs co-residency)
-    static int coop_blocks_per_sm = -1, coop_sms = 0, coop_ok = 0;
-    if (coop_blocks_per_sm < 0) {
-        cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, ctx->device);
-        cudaDeviceGetAttribute(&coop_sms, cudaDevAttrMultiProcessorCount, ctx->device);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks_per_sm, k_merkle_upper, HASH_CTA, 0) != cudaSuccess)
-            coop_blocks_per_sm = 0;
-    }
-    const size_t coop_threads = coop_ok ? (size_t)coop_blocks_per_sm * coop_sms * HASH_CTA : 0;
+    // (per-context, i.e. per-device, values: gl_ctx_create)
+    const size_t coop_threads = ctx->coop_ok ? (size_t)ctx->coop_blocks_per_sm * ctx->sm_count * HASH_CTA : 0;
     for (uint32_t i = 1; i <= sub_log; i++) {
         size_t total = (size_t)1 << (t.log_n - i);
         if (coop_threads && total <= coop_threads && i < sub_log) {
@@ -870,7 +878,13 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
     // overlaps the transforms of chunk k.
     const uint32_t CH = 32;  // 32 columns: launches big enough for full waves, first-chunk H2D exposure ~5 ms at n = 2^20
     const bool overlap = (mem == GL_MEM_HOST) && B > CH;
-    std::vector<cudaEvent_t> evs;
+    struct EventList {  // destroyed on every exit path
+        std::vector<cudaEvent_t> v;
+        ~EventList() {
+            for (auto e : v) cudaEventDestroy(e);
+        }
+    } evl;
+    std::vector<cudaEvent_t>& evs = evl.v;
     if (overlap) {
         if (!ctx->copy_stream) CK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         cudaEvent_t ready;
@@ -950,7 +964,6 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
         };
         rc_loop = chunk();
     }
-    for (auto e : evs) cudaEventDestroy(e);
     TRY(rc_loop);
     if (salt) {
         u64* dsalt = nullptr;
@@ -1003,6 +1016,48 @@ __global__ void k_fill_e2_pows(E2 base, size_t count, u64* out) {
     out[2 * i] = r.a;
     out[2 * i + 1] = r.b;
 }
+// four power tables in one launch: segment t holds base[t]^i, i < count[t]
+struct E2Pows4 {
+    E2 base[4];
+    size_t count[4];
+    u64* out[4];
+};
+__global__ void k_fill_e2_pows4(E2Pows4 p) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        if (i < p.count[t]) {
+            E2 r = e2_pow(p.base[t], i);
+            p.out[t][2 * i] = r.a;
+            p.out[t][2 * i + 1] = r.b;
+            return;
+        }
+        i -= p.count[t];
+    }
+}
+// CTA-wide exclusive SUFFIX sum over F_{p^2} (thread t gets the sum of the values of threads > t, plus `carry`);
+// log-step Hillis-Steele in shared memory (sh: 2 * blockDim.x words).
+__device__ __forceinline__ E2 block_suffix_excl(E2 v, E2 carry, u64* sh) {
+    const int t = threadIdx.x, nt = blockDim.x;
+    sh[2 * t] = v.a;
+    sh[2 * t + 1] = v.b;
+    __syncthreads();
+    E2 acc = v;
+    for (int off = 1; off < nt; off <<= 1) {
+        E2 o = {0, 0};
+        if (t + off < nt) o = E2{sh[2 * (t + off)], sh[2 * (t + off) + 1]};
+        __syncthreads();
+        acc = e2_add(acc, o);
+        sh[2 * t] = acc.a;
+        sh[2 * t + 1] = acc.b;
+        __syncthreads();
+    }
+    // acc = inclusive suffix; exclusive = inclusive of t+1
+    E2 ex = carry;
+    if (t + 1 < nt) ex = e2_add(carry, E2{sh[2 * (t + 1)], sh[2 * (t + 1) + 1]});
+    __syncthreads();
+    return ex;
+}
 // divide_by_linear (division.rs:75-88) as a suffix scan: acc_k = sum_{m>=k} c_m z^{m-k}
 //   = z^{-k} * S_k,  S_k = sum_{m>=k} c_m z^m ;  quotient q_k = acc_{k+1}, q_{n-1} = 0.
 constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;
@@ -1036,11 +1091,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_phase1(u64* comp, size_t 
         chunk_tot[2 * blockIdx.x + 1] = sh[1];
     }
 }
-// phase 2: exclusive suffix sums of the chunk totals (single thread; <= 8192 chunks)
-__global__ void k_scan_phase2(u64* chunk_tot, size_t nchunks) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    E2 run = {0, 0};
-    for (size_t i = nchunks; i-- > 0;) {
+// phase 2: exclusive suffix sums of the chunk totals, one CTA: each thread owns a contiguous run of chunks
+__global__ void __launch_bounds__(1024) k_scan_phase2(u64* chunk_tot, size_t nchunks) {
+    __shared__ u64 sh[2 * 1024];
+    const size_t per = (nchunks + blockDim.x - 1) / blockDim.x;
+    const size_t lo = (size_t)threadIdx.x * per < nchunks ? (size_t)threadIdx.x * per : nchunks;
+    const size_t hi = lo + per < nchunks ? lo + per : nchunks;
+    E2 tot = {0, 0};
+    for (size_t i = lo; i < hi; i++) tot = e2_add(tot, E2{chunk_tot[2 * i], chunk_tot[2 * i + 1]});
+    E2 run = block_suffix_excl(tot, E2{0, 0}, sh);
+    for (size_t i = hi; i-- > lo;) {
         E2 t = {chunk_tot[2 * i], chunk_tot[2 * i + 1]};
         chunk_tot[2 * i] = run.a;
         chunk_tot[2 * i + 1] = run.b;
@@ -1062,21 +1122,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_phase3(const u64* d, size
         if (m < n) run = e2_add(run, E2{d[2 * m], d[2 * m + 1]});
         loc[i] = run;
     }
-    sh[2 * threadIdx.x] = run.a;
-    sh[2 * threadIdx.x + 1] = run.b;
-    __syncthreads();
-    // exclusive suffix over threads (serial in thread 0: 256 adds)
-    if (threadIdx.x == 0) {
-        E2 r = {chunk_carry[2 * blockIdx.x], chunk_carry[2 * blockIdx.x + 1]};
-        for (int t = SCAN_THREADS - 1; t >= 0; t--) {
-            E2 v = {sh[2 * t], sh[2 * t + 1]};
-            sh[2 * t] = r.a;
-            sh[2 * t + 1] = r.b;
-            r = e2_add(r, v);
-        }
-    }
-    __syncthreads();
-    const E2 carry = {sh[2 * threadIdx.x], sh[2 * threadIdx.x + 1]};
+    // exclusive suffix over the CTA's threads (log-step scan) + the carry of the later chunks
+    const E2 carry = block_suffix_excl(run, E2{chunk_carry[2 * blockIdx.x], chunk_carry[2 * blockIdx.x + 1]}, sh);
     // S_m = loc[i] + carry for m = base + i. q_k = z^{-(k+1)} * S_{k+1}.
     // This thread owns S_m for m in [base, base+ITEMS): emits q_{m-1}.
     for (int i = 0; i < SCAN_ITEMS; i++) {
@@ -1378,12 +1425,28 @@ int gl_ctx_create(int device, void* stream, gl_ctx** out) {
     if (device < 0 || device >= count) return set_err(nullptr, GL_ERR_BAD_ARG, "device %d out of range", device);
     gl_ctx* ctx = new gl_ctx();
     ctx->device = device;
-    CK(ctx, cudaSetDevice(device));
-    if (stream) {
-        ctx->stream = (cudaStream_t)stream;
-    } else {
-        CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        ctx->own_stream = true;
+    auto init = [&]() -> int {
+        CK(ctx, cudaSetDevice(device));
+        if (stream) {
+            ctx->stream = (cudaStream_t)stream;
+        } else {
+            CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+            ctx->own_stream = true;
+        }
+        CK(ctx, cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+        CK(ctx, cudaDeviceGetAttribute(&ctx->coop_ok, cudaDevAttrCooperativeLaunch, device));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->coop_blocks_per_sm, k_merkle_upper, HASH_CTA, 0) !=
+            cudaSuccess)
+            ctx->coop_blocks_per_sm = 0;
+        const PoseidonTables& t = host_poseidon_tables();
+        CK(ctx, cudaMemcpyToSymbol(c_pos, &t, sizeof(PoseidonTables)));
+        return GL_OK;
+    };
+    const int rc_init = init();
+    if (rc_init != GL_OK) {  // no half-built context escapes (and none leaks)
+        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return rc_init;
     }
     // keep freed blocks in the pool: the commit buffers are large and re-allocated every call
     cudaMemPool_t pool;
@@ -1391,8 +1454,6 @@ int gl_ctx_create(int device, void* stream, gl_ctx** out) {
         unsigned long long thr = ~0ULL;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
-    const PoseidonTables& t = host_poseidon_tables();
-    CK(ctx, cudaMemcpyToSymbol(c_pos, &t, sizeof(PoseidonTables)));
     *out = ctx;
     return GL_OK;
 }
@@ -1475,14 +1536,14 @@ int gl_ntt(gl_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t batch, size_t s
     if (mem == GL_MEM_DEVICE) return ntt_natural(ctx, data, stride, data, stride, (int)log_n, batch, inverse != 0, coset_shift);
     u64* d;
     TRY(dmalloc(ctx, &d, (size_t)batch * n));
-    for (uint32_t b = 0; b < batch; b++) TRY(h2d(ctx, d + (size_t)b * n, data + (size_t)b * stride, n));
-    int rc = ntt_natural(ctx, d, n, d, n, (int)log_n, batch, inverse != 0, coset_shift);
+    const size_t pitch = (batch > 1 ? stride : n) * 8;  // one strided copy each way
+    int rc = GL_OK;
+    if (cudaMemcpy2DAsync(d, n * 8, data, pitch, n * 8, batch, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+        rc = set_err(ctx, GL_ERR_CUDA, "H2D: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc == GL_OK) rc = ntt_natural(ctx, d, n, d, n, (int)log_n, batch, inverse != 0, coset_shift);
     if (rc == GL_OK) {
-        for (uint32_t b = 0; b < batch && rc == GL_OK; b++) {
-            cudaError_t e = cudaMemcpyAsync(data + (size_t)b * stride, d + (size_t)b * n, n * 8, cudaMemcpyDeviceToHost,
-                                            ctx->stream);
-            if (e != cudaSuccess) rc = set_err(ctx, GL_ERR_CUDA, "D2H: %s", cudaGetErrorString(e));
-        }
+        cudaError_t e = cudaMemcpy2DAsync(data, pitch, d, n * 8, n * 8, batch, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = set_err(ctx, GL_ERR_CUDA, "D2H: %s", cudaGetErrorString(e));
         if (rc == GL_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
             rc = set_err(ctx, GL_ERR_CUDA, "sync failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -1648,7 +1709,7 @@ int gl_partial_products_and_zs(gl_ctx* ctx, const uint64_t* wires, const uint64_
         CKL(ctx);
         u64 flag = 0;
         TRY(d2h(ctx, &flag, dflag, 1));
-        if (flag & 0xFFFFFFFFu) return set_err(ctx, GL_ERR_BAD_ARG, "Tried to invert zero");
+        if (flag & 0xFFFFFFFFu) return set_err(ctx, GL_ERR_DIV_ZERO, "Tried to invert zero");
         if (mem == GL_MEM_HOST) TRY(d2h(ctx, out, dout, (size_t)M * n));
         return GL_OK;
     };
@@ -1708,6 +1769,29 @@ int gl_poseidon_two_to_one_many(gl_ctx* ctx, const uint64_t* in, size_t n_items,
     if (!ctx || !out || !in) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
     CK(ctx, cudaSetDevice(ctx->device));
     return hash_many_impl(ctx, in, n_items, 8, out, mem, 1, 8);
+}
+
+int gl_poseidon_permute_many(gl_ctx* ctx, uint64_t* states, size_t n_items, int mem) {
+    if (!ctx || !states) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (n_items == 0) return GL_OK;
+    u64* d = states;
+    if (mem == GL_MEM_HOST) {
+        TRY(dmalloc(ctx, &d, n_items * 12));
+        int rc = h2d(ctx, d, states, n_items * 12);
+        if (rc != GL_OK) {
+            dfree(ctx, d);
+            return rc;
+        }
+    }
+    k_permute_many<<<(unsigned)((n_items + 127) / 128), 128, 0, ctx->stream>>>(d, n_items);
+    ctx->launches++;
+    int rc = cudaGetLastError() == cudaSuccess ? GL_OK : set_err(ctx, GL_ERR_CUDA, "k_permute_many launch failed");
+    if (mem == GL_MEM_HOST) {
+        if (rc == GL_OK) rc = d2h(ctx, states, d, n_items * 12);
+        dfree(ctx, d);
+    }
+    return rc;
 }
 
 struct gl_merkle {
@@ -1775,38 +1859,45 @@ int gl_fri_begin(gl_ctx* ctx, gl_commit* const* oracles, size_t n_oracles, const
     f->rate_bits = rate_bits;
     f->cap_height = cap_height;
     int rc = GL_OK;
-    u64 *comp = nullptr, *chunk = nullptr, *drefs = nullptr;
+    u64 *comp = nullptr, *chunk = nullptr, *drefs = nullptr, *ztab = nullptr;
     const E2 alpha = {canon(alpha_in[0]), canon(alpha_in[1])};
     const size_t nchunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    const size_t hi_cnt = (n >> 12) + 1;
     auto body = [&]() -> int {
         TRY(dmalloc(ctx, &f->coeff_cols, 2 * n));
         TRY(dmalloc(ctx, &comp, 2 * n));
         TRY(dmalloc(ctx, &chunk, 2 * nchunks));
-        size_t max_polys = 0;
-        for (size_t b = 0; b < n_batches; b++) max_polys = batches[b].num_polys > max_polys ? batches[b].num_polys : max_polys;
-        const size_t ref_words = max_polys * sizeof(PolyRef) / 8;
-        TRY(dmalloc(ctx, &drefs, ref_words));
-        for (size_t b = 0; b < n_batches; b++) {
+        // z / z^-1 power tables: [zhi | zlo | zihi | zilo], one allocation reused by every batch (stream-ordered)
+        TRY(dmalloc(ctx, &ztab, 2 * (2 * hi_cnt + 2 * 4096)));
+        u64 *zhi = ztab, *zlo = zhi + 2 * hi_cnt, *zihi = zlo + 2 * 4096, *zilo = zihi + 2 * hi_cnt;
+        // alpha^j per polynomial (ReducingFactor restarts at alpha^0 for every batch): the references of ALL batches
+        // go up in one copy (a pageable source is staged by the runtime before cudaMemcpyAsync returns)
+        size_t total_polys = 0;
+        for (size_t b = 0; b < n_batches; b++) total_polys += batches[b].num_polys;
+        std::vector<PolyRef> refs(total_polys);
+        std::vector<E2> shiftmuls(n_batches);
+        for (size_t b = 0, at = 0; b < n_batches; b++) {
             const gl_fri_batch& batch = batches[b];
-            // alpha^j per polynomial (ReducingFactor restarts at alpha^0 for every batch)
-            TRY(ensure_pinned(ctx, ref_words));
-            CK(ctx, cudaStreamSynchronize(ctx->stream));
-            PolyRef* refs = (PolyRef*)ctx->pinned;
             E2 ap = {1, 0};
-            for (size_t j = 0; j < batch.num_polys; j++) {
+            for (size_t j = 0; j < batch.num_polys; j++, at++) {
                 const uint32_t oi = batch.oracle_index[j], pi = batch.poly_index[j];
                 if (oi >= n_oracles || pi >= oracles[oi]->B) return set_err(ctx, GL_ERR_BAD_ARG, "bad polynomial reference");
-                refs[j].ptr = oracles[oi]->coeffs + (size_t)pi * n;
-                refs[j].a0 = canon(ap.a);
-                refs[j].a1 = canon(ap.b);
+                refs[at].ptr = oracles[oi]->coeffs + (size_t)pi * n;
+                refs[at].a0 = canon(ap.a);
+                refs[at].a1 = canon(ap.b);
                 ap = e2_mul(ap, alpha);
             }
-            const E2 shiftmul = {canon(ap.a), canon(ap.b)};  // alpha^count: alpha.shift_poly (reducing.rs:102-106)
-            TRY(h2d(ctx, drefs, ctx->pinned, batch.num_polys * sizeof(PolyRef) / 8));
-            k_fri_compose<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const PolyRef*)drefs,
+            shiftmuls[b] = E2{canon(ap.a), canon(ap.b)};  // alpha^count: alpha.shift_poly (reducing.rs:102-106)
+        }
+        const size_t ref_words = total_polys * sizeof(PolyRef) / 8;
+        TRY(dmalloc(ctx, &drefs, ref_words));
+        if (ref_words) TRY(h2d(ctx, drefs, (const u64*)refs.data(), ref_words));
+        for (size_t b = 0, at = 0; b < n_batches; at += batches[b].num_polys, b++) {
+            const gl_fri_batch& batch = batches[b];
+            const E2 shiftmul = shiftmuls[b];
+            k_fri_compose<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const PolyRef*)drefs + at,
                                                                               (uint32_t)batch.num_polys, n, comp);
             CKL(ctx);
-            CK(ctx, cudaStreamSynchronize(ctx->stream));  // pinned refs consumed
             const E2 z = {canon(batch.point[0]), canon(batch.point[1])};
             if (z.a == 0 && z.b == 0) {
                 k_div_by_x<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(comp, n, shiftmul, b == 0, f->coeff_cols);
@@ -1814,31 +1905,17 @@ int gl_fri_begin(gl_ctx* ctx, gl_commit* const* oracles, size_t n_oracles, const
                 continue;
             }
             const E2 zi = e2_inv(z);
-            const size_t hi_cnt = (n >> 12) + 1;
-            u64 *zhi, *zlo, *zihi, *zilo;
-            TRY(dmalloc(ctx, &zhi, 2 * hi_cnt));
-            TRY(dmalloc(ctx, &zlo, 2 * 4096));
-            TRY(dmalloc(ctx, &zihi, 2 * hi_cnt));
-            TRY(dmalloc(ctx, &zilo, 2 * 4096));
-            k_fill_e2_pows<<<(unsigned)((hi_cnt + 127) / 128), 128, 0, ctx->stream>>>(e2_pow(z, 4096), hi_cnt, zhi);
-            CKL(ctx);
-            k_fill_e2_pows<<<32, 128, 0, ctx->stream>>>(z, 4096, zlo);
-            CKL(ctx);
-            k_fill_e2_pows<<<(unsigned)((hi_cnt + 127) / 128), 128, 0, ctx->stream>>>(e2_pow(zi, 4096), hi_cnt, zihi);
-            CKL(ctx);
-            k_fill_e2_pows<<<32, 128, 0, ctx->stream>>>(zi, 4096, zilo);
+            E2Pows4 pw{{e2_pow(z, 4096), z, e2_pow(zi, 4096), zi}, {hi_cnt, 4096, hi_cnt, 4096}, {zhi, zlo, zihi, zilo}};
+            const size_t fill_total = 2 * hi_cnt + 2 * 4096;
+            k_fill_e2_pows4<<<(unsigned)((fill_total + 127) / 128), 128, 0, ctx->stream>>>(pw);
             CKL(ctx);
             k_scan_phase1<<<(unsigned)nchunks, SCAN_THREADS, 0, ctx->stream>>>(comp, n, zhi, zlo, chunk);
             CKL(ctx);
-            k_scan_phase2<<<1, 32, 0, ctx->stream>>>(chunk, nchunks);
+            k_scan_phase2<<<1, 1024, 0, ctx->stream>>>(chunk, nchunks);
             CKL(ctx);
             k_scan_phase3<<<(unsigned)nchunks, SCAN_THREADS, 0, ctx->stream>>>(comp, n, chunk, zihi, zilo, shiftmul,
                                                                               b == 0, f->coeff_cols);
             CKL(ctx);
-            dfree(ctx, zhi);
-            dfree(ctx, zlo);
-            dfree(ctx, zihi);
-            dfree(ctx, zilo);
         }
         TRY(fri_finish_begin(ctx, f));
         return GL_OK;
@@ -1847,6 +1924,7 @@ int gl_fri_begin(gl_ctx* ctx, gl_commit* const* oracles, size_t n_oracles, const
     dfree(ctx, comp);
     dfree(ctx, chunk);
     dfree(ctx, drefs);
+    dfree(ctx, ztab);
     if (rc != GL_OK) {
         gl_fri_destroy(f);
         return rc;
@@ -2042,12 +2120,20 @@ int gl_fri_pow(gl_ctx* ctx, const uint64_t state[12], uint32_t pos, uint32_t min
     int rc = GL_OK;
     u64 found = ~0ULL;
     for (u64 start = 0; start < P; start += batch, batch = batch < ((u64)1 << 24) ? batch * 4 : batch) {
-        CK(ctx, cudaMemsetAsync(dres, 0xFF, 8, ctx->stream));
+        if (cudaMemsetAsync(dres, 0xFF, 8, ctx->stream) != cudaSuccess) {
+            rc = set_err(ctx, GL_ERR_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
         pp.start = start;
         pp.count = (P - start < batch) ? P - start : batch;
-        const unsigned nb = (unsigned)((pp.count + 127) / 128 < 148 * 8 ? (pp.count + 127) / 128 : 148 * 8);
+        const u64 nb_max = (u64)ctx->sm_count * 8;
+        const unsigned nb = (unsigned)((pp.count + 127) / 128 < nb_max ? (pp.count + 127) / 128 : nb_max);
         k_fri_pow<<<nb, 128, 0, ctx->stream>>>(pp, dres);
-        CKL(ctx);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) {
+            rc = set_err(ctx, GL_ERR_CUDA, "k_fri_pow launch failed");
+            break;
+        }
         rc = d2h(ctx, &found, (u64*)dres, 1);
         if (rc != GL_OK || found != ~0ULL) break;
         if (start > ((u64)1 << 40)) {

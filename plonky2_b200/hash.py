@@ -54,6 +54,15 @@ class PoseidonHash:
     HASH_SIZE = 32
 
     @staticmethod
+    def permute_many(states, ctx=None):
+        """PoseidonPermutation::permute on every row of an (n_items, 12) array, on the device -> (n_items, 12)."""
+        ctx = ctx or N.default_context()
+        st = np.array(states, dtype=np.uint64).reshape(-1, SPONGE_WIDTH).copy()
+        if len(st):
+            N.check(N.lib().gl_poseidon_permute_many(ctx.h, N.np_ptr(st), len(st), N.MEM_HOST), ctx.h)
+        return st
+
+    @staticmethod
     def hash_many(rows, ctx=None):
         """hash_or_noop for every row of an (n_items, W) array -> (n_items, 4)."""
         ctx = ctx or N.default_context()

@@ -21,7 +21,5 @@ def wires_permutation_partial_products_and_zs(wires, sigmas, k_is, beta, gamma, 
     out = np.empty(((R + degree - 1) // degree, n), dtype=np.uint64)
     rc = N.lib().gl_partial_products_and_zs(ctx.h, N.np_ptr(wires), N.np_ptr(sigmas), N.np_ptr(k_is), log_n, R,
                                             int(beta), int(gamma), int(degree), N.np_ptr(out), N.MEM_HOST)
-    if rc == N.GL_ERR_BAD_ARG:
-        raise ZeroDivisionError(N.lib().gl_last_error(ctx.h).decode())
-    N.check(rc, ctx.h)
+    N.check(rc, ctx.h)   # GL_ERR_DIV_ZERO -> ZeroDivisionError ("Tried to invert zero"), others keep their own type
     return out

@@ -17,7 +17,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def pb():
     import torch
 
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    if not torch.cuda.is_available():
+        # on the B200 box (GL_REQUIRE_GPU=1) a missing device is a loud failure, elsewhere the gpu tests skip
+        if os.environ.get("GL_REQUIRE_GPU") == "1":
+            raise AssertionError("GPU tests need a CUDA device")
+        pytest.skip("no CUDA device (gpu-marked tests run on the B200 box)")
     import plonky2_b200 as p
 
     p.default_context()  # fails loudly if the CUDA extension is missing
@@ -98,26 +102,25 @@ def test_ntt_shape_errors(pb):
 
 
 # ----------------------------------------------------------------------------- Poseidon / Merkle
-def test_poseidon_kats_on_device(pb):
+def test_poseidon_kats_on_device(pb, oracle):
+    # the reference's 4 stored known-answer vectors (plonky2/src/hash/poseidon_goldilocks.rs:466-487) straight
+    # through the DEVICE permutation (FP64-pipe formulation), 12 lanes in, 12 lanes out
     kat = json.load(open(os.path.join(ROOT, "tests", "golden", "poseidon_kat.json")))
-    for v in kat["vectors"]:
-        inp = np.array([int(x) for x in v["input"]], dtype=np.uint64)
-        exp = [int(x) for x in v["output"]]
-        # hash_no_pad over 8 + 4 lanes exposes lanes 0..3 only; use two_to_one/compress + sponge identities
-        # and check the full state through the sponge: absorb 8 lanes with capacity lanes = 0 is not the KAT
-        # input in general, so check the device permutation through the PoW kernel's sibling: hash_many on a
-        # 12-word leaf equals permute(permute([x0..x7,0,0,0,0]) overwritten by x8..x11).
-        got = pb.PoseidonHash.hash_no_pad(inp)
-        st = np.zeros(12, dtype=np.uint64)
-        st[:8] = inp[:8]
-        pb._native.lib().gl_poseidon_permute_host(pb._native.np_ptr(st))
-        st[:4] = inp[8:]
-        pb._native.lib().gl_poseidon_permute_host(pb._native.np_ptr(st))
-        assert got.tolist() == st[:4].tolist()
-        # the all-zero KAT is directly visible: compress(0, 0) = permute(0)[0..4]
-        if not any(int(x) for x in v["input"]):
-            z = np.zeros(4, dtype=np.uint64)
-            assert pb.PoseidonHash.two_to_one(z, z).tolist() == exp[:4]
+    ins = np.array([[int(x) for x in v["input"]] for v in kat["vectors"]], dtype=np.uint64)
+    exp = np.array([[int(x) for x in v["output"]] for v in kat["vectors"]], dtype=np.uint64)
+    assert len(ins) == 4
+    got = pb.PoseidonHash.permute_many(ins)
+    assert np.array_equal(got, exp)
+    # a few thousand random / non-canonical states against the oracle permutation (both forms agree on the KATs)
+    st = synth(0x4B, (3000, 12), canonical=False)
+    st[:len(EDGE)] = np.array([EDGE] * 12, dtype=np.uint64).T[:, :12]
+    got = pb.PoseidonHash.permute_many(st)
+    for i in list(range(40)) + list(range(2990, 3000)):
+        assert got[i].tolist() == (oracle.poseidon(st[i]) % np.uint64(P)).tolist(), i
+    # host transcript permutation = the same function
+    h = st[17].copy()
+    pb._native.lib().gl_poseidon_permute_host(pb._native.np_ptr(h))
+    assert h.tolist() == got[17].tolist()
 
 
 @pytest.mark.parametrize("W", [0, 1, 3, 4, 5, 7, 8, 9, 12, 16, 17, 33, 135])
