@@ -36,7 +36,7 @@ extern "C" {
 #define GL_ERR_BAD_SHAPE 1   /* not a power of two, inconsistent degrees, cap_height > log2(leaves) ... */
 #define GL_ERR_OOM 2
 #define GL_ERR_CUDA 3
-#define GL_ERR_UNSUPPORTED 4 /* size beyond this build's limits (log_n > 24 per transform) */
+#define GL_ERR_UNSUPPORTED 4 /* size beyond this build's limits (log_n > 30 per transform) */
 #define GL_ERR_BAD_ARG 5
 #define GL_ERR_POW_FAILED 6
 #define GL_ERR_DIV_ZERO 7    /* "Tried to invert zero" (field/src/types.rs batch_multiplicative_inverse panics) */
@@ -59,10 +59,8 @@ const char* gl_last_error(const gl_ctx* ctx); /* ctx may be NULL: last error of 
 int gl_ctx_synchronize(gl_ctx* ctx);
 /* number of kernels this context has launched so far (for bench.py's gpu_launches) */
 uint64_t gl_ctx_launch_count(const gl_ctx* ctx);
-/* tuning: columns per NTT group (scratch = group * n * 8 bytes; sized so pass A -> pass B stays in L2) */
+/* tuning: columns per multi-pass NTT group (scratch = group * n * 8 bytes; default: as many as fit 1 GiB) */
 int gl_ctx_set_ntt_group(gl_ctx* ctx, uint32_t columns);
-/* tuning: log2 of the contiguous (pass B) transform size for two-pass NTTs; 0 = balanced split */
-int gl_ctx_set_ntt_split(gl_ctx* ctx, int log_contiguous);
 /* Optional CUDA-event phase timing on the context's stream (the analogue of the reference's TimingTree
  * scopes "IFFT" / "FFT + blinding" / "build Merkle tree", plonky2/src/fri/oracle.rs:65-103). */
 #define GL_PHASE_INTT 0          /* from_values' iNTT of all columns */
@@ -90,7 +88,7 @@ int gl_ntt(gl_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t batch, size_t s
  * cols + b*col_stride.  salt: NULL (blinding = false) or GL_SALT_SIZE columns of N = n << rate_bits
  * words (column s at salt + s*N) appended to every leaf -- the reference draws them from OsRng
  * (oracle.rs:133-137); here the caller supplies them so the result is deterministic.
- * The handle keeps coefficients (B x n), leaves (N x W row-major, leaf j = LDE row bitrev(j)),
+ * The handle keeps coefficients (B x n), the LDE (W columns of N values in leaf order, leaf j = LDE row bitrev(j)),
  * digests (reference layout, merkle_tree.rs:50-58) and the cap on the device. */
 int gl_commit_create(gl_ctx* ctx, const uint64_t* cols, size_t col_stride, uint32_t B, uint32_t log_n,
                      uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, int is_coeffs,
@@ -129,8 +127,11 @@ int gl_commit_open(gl_commit* c, const uint64_t* leaf_indices, size_t count, uin
  * evaluated at one point z of F_{p^2}: out = B x 2 words (host). First "next" row of SURVEY section 8(f):
  * it keeps the coefficient D2H off the prover's critical path. */
 int gl_commit_eval_ext(gl_commit* c, const uint64_t point[2], uint64_t* out);
-/* device views (valid until destroy; for device-resident pipelines and benchmarks) */
-const uint64_t* gl_commit_dev_leaves(const gl_commit* c);
+/* device views (valid until destroy; for device-resident pipelines such as quotient evaluation).
+ * The LDE is kept COLUMN-MAJOR on the device: the value of polynomial (or salt column) k at leaf j -- the LDE row
+ * reverse_bits(j), oracle.rs:142-147 -- is at lde[k * col_stride + j]; col_stride = number of local leaves. The
+ * reference's row-major MerkleTree.leaves is what gl_commit_leaves / gl_commit_open return. */
+const uint64_t* gl_commit_dev_lde(const gl_commit* c, size_t* col_stride);
 const uint64_t* gl_commit_dev_coeffs(const gl_commit* c);
 
 /* ---- "next" rows ------------------------------------------------------------------ */

@@ -20,11 +20,11 @@ vp = C.c_void_p
 
 EXPORTS = [
     "gl_ctx_create", "gl_ctx_destroy", "gl_last_error", "gl_ctx_synchronize", "gl_ctx_launch_count",
-    "gl_ctx_set_ntt_group", "gl_ctx_set_ntt_split", "gl_ctx_set_profiling", "gl_ctx_phase_ms", "gl_ctx_reset_phases", "gl_ntt",
+    "gl_ctx_set_ntt_group", "gl_ctx_set_profiling", "gl_ctx_phase_ms", "gl_ctx_reset_phases", "gl_ntt",
     "gl_commit_create", "gl_commit_create_sharded", "gl_commit_shard", "gl_commit_destroy", "gl_commit_num_polys",
     "gl_commit_leaf_width", "gl_commit_degree_log", "gl_commit_rate_bits", "gl_commit_cap_height",
     "gl_commit_cap", "gl_commit_coeffs", "gl_commit_leaves", "gl_commit_digests", "gl_commit_get_lde_values",
-    "gl_commit_open", "gl_commit_eval_ext", "gl_commit_dev_leaves", "gl_commit_dev_coeffs", "gl_partial_products_and_zs", "gl_poseidon_permute_host",
+    "gl_commit_open", "gl_commit_eval_ext", "gl_commit_dev_lde", "gl_commit_dev_coeffs", "gl_partial_products_and_zs", "gl_poseidon_permute_host",
     "gl_poseidon_permute_many", "gl_poseidon_hash_many", "gl_poseidon_hash_no_pad_many", "gl_poseidon_two_to_one_many", "gl_merkle_build", "gl_merkle_destroy",
     "gl_merkle_cap", "gl_merkle_digests", "gl_merkle_open", "gl_fri_begin", "gl_fri_begin_from_coeffs",
     "gl_fri_destroy", "gl_fri_coeffs", "gl_fri_commit_round", "gl_fri_fold", "gl_fri_final_poly",
@@ -66,7 +66,6 @@ def lib():
     L.gl_ctx_launch_count.argtypes = [vp]
     L.gl_ctx_launch_count.restype = C.c_uint64
     L.gl_ctx_set_ntt_group.argtypes = [vp, C.c_uint32]
-    L.gl_ctx_set_ntt_split.argtypes = [vp, C.c_int]
     L.gl_ntt.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_size_t, C.c_int, C.c_uint32, C.c_uint64, C.c_int]
     L.gl_commit_create.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp,
                                    C.c_int, C.c_int, C.POINTER(vp)]
@@ -89,8 +88,8 @@ def lib():
     L.gl_commit_get_lde_values.argtypes = [vp, C.c_size_t, C.c_size_t, vp]
     L.gl_commit_open.argtypes = [vp, vp, C.c_size_t, vp, vp]
     L.gl_commit_eval_ext.argtypes = [vp, vp, vp]
-    L.gl_commit_dev_leaves.argtypes = [vp]
-    L.gl_commit_dev_leaves.restype = vp
+    L.gl_commit_dev_lde.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.gl_commit_dev_lde.restype = vp
     L.gl_commit_dev_coeffs.argtypes = [vp]
     L.gl_commit_dev_coeffs.restype = vp
     L.gl_partial_products_and_zs.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64,
@@ -161,9 +160,6 @@ class Context:
 
     def set_ntt_group(self, columns):
         check(lib().gl_ctx_set_ntt_group(self.h, int(columns)), self.h)
-
-    def set_ntt_split(self, log_contiguous):
-        check(lib().gl_ctx_set_ntt_split(self.h, int(log_contiguous)), self.h)
 
     PHASES = {"intt": 0, "lde": 1, "leaf_hash": 2, "merkle_levels": 3}
 

@@ -1,265 +1,426 @@
-// gl_ntt.cuh -- batched Goldilocks NTT as a four-step (six-step without the explicit transposes)
-// decomposition n = R * C, R = 2^a (strided pass "A"), C = 2^b (contiguous pass "B").
+// gl_ntt.cuh -- batched Goldilocks NTT, multi-pass (n = 2^(a1 [+ a2] + b)), every pass a two-step radix-(<=32)
+// in-register transform with ONE shared-memory exchange.
 //
 // Replaces (reference, CPU): fft_classic / ifft_with_options      field/src/fft.rs:68-202
 //                            coset_fft_with_options, lde          field/src/polynomial/mod.rs:199-201,280-293
 //                            lde_values + transpose + bit-reverse plonky2/src/fri/oracle.rs:97-98,114-139
 //
+// Decomposition (four-/six-step without explicit transposes), for two passes n = R * C:
 //   X[k1 + R*k2] = sum_{j2<C} w_n^{j2*k1} w_C^{j2*k2} ( sum_{j1<R} x[j1*C + j2] w_R^{j1*k1} )
+// * column pass ("A", strided): a CTA owns T adjacent j2 (T*8-byte global segments) and all R = 2^LOG values of
+//   j1; writes Y[p][j2] * w_n^{k1*j2} with p = bitrev(k1) (the in-place DIF order).
+// * row pass ("B", contiguous): TPT threads own one row of C = 2^LOG contiguous elements and store either
+//     - bit-reversed   out[row_base + bitrev(k2)]  -- the LDE: with column-major leaves this IS the reference's
+//                       leaf order (transpose + reverse_index_bits, oracle.rs:97-98), written with 128-bit stores, or
+//     - natural order  out[k1 + R*k2] (NTT / iNTT API), gathered through shared memory so that a CTA writes
+//                       segments of adjacent k1 (optional index reversal for the inverse, fft.rs:80-90).
+//   Three passes (n > 2^20) run the column pass twice (the second time inside every row of the first).
+// Inside a pass, 2^LOG = E * TPT with E = 2^ceil(LOG/2) <= 32 values per thread:
+//   step 1: radix-E DIF over the high index bits in registers (lazy 3-word butterflies with shift twiddles,
+//           gl_lazy.cuh; w_32 = 2^6), one general multiply by  scale * base^t * w_{2^LOG}^{t * k}  per element,
+//   exchange through shared memory (padded pitch: conflict-free 64-bit accesses; a warp-local __syncwarp for rows),
+//   step 2: radix-TPT DIF over the low bits; element (q, j) is the output of bit-reversed position q*TPT + j.
+// Coset scaling s^j of the forward coset NTT (j = (t + TPT*q)*C + j2) costs ONE extra multiply per element:
+// (s^(C*TPT))^q are per-register constants, (s^C)^t is folded into the step table and s^j2 into the post table.
 //
-// Pass A: a CTA owns a tile of T adjacent j2 and all R values of j1 (global accesses are T*8-byte
-//         segments), runs T interleaved R-point DIF transforms in shared memory, multiplies by
-//         w_n^{j2*k1} and writes Y[p][j2] with p = bitrev_a(k1) (the in-place DIF order).
-// Pass B: a CTA owns T "lines" of C contiguous elements (rows p of one column, or the same row of
-//         T adjacent columns), runs T interleaved C-point DIF transforms and stores either
-//           - natural order  out[k1 + R*k2]            (NTT / iNTT API, optional index reversal), or
-//           - leaf-major     leaves[row0 + p*C + q][c] (LDE; q = bitrev_b(k2), i.e. exactly the
-//             bit-reversed row order the reference produces with transpose + reverse_index_bits).
-// In-tile transforms are radix-16 register butterflies whose internal twiddles are powers of two
-// (w_16 = 2^12) - shifts, no multiplies; only the inter-step twiddles are
-// general 64x64 multiplies, read from a shared-memory table staged by a TMA bulk copy.
-//
-// Every per-thread phase below is a plain function of (tid, nthreads) so that tests/emu can run
-// the same code on the CPU (threads as a loop, phases as barriers) to check indexing.
+// Every per-thread phase below is a plain function so that tests/emu can run the same code on the CPU
+// (threads as a loop, barriers between phases) to check indexing and the table formulas.
 #pragma once
-#include "gl_field.cuh"
+#include "gl_lazy.cuh"
 
 namespace gl {
 
-constexpr int NTT_MAX_LOG_TILE = 12;  // largest in-CTA transform
+constexpr int NTT_MAX_LOG_PASS = 10;  // largest single pass: 32 x 32
+constexpr int NTT_COL_MIN_LOG = 5;    // smallest strided pass the planner uses
 
-GL_HD constexpr int ntt_tile_T(int log) { return log >= 12 ? 4 : 8; }
-GL_HD constexpr int ntt_tile_TS(int log) { return ntt_tile_T(log) + 1; }  // odd stride: conflict-free columns
-GL_HD constexpr int ntt_tile_threads(int log) {
-    int n = ((1 << log) * ntt_tile_T(log)) / 16;
-    return n < 32 ? 32 : (n > 1024 ? 1024 : n);
-}
-// resident CTAs per SM the kernels are compiled for (register cap = 65536 / (threads * blocks))
-GL_HD constexpr int ntt_tile_min_blocks(int log) {
-    int b = 1024 / ntt_tile_threads(log);
-    return b < 1 ? 1 : (b > 8 ? 8 : b);
-}
-GL_HD constexpr size_t ntt_tile_smem_bytes(int log) {
-    // data tile + full-cycle twiddle table + mbarrier slot
-    return ((size_t)(1 << log) * ntt_tile_TS(log) + (size_t)(1 << log)) * 8 + 16;
-}
+GL_HD constexpr int ntt_r2(int log) { return log / 2; }
+GL_HD constexpr int ntt_r1(int log) { return log - log / 2; }
 
-// 2^M-point DIF DFT in registers, natural in, bit-reversed out, w_{2^M} = 2^(192 / 2^M).
-template <int M>
-GL_HD void dft_regs(uint64_t* r) {
-#pragma unroll
-    for (int l = 0; l < M; l++) {
-        const int half = 1 << (M - 1 - l);
-#pragma unroll
-        for (int blk = 0; blk < (1 << M); blk += 2 * half) {
-#pragma unroll
-            for (int j = 0; j < half; j++) {
-                uint64_t u = r[blk + j], v = r[blk + j + half];
-                r[blk + j] = add(u, v);
-                uint64_t d = sub(u, v);
-                r[blk + j + half] = mul_pow2(d, (uint32_t)((96 / half) * j));
-            }
-        }
-    }
-}
-
-// One radix-2^M DIF step over index bits [sbit-M+1 .. sbit] of T interleaved 2^LOG-point
-// transforms stored as s[i*TS + t]. wt = full-cycle table w_{2^LOG}^j, j < 2^LOG.
-template <int LOG, int M>
-GL_HD void radix_step(uint64_t* s, const uint64_t* wt, int sbit, int tid, int nthreads) {
-    constexpr int T = ntt_tile_T(LOG), TS = ntt_tile_TS(LOG);
-    const int sh = sbit - M + 1;
-    const int ngroups = (1 << (LOG - M)) * T;
-    for (int g = tid; g < ngroups; g += nthreads) {
-        const int t = g % T, gi = g / T;
-        const int low = gi & ((1 << sh) - 1), high = gi >> sh;
-        const int base = (high << (sbit + 1)) | low;
-        uint64_t r[1 << M];
-#pragma unroll
-        for (int q = 0; q < (1 << M); q++) r[q] = s[(base | (q << sh)) * TS + t];
-        dft_regs<M>(r);
-        if (sh > 0) {
-            // slot q holds frequency k = bitrev_M(q); twiddle w_{2^(sbit+1)}^{low*k}
-            const int step = low << (LOG - sbit - 1);
-#pragma unroll
-            for (int q = 1; q < (1 << M); q++) {
-                const int k = (int)bitrev32((uint32_t)q, M);
-                r[q] = mul(r[q], wt[(step * k) & ((1 << LOG) - 1)]);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < (1 << M); q++) s[(base | (q << sh)) * TS + t] = r[q];
-    }
-}
-
-// Number of radix steps and the M of step i for a 2^LOG transform: 4,4,...,rem.
-GL_HD constexpr int ntt_num_steps(int log) { return (log + 3) / 4; }
-
-// ---------------------------------------------------------------- pass descriptors
-struct PassA {
-    const uint64_t* in;    // column b at in + b*in_stride, natural order
-    uint64_t* out;         // column b at out + b*out_stride, layout [p][j2]
-    size_t in_stride, out_stride;
-    const uint64_t* twa;   // n entries: w_n^{bitrev_a(p)*j2} at [p*C + j2]
-    const uint64_t* u;     // optional coset scale (s^C)^{j1}, R entries (nullptr = none)
-    const uint64_t* v;     // optional coset scale s^{j2}, C entries
-    const uint64_t* wt;    // full-cycle table for 2^a
-    int log_c;             // b
-    int tiles_per_col;     // C / T
+template <int LOG>
+struct PassCfg {
+    static constexpr int R1 = ntt_r1(LOG), R2 = ntt_r2(LOG);
+    static constexpr int E = 1 << R1, TPT = 1 << R2, NSUB = E / TPT;  // NSUB = 1 or 2 sub-transforms per thread in step 2
+    // ---- row pass: TPT threads per row, rows packed into warps; LPC rows ("lines") per CTA
+    static constexpr int ROW_THREADS = (TPT * 8 < 32) ? 32 : TPT * 8;
+    static constexpr int LPC = ROW_THREADS / TPT;
+    // resident CTAs per SM the kernels are compiled for: 512 threads/SM (128 registers) when a thread holds 32 lazy
+    // values, 768 threads/SM (80 registers) below
+    static constexpr int ROW_MIN_BLOCKS = (E >= 32 ? 512 : 768) / ROW_THREADS;
+    static constexpr int ROW_PITCH = TPT + 1;                 // u64 words: odd => conflict-free exchange
+    static constexpr int ROW_S_WORDS = E * ROW_PITCH;         // exchange buffer per line
+    static constexpr int GATHER_PITCH = (1 << LOG) + 2;       // natural-order gather tile: line pitch = 2 (mod 16)
+    // ---- column pass: T adjacent columns-of-the-matrix per CTA
+    static constexpr int T = (256 / TPT) < 8 ? 8 : (256 / TPT);
+    static constexpr int COL_THREADS = T * TPT;
+    static constexpr int COL_MIN_BLOCKS = (E >= 32 ? 512 : 768) / COL_THREADS;
+    static constexpr int COL_QPITCH = TPT * T + 8;            // words per q-row: 8 (mod 16) => conflict-free when T = 8
+    static constexpr int COL_S_WORDS = E * COL_QPITCH;
 };
-
-template <int LOG>
-GL_HD void passA_load(const PassA& pa, uint64_t* s, int blk, int tid, int nthreads) {
-    constexpr int T = ntt_tile_T(LOG), TS = ntt_tile_TS(LOG);
-    const int col = blk / pa.tiles_per_col, tile = blk % pa.tiles_per_col;
-    const size_t C = (size_t)1 << pa.log_c;
-    const uint64_t* src = pa.in + (size_t)col * pa.in_stride + (size_t)tile * T;
-    for (int e = tid; e < (1 << LOG) * T; e += nthreads) {
-        const int j1 = e / T, tt = e % T;
-        uint64_t x = src[(size_t)j1 * C + tt];
-        if (pa.u) x = mul(x, pa.u[j1]);
-        s[j1 * TS + tt] = x;
-    }
+GL_HD constexpr size_t ntt_row_smem_bytes(int log, bool natural) {
+    const int r1 = ntt_r1(log), r2 = ntt_r2(log), E = 1 << r1, TPT = 1 << r2;
+    const int threads = (TPT * 8 < 32) ? 32 : TPT * 8, lpc = threads / TPT;
+    const size_t s = (size_t)lpc * E * (TPT + 1), g = natural ? (size_t)lpc * ((1 << log) + 2) : 0;
+    return (s > g ? s : g) * 8;
 }
-template <int LOG>
-GL_HD void passA_store(const PassA& pa, const uint64_t* s, int blk, int tid, int nthreads) {
-    constexpr int T = ntt_tile_T(LOG), TS = ntt_tile_TS(LOG);
-    const int col = blk / pa.tiles_per_col, tile = blk % pa.tiles_per_col;
-    const size_t C = (size_t)1 << pa.log_c;
-    uint64_t* dst = pa.out + (size_t)col * pa.out_stride + (size_t)tile * T;
-    const uint64_t* tw = pa.twa + (size_t)tile * T;
-    for (int e = tid; e < (1 << LOG) * T; e += nthreads) {
-        const int p = e / T, tt = e % T;
-        uint64_t y = mul(s[p * TS + tt], tw[(size_t)p * C + tt]);
-        if (pa.v) y = mul(y, pa.v[tile * T + tt]);
-        dst[(size_t)p * C + tt] = y;
-    }
+GL_HD constexpr size_t ntt_col_smem_bytes(int log) {
+    const int r1 = ntt_r1(log), r2 = ntt_r2(log), E = 1 << r1, TPT = 1 << r2;
+    const int T = (256 / TPT) < 8 ? 8 : (256 / TPT);
+    return (size_t)E * (TPT * T + 8) * 8;
 }
 
-enum PassBMode { PB_NATURAL = 0, PB_NATURAL_COLS = 1, PB_LEAVES = 2 };
-
-struct PassB {
-    const uint64_t* in;   // column b at in + b*in_stride, layout [p][j2] (p = row of C elements)
-    size_t in_stride;
-    uint64_t* out;
-    size_t out_stride;    // natural modes: column stride; leaves mode: leaf width W
-    const uint64_t* wt;   // full-cycle table for 2^b
-    const uint64_t* pre;  // single-pass only (log_r == 0): optional coset pre-scale s^j, n entries
-    int log_r;            // a (0 for single-pass)
-    int ncols;            // number of columns in this launch
-    int reverse;          // natural modes: write to (n - k) mod n   (ifft index reversal, fft.rs:80-90)
-    uint64_t scale;       // natural modes: multiply outputs (1 = none)  (n^-1 for the inverse)
-    size_t row0;          // leaves mode: first leaf row of this coset
-    int col0;             // leaves mode: first leaf column of this launch
-};
-
-// number of CTAs for a pass-B launch
-template <int LOG>
-GL_HD int passB_blocks(const PassB& pb, int mode) {
-    constexpr int T = ntt_tile_T(LOG);
-    const int R = 1 << pb.log_r;
-    if (mode == PB_NATURAL) return pb.ncols * (R / T);
-    const int ctiles = (pb.ncols + T - 1) / T;
-    return ctiles * R;  // PB_NATURAL_COLS has R == 1
+// ---------------------------------------------------------------- table entries
+// step table of a 2^LOG pass: tw[q*TPT + t] = scale * base^t * w_{2^LOG}^(t * bitrev_R1(q))
+GL_HD uint64_t table_step_entry(int log, uint32_t idx, uint64_t scale, uint64_t base) {
+    const int r1 = ntt_r1(log), r2 = ntt_r2(log);
+    const uint32_t t = idx & ((1u << r2) - 1), q = idx >> r2;
+    const uint64_t k = bitrev32(q, (uint32_t)r1);
+    uint64_t v = pow(root_of_unity((uint32_t)log), k * t);
+    if (base != 1) v = mul(v, pow(base, t));
+    if (scale != 1) v = mul(v, scale);
+    return v;
 }
-
-// line t of CTA blk -> (column, row p); returns false if the line is past the end
-template <int LOG, int MODE>
-GL_HD bool passB_line(const PassB& pb, int blk, int t, int& col, int& p, int& k1) {
-    constexpr int T = ntt_tile_T(LOG);
-    const int R = 1 << pb.log_r;
-    if (MODE == PB_NATURAL) {
-        const int per_col = R / T;
-        col = blk / per_col;
-        k1 = (blk % per_col) * T + t;
-        p = (int)bitrev32((uint32_t)k1, pb.log_r);
-        return true;
-    } else {
-        const int ctile = blk / R;
-        p = blk % R;
-        k1 = (int)bitrev32((uint32_t)p, pb.log_r);
-        col = ctile * T + t;
-        return col < pb.ncols;
-    }
-}
-
-template <int LOG, int MODE>
-GL_HD void passB_load(const PassB& pb, uint64_t* s, int blk, int tid, int nthreads) {
-    constexpr int T = ntt_tile_T(LOG), TS = ntt_tile_TS(LOG);
-    for (int e = tid; e < (1 << LOG) * T; e += nthreads) {
-        const int t = e >> LOG, i = e & ((1 << LOG) - 1);
-        int col, p, k1;
-        uint64_t x = 0;
-        if (passB_line<LOG, MODE>(pb, blk, t, col, p, k1))
-            x = pb.in[(size_t)col * pb.in_stride + ((size_t)p << LOG) + i];
-        if (pb.pre) x = mul(x, pb.pre[i]);
-        s[i * TS + t] = x;
-    }
-}
-
-template <int LOG, int MODE>
-GL_HD void passB_store(const PassB& pb, const uint64_t* s, int blk, int tid, int nthreads) {
-    constexpr int T = ntt_tile_T(LOG), TS = ntt_tile_TS(LOG);
-    const size_t n = (size_t)1 << (LOG + pb.log_r);
-    for (int e = tid; e < (1 << LOG) * T; e += nthreads) {
-        int t, q;
-        if (MODE == PB_NATURAL_COLS) {
-            // consecutive threads -> consecutive output index k2
-            t = e >> LOG;
-            q = (int)bitrev32((uint32_t)(e & ((1 << LOG) - 1)), LOG);
-        } else {
-            t = e % T;
-            q = e / T;
-        }
-        int col, p, k1;
-        if (!passB_line<LOG, MODE>(pb, blk, t, col, p, k1)) continue;
-        uint64_t y = s[q * TS + t];
-        if (MODE == PB_LEAVES) {
-            pb.out[(pb.row0 + ((size_t)p << LOG) + q) * pb.out_stride + pb.col0 + col] = canon(y);
-        } else {
-            const size_t k2 = bitrev32((uint32_t)q, LOG);
-            size_t k = (size_t)k1 + (k2 << pb.log_r);
-            if (pb.reverse) k = (n - k) & (n - 1);
-            if (pb.scale != 1) y = mul(y, pb.scale);
-            pb.out[(size_t)col * pb.out_stride + k] = canon(y);
-        }
-    }
-}
-
-// ---------------------------------------------------------------- all radix steps of a tile
-// (callers put a barrier between consecutive calls: step index `i`)
-template <int LOG>
-GL_HD void tile_step(uint64_t* s, const uint64_t* wt, int i, int tid, int nthreads) {
-    const int sbit = LOG - 1 - 4 * i;
-    if (i < LOG / 4) {
-        if constexpr (LOG >= 4) radix_step<LOG, 4>(s, wt, sbit, tid, nthreads);
-    } else {
-        constexpr int REM = LOG % 4;
-        if constexpr (REM > 0) radix_step<LOG, REM>(s, wt, sbit, tid, nthreads);
-    }
-}
-
-// ---------------------------------------------------------------- plan + table entries
-// n = 2^log_n = R*C with R = 2^a (pass A, absent when a == 0) and C = 2^b (pass B).
-GL_HD void ntt_split(int log_n, int& a, int& b, int force_b = 0) {
-    if (log_n <= NTT_MAX_LOG_TILE) {
-        a = 0;
-        b = log_n;
-    } else {
-        b = (log_n + 1) / 2;
-        // tuning override (gl_ctx_set_ntt_split): any b with 6 <= a, b <= 12
-        if (force_b >= 6 && force_b <= NTT_MAX_LOG_TILE && log_n - force_b >= 6 && log_n - force_b <= NTT_MAX_LOG_TILE)
-            b = force_b;
-        a = log_n - b;
-    }
-}
-// full-cycle in-tile table: w_{2^log}^j
-GL_HD uint64_t table_wt_entry(int log, uint32_t j) { return pow(root_of_unity((uint32_t)log), j); }
-// pass-A post-twiddle: w_n^{bitrev_a(p) * j2} at index p*C + j2
-GL_HD uint64_t table_twa_entry(int a, int b, size_t idx) {
+// post table of a column pass with R = 2^a rows over C = 2^b columns: twa[p*C + j2] = w_{R*C}^(bitrev_a(p) * j2) * base^j2
+GL_HD uint64_t table_post_entry(int a, int b, size_t idx, uint64_t base) {
     const size_t p = idx >> b, j2 = idx & (((size_t)1 << b) - 1);
     const uint64_t k1 = bitrev32((uint32_t)p, (uint32_t)a);
-    return pow(root_of_unity((uint32_t)(a + b)), k1 * j2);
+    uint64_t v = pow(root_of_unity((uint32_t)(a + b)), k1 * j2);
+    if (base != 1) v = mul(v, pow(base, j2));
+    return v;
+}
+
+// ---------------------------------------------------------------- shared step code
+// step 1 of a pass on one thread: x[q] (q < E) natural -> y[q] = DFT_E(x)[bitrev(q)] * tw[q*TPT + t], normalised u64.
+// uq: optional per-register pre-scale (coset), uq[0] unused. tw_full: multiply slot 0 too (scale/base non-trivial).
+template <int LOG>
+GL_HD void pass_step1(uint64_t* x, const uint64_t* tw, const uint64_t* uq, bool tw_full, int t) {
+    using Cf = PassCfg<LOG>;
+    L3 r[Cf::E];
+#pragma unroll
+    for (int q = 0; q < Cf::E; q++) {
+        uint64_t v = x[q];
+        if (uq && q) v = mul(v, uq[q]);
+        r[q] = l3_from(v);
+    }
+    dft_lazy<Cf::R1>(r);
+#pragma unroll
+    for (int q = 0; q < Cf::E; q++) {
+        uint64_t y = l3_norm(r[q]);
+        if (Cf::R2 > 0 && (q || tw_full)) y = mul(y, tw[q * Cf::TPT + t]);
+        if (Cf::R2 == 0 && tw_full) y = mul(y, tw[0]);  // 2-point pass: only the scale (t = 0)
+        x[q] = y;
+    }
+}
+// step 2 on one thread: z[j] (j < TPT) natural -> z[j] = DFT_TPT(z)[bitrev(j)], normalised u64 (not canonical)
+template <int LOG>
+GL_HD void pass_step2(uint64_t* z) {
+    using Cf = PassCfg<LOG>;
+    L3 r[Cf::TPT];
+#pragma unroll
+    for (int j = 0; j < Cf::TPT; j++) r[j] = l3_from(z[j]);
+    dft_lazy<Cf::R2>(r);
+#pragma unroll
+    for (int j = 0; j < Cf::TPT; j++) z[j] = l3_norm(r[j]);
+}
+
+// ---------------------------------------------------------------- column pass
+struct ColPass {
+    const uint64_t* in;    // unit (col, rb): in + col*in_stride + rb*(R*C); element (j1, j2) at [j1*C + j2]
+    uint64_t* out;         // same addressing with out_stride; element (p, j2) at [p*C + j2]  (may alias `in`)
+    size_t in_stride, out_stride;
+    const uint64_t* tw;    // step table, R entries
+    const uint64_t* twa;   // post table, R*C entries
+    int log_c;             // log2 C
+    int log_rb;            // log2 (row blocks per column): 0 except for the middle pass of a three-pass plan
+    int tw_full;
+    int has_uq;
+    uint64_t uq[32];
+};
+template <int LOG>
+GL_HD void col_unit(const ColPass& cp, int blk, size_t& in_off, size_t& out_off, int& tile) {
+    using Cf = PassCfg<LOG>;
+    const int tiles = (1 << cp.log_c) / Cf::T;
+    tile = blk % tiles;
+    const int unit = blk / tiles;
+    const size_t rb = (size_t)unit & (((size_t)1 << cp.log_rb) - 1), col = (size_t)unit >> cp.log_rb;
+    const size_t blk_words = (size_t)1 << (LOG + cp.log_c);
+    in_off = col * cp.in_stride + rb * blk_words;
+    out_off = col * cp.out_stride + rb * blk_words;
+}
+// phase 1a: global loads (tid < COL_THREADS); phase 1b: step 1 + write the exchange tile
+template <int LOG>
+GL_HD void col_load(const ColPass& cp, int blk, int tid, uint64_t* x) {
+    using Cf = PassCfg<LOG>;
+    const int tt = tid % Cf::T, t = tid / Cf::T;
+    size_t in_off, out_off;
+    int tile;
+    col_unit<LOG>(cp, blk, in_off, out_off, tile);
+    const size_t C = (size_t)1 << cp.log_c;
+    const uint64_t* src = cp.in + in_off + (size_t)tile * Cf::T + tt;
+#pragma unroll
+    for (int q = 0; q < Cf::E; q++) x[q] = src[(size_t)(t + Cf::TPT * q) * C];
+}
+template <int LOG>
+GL_HD void col_phase1(const ColPass& cp, uint64_t* S, int blk, int tid, uint64_t* x) {
+    using Cf = PassCfg<LOG>;
+    const int tt = tid % Cf::T, t = tid / Cf::T;
+    size_t in_off, out_off;
+    int tile;
+    col_unit<LOG>(cp, blk, in_off, out_off, tile);
+    const size_t C = (size_t)1 << cp.log_c;
+    pass_step1<LOG>(x, cp.tw, cp.has_uq ? cp.uq : nullptr, cp.tw_full != 0, t);
+    if (Cf::R2 == 0) {  // single step: x[q] is the output of position q
+        uint64_t* dst = cp.out + out_off + (size_t)tile * Cf::T + tt;
+        const uint64_t* twa = cp.twa + (size_t)tile * Cf::T + tt;
+#pragma unroll
+        for (int q = 0; q < Cf::E; q++) dst[(size_t)q * C] = mul(x[q], twa[(size_t)q * C]);
+        return;
+    }
+#pragma unroll
+    for (int q = 0; q < Cf::E; q++) S[q * Cf::COL_QPITCH + t * Cf::T + tt] = x[q];
+}
+// phase 2 (after a CTA barrier): step 2, post twiddle, store
+template <int LOG>
+GL_HD void col_phase2(const ColPass& cp, const uint64_t* S, int blk, int tid) {
+    using Cf = PassCfg<LOG>;
+    if (Cf::R2 == 0) return;
+    const int tt = tid % Cf::T, t = tid / Cf::T;
+    size_t in_off, out_off;
+    int tile;
+    col_unit<LOG>(cp, blk, in_off, out_off, tile);
+    const size_t C = (size_t)1 << cp.log_c;
+    uint64_t* dst = cp.out + out_off + (size_t)tile * Cf::T + tt;
+    const uint64_t* twa = cp.twa + (size_t)tile * Cf::T + tt;
+#pragma unroll
+    for (int m = 0; m < Cf::NSUB; m++) {
+        const int q = t + Cf::TPT * m;
+        uint64_t z[Cf::TPT];
+#pragma unroll
+        for (int j = 0; j < Cf::TPT; j++) z[j] = S[q * Cf::COL_QPITCH + j * Cf::T + tt];
+        pass_step2<LOG>(z);
+#pragma unroll
+        for (int j = 0; j < Cf::TPT; j++) {
+            const size_t p = (size_t)q * Cf::TPT + j;
+            dst[p * C] = mul(z[j], twa[p * C]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- row pass
+enum RowMode { RM_BITREV = 0, RM_NATURAL = 1 };
+struct RowPass {
+    const uint64_t* in;    // line (col, prow): in + col*in_stride + (prow << LOG)
+    uint64_t* out;
+    size_t in_stride, out_stride;
+    const uint64_t* tw;    // step table, 2^LOG entries
+    int log_r;             // log2 (rows per column) = log2(n) - LOG
+    int ncols;
+    int tw_full;
+    int has_uq;
+    int reverse;           // RM_NATURAL: write to (n - k) mod n   (ifft index reversal, fft.rs:80-90)
+    size_t row0;           // RM_BITREV: offset added to the output position (first row of this coset block)
+    uint64_t uq[32];
+};
+// line l of CTA blk -> (col, prow, kbase). RM_BITREV enumerates rows in storage order; RM_NATURAL enumerates them by
+// the natural low index kbase (adjacent lines of a CTA = adjacent output addresses), prow = bitrev(kbase).
+template <int LOG, int MODE>
+GL_HD bool row_line(const RowPass& rp, int blk, int l, size_t& col, size_t& prow, size_t& kbase) {
+    using Cf = PassCfg<LOG>;
+    const size_t L = (size_t)blk * Cf::LPC + l;
+    const size_t R = (size_t)1 << rp.log_r;
+    col = L >> rp.log_r;
+    const size_t low = L & (R - 1);
+    if (MODE == RM_BITREV) {
+        prow = low;
+        kbase = 0;
+    } else {
+        kbase = low;
+        prow = rp.log_r ? (size_t)bitrev32((uint32_t)low, (uint32_t)rp.log_r) : 0;
+    }
+    return col < (size_t)rp.ncols;
+}
+template <int LOG>
+GL_HD int row_blocks(const RowPass& rp) {
+    using Cf = PassCfg<LOG>;
+    const size_t lines = (size_t)rp.ncols << rp.log_r;
+    return (int)((lines + Cf::LPC - 1) / Cf::LPC);
+}
+// phase 1a: global loads; phase 1b: step 1, write this line's exchange buffer (lines of a warp are independent:
+// warp-level barrier). For LOG with R2 == 0 the outputs stay in x[] (returned) and phase 2 is skipped.
+template <int LOG, int MODE>
+GL_HD void row_load(const RowPass& rp, int blk, int tid, uint64_t* x) {
+    using Cf = PassCfg<LOG>;
+    const int l = tid / Cf::TPT, t = tid % Cf::TPT;
+    size_t col, prow, kbase;
+    const bool live = row_line<LOG, MODE>(rp, blk, l, col, prow, kbase);
+    const uint64_t* src = rp.in + col * rp.in_stride + (prow << LOG) + t;
+#pragma unroll
+    for (int q = 0; q < Cf::E; q++) x[q] = live ? src[Cf::TPT * q] : 0;
+}
+template <int LOG, int MODE>
+GL_HD void row_phase1(const RowPass& rp, uint64_t* S, int blk, int tid, uint64_t* x) {
+    using Cf = PassCfg<LOG>;
+    const int l = tid / Cf::TPT, t = tid % Cf::TPT;
+    pass_step1<LOG>(x, rp.tw, rp.has_uq ? rp.uq : nullptr, rp.tw_full != 0, t);
+    if (Cf::R2 == 0) return;
+    uint64_t* Sl = S + (size_t)l * Cf::ROW_S_WORDS;
+#pragma unroll
+    for (int q = 0; q < Cf::E; q++) Sl[q * Cf::ROW_PITCH + t] = x[q];
+}
+// natural index of the element at bit-reversed position pos = q*TPT + j
+template <int LOG>
+GL_HD uint32_t row_natural_index(int q, int j) {
+    using Cf = PassCfg<LOG>;
+    return bitrev32((uint32_t)q, Cf::R1) + (uint32_t)Cf::E * (Cf::R2 ? bitrev32((uint32_t)j, Cf::R2) : 0u);
+}
+// phase 2: step 2 and the output of RM_BITREV (canonical u64, pairs of adjacent positions), or the gather tile of
+// RM_NATURAL (G may alias S: the caller puts a CTA barrier between the reads of S and the writes of G).
+template <int LOG>
+GL_HD void row_phase2_load(const uint64_t* S, int tid, int m, uint64_t* z) {
+    using Cf = PassCfg<LOG>;
+    const int l = tid / Cf::TPT, t = tid % Cf::TPT;
+    const uint64_t* Sl = S + (size_t)l * Cf::ROW_S_WORDS;
+    const int q = t + Cf::TPT * m;
+#pragma unroll
+    for (int j = 0; j < Cf::TPT; j++) z[j] = Sl[q * Cf::ROW_PITCH + j];
+}
+template <int LOG>
+GL_HD void row_store_bitrev(const RowPass& rp, int blk, int tid, int m, const uint64_t* z) {
+    using Cf = PassCfg<LOG>;
+    const int l = tid / Cf::TPT, t = tid % Cf::TPT;
+    size_t col, prow, kbase;
+    if (!row_line<LOG, RM_BITREV>(rp, blk, l, col, prow, kbase)) return;
+    uint64_t* dst = rp.out + col * rp.out_stride + rp.row0 + (prow << LOG);
+    if constexpr (Cf::R2 == 0) {  // z = x[q]: position q, this thread holds the whole line
+#pragma unroll
+        for (int q = 0; q < Cf::E; q++) dst[q] = canon(z[q]);
+    } else {
+        const int q = t + Cf::TPT * m;
+        uint64_t* d = dst + (size_t)q * Cf::TPT;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+        for (int j = 0; j < Cf::TPT; j += 2) {
+            ulonglong2 v;
+            v.x = canon(z[j]);
+            v.y = canon(z[j + 1]);
+            *reinterpret_cast<ulonglong2*>(d + j) = v;  // 16-byte aligned: q*TPT + j even, rows 8*2^LOG bytes
+        }
+#else
+        for (int j = 0; j < Cf::TPT; j++) d[j] = canon(z[j]);
+#endif
+    }
+}
+template <int LOG>
+GL_HD void row_gather_write(uint64_t* G, int tid, int m, const uint64_t* z) {
+    using Cf = PassCfg<LOG>;
+    const int l = tid / Cf::TPT, t = tid % Cf::TPT;
+    uint64_t* Gl = G + (size_t)l * Cf::GATHER_PITCH;
+    if (Cf::R2 == 0) {
+#pragma unroll
+        for (int q = 0; q < Cf::E; q++) Gl[row_natural_index<LOG>(q, 0)] = canon(z[q]);
+        return;
+    }
+    const int q = t + Cf::TPT * m;
+#pragma unroll
+    for (int j = 0; j < Cf::TPT; j++) Gl[row_natural_index<LOG>(q, j)] = canon(z[j]);
+}
+// phase 3 (RM_NATURAL, after a CTA barrier): G[line][k2] -> out[col][kbase + R*k2] (or the reversed index)
+template <int LOG>
+GL_HD void row_store_natural(const RowPass& rp, const uint64_t* G, int blk, int tid, int nthreads) {
+    using Cf = PassCfg<LOG>;
+    const size_t R = (size_t)1 << rp.log_r, n = R << LOG;
+    for (int e = tid; e < Cf::LPC * (1 << LOG); e += nthreads) {
+        int l, k2;
+        if (rp.log_r) {  // adjacent lines = adjacent addresses: lines fastest
+            l = e % Cf::LPC;
+            k2 = e / Cf::LPC;
+        } else {         // single pass: a line is contiguous in k2
+            k2 = e & ((1 << LOG) - 1);
+            l = e >> LOG;
+        }
+        size_t col, prow, kbase;
+        if (!row_line<LOG, RM_NATURAL>(rp, blk, l, col, prow, kbase)) continue;
+        size_t k = kbase + ((size_t)k2 << rp.log_r);
+        if (rp.reverse) k = (n - k) & (n - 1);
+        rp.out[col * rp.out_stride + k] = G[(size_t)l * Cf::GATHER_PITCH + k2];
+    }
+}
+
+// ---------------------------------------------------------------- plan
+// n = 2^log_n as up to three passes: a1 (strided), a2 (strided inside the rows of the first), b (contiguous).
+struct NttPlan {
+    int a1, a2, b;
+};
+GL_HD NttPlan ntt_plan(int log_n) {
+    NttPlan p{0, 0, log_n};
+    if (log_n <= NTT_MAX_LOG_PASS) return p;
+    if (log_n <= 2 * NTT_MAX_LOG_PASS) {
+        p.b = (log_n + 1) / 2;
+        p.a1 = log_n - p.b;
+        return p;
+    }
+    p.b = (log_n + 2) / 3;
+    p.a2 = (log_n - p.b + 1) / 2;
+    p.a1 = log_n - p.b - p.a2;
+    return p;
+}
+
+
+// ---------------------------------------------------------------- job = the passes of one forward transform
+// Everything except device pointers: which tables each pass needs (TableReq) and the scalar parameters of the
+// pass descriptors. Shared by the CUDA host code (tables from the per-context cache) and tests/emu (tables computed
+// on the CPU), so the orchestration arithmetic -- coset bases, uq constants, scale placement -- is tested without a GPU.
+struct TableReq {
+    int a, b;              // step table: log = a (b unused); post table: (a, b)
+    uint64_t scale, base;
+};
+struct NttJob {
+    NttPlan pl;
+    ColPass c1, c2;        // c1 used iff pl.a1, c2 iff pl.a2
+    RowPass rp;
+    TableReq c1_step, c1_post, c2_step, c2_post, row_step;
+};
+// Forward transform of size 2^log_n on the coset shift*<w_n> (shift = 1: none), outputs multiplied by `scale`.
+inline void ntt_make_job(int log_n, NttPlan pl, uint64_t scale, uint64_t shift, NttJob& job) {
+    job = NttJob{};
+    job.pl = pl;
+    const bool coset = canon(shift) != 1;
+    const uint64_t one = 1;
+    RowPass& rp = job.rp;
+    rp.log_r = log_n - pl.b;
+    auto fill_uq = [](uint64_t* uq, int log_pass, uint64_t sq) {
+        const int E = 1 << ntt_r1(log_pass);
+        uint64_t acc = 1;
+        for (int q = 0; q < E; q++, acc = mul(acc, sq)) uq[q] = canon(acc);
+    };
+    if (pl.a1 == 0) {  // single pass: j = t + TPT*q
+        job.row_step = TableReq{pl.b, 0, scale, coset ? shift : one};
+        rp.tw_full = (canon(scale) != 1 || coset) ? 1 : 0;
+        rp.has_uq = coset ? 1 : 0;
+        if (coset) fill_uq(rp.uq, pl.b, pow(shift, (uint64_t)1 << ntt_r2(pl.b)));
+        return;
+    }
+    const int c1_log = log_n - pl.a1;  // j = j1*C1 + j', j1 = t + TPT*q
+    ColPass& c1 = job.c1;
+    c1.log_c = c1_log;
+    c1.log_rb = 0;
+    job.c1_step = TableReq{pl.a1, 0, one, coset ? pow(shift, (uint64_t)1 << c1_log) : one};
+    job.c1_post = TableReq{pl.a1, c1_log, one, coset ? shift : one};
+    c1.tw_full = coset ? 1 : 0;
+    c1.has_uq = coset ? 1 : 0;
+    if (coset) fill_uq(c1.uq, pl.a1, pow(shift, ((uint64_t)1 << ntt_r2(pl.a1)) << c1_log));
+    if (pl.a2) {
+        ColPass& c2 = job.c2;
+        c2.log_c = pl.b;
+        c2.log_rb = pl.a1;
+        job.c2_step = TableReq{pl.a2, 0, one, one};
+        job.c2_post = TableReq{pl.a2, pl.b, one, one};
+    }
+    job.row_step = TableReq{pl.b, 0, scale, one};
+    rp.tw_full = canon(scale) != 1 ? 1 : 0;
+}
+template <int LOG>
+GL_HD int col_blocks(const ColPass& cp, size_t ncols) {
+    return (int)((ncols << cp.log_rb) * (((size_t)1 << cp.log_c) / PassCfg<LOG>::T));
 }
 
 }  // namespace gl

@@ -37,9 +37,9 @@ struct gl_ctx {
     bool own_stream = false;
     u64 launches = 0;
     std::string err;
-    u64* wt[NTT_MAX_LOG_TILE + 1] = {nullptr};  // full-cycle in-tile tables, wt[log][j] = w_{2^log}^j
-    std::map<int, u64*> twa;                    // pass-A twiddles by log_n
-    std::map<std::tuple<int, int, u64>, u64*> coset_tabs;  // LDE coset scale tables by (log_n, rate_bits, shift)
+    std::map<std::tuple<int, u64, u64>, u64*> step_tabs;  // in-pass step tables by (log, scale, base)
+    std::map<std::tuple<int, int, u64>, u64*> post_tabs;  // column-pass post tables by (a, b, base)
+    size_t table_bytes = 0;
     std::map<int, u64*> fold_tabs;              // FRI fold tables (w_N^-1 powers, hi | lo) by log N
     cudaStream_t copy_stream = nullptr;         // H2D of column chunks, overlapped with the NTTs of earlier chunks
     std::set<const void*> smem_attr_done;       // kernels whose dynamic-smem attributes are set on THIS device
@@ -50,7 +50,6 @@ struct gl_ctx {
     u64* dstage = nullptr;                      // device staging for openings
     size_t dstage_words = 0;
     uint32_t ntt_group = 0;                     // 0 = auto
-    int ntt_force_b = 0;                        // 0 = balanced split; else log2 of the contiguous pass size
     int sm_count = 0;                           // queried once for ctx->device in gl_ctx_create
     int coop_ok = 0;                            // cooperative launch supported on this device
     int coop_blocks_per_sm = 0;                 // resident CTAs/SM of k_merkle_upper on this device
@@ -207,395 +206,19 @@ __device__ __forceinline__ void tma_table_wait(u64* mbar) {
 }
 
 // =====================================================================================
-// NTT kernels
+// NTT kernels + orchestration
 // =====================================================================================
-template <int LOG>
-__global__ void __launch_bounds__(ntt_tile_threads(LOG), ntt_tile_min_blocks(LOG)) k_passA(PassA pa) {
-    extern __shared__ __align__(16) u64 smem[];
-    u64* wt_s = smem;
-    u64* s = smem + (1 << LOG);
-    u64* mbar = s + (size_t)(1 << LOG) * ntt_tile_TS(LOG);
-    tma_table_issue(wt_s, pa.wt, (uint32_t)((1 << LOG) * 8), mbar);
-    passA_load<LOG>(pa, s, blockIdx.x, threadIdx.x, blockDim.x);
-    __syncthreads();
-    tma_table_wait(mbar);
-#pragma unroll 1
-    for (int i = 0; i < ntt_num_steps(LOG); i++) {
-        tile_step<LOG>(s, wt_s, i, threadIdx.x, blockDim.x);
-        __syncthreads();
-    }
-    passA_store<LOG>(pa, s, blockIdx.x, threadIdx.x, blockDim.x);
-}
-
-template <int LOG, int MODE>
-__global__ void __launch_bounds__(ntt_tile_threads(LOG), ntt_tile_min_blocks(LOG)) k_passB(PassB pb) {
-    extern __shared__ __align__(16) u64 smem[];
-    u64* wt_s = smem;
-    u64* s = smem + (1 << LOG);
-    u64* mbar = s + (size_t)(1 << LOG) * ntt_tile_TS(LOG);
-    tma_table_issue(wt_s, pb.wt, (uint32_t)((1 << LOG) * 8), mbar);
-    passB_load<LOG, MODE>(pb, s, blockIdx.x, threadIdx.x, blockDim.x);
-    __syncthreads();
-    tma_table_wait(mbar);
-#pragma unroll 1
-    for (int i = 0; i < ntt_num_steps(LOG); i++) {
-        tile_step<LOG>(s, wt_s, i, threadIdx.x, blockDim.x);
-        __syncthreads();
-    }
-    passB_store<LOG, MODE>(pb, s, blockIdx.x, threadIdx.x, blockDim.x);
-}
-
-__global__ void k_fill_wt(int log, u64* out) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < (1u << log)) out[j] = table_wt_entry(log, j);
-}
-__global__ void k_fill_twa(int a, int b, u64* out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ((size_t)1 << (a + b))) out[i] = table_twa_entry(a, b, i);
-}
-// out[t*count + i] = bases[t]^i  for t < ntab
-__global__ void k_fill_pows(const u64* bases, int ntab, size_t count, u64* out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count * ntab) return;
-    size_t t = i / count, e = i % count;
-    out[i] = gl::pow(bases[t], e);
-}
-// data[b*stride + k] *= hi[k >> lowbits] * lo[k & mask]
-__global__ void k_mul_pows(u64* data, size_t stride, size_t n, const u64* hi, const u64* lo, int lowbits) {
-    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    u64* col = data + (size_t)blockIdx.y * stride;
-    u64 f = mul(hi[k >> lowbits], lo[k & (((size_t)1 << lowbits) - 1)]);
-    col[k] = canon(mul(col[k], f));
-}
-
-template <int LOG>
-static int launch_passA(gl_ctx* ctx, const PassA& pa, int nblocks) {
-    const size_t smem = ntt_tile_smem_bytes(LOG);
-    const void* fn = (const void*)k_passA<LOG>;
-    if (!ctx->smem_attr_done.count(fn)) {  // function attributes are per device: track them per context
-        CK(ctx, cudaFuncSetAttribute(k_passA<LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(ctx, cudaFuncSetAttribute(k_passA<LOG>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared));
-        ctx->smem_attr_done.insert(fn);
-    }
-    k_passA<LOG><<<nblocks, ntt_tile_threads(LOG), smem, ctx->stream>>>(pa);
-    CKL(ctx);
-    return GL_OK;
-}
-template <int LOG, int MODE>
-static int launch_passB(gl_ctx* ctx, const PassB& pb) {
-    const size_t smem = ntt_tile_smem_bytes(LOG);
-    const void* fn = (const void*)k_passB<LOG, MODE>;
-    if (!ctx->smem_attr_done.count(fn)) {
-        CK(ctx, cudaFuncSetAttribute(k_passB<LOG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(ctx, cudaFuncSetAttribute(k_passB<LOG, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared));
-        ctx->smem_attr_done.insert(fn);
-    }
-    const int nblocks = passB_blocks<LOG>(pb, MODE);
-    k_passB<LOG, MODE><<<nblocks, ntt_tile_threads(LOG), smem, ctx->stream>>>(pb);
-    CKL(ctx);
-    return GL_OK;
-}
-#define LOG_SWITCH(LOGV, LO, EXPR)                                                 \
-    switch (LOGV) {                                                                \
-        case 1: { constexpr int L = 1; EXPR; } break;                              \
-        case 2: { constexpr int L = 2; EXPR; } break;                              \
-        case 3: { constexpr int L = 3; EXPR; } break;                              \
-        case 4: { constexpr int L = 4; EXPR; } break;                              \
-        case 5: { constexpr int L = 5; EXPR; } break;                              \
-        case 6: { constexpr int L = 6; EXPR; } break;                              \
-        case 7: { constexpr int L = 7; EXPR; } break;                              \
-        case 8: { constexpr int L = 8; EXPR; } break;                              \
-        case 9: { constexpr int L = 9; EXPR; } break;                              \
-        case 10: { constexpr int L = 10; EXPR; } break;                            \
-        case 11: { constexpr int L = 11; EXPR; } break;                            \
-        case 12: { constexpr int L = 12; EXPR; } break;                            \
-        default: return set_err(ctx, GL_ERR_UNSUPPORTED, "tile log %d", (int)(LOGV)); \
-    }
-
-static int dispatch_passA(gl_ctx* ctx, int a, const PassA& pa, int nblocks) {
-    if (a < 6) return set_err(ctx, GL_ERR_UNSUPPORTED, "pass A log %d", a);
-    switch (a) {
-        case 6: return launch_passA<6>(ctx, pa, nblocks);
-        case 7: return launch_passA<7>(ctx, pa, nblocks);
-        case 8: return launch_passA<8>(ctx, pa, nblocks);
-        case 9: return launch_passA<9>(ctx, pa, nblocks);
-        case 10: return launch_passA<10>(ctx, pa, nblocks);
-        case 11: return launch_passA<11>(ctx, pa, nblocks);
-        case 12: return launch_passA<12>(ctx, pa, nblocks);
-    }
-    return set_err(ctx, GL_ERR_UNSUPPORTED, "pass A log %d", a);
-}
-static int dispatch_passB(gl_ctx* ctx, int b, int mode, const PassB& pb) {
-    if (mode == PB_NATURAL) {
-        LOG_SWITCH(b, 1, return (launch_passB<L, PB_NATURAL>(ctx, pb)));
-    } else if (mode == PB_NATURAL_COLS) {
-        LOG_SWITCH(b, 1, return (launch_passB<L, PB_NATURAL_COLS>(ctx, pb)));
-    } else {
-        LOG_SWITCH(b, 1, return (launch_passB<L, PB_LEAVES>(ctx, pb)));
-    }
-    return GL_OK;
-}
-
-static int get_wt(gl_ctx* ctx, int log, const u64** out) {
-    if (log < 1 || log > NTT_MAX_LOG_TILE) return set_err(ctx, GL_ERR_UNSUPPORTED, "wt log %d", log);
-    if (!ctx->wt[log]) {
-        CK(ctx, cudaMalloc((void**)&ctx->wt[log], ((size_t)8 << log) < 16 ? 16 : ((size_t)8 << log)));
-        k_fill_wt<<<((1 << log) + 255) / 256, 256, 0, ctx->stream>>>(log, ctx->wt[log]);
-        CKL(ctx);
-    }
-    *out = ctx->wt[log];
-    return GL_OK;
-}
-static int get_twa(gl_ctx* ctx, int log_n, const u64** out) {
-    auto it = ctx->twa.find(log_n);
-    if (it == ctx->twa.end()) {
-        int a, b;
-        ntt_split(log_n, a, b, ctx->ntt_force_b);
-        u64* p;
-        CK(ctx, cudaMalloc((void**)&p, (size_t)8 << log_n));
-        size_t n = (size_t)1 << log_n;
-        k_fill_twa<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a, b, p);
-        CKL(ctx);
-        ctx->twa[log_n] = p;
-        *out = p;
-        return GL_OK;
-    }
-    *out = it->second;
-    return GL_OK;
-}
-// Columns per two-pass group (scratch = group * n * 8 bytes, multiple of 8 columns). Measured on B200
-// (tools/ntt_sweep.py): the passes are integer-issue bound, so keeping the intermediate L2-resident buys nothing,
-// while larger launches amortise wave quantisation (1024-CTA launches fill 3.46 waves of 296 resident CTAs):
-// 64 x 2^20 NTT 1.65 ms at 8 columns/group -> 1.46 ms at 64. Default: as many columns as fit 1 GiB of scratch.
-static uint32_t group_cols(const gl_ctx* ctx, int log_n, uint32_t ncols) {
-    uint32_t g = ctx->ntt_group;
-    if (g == 0) {
-        size_t col_bytes = (size_t)8 << log_n;
-        size_t target = (size_t)1 << 30;
-        g = (uint32_t)(target / col_bytes);
-        if (g < 8) g = 8;
-    }
-    g = (g + 7) & ~7u;
-    if (g > ((ncols + 7) & ~7u)) g = (ncols + 7) & ~7u;
-    return g;
-}
-
-// Upload `bases` (host) and build ntab tables of `count` powers each on the device.
-static int build_pow_tables(gl_ctx* ctx, const std::vector<u64>& bases, size_t count, u64** out) {
-    const int ntab = (int)bases.size();
-    u64* dbases;
-    TRY(dmalloc(ctx, &dbases, ntab));
-    TRY(ensure_pinned(ctx, ntab));
-    // pinned staging is reused: make sure earlier async copies from it are done
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
-    memcpy(ctx->pinned, bases.data(), ntab * 8);
-    TRY(h2d(ctx, dbases, ctx->pinned, ntab));
-    TRY(dmalloc(ctx, out, count * ntab));
-    size_t total = count * ntab;
-    k_fill_pows<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(dbases, ntab, count, *out);
-    CKL(ctx);
-    CK(ctx, cudaStreamSynchronize(ctx->stream));  // pinned buffer free for reuse
-    dfree(ctx, dbases);
-    return GL_OK;
-}
-
-// Natural-order NTT of `ncols` device columns (in -> out, may alias), optional forward coset pre-scale.
-static int ntt_natural(gl_ctx* ctx, const u64* in, size_t in_stride, u64* out, size_t out_stride, int log_n,
-                       uint32_t ncols, bool inverse, u64 shift) {
-    if (ncols == 0) return GL_OK;
-    const size_t n = (size_t)1 << log_n;
-    if (log_n == 0) {
-        if (in != out)
-            for (uint32_t c = 0; c < ncols; c++)
-                CK(ctx, cudaMemcpyAsync(out + c * out_stride, in + c * in_stride, 8, cudaMemcpyDeviceToDevice,
-                                        ctx->stream));
-        // canonicalise via a multiply by one
-        u64 one = 1;
-        u64* tabs;
-        TRY(build_pow_tables(ctx, std::vector<u64>{one, one}, 1, &tabs));
-        k_mul_pows<<<dim3(1, ncols), 32, 0, ctx->stream>>>(out, out_stride, 1, tabs, tabs + 1, 0);
-        CKL(ctx);
-        dfree(ctx, tabs);
-        return GL_OK;
-    }
-    if (log_n > 2 * NTT_MAX_LOG_TILE) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %d > 24", log_n);
-    int a, b;
-    ntt_split(log_n, a, b, ctx->ntt_force_b);
-    const u64 *wta = nullptr, *wtb = nullptr, *twa = nullptr;
-    TRY(get_wt(ctx, b, &wtb));
-    const bool coset = (!inverse) && (canon(shift) != 1);
-    u64* ctab = nullptr;  // [u (R entries) | v (C entries)] for the forward coset
-    if (a > 0) {
-        TRY(get_wt(ctx, a, &wta));
-        TRY(get_twa(ctx, log_n, &twa));
-    }
-    const size_t R = (size_t)1 << a, C = (size_t)1 << b;
-    if (coset) {
-        size_t cnt = R > C ? R : C;
-        std::vector<u64> bases = {gl::pow(shift, C), shift};
-        TRY(build_pow_tables(ctx, bases, cnt, &ctab));  // ctab[0..cnt) = (s^C)^i ; ctab[cnt..) = s^i
-        // single-pass: v must have n = C entries (cnt == C)
-        (void)cnt;
-    }
-    const size_t cnt = R > C ? R : C;
-    PassB pb{};
-    pb.wt = wtb;
-    pb.log_r = a;
-    pb.reverse = inverse ? 1 : 0;
-    pb.scale = inverse ? inverse_2exp((uint32_t)log_n) : 1;
-    if (a == 0) {
-        pb.in = in;
-        pb.in_stride = in_stride;
-        pb.out = out;
-        pb.out_stride = out_stride;
-        pb.ncols = (int)ncols;
-        pb.pre = coset ? ctab + cnt : nullptr;
-        TRY(dispatch_passB(ctx, b, PB_NATURAL_COLS, pb));
-    } else {
-        const uint32_t G = group_cols(ctx, log_n, ncols);
-        TRY(ensure_scratch(ctx, (size_t)G * n));
-        for (uint32_t g0 = 0; g0 < ncols; g0 += G) {
-            const uint32_t gc = (ncols - g0 < G) ? ncols - g0 : G;
-            PassA pa{};
-            pa.in = in + (size_t)g0 * in_stride;
-            pa.in_stride = in_stride;
-            pa.out = ctx->scratch;
-            pa.out_stride = n;
-            pa.twa = twa;
-            pa.wt = wta;
-            pa.log_c = b;
-            pa.tiles_per_col = (int)(C / ntt_tile_T(a));
-            pa.u = coset ? ctab : nullptr;
-            pa.v = coset ? ctab + cnt : nullptr;
-            TRY(dispatch_passA(ctx, a, pa, (int)gc * pa.tiles_per_col));
-            pb.in = ctx->scratch;
-            pb.in_stride = n;
-            pb.out = out + (size_t)g0 * out_stride;
-            pb.out_stride = out_stride;
-            pb.ncols = (int)gc;
-            TRY(dispatch_passB(ctx, b, PB_NATURAL, pb));
-        }
-    }
-    if (ctab) dfree(ctx, ctab);
-    if (inverse && canon(shift) != 1) {
-        // coset_ifft: coefficients *= shift^-k   (polynomial/mod.rs:63-73)
-        const int lowbits = log_n > 12 ? 12 : log_n;
-        const size_t lo_cnt = (size_t)1 << lowbits, hi_cnt = (size_t)1 << (log_n - lowbits);
-        const u64 sinv = gl::inv(shift);
-        const size_t tcnt = lo_cnt > hi_cnt ? lo_cnt : hi_cnt;
-        u64* tabs;
-        TRY(build_pow_tables(ctx, std::vector<u64>{gl::pow(sinv, lo_cnt), sinv}, tcnt, &tabs));
-        k_mul_pows<<<dim3((unsigned)((n + 255) / 256), ncols), 256, 0, ctx->stream>>>(out, out_stride, n, tabs,
-                                                                                     tabs + tcnt, lowbits);
-        CKL(ctx);
-        dfree(ctx, tabs);
-    }
-    return GL_OK;
-}
-
-// Coset LDE of device coefficient columns into leaf-major rows:
-// leaves[(c*n + j)*W + col0 + col] = P_col( g * w_N^{bitrev_r(c)} * w_n^{bitrev(j)} ), base shift g.
-static int lde_leaves(gl_ctx* ctx, const u64* coeffs, size_t coeff_stride, uint32_t ncols, int log_n, int rate_bits,
-                      u64 base_shift, u64* leaves, size_t W, int col0) {
-    if (ncols == 0) return GL_OK;
-    if (log_n > 2 * NTT_MAX_LOG_TILE) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %d > 24", log_n);
-    if (log_n < 1) return set_err(ctx, GL_ERR_BAD_SHAPE, "lde_leaves needs n >= 2");
-    const size_t n = (size_t)1 << log_n;
-    const int ncos = 1 << rate_bits;
-    int a = 0, b = log_n;
-    ntt_split(log_n, a, b, ctx->ntt_force_b);
-    const size_t R = (size_t)1 << a, C = (size_t)1 << b;
-    const size_t cnt = R > C ? R : C;
-    // per-coset scale tables: [c][0] = (s_c^C)^i, [c][1] = s_c^i  (cached per context)
-    u64* ctab;
-    {
-        auto key = std::make_tuple(log_n, rate_bits, canon(base_shift));
-        auto it = ctx->coset_tabs.find(key);
-        if (it == ctx->coset_tabs.end()) {
-            std::vector<u64> bases;
-            const u64 wN = root_of_unity((uint32_t)(log_n + rate_bits));
-            for (int c = 0; c < ncos; c++) {
-                u64 s = mul(base_shift, gl::pow(wN, bitrev32((uint32_t)c, (uint32_t)rate_bits)));
-                bases.push_back(gl::pow(s, C));
-                bases.push_back(s);
-            }
-            TRY(build_pow_tables(ctx, bases, cnt, &ctab));
-            if (ctx->coset_tabs.size() > 64) {  // bound the cache
-                for (auto& kv : ctx->coset_tabs) dfree(ctx, kv.second);
-                ctx->coset_tabs.clear();
-            }
-            ctx->coset_tabs[key] = ctab;
-        } else {
-            ctab = it->second;
-        }
-    }
-    const u64 *wta = nullptr, *wtb = nullptr, *twa = nullptr;
-    if (b > 0) TRY(get_wt(ctx, b, &wtb));
-    if (a > 0) {
-        TRY(get_wt(ctx, a, &wta));
-        TRY(get_twa(ctx, log_n, &twa));
-    }
-    const uint32_t G = a > 0 ? group_cols(ctx, log_n, ncols) : ncols;
-    if (a > 0) TRY(ensure_scratch(ctx, (size_t)G * n));
-    for (uint32_t g0 = 0; g0 < ncols; g0 += G) {
-        const uint32_t gc = (ncols - g0 < G) ? ncols - g0 : G;
-        for (int c = 0; c < ncos; c++) {
-            const u64* u = ctab + (size_t)(2 * c) * cnt;
-            const u64* v = ctab + (size_t)(2 * c + 1) * cnt;
-            PassB pb{};
-            pb.wt = wtb;
-            pb.log_r = a;
-            pb.scale = 1;
-            pb.out = leaves;
-            pb.out_stride = W;
-            pb.row0 = (size_t)c * n;
-            pb.col0 = col0 + (int)g0;
-            pb.ncols = (int)gc;
-            if (a == 0) {
-                pb.in = coeffs + (size_t)g0 * coeff_stride;
-                pb.in_stride = coeff_stride;
-                pb.pre = v;
-            } else {
-                PassA pa{};
-                pa.in = coeffs + (size_t)g0 * coeff_stride;
-                pa.in_stride = coeff_stride;
-                pa.out = ctx->scratch;
-                pa.out_stride = n;
-                pa.twa = twa;
-                pa.wt = wta;
-                pa.log_c = b;
-                pa.tiles_per_col = (int)(C / ntt_tile_T(a));
-                pa.u = u;
-                pa.v = v;
-                TRY(dispatch_passA(ctx, a, pa, (int)gc * pa.tiles_per_col));
-                pb.in = ctx->scratch;
-                pb.in_stride = n;
-            }
-            TRY(dispatch_passB(ctx, b, PB_LEAVES, pb));
-        }
-    }
-    return GL_OK;
-}
-
-// degenerate n = 1 LDE: leaves[c][col] = coeff[col]
-__global__ void k_lde_const(const u64* coeffs, size_t stride, uint32_t ncols, int ncos, u64* leaves, size_t W, int col0) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ncols * (uint32_t)ncos) return;
-    uint32_t col = i % ncols, c = i / ncols;
-    leaves[(size_t)c * W + col0 + col] = canon(coeffs[(size_t)col * stride]);
-}
+#include "gl_ntt_host.cuh"
 
 // =====================================================================================
 // Poseidon / Merkle kernels
 // =====================================================================================
 struct TreeView {
-    const u64* leaves;  // N x W row-major
+    const u64* leaves;  // element k of leaf j at leaves[j*ls + k*es]: row-major (ls = W, es = 1) for MerkleTree::new
+                        // and the FRI trees, column-major (ls = 1, es = column stride) for PolynomialBatch LDEs
     u64* digests;       // 4 * 2 * (N - C)
     u64* cap;           // 4 * C
-    size_t N;
+    size_t N, ls, es;
     uint32_t W, log_n, cap_height;
 };
 
@@ -611,7 +234,7 @@ __global__ void __launch_bounds__(HASH_CTA, HASH_MINB) k_leaf_hash(TreeView t) {
     const bool live = j < t.N;
     if (!live) j = t.N - 1;  // keep the whole CTA in the per-round barriers; the result is discarded
     u64 h[4];
-    hash_or_noop_strided<true, true>(t.leaves + j * t.W, 1, t.W, h);
+    hash_or_noop_strided<true, true>(t.leaves + j * t.ls, t.es, t.W, h);
     if (!live) return;
     u64* dst;
     const uint32_t sub_log = t.log_n - t.cap_height;  // log2(leaves per cap subtree)
@@ -720,7 +343,7 @@ __global__ void k_tree_open(TreeView t, const u64* indices, u64* out_leaves, u64
     const size_t idx = indices[blockIdx.x];
     const uint32_t num_layers = t.log_n - t.cap_height;
     for (uint32_t k = threadIdx.x; k < t.W; k += blockDim.x)
-        out_leaves[(size_t)blockIdx.x * t.W + k] = t.leaves[idx * t.W + k];
+        out_leaves[(size_t)blockIdx.x * t.W + k] = t.leaves[idx * t.ls + (size_t)k * t.es];
     const size_t L = (size_t)1 << num_layers;
     const size_t tree_index = idx >> num_layers;
     const u64* sub = t.digests + 4 * (tree_index * 2 * (L - 1));
@@ -738,8 +361,9 @@ struct Tree {
     u64* digests = nullptr;
     u64* cap = nullptr;
     size_t N = 0;
+    size_t ls = 0, es = 1;  // leaf / element strides (ls == 0: row-major, ls = W)
     uint32_t W = 0, log_n = 0, cap_height = 0;
-    TreeView view() const { return TreeView{leaves, digests, cap, N, W, log_n, cap_height}; }
+    TreeView view() const { return TreeView{leaves, digests, cap, N, ls ? ls : (size_t)W, es, W, log_n, cap_height}; }
     size_t digest_words() const { return 8 * (N - ((size_t)1 << cap_height)); }
     size_t cap_words() const { return (size_t)4 << cap_height; }
 };
@@ -830,14 +454,32 @@ struct gl_commit {
     Tree tree;
 };
 
-// leaves[j][B + s] = salt[s][bitrev(j)]  (salt columns are LDE columns in natural order, oracle.rs:133-137)
-__global__ void k_salt(const u64* salt, size_t N, uint32_t log_N, size_t row0, size_t rows, u64* leaves, size_t W,
+// lde[B + s][j] = salt[s][bitrev(j)]  (salt columns are LDE columns in natural order, oracle.rs:133-137)
+__global__ void k_salt(const u64* salt, size_t N, uint32_t log_N, size_t row0, size_t rows, u64* lde, size_t lde_stride,
                        uint32_t B) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= rows) return;
     size_t i = (size_t)(__brevll(row0 + j) >> (64 - log_N));
     if (log_N == 0) i = 0;
-    for (int s = 0; s < GL_SALT_SIZE; s++) leaves[j * W + B + s] = canon(salt[(size_t)s * N + i]);
+    for (int s = 0; s < GL_SALT_SIZE; s++) lde[(size_t)(B + s) * lde_stride + j] = canon(salt[(size_t)s * N + i]);
+}
+// row-major view of a block of LDE rows (MerkleTree.leaves as the reference stores them): out[r*W + k] = lde[k][row0 + r],
+// through a 32 x 32 shared-memory tile so that both sides are coalesced
+__global__ void k_rows_from_columns(const u64* lde, size_t lde_stride, size_t row0, size_t rows, uint32_t W, u64* out) {
+    __shared__ u64 tile[32][33];
+    const size_t rb = (size_t)blockIdx.x * 32;
+    const uint32_t kb = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const size_t r = rb + threadIdx.x;
+        const uint32_t k = kb + i;
+        if (r < rows && k < W) tile[i][threadIdx.x] = lde[(size_t)k * lde_stride + row0 + r];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const size_t r = rb + i;
+        const uint32_t k = kb + threadIdx.x;
+        if (r < rows && k < W) out[r * W + k] = tile[threadIdx.x][i];
+    }
 }
 // Restriction of a degree-<n polynomial to a coset of size M < n (x^M = sM on it):
 // a'[k0] = sum_{k1 < n/M} a[k0 + M*k1] * sM^k1     ("fold coefficients mod X^M - s^M")
@@ -871,6 +513,8 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
     t.W = c->W;
     t.cap_height = cap_height - sl;
     t.own_leaves = true;
+    t.ls = 1;       // column-major LDE: column k at leaves + k*Nloc, leaf order inside
+    t.es = Nloc;
     TRY(dmalloc(ctx, &t.leaves, Nloc * (size_t)c->W));
 
     // Column chunks flow through  H2D copy -> iNTT ("IFFT", oracle.rs:65-69) -> leaf-major coset LDE
@@ -934,13 +578,7 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
             PhaseScope ps(ctx, GL_PHASE_LDE);
             if (sl <= c->rate_bits) {
                 const uint32_t rloc = c->rate_bits - sl;
-                if (c->degree_log == 0) {
-                    const int ncos = 1 << rloc;
-                    k_lde_const<<<(gc * ncos + 127) / 128, 128, 0, ctx->stream>>>(cg, n, gc, ncos, t.leaves, c->W, (int)g0);
-                    CKL(ctx);
-                } else {
-                    TRY(lde_leaves(ctx, cg, n, gc, (int)c->degree_log, (int)rloc, sg, t.leaves, c->W, (int)g0));
-                }
+                TRY(lde_columns(ctx, cg, n, gc, (int)c->degree_log, (int)rloc, sg, t.leaves + (size_t)g0 * Nloc, Nloc));
             } else {
                 // fewer than n points per shard: restrict the polynomials to the sub-coset first
                 const uint32_t logM = c->degree_log + c->rate_bits - sl;
@@ -950,13 +588,7 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
                 k_fold_coeffs<<<dim3((unsigned)((M + 127) / 128), gc), 128, 0, ctx->stream>>>(cg, n, n, M, gl::pow(sg, M),
                                                                                             folded);
                 CKL(ctx);
-                int rc2 = GL_OK;
-                if (logM == 0) {
-                    k_lde_const<<<(gc + 127) / 128, 128, 0, ctx->stream>>>(folded, 1, gc, 1, t.leaves, c->W, (int)g0);
-                    ctx->launches++;
-                } else {
-                    rc2 = lde_leaves(ctx, folded, M, gc, (int)logM, 0, sg, t.leaves, c->W, (int)g0);
-                }
+                const int rc2 = lde_columns(ctx, folded, M, gc, (int)logM, 0, sg, t.leaves + (size_t)g0 * Nloc, Nloc);
                 dfree(ctx, folded);
                 TRY(rc2);
             }
@@ -975,7 +607,7 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
         }
         k_salt<<<(unsigned)((Nloc + 255) / 256), 256, 0, ctx->stream>>>(sp, N, c->degree_log + c->rate_bits,
                                                                        (size_t)c->shard_index * Nloc, Nloc, t.leaves,
-                                                                       c->W, B);
+                                                                       Nloc, B);
         CKL(ctx);
         if (dsalt) dfree(ctx, dsalt);
     }
@@ -1396,14 +1028,15 @@ static int fri_finish_begin(gl_ctx* ctx, gl_fri* f) {
     // lde_final_poly / coset_fft (oracle.rs:215-220) on both F_{p^2} components, leaf-major W = 2
     const size_t n = (size_t)1 << f->log_n, N = n << f->rate_bits;
     TRY(dmalloc(ctx, &f->values, 2 * N));
-    if (f->log_n == 0) {
-        const int ncos = 1 << f->rate_bits;
-        k_lde_const<<<(2 * ncos + 127) / 128, 128, 0, ctx->stream>>>(f->coeff_cols, n, 2, ncos, f->values, 2, 0);
-        CKL(ctx);
-    } else {
-        TRY(lde_leaves(ctx, f->coeff_cols, n, 2, (int)f->log_n, (int)f->rate_bits, MULTIPLICATIVE_GROUP_GENERATOR,
-                       f->values, 2, 0));
+    u64* cols;
+    TRY(dmalloc(ctx, &cols, 2 * N));
+    int rc = lde_columns(ctx, f->coeff_cols, n, 2, (int)f->log_n, (int)f->rate_bits, MULTIPLICATIVE_GROUP_GENERATOR, cols, N);
+    if (rc == GL_OK) {  // (c0 column | c1 column) -> interleaved F_{p^2} values, the FRI leaves' layout
+        k_interleave<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(cols, N, N, f->values);
+        ctx->launches++;
     }
+    dfree(ctx, cols);
+    TRY(rc);
     f->log_cur = f->log_n + f->rate_bits;
     f->shift = MULTIPLICATIVE_GROUP_GENERATOR;
     return GL_OK;
@@ -1461,10 +1094,8 @@ void gl_ctx_destroy(gl_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& w : ctx->wt)
-        if (w) cudaFree(w);
-    for (auto& kv : ctx->twa) cudaFree(kv.second);
-    for (auto& kv : ctx->coset_tabs) cudaFreeAsync(kv.second, ctx->stream);
+    for (auto& kv : ctx->step_tabs) cudaFreeAsync(kv.second, ctx->stream);
+    for (auto& kv : ctx->post_tabs) cudaFreeAsync(kv.second, ctx->stream);
     for (auto& kv : ctx->fold_tabs) cudaFreeAsync(kv.second, ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->scratch) cudaFreeAsync(ctx->scratch, ctx->stream);
@@ -1482,15 +1113,6 @@ int gl_ctx_synchronize(gl_ctx* ctx) {
 uint64_t gl_ctx_launch_count(const gl_ctx* ctx) { return ctx->launches; }
 int gl_ctx_set_ntt_group(gl_ctx* ctx, uint32_t columns) {
     ctx->ntt_group = columns;
-    return GL_OK;
-}
-int gl_ctx_set_ntt_split(gl_ctx* ctx, int log_contiguous) {
-    // the pass-A twiddle table depends on the split: drop cached tables
-    for (auto& kv : ctx->twa) cudaFree(kv.second);
-    ctx->twa.clear();
-    for (auto& kv : ctx->coset_tabs) cudaFreeAsync(kv.second, ctx->stream);
-    ctx->coset_tabs.clear();
-    ctx->ntt_force_b = log_contiguous;
     return GL_OK;
 }
 int gl_ctx_set_profiling(gl_ctx* ctx, int on) {
@@ -1529,7 +1151,7 @@ int gl_ntt(gl_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t batch, size_t s
     (void)zero_factor_log;
     if (!ctx || !data) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
     CK(ctx, cudaSetDevice(ctx->device));
-    if (log_n > 2 * NTT_MAX_LOG_TILE) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %u > 24", log_n);
+    if (log_n > 3 * NTT_MAX_LOG_PASS) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %u > 30", log_n);
     const size_t n = (size_t)1 << log_n;
     if (batch > 1 && stride < n) return set_err(ctx, GL_ERR_BAD_SHAPE, "stride %zu < n %zu", stride, n);
     if (canon(coset_shift) == 0) return set_err(ctx, GL_ERR_BAD_ARG, "coset_shift must be non-zero");
@@ -1570,7 +1192,7 @@ int gl_commit_create_sharded(gl_ctx* ctx, const uint64_t* cols, size_t col_strid
     *out = nullptr;
     CK(ctx, cudaSetDevice(ctx->device));
     if (B == 0) return set_err(ctx, GL_ERR_BAD_SHAPE, "empty polynomial batch");
-    if (log_n > 2 * NTT_MAX_LOG_TILE) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %u > 24", log_n);
+    if (log_n > 3 * NTT_MAX_LOG_PASS) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %u > 30", log_n);
     if (log_n + rate_bits > 32) return set_err(ctx, GL_ERR_BAD_SHAPE, "LDE size exceeds the field's 2-adicity");
     if (cap_height > log_n + rate_bits)
         return set_err(ctx, GL_ERR_BAD_SHAPE, "cap_height=%u should be at most log2(leaves.len())=%u", cap_height,
@@ -1611,8 +1233,26 @@ int gl_commit_coeffs(gl_commit* c, uint64_t* out, int mem) {
     return copy_out(c->ctx, out, c->coeffs, (size_t)c->B << c->degree_log, mem);
 }
 int gl_commit_leaves(gl_commit* c, size_t row_begin, size_t row_count, uint64_t* out, int mem) {
-    if (row_begin + row_count > c->tree.N) return set_err(c->ctx, GL_ERR_BAD_ARG, "row range out of bounds");
-    return copy_out(c->ctx, out, c->tree.leaves + row_begin * c->W, row_count * c->W, mem);
+    gl_ctx* ctx = c->ctx;
+    if (row_begin + row_count > c->tree.N) return set_err(ctx, GL_ERR_BAD_ARG, "row range out of bounds");
+    if (row_count == 0) return GL_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    // the LDE is column-major on the device; the reference's row-major leaves are produced on demand, in slabs
+    const size_t slab = ((size_t)1 << 27) / c->W + 1;  // ~1 GiB of staging at most
+    u64* stage = nullptr;
+    if (mem == GL_MEM_HOST) TRY(dmalloc(ctx, &stage, (row_count < slab ? row_count : slab) * c->W));
+    int rc = GL_OK;
+    for (size_t r0 = 0; r0 < row_count && rc == GL_OK; r0 += slab) {
+        const size_t rows = row_count - r0 < slab ? row_count - r0 : slab;
+        u64* dst = mem == GL_MEM_HOST ? stage : out + r0 * c->W;
+        k_rows_from_columns<<<dim3((unsigned)((rows + 31) / 32), (c->W + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(
+            c->tree.leaves, c->tree.es, row_begin + r0, rows, c->W, dst);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = set_err(ctx, GL_ERR_CUDA, "k_rows_from_columns launch failed");
+        if (rc == GL_OK && mem == GL_MEM_HOST) rc = d2h(ctx, out + r0 * c->W, stage, rows * c->W);
+    }
+    dfree(ctx, stage);
+    return rc;
 }
 int gl_commit_digests(gl_commit* c, uint64_t* out, int mem) {
     return copy_out(c->ctx, out, c->tree.digests, c->tree.digest_words(), mem);
@@ -1625,7 +1265,10 @@ int gl_commit_get_lde_values(gl_commit* c, size_t index, size_t step, uint64_t* 
     for (uint32_t i = 0; i < bits; i++) rev |= ((idx >> i) & 1) << (bits - 1 - i);
     const size_t row0 = (size_t)c->shard_index * c->tree.N;
     if (rev < row0 || rev >= row0 + c->tree.N) return set_err(c->ctx, GL_ERR_BAD_ARG, "LDE row held by another shard");
-    return d2h(c->ctx, out, c->tree.leaves + (rev - row0) * c->W, c->B);
+    CK(c->ctx, cudaMemcpy2DAsync(out, 8, c->tree.leaves + (rev - row0), c->tree.es * 8, 8, c->B, cudaMemcpyDeviceToHost,
+                                 c->ctx->stream));
+    CK(c->ctx, cudaStreamSynchronize(c->ctx->stream));
+    return GL_OK;
 }
 int gl_commit_shard(const gl_commit* c, uint32_t* shard_index, uint32_t* num_shards) {
     if (shard_index) *shard_index = c->shard_index;
@@ -1665,7 +1308,10 @@ int gl_commit_eval_ext(gl_commit* c, const uint64_t point[2], uint64_t* out) {
     dfree(ctx, dout);
     return rc;
 }
-const uint64_t* gl_commit_dev_leaves(const gl_commit* c) { return c->tree.leaves; }
+const uint64_t* gl_commit_dev_lde(const gl_commit* c, size_t* col_stride) {
+    if (col_stride) *col_stride = c->tree.es;
+    return c->tree.leaves;
+}
 const uint64_t* gl_commit_dev_coeffs(const gl_commit* c) { return c->coeffs; }
 
 int gl_partial_products_and_zs(gl_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, const uint64_t* k_is,
@@ -1944,7 +1590,7 @@ int gl_fri_begin_from_coeffs(gl_ctx* ctx, const uint64_t* coeffs_ext, uint32_t l
     if (!ctx || !coeffs_ext || !out) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
     *out = nullptr;
     CK(ctx, cudaSetDevice(ctx->device));
-    if (log_n > 2 * NTT_MAX_LOG_TILE) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %u > 24", log_n);
+    if (log_n > 3 * NTT_MAX_LOG_PASS) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %u > 30", log_n);
     const size_t n = (size_t)1 << log_n;
     gl_fri* f = new gl_fri();
     f->ctx = ctx;

@@ -405,9 +405,18 @@ def test_large_ntt_against_oracle_and_roundtrip(pb, oracle, log_n):
     assert np.array_equal(pb.ifft(y), x)
 
 
-def test_ntt_rejects_sizes_beyond_the_build_limit(pb):
-    with pytest.raises(pb.NativeError):
-        pb.fft(np.zeros(1 << 25, dtype=np.uint64))
+@pytest.mark.parametrize("log_n", [21, 22, 25])
+def test_three_pass_ntt_spot_checks_and_roundtrip(pb, oracle, log_n):
+    # n > 2^20 runs three passes (7+7+7 ... 9+8+8): a few outputs against Horner evaluation of the input polynomial
+    # at w_n^k on the CPU (size-independent check), then ifft(fft(x)) == x
+    n = 1 << log_n
+    x = synth(0x90 + log_n, (n,))
+    y = pb.fft(x)
+    w = pb.field.primitive_root_of_unity(log_n)
+    for k in (0, 1, 2, n // 2 + 5, n - 1, 0x12345 % n, (1 << (log_n - 7)) + 3):
+        pt = (pow(w, k, P), 0)
+        assert int(y[k]) == oracle.eval_poly_base_at_ext(x, pt)[0], (log_n, k)
+    assert np.array_equal(pb.ifft(y), x)
 
 
 def test_cfg3_merkle_2pow23_leaves_width12(pb, oracle):

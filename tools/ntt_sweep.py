@@ -14,7 +14,7 @@ with torch.cuda.stream(stream):
     buf = torch.randint(0, 2**63 - 1, (cols, n), dtype=torch.int64, device=dev)
     for b in (0, 8, 9, 11, 12):
         for grp in (32, 64):
-            ctx.set_ntt_split(b); ctx.set_ntt_group(grp)
+            ctx.set_ntt_group(grp)
             for _ in range(3):
                 N.check(L.gl_ntt(ctx.h, C.c_void_p(buf.data_ptr()), log_n, cols, n, 0, 0, 1, N.MEM_DEVICE), ctx.h)
             torch.cuda.synchronize()
