@@ -44,12 +44,58 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+PRESETS = {  # --config name: (columns, log_n, rate_bits, cap_height, generator seed, BASELINE.json configs index)
+    "cfg2": (234, 20, 3, 4, 0x02, 1),
+    "cfg5": (64, 24, 1, 4, 0x05, 4),
+}
+
+
+def preset_of(args):
+    for name, (B, log_n, r, h, seed, idx) in PRESETS.items():
+        if (args.cols, args.log_n, args.rate_bits, args.cap_height) == (B, log_n, r, h):
+            return name, seed, idx
+    return None, 0x02, None
+
+
+def load_fixture(args):
+    """Golden cap of this exact workload from the CPU oracle (tools/make_fullscale_fixtures.py), or None."""
+    name, seed, _ = preset_of(args)
+    path = os.path.join(ROOT, "tests", "golden", "fullscale_%s.json" % name) if name else None
+    if path and os.path.exists(path) and args.seed == seed:
+        return json.load(open(path))
+    return None
+
+
+def synth_torch(seed, shape, device):
+    """tests/conftest.py synth() (the SURVEY 8(d) splitmix64 counter generator) on the device, bit for bit:
+    int64 arithmetic wraps like uint64; logical shifts are emulated with masks."""
+    import torch
+
+    def s64(v):
+        v &= (1 << 64) - 1
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    def lsr(z, k):
+        return (z >> k) & ((1 << (64 - k)) - 1)
+
+    n = 1
+    for d in shape:
+        n *= d
+    z = torch.arange(n, dtype=torch.int64, device=device) + s64(seed * 0x1000000000 + 0x9E3779B97F4A7C15)
+    z = (z ^ lsr(z, 30)) * s64(0xBF58476D1CE4E5B9)
+    z = (z ^ lsr(z, 27)) * s64(0x94D049BB133111EB)
+    z = z ^ lsr(z, 31)
+    z = torch.where((z < 0) & (z >= -0xFFFFFFFF), z + 0xFFFFFFFF, z)  # z >= p (unsigned)  ->  z - p
+    return z.reshape(shape)
+
+
 def workload_config(args, world):
     n, N = 1 << args.log_n, 1 << (args.log_n + args.rate_bits)
     name = "from_values: %d columns x 2^%d values, rate_bits=%d, cap_height=%d (2^%d leaves x %d)" % (
         args.cols, args.log_n, args.rate_bits, args.cap_height, args.log_n + args.rate_bits, args.cols)
-    if (args.cols, args.log_n, args.rate_bits, args.cap_height) == (234, 20, 3, 4):
-        name = "BASELINE configs[1]: " + name
+    pname, _, idx = preset_of(args)
+    if pname:
+        name = "BASELINE configs[%d]: " % idx + name
     return {
         "workload": name,
         "columns": args.cols, "log_n": args.log_n, "rate_bits": args.rate_bits, "cap_height": args.cap_height,
@@ -65,16 +111,45 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------
 # reference arm: the CPU path (oracle port; the Rust reference cannot be built in this image)
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(args, cores, target_seconds=3.0):
-    """Bounded sample of the same workload for the CPU arm: same columns/rate/cap, fewer rows. Calibrated by
-    timing a small sample and scaling linearly in n so that one step takes about `target_seconds`."""
-    import math
+CPU_STEP_SECONDS = 8.0  # one CPU step of the bounded sample (both the --impl reference arm and the cpu_baseline leg)
 
-    base = min(12, args.log_n)
-    run_cpu_once(args, base, cores, 7)          # warm-up (thread pool, page faults)
+
+def cpu_sample(args, cores, target_seconds=CPU_STEP_SECONDS):
+    """Rows per CPU step: the FULL workload when one step fits `target_seconds` on this box's cores, otherwise the
+    largest power-of-two row count that does (same columns / rate / cap). Calibrated at 2^14 rows, where the CPU
+    path is already bandwidth- and hash-bound like the full size, scaling n log n."""
+    base = min(14, args.log_n)
+    run_cpu_once(args, min(12, base), cores, 7)  # warm-up (thread pool, page faults)
     dt, _ = run_cpu_once(args, base, cores, 8)
-    grow = int(math.floor(math.log2(max(target_seconds / max(dt, 1e-4), 1.0))))
-    return max(base, min(args.log_n, base + grow))
+    log_n_s = base
+    while log_n_s < args.log_n and dt * 2.0 * (log_n_s + 1 + 8) / (log_n_s + 8) <= target_seconds:
+        dt *= 2.0 * (log_n_s + 1 + 8) / (log_n_s + 8)
+        log_n_s += 1
+    avail = 0
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        pass
+    while avail and log_n_s > base and 8 * args.cols * ((2 << (log_n_s + args.rate_bits)) + (2 << log_n_s)) > 0.7 * avail:
+        log_n_s -= 1  # the oracle holds the column-major LDE and the row-major leaves at once
+    return log_n_s
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def sample_text(args, log_n_s):
+    if log_n_s == args.log_n:
+        return "the full workload (n=2^%d rows per step)" % log_n_s
+    return "same columns/rate/cap, n=2^%d rows per step (bounded sample: 1/%d of the n=2^%d workload)" % (
+        log_n_s, 1 << (args.log_n - log_n_s), args.log_n)
 
 
 def run_cpu_once(args, log_n_s, cores, seed):
@@ -82,7 +157,7 @@ def run_cpu_once(args, log_n_s, cores, seed):
 
     from conftest import synth
 
-    vals = synth(seed, (args.cols, 1 << log_n_s))
+    vals = synth(seed, (args.cols, 1 << log_n_s))  # seeds >= 7 are bench-only; a full-size run at args.seed is the fixture
     t0 = time.perf_counter()
     c = oracle_lib.Commit(vals, args.rate_bits, args.cap_height, nthreads=cores)
     dt = time.perf_counter() - t0
@@ -107,15 +182,17 @@ def reference_arm(args, rank, world):
     elems = args.cols * (1 << (log_n_s + args.rate_bits))
     total = sum(times)
     value = elems * len(times) / total
-    sample = "same columns/rate/cap, n=2^%d rows per step (bounded sample of n=2^%d)" % (log_n_s, args.log_n)
+    sample = sample_text(args, log_n_s)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic", "config": workload_config(args, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "note": "C++ restatement of the reference CPU algorithm (oracle/); the Rust reference "
-                                 "needs nightly cargo, absent from this image"},
+                         "cpu_model": cpu_model(), "sample_log_n": log_n_s,
+                         "note": "C++ restatement of the reference CPU algorithm (oracle/) on a persistent thread "
+                                 "pool; the Rust reference needs nightly cargo, absent from this image"},
+        "sample": sample,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -195,9 +272,8 @@ def gpu_arm(args, rank, local_rank, world):
     peak, peak_src = load_peaks()
 
     with torch.cuda.stream(stream):
-        g = torch.Generator(device=dev)
-        g.manual_seed(0x02)
-        vals = torch.randint(0, 2**63 - 1, (B, n), dtype=torch.int64, device=dev, generator=g)  # canonical (< p)
+        vals = synth_torch(args.seed, (B, n), dev)  # SURVEY 8(d) generator: the oracle can reproduce cap0 without torch
+        fixture = load_fixture(args)
         cap_local = torch.empty(cap_local_words, dtype=torch.int64, device=dev)
         cap_full = torch.empty(cap_local_words * world, dtype=torch.int64, device=dev)
 
@@ -250,6 +326,10 @@ def gpu_arm(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_max = float(t.item())
         cap_dev = cap_full.cpu().numpy().view(np.uint64).reshape(-1, 4).copy()
+        cap_ok = None
+        if fixture is not None:  # golden cap of this exact workload from the CPU oracle (tests/golden/fullscale_*.json)
+            cap_ok = bool(np.array_equal(cap_dev, np.array(fixture["cap"], dtype=np.uint64)))
+            assert cap_ok, "rank %d: the gathered Merkle cap differs from the oracle fixture" % rank
 
         # ---- end to end through the C ABI with HOST buffers (pinned): H2D of the columns + D2H of the cap
         host_vals = torch.empty((B, n), dtype=torch.int64, pin_memory=True)
@@ -373,6 +453,8 @@ def gpu_arm(args, rank, local_rank, world):
                          "unit": "GB/s", "frac": lde_bytes / (lde_ms * 1e-3) / 1e9 / peak if lde_ms else None},
         "roofline_ntt": ntt,
         "cap0": [int(x) for x in cap_dev[0]],
+        "cap_matches_fixture": cap_ok,
+        "input": "splitmix64 counter generator, seed 0x%02x (tests/conftest.py synth; SURVEY 8d)" % args.seed,
     }
     # ---- CPU baseline (bounded sample, rank 0, N=1 only)
     if world == 1 and not args.no_cpu:
@@ -380,11 +462,11 @@ def gpu_arm(args, rank, local_rank, world):
 
         cores = oracle_lib.nproc()
         log_n_s = cpu_sample(args, cores)
-        run_cpu_once(args, min(log_n_s, 12), cores, 1)
-        dt, _ = run_cpu_once(args, log_n_s, cores, 2)
+        dt, _ = run_cpu_once(args, log_n_s, cores, 200)
         line["cpu_baseline"] = {
             "value": B * (1 << (log_n_s + r)) / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "same columns/rate/cap, n=2^%d rows (bounded sample of n=2^%d), %.2f s" % (log_n_s, log_n, dt)}
+            "cpu_model": cpu_model(), "sample_log_n": log_n_s,
+            "sample": sample_text(args, log_n_s) + ", one step, %.2f s" % dt}
     if world == 1 and not args.no_extra:
         try:
             line["prove_recursion_shape"] = recursion_shape(local_rank)
@@ -491,16 +573,22 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default=None, choices=sorted(PRESETS), help="BASELINE.json preset (default cfg2 shape)")
     ap.add_argument("--cols", type=int, default=234)
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--rate-bits", type=int, default=3)
     ap.add_argument("--cap-height", type=int, default=4)
+    ap.add_argument("--seed", type=lambda v: int(v, 0), default=None, help="input generator seed (default: the preset's)")
     ap.add_argument("--ntt-cols", type=int, default=64)
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--ntt-group", type=int, default=0, help="columns per NTT group (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the recursion-shaped prove() timing")
     args = ap.parse_args()
+    if args.config:
+        args.cols, args.log_n, args.rate_bits, args.cap_height = PRESETS[args.config][:4]
+    if args.seed is None:
+        args.seed = preset_of(args)[1]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -12,6 +12,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -21,6 +25,124 @@ typedef unsigned __int128 u128;
 typedef uint64_t u64;
 
 namespace {
+
+// ------------------------------------------------------------------ parallelism (stands in for rayon)
+// A persistent worker pool with dynamically scheduled chunks: the reference runs its par_iter / join calls on
+// rayon's global pool (maybe_rayon/src/lib.rs), which neither respawns threads per call nor splits statically.
+class Pool {
+   public:
+    static Pool& get() {
+        static Pool p;
+        return p;
+    }
+    // run job(chunk_index) for chunk_index < nchunks on up to `nthreads` threads (the caller is one of them)
+    void run(size_t nchunks, int nthreads, const std::function<void(size_t)>& job) {
+        if (nthreads <= 1 || nchunks <= 1) {
+            for (size_t i = 0; i < nchunks; i++) job(i);
+            return;
+        }
+        std::unique_lock<std::mutex> api(api_mu_);  // one parallel region at a time (no nesting in this file)
+        ensure(nthreads - 1);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            job_ = &job;
+            nchunks_ = nchunks;
+            next_.store(0);
+            active_ = std::min<size_t>(workers_.size(), (size_t)nthreads - 1);
+            pending_ = active_;
+            epoch_++;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            epoch_++;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+
+   private:
+    void work() {
+        for (;;) {
+            size_t i = next_.fetch_add(1);
+            if (i >= nchunks_) break;
+            (*job_)(i);
+        }
+    }
+    void ensure(size_t n) {
+        while (workers_.size() < n) {
+            size_t id = workers_.size();
+            workers_.emplace_back([this, id] {
+                size_t seen = 0;
+                for (;;) {
+                    std::unique_lock<std::mutex> lk(mu_);
+                    cv_.wait(lk, [&] { return stop_ || (epoch_ != seen && id < active_); });
+                    if (stop_) return;
+                    seen = epoch_;
+                    lk.unlock();
+                    work();
+                    lk.lock();
+                    if (--pending_ == 0) done_cv_.notify_all();
+                }
+            });
+        }
+    }
+    std::mutex api_mu_, mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> workers_;
+    const std::function<void(size_t)>* job_ = nullptr;
+    std::atomic<size_t> next_{0};
+    size_t nchunks_ = 0, active_ = 0, pending_ = 0, epoch_ = 0;
+    bool stop_ = false;
+};
+// f(i) for i < n, in chunks of `grain` consecutive indices
+template <class F>
+void parallel_for(size_t n, int nthreads, F f, size_t grain = 1) {
+    if (grain < 1) grain = 1;
+    const size_t nchunks = (n + grain - 1) / grain;
+    Pool::get().run(nchunks, nthreads, [&](size_t c) {
+        const size_t lo = c * grain, hi = std::min(n, lo + grain);
+        for (size_t i = lo; i < hi; i++) f(i);
+    });
+}
+
+// Uninitialised storage (Rust's Vec::with_capacity + set_len / collect: no serial zero-fill, pages are first
+// touched by the threads that write them).
+template <class T>
+struct RawVec {
+    T* p = nullptr;
+    size_t n = 0;
+    RawVec() {}
+    RawVec(const RawVec&) = delete;
+    RawVec& operator=(const RawVec&) = delete;
+    ~RawVec() { free(p); }
+    void resize(size_t m) {
+        free(p);
+        p = m ? (T*)malloc(m * sizeof(T)) : nullptr;
+        if (m && !p) {
+            fprintf(stderr, "oracle: out of memory (%zu bytes)\n", m * sizeof(T));
+            abort();
+        }
+        n = m;
+    }
+    void clear() { resize(0); }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    size_t size() const { return n; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+    T* begin() { return p; }
+    T* end() { return p + n; }
+    const T* begin() const { return p; }
+    const T* end() const { return p + n; }
+};
 
 // ------------------------------------------------------------------ field
 // field/src/goldilocks_field.rs:13-25,198
@@ -302,25 +424,48 @@ inline void full_rounds(u64 st[12], int* round_ctr) {
         (*round_ctr)++;
     }
 }
-// mds_partial_layer_init, poseidon.rs:413-441
+// u160 accumulator of 64x64 products and its reduction (poseidon.rs:40-53: add_u160_u128, reduce_u160)
+struct U160 {
+    u128 lo;
+    uint32_t hi;
+};
+inline void add_u160_u128(U160& x, u128 y) {
+    x.lo += y;
+    x.hi += (uint32_t)(x.lo < y);
+}
+// reduce96 / from_noncanonical_u96, goldilocks_field.rs:159-161,392-398
+inline u64 reduce96(u64 n_lo, uint32_t n_hi) {
+    u64 t1 = (u64)n_hi * EPS;
+    u64 res = n_lo + t1;
+    res += (0 - (u64)(res < t1)) & EPS;
+    return res;
+}
+inline u64 reduce_u160(const U160& x) {
+    u64 reduced_hi = reduce96((u64)(x.lo >> 64), x.hi);
+    return reduce128(((u128)reduced_hi << 64) + (u128)(u64)x.lo);
+}
+// mds_partial_layer_init, poseidon.rs:413-441. The reference accumulates result[c] += state[r] * t in the field;
+// the sums are evaluated here in a u160 accumulator with ONE reduction per output lane (same field value).
 inline void mds_partial_layer_init(u64 st[12]) {
-    u64 result[12] = {0};
+    u64 result[12];
     result[0] = st[0];
-    for (int r = 1; r < 12; r++)
-        for (int c = 1; c < 12; c++)
-            result[c] = fadd(result[c], fmul(st[r], GL_POSEIDON_FAST_INIT_MATRIX[(r - 1) * 11 + (c - 1)]));
+    for (int c = 1; c < 12; c++) {
+        U160 acc = {0, 0};
+        for (int r = 1; r < 12; r++) add_u160_u128(acc, (u128)st[r] * GL_POSEIDON_FAST_INIT_MATRIX[(r - 1) * 11 + (c - 1)]);
+        result[c] = reduce_u160(acc);
+    }
     memcpy(st, result, sizeof(result));
 }
-// mds_partial_layer_fast, poseidon.rs:514-542
+// mds_partial_layer_fast, poseidon.rs:514-542: u160 accumulator for d, multiply_accumulate for the other lanes
+// (goldilocks_field.rs:118-123: reduce128(a*b + c))
 inline void mds_partial_layer_fast(u64 st[12], int r) {
-    // d = s0*(circ0+diag0) + sum_i w_hat[i]*s[i]; each product < 2^128, 12 of them < 2^132:
-    // accumulate the field value (the reference uses a u160 accumulator + reduce_u160).
-    u64 d = fmul(st[0], GL_POSEIDON_MDS_CIRC[0] + GL_POSEIDON_MDS_DIAG[0]);
-    for (int i = 1; i < 12; i++) d = fadd(d, fmul(st[i], GL_POSEIDON_FAST_W_HATS[r * 11 + i - 1]));
+    U160 d_sum = {0, 0};
+    for (int i = 1; i < 12; i++) add_u160_u128(d_sum, (u128)st[i] * GL_POSEIDON_FAST_W_HATS[r * 11 + i - 1]);
+    add_u160_u128(d_sum, (u128)st[0] * (GL_POSEIDON_MDS_CIRC[0] + GL_POSEIDON_MDS_DIAG[0]));
     u64 result[12];
-    result[0] = d;
+    result[0] = reduce_u160(d_sum);
     for (int i = 1; i < 12; i++)
-        result[i] = fadd(st[i], fmul(st[0], GL_POSEIDON_FAST_VS[r * 11 + i - 1]));  // multiply_accumulate
+        result[i] = reduce128((u128)st[0] * GL_POSEIDON_FAST_VS[r * 11 + i - 1] + (u128)st[i]);
     memcpy(st, result, sizeof(result));
 }
 // partial_rounds, poseidon.rs:751-764
@@ -391,8 +536,7 @@ inline bool heq(const Hash& a, const Hash& b) { return memcmp(a.e, b.e, 32) == 0
 
 // ------------------------------------------------------------------ Merkle tree
 // fill_subtree, merkle_tree.rs:86-113. digests_buf has 2*(n_leaves-1) hashes.
-Hash fill_subtree(Hash* digests_buf, size_t buf_len, const u64* leaves, size_t n_leaves, size_t W,
-                  int par_depth) {
+Hash fill_subtree(Hash* digests_buf, size_t buf_len, const u64* leaves, size_t n_leaves, size_t W) {
     assert(n_leaves == buf_len / 2 + 1);
     if (buf_len == 0) return hash_or_noop(leaves, W);
     size_t half = buf_len / 2;
@@ -402,23 +546,39 @@ Hash fill_subtree(Hash* digests_buf, size_t buf_len, const u64* leaves, size_t n
     Hash* right_buf = digests_buf + half + 1;
     size_t sub_len = half - 1;
     size_t nl = n_leaves / 2;
-    Hash ld, rd;
-    if (par_depth > 0) {  // rayon::join
-        std::thread t([&] { ld = fill_subtree(left_buf, sub_len, leaves, nl, W, par_depth - 1); });
-        rd = fill_subtree(right_buf, sub_len, leaves + nl * W, nl, W, par_depth - 1);
-        t.join();
-    } else {
-        ld = fill_subtree(left_buf, sub_len, leaves, nl, W, 0);
-        rd = fill_subtree(right_buf, sub_len, leaves + nl * W, nl, W, 0);
-    }
+    Hash ld = fill_subtree(left_buf, sub_len, leaves, nl, W);
+    Hash rd = fill_subtree(right_buf, sub_len, leaves + nl * W, nl, W);
     *left_digest_mem = ld;
     *right_digest_mem = rd;
     return two_to_one(ld, rd);
 }
-int ceil_log2(int x) {
-    int l = 0;
-    while ((1 << l) < x) l++;
-    return l;
+// rayon::join of the recursion (merkle_tree.rs:100-104) as pool tasks: the subtrees `depth` levels down are the
+// tasks; the few nodes above them are combined afterwards in the same recursive order.
+struct SubTask {
+    Hash* buf;
+    size_t buf_len;
+    const u64* leaves;
+    size_t n_leaves;
+    Hash out;
+};
+void collect_subtasks(Hash* buf, size_t buf_len, const u64* leaves, size_t n_leaves, size_t W, int depth,
+                      std::vector<SubTask>& tasks) {
+    if (depth == 0 || buf_len == 0) {
+        tasks.push_back(SubTask{buf, buf_len, leaves, n_leaves, Hash()});
+        return;
+    }
+    size_t half = buf_len / 2, sub_len = half - 1, nl = n_leaves / 2;
+    collect_subtasks(buf, sub_len, leaves, nl, W, depth - 1, tasks);
+    collect_subtasks(buf + half + 1, sub_len, leaves + nl * W, nl, W, depth - 1, tasks);
+}
+Hash combine_subtasks(Hash* buf, size_t buf_len, int depth, const SubTask*& it) {
+    if (depth == 0 || buf_len == 0) return (it++)->out;
+    size_t half = buf_len / 2, sub_len = half - 1;
+    Hash ld = combine_subtasks(buf, sub_len, depth - 1, it);
+    Hash rd = combine_subtasks(buf + half + 1, sub_len, depth - 1, it);
+    buf[half - 1] = ld;
+    buf[half] = rd;
+    return two_to_one(ld, rd);
 }
 // MerkleTree::new + fill_digests_buf, merkle_tree.rs:115-149,193-224
 int merkle_build(const u64* leaves, size_t N, size_t W, uint32_t cap_height, Hash* digests, Hash* cap,
@@ -432,24 +592,23 @@ int merkle_build(const u64* leaves, size_t N, size_t W, uint32_t cap_height, Has
     size_t num_digests = 2 * (N - C);
     if (nthreads < 1) nthreads = 1;
     if (num_digests == 0) {
-        for (size_t i = 0; i < N; i++) cap[i] = hash_or_noop(leaves + i * W, W);
+        parallel_for(N, nthreads, [&](size_t i) { cap[i] = hash_or_noop(leaves + i * W, W); }, 64);
         return 0;
     }
     size_t sub_digests = num_digests >> cap_height;
     size_t sub_leaves = N >> cap_height;
-    // one task per cap subtree (par_chunks), recursive join inside
-    int par_total = ceil_log2(nthreads);
-    int par_inside = std::max(0, par_total - (int)cap_height);
-    int outer = std::min<size_t>(C, (size_t)nthreads);
-    std::vector<std::thread> ths;
-    for (int t = 0; t < outer; t++) {
-        ths.emplace_back([=] {
-            for (size_t c = t; c < C; c += outer)
-                cap[c] = fill_subtree(digests + c * sub_digests, sub_digests, leaves + c * sub_leaves * W,
-                                      sub_leaves, W, par_inside);
-        });
-    }
-    for (auto& t : ths) t.join();
+    // one task per cap subtree (par_chunks), recursive join inside: split until there are ~8 tasks per thread
+    int depth = 0;
+    while (((size_t)C << depth) < (size_t)nthreads * 8 && ((size_t)1 << (depth + 1)) <= sub_leaves / 2) depth++;
+    std::vector<SubTask> tasks;
+    for (size_t c = 0; c < C; c++)
+        collect_subtasks(digests + c * sub_digests, sub_digests, leaves + c * sub_leaves * W, sub_leaves, W, depth, tasks);
+    parallel_for(tasks.size(), nthreads, [&](size_t t) {
+        SubTask& k = tasks[t];
+        k.out = fill_subtree(k.buf, k.buf_len, k.leaves, k.n_leaves, W);
+    });
+    const SubTask* it = tasks.data();
+    for (size_t c = 0; c < C; c++) cap[c] = combine_subtasks(digests + c * sub_digests, sub_digests, depth, it);
     return 0;
 }
 // merkle_tree_prove, merkle_tree.rs:151-190
@@ -481,21 +640,6 @@ bool merkle_verify(const u64* leaf, size_t W, size_t leaf_index, const Hash* sib
     return heq(cur, cap[leaf_index]);
 }
 
-template <class F>
-void parallel_for(size_t n, int nthreads, F f) {
-    if (nthreads <= 1 || n <= 1) {
-        for (size_t i = 0; i < n; i++) f(i);
-        return;
-    }
-    int T = (int)std::min<size_t>(n, nthreads);
-    std::vector<std::thread> ths;
-    for (int t = 0; t < T; t++)
-        ths.emplace_back([=] {
-            for (size_t i = t; i < n; i += T) f(i);
-        });
-    for (auto& t : ths) t.join();
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------ PolynomialBatch
@@ -503,10 +647,10 @@ struct glo_commit {
     size_t B, W, n, N;
     uint32_t degree_log, rate_bits, cap_height;
     bool blinding;
-    std::vector<u64> coeffs;   // B x n column-major ("polynomials")
-    std::vector<u64> leaves;   // N x W row-major
-    std::vector<Hash> digests; // 2*(N-C)
-    std::vector<Hash> cap;     // C
+    RawVec<u64> coeffs;        // B x n column-major ("polynomials")
+    RawVec<u64> leaves;        // N x W row-major
+    RawVec<Hash> digests;      // 2*(N-C)
+    RawVec<Hash> cap;          // C
 };
 
 namespace {
@@ -541,13 +685,15 @@ glo_commit* commit_new(const u64* cols, size_t col_stride, size_t B, uint32_t lo
         else
             for (size_t i = 0; i < n; i++) dst[i] = canon(dst[i]);
     });
-    for (auto& x : c->coeffs) x = canon(x);
     // "FFT + blinding": lde_values
     RootTable rt_N = fft_root_table(N);
-    std::vector<u64> lde(W * N);  // column-major Vec<Vec<F>>
+    RawVec<u64> lde;  // column-major Vec<Vec<F>>
+    lde.resize(W * N);
     parallel_for(B, nthreads, [&](size_t b) {
+        u64* src = c->coeffs.data() + b * n;
+        for (size_t i = 0; i < n; i++) src[i] = canon(src[i]);
         u64* dst = lde.data() + b * N;
-        memcpy(dst, c->coeffs.data() + b * n, n * 8);
+        memcpy(dst, src, n * 8);
         memset(dst + n, 0, (N - n) * 8);  // p.lde(rate_bits): zero-pad
         coset_fft_with_options(dst, N, MULTIPLICATIVE_GROUP_GENERATOR, rate_bits, &rt_N);
     });
@@ -555,15 +701,20 @@ glo_commit* commit_new(const u64* cols, size_t col_stride, size_t B, uint32_t lo
         for (size_t s = 0; s < SALT_SIZE; s++) memcpy(lde.data() + (B + s) * N, salt + s * N, N * 8);
     // "transpose LDEs" + reverse_index_bits_in_place(&mut leaves) (oracle.rs:97-98): the reference transposes
     // into one Vec per LDE point and then permutes the Vec headers; writing row i straight to position
-    // bitrev(i) is the same permutation without moving W-word rows twice.
+    // bitrev(i) is the same permutation without moving W-word rows twice. Blocks of 8 consecutive LDE points
+    // (one cache line of every column) per step, like the reference's blocked transpose (util/mod.rs:25-31).
     c->leaves.resize(N * W);
     const uint32_t lgN = log_n + rate_bits;
-    parallel_for(N, nthreads, [&](size_t i) {
-        u64* row = c->leaves.data() + (size_t)reverse_bits(i, lgN) * W;
-        for (size_t b = 0; b < W; b++) row[b] = canon(lde[b * N + i]);
-    });
+    const size_t TB = N >= 8 ? 8 : N;
+    parallel_for(N / TB, nthreads, [&](size_t blk) {
+        u64* rows[8];
+        for (size_t k = 0; k < TB; k++) rows[k] = c->leaves.data() + (size_t)reverse_bits(blk * TB + k, lgN) * W;
+        for (size_t b = 0; b < W; b++) {
+            const u64* src = lde.data() + b * N + blk * TB;
+            for (size_t k = 0; k < TB; k++) rows[k][b] = canon(src[k]);
+        }
+    }, 64);
     lde.clear();
-    lde.shrink_to_fit();
     // "build Merkle tree"
     size_t C = (size_t)1 << cap_height;
     c->digests.resize(2 * (N - C));

@@ -12,6 +12,24 @@ from .hash import MerkleCap, MerkleProof
 SALT_SIZE = 4  # oracle.rs:26
 
 
+def random_field_elements(count):
+    """Uniform canonical field elements from the OS CSPRNG (F::rand, field/src/goldilocks_field.rs:61-64):
+    64-bit draws, rejecting values >= p -- vectorised (a 2^23 x 4 salt takes ~0.3 s, not minutes)."""
+    import os
+
+    from .field import ORDER
+
+    out = np.empty(count, dtype=np.uint64)
+    filled = 0
+    while filled < count:
+        need = count - filled
+        cand = np.frombuffer(os.urandom(8 * (need + need // 1024 + 16)), dtype="<u8")
+        cand = cand[cand < np.uint64(ORDER)][:need]
+        out[filled:filled + len(cand)] = cand
+        filled += len(cand)
+    return out
+
+
 class _DeviceMerkleTree:
     """View of PolynomialBatch.merkle_tree (merkle_tree.rs:46-62) living on the device."""
 
@@ -88,11 +106,7 @@ class PolynomialBatch:
         if blinding:
             if salt is None:
                 # the reference draws the salt from OsRng (oracle.rs:133-137); same source here
-                import secrets
-
-                from .field import ORDER
-                salt = np.array([secrets.randbelow(ORDER) for _ in range(SALT_SIZE * (n << rate_bits))],
-                                dtype=np.uint64).reshape(SALT_SIZE, -1)
+                salt = random_field_elements(SALT_SIZE * (n << rate_bits)).reshape(SALT_SIZE, -1)
             salt = np.ascontiguousarray(salt, dtype=np.uint64)
             if salt.shape != (SALT_SIZE, n << rate_bits):
                 raise N.ShapeError("salt must be (4, n << rate_bits)")

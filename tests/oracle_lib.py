@@ -281,6 +281,19 @@ class Commit:
     def cap(self):
         return self._arr(lib().glo_commit_cap(self.h), (1 << self.cap_height, 4))
 
+    def leaf_rows(self, indices):
+        """Rows of the leaf matrix without copying all of it (full-scale fixtures)."""
+        view = np.ctypeslib.as_array(lib().glo_commit_leaves(self.h), shape=(self.N * self.W,)).reshape(self.N, self.W)
+        return np.stack([view[int(i)].copy() for i in indices])
+
+    def prove(self, leaf_index):
+        """Merkle siblings of one leaf, bottom-up (merkle_tree.rs:151-190), without copying the digests."""
+        nl = self.log_n + self.rate_bits - self.cap_height
+        sib = np.zeros((nl, 4), dtype=np.uint64)
+        if nl:
+            lib().glo_merkle_prove(int(leaf_index), self.N, self.cap_height, lib().glo_commit_digests(self.h), ptr(sib))
+        return sib
+
     def get_lde_values(self, index, step):
         out = np.empty(self.B, dtype=np.uint64)
         lib().glo_commit_get_lde_values(self.h, index, step, ptr(out))
