@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <sys/mman.h>
+
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -114,7 +116,63 @@ void parallel_for(size_t n, int nthreads, F f, size_t grain = 1) {
 }
 
 // Uninitialised storage (Rust's Vec::with_capacity + set_len / collect: no serial zero-fill, pages are first
-// touched by the threads that write them).
+// touched by the threads that write them). Large blocks are recycled through a small free list, like the
+// reference's allocator (jemalloc/system malloc keep freed arenas mapped): without it every call re-faults
+// gigabytes of fresh pages, which serialises on the kernel's mm lock when 128 threads touch them at once.
+struct BlockCache {
+    static const size_t MIN_BYTES = (size_t)1 << 20, MAX_BLOCKS = 8;
+    std::mutex mu;
+    std::vector<std::pair<size_t, void*>> free_blocks;
+    void* get(size_t bytes) {
+        if (bytes >= MIN_BYTES) {
+            std::lock_guard<std::mutex> lk(mu);
+            size_t best = free_blocks.size();
+            for (size_t i = 0; i < free_blocks.size(); i++)
+                if (free_blocks[i].first >= bytes && free_blocks[i].first <= bytes + bytes / 4 &&
+                    (best == free_blocks.size() || free_blocks[i].first < free_blocks[best].first))
+                    best = i;
+            if (best != free_blocks.size()) {
+                void* q = free_blocks[best].second;
+                free_blocks.erase(free_blocks.begin() + best);
+                return q;
+            }
+        }
+        void* q = nullptr;
+        if (bytes >= MIN_BYTES) {
+            if (posix_memalign(&q, (size_t)2 << 20, bytes) != 0) q = nullptr;
+#if defined(MADV_HUGEPAGE)
+            if (q) madvise(q, bytes, MADV_HUGEPAGE);
+#endif
+        } else {
+            q = malloc(bytes);
+        }
+        return q;
+    }
+    void put(void* q, size_t bytes) {
+        if (!q) return;
+        if (bytes >= MIN_BYTES) {
+            std::lock_guard<std::mutex> lk(mu);
+            if (free_blocks.size() < MAX_BLOCKS) {
+                free_blocks.emplace_back(bytes, q);
+                return;
+            }
+            // evict the smallest cached block in favour of a larger one
+            size_t sm = 0;
+            for (size_t i = 1; i < free_blocks.size(); i++)
+                if (free_blocks[i].first < free_blocks[sm].first) sm = i;
+            if (free_blocks[sm].first < bytes) {
+                free(free_blocks[sm].second);
+                free_blocks[sm] = std::make_pair(bytes, q);
+                return;
+            }
+        }
+        free(q);
+    }
+    static BlockCache& get_cache() {
+        static BlockCache* c = new BlockCache();  // leaked on purpose: blocks may outlive static destruction order
+        return *c;
+    }
+};
 template <class T>
 struct RawVec {
     T* p = nullptr;
@@ -122,10 +180,10 @@ struct RawVec {
     RawVec() {}
     RawVec(const RawVec&) = delete;
     RawVec& operator=(const RawVec&) = delete;
-    ~RawVec() { free(p); }
+    ~RawVec() { BlockCache::get_cache().put(p, n * sizeof(T)); }
     void resize(size_t m) {
-        free(p);
-        p = m ? (T*)malloc(m * sizeof(T)) : nullptr;
+        BlockCache::get_cache().put(p, n * sizeof(T));
+        p = m ? (T*)BlockCache::get_cache().get(m * sizeof(T)) : nullptr;
         if (m && !p) {
             fprintf(stderr, "oracle: out of memory (%zu bytes)\n", m * sizeof(T));
             abort();
