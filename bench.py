@@ -94,6 +94,8 @@ def workload_config(args, world):
     name = "from_values: %d columns x 2^%d values, rate_bits=%d, cap_height=%d (2^%d leaves x %d)" % (
         args.cols, args.log_n, args.rate_bits, args.cap_height, args.log_n + args.rate_bits, args.cols)
     pname, _, idx = preset_of(args)
+    if getattr(args, "fri_commit", False):
+        name += " + FRI commit phase of its opening proof"
     if pname:
         name = "BASELINE configs[%d]: " % idx + name
     return {
@@ -102,9 +104,9 @@ def workload_config(args, world):
         "lde_elements": args.cols * N,
         "l2": "inputs %.2f GB + leaves %.2f GB per step, far larger than the 126 MB L2 (no flush needed)" % (
             args.cols * n * 8 / 1e9, args.cols * N * 8 / 1e9),
-        "parallelism": (("column-sharded iNTT + NCCL all-gather of coefficients, then " if world >= 4 else "") +
-                        "row-block (coset) sharded LDE + Merkle x%d + NCCL all-gather of cap entries" % world) if world > 1
-        else "single GPU",
+        "parallelism": ("column-sharded iNTT storing into every rank's coefficient matrix over NVLink (64-column "
+                        "chunks), then row-block (coset) sharded LDE + Merkle x%d + NCCL all-gather of cap "
+                        "entries" % world) if world > 1 else "single GPU",
     }
 
 
@@ -296,16 +298,49 @@ def gpu_arm(args, rank, local_rank, world):
         cap_full = torch.empty(cap_local_words * world, dtype=torch.int64, device=dev)
 
         committer = None
-        if world >= 4:  # at 2 ranks the replicated iNTT with chunk-overlapped H2D has the better end-to-end time
-            from plonky2_b200.distributed import ColumnShardedCommitter
+        if world >= 2:
+            # column-sharded iNTT whose stores are the coefficient all-gather (NVLink), pipelined under the LDE
+            from plonky2_b200.distributed import PipelinedCommitter
 
-            committer = ColumnShardedCommitter(ctx, B, log_n, r, h, rank, world, dev)
-            my_cols = vals[committer.b0:committer.b1]
+            committer = PipelinedCommitter(ctx, B, log_n, r, h, rank, world, dev, transport=args.transport)
+
+        fri_ctx = None
+        if args.fri_commit:
+            # BASELINE configs[4] ("LDE + FRI commit"): after the trace commitment, the FRI commit phase of its opening
+            # proof (starky/src/prover.rs:83-94 -> fri/oracle.rs:176-220 + fri/prover.rs:84-150) with the real host
+            # transcript: observe cap -> alpha -> batch-combine at zeta / g*zeta -> fold rounds (arity 16 x5), caps out.
+            import plonky2_b200 as pb
+            from plonky2_b200 import fri as F
+
+            cfg = pb.starky_standard_fast_fri_config() if r == 1 else pb.standard_recursion_fri_config()
+            params = cfg.fri_params(log_n, False)
+            zeta = (0x1122334455667788 % pb.field.ORDER, 0x99AABBCCDDEEFF00 % pb.field.ORDER)
+            gz = pb.field.ext_mul(zeta, (pb.field.primitive_root_of_unity(log_n), 0))
+            inst = pb.FriInstanceInfo([pb.FriOracleInfo(B, False)],
+                                      [pb.FriBatchInfo(zeta, [pb.FriPolynomialInfo(0, i) for i in range(B)]),
+                                       pb.FriBatchInfo(gz, [pb.FriPolynomialInfo(0, 0), pb.FriPolynomialInfo(0, 1)])])
+
+            class _Oracle:  # what fri._begin needs of a PolynomialBatch
+                def __init__(self, h):
+                    self.h, self.ctx = h, ctx
+
+            def fri_commit_phase(hnd, cap_np):
+                ch = pb.Challenger()
+                ch.observe_cap(pb.MerkleCap(np.ascontiguousarray(cap_np).view(np.uint64).reshape(-1, 4)))
+                st = F._begin(inst, [_Oracle(hnd)], ch.get_extension_challenge(), params)
+                try:
+                    caps, final = F.fri_committed_trees(st, ch, params)
+                finally:
+                    st.close()
+                return caps, final
+
+            fri_ctx = fri_commit_phase
+        fri_out = [None]
 
         def step_device():
             if committer is not None:
                 # column-sharded iNTT -> NCCL all-gather of coefficients -> row-block sharded LDE + Merkle
-                hnd = committer.commit(my_cols, from_host=False)
+                hnd = committer.commit(vals, from_host=False)
             else:
                 hnd = N.vp()
                 N.check(L.gl_commit_create_sharded(ctx.h, C.c_void_p(vals.data_ptr()), n, B, log_n, r, h, None, 0,
@@ -315,6 +350,8 @@ def gpu_arm(args, rank, local_rank, world):
                 dist.all_gather_into_tensor(cap_full, cap_local)
             else:
                 cap_full.copy_(cap_local)
+            if fri_ctx is not None:
+                fri_out[0] = fri_ctx(hnd, cap_full.cpu().numpy())
             L.gl_commit_destroy(hnd)
 
         def sync_all():
@@ -327,6 +364,9 @@ def gpu_arm(args, rank, local_rank, world):
             step_device()
         sync_all()
         ctx.reset_phases()
+        if committer is not None:
+            committer.timing = True
+            committer.transfer_ms()
         launches0 = ctx.launch_count
         sampler = ClockSampler(local_rank) if rank == 0 else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -337,6 +377,9 @@ def gpu_arm(args, rank, local_rank, world):
         sync_all()
         ms = e0.elapsed_time(e1)
         launches = ctx.launch_count - launches0
+        side = committer.transfer_ms() if committer is not None else None
+        if committer is not None:
+            committer.timing = False
         clocks = sampler.stop() if sampler else None
         phases = ctx.phase_ms()
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -357,7 +400,7 @@ def gpu_arm(args, rank, local_rank, world):
 
         def step_e2e():
             if committer is not None:
-                hnd = committer.commit(host_vals[committer.b0:committer.b1], from_host=True)  # H2D of 1/G of the columns
+                hnd = committer.commit(host_vals, from_host=True)  # every rank uploads 1/G of the columns
             else:
                 hnd = N.vp()
                 N.check(L.gl_commit_create_sharded(ctx.h, C.c_void_p(host_vals.data_ptr()), n, B, log_n, r, h, None, 0,
@@ -366,6 +409,8 @@ def gpu_arm(args, rank, local_rank, world):
             if world > 1:
                 cap_local.copy_(torch.from_numpy(host_cap.view(np.int64)))
                 dist.all_gather_into_tensor(cap_full, cap_local)
+            if fri_ctx is not None:
+                fri_ctx(hnd, cap_full.cpu().numpy() if world > 1 else host_cap)
             L.gl_commit_destroy(hnd)
 
         step_e2e()
@@ -457,21 +502,29 @@ def gpu_arm(args, rank, local_rank, world):
         "dtype": "u64", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks,
         "e2e": {"value": B * NN / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": (B * n * 8 * world) if world < 4 else ((B + world - 1) // world) * n * 8 * world,
+                "h2d_bytes_per_step": B * n * 8,  # whole job: with G ranks each uploads its 1/G of the columns
                 "d2h_bytes_per_step": cap_local_words * 8,
                 "note": "host (pinned) columns -> gl_commit_create -> cap on host; leaves/digests stay on the "
                         "device behind the handle (fetched on demand by gl_commit_leaves/_open)"},
         "gpu_launches": int(launches),
         "roofline": roof,
         "roofline_issue": issue,
-        "phases_ms_per_step": {k: v[0] / steps for k, v in phases.items()},
+        "phases_ms_per_step": dict({k: v[0] / steps for k, v in phases.items()},
+                                   **({"side_stream_nvlink_copy_and_barriers (under the main stream)": side[0] / max(1, side[1])}
+                                      if side else {})),
         "roofline_lde": {"kernels": "k_passA + k_passB (iNTT + 2^r coset NTTs, leaf-major stores)", "bound": "hbm",
                          "algorithmic_bytes": lde_bytes, "ms": lde_ms,
                          "achieved": lde_bytes / (lde_ms * 1e-3) / 1e9 if lde_ms else None, "peak": peak,
                          "unit": "GB/s", "frac": lde_bytes / (lde_ms * 1e-3) / 1e9 / peak if lde_ms else None},
         "roofline_ntt": ntt,
+        "fri_commit_phase": ({"rounds": len(fri_out[0][0]), "final_poly_len": int(len(fri_out[0][1])),
+                              "last_round_cap0": [int(x) for x in fri_out[0][0][-1].hashes[0]],
+                              "note": "inside the timed step: alpha/betas from the host transcript, caps to the host"}
+                             if fri_out[0] is not None else None),
         "cap0": [int(x) for x in cap_dev[0]],
         "cap_matches_fixture": cap_ok,
+        "coefficient_transport": (committer.transport + (" (%s)" % committer.transport_note if committer.transport_note else ""))
+        if committer is not None else None,
         "input": "splitmix64 counter generator, seed 0x%02x (tests/conftest.py synth; SURVEY 8d)" % args.seed,
     }
     # ---- CPU baseline (bounded sample, rank 0, N=1 only)
@@ -599,6 +652,10 @@ def main():
     ap.add_argument("--cap-height", type=int, default=4)
     ap.add_argument("--seed", type=lambda v: int(v, 0), default=None, help="input generator seed (default: the preset's)")
     ap.add_argument("--ntt-cols", type=int, default=64)
+    ap.add_argument("--transport", default="auto", choices=["auto", "multimem", "p2p", "fused", "nccl"],
+                    help="N > 1: how the coefficients reach the other ranks (auto = fused NVLink stores, NCCL fallback)")
+    ap.add_argument("--fri-commit", action="store_true", default=None,
+                    help="include the FRI commit phase of the opening proof in every step (default: on for cfg5)")
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--ntt-group", type=int, default=0, help="columns per NTT group (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -608,6 +665,8 @@ def main():
         args.cols, args.log_n, args.rate_bits, args.cap_height = PRESETS[args.config][:4]
     if args.seed is None:
         args.seed = preset_of(args)[1]
+    if args.fri_commit is None:
+        args.fri_commit = preset_of(args)[0] == "cfg5"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -57,6 +57,9 @@ int gl_ctx_create(int device, void* stream, gl_ctx** out);
 void gl_ctx_destroy(gl_ctx* ctx);
 const char* gl_last_error(const gl_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
 int gl_ctx_synchronize(gl_ctx* ctx);
+/* the cudaStream_t every call on this context is ordered on (callers that mix their own stream work with the
+ * library's -- torch tensors, NCCL -- must issue it on this stream or order it with events) */
+void* gl_ctx_stream(const gl_ctx* ctx);
 /* number of kernels this context has launched so far (for bench.py's gpu_launches) */
 uint64_t gl_ctx_launch_count(const gl_ctx* ctx);
 /* tuning: columns per multi-pass NTT group (scratch = group * n * 8 bytes; default: as many as fit 1 GiB) */
@@ -83,6 +86,20 @@ int gl_ctx_reset_phases(gl_ctx* ctx);
 int gl_ntt(gl_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t batch, size_t stride, int inverse,
            uint32_t zero_factor_log, uint64_t coset_shift, int mem);
 
+/* Out-of-place, device-resident variant with up to 8 destinations: column b of the result is written to
+ * outs[i] + b*out_stride for EVERY i. With outs[] = the same offset inside each peer GPU's (NVLink-mapped) coefficient
+ * buffer -- or one multicast address -- the last pass of the column-sharded iNTT IS the all-gather of SURVEY.md
+ * section 8(e): no separate collective, the transfer overlaps the butterflies tile by tile. Natural order in and out,
+ * no coset shift; replaces `values.into_par_iter().map(|v| v.ifft())` (oracle.rs:65-69) on G GPUs. */
+int gl_ntt_bcast(gl_ctx* ctx, const uint64_t* in, size_t in_stride, uint32_t log_n, uint32_t batch, int inverse,
+                 uint64_t* const* outs, uint32_t n_outs, size_t out_stride);
+
+/* Device copy of `words` u64 (even, 16-byte aligned) from this GPU's memory to every destination with 128-byte
+ * line stores: the transfer half of the coefficient all-gather when the destinations are peer mappings or a multicast
+ * address (measured at link speed, unlike the 64-byte segments gl_ntt_bcast's transposing stores produce).
+ * max_ctas bounds the grid (0 = 2 per SM) so the copy can share the GPU with a compute stream. */
+int gl_bcast(gl_ctx* ctx, const uint64_t* src, size_t words, uint64_t* const* dests, uint32_t n_dests, uint32_t max_ctas);
+
 /* ---- PolynomialBatch  (plonky2/src/fri/oracle.rs:30-37,57-147) -------------------------------- */
 /* from_values (is_coeffs = 0) / from_coeffs (is_coeffs = 1): B columns of n = 2^log_n words at
  * cols + b*col_stride.  salt: NULL (blinding = false) or GL_SALT_SIZE columns of N = n << rate_bits
@@ -101,6 +118,23 @@ int gl_commit_create(gl_ctx* ctx, const uint64_t* cols, size_t col_stride, uint3
 int gl_commit_create_sharded(gl_ctx* ctx, const uint64_t* cols, size_t col_stride, uint32_t B, uint32_t log_n,
                              uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, int is_coeffs,
                              int mem, uint32_t shard_index, uint32_t num_shards, gl_commit** out);
+/* The same commitment built incrementally, for pipelines whose columns become available in groups (chunks of a
+ * host trace in flight, coefficient groups arriving from peer GPUs, Z / partial-product columns computed on the device):
+ *   gl_commit_begin        allocates the handle's device state. coeff_storage: NULL, or a caller-owned device matrix of
+ *                          B x n words (column b at + b*n) that the handle uses as PolynomialBatch.polynomials (it must
+ *                          outlive the handle; columns passed from inside it are not copied);
+ *   gl_commit_add_columns  columns [first_col, first_col + count), each exactly once, in any order:
+ *                          kind GL_COLS_VALUES (iNTT + LDE), GL_COLS_COEFFS (canonicalise + LDE) or
+ *                          GL_COLS_COEFFS_CANONICAL (LDE only);
+ *   gl_commit_finish       salt columns (iff blinding) and the Merkle tree. Accessors are valid after it. */
+#define GL_COLS_VALUES 0
+#define GL_COLS_COEFFS 1
+#define GL_COLS_COEFFS_CANONICAL 2
+int gl_commit_begin(gl_ctx* ctx, uint32_t B, uint32_t log_n, uint32_t rate_bits, uint32_t cap_height, int blinding,
+                    uint32_t shard_index, uint32_t num_shards, uint64_t* coeff_storage, gl_commit** out);
+int gl_commit_add_columns(gl_commit* c, uint32_t first_col, uint32_t count, const uint64_t* cols, size_t col_stride,
+                          int kind, int mem);
+int gl_commit_finish(gl_commit* c, const uint64_t* salt, int mem);
 int gl_commit_shard(const gl_commit* c, uint32_t* shard_index, uint32_t* num_shards);
 void gl_commit_destroy(gl_commit* c);
 /* shape queries */

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libplonky2_b200.so")
 GL_OK = 0
 GL_ERR_BAD_SHAPE, GL_ERR_OOM, GL_ERR_CUDA, GL_ERR_UNSUPPORTED, GL_ERR_BAD_ARG, GL_ERR_POW_FAILED, GL_ERR_DIV_ZERO = 1, 2, 3, 4, 5, 6, 7
 MEM_HOST, MEM_DEVICE = 0, 1
+COLS_VALUES, COLS_COEFFS, COLS_COEFFS_CANONICAL = 0, 1, 2
 
 u64p = C.POINTER(C.c_uint64)
 u32p = C.POINTER(C.c_uint32)
@@ -20,8 +21,9 @@ vp = C.c_void_p
 
 EXPORTS = [
     "gl_ctx_create", "gl_ctx_destroy", "gl_last_error", "gl_ctx_synchronize", "gl_ctx_launch_count",
-    "gl_ctx_set_ntt_group", "gl_ctx_set_profiling", "gl_ctx_phase_ms", "gl_ctx_reset_phases", "gl_ntt",
-    "gl_commit_create", "gl_commit_create_sharded", "gl_commit_shard", "gl_commit_destroy", "gl_commit_num_polys",
+    "gl_ctx_set_ntt_group", "gl_ctx_set_profiling", "gl_ctx_phase_ms", "gl_ctx_reset_phases", "gl_ctx_stream", "gl_ntt",
+    "gl_ntt_bcast", "gl_bcast", "gl_commit_create", "gl_commit_create_sharded", "gl_commit_begin", "gl_commit_add_columns",
+    "gl_commit_finish", "gl_commit_shard", "gl_commit_destroy", "gl_commit_num_polys",
     "gl_commit_leaf_width", "gl_commit_degree_log", "gl_commit_rate_bits", "gl_commit_cap_height",
     "gl_commit_cap", "gl_commit_coeffs", "gl_commit_leaves", "gl_commit_digests", "gl_commit_get_lde_values",
     "gl_commit_open", "gl_commit_eval_ext", "gl_commit_dev_lde", "gl_commit_dev_coeffs", "gl_partial_products_and_zs", "gl_poseidon_permute_host",
@@ -67,6 +69,14 @@ def lib():
     L.gl_ctx_launch_count.restype = C.c_uint64
     L.gl_ctx_set_ntt_group.argtypes = [vp, C.c_uint32]
     L.gl_ntt.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_size_t, C.c_int, C.c_uint32, C.c_uint64, C.c_int]
+    L.gl_ctx_stream.argtypes = [vp]
+    L.gl_ctx_stream.restype = vp
+    L.gl_ntt_bcast.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp), C.c_uint32, C.c_size_t]
+    L.gl_bcast.argtypes = [vp, vp, C.c_size_t, C.POINTER(vp), C.c_uint32, C.c_uint32]
+    L.gl_commit_begin.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32,
+                                  vp, C.POINTER(vp)]
+    L.gl_commit_add_columns.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_size_t, C.c_int, C.c_int]
+    L.gl_commit_finish.argtypes = [vp, vp, C.c_int]
     L.gl_commit_create.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp,
                                    C.c_int, C.c_int, C.POINTER(vp)]
     L.gl_commit_create_sharded.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp,
@@ -153,6 +163,11 @@ class Context:
 
     def synchronize(self):
         check(lib().gl_ctx_synchronize(self.h), self.h)
+
+    @property
+    def stream(self):
+        """The cudaStream_t (as an int) every call on this context is ordered on."""
+        return int(lib().gl_ctx_stream(self.h) or 0)
 
     @property
     def launch_count(self):

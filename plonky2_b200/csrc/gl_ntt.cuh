@@ -178,31 +178,72 @@ GL_HD void col_phase1(const ColPass& cp, uint64_t* S, int blk, int tid, uint64_t
 #pragma unroll
     for (int q = 0; q < Cf::E; q++) S[q * Cf::COL_QPITCH + t * Cf::T + tt] = x[q];
 }
-// phase 2 (after a CTA barrier): step 2, post twiddle, store
+// phase 2 (after a CTA barrier), in three parts so that the kernel can fetch the post twiddles asynchronously while
+// step 2 computes:  (a) exchange tile -> registers,  (b) step 2,  (c) post twiddle + store.
+// Twiddle of output (m, j) of thread tid: twa[p*C] with p = (t + TPT*m)*TPT + j; col_twiddle_slot() is where the
+// kernel parks it in shared memory (thread-private slots, consecutive threads -> consecutive words).
 template <int LOG>
-GL_HD void col_phase2(const ColPass& cp, const uint64_t* S, int blk, int tid) {
+GL_HD void col_phase2_load(const uint64_t* S, int tid, uint64_t* z /* [NSUB * TPT] */) {
     using Cf = PassCfg<LOG>;
-    if (Cf::R2 == 0) return;
+    const int tt = tid % Cf::T, t = tid / Cf::T;
+#pragma unroll
+    for (int m = 0; m < Cf::NSUB; m++) {
+        const int q = t + Cf::TPT * m;
+#pragma unroll
+        for (int j = 0; j < Cf::TPT; j++) z[m * Cf::TPT + j] = S[q * Cf::COL_QPITCH + j * Cf::T + tt];
+    }
+}
+template <int LOG>
+GL_HD void col_phase2_dft(uint64_t* z) {
+    using Cf = PassCfg<LOG>;
+#pragma unroll
+    for (int m = 0; m < Cf::NSUB; m++) pass_step2<LOG>(z + m * Cf::TPT);
+}
+template <int LOG>
+GL_HD int col_twiddle_slot(int tid, int i) { return i * PassCfg<LOG>::COL_THREADS + tid; }
+template <int LOG>
+GL_HD const uint64_t* col_twiddle_src(const ColPass& cp, int blk, int tid, int i) {
+    using Cf = PassCfg<LOG>;
+    const int tt = tid % Cf::T, t = tid / Cf::T;
+    size_t in_off, out_off;
+    int tile;
+    col_unit<LOG>(cp, blk, in_off, out_off, tile);
+    const int m = i / Cf::TPT, j = i % Cf::TPT;
+    const size_t p = (size_t)(t + Cf::TPT * m) * Cf::TPT + j;
+    return cp.twa + (p << cp.log_c) + (size_t)tile * Cf::T + tt;
+}
+// tws: the E twiddles of this thread, that of output (m, j) at tws[m * stride_m + j * stride_j]
+template <int LOG>
+GL_HD void col_phase2_store(const ColPass& cp, int blk, int tid, const uint64_t* z, const uint64_t* tws, size_t stride_j,
+                            size_t stride_m) {
+    using Cf = PassCfg<LOG>;
     const int tt = tid % Cf::T, t = tid / Cf::T;
     size_t in_off, out_off;
     int tile;
     col_unit<LOG>(cp, blk, in_off, out_off, tile);
     const size_t C = (size_t)1 << cp.log_c;
     uint64_t* dst = cp.out + out_off + (size_t)tile * Cf::T + tt;
-    const uint64_t* twa = cp.twa + (size_t)tile * Cf::T + tt;
 #pragma unroll
     for (int m = 0; m < Cf::NSUB; m++) {
-        const int q = t + Cf::TPT * m;
-        uint64_t z[Cf::TPT];
-#pragma unroll
-        for (int j = 0; j < Cf::TPT; j++) z[j] = S[q * Cf::COL_QPITCH + j * Cf::T + tt];
-        pass_step2<LOG>(z);
 #pragma unroll
         for (int j = 0; j < Cf::TPT; j++) {
-            const size_t p = (size_t)q * Cf::TPT + j;
-            dst[p * C] = mul(z[j], twa[p * C]);
+            const int i = m * Cf::TPT + j;
+            const size_t p = (size_t)(t + Cf::TPT * m) * Cf::TPT + j;
+            dst[p * C] = mul(z[i], tws[m * stride_m + j * stride_j]);
         }
     }
+}
+// the whole phase on one thread, twiddles straight from the table (tests/emu; the kernel interleaves the parts)
+template <int LOG>
+GL_HD void col_phase2(const ColPass& cp, const uint64_t* S, int blk, int tid) {
+    using Cf = PassCfg<LOG>;
+    if (Cf::R2 == 0) return;
+    uint64_t z[Cf::E];
+    col_phase2_load<LOG>(S, tid, z);
+    col_phase2_dft<LOG>(z);
+    // consecutive outputs of a thread are rows p, p+1, ...: their twiddles are 2^log_c words apart in the table
+    const size_t C = (size_t)1 << cp.log_c;
+    col_phase2_store<LOG>(cp, blk, tid, z, col_twiddle_src<LOG>(cp, blk, tid, 0), C, (size_t)Cf::TPT * Cf::TPT * C);
 }
 
 // ---------------------------------------------------------------- row pass
@@ -218,6 +259,8 @@ struct RowPass {
     int has_uq;
     int reverse;           // RM_NATURAL: write to (n - k) mod n   (ifft index reversal, fft.rs:80-90)
     size_t row0;           // RM_BITREV: offset added to the output position (first row of this coset block)
+    int n_peer;            // RM_NATURAL: additional destinations with the same addressing as `out` (peer GPUs'
+    uint64_t* out_peer[7]; // coefficient buffers mapped over NVLink: the store IS the all-gather)
     uint64_t uq[32];
 };
 // line l of CTA blk -> (col, prow, kbase). RM_BITREV enumerates rows in storage order; RM_NATURAL enumerates them by
@@ -341,7 +384,10 @@ GL_HD void row_store_natural(const RowPass& rp, const uint64_t* G, int blk, int 
         if (!row_line<LOG, RM_NATURAL>(rp, blk, l, col, prow, kbase)) continue;
         size_t k = kbase + ((size_t)k2 << rp.log_r);
         if (rp.reverse) k = (n - k) & (n - 1);
-        rp.out[col * rp.out_stride + k] = G[(size_t)l * Cf::GATHER_PITCH + k2];
+        const uint64_t v = G[(size_t)l * Cf::GATHER_PITCH + k2];
+        const size_t at = col * rp.out_stride + k;
+        rp.out[at] = v;
+        for (int p = 0; p < rp.n_peer; p++) rp.out_peer[p][at] = v;
     }
 }
 

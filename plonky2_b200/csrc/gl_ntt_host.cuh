@@ -5,22 +5,47 @@
 // mbarrier) that overlaps the global loads of the data; the exchange tile lives next to it.
 #pragma once
 
-template <int LOG>
+// ASYNC_TW: fetch the post twiddles with cp.async under step 2 (below). Measured on B200 (profiles/r02): it removes the
+// long-scoreboard stalls (3.0 -> 0.5 per issue) and wins where a pass has the extra coset multiplies to hide them under
+// (LDE 34.3 -> 32.7 ms for cfg2), but costs 8 % more instructions and one more barrier, which loses on the plain
+// transform (bare 2^20 NTT 1.15 -> 1.20 ms): used for coset passes only.
+template <int LOG, bool ASYNC_TW>
 __global__ void __launch_bounds__(PassCfg<LOG>::COL_THREADS, PassCfg<LOG>::COL_MIN_BLOCKS) k_ntt_col(ColPass cp) {
+    using Cf = PassCfg<LOG>;
     extern __shared__ __align__(16) u64 smem[];
     u64* tw_s = smem;                    // 2^LOG words
     u64* S = smem + (1 << LOG);          // exchange tile
-    u64* mbar = S + PassCfg<LOG>::COL_S_WORDS;
+    u64* mbar = S + Cf::COL_S_WORDS;
     tma_table_issue(tw_s, cp.tw, (uint32_t)((1 << LOG) * 8), mbar);
-    u64 x[PassCfg<LOG>::E];
+    u64 x[Cf::E];
     col_load<LOG>(cp, blockIdx.x, threadIdx.x, x);  // the data loads overlap the table copy
     __syncthreads();                     // mbarrier initialised before anyone polls it
     ColPass c2 = cp;
     c2.tw = tw_s;
     tma_table_wait(mbar);
     col_phase1<LOG>(c2, S, blockIdx.x, threadIdx.x, x);
+    if (Cf::R2 == 0) return;
     __syncthreads();
-    col_phase2<LOG>(c2, S, blockIdx.x, threadIdx.x);
+    if (!ASYNC_TW) {
+        col_phase2<LOG>(c2, S, blockIdx.x, threadIdx.x);
+        return;
+    }
+    col_phase2_load<LOG>(S, threadIdx.x, x);
+    __syncthreads();                     // every thread holds its part of the tile: S is free
+    // the E post twiddles of this thread (L2-resident table, 8 KiB row stride) go to thread-private shared-memory
+    // slots by cp.async WHILE step 2 runs: as plain loads at their use they were the kernel's main stall
+    // (long-scoreboard 3.0 per issue, profiles/r02 ncu) because 128 registers leave no room to hoist them
+#pragma unroll
+    for (int i = 0; i < Cf::E; i++) {
+        const u64* src = col_twiddle_src<LOG>(cp, blockIdx.x, threadIdx.x, i);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(S + col_twiddle_slot<LOG>(threadIdx.x, i))), "l"(src)
+                     : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    col_phase2_dft<LOG>(x);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    col_phase2_store<LOG>(cp, blockIdx.x, threadIdx.x, x, S + col_twiddle_slot<LOG>(threadIdx.x, 0), Cf::COL_THREADS,
+                          (size_t)Cf::TPT * Cf::COL_THREADS);
 }
 
 template <int LOG, int MODE>
@@ -104,16 +129,18 @@ template <int LOG>
 static int launch_col(gl_ctx* ctx, const ColPass& cp, size_t ncols) {
     const int nblocks = col_blocks<LOG>(cp, ncols);
     const size_t smem = ((size_t)(1 << LOG) + PassCfg<LOG>::COL_S_WORDS) * 8 + 16;
-    const void* fn = (const void*)k_ntt_col<LOG>;
-    if (!ctx->smem_attr_done.count(fn)) {  // function attributes are per device: track them per context
-        CK(ctx, cudaFuncSetAttribute(k_ntt_col<LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(ctx, cudaFuncSetAttribute(k_ntt_col<LOG>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared));
-        ctx->smem_attr_done.insert(fn);
-    }
-    k_ntt_col<LOG><<<nblocks, PassCfg<LOG>::COL_THREADS, smem, ctx->stream>>>(cp);
-    CKL(ctx);
-    return GL_OK;
+    auto go = [&](auto kern) -> int {
+        const void* fn = (const void*)kern;
+        if (!ctx->smem_attr_done.count(fn)) {  // function attributes are per device: track them per context
+            CK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            ctx->smem_attr_done.insert(fn);
+        }
+        kern<<<nblocks, PassCfg<LOG>::COL_THREADS, smem, ctx->stream>>>(cp);
+        CKL(ctx);
+        return GL_OK;
+    };
+    return cp.has_uq ? go(k_ntt_col<LOG, true>) : go(k_ntt_col<LOG, false>);
 }
 template <int LOG, int MODE>
 static int launch_row(gl_ctx* ctx, const RowPass& rp) {
@@ -226,8 +253,12 @@ static int build_pow_tables(gl_ctx* ctx, const std::vector<u64>& bases, size_t c
 // One forward transform of `ncols` device columns: in (natural order) -> out, either natural order (mode RM_NATURAL,
 // optional index reversal + scale for the inverse) or bit-reversed order at out + col*out_stride + row0 (RM_BITREV).
 // shift != 1: evaluate on the coset shift*<w_n> (input scaled by shift^j). `in` is never written unless in == out.
+struct PeerOuts {  // extra destinations of a natural-order transform (same addressing as `out`)
+    int n = 0;
+    u64* p[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
 static int ntt_forward(gl_ctx* ctx, const u64* in, size_t in_stride, u64* out, size_t out_stride, size_t row0, int log_n,
-                       uint32_t ncols, int mode, bool reverse, u64 scale, u64 shift) {
+                       uint32_t ncols, int mode, bool reverse, u64 scale, u64 shift, const PeerOuts* peers = nullptr) {
     if (ncols == 0) return GL_OK;
     if (log_n < 1 || log_n > 3 * NTT_MAX_LOG_PASS) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %d not in 1..30", log_n);
     const NttPlan pl = ntt_plan(log_n);
@@ -239,6 +270,8 @@ static int ntt_forward(gl_ctx* ctx, const u64* in, size_t in_stride, u64* out, s
     rp.out_stride = out_stride;
     rp.reverse = reverse ? 1 : 0;
     rp.row0 = row0;
+    rp.n_peer = peers ? peers->n : 0;
+    for (int i = 0; i < rp.n_peer; i++) rp.out_peer[i] = peers->p[i];
     TRY(get_step(ctx, job.row_step.a, job.row_step.scale, job.row_step.base, &rp.tw));
     if (pl.a1 == 0) {  // single pass
         rp.in = in;
@@ -270,6 +303,7 @@ static int ntt_forward(gl_ctx* ctx, const u64* in, size_t in_stride, u64* out, s
         TRY(dispatch_col(ctx, pl.a1, c1, gc));
         if (pl.a2) TRY(dispatch_col(ctx, pl.a2, c2, gc));
         rp.out = out + (size_t)g0 * out_stride;
+        for (int i = 0; i < rp.n_peer; i++) rp.out_peer[i] = peers->p[i] + (size_t)g0 * out_stride;
         rp.ncols = (int)gc;
         TRY(dispatch_row(ctx, pl.b, mode, rp));
     }
@@ -285,9 +319,11 @@ __global__ void k_scale1(u64* data, size_t stride, uint32_t ncols, u64 f) {
 // Natural-order NTT / iNTT of `ncols` device columns (in -> out, may alias), optional coset shift
 // (forward: evaluate on shift*<w_n>; inverse: interpolate from values on shift*<w_n>).
 static int ntt_natural(gl_ctx* ctx, const u64* in, size_t in_stride, u64* out, size_t out_stride, int log_n,
-                       uint32_t ncols, bool inverse, u64 shift) {
+                       uint32_t ncols, bool inverse, u64 shift, const PeerOuts* peers = nullptr) {
     if (ncols == 0) return GL_OK;
     const size_t n = (size_t)1 << log_n;
+    if (peers && peers->n && (log_n == 0 || canon(shift) != 1))
+        return set_err(ctx, GL_ERR_UNSUPPORTED, "multi-destination transforms need log_n >= 1 and no coset shift");
     if (log_n == 0) {
         if (in != out)
             CK(ctx, cudaMemcpy2DAsync(out, out_stride * 8, in, in_stride * 8, 8, ncols, cudaMemcpyDeviceToDevice,
@@ -296,9 +332,10 @@ static int ntt_natural(gl_ctx* ctx, const u64* in, size_t in_stride, u64* out, s
         CKL(ctx);
         return GL_OK;
     }
-    if (!inverse) return ntt_forward(ctx, in, in_stride, out, out_stride, 0, log_n, ncols, RM_NATURAL, false, 1, shift);
+    if (!inverse) return ntt_forward(ctx, in, in_stride, out, out_stride, 0, log_n, ncols, RM_NATURAL, false, 1, shift, peers);
     // inverse = forward + index reversal + 1/n (fft.rs:68-91), then coefficients *= shift^-k (polynomial/mod.rs:63-73)
-    TRY(ntt_forward(ctx, in, in_stride, out, out_stride, 0, log_n, ncols, RM_NATURAL, true, inverse_2exp((uint32_t)log_n), 1));
+    TRY(ntt_forward(ctx, in, in_stride, out, out_stride, 0, log_n, ncols, RM_NATURAL, true, inverse_2exp((uint32_t)log_n), 1,
+                    peers));
     if (canon(shift) != 1) {
         const int lowbits = log_n > 12 ? 12 : log_n;
         const size_t lo_cnt = (size_t)1 << lowbits, hi_cnt = (size_t)1 << (log_n - lowbits);

@@ -451,6 +451,9 @@ struct gl_commit {
     uint32_t shard_index = 0, shard_log = 0;  // this handle holds leaf rows [g*N/G, (g+1)*N/G)
     bool blinding;
     u64* coeffs = nullptr;  // B x n
+    bool own_coeffs = true; // false: caller-owned storage handed to gl_commit_begin
+    bool finished = false;  // tree built (handles from gl_commit_begin: after gl_commit_finish)
+    u64 sg = 0;             // coset shift of this shard's row block
     Tree tree;
 };
 
@@ -496,18 +499,21 @@ __global__ void k_canon(u64* data, size_t n) {
     if (i < n) data[i] = canon(data[i]);
 }
 
-static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_stride, const u64* salt, int is_coeffs,
-                        int mem, uint32_t cap_height) {
+// Allocate the device state of a commitment: coefficients (or adopt the caller's matrix) and the column-major LDE.
+static int commit_alloc(gl_ctx* ctx, gl_commit* c, uint32_t cap_height, u64* ext_coeffs) {
     const size_t n = (size_t)1 << c->degree_log, N = n << c->rate_bits;
-    const uint32_t B = c->B;
-    TRY(dmalloc(ctx, &c->coeffs, (size_t)B * n));
+    if (ext_coeffs) {
+        c->coeffs = ext_coeffs;
+        c->own_coeffs = false;
+    } else {
+        TRY(dmalloc(ctx, &c->coeffs, (size_t)c->B * n));
+    }
     // Row-block sharding: shard g of G = 2^s owns leaves [g*N/G, (g+1)*N/G), i.e. the
     // LDE points i = g' (mod G), g' = bitrev_s(g): the coset (g * w_N^{g'}) <w_{N/G}> in bit-reversed order.
     const uint32_t sl = c->shard_log;
     const size_t Nloc = N >> sl;
     const uint32_t gprime = bitrev32(c->shard_index, sl);
-    const u64 sg = mul(MULTIPLICATIVE_GROUP_GENERATOR,
-                       gl::pow(root_of_unity(c->degree_log + c->rate_bits), gprime));
+    c->sg = mul(MULTIPLICATIVE_GROUP_GENERATOR, gl::pow(root_of_unity(c->degree_log + c->rate_bits), gprime));
     Tree& t = c->tree;
     t.N = Nloc;
     t.W = c->W;
@@ -516,10 +522,74 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
     t.ls = 1;       // column-major LDE: column k at leaves + k*Nloc, leaf order inside
     t.es = Nloc;
     TRY(dmalloc(ctx, &t.leaves, Nloc * (size_t)c->W));
+    return GL_OK;
+}
+// Columns [g0, g0 + gc) sit in c->coeffs as values (kind 0), coefficients (1) or canonical coefficients (2):
+// iNTT ("IFFT", oracle.rs:65-69) / canonicalise, then the leaf-major coset LDE ("FFT + blinding" + "transpose LDEs" +
+// bit-reversal, fused) into this shard's rows.
+static int commit_chunk(gl_ctx* ctx, gl_commit* c, uint32_t g0, uint32_t gc, int kind) {
+    const size_t n = (size_t)1 << c->degree_log;
+    const uint32_t sl = c->shard_log;
+    Tree& t = c->tree;
+    const size_t Nloc = t.N;
+    u64* cg = c->coeffs + (size_t)g0 * n;
+    if (kind == 0) {
+        PhaseScope ps(ctx, GL_PHASE_INTT);
+        TRY(ntt_natural(ctx, cg, n, cg, n, (int)c->degree_log, gc, true, 1));
+    } else if (kind == 1) {
+        size_t tot = (size_t)gc * n;
+        k_canon<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(cg, tot);
+        CKL(ctx);
+    }
+    PhaseScope ps(ctx, GL_PHASE_LDE);
+    if (sl <= c->rate_bits) {
+        const uint32_t rloc = c->rate_bits - sl;
+        TRY(lde_columns(ctx, cg, n, gc, (int)c->degree_log, (int)rloc, c->sg, t.leaves + (size_t)g0 * Nloc, Nloc));
+    } else {
+        // fewer than n points per shard: restrict the polynomials to the sub-coset first
+        const uint32_t logM = c->degree_log + c->rate_bits - sl;
+        const size_t M = (size_t)1 << logM;
+        u64* folded;
+        TRY(dmalloc(ctx, &folded, (size_t)gc * M));
+        k_fold_coeffs<<<dim3((unsigned)((M + 127) / 128), gc), 128, 0, ctx->stream>>>(cg, n, n, M, gl::pow(c->sg, M), folded);
+        CKL(ctx);
+        const int rc2 = lde_columns(ctx, folded, M, gc, (int)logM, 0, c->sg, t.leaves + (size_t)g0 * Nloc, Nloc);
+        dfree(ctx, folded);
+        TRY(rc2);
+    }
+    return GL_OK;
+}
+// salt columns (blinding) + "build Merkle tree"
+static int commit_finish(gl_ctx* ctx, gl_commit* c, const u64* salt, int mem) {
+    const size_t n = (size_t)1 << c->degree_log, N = n << c->rate_bits;
+    Tree& t = c->tree;
+    const size_t Nloc = t.N;
+    if (salt) {
+        u64* dsalt = nullptr;
+        const u64* sp = salt;
+        if (mem == GL_MEM_HOST) {
+            TRY(dmalloc(ctx, &dsalt, GL_SALT_SIZE * N));
+            TRY(h2d(ctx, dsalt, salt, GL_SALT_SIZE * N));
+            sp = dsalt;
+        }
+        k_salt<<<(unsigned)((Nloc + 255) / 256), 256, 0, ctx->stream>>>(sp, N, c->degree_log + c->rate_bits,
+                                                                       (size_t)c->shard_index * Nloc, Nloc, t.leaves,
+                                                                       Nloc, c->B);
+        CKL(ctx);
+        if (dsalt) dfree(ctx, dsalt);
+    }
+    TRY(tree_build(ctx, t));
+    c->finished = true;
+    return GL_OK;
+}
 
-    // Column chunks flow through  H2D copy -> iNTT ("IFFT", oracle.rs:65-69) -> leaf-major coset LDE
-    // ("FFT + blinding" + "transpose LDEs" + bit-reversal, fused); the copy of chunk k+1 (separate stream)
-    // overlaps the transforms of chunk k.
+static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_stride, const u64* salt, int is_coeffs,
+                        int mem, uint32_t cap_height) {
+    const size_t n = (size_t)1 << c->degree_log;
+    const uint32_t B = c->B;
+    TRY(commit_alloc(ctx, c, cap_height, nullptr));
+    // Column chunks flow through  H2D copy -> iNTT -> LDE; the copy of chunk k+1 (separate stream) overlaps the
+    // transforms of chunk k.
     const uint32_t CH = 32;  // 32 columns: launches big enough for full waves, first-chunk H2D exposure ~5 ms at n = 2^20
     const bool overlap = (mem == GL_MEM_HOST) && B > CH;
     struct EventList {  // destroyed on every exit path
@@ -551,69 +621,18 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
             evs.push_back(e);
         }
     } else if (mem == GL_MEM_HOST) {
-        if (col_stride == n) {
-            TRY(h2d(ctx, c->coeffs, cols, (size_t)B * n));
-        } else {
-            for (uint32_t b = 0; b < B; b++) TRY(h2d(ctx, c->coeffs + (size_t)b * n, cols + (size_t)b * col_stride, n));
-        }
+        CK(ctx, cudaMemcpy2DAsync(c->coeffs, n * 8, cols, col_stride * 8, n * 8, B, cudaMemcpyHostToDevice, ctx->stream));
     } else {
         CK(ctx, cudaMemcpy2DAsync(c->coeffs, n * 8, cols, col_stride * 8, n * 8, B, cudaMemcpyDeviceToDevice,
                                   ctx->stream));
     }
     const uint32_t step = overlap ? CH : B;
-    int rc_loop = GL_OK;
-    for (uint32_t g0 = 0, k = 0; g0 < B && rc_loop == GL_OK; g0 += step, k++) {
+    for (uint32_t g0 = 0, k = 0; g0 < B; g0 += step, k++) {
         const uint32_t gc = (B - g0 < step) ? B - g0 : step;
-        u64* cg = c->coeffs + (size_t)g0 * n;
-        if (overlap) cudaStreamWaitEvent(ctx->stream, evs[k], 0);
-        auto chunk = [&]() -> int {
-            if (!is_coeffs) {
-                PhaseScope ps(ctx, GL_PHASE_INTT);
-                TRY(ntt_natural(ctx, cg, n, cg, n, (int)c->degree_log, gc, true, 1));
-            } else {
-                size_t tot = (size_t)gc * n;
-                k_canon<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(cg, tot);
-                CKL(ctx);
-            }
-            PhaseScope ps(ctx, GL_PHASE_LDE);
-            if (sl <= c->rate_bits) {
-                const uint32_t rloc = c->rate_bits - sl;
-                TRY(lde_columns(ctx, cg, n, gc, (int)c->degree_log, (int)rloc, sg, t.leaves + (size_t)g0 * Nloc, Nloc));
-            } else {
-                // fewer than n points per shard: restrict the polynomials to the sub-coset first
-                const uint32_t logM = c->degree_log + c->rate_bits - sl;
-                const size_t M = (size_t)1 << logM;
-                u64* folded;
-                TRY(dmalloc(ctx, &folded, (size_t)gc * M));
-                k_fold_coeffs<<<dim3((unsigned)((M + 127) / 128), gc), 128, 0, ctx->stream>>>(cg, n, n, M, gl::pow(sg, M),
-                                                                                            folded);
-                CKL(ctx);
-                const int rc2 = lde_columns(ctx, folded, M, gc, (int)logM, 0, sg, t.leaves + (size_t)g0 * Nloc, Nloc);
-                dfree(ctx, folded);
-                TRY(rc2);
-            }
-            return GL_OK;
-        };
-        rc_loop = chunk();
+        if (overlap) CK(ctx, cudaStreamWaitEvent(ctx->stream, evs[k], 0));
+        TRY(commit_chunk(ctx, c, g0, gc, is_coeffs ? 1 : 0));
     }
-    TRY(rc_loop);
-    if (salt) {
-        u64* dsalt = nullptr;
-        const u64* sp = salt;
-        if (mem == GL_MEM_HOST) {
-            TRY(dmalloc(ctx, &dsalt, GL_SALT_SIZE * N));
-            TRY(h2d(ctx, dsalt, salt, GL_SALT_SIZE * N));
-            sp = dsalt;
-        }
-        k_salt<<<(unsigned)((Nloc + 255) / 256), 256, 0, ctx->stream>>>(sp, N, c->degree_log + c->rate_bits,
-                                                                       (size_t)c->shard_index * Nloc, Nloc, t.leaves,
-                                                                       Nloc, B);
-        CKL(ctx);
-        if (dsalt) dfree(ctx, dsalt);
-    }
-    // "build Merkle tree"
-    TRY(tree_build(ctx, t));
-    return GL_OK;
+    return commit_finish(ctx, c, salt, mem);
 }
 
 // =====================================================================================
@@ -1173,6 +1192,125 @@ int gl_ntt(gl_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t batch, size_t s
     return rc;
 }
 
+void* gl_ctx_stream(const gl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int gl_ntt_bcast(gl_ctx* ctx, const uint64_t* in, size_t in_stride, uint32_t log_n, uint32_t batch, int inverse,
+                 uint64_t* const* outs, uint32_t n_outs, size_t out_stride) {
+    if (!ctx || !in || !outs || n_outs == 0 || n_outs > 8) return set_err(ctx, GL_ERR_BAD_ARG, "need 1..8 destinations");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (log_n < 1 || log_n > 3 * NTT_MAX_LOG_PASS) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %u not in 1..30", log_n);
+    const size_t n = (size_t)1 << log_n;
+    if (batch > 1 && (in_stride < n || out_stride < n)) return set_err(ctx, GL_ERR_BAD_SHAPE, "stride < n");
+    PeerOuts po;
+    for (uint32_t i = 0; i < n_outs; i++) {
+        if (!outs[i]) return set_err(ctx, GL_ERR_BAD_ARG, "destination %u is NULL", i);
+        if (outs[i] == in) return set_err(ctx, GL_ERR_BAD_ARG, "gl_ntt_bcast is out of place");
+        if (i) po.p[po.n++] = outs[i];
+    }
+    return ntt_natural(ctx, in, in_stride, outs[0], out_stride, (int)log_n, batch, inverse != 0, 1, &po);
+}
+
+// src (this GPU's memory) -> every destination, 16 bytes per thread per step: full 128-byte lines per warp instruction,
+// the granularity NVLink / NVSwitch multicast writes need to run at link speed (the 64-byte segments of the fused
+// natural-order stores reach ~120 GB/s; this copy is bound by the link).
+struct BcastDests {
+    ulonglong2* p[8];
+    int n;
+};
+__global__ void __launch_bounds__(256) k_bcast_copy(const ulonglong2* __restrict__ src, size_t n16, BcastDests d) {
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += step) {
+        const ulonglong2 v = src[i];
+        for (int k = 0; k < d.n; k++) d.p[k][i] = v;
+    }
+}
+int gl_bcast(gl_ctx* ctx, const uint64_t* src, size_t words, uint64_t* const* dests, uint32_t n_dests, uint32_t max_ctas) {
+    if (!ctx || !src || !dests || n_dests == 0 || n_dests > 8) return set_err(ctx, GL_ERR_BAD_ARG, "need 1..8 destinations");
+    if (words == 0) return GL_OK;
+    if ((words & 1) || ((uintptr_t)src & 15)) return set_err(ctx, GL_ERR_BAD_ARG, "gl_bcast needs 16-byte aligned, even-length buffers");
+    CK(ctx, cudaSetDevice(ctx->device));
+    BcastDests d;
+    d.n = (int)n_dests;
+    for (uint32_t i = 0; i < n_dests; i++) {
+        if (!dests[i] || ((uintptr_t)dests[i] & 15)) return set_err(ctx, GL_ERR_BAD_ARG, "destination %u is NULL or misaligned", i);
+        d.p[i] = (ulonglong2*)dests[i];
+    }
+    const size_t n16 = words / 2;
+    size_t ctas = (n16 + 255) / 256;
+    const size_t cap = max_ctas ? max_ctas : (size_t)ctx->sm_count * 2;
+    if (ctas > cap) ctas = cap;
+    k_bcast_copy<<<(unsigned)ctas, 256, 0, ctx->stream>>>((const ulonglong2*)src, n16, d);
+    CKL(ctx);
+    return GL_OK;
+}
+
+static int commit_check_shape(gl_ctx* ctx, uint32_t B, uint32_t log_n, uint32_t rate_bits, uint32_t cap_height,
+                              uint32_t shard_index, uint32_t num_shards, uint32_t* shard_log) {
+    *shard_log = 0;
+    if (log2_exact(num_shards, shard_log) || shard_index >= num_shards)
+        return set_err(ctx, GL_ERR_BAD_ARG, "bad shard %u of %u (power of two required)", shard_index, num_shards);
+    if (*shard_log > cap_height)
+        return set_err(ctx, GL_ERR_BAD_SHAPE, "num_shards=%u exceeds the cap size 2^%u: shards must own whole cap subtrees",
+                       num_shards, cap_height);
+    if (B == 0) return set_err(ctx, GL_ERR_BAD_SHAPE, "empty polynomial batch");
+    if (log_n > 3 * NTT_MAX_LOG_PASS) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %u > 30", log_n);
+    if (log_n + rate_bits > 32) return set_err(ctx, GL_ERR_BAD_SHAPE, "LDE size exceeds the field's 2-adicity");
+    if (cap_height > log_n + rate_bits)
+        return set_err(ctx, GL_ERR_BAD_SHAPE, "cap_height=%u should be at most log2(leaves.len())=%u", cap_height,
+                       log_n + rate_bits);
+    return GL_OK;
+}
+
+int gl_commit_begin(gl_ctx* ctx, uint32_t B, uint32_t log_n, uint32_t rate_bits, uint32_t cap_height, int blinding,
+                    uint32_t shard_index, uint32_t num_shards, uint64_t* coeff_storage, gl_commit** out) {
+    if (!ctx || !out) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    uint32_t shard_log = 0;
+    TRY(commit_check_shape(ctx, B, log_n, rate_bits, cap_height, shard_index, num_shards, &shard_log));
+    CK(ctx, cudaSetDevice(ctx->device));
+    gl_commit* c = new gl_commit();
+    c->ctx = ctx;
+    c->B = B;
+    c->W = B + (blinding ? GL_SALT_SIZE : 0);
+    c->degree_log = log_n;
+    c->rate_bits = rate_bits;
+    c->blinding = blinding != 0;
+    c->shard_index = shard_index;
+    c->shard_log = shard_log;
+    int rc = commit_alloc(ctx, c, cap_height, coeff_storage);
+    if (rc != GL_OK) {
+        gl_commit_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return GL_OK;
+}
+int gl_commit_add_columns(gl_commit* c, uint32_t first_col, uint32_t count, const uint64_t* cols, size_t col_stride,
+                          int kind, int mem) {
+    if (!c) return set_err(nullptr, GL_ERR_BAD_ARG, "null handle");
+    gl_ctx* ctx = c->ctx;
+    if (c->finished) return set_err(ctx, GL_ERR_BAD_ARG, "commitment already finished");
+    if (!cols || kind < 0 || kind > 2) return set_err(ctx, GL_ERR_BAD_ARG, "bad argument");
+    if (count == 0) return GL_OK;
+    if ((size_t)first_col + count > c->B) return set_err(ctx, GL_ERR_BAD_SHAPE, "columns %u..%u outside the batch of %u", first_col, first_col + count, c->B);
+    const size_t n = (size_t)1 << c->degree_log;
+    if (count > 1 && col_stride < n) return set_err(ctx, GL_ERR_BAD_SHAPE, "Polynomial degrees inconsistent (stride < n)");
+    CK(ctx, cudaSetDevice(ctx->device));
+    u64* dst = c->coeffs + (size_t)first_col * n;
+    if (!(mem == GL_MEM_DEVICE && cols == dst && (col_stride == n || count == 1)))
+        CK(ctx, cudaMemcpy2DAsync(dst, n * 8, cols, col_stride * 8, n * 8, count,
+                                  mem == GL_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+    return commit_chunk(ctx, c, first_col, count, kind);
+}
+int gl_commit_finish(gl_commit* c, const uint64_t* salt, int mem) {
+    if (!c) return set_err(nullptr, GL_ERR_BAD_ARG, "null handle");
+    gl_ctx* ctx = c->ctx;
+    if (c->finished) return set_err(ctx, GL_ERR_BAD_ARG, "commitment already finished");
+    if (c->blinding != (salt != nullptr)) return set_err(ctx, GL_ERR_BAD_ARG, "salt must be given exactly when blinding was requested");
+    CK(ctx, cudaSetDevice(ctx->device));
+    return commit_finish(ctx, c, salt, mem);
+}
+
 int gl_commit_create(gl_ctx* ctx, const uint64_t* cols, size_t col_stride, uint32_t B, uint32_t log_n,
                      uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, int is_coeffs, int mem,
                      gl_commit** out) {
@@ -1183,20 +1321,10 @@ int gl_commit_create_sharded(gl_ctx* ctx, const uint64_t* cols, size_t col_strid
                              uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, int is_coeffs, int mem,
                              uint32_t shard_index, uint32_t num_shards, gl_commit** out) {
     if (!ctx || !cols || !out) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
-    uint32_t shard_log = 0;
-    if (log2_exact(num_shards, &shard_log) || shard_index >= num_shards)
-        return set_err(ctx, GL_ERR_BAD_ARG, "bad shard %u of %u (power of two required)", shard_index, num_shards);
-    if (shard_log > cap_height)
-        return set_err(ctx, GL_ERR_BAD_SHAPE, "num_shards=%u exceeds the cap size 2^%u: shards must own whole cap subtrees",
-                       num_shards, cap_height);
     *out = nullptr;
+    uint32_t shard_log = 0;
+    TRY(commit_check_shape(ctx, B, log_n, rate_bits, cap_height, shard_index, num_shards, &shard_log));
     CK(ctx, cudaSetDevice(ctx->device));
-    if (B == 0) return set_err(ctx, GL_ERR_BAD_SHAPE, "empty polynomial batch");
-    if (log_n > 3 * NTT_MAX_LOG_PASS) return set_err(ctx, GL_ERR_UNSUPPORTED, "log_n %u > 30", log_n);
-    if (log_n + rate_bits > 32) return set_err(ctx, GL_ERR_BAD_SHAPE, "LDE size exceeds the field's 2-adicity");
-    if (cap_height > log_n + rate_bits)
-        return set_err(ctx, GL_ERR_BAD_SHAPE, "cap_height=%u should be at most log2(leaves.len())=%u", cap_height,
-                       log_n + rate_bits);
     if (B > 1 && col_stride < ((size_t)1 << log_n))
         return set_err(ctx, GL_ERR_BAD_SHAPE, "Polynomial degrees inconsistent (stride < n)");
     gl_commit* c = new gl_commit();
@@ -1219,7 +1347,7 @@ int gl_commit_create_sharded(gl_ctx* ctx, const uint64_t* cols, size_t col_strid
 void gl_commit_destroy(gl_commit* c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
-    dfree(c->ctx, c->coeffs);
+    if (c->own_coeffs) dfree(c->ctx, c->coeffs);
     tree_free(c->ctx, c->tree);
     delete c;
 }
@@ -1228,7 +1356,14 @@ uint32_t gl_commit_leaf_width(const gl_commit* c) { return c->W; }
 uint32_t gl_commit_degree_log(const gl_commit* c) { return c->degree_log; }
 uint32_t gl_commit_rate_bits(const gl_commit* c) { return c->rate_bits; }
 uint32_t gl_commit_cap_height(const gl_commit* c) { return c->tree.cap_height + c->shard_log; }
-int gl_commit_cap(gl_commit* c, uint64_t* out, int mem) { return copy_out(c->ctx, out, c->tree.cap, c->tree.cap_words(), mem); }
+#define NEED_FINISHED(c)                                                                                     \
+    do {                                                                                                     \
+        if (!(c)->finished) return set_err((c)->ctx, GL_ERR_BAD_ARG, "gl_commit_finish has not been called"); \
+    } while (0)
+int gl_commit_cap(gl_commit* c, uint64_t* out, int mem) {
+    NEED_FINISHED(c);
+    return copy_out(c->ctx, out, c->tree.cap, c->tree.cap_words(), mem);
+}
 int gl_commit_coeffs(gl_commit* c, uint64_t* out, int mem) {
     return copy_out(c->ctx, out, c->coeffs, (size_t)c->B << c->degree_log, mem);
 }
@@ -1255,6 +1390,7 @@ int gl_commit_leaves(gl_commit* c, size_t row_begin, size_t row_count, uint64_t*
     return rc;
 }
 int gl_commit_digests(gl_commit* c, uint64_t* out, int mem) {
+    NEED_FINISHED(c);
     return copy_out(c->ctx, out, c->tree.digests, c->tree.digest_words(), mem);
 }
 int gl_commit_get_lde_values(gl_commit* c, size_t index, size_t step, uint64_t* out) {
@@ -1276,6 +1412,7 @@ int gl_commit_shard(const gl_commit* c, uint32_t* shard_index, uint32_t* num_sha
     return GL_OK;
 }
 int gl_commit_open(gl_commit* c, const uint64_t* leaf_indices, size_t count, uint64_t* out_leaves, uint64_t* out_paths) {
+    NEED_FINISHED(c);
     return tree_open(c->ctx, c->tree, leaf_indices, count, out_leaves, out_paths);
 }
 int gl_commit_eval_ext(gl_commit* c, const uint64_t point[2], uint64_t* out) {

@@ -1,6 +1,7 @@
 """Multi-GPU plumbing for the row-block sharded commitment: one process per GPU,
-torch.distributed (NCCL on GPUs, gloo in CPU tests) for the single exchange the path needs -- an
-all-gather of the shards' Merkle-cap entries (2^cap_height x 32 bytes in total).
+torch.distributed (NCCL on GPUs, gloo in CPU tests) for the exchange the path needs -- an all-gather of the shards'
+Merkle-cap entries (2^cap_height x 32 bytes in total) -- and PipelinedCommitter for the optional second axis
+(column-sharded iNTT whose stores are the coefficient all-gather over NVLink).
 
 No LDE data ever crosses NVLink: shard g of G evaluates every column on its own coset
 (g_shift * w_N^{bitrev(g)}) <w_{N/G}>, hashes its leaves and reduces its own cap subtrees."""
@@ -111,35 +112,109 @@ def prove_openings_sharded(instance, oracles, challenger, fri_params, group=None
         state.close()
 
 
-def column_slice(num_polys, rank, world):
-    """Columns [b0, b1) whose iNTT rank `rank` computes; slices are equal-sized (the last ones may be padded)."""
-    per = (num_polys + world - 1) // world
-    b0 = min(rank * per, num_polys)
-    return b0, min(b0 + per, num_polys), per
+def chunk_layout(num_polys, world, chunk_cols=64):
+    """Column layout of the pipelined multi-GPU commitment: K chunks of Wc = pc*world consecutive columns; inside
+    chunk c rank r transforms columns [c*Wc + r*pc, c*Wc + (r+1)*pc) (clipped to num_polys). Returns (pc, Wc, K)."""
+    pc = max(1, chunk_cols // world)
+    wc = pc * world
+    return pc, wc, (num_polys + wc - 1) // wc
 
 
-class ColumnShardedCommitter:
-    """from_values over G ranks with BOTH axes of SURVEY.md section 8e: each rank uploads and inverse-transforms
-    only its own slice of the columns (the reference's rayon axis, oracle.rs:65-69), the ranks all-gather the
-    coefficients over NVLink (NCCL; the optional second collective of section 8e), then every rank extends all
-    columns on its own row block / coset and hashes its own leaves (gl_commit_create_sharded, is_coeffs=1).
-    Compared with replicating the iNTT this cuts the per-rank H2D and iNTT work by G; the commitment is bit-identical.
+def chunk_columns(num_polys, rank, world, chunk, chunk_cols=64):
+    """(first global column, count) of rank `rank`'s sub-block of chunk `chunk` (count may be 0 in the last chunk)."""
+    pc, wc, _ = chunk_layout(num_polys, world, chunk_cols)
+    b0 = min(chunk * wc + rank * pc, num_polys)
+    return b0, min(b0 + pc, num_polys) - b0
 
-    Buffers (device slice, gathered coefficients) are torch tensors allocated once and reused across calls."""
 
-    def __init__(self, ctx, num_polys, log_n, rate_bits, cap_height, rank, world, device, group=None):
+class PipelinedCommitter:
+    """from_values over G ranks with BOTH axes of SURVEY.md section 8e, in 64-column chunks:
+
+      copy stream : H2D of my 64/G columns of each chunk (host input), issued ahead
+      main stream : iNTT(0), iNTT(1), LDE(0), iNTT(2), LDE(1), ... , LDE(K-1), leaf hash, cap subtrees
+                    iNTT(c)  = column-sharded inverse transform of MY columns of chunk c into my copy of the matrix
+                    LDE(c)   = coset LDE of all 64 columns of chunk c on this rank's row block (gl_commit_add_columns)
+      side stream : after iNTT(c): my coefficients -> EVERY rank's matrix over NVLink with 128-byte line stores to the
+                    NVSwitch multicast address (gl_bcast; one store per peer mapping without multicast), then a
+                    device-side barrier (symmetric-memory signal pads). LDE(c) waits for it; the transfer runs under
+                    iNTT(c+1) / LDE(c-1) on a handful of SMs.
+
+    The iNTT (the reference's rayon axis, oracle.rs:65-69) and the H2D are divided by G. Transports:
+      "multimem" / "p2p"  as above (torch symmetric memory: CUDA IPC / fabric handles);
+      "fused"             the iNTT's last pass stores straight to the multicast address (gl_ntt_bcast): no second
+                          kernel, but its transposing stores are 64-byte segments and NVLink runs them at ~120 GB/s
+                          (measured, profiles/r02) -- kept for comparison;
+      "nccl"              ncclAllGather per chunk on the main stream (fallback when peer mappings are unavailable).
+    The commitment is bit-identical to the single-device one.
+
+    Stream contract (checked): `ctx` must have been created on the torch stream that is current when commit() is
+    called. The returned handle BORROWS the committer's coefficient matrix: it is valid until the next commit()."""
+
+    def __init__(self, ctx, num_polys, log_n, rate_bits, cap_height, rank, world, device, group=None,
+                 transport="auto", chunk_cols=64, copy_ctas=32):
         import torch
+        import torch.distributed as dist
+
+        from . import _native as N
 
         self.ctx, self.B, self.log_n, self.r, self.h = ctx, num_polys, log_n, rate_bits, cap_height
         self.rank, self.world, self.group, self.device = rank, world, group, device
         self.n = 1 << log_n
-        self.b0, self.b1, self.per = column_slice(num_polys, rank, world)
-        self.slice = torch.zeros((self.per, self.n), dtype=torch.int64, device=device)   # padded columns stay 0
-        self.coeffs = torch.empty((self.per * world, self.n), dtype=torch.int64, device=device)
+        self.chunk_cols, self.copy_ctas = chunk_cols, copy_ctas
+        self.pc, self.wc, self.K = chunk_layout(num_polys, world, chunk_cols)
+        self.copy = torch.cuda.Stream(device=device)
+        self.side = torch.cuda.Stream(device=device)
+        self.ctx_side = N.Context(device.index if hasattr(device, "index") else int(device), stream=self.side.cuda_stream)
+        self.stage = torch.empty((self.K, self.pc, self.n), dtype=torch.int64, device=device)
+        self.h2d_events = [torch.cuda.Event() for _ in range(self.K)]
+        self.intt_events = [torch.cuda.Event() for _ in range(self.K)]
+        self.bcast_events = [torch.cuda.Event() for _ in range(self.K)]
+        self.ready = torch.cuda.Event()
+        self.timing = False          # set True to collect the transfer spans per commit()
+        self._spans = []
+        rows = self.K * self.wc
+        self.symm, self.transport, self.transport_note = None, "nccl", ""
+        if world > 1 and transport != "nccl":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                g = group if group is not None else dist.group.WORLD
+                self.coeffs = symm_mem.empty((rows, self.n), dtype=torch.int64, device=device)
+                self.symm = symm_mem.rendezvous(self.coeffs, g)
+                mc = int(getattr(self.symm, "multicast_ptr", 0) or 0)
+                if transport in ("multimem", "fused") and not mc:
+                    raise RuntimeError("no multicast mapping on this system")
+                self.transport = transport if transport in ("fused", "p2p") else ("multimem" if mc else "p2p")
+                ptrs = [int(p) for p in self.symm.buffer_ptrs]
+                self.local = ptrs[rank]
+                # multicast: one store reaches every rank (mine included); p2p: one store per peer mapping
+                self.dests = [mc] if self.transport in ("multimem", "fused") else [p for i, p in enumerate(ptrs) if i != rank]
+                if len(self.dests) > 8:
+                    raise RuntimeError("more than 8 peers")
+            except Exception as e:  # no peer mappings here: same loop over ncclAllGather
+                if transport != "auto":
+                    raise
+                self.symm, self.transport = None, "nccl"
+                self.transport_note = "symmetric memory unavailable: %r" % (e,)
+        if self.symm is None:
+            self.coeffs = torch.empty((rows, self.n), dtype=torch.int64, device=device)
+
+    def _check_stream(self):
+        import torch
+
+        cur = torch.cuda.current_stream(self.device)
+        if self.ctx.stream != cur.cuda_stream:
+            raise RuntimeError("PipelinedCommitter: the context's stream (0x%x) is not the current torch stream (0x%x); "
+                               "create the Context on the torch stream you call commit() under" % (self.ctx.stream, cur.cuda_stream))
+        return cur
+
+    def my_columns(self):
+        """[(first global column, count)] per chunk: the columns this rank uploads and inverse-transforms."""
+        return [chunk_columns(self.B, self.rank, self.world, c, self.chunk_cols) for c in range(self.K)]
 
     def commit(self, values, from_host):
-        """values: torch int64 tensor holding THIS RANK'S columns [b0, b1) x n (pinned host if from_host, else on
-        the device). Returns the gl_commit handle (row-block shard `rank` of `world`)."""
+        """values: torch int64 tensor of ALL columns (B x n) -- pinned host memory if from_host (only this rank's
+        sub-blocks are read and uploaded), else on the device. Returns the gl_commit handle (row-block shard)."""
         import ctypes as C
 
         import torch
@@ -148,17 +223,94 @@ class ColumnShardedCommitter:
         from . import _native as N
 
         L = N.lib()
-        cnt = self.b1 - self.b0
-        if cnt:
-            self.slice[:cnt].copy_(values[:cnt], non_blocking=True)   # H2D of 1/G of the trace (or D2D)
-            N.check(L.gl_ntt(self.ctx.h, C.c_void_p(self.slice.data_ptr()), self.log_n, cnt, self.n, 1, 0, 1,
-                             N.MEM_DEVICE), self.ctx.h)
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.coeffs, self.slice, group=self.group)
-            src = self.coeffs
-        else:
-            src = self.slice
+        main = self._check_stream()
+        n, nbytes = self.n, self.n * 8
+        base = self.coeffs.data_ptr()
+        mine = self.my_columns()
+        if from_host:
+            with torch.cuda.stream(self.copy):
+                self.copy.wait_stream(main)           # the staging slots' previous readers are queued on `main`
+                for c, (b0, cnt) in enumerate(mine):
+                    if cnt:
+                        self.stage[c, :cnt].copy_(values[b0:b0 + cnt], non_blocking=True)  # H2D of 1/G of the chunk
+                    self.h2d_events[c].record(self.copy)
+        if self.symm is not None:
+            self.symm.barrier(channel=0)              # every rank's LDEs of the previous commitment have read the matrix
+            self.ready.record(main)
         h = N.vp()
-        N.check(L.gl_commit_create_sharded(self.ctx.h, C.c_void_p(src.data_ptr()), self.n, self.B, self.log_n, self.r,
-                                           self.h, None, 1, N.MEM_DEVICE, self.rank, self.world, C.byref(h)), self.ctx.h)
+        N.check(L.gl_commit_begin(self.ctx.h, self.B, self.log_n, self.r, self.h, 0, self.rank, self.world, N.vp(base),
+                                  C.byref(h)), self.ctx.h)
+
+        def transform(c):
+            b0, cnt = mine[c]
+            if from_host:
+                main.wait_event(self.h2d_events[c])
+            src = self.stage[c].data_ptr() if from_host else (values[b0:b0 + cnt].data_ptr() if cnt else 0)
+            off = b0 * nbytes
+            if self.transport == "fused":
+                if cnt:
+                    outs = (N.vp * 1)(N.vp(self.dests[0] + off))
+                    N.check(L.gl_ntt_bcast(self.ctx.h, N.vp(src), n, self.log_n, cnt, 1, outs, 1, n), self.ctx.h)
+                self.symm.barrier(channel=1)
+            elif self.symm is not None:
+                if cnt:  # out of place into MY copy of the matrix
+                    outs = (N.vp * 1)(N.vp(self.local + off))
+                    N.check(L.gl_ntt_bcast(self.ctx.h, N.vp(src), n, self.log_n, cnt, 1, outs, 1, n), self.ctx.h)
+                self.intt_events[c].record(main)
+                with torch.cuda.stream(self.side):
+                    if c == 0:
+                        self.side.wait_event(self.ready)
+                    self.side.wait_event(self.intt_events[c])
+                    if self.timing:
+                        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        t0.record(self.side)
+                    if cnt:
+                        outs = (N.vp * len(self.dests))(*[N.vp(d + off) for d in self.dests])
+                        N.check(L.gl_bcast(self.ctx_side.h, N.vp(self.local + off), cnt * n, outs, len(self.dests),
+                                           self.copy_ctas), self.ctx_side.h)
+                    self.symm.barrier(channel=1)
+                    if self.timing:
+                        t1.record(self.side)
+                        self._spans.append((t0, t1))
+                    self.bcast_events[c].record(self.side)
+            else:
+                if cnt:
+                    if not from_host:
+                        self.stage[c, :cnt].copy_(values[b0:b0 + cnt], non_blocking=True)
+                    N.check(L.gl_ntt(self.ctx.h, N.vp(self.stage[c].data_ptr()), self.log_n, cnt, n, 1, 0, 1, N.MEM_DEVICE),
+                            self.ctx.h)
+                dist.all_gather_into_tensor(self.coeffs[c * self.wc:(c + 1) * self.wc], self.stage[c], group=self.group)
+
+        def extend(c):
+            if self.symm is not None and self.transport != "fused":
+                main.wait_event(self.bcast_events[c])
+            c0 = c * self.wc
+            N.check(L.gl_commit_add_columns(h, c0, min(self.wc, self.B - c0), N.vp(base + c0 * nbytes), n,
+                                            N.COLS_COEFFS_CANONICAL, N.MEM_DEVICE), self.ctx.h)
+
+        try:
+            for c in range(self.K):
+                transform(c)
+                if c:
+                    extend(c - 1)
+            extend(self.K - 1)
+            N.check(L.gl_commit_finish(h, None, N.MEM_DEVICE), self.ctx.h)
+        except Exception:
+            L.gl_commit_destroy(h)
+            raise
         return h
+
+    def transfer_ms(self, reset=True):
+        """(accumulated ms, commits) of the side-stream [NVLink copy + barrier] spans since the last reset; they run
+        under the main stream's transforms except for the last chunk's."""
+        import torch
+
+        torch.cuda.synchronize(self.device)
+        ms = sum(a.elapsed_time(b) for a, b in self._spans)
+        cnt = len(self._spans) // max(1, self.K)
+        if reset:
+            self._spans = []
+        return ms, cnt
+
+
+ColumnShardedCommitter = PipelinedCommitter  # round-1 name

@@ -41,23 +41,33 @@ def main():
     params = pb.FriParams(pb.FriConfig(r, h, 8, ("Fixed", [4, 2]), 12), False, log_n, [4, 2])
     proof = D.prove_openings_sharded(inst, commits, ch, params)
     ok = True
-    # column-sharded iNTT + all-gather of coefficients + row-block sharded LDE/Merkle (ColumnShardedCommitter)
+    # column-sharded iNTT whose stores are the coefficient all-gather + row-block sharded LDE/Merkle (PipelinedCommitter)
     import ctypes as C
     from plonky2_b200 import _native as N_
-    Bc, lg = 11, 12
+    Bc, lg = 70, 12  # two chunks of 64 columns, the second one partial
     vals_c = synth(0x77, (Bc, 1 << lg))
     # torch copies / NCCL and the library must share ONE stream: make the context on a torch stream
     tstream = torch.cuda.Stream(device=dev)
     ctx2 = pb.Context(local, stream=tstream.cuda_stream)
     with torch.cuda.stream(tstream):
-        cm = D.ColumnShardedCommitter(ctx2, Bc, lg, 2, 3, rank, world, dev)
-        mine = torch.from_numpy(np.ascontiguousarray(vals_c[cm.b0:cm.b1]).view(np.int64).copy()).pin_memory()
-        hnd = cm.commit(mine, from_host=True)
-        lcap = np.empty(((1 << 3) // world, 4), dtype=np.uint64)
-        N_.check(N_.lib().gl_commit_cap(hnd, N_.np_ptr(lcap), N_.MEM_HOST), ctx2.h)
-        N_.lib().gl_commit_destroy(hnd)
+        host = torch.from_numpy(vals_c.view(np.int64).copy()).pin_memory()
+        caps_c, transports = [], []
+        for transport in ("auto", "fused", "p2p", "nccl"):
+            try:
+                cm = D.PipelinedCommitter(ctx2, Bc, lg, 2, 3, rank, world, dev, transport=transport)
+            except Exception as e:  # a transport this system lacks (no multicast / no peer mappings) is reported, not fatal
+                transports.append("%s unavailable: %r" % (transport, e))
+                continue
+            transports.append(cm.transport + (" (%s)" % cm.transport_note if cm.transport_note else ""))
+            for from_host in (True, False, True):  # back-to-back commitments reuse the matrix: exercises the hand-over barriers
+                src = host if from_host else host.to(dev)
+                hnd = cm.commit(src, from_host=from_host)
+                lcap = np.empty(((1 << 3) // world, 4), dtype=np.uint64)
+                N_.check(N_.lib().gl_commit_cap(hnd, N_.np_ptr(lcap), N_.MEM_HOST), ctx2.h)
+                N_.lib().gl_commit_destroy(hnd)
+                caps_c.append(lcap)
     torch.cuda.synchronize(dev)
-    full_cap_c = D.gather_cap(lcap, device=dev)
+    full_caps_c = [D.gather_cap(lc, device=dev) for lc in caps_c]
     if rank == 0:
         import oracle_lib
 
@@ -70,8 +80,10 @@ def main():
         obatches = [(b.point, [(p.oracle_index, p.polynomial_index) for p in b.polynomials]) for b in inst.batches]
         oproof = oracle_lib.prove_openings(ocommits, obatches, och, oracle_lib.make_params(r, h, 8, 12, [4, 2]))
         ok &= proof.to_bytes() == oproof
-        ok &= bool(np.array_equal(full_cap_c.hashes, oracle_lib.Commit(vals_c, 2, 3).cap))
-        print("MGPU_PROVE_CHECK", "OK" if ok else "FAILED", "world", world, flush=True)
+        want = oracle_lib.Commit(vals_c, 2, 3).cap
+        for fc in full_caps_c:
+            ok &= bool(np.array_equal(fc.hashes, want))
+        print("MGPU_PROVE_CHECK", "OK" if ok else "FAILED", "world", world, "transports", transports, flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

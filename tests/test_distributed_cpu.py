@@ -102,20 +102,59 @@ def test_open_sharded_routing_single_process():
         D.open_sharded(FakeBatch(), [5])             # owned by shard 0, nobody serves it here
 
 
-@pytest.mark.parametrize("num_polys,world", [(234, 8), (234, 4), (64, 8), (5, 4), (3, 8), (16, 1)])
-def test_column_slices_tile_the_all_gathered_coefficient_buffer(num_polys, world):
-    """ColumnShardedCommitter's layout contract (column axis): equal-sized (padded) slices, in rank order,
-    so that all_gather_into_tensor of the per-rank (per, n) buffers IS the (world*per, n) coefficient matrix whose
-    first num_polys rows are the columns in order."""
+@pytest.mark.parametrize("num_polys,world", [(234, 8), (234, 4), (234, 2), (64, 8), (5, 4), (3, 8), (16, 1), (300, 2)])
+def test_chunk_layout_tiles_the_coefficient_matrix(num_polys, world):
+    """PipelinedCommitter's layout contract (SURVEY 8e, column axis): chunk c = Wc consecutive global columns, rank r's
+    sub-block = pc consecutive columns at c*Wc + r*pc, so that (a) the fused iNTT stores / the per-chunk all-gather of
+    the ranks' (pc, n) blocks in rank order IS rows [c*Wc, (c+1)*Wc) of the coefficient matrix, (b) every column is
+    transformed by exactly one rank, (c) gathered chunks are contiguous column ranges for gl_commit_add_columns."""
     from plonky2_b200 import distributed as D
 
-    per_all, covered = None, []
-    for rank in range(world):
-        b0, b1, per = D.column_slice(num_polys, rank, world)
-        per_all = per if per_all is None else per_all
-        assert per == per_all and 0 <= b0 <= b1 <= num_polys and b1 - b0 <= per
-        # a rank's real columns sit at the start of its padded slot: global row rank*per + k <-> column b0 + k
-        assert b0 == min(rank * per, num_polys)
-        covered += list(range(b0, b1))
+    pc, wc, K = D.chunk_layout(num_polys, world)
+    assert wc == pc * world and K * wc >= num_polys > (K - 1) * wc
+    covered = []
+    for c in range(K):
+        for rank in range(world):
+            b0, cnt = D.chunk_columns(num_polys, rank, world, c)
+            assert 0 <= cnt <= pc and b0 == min(c * wc + rank * pc, num_polys) and b0 + cnt <= num_polys
+            covered += list(range(b0, b0 + cnt))
     assert covered == list(range(num_polys))
-    assert per_all * world >= num_polys
+
+
+def _pipeline_worker(rank, world, port, num_polys, n, out):
+    """The committer's data movement with gloo standing in for NCCL: per chunk every rank contributes its (pc, n)
+    block and the all-gather lands in rows [c*Wc, (c+1)*Wc) of the matrix."""
+    import torch
+    import torch.distributed as dist
+
+    from plonky2_b200 import distributed as D
+
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        pc, wc, K = D.chunk_layout(num_polys, world)
+        full = torch.arange(num_polys * n, dtype=torch.int64).reshape(num_polys, n) * 3 + 1  # "coefficients" of column b
+        coeffs = torch.zeros((K * wc, n), dtype=torch.int64)
+        for c in range(K):
+            b0, cnt = D.chunk_columns(num_polys, rank, world, c)
+            stage = torch.full((pc, n), -1, dtype=torch.int64)
+            stage[:cnt] = full[b0:b0 + cnt]
+            dist.all_gather_into_tensor(coeffs[c * wc:(c + 1) * wc], stage)
+        out.put((rank, bool(torch.equal(coeffs[:num_polys], full))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("num_polys", [11, 70])
+def test_pipelined_gather_layout_two_ranks_gloo(num_polys):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + (os.getpid() % 1000) + num_polys
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, 2, port, num_polys, 8, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(out.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]

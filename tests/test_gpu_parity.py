@@ -641,3 +641,80 @@ def test_randomised_shapes_against_oracle(pb, oracle):
         lv, pt = c.merkle_tree.open_many([lo])
         assert np.array_equal(pt[0], oracle.merkle_prove(lo, N, h, o.digests)), tag
         c.close()
+
+
+# ----------------------------------------------------------------------------- round-2 ABI: multi-destination iNTT, incremental commit
+@pytest.mark.parametrize("log_n", [3, 10, 13])
+def test_ntt_bcast_writes_every_destination(pb, oracle, log_n):
+    """gl_ntt_bcast: the natural-order pass stores each coefficient to all destinations (peer mappings in production)."""
+    import ctypes as C
+
+    import torch
+
+    from plonky2_b200 import _native as N
+
+    n, B = 1 << log_n, 5
+    x = synth(0x90 + log_n, (B, n), canonical=False)
+    ctx = pb.default_context()
+    src = torch.from_numpy(x.view(np.int64).copy()).cuda()
+    dests = [torch.zeros((B + 2, n), dtype=torch.int64, device="cuda") for _ in range(3)]
+    torch.cuda.synchronize()
+    outs = (N.vp * 3)(*[N.vp(d[1:].data_ptr()) for d in dests])  # column b lands at row b + 1 of each destination
+    N.check(N.lib().gl_ntt_bcast(ctx.h, N.vp(src.data_ptr()), n, log_n, B, 1, outs, 3, n), ctx.h)
+    ctx.synchronize()
+    want = np.stack([oracle.ifft(x[b]) for b in range(B)])
+    for d in dests:
+        got = d.cpu().numpy().view(np.uint64)
+        assert np.array_equal(got[1:B + 1], want)
+        assert not got[0].any() and not got[B + 1].any()
+    assert np.array_equal(src.cpu().numpy().view(np.uint64), x)  # out of place: the input is untouched
+
+
+@pytest.mark.parametrize("external", [False, True])
+def test_incremental_commit_matches_oracle(pb, oracle, external):
+    """gl_commit_begin / add_columns (any order, mixed kinds, host and device sources) / finish == from_values."""
+    import ctypes as C
+
+    import torch
+
+    from plonky2_b200 import _native as N
+
+    B, log_n, r, h = 13, 11, 3, 4
+    n = 1 << log_n
+    vals = synth(0xA1, (B, n))
+    o = oracle.Commit(vals, r, h)
+    coeffs = o.coeffs
+    ctx = pb.default_context()
+    L = N.lib()
+    storage = torch.zeros((B, n), dtype=torch.int64, device="cuda") if external else None
+    hnd = N.vp()
+    N.check(L.gl_commit_begin(ctx.h, B, log_n, r, h, 0, 0, 1, N.vp(storage.data_ptr()) if external else None, C.byref(hnd)), ctx.h)
+    try:
+        cap = np.empty((1 << h, 4), dtype=np.uint64)
+        assert L.gl_commit_cap(hnd, N.np_ptr(cap), N.MEM_HOST) != 0  # not finished yet
+        # columns 8..12 as canonical coefficients from the device (in place when the storage is external)
+        if external:
+            storage[8:13].copy_(torch.from_numpy(coeffs[8:13].view(np.int64).copy()))
+            src = storage[8:13]
+        else:
+            src = torch.from_numpy(coeffs[8:13].view(np.int64).copy()).cuda()
+        torch.cuda.synchronize()
+        N.check(L.gl_commit_add_columns(hnd, 8, 5, N.vp(src.data_ptr()), n, N.COLS_COEFFS_CANONICAL, N.MEM_DEVICE), ctx.h)
+        # columns 0..2 as values from the host, 3..7 as (non-canonical) coefficients from the host
+        N.check(L.gl_commit_add_columns(hnd, 0, 3, N.np_ptr(np.ascontiguousarray(vals[0:3])), n, N.COLS_VALUES, N.MEM_HOST), ctx.h)
+        nc = coeffs[3:8].copy()
+        nc[:, 0] = np.where(nc[:, 0] < np.uint64(2**32 - 1), nc[:, 0] + np.uint64(P), nc[:, 0])  # same residues, >= p
+        N.check(L.gl_commit_add_columns(hnd, 3, 5, N.np_ptr(nc), n, N.COLS_COEFFS, N.MEM_HOST), ctx.h)
+        assert L.gl_commit_add_columns(hnd, 12, 2, N.np_ptr(nc), n, N.COLS_COEFFS, N.MEM_HOST) != 0  # outside the batch
+        N.check(L.gl_commit_finish(hnd, None, N.MEM_HOST), ctx.h)
+        N.check(L.gl_commit_cap(hnd, N.np_ptr(cap), N.MEM_HOST), ctx.h)
+        assert np.array_equal(cap, o.cap)
+        got = np.empty((B, n), dtype=np.uint64)
+        N.check(L.gl_commit_coeffs(hnd, N.np_ptr(got), N.MEM_HOST), ctx.h)
+        assert np.array_equal(got, coeffs)
+        rows = np.empty((16, B), dtype=np.uint64)
+        N.check(L.gl_commit_leaves(hnd, 100, 16, N.np_ptr(rows), N.MEM_HOST), ctx.h)
+        assert np.array_equal(rows, o.leaves[100:116])
+        assert L.gl_commit_finish(hnd, None, N.MEM_HOST) != 0  # already finished
+    finally:
+        L.gl_commit_destroy(hnd)
