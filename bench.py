@@ -467,7 +467,7 @@ def gpu_arm(args, rank, local_rank, world):
     perms = N_loc * ((B + 7) // 8 if B > 4 else 0)
     traffic, traffic_note = None, None
     try:  # DRAM bytes per launch from the committed ncu --set full capture (scaled by the algorithmic bytes)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["k_leaf_hash"]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["k_leaf_hash"]
         traffic = tr["dram_bytes_per_algorithmic_byte"] * leaf_bytes
         traffic_note = "ncu dram read+write per algorithmic byte x this launch's algorithmic bytes; " + tr["source"]
     except Exception:
@@ -484,7 +484,7 @@ def gpu_arm(args, rank, local_rank, world):
     # integer-issue roofline (what actually bounds these kernels): thread-instructions/s vs 128 lanes/clk/SM
     issue = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
         peak_issue = 148 * 128 * sm_clk * 1e6
         ipp = tr["k_leaf_hash"]["thread_instructions_per_permutation"]

@@ -151,7 +151,7 @@ class PipelinedCommitter:
     called. The returned handle BORROWS the committer's coefficient matrix: it is valid until the next commit()."""
 
     def __init__(self, ctx, num_polys, log_n, rate_bits, cap_height, rank, world, device, group=None,
-                 transport="auto", chunk_cols=64, copy_ctas=32):
+                 transport="auto", chunk_cols=None, copy_ctas=32):
         import torch
         import torch.distributed as dist
 
@@ -160,6 +160,9 @@ class PipelinedCommitter:
         self.ctx, self.B, self.log_n, self.r, self.h = ctx, num_polys, log_n, rate_bits, cap_height
         self.rank, self.world, self.group, self.device = rank, world, group, device
         self.n = 1 << log_n
+        if chunk_cols is None:  # 64-column chunks, but at least ~4 chunks so that transfers have an LDE to hide under
+            per = -(-num_polys // 4)
+            chunk_cols = max(world, min(64, -(-per // world) * world))
         self.chunk_cols, self.copy_ctas = chunk_cols, copy_ctas
         self.pc, self.wc, self.K = chunk_layout(num_polys, world, chunk_cols)
         self.copy = torch.cuda.Stream(device=device)
