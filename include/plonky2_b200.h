@@ -161,6 +161,12 @@ int gl_commit_open(gl_commit* c, const uint64_t* leaf_indices, size_t count, uin
  * evaluated at one point z of F_{p^2}: out = B x 2 words (host). First "next" row of SURVEY section 8(f):
  * it keeps the coefficient D2H off the prover's critical path. */
 int gl_commit_eval_ext(gl_commit* c, const uint64_t point[2], uint64_t* out);
+/* OpeningSet::new (plonky2/src/plonk/proof.rs:313-351) / StarkOpeningSet::new (starky/src/proof.rs:221-260) as ONE call:
+ * request i = every polynomial of commits[i] at points[point_index[i]] (F_{p^2}, 2 words each; e.g. zeta and g*zeta);
+ * out = the requests' results concatenated in order, B_i x 2 words each; one power table per distinct point, one
+ * D2H (mem = GL_MEM_HOST) or none (GL_MEM_DEVICE). Coefficients never leave the device. */
+int gl_openings(gl_ctx* ctx, gl_commit* const* commits, const uint32_t* point_index, size_t n_evals,
+                const uint64_t* points, size_t n_points, uint64_t* out, int mem);
 /* device views (valid until destroy; for device-resident pipelines such as quotient evaluation).
  * The LDE is kept COLUMN-MAJOR on the device: the value of polynomial (or salt column) k at leaf j -- the LDE row
  * reverse_bits(j), oracle.rs:142-147 -- is at lde[k * col_stride + j]; col_stride = number of local leaves. The
@@ -177,6 +183,36 @@ const uint64_t* gl_commit_dev_coeffs(const gl_commit* c);
 int gl_partial_products_and_zs(gl_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, const uint64_t* k_is,
                                uint32_t log_n, uint32_t num_routed, uint64_t beta, uint64_t gamma, uint32_t degree,
                                uint64_t* out, int mem);
+
+/* compute_quotient_polys of a STARK (starky/src/prover.rs:488-668): for every challenge alpha_j the values
+ * (sum_k alpha_j^.. C_k(x)) / Z_H(x) on the coset g<w_size>, size = n << log2_ceil(quotient_degree_factor), read from the
+ * trace commitment's LDE IN PLACE on the device (get_lde_values addressing, oracle.rs:142-147), then coset_ifft: n_alphas
+ * polynomials of `size` coefficients at out_coeffs + j*size (DEVICE memory). The coefficients beyond
+ * n * quotient_degree_factor are checked to vanish ("Quotient has failed ...", prover.rs:396-401 -> GL_ERR_BAD_ARG).
+ * The constraints (Stark::eval_packed_generic, starky/src/stark.rs:40-70) are a straight-line program: value k is the
+ * result of instruction k; GL_STARK_EMIT feeds a value to the ConstraintConsumer (constraint_consumer.rs:46-84).
+ * consts = the public inputs followed by the program's constants. Split the result into degree-n chunks with
+ * gl_commit_begin / gl_commit_add_columns(GL_COLS_COEFFS) to obtain the quotient commitment (prover.rs:391-421). */
+#define GL_STARK_LOCAL 0 /* a = trace column: local row value */
+#define GL_STARK_NEXT 1  /* a = trace column: next row value */
+#define GL_STARK_CONST 2 /* a = index into consts */
+#define GL_STARK_ADD 3   /* values a + b */
+#define GL_STARK_SUB 4
+#define GL_STARK_MUL 5
+#define GL_STARK_EMIT 6  /* a = value, b = GL_STARK_CONSTRAINT / _TRANSITION / _FIRST_ROW / _LAST_ROW */
+#define GL_STARK_CONSTRAINT 0
+#define GL_STARK_TRANSITION 1
+#define GL_STARK_FIRST_ROW 2
+#define GL_STARK_LAST_ROW 3
+#define GL_STARK_MAX_INSTR 256
+#define GL_STARK_MAX_ALPHAS 4
+#define GL_STARK_MAX_QD 8
+typedef struct {
+    uint16_t op, a, b, pad_;
+} gl_stark_instr;
+int gl_stark_quotient(gl_ctx* ctx, gl_commit* trace, const gl_stark_instr* program, uint32_t n_instr,
+                      const uint64_t* consts, uint32_t n_consts, const uint64_t* alphas, uint32_t n_alphas,
+                      uint32_t quotient_degree_factor, uint64_t* out_coeffs);
 
 /* ---- Hasher / MerkleTree  (plonky2/src/plonk/config.rs:36-77, plonky2/src/hash/merkle_tree.rs:193-237) */
 /* PoseidonPermutation::permute on the HOST for the sequential Fiat-Shamir transcript

@@ -1040,6 +1040,84 @@ int glo_partial_products_and_zs(const uint64_t* wires, const uint64_t* sigmas, c
     return 0;
 }
 
+// ------------------------------------------------------------------ STARK quotient
+// compute_quotient_polys (starky/src/prover.rs:488-668) for FibonacciStark (starky/src/fibonacci_stark.rs:73-95),
+// restated with the reference's own steps: Lagrange selectors by `PolynomialValues::selector(..).lde_onto_coset`
+// (ifft, zero-pad, coset FFT), ZeroPolyOnCoset (field/src/zero_poly_coset.rs), the ConstraintConsumer accumulation
+// (constraint_consumer.rs:60-84), division by Z_H, transpose, coset_ifft. P::WIDTH = 1 (scalar packing).
+int glo_stark_quotient_fibonacci(const glo_commit* trace, const uint64_t pi[3], const uint64_t* alphas,
+                                 size_t n_alphas, uint64_t* out) {
+    if (trace->B != 2) return 1;
+    const uint32_t degree_bits = trace->degree_log, rate_bits = trace->rate_bits;
+    const size_t degree = (size_t)1 << degree_bits;
+    const size_t constraint_degree = 2;
+    const size_t quotient_degree_factor = std::max<size_t>(1, constraint_degree - 1);  // stark.rs:87-92
+    uint32_t quotient_degree_bits = 0;
+    while (((size_t)1 << quotient_degree_bits) < quotient_degree_factor) quotient_degree_bits++;
+    if (quotient_degree_bits > rate_bits) return 2;
+    const size_t step = (size_t)1 << (rate_bits - quotient_degree_bits);
+    const size_t next_step = (size_t)1 << quotient_degree_bits;
+    const size_t size = degree << quotient_degree_bits;
+    auto lde_onto_coset = [&](size_t index) {  // selector(degree, index).lde_onto_coset(quotient_degree_bits)
+        std::vector<u64> v(size, 0);
+        v[index] = 1;
+        ifft_with_options(v.data(), degree, nullptr);
+        coset_fft_with_options(v.data(), size, MULTIPLICATIVE_GROUP_GENERATOR, quotient_degree_bits, nullptr);
+        return v;
+    };
+    std::vector<u64> lagrange_first = lde_onto_coset(0), lagrange_last = lde_onto_coset(degree - 1);
+    // ZeroPolyOnCoset::new(degree_bits, quotient_degree_bits)
+    u64 g_pow_n = MULTIPLICATIVE_GROUP_GENERATOR;
+    for (uint32_t k = 0; k < degree_bits; k++) g_pow_n = fsqr(g_pow_n);
+    const size_t rate = (size_t)1 << quotient_degree_bits;
+    std::vector<u64> zh_inv(rate);
+    {
+        u64 w = primitive_root_of_unity(quotient_degree_bits), x = 1;
+        for (size_t j = 0; j < rate; j++) {
+            zh_inv[j] = finv(fsub(fmul(g_pow_n, x), 1));
+            x = fmul(x, w);
+        }
+    }
+    const u64 last = finv(primitive_root_of_unity(degree_bits));
+    const u64 wsize = primitive_root_of_unity(degree_bits + quotient_degree_bits);
+    std::vector<u64> coset(size);
+    {
+        u64 x = MULTIPLICATIVE_GROUP_GENERATOR;  // cyclic_subgroup_coset_known_order(w, shift, size)
+        for (size_t i = 0; i < size; i++) {
+            coset[i] = x;
+            x = fmul(x, wsize);
+        }
+    }
+    std::vector<u64> quotient_values(size * n_alphas);  // [i][j]
+    u64 lv[2], nv[2];
+    for (size_t i_start = 0; i_start < size; i_start++) {
+        const size_t i_next_start = (i_start + next_step) % size;
+        const u64 x = coset[i_start];
+        const u64 z_last = fsub(x, last);
+        glo_commit_get_lde_values(trace, i_start, step, lv);
+        glo_commit_get_lde_values(trace, i_next_start, step, nv);
+        std::vector<u64> acc(n_alphas, 0);
+        auto constraint = [&](u64 c) {
+            for (size_t j = 0; j < n_alphas; j++) acc[j] = fadd(fmul(acc[j], alphas[j]), c);
+        };
+        // eval_packed_generic, fibonacci_stark.rs:73-95
+        constraint(fmul(fsub(lv[0], pi[0]), lagrange_first[i_start]));
+        constraint(fmul(fsub(lv[1], pi[1]), lagrange_first[i_start]));
+        constraint(fmul(fsub(lv[1], pi[2]), lagrange_last[i_start]));
+        constraint(fmul(fsub(nv[0], lv[1]), z_last));
+        constraint(fmul(fsub(fsub(nv[1], lv[0]), lv[1]), z_last));
+        const u64 denominator_inv = zh_inv[i_start % rate];
+        for (size_t j = 0; j < n_alphas; j++) quotient_values[i_start * n_alphas + j] = fmul(acc[j], denominator_inv);
+    }
+    for (size_t j = 0; j < n_alphas; j++) {  // transpose + coset_ifft
+        u64* col = out + j * size;
+        for (size_t i = 0; i < size; i++) col[i] = quotient_values[i * n_alphas + j];
+        coset_ifft(col, size, MULTIPLICATIVE_GROUP_GENERATOR);
+        for (size_t i = 0; i < size; i++) col[i] = canon(col[i]);
+    }
+    return 0;
+}
+
 void glo_eval_poly_base_at_ext(const uint64_t* coeffs, size_t n, const uint64_t z[2], uint64_t out[2]) {
     E2 zz{z[0], z[1]}, acc = e2(0);
     for (size_t k = n; k-- > 0;) acc = eadd(emul(acc, zz), e2(coeffs[k]));

@@ -164,6 +164,12 @@ int glo_partial_products_and_zs(const uint64_t* wires, const uint64_t* sigmas, c
                                 uint32_t log_n, uint32_t num_routed, uint64_t beta, uint64_t gamma,
                                 uint32_t degree, uint64_t* out);
 
+/* ---- "next" row: compute_quotient_polys of starky for FibonacciStark
+ *      (starky/src/prover.rs:488-668, starky/src/fibonacci_stark.rs:73-95). trace: a 2-column commitment; pi = (x0, x1,
+ *      result); out = n_alphas polynomials of (n << quotient_degree_bits) coefficients. Returns 0 on success. */
+int glo_stark_quotient_fibonacci(const glo_commit* trace, const uint64_t pi[3], const uint64_t* alphas,
+                                 size_t n_alphas, uint64_t* out);
+
 /* polynomial evaluation helper for the verifier test: f(z) for base coeffs, z in F_{p^2} */
 void glo_eval_poly_base_at_ext(const uint64_t* coeffs, size_t n, const uint64_t z[2], uint64_t out[2]);
 

@@ -13,3 +13,5 @@ from .fri import (FriBatchInfo, FriConfig, FriInstanceInfo, FriOracleInfo, FriPa
 from .hash import (MerkleCap, MerkleProof, MerkleTree, PoseidonHash, PoseidonPermutation,  # noqa: F401
                    verify_merkle_proof_to_cap)
 from .polynomial_batch import SALT_SIZE, PolynomialBatch  # noqa: F401
+from .proof import OpeningSet, StarkOpeningSet, eval_commitments  # noqa: F401
+from .stark import FibonacciStark, Stark, commit_quotient_polys, compute_quotient_polys  # noqa: F401

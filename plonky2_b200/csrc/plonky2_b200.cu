@@ -915,25 +915,42 @@ struct PPParams {
     const u64 *wires, *sigmas, *k_is;
     size_t n;
     uint32_t log_n, num_routed, degree, num_chunks;
-    u64 beta, gamma, omega;
-    u64* seq;            // n * num_chunks chunk products, row-major
-    unsigned int* flag;  // set when a denominator is zero
+    u64 beta, gamma;
+    const u64 *xhi, *xlo;  // subgroup element of row i: xhi[i >> 12] * xlo[i & 4095] (w_n^(4096*k), w_n^k)
+    u64* seq;              // n * num_chunks chunk products, row-major
+    unsigned int* flag;    // set when a denominator is zero
 };
+constexpr int PP_MAX_CHUNKS = 32;
+// One thread per row: the num_chunks chunk denominators of the row are inverted TOGETHER (Montgomery's trick, the
+// reference's F::batch_multiplicative_inverse per row, field/src/types.rs:133-223 / prover.rs:421): one field inversion
+// and 3 multiplies per chunk instead of one 64-squaring inversion per chunk.
 __global__ void __launch_bounds__(128) k_pp_chunks(PPParams p) {
-    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= p.n * p.num_chunks) return;
-    const size_t m = g / p.n, i = g % p.n;  // consecutive threads -> consecutive rows: coalesced column reads
-    const u64 bx = mul(p.beta, gl::pow(p.omega, i));
-    u64 num = 1, den = 1;
-    const uint32_t j1 = min((uint32_t)((m + 1) * p.degree), p.num_routed);
-    for (uint32_t j = (uint32_t)(m * p.degree); j < j1; j++) {
-        const u64 w = p.wires[(size_t)j * p.n + i];
-        const u64 wg = add(w, p.gamma);
-        num = mul(num, add(wg, mul(bx, p.k_is[j])));
-        den = mul(den, add(wg, mul(p.beta, p.sigmas[(size_t)j * p.n + i])));
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const u64 bx = mul(p.beta, mul(p.xhi[i >> 12], p.xlo[i & 4095]));
+    u64 num[PP_MAX_CHUNKS], den[PP_MAX_CHUNKS], pre[PP_MAX_CHUNKS];  // pre[m] = den_0 * ... * den_m
+    u64 run = 1;
+    for (uint32_t m = 0; m < p.num_chunks; m++) {
+        u64 nm = 1, dn = 1;
+        const uint32_t j1 = min((m + 1) * p.degree, p.num_routed);
+        for (uint32_t j = m * p.degree; j < j1; j++) {  // consecutive threads -> consecutive rows: coalesced column reads
+            const u64 w = p.wires[(size_t)j * p.n + i];
+            const u64 wg = add(w, p.gamma);
+            nm = mul(nm, add(wg, mul(bx, p.k_is[j])));
+            dn = mul(dn, add(wg, mul(p.beta, p.sigmas[(size_t)j * p.n + i])));
+        }
+        if (canon(dn) == 0) atomicOr(p.flag, 1u);
+        num[m] = nm;
+        den[m] = dn;
+        run = mul(run, dn);
+        pre[m] = run;
     }
-    if (canon(den) == 0) atomicOr(p.flag, 1u);
-    p.seq[i * p.num_chunks + m] = mul(num, gl::inv(den));
+    u64 inv_run = gl::inv(run);  // 1 / (den_0 ... den_{M-1})
+    for (uint32_t m = p.num_chunks; m-- > 0;) {  // 1/den_m = inv_run * pre[m-1], then inv_run *= den_m
+        const u64 dinv = m ? mul(inv_run, pre[m - 1]) : inv_run;
+        p.seq[i * p.num_chunks + m] = mul(num[m], dinv);
+        inv_run = mul(inv_run, den[m]);
+    }
 }
 // multiplicative inclusive prefix scan, 3 phases
 __global__ void __launch_bounds__(SCAN_THREADS) k_mscan_phase1(const u64* seq, size_t L, u64* chunk_tot) {
@@ -1008,6 +1025,82 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_mscan_phase3(const u64* seq, s
         else if (i + 1 < n) out[(size_t)(M - 1) * n + i + 1] = acc;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) out[(size_t)(M - 1) * n] = 1;
+}
+
+// ---- STARK quotient evaluation (compute_quotient_polys, starky/src/prover.rs:488-668) ----
+// The constraints (Stark::eval_packed_generic, starky/src/stark.rs) arrive as a small straight-line program over the
+// local row, the next row and the public inputs; value k = result of instruction k. One thread per point of the
+// quotient coset g*<w_size>, size = n << quotient_degree_bits, reading the trace LDE in place (column-major leaves):
+//   local = leaf bitrev(i*step), next = leaf bitrev(((i + next_step) % size) * step)      (get_lde_values, oracle.rs:142-147)
+struct StarkQuotientParams {
+    const u64* lde;        // trace LDE, column k at lde + k*lde_stride, leaf order
+    size_t lde_stride;
+    uint32_t log_N;        // log2 of the LDE size
+    uint32_t degree_bits, qd_bits;
+    const gl_stark_instr* prog;
+    uint32_t n_instr;
+    const u64* consts;     // public inputs first, then the program's constants
+    u64 alphas[GL_STARK_MAX_ALPHAS];
+    uint32_t n_alphas;
+    const u64 *xhi, *xlo;  // w_size^i = xhi[i >> 12] * xlo[i & 4095]
+    u64 shift;             // coset shift g
+    u64 last;              // w_n^-1, the last element of the trace subgroup
+    u64 n_field;           // n as a field element
+    u64 zh[GL_STARK_MAX_QD], zh_inv[GL_STARK_MAX_QD];  // Z_H on the coset: g^n * w_{2^qd}^j - 1 and inverses (ZeroPolyOnCoset)
+    u64* out;              // n_alphas columns of `size` values
+    unsigned int* flag;
+};
+__global__ void __launch_bounds__(128) k_stark_quotient(StarkQuotientParams p) {
+    const size_t size = (size_t)1 << (p.degree_bits + p.qd_bits);
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= size) return;
+    const uint32_t step_log = p.log_N - p.degree_bits - p.qd_bits;   // step = 2^(rate_bits - qd_bits)
+    const size_t inext = (i + ((size_t)1 << p.qd_bits)) & (size - 1);
+    const size_t jl = (size_t)(__brevll((unsigned long long)(i << step_log)) >> (64 - p.log_N));
+    const size_t jn = (size_t)(__brevll((unsigned long long)(inext << step_log)) >> (64 - p.log_N));
+    const u64 x = mul(p.shift, mul(p.xhi[i >> 12], p.xlo[i & 4095]));
+    const u64 z_last = sub(x, p.last);
+    const u64 zh = p.zh[i & (((size_t)1 << p.qd_bits) - 1)];
+    // Lagrange selectors on the coset (PolynomialValues::selector(..).lde_onto_coset, prover.rs:527-531) in closed form:
+    // L_0(x) = Z_H(x) / (n (x - 1)),  L_{n-1}(x) = Z_H(x) * last / (n (x - last)); one inversion for both
+    const u64 xm1 = sub(x, 1);
+    const u64 den = mul(p.n_field, mul(xm1, z_last));
+    if (canon(den) == 0) atomicOr(p.flag, 1u);
+    const u64 t = mul(zh, gl::inv(den));
+    const u64 l_first = mul(t, z_last);
+    const u64 l_last = mul(mul(t, p.last), xm1);
+    u64 acc[GL_STARK_MAX_ALPHAS];
+#pragma unroll
+    for (int a = 0; a < GL_STARK_MAX_ALPHAS; a++) acc[a] = 0;
+    u64 v[GL_STARK_MAX_INSTR];
+    for (uint32_t k = 0; k < p.n_instr; k++) {
+        const gl_stark_instr in = p.prog[k];
+        u64 r = 0;
+        switch (in.op) {
+            case GL_STARK_LOCAL: r = p.lde[(size_t)in.a * p.lde_stride + jl]; break;
+            case GL_STARK_NEXT: r = p.lde[(size_t)in.a * p.lde_stride + jn]; break;
+            case GL_STARK_CONST: r = p.consts[in.a]; break;
+            case GL_STARK_ADD: r = add(v[in.a], v[in.b]); break;
+            case GL_STARK_SUB: r = sub(v[in.a], v[in.b]); break;
+            case GL_STARK_MUL: r = mul(v[in.a], v[in.b]); break;
+            default: {  // GL_STARK_EMIT: ConstraintConsumer::constraint* (constraint_consumer.rs:60-84)
+                u64 c = v[in.a];
+                if (in.b == GL_STARK_TRANSITION) c = mul(c, z_last);
+                else if (in.b == GL_STARK_FIRST_ROW) c = mul(c, l_first);
+                else if (in.b == GL_STARK_LAST_ROW) c = mul(c, l_last);
+                for (uint32_t a = 0; a < p.n_alphas; a++) acc[a] = add(mul(acc[a], p.alphas[a]), c);
+            }
+        }
+        v[k] = r;
+    }
+    const u64 zi = p.zh_inv[i & (((size_t)1 << p.qd_bits) - 1)];
+    for (uint32_t a = 0; a < p.n_alphas; a++) p.out[(size_t)a * size + i] = canon(mul(acc[a], zi));
+}
+// any non-zero word in [begin, begin + count) of each of `cols` columns (stride `stride`) -> flag
+__global__ void k_any_nonzero(const u64* data, size_t stride, size_t begin, size_t count, unsigned int* flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    if (canon(data[(size_t)blockIdx.y * stride + begin + i]) != 0) atomicOr(flag, 2u);
 }
 
 // proof-of-work grind (prover.rs:183-194): smallest qualifying nonce via atomicMin
@@ -1445,6 +1538,61 @@ int gl_commit_eval_ext(gl_commit* c, const uint64_t point[2], uint64_t* out) {
     dfree(ctx, dout);
     return rc;
 }
+// OpeningSet::new / StarkOpeningSet::new (plonk/proof.rs:313-351, starky/src/proof.rs:221-260) in ONE call: every
+// polynomial of commits[i] evaluated at points[point_index[i]], results concatenated in request order, one D2H.
+int gl_openings(gl_ctx* ctx, gl_commit* const* commits, const uint32_t* point_index, size_t n_evals, const uint64_t* points,
+                size_t n_points, uint64_t* out, int mem) {
+    if (!ctx || !commits || !point_index || !points || !out) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
+    if (n_evals == 0) return GL_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    uint32_t max_log = 0;
+    size_t total = 0;
+    for (size_t i = 0; i < n_evals; i++) {
+        if (!commits[i] || commits[i]->ctx->device != ctx->device) return set_err(ctx, GL_ERR_BAD_ARG, "bad commitment %zu", i);
+        if (point_index[i] >= n_points) return set_err(ctx, GL_ERR_BAD_ARG, "point index %u out of range", point_index[i]);
+        if (commits[i]->degree_log > max_log) max_log = commits[i]->degree_log;
+        total += commits[i]->B;
+    }
+    const size_t n = (size_t)1 << max_log, hi_cnt = (n >> 12) + 1;
+    u64 *zhi = nullptr, *zlo = nullptr, *zt = nullptr, *dout = nullptr;
+    auto body = [&]() -> int {
+        TRY(dmalloc(ctx, &zhi, 2 * hi_cnt));
+        TRY(dmalloc(ctx, &zlo, 2 * 4096));
+        TRY(dmalloc(ctx, &zt, 2 * n));
+        if (mem == GL_MEM_HOST) TRY(dmalloc(ctx, &dout, 2 * total));
+        else dout = out;
+        for (size_t p = 0; p < n_points; p++) {  // one power table per distinct point, shared by every request at it
+            bool used = false;
+            for (size_t i = 0; i < n_evals; i++) used |= point_index[i] == p;
+            if (!used) continue;
+            const E2 z = {canon(points[2 * p]), canon(points[2 * p + 1])};
+            k_fill_e2_pows<<<(unsigned)((hi_cnt + 127) / 128), 128, 0, ctx->stream>>>(e2_pow(z, 4096), hi_cnt, zhi);
+            CKL(ctx);
+            k_fill_e2_pows<<<32, 128, 0, ctx->stream>>>(z, 4096, zlo);
+            CKL(ctx);
+            k_e2_pow_table<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(zhi, zlo, n, zt);
+            CKL(ctx);
+            size_t off = 0;
+            for (size_t i = 0; i < n_evals; i++) {
+                const gl_commit* c = commits[i];
+                if (point_index[i] == p) {
+                    const size_t nc = (size_t)1 << c->degree_log;
+                    k_eval_ext<<<c->B, 256, 0, ctx->stream>>>(c->coeffs, nc, nc, zt, dout + 2 * off);
+                    CKL(ctx);
+                }
+                off += c->B;
+            }
+        }
+        if (mem == GL_MEM_HOST) return d2h(ctx, out, dout, 2 * total);
+        return GL_OK;
+    };
+    int rc = body();
+    dfree(ctx, zhi);
+    dfree(ctx, zlo);
+    dfree(ctx, zt);
+    if (mem == GL_MEM_HOST) dfree(ctx, dout);
+    return rc;
+}
 const uint64_t* gl_commit_dev_lde(const gl_commit* c, size_t* col_stride) {
     if (col_stride) *col_stride = c->tree.es;
     return c->tree.leaves;
@@ -1456,11 +1604,14 @@ int gl_partial_products_and_zs(gl_ctx* ctx, const uint64_t* wires, const uint64_
                                uint64_t* out, int mem) {
     if (!ctx || !wires || !sigmas || !k_is || !out) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
     if (degree < 2 || num_routed == 0 || log_n > 26) return set_err(ctx, GL_ERR_BAD_SHAPE, "bad partial-product shape");
+    if ((num_routed + degree - 1) / degree > (uint32_t)PP_MAX_CHUNKS)
+        return set_err(ctx, GL_ERR_UNSUPPORTED, "more than %d partial-product chunks per row", PP_MAX_CHUNKS);
     CK(ctx, cudaSetDevice(ctx->device));
     const size_t n = (size_t)1 << log_n;
     const uint32_t M = (num_routed + degree - 1) / degree;
     const size_t L = n * M, nchunks = (L + SCAN_CHUNK - 1) / SCAN_CHUNK;
     u64 *dw = nullptr, *ds = nullptr, *dk = nullptr, *seq = nullptr, *tot = nullptr, *dout = nullptr, *dflag = nullptr;
+    u64* xtab = nullptr;
     auto body = [&]() -> int {
         const u64 *pw = wires, *ps = sigmas;
         if (mem == GL_MEM_HOST) {
@@ -1480,9 +1631,12 @@ int gl_partial_products_and_zs(gl_ctx* ctx, const uint64_t* wires, const uint64_
         TRY(dmalloc(ctx, &tot, nchunks));
         TRY(dmalloc(ctx, &dflag, 1));
         CK(ctx, cudaMemsetAsync(dflag, 0, 8, ctx->stream));
-        PPParams pp{pw, ps, dk, n, log_n, num_routed, degree, M, canon(beta), canon(gamma), root_of_unity(log_n), seq,
+        const u64 wn = root_of_unity(log_n);
+        const size_t tcnt = 4096 > (n >> 12) + 1 ? 4096 : (n >> 12) + 1;
+        TRY(build_pow_tables(ctx, std::vector<u64>{gl::pow(wn, 4096), wn}, tcnt, &xtab));
+        PPParams pp{pw, ps, dk, n, log_n, num_routed, degree, M, canon(beta), canon(gamma), xtab, xtab + tcnt, seq,
                     (unsigned int*)dflag};
-        k_pp_chunks<<<(unsigned)((L + 127) / 128), 128, 0, ctx->stream>>>(pp);
+        k_pp_chunks<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(pp);
         CKL(ctx);
         k_mscan_phase1<<<(unsigned)nchunks, SCAN_THREADS, 0, ctx->stream>>>(seq, L, tot);
         CKL(ctx);
@@ -1503,7 +1657,101 @@ int gl_partial_products_and_zs(gl_ctx* ctx, const uint64_t* wires, const uint64_
     dfree(ctx, seq);
     dfree(ctx, tot);
     dfree(ctx, dflag);
+    dfree(ctx, xtab);
     if (mem == GL_MEM_HOST) dfree(ctx, dout);
+    return rc;
+}
+
+int gl_stark_quotient(gl_ctx* ctx, gl_commit* trace, const gl_stark_instr* program, uint32_t n_instr,
+                      const uint64_t* consts, uint32_t n_consts, const uint64_t* alphas, uint32_t n_alphas,
+                      uint32_t quotient_degree_factor, uint64_t* out_coeffs) {
+    if (!ctx || !trace || !program || !alphas || !out_coeffs) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
+    if (n_instr == 0 || n_instr > GL_STARK_MAX_INSTR) return set_err(ctx, GL_ERR_UNSUPPORTED, "program of %u instructions (max %d)", n_instr, GL_STARK_MAX_INSTR);
+    if (n_alphas == 0 || n_alphas > GL_STARK_MAX_ALPHAS) return set_err(ctx, GL_ERR_UNSUPPORTED, "1..%d challenges", GL_STARK_MAX_ALPHAS);
+    if (quotient_degree_factor == 0) return set_err(ctx, GL_ERR_BAD_ARG, "quotient_degree_factor is 0: the STARK has no quotient");
+    if (trace->shard_log) return set_err(ctx, GL_ERR_UNSUPPORTED, "quotient evaluation needs the whole LDE on this device");
+    NEED_FINISHED(trace);
+    uint32_t qd_bits = 0;
+    while ((1u << qd_bits) < quotient_degree_factor) qd_bits++;  // log2_ceil
+    if (qd_bits > trace->rate_bits)
+        return set_err(ctx, GL_ERR_UNSUPPORTED, "Having constraints of degree higher than the rate is not supported yet.");
+    if ((1u << qd_bits) > GL_STARK_MAX_QD) return set_err(ctx, GL_ERR_UNSUPPORTED, "quotient degree factor too large");
+    for (uint32_t k = 0; k < n_instr; k++) {  // validate once on the host: the kernel trusts the program
+        const gl_stark_instr in = program[k];
+        bool ok = true;
+        switch (in.op) {
+            case GL_STARK_LOCAL: case GL_STARK_NEXT: ok = in.a < trace->B; break;
+            case GL_STARK_CONST: ok = in.a < n_consts; break;
+            case GL_STARK_ADD: case GL_STARK_SUB: case GL_STARK_MUL: ok = in.a < k && in.b < k; break;
+            case GL_STARK_EMIT: ok = in.a < k && in.b <= GL_STARK_LAST_ROW; break;
+            default: ok = false;
+        }
+        if (!ok) return set_err(ctx, GL_ERR_BAD_ARG, "constraint program: bad instruction %u", k);
+    }
+    CK(ctx, cudaSetDevice(ctx->device));
+    const uint32_t db = trace->degree_log, size_log = db + qd_bits;
+    const size_t size = (size_t)1 << size_log;
+    u64 *dprog = nullptr, *dconst = nullptr, *xtab = nullptr, *dflag = nullptr;
+    auto body = [&]() -> int {
+        const size_t prog_words = ((size_t)n_instr * sizeof(gl_stark_instr) + 7) / 8;
+        TRY(dmalloc(ctx, &dprog, prog_words));
+        CK(ctx, cudaMemcpyAsync(dprog, program, (size_t)n_instr * sizeof(gl_stark_instr), cudaMemcpyHostToDevice, ctx->stream));
+        TRY(dmalloc(ctx, &dconst, n_consts ? n_consts : 1));
+        if (n_consts) TRY(h2d(ctx, dconst, consts, n_consts));
+        TRY(dmalloc(ctx, &dflag, 1));
+        CK(ctx, cudaMemsetAsync(dflag, 0, 8, ctx->stream));
+        const u64 ws = root_of_unity(size_log);
+        const size_t tcnt = 4096 > (size >> 12) + 1 ? 4096 : (size >> 12) + 1;
+        TRY(build_pow_tables(ctx, std::vector<u64>{gl::pow(ws, 4096), ws}, tcnt, &xtab));
+        StarkQuotientParams p;
+        p.lde = trace->tree.leaves;
+        p.lde_stride = trace->tree.es;
+        p.log_N = db + trace->rate_bits;
+        p.degree_bits = db;
+        p.qd_bits = qd_bits;
+        p.prog = (const gl_stark_instr*)dprog;
+        p.n_instr = n_instr;
+        p.consts = dconst;
+        p.n_alphas = n_alphas;
+        for (uint32_t a = 0; a < GL_STARK_MAX_ALPHAS; a++) p.alphas[a] = a < n_alphas ? canon(alphas[a]) : 0;
+        p.xhi = xtab;
+        p.xlo = xtab + tcnt;
+        p.shift = MULTIPLICATIVE_GROUP_GENERATOR;
+        p.last = gl::inv(root_of_unity(db));
+        p.n_field = canon((u64)1 << db);
+        // ZeroPolyOnCoset::new(degree_bits, qd_bits) (field/src/zero_poly_coset.rs:20-34)
+        u64 g_pow_n = MULTIPLICATIVE_GROUP_GENERATOR;
+        for (uint32_t k = 0; k < db; k++) g_pow_n = sqr(g_pow_n);
+        const u64 wq = root_of_unity(qd_bits);
+        u64 xq = 1;
+        for (uint32_t j = 0; j < (1u << qd_bits); j++, xq = mul(xq, wq)) {
+            p.zh[j] = canon(sub(mul(g_pow_n, xq), 1));
+            p.zh_inv[j] = canon(gl::inv(p.zh[j]));
+        }
+        p.out = out_coeffs;
+        p.flag = (unsigned int*)dflag;
+        k_stark_quotient<<<(unsigned)((size + 127) / 128), 128, 0, ctx->stream>>>(p);
+        CKL(ctx);
+        // .coset_ifft(F::coset_shift()) of every challenge's values (prover.rs:661-667)
+        TRY(ntt_natural(ctx, out_coeffs, size, out_coeffs, size, (int)size_log, n_alphas, true, MULTIPLICATIVE_GROUP_GENERATOR));
+        // trim_to_len(degree * quotient_degree_factor) (prover.rs:396-401): the rest must vanish
+        const size_t keep = ((size_t)quotient_degree_factor) << db;
+        if (keep < size) {
+            k_any_nonzero<<<dim3((unsigned)((size - keep + 255) / 256), n_alphas), 256, 0, ctx->stream>>>(out_coeffs, size, keep,
+                                                                                                   size - keep, (unsigned int*)dflag);
+            CKL(ctx);
+        }
+        u64 flag = 0;
+        TRY(d2h(ctx, &flag, dflag, 1));
+        if (flag & 1u) return set_err(ctx, GL_ERR_DIV_ZERO, "Tried to invert zero");
+        if (flag & 2u) return set_err(ctx, GL_ERR_BAD_ARG, "Quotient has failed, the vanishing polynomial is not divisible by Z_H");
+        return GL_OK;
+    };
+    int rc = body();
+    dfree(ctx, dprog);
+    dfree(ctx, dconst);
+    dfree(ctx, xtab);
+    dfree(ctx, dflag);
     return rc;
 }
 

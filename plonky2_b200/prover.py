@@ -23,3 +23,51 @@ def wires_permutation_partial_products_and_zs(wires, sigmas, k_is, beta, gamma, 
                                             int(beta), int(gamma), int(degree), N.np_ptr(out), N.MEM_HOST)
     N.check(rc, ctx.h)   # GL_ERR_DIV_ZERO -> ZeroDivisionError ("Tried to invert zero"), others keep their own type
     return out
+
+
+def commit_zs_partial_products(wires_dev, sigmas_dev, k_is, betas, gammas, degree, rate_bits, cap_height, ctx=None):
+    """The second commitment of prove() without leaving the device (prover.rs:220-254):
+    all_wires_permutation_partial_products for every challenge pair (beta_i, gamma_i) -> Z's moved to the front
+    (`[plonk_z_vecs, partial_products.concat()].concat()`) -> PolynomialBatch::from_values.
+
+    wires_dev, sigmas_dev: torch int64 CUDA tensors of shape (num_routed, n) -- the routed wire columns (the same
+    device matrix the wires commitment was built from) and the sigma value columns (resident since circuit build).
+    Each gl_partial_products_and_zs call writes its columns straight into a device staging matrix; each column group is
+    then handed to the incremental commitment (gl_commit_add_columns, GL_MEM_DEVICE): no H2D, no D2H.
+    The caller's tensors must be complete (their producing stream synchronised or ordered before ctx's stream).
+    Returns the PolynomialBatch (num_challenges * (num_partial_products + 1) polynomials)."""
+    import ctypes as C
+
+    import torch
+
+    from .polynomial_batch import PolynomialBatch
+
+    ctx = ctx or N.default_context()
+    R, n = wires_dev.shape
+    if sigmas_dev.shape != (R, n) or len(k_is) != R or len(betas) != len(gammas):
+        raise N.ShapeError("wires, sigmas must be (num_routed, n), k_is (num_routed,), betas/gammas equally long")
+    log_n = log2_strict(n)
+    k_is = np.ascontiguousarray(k_is, dtype=np.uint64)
+    nch = len(betas)
+    M = (R + degree - 1) // degree          # columns per challenge: M - 1 partial products, then Z
+    B = nch * M
+    L = N.lib()
+    h = N.vp()
+    N.check(L.gl_commit_begin(ctx.h, B, log_n, rate_bits, cap_height, 0, 0, 1, None, C.byref(h)), ctx.h)
+    try:
+        stage = torch.empty((M, n), dtype=torch.int64, device=wires_dev.device)
+        for i in range(nch):
+            N.check(L.gl_partial_products_and_zs(ctx.h, N.vp(wires_dev.data_ptr()), N.vp(sigmas_dev.data_ptr()),
+                                                 N.np_ptr(k_is), log_n, R, int(betas[i]), int(gammas[i]), int(degree),
+                                                 N.vp(stage.data_ptr()), N.MEM_DEVICE), ctx.h)
+            # Z (last column of the call) is polynomial i; the partial products follow all Z's
+            N.check(L.gl_commit_add_columns(h, i, 1, N.vp(stage[M - 1].data_ptr()), n, N.COLS_VALUES, N.MEM_DEVICE), ctx.h)
+            if M > 1:
+                N.check(L.gl_commit_add_columns(h, nch + i * (M - 1), M - 1, N.vp(stage.data_ptr()), n, N.COLS_VALUES,
+                                                N.MEM_DEVICE), ctx.h)
+        N.check(L.gl_commit_finish(h, None, N.MEM_DEVICE), ctx.h)
+        ctx.synchronize()  # the staging matrix (a torch allocation) must outlive the library's stream-ordered reads
+    except Exception:
+        L.gl_commit_destroy(h)
+        raise
+    return PolynomialBatch(h, ctx, B, log_n, rate_bits, cap_height, False)

@@ -121,6 +121,8 @@ def lib():
                                        C.c_size_t, C.POINTER(FriBatch), C.c_size_t, u64p, C.c_uint32,
                                        C.c_void_p, C.POINTER(FriParams), C.POINTER(C.c_uint8), C.c_size_t]
     L.glo_eval_poly_base_at_ext.argtypes = [u64p, C.c_size_t, u64p, u64p]
+    L.glo_stark_quotient_fibonacci.restype = C.c_int
+    L.glo_stark_quotient_fibonacci.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t, u64p]
     L.glo_partial_products_and_zs.restype = C.c_int
     L.glo_partial_products_and_zs.argtypes = [u64p, u64p, u64p, C.c_uint32, C.c_uint32, u64, u64, C.c_uint32, u64p]
     _lib = L
@@ -429,4 +431,16 @@ def partial_products_and_zs(wires, sigmas, k_is, beta, gamma, degree):
                                            int(gamma), degree, ptr(out))
     if rc != 0:
         raise ZeroDivisionError("Tried to invert zero")
+    return out
+
+
+def stark_quotient_fibonacci(trace_commit, public_inputs, alphas):
+    """compute_quotient_polys for FibonacciStark on an oracle Commit of the 2-column trace: (num_alphas, size) coeffs."""
+    pi = np.array([int(x) for x in public_inputs], dtype=np.uint64)
+    al = np.array([int(x) for x in alphas], dtype=np.uint64)
+    size = trace_commit.n  # quotient_degree_factor = 1
+    out = np.zeros((len(al), size), dtype=np.uint64)
+    rc = lib().glo_stark_quotient_fibonacci(trace_commit.h, ptr(pi), ptr(al), len(al), ptr(out))
+    if rc != 0:
+        raise RuntimeError("oracle stark quotient rc=%d" % rc)
     return out

@@ -718,3 +718,223 @@ def test_incremental_commit_matches_oracle(pb, oracle, external):
         assert L.gl_commit_finish(hnd, None, N.MEM_HOST) != 0  # already finished
     finally:
         L.gl_commit_destroy(hnd)
+
+
+def test_opening_set_one_call_matches_oracle(pb, oracle):
+    """OpeningSet::new (proof.rs:313-351) through gl_openings: four commitments, zeta and g*zeta, one native call;
+    every value equals the oracle's Horner evaluation of the oracle's coefficients."""
+    log_n, r, h = 9, 3, 2
+    n = 1 << log_n
+    Bs = [9, 7, 6, 4]  # constants+sigmas, wires, zs+partial products(+lookup), quotient
+    data = [synth(0xB0 + i, (B, n)) for i, B in enumerate(Bs)]
+    batches = [pb.PolynomialBatch.from_values(d, r, False, h) for d in data[:3]] + [pb.PolynomialBatch.from_coeffs(data[3], r, False, h)]
+    ocoeffs = [oracle.Commit(d, r, h).coeffs for d in data[:3]] + [data[3]]
+    zeta = (int(synth(0xB7, (1,))[0]), int(synth(0xB8, (1,))[0]))
+    g = pb.field.primitive_root_of_unity(log_n)
+    gz = pb.field.ext_mul((g, 0), zeta)
+    os_ = pb.OpeningSet.new(zeta, g, batches[0], batches[1], batches[2], batches[3], constants_range=range(0, 4),
+                            sigmas_range=range(4, 9), zs_range=range(0, 2), partial_products_range=range(2, 5),
+                            lookup_range=range(5, 6))
+
+    def ev(co, z):
+        return np.array([oracle.eval_poly_base_at_ext(c, z) for c in co], dtype=np.uint64)
+
+    assert np.array_equal(os_.constants, ev(ocoeffs[0][0:4], zeta))
+    assert np.array_equal(os_.plonk_sigmas, ev(ocoeffs[0][4:9], zeta))
+    assert np.array_equal(os_.wires, ev(ocoeffs[1], zeta))
+    assert np.array_equal(os_.plonk_zs, ev(ocoeffs[2][0:2], zeta))
+    assert np.array_equal(os_.plonk_zs_next, ev(ocoeffs[2][0:2], gz))
+    assert np.array_equal(os_.partial_products, ev(ocoeffs[2][2:5], zeta))
+    assert np.array_equal(os_.lookup_zs, ev(ocoeffs[2][5:6], zeta))
+    assert np.array_equal(os_.lookup_zs_next, ev(ocoeffs[2][5:6], gz))
+    assert np.array_equal(os_.quotient_polys, ev(ocoeffs[3], zeta))
+    zb, nb = os_.to_fri_openings()
+    assert zb.shape == (9 + 7 + 5 + 4 + 1, 2) and nb.shape == (3, 2)
+    so = pb.StarkOpeningSet.new(zeta, g, batches[1], None, batches[3])
+    assert np.array_equal(so.local_values, ev(ocoeffs[1], zeta)) and np.array_equal(so.next_values, ev(ocoeffs[1], gz))
+    assert np.array_equal(so.quotient_polys, ev(ocoeffs[3], zeta))
+    for b in batches:
+        b.close()
+
+
+def test_zs_partial_products_commit_stays_on_device(pb, oracle):
+    """prover.rs:220-254 chained on the device: wires (device) -> partial products / Z per challenge -> Z's first ->
+    from_values, compared with the oracle's partial_products_and_zs + Commit on the host-assembled columns."""
+    import torch
+
+    from plonky2_b200.prover import commit_zs_partial_products
+
+    R, log_n, deg, r, h = 20, 10, 8, 3, 4
+    n = 1 << log_n
+    w = synth(0xC1, (R, n))
+    sg = synth(0xC2, (R, n))
+    k = synth(0xC3, (R,))
+    betas, gammas = [int(x) for x in synth(0xC4, (2,))], [int(x) for x in synth(0xC5, (2,))]
+    wd = torch.from_numpy(w.view(np.int64).copy()).cuda()
+    sd = torch.from_numpy(sg.view(np.int64).copy()).cuda()
+    torch.cuda.synchronize()
+    batch = commit_zs_partial_products(wd, sd, k, betas, gammas, deg, r, h)
+    per = [oracle.partial_products_and_zs(w, sg, k, betas[i], gammas[i], deg) for i in range(2)]  # pp..., Z
+    cols = np.concatenate([np.stack([p[-1] for p in per])] + [p[:-1] for p in per])                # Z's first
+    o = oracle.Commit(cols, r, h)
+    assert batch.num_polys == cols.shape[0] == 2 * 3
+    assert np.array_equal(batch.merkle_tree.cap.hashes, o.cap)
+    assert np.array_equal(batch.polynomials, o.coeffs)
+    batch.close()
+
+
+# ----------------------------------------------------------------------------- SURVEY 8(f) row 1: STARK quotient on the device
+@pytest.mark.parametrize("log_n,r,num_alphas", [(5, 1, 1), (10, 1, 2), (13, 2, 2)])
+def test_stark_quotient_fibonacci_matches_oracle(pb, oracle, log_n, r, num_alphas):
+    """compute_quotient_polys (starky/src/prover.rs:488-668) for FibonacciStark: constraint program evaluated on the
+    device over the trace LDE in place, bit for bit equal to the oracle's restatement; then the quotient commitment
+    (prover.rs:391-421) equals from_coeffs of the oracle's chunks."""
+    h = 2
+    n = 1 << log_n
+    stark = pb.FibonacciStark(n)
+    trace = stark.generate_trace(7, 11)
+    pi = [7, 11, int(trace[1, n - 1])]
+    alphas = [int(x) for x in synth(0xE0 + log_n, (num_alphas,))]
+    tc = pb.PolynomialBatch.from_values(trace, r, False, h)
+    q = pb.compute_quotient_polys(stark, tc, pi, alphas)
+    want = oracle.stark_quotient_fibonacci(oracle.Commit(trace, r, h), pi, alphas)
+    got = q.cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, want)
+    qc = pb.commit_quotient_polys(stark, q, log_n, r, h)
+    oq = oracle.Commit(want, r, h, is_coeffs=True)   # quotient_degree_factor = 1: one chunk per challenge
+    assert np.array_equal(qc.merkle_tree.cap.hashes, oq.cap)
+    assert np.array_equal(qc.polynomials, want)
+    tc.close()
+    qc.close()
+
+
+def test_stark_quotient_generic_program_higher_degree(pb):
+    """The constraint program is generic: a toy STARK with products (declared constraint degree 4: quotient_degree_factor
+    3, coset of size 4n, three chunks per challenge) checked by the verifier's identity (starky/src/verifier.rs:150-190)
+    at a random point, and rejected ("Quotient has failed", prover.rs:396-401) when the trace is wrong."""
+    from plonky2_b200 import NativeError
+    from plonky2_b200.stark import Stark
+
+    P_ = int(P)
+
+    class CubicStark(Stark):
+        COLUMNS, PUBLIC_INPUTS = 2, 1
+
+        def eval(self, v, y):
+            a, b = v.local(0), v.local(1)
+            y.constraint_first_row(a - v.public_input(0))
+            y.constraint_transition(v.next(0) - (a * a * b + 1))     # a' = a^2 b + 1
+            y.constraint_transition(v.next(1) - (b + a * 3))          # b' = b + 3a
+            y.constraint(a * 0)                                       # an unfiltered (trivially satisfied) constraint
+
+        def constraint_degree(self):
+            return 4   # an upper bound is allowed: the quotient then has zero top chunks, which trim_to_len checks
+
+    log_n, r, h = 8, 2, 1
+    n = 1 << log_n
+    tr = np.empty((2, n), dtype=np.uint64)
+    a, b = 5, 9
+    for i in range(n):
+        tr[0, i], tr[1, i] = a, b
+        a, b = (a * a * b + 1) % P_, (b + 3 * a) % P_
+    stark = CubicStark()
+    assert stark.quotient_degree_factor() == 3
+    alphas = [int(x) for x in synth(0xE9, (2,))]
+    tc = pb.PolynomialBatch.from_values(tr, r, False, h)
+    q = pb.compute_quotient_polys(stark, tc, [5], alphas).cpu().numpy().view(np.uint64)
+    assert q.shape == (2, 4 * n) and not q[:, 3 * n:].any()
+    coeffs = tc.polynomials
+    z = int(synth(0xEA, (1,))[0])
+    w = pb.field.primitive_root_of_unity(log_n)
+    last = pow(w, P_ - 2, P_)
+
+    def ev(c, x):
+        acc = 0
+        for v in c[::-1]:
+            acc = (acc * x + int(v)) % P_
+        return acc
+
+    la, lb = ev(coeffs[0], z), ev(coeffs[1], z)
+    na, nb = ev(coeffs[0], z * w % P_), ev(coeffs[1], z * w % P_)
+    zh = (pow(z, n, P_) - 1) % P_
+    l_first = zh * pow(n * (z - 1) % P_, P_ - 2, P_) % P_
+    z_last = (z - last) % P_
+    cons = [(la - 5) * l_first, (na - (la * la * lb + 1)) * z_last, (nb - (lb + 3 * la)) * z_last, 0]
+    for j, al in enumerate(alphas):
+        acc = 0
+        for c in cons:
+            acc = (acc * al + c) % P_
+        assert acc == zh * ev(q[j], z) % P_
+    qc = pb.commit_quotient_polys(stark, pb.compute_quotient_polys(stark, tc, [5], alphas), log_n, r, h)
+    assert qc.num_polys == 6 and np.array_equal(qc.polynomials, q[:, :3 * n].reshape(6, n))   # 3 chunks of n per challenge
+    qc.close()
+    tc.close()
+    tr[1, n // 2] ^= np.uint64(1)   # one wrong cell: the vanishing polynomial is no longer divisible by Z_H
+    tb = pb.PolynomialBatch.from_values(tr, r, False, h)
+    with pytest.raises(NativeError, match="Quotient has failed"):
+        pb.compute_quotient_polys(stark, tb, [5], alphas)
+    tb.close()
+
+
+def test_stark_prove_pipeline_on_device(pb, oracle):
+    """The starky prover's commitment path end to end on the device (starky/src/prover.rs:83-94,391-470): trace
+    commitment -> quotient polynomials from the LDE in place -> quotient commitment -> StarkOpeningSet (one call) ->
+    prove_openings; the FRI proof is accepted by the restated verifier with exactly those openings."""
+    log_n, r, h = 10, 1, 4
+    n = 1 << log_n
+    stark = pb.FibonacciStark(n)
+    trace = stark.generate_trace(1, 1)
+    pi = [1, 1, int(trace[1, n - 1])]
+    cfg = pb.starky_standard_fast_fri_config()
+    params = cfg.fri_params(log_n, False)
+    ch, och = pb.Challenger(), oracle.Challenger()
+    tc = pb.PolynomialBatch.from_values(trace, r, False, h)
+    ch.observe_cap(tc.merkle_tree.cap)
+    alphas = ch.get_n_challenges(2)
+    q = pb.compute_quotient_polys(stark, tc, pi, alphas)
+    qc = pb.commit_quotient_polys(stark, q, log_n, r, h)
+    ch.observe_cap(qc.merkle_tree.cap)
+    zeta = ch.get_extension_challenge()
+    g = pb.field.primitive_root_of_unity(log_n)
+    openings = pb.StarkOpeningSet.new(zeta, g, tc, None, qc)
+    zb, nb = openings.to_fri_openings()
+    for batch in (zb, nb):
+        ch.observe_elements(batch.reshape(-1))
+    gz = pb.field.ext_mul((g, 0), zeta)
+    inst = pb.FriInstanceInfo([pb.FriOracleInfo(2, False), pb.FriOracleInfo(2, False)],
+                              [pb.FriBatchInfo(zeta, [pb.FriPolynomialInfo(0, 0), pb.FriPolynomialInfo(0, 1),
+                                                      pb.FriPolynomialInfo(1, 0), pb.FriPolynomialInfo(1, 1)]),
+                               pb.FriBatchInfo(gz, [pb.FriPolynomialInfo(0, 0), pb.FriPolynomialInfo(0, 1)])])
+    # the oracle verifier replays the transcript from the same state
+    och.observe_cap(tc.merkle_tree.cap.hashes)
+    assert och.get_n_challenges(2) == alphas
+    och.observe_cap(qc.merkle_tree.cap.hashes)
+    assert och.get_extension_challenge() == zeta
+    for batch in (zb, nb):
+        och.observe_elements(batch.reshape(-1))
+    proof = pb.prove_openings(inst, [tc, qc], ch, params)
+    obatches = [(b.point, [(p.oracle_index, p.polynomial_index) for p in b.polynomials]) for b in inst.batches]
+    oparams = oracle.make_params(r, h, cfg.proof_of_work_bits, cfg.num_query_rounds, params.reduction_arity_bits)
+    rc = oracle.verify_fri_proof([tc.merkle_tree.cap.hashes, qc.merkle_tree.cap.hashes], [2, 2], [2, 2], obatches,
+                                 np.concatenate([zb.reshape(-1), nb.reshape(-1)]), log_n, och, oparams, proof.to_bytes())
+    assert rc == 0
+    # the verifier's quotient identity at zeta (starky/src/verifier.rs:150-190) with the opened values, in F_{p^2}
+    E = pb.field
+    lv, nv, qv = [tuple(int(x) for x in v) for v in openings.local_values], [tuple(int(x) for x in v) for v in openings.next_values], \
+        [tuple(int(x) for x in v) for v in openings.quotient_polys]
+    zn = E.ext_pow(zeta, n)
+    zh = E.ext_sub(zn, (1, 0))
+    last = pow(g, int(P) - 2, int(P))
+    l_first = E.ext_mul(zh, E.ext_inverse(E.ext_mul((n, 0), E.ext_sub(zeta, (1, 0)))))
+    l_last = E.ext_mul(E.ext_mul(zh, (last, 0)), E.ext_inverse(E.ext_mul((n, 0), E.ext_sub(zeta, (last, 0)))))
+    z_last = E.ext_sub(zeta, (last, 0))
+    cons = [E.ext_mul(E.ext_sub(lv[0], (pi[0], 0)), l_first), E.ext_mul(E.ext_sub(lv[1], (pi[1], 0)), l_first),
+            E.ext_mul(E.ext_sub(lv[1], (pi[2], 0)), l_last), E.ext_mul(E.ext_sub(nv[0], lv[1]), z_last),
+            E.ext_mul(E.ext_sub(E.ext_sub(nv[1], lv[0]), lv[1]), z_last)]
+    for j, al in enumerate(alphas):
+        acc = (0, 0)
+        for c in cons:
+            acc = E.ext_add(E.ext_mul(acc, (al, 0)), c)
+        assert acc == E.ext_mul(zh, qv[j])
+    tc.close()
+    qc.close()

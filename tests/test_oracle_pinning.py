@@ -220,3 +220,50 @@ def test_challenger_semantics(oracle):
     assert got == st[:8][::-1].tolist()
     nxt = oracle.poseidon(st)
     assert ch.get_challenge() == int(nxt[7])
+
+
+def test_stark_quotient_fibonacci_satisfies_the_verifier_identity(oracle):
+    """The oracle's compute_quotient_polys restatement (starky/src/prover.rs:488-668) is pinned by the verifier's own
+    check (starky/src/verifier.rs:150-190): at a random point z, sum_k alpha^.. C_k(z) == Z_H(z) * q(z)."""
+    import plonky2_b200 as pb
+
+    P_ = int(P)
+    log_n, r, h = 7, 1, 0
+    n = 1 << log_n
+    stark = pb.FibonacciStark(n)
+    trace = stark.generate_trace(3, 5)
+    pi = [3, 5, int(trace[1, n - 1])]
+    alphas = [int(x) for x in synth(0xD1, (2,))]
+    tc = oracle.Commit(trace, r, h)
+    q = oracle.stark_quotient_fibonacci(tc, pi, alphas)
+    assert q.shape == (2, n)
+    coeffs = tc.coeffs
+    z = int(synth(0xD2, (1,))[0])
+    w = pb.field.primitive_root_of_unity(log_n)
+    last = pow(w, P_ - 2, P_)
+
+    def ev(c, x):
+        acc = 0
+        for v in c[::-1]:
+            acc = (acc * x + int(v)) % P_
+        return acc
+
+    l = [ev(coeffs[k], z) for k in range(2)]
+    nx = [ev(coeffs[k], z * w % P_) for k in range(2)]
+    zh = (pow(z, n, P_) - 1) % P_
+    l_first = zh * pow(n * (z - 1) % P_, P_ - 2, P_) % P_
+    l_last = zh * last % P_ * pow(n * (z - last) % P_, P_ - 2, P_) % P_
+    z_last = (z - last) % P_
+    cons = [(l[0] - pi[0]) * l_first, (l[1] - pi[1]) * l_first, (l[1] - pi[2]) * l_last, (nx[0] - l[1]) * z_last,
+            (nx[1] - l[0] - l[1]) * z_last]
+    for j, a in enumerate(alphas):
+        acc = 0
+        for c in cons:
+            acc = (acc * a + c) % P_
+        assert acc == zh * ev(q[j], z) % P_
+    # a wrong public input makes the vanishing polynomial indivisible by Z_H: the "quotient" picks up high coefficients
+    bad = oracle.stark_quotient_fibonacci(tc, [3, 5, (pi[2] + 1) % P_], alphas)
+    acc = 0
+    for c in [(l[0] - 3) * l_first, (l[1] - 5) * l_first, (l[1] - pi[2] - 1) * l_last, cons[3], cons[4]]:
+        acc = (acc * alphas[0] + c) % P_
+    assert acc != zh * ev(bad[0], z) % P_
