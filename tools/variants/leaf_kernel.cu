@@ -17,7 +17,7 @@ k_leaf(const uint64_t* leaves, size_t N, uint32_t W, uint64_t* out) {
     const bool live = j < N;
     if (!live) j = N - 1;
     uint64_t h[4];
-    gl::hash_or_noop_strided<true, VB_SYNC != 0>(leaves + j * W, 1, W, h);
+    gl::hash_or_noop_strided<true, VB_SYNC != 0>(leaves + j, N, W, h);  // column-major, like the production LDE
     if (!live) return;
     out[4 * j] = h[0];
     out[4 * j + 1] = h[1];

@@ -22,7 +22,7 @@ int main(int argc, char** argv) {
     CU(cuMemcpyHtoD(d_in, h.data(), h.size() * 8));
     const int NCHK = 512;
     std::vector<uint64_t> ref(NCHK * 4), got(NCHK * 4);
-    for (int j = 0; j < NCHK; j++) gl::hash_or_noop_strided<true, false>(h.data() + (size_t)j * W, 1, W, &ref[4 * j]);
+    for (int j = 0; j < NCHK; j++) gl::hash_or_noop_strided<true, false>(h.data() + (size_t)j, N, W, &ref[4 * j]);  // column-major input
     const gl::PoseidonTables& T = gl::host_poseidon_tables();
     CUevent e0, e1; CU(cuEventCreate(&e0, 0)); CU(cuEventCreate(&e1, 0));
     const double perms = (double)N * ((W + 7) / 8);
