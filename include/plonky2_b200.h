@@ -184,6 +184,17 @@ int gl_partial_products_and_zs(gl_ctx* ctx, const uint64_t* wires, const uint64_
                                uint32_t log_n, uint32_t num_routed, uint64_t beta, uint64_t gamma, uint32_t degree,
                                uint64_t* out, int mem);
 
+/* compute_lookup_polys (plonky2/src/plonk/prover.rs:458-577) for ONE challenge set deltas = (A, B, alpha, delta): the RE
+ * polynomial followed by the num_partial_lookups partial Sum/LDC polynomials, as value columns of n = 2^log_n rows:
+ * out = (num_partial_lookups + 1) columns of n words (column-major), num_partial_lookups =
+ * ceil((num_routed_wires / 2) / (max_quotient_degree_factor - 1)). wires: the witness matrix, wire w of row i at
+ * wires[w*n + i] (LookupGate wires 2s, 2s+1; LookupTableGate wires 3s, 3s+1, 3s+2: gates/lookup.rs:58-70,
+ * gates/lookup_table.rs:64-83). lookup_rows: n_lookup_wires triples (last_lu_gate, last_lut_gate, first_lut_gate)
+ * (LookupWire, plonk/circuit_builder.rs:75-87), processed in order like the reference. */
+int gl_lookup_polys(gl_ctx* ctx, const uint64_t* wires, uint32_t log_n, uint32_t num_routed_wires,
+                    uint32_t max_quotient_degree_factor, const uint64_t deltas[4], const uint32_t* lookup_rows,
+                    uint32_t n_lookup_wires, uint64_t* out, int mem);
+
 /* compute_quotient_polys of a STARK (starky/src/prover.rs:488-668): for every challenge alpha_j the values
  * (sum_k alpha_j^.. C_k(x)) / Z_H(x) on the coset g<w_size>, size = n << log2_ceil(quotient_degree_factor), read from the
  * trace commitment's LDE IN PLACE on the device (get_lde_values addressing, oracle.rs:142-147), then coset_ifft: n_alphas

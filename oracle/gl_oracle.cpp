@@ -1040,6 +1040,64 @@ int glo_partial_products_and_zs(const uint64_t* wires, const uint64_t* sigmas, c
     return 0;
 }
 
+// ------------------------------------------------------------------ lookup helper polynomials
+// compute_lookup_polys, plonky2/src/plonk/prover.rs:458-577, line by line. witness.get_wire(row, w) = wires[w*n + row].
+int glo_lookup_polys(const uint64_t* wires, uint32_t log_n, uint32_t num_routed_wires,
+                     uint32_t max_quotient_degree_factor, const uint64_t deltas[4], const uint32_t* lookup_rows,
+                     uint32_t n_lookup_wires, uint64_t* out) {
+    const size_t degree = (size_t)1 << log_n;
+    const size_t num_lu_slots = num_routed_wires / 2;         // LookupGate::num_slots, gates/lookup.rs:58-61
+    const size_t max_lookup_degree = max_quotient_degree_factor - 1;
+    const size_t num_partial_lookups = (num_lu_slots + max_lookup_degree - 1) / max_lookup_degree;
+    const size_t num_lut_slots = num_routed_wires / 3;        // LookupTableGate::num_slots, gates/lookup_table.rs:64-67
+    const size_t max_lookup_table_degree = (num_lut_slots + num_partial_lookups - 1) / num_partial_lookups;
+    auto get_wire = [&](size_t row, size_t w) { return wires[w * degree + row]; };
+    auto poly = [&](size_t k) { return out + k * degree; };   // final_poly_vecs[k].values
+    for (size_t i = 0; i < (num_partial_lookups + 1) * degree; i++) out[i] = 0;
+    const u64 dA = deltas[0], dB = deltas[1], dAlpha = deltas[2], dDelta = deltas[3];
+    for (uint32_t lw = 0; lw < n_lookup_wires; lw++) {
+        const size_t last_lu_row = lookup_rows[3 * lw], last_lut_row = lookup_rows[3 * lw + 1], first_lut_row = lookup_rows[3 * lw + 2];
+        // Set values for partial Sums and RE.
+        for (size_t row = first_lut_row + 1; row-- > last_lut_row;) {
+            std::vector<u64> looked_combo_inverses(num_lut_slots), lookup_combos(num_lut_slots);
+            for (size_t s = 0; s < num_lut_slots; s++) {
+                const u64 looked_inp = get_wire(row, 3 * s), looked_out = get_wire(row, 3 * s + 1);
+                const u64 minus = fsub(dAlpha, fadd(looked_inp, fmul(dA, looked_out)));
+                if (canon(minus) == 0) return 1;  // batch_multiplicative_inverse would panic
+                looked_combo_inverses[s] = finv(minus);
+                lookup_combos[s] = fadd(looked_inp, fmul(dB, looked_out));
+            }
+            u64 new_re = poly(0)[row + 1];
+            for (u64 elt : lookup_combos) new_re = fadd(fmul(new_re, dDelta), elt);
+            poly(0)[row] = canon(new_re);
+            for (size_t slot = 0; slot < num_partial_lookups; slot++) {
+                u64 sum = slot != 0 ? poly(slot)[row] : poly(num_partial_lookups)[row + 1];
+                for (size_t s = slot * max_lookup_table_degree; s < std::min((slot + 1) * max_lookup_table_degree, num_lut_slots); s++)
+                    sum = fadd(sum, fmul(get_wire(row, 3 * s + 2), looked_combo_inverses[s]));
+                poly(slot + 1)[row] = canon(sum);
+            }
+        }
+        // Set values for partial LDCs.
+        for (size_t row = last_lut_row; row-- > last_lu_row;) {
+            std::vector<u64> looking_combo_inverses(num_lu_slots);
+            for (size_t s = 0; s < num_lu_slots; s++) {
+                const u64 looking_in = get_wire(row, 2 * s), looking_out = get_wire(row, 2 * s + 1);
+                const u64 minus = fsub(dAlpha, fadd(looking_in, fmul(dA, looking_out)));
+                if (canon(minus) == 0) return 1;
+                looking_combo_inverses[s] = finv(minus);
+            }
+            for (size_t slot = 0; slot < num_partial_lookups; slot++) {
+                const u64 prev = slot == 0 ? poly(num_partial_lookups)[row + 1] : poly(slot)[row];
+                u64 sum = 0;
+                for (size_t s = slot * max_lookup_degree; s < std::min((slot + 1) * max_lookup_degree, num_lu_slots); s++)
+                    sum = fadd(sum, looking_combo_inverses[s]);
+                poly(slot + 1)[row] = canon(fsub(prev, sum));
+            }
+        }
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------ STARK quotient
 // compute_quotient_polys (starky/src/prover.rs:488-668) for FibonacciStark (starky/src/fibonacci_stark.rs:73-95),
 // restated with the reference's own steps: Lagrange selectors by `PolynomialValues::selector(..).lde_onto_coset`

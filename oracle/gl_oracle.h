@@ -164,6 +164,14 @@ int glo_partial_products_and_zs(const uint64_t* wires, const uint64_t* sigmas, c
                                 uint32_t log_n, uint32_t num_routed, uint64_t beta, uint64_t gamma,
                                 uint32_t degree, uint64_t* out);
 
+/* ---- "next" row (second half): compute_lookup_polys (plonky2/src/plonk/prover.rs:458-577) for one
+ *      challenge set deltas = (A, B, alpha, delta). wires: witness matrix, wire w of row i at wires[w*n + i].
+ *      lookup_rows: triples (last_lu_gate, last_lut_gate, first_lut_gate). out: (num_partial_lookups + 1) columns of n.
+ *      Returns 0, or 1 on a zero denominator. */
+int glo_lookup_polys(const uint64_t* wires, uint32_t log_n, uint32_t num_routed_wires,
+                     uint32_t max_quotient_degree_factor, const uint64_t deltas[4], const uint32_t* lookup_rows,
+                     uint32_t n_lookup_wires, uint64_t* out);
+
 /* ---- "next" row: compute_quotient_polys of starky for FibonacciStark
  *      (starky/src/prover.rs:488-668, starky/src/fibonacci_stark.rs:73-95). trace: a 2-column commitment; pi = (x0, x1,
  *      result); out = n_alphas polynomials of (n << quotient_degree_bits) coefficients. Returns 0 on success. */

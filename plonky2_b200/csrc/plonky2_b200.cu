@@ -1027,6 +1027,100 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_mscan_phase3(const u64* seq, s
     if (blockIdx.x == 0 && threadIdx.x == 0) out[(size_t)(M - 1) * n] = 1;
 }
 
+// ---- lookup argument helper columns (compute_lookup_polys, plonk/prover.rs:458-577) ----
+// For one LookupWire the reference walks the rows from first_lut_row down to last_lu_row and fills
+//   RE[row]          = RE[row+1] * delta^L + sum_s combo_B(row, s) * delta^(L-1-s)          (LUT rows only, L = num_lut_slots)
+//   SLDC[slot][row]  = running sum over (row descending, slot ascending) of
+//                        + sum_{s in slot} multiplicity(row, s) / (alpha - combo_A(row, s))    on LookupTableGate rows
+//                        - sum_{s in slot} 1 / (alpha - combo_A(row, s))                        on LookupGate rows
+// i.e. one affine and one additive scan over a sequence of T rows (x P slots). k_lookup_terms computes the per-row
+// terms (one batch inversion per row, field/src/types.rs:133-223), k_affine_scan runs both scans in one CTA.
+struct LookupParams {
+    const u64* wires;      // column-major, wire w of row i at wires[w*n + i]
+    size_t n;
+    uint32_t num_lu_slots, num_lut_slots, P, max_lookup_degree, max_lookup_table_degree;
+    u64 dA, dB, dAlpha, dDelta;
+    uint32_t first_lut, last_lut, last_lu;  // rows (first_lut >= last_lut > last_lu allowed to be equal ranges)
+    u64* term;             // T * P additive terms in scan order
+    u64* reh;              // rows_lut Horner values H(row)
+    unsigned int* flag;
+};
+constexpr int LOOKUP_MAX_SLOTS = 64;
+__global__ void __launch_bounds__(128) k_lookup_terms(LookupParams p) {
+    const uint32_t rows_lut = p.first_lut - p.last_lut + 1, rows_lu = p.last_lut - p.last_lu;
+    const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= rows_lut + rows_lu) return;
+    const bool lut = pos < rows_lut;
+    const size_t row = lut ? (size_t)p.first_lut - pos : (size_t)p.last_lut - 1 - (pos - rows_lut);
+    const uint32_t ns = lut ? p.num_lut_slots : p.num_lu_slots, wpe = lut ? 3u : 2u;
+    u64 pre[LOOKUP_MAX_SLOTS], den[LOOKUP_MAX_SLOTS];
+    u64 run = 1, h = 0;
+    for (uint32_t s = 0; s < ns; s++) {
+        const u64 inp = p.wires[(size_t)(wpe * s) * p.n + row], out = p.wires[(size_t)(wpe * s + 1) * p.n + row];
+        const u64 d = sub(p.dAlpha, add(inp, mul(p.dA, out)));  // alpha - (inp + A * out)
+        if (canon(d) == 0) atomicOr(p.flag, 1u);
+        den[s] = d;
+        run = mul(run, d);
+        pre[s] = run;
+        if (lut) h = add(mul(h, p.dDelta), add(inp, mul(p.dB, out)));  // new_re = new_re * delta + lookup_combo
+    }
+    if (lut) p.reh[pos] = h;
+    u64 inv_run = gl::inv(run);
+    for (uint32_t s = ns; s-- > 0;) {  // den[s] <- 1 / den[s]
+        const u64 di = s ? mul(inv_run, pre[s - 1]) : inv_run;
+        inv_run = mul(inv_run, den[s]);
+        den[s] = di;
+    }
+    const uint32_t per = lut ? p.max_lookup_table_degree : p.max_lookup_degree;
+    for (uint32_t slot = 0; slot < p.P; slot++) {
+        u64 acc = 0;
+        const uint32_t s1 = min((slot + 1) * per, ns);
+        for (uint32_t s = slot * per; s < s1; s++)
+            acc = lut ? add(acc, mul(p.wires[(size_t)(3 * s + 2) * p.n + row], den[s])) : add(acc, den[s]);
+        p.term[(size_t)pos * p.P + slot] = lut ? acc : neg(acc);
+    }
+}
+// y_k = y_{k-1} * a + b_k over `len` items (a constant; a = 1: additive scan), y_{-1} = init; one CTA of 1024 threads.
+// out_of(k) maps item k to its output address (two layouts: SLDC and RE), given by (P, rows_lut, ...) in `p`.
+__global__ void __launch_bounds__(1024) k_affine_scan(const u64* b, size_t len, u64 a, u64 init, LookupParams p, int re_mode,
+                                                      u64* out) {
+    __shared__ u64 sa[1024], sb[1024];
+    const size_t per = (len + 1023) / 1024;
+    const size_t lo = (size_t)threadIdx.x * per, hi = lo + per < len ? lo + per : len;
+    u64 ca = 1, cb = 0;  // composition of my run: y -> y * ca + cb
+    for (size_t k = lo; k < hi; k++) {
+        ca = mul(ca, a);
+        cb = add(mul(cb, a), b[k]);
+    }
+    sa[threadIdx.x] = ca;
+    sb[threadIdx.x] = cb;
+    __syncthreads();
+    if (threadIdx.x == 0) {  // exclusive scan of the 1024 run compositions, applied to init
+        u64 y = init;
+        for (int t = 0; t < 1024; t++) {
+            const u64 na = sa[t], nb = sb[t];
+            sb[t] = y;
+            y = add(mul(y, na), nb);
+        }
+    }
+    __syncthreads();
+    u64 y = sb[threadIdx.x];
+    const uint32_t rows_lut = p.first_lut - p.last_lut + 1;
+    for (size_t k = lo; k < hi; k++) {
+        y = add(mul(y, a), b[k]);
+        size_t pos, col;
+        if (re_mode) {
+            pos = k;
+            col = 0;
+        } else {
+            pos = k / p.P;
+            col = 1 + k % p.P;
+        }
+        const size_t row = pos < rows_lut ? (size_t)p.first_lut - pos : (size_t)p.last_lut - 1 - (pos - rows_lut);
+        out[col * p.n + row] = canon(y);
+    }
+}
+
 // ---- STARK quotient evaluation (compute_quotient_polys, starky/src/prover.rs:488-668) ----
 // The constraints (Stark::eval_packed_generic, starky/src/stark.rs) arrive as a small straight-line program over the
 // local row, the next row and the public inputs; value k = result of instruction k. One thread per point of the
@@ -1658,6 +1752,93 @@ int gl_partial_products_and_zs(gl_ctx* ctx, const uint64_t* wires, const uint64_
     dfree(ctx, tot);
     dfree(ctx, dflag);
     dfree(ctx, xtab);
+    if (mem == GL_MEM_HOST) dfree(ctx, dout);
+    return rc;
+}
+
+int gl_lookup_polys(gl_ctx* ctx, const uint64_t* wires, uint32_t log_n, uint32_t num_routed_wires,
+                    uint32_t max_quotient_degree_factor, const uint64_t deltas[4], const uint32_t* lookup_rows,
+                    uint32_t n_lookup_wires, uint64_t* out, int mem) {
+    if (!ctx || !wires || !deltas || !out || (n_lookup_wires && !lookup_rows)) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
+    if (max_quotient_degree_factor < 2 || log_n > 26) return set_err(ctx, GL_ERR_BAD_SHAPE, "bad lookup shape");
+    const uint32_t num_lu_slots = num_routed_wires / 2, num_lut_slots = num_routed_wires / 3;  // lookup.rs:58-61, lookup_table.rs:64-67
+    if (num_lu_slots == 0 || num_lut_slots == 0 || num_lu_slots > (uint32_t)LOOKUP_MAX_SLOTS)
+        return set_err(ctx, GL_ERR_UNSUPPORTED, "1..%d lookup slots per row", LOOKUP_MAX_SLOTS);
+    const uint32_t max_lookup_degree = max_quotient_degree_factor - 1;
+    const uint32_t P = (num_lu_slots + max_lookup_degree - 1) / max_lookup_degree;
+    const uint32_t max_lookup_table_degree = (num_lut_slots + P - 1) / P;
+    const size_t n = (size_t)1 << log_n;
+    const uint32_t num_wires_read = 3 * num_lut_slots > 2 * num_lu_slots ? 3 * num_lut_slots : 2 * num_lu_slots;
+    for (uint32_t k = 0; k < n_lookup_wires; k++) {
+        const uint32_t last_lu = lookup_rows[3 * k], last_lut = lookup_rows[3 * k + 1], first_lut = lookup_rows[3 * k + 2];
+        if (!(last_lu <= last_lut && last_lut <= first_lut && (size_t)first_lut + 1 < n))
+            return set_err(ctx, GL_ERR_BAD_ARG, "lookup rows %u: need last_lu <= last_lut <= first_lut < n - 1", k);
+    }
+    CK(ctx, cudaSetDevice(ctx->device));
+    u64 *dw = nullptr, *dout = nullptr, *term = nullptr, *reh = nullptr, *dflag = nullptr;
+    auto body = [&]() -> int {
+        const u64* pw = wires;
+        if (mem == GL_MEM_HOST) {
+            TRY(dmalloc(ctx, &dw, (size_t)num_wires_read * n));
+            TRY(h2d(ctx, dw, wires, (size_t)num_wires_read * n));
+            pw = dw;
+            TRY(dmalloc(ctx, &dout, (size_t)(P + 1) * n));
+        } else {
+            dout = out;
+        }
+        CK(ctx, cudaMemsetAsync(dout, 0, (size_t)(P + 1) * n * 8, ctx->stream));  // vec![F::ZERO; degree]
+        TRY(dmalloc(ctx, &dflag, 1));
+        CK(ctx, cudaMemsetAsync(dflag, 0, 8, ctx->stream));
+        u64 dL = 1;  // delta^num_lut_slots
+        for (uint32_t s = 0; s < num_lut_slots; s++) dL = mul(dL, canon(deltas[3]));
+        for (uint32_t k = 0; k < n_lookup_wires; k++) {
+            LookupParams p;
+            p.wires = pw;
+            p.n = n;
+            p.num_lu_slots = num_lu_slots;
+            p.num_lut_slots = num_lut_slots;
+            p.P = P;
+            p.max_lookup_degree = max_lookup_degree;
+            p.max_lookup_table_degree = max_lookup_table_degree;
+            p.dA = canon(deltas[0]);
+            p.dB = canon(deltas[1]);
+            p.dAlpha = canon(deltas[2]);
+            p.dDelta = canon(deltas[3]);
+            p.last_lu = lookup_rows[3 * k];
+            p.last_lut = lookup_rows[3 * k + 1];
+            p.first_lut = lookup_rows[3 * k + 2];
+            const uint32_t rows_lut = p.first_lut - p.last_lut + 1, T = rows_lut + (p.last_lut - p.last_lu);
+            dfree(ctx, term);
+            dfree(ctx, reh);
+            term = reh = nullptr;
+            TRY(dmalloc(ctx, &term, (size_t)T * P));
+            TRY(dmalloc(ctx, &reh, rows_lut));
+            p.term = term;
+            p.reh = reh;
+            p.flag = (unsigned int*)dflag;
+            k_lookup_terms<<<(T + 127) / 128, 128, 0, ctx->stream>>>(p);
+            CKL(ctx);
+            // initial values: the arrays' entries at first_lut_row + 1 (zero unless an earlier LookupWire wrote them)
+            u64 init[2];
+            CK(ctx, cudaMemcpyAsync(&init[0], dout + p.first_lut + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(ctx, cudaMemcpyAsync(&init[1], dout + (size_t)P * n + p.first_lut + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(ctx, cudaStreamSynchronize(ctx->stream));
+            k_affine_scan<<<1, 1024, 0, ctx->stream>>>(reh, rows_lut, dL, init[0], p, 1, dout);
+            CKL(ctx);
+            k_affine_scan<<<1, 1024, 0, ctx->stream>>>(term, (size_t)T * P, 1, init[1], p, 0, dout);
+            CKL(ctx);
+        }
+        u64 flag = 0;
+        TRY(d2h(ctx, &flag, dflag, 1));
+        if (flag & 1u) return set_err(ctx, GL_ERR_DIV_ZERO, "Tried to invert zero");
+        if (mem == GL_MEM_HOST) TRY(d2h(ctx, out, dout, (size_t)(P + 1) * n));
+        return GL_OK;
+    };
+    int rc = body();
+    dfree(ctx, dw);
+    dfree(ctx, term);
+    dfree(ctx, reh);
+    dfree(ctx, dflag);
     if (mem == GL_MEM_HOST) dfree(ctx, dout);
     return rc;
 }

@@ -71,3 +71,34 @@ def commit_zs_partial_products(wires_dev, sigmas_dev, k_is, betas, gammas, degre
         L.gl_commit_destroy(h)
         raise
     return PolynomialBatch(h, ctx, B, log_n, rate_bits, cap_height, False)
+
+
+def compute_lookup_polys(wires, num_routed_wires, max_quotient_degree_factor, deltas, lookup_rows, ctx=None):
+    """compute_lookup_polys (prover.rs:458-577) for one challenge set deltas = (A, B, alpha, delta): the RE polynomial
+    and the partial Sum/LDC polynomials as value columns, (num_partial_lookups + 1, n). wires: (num_wires, n) witness
+    matrix (host array); lookup_rows: [(last_lu_gate, last_lut_gate, first_lut_gate)] (LookupWire)."""
+    ctx = ctx or N.default_context()
+    wires = np.ascontiguousarray(wires, dtype=np.uint64)
+    if wires.ndim != 2:
+        raise N.ShapeError("wires must be (num_wires, n)")
+    n = wires.shape[1]
+    log_n = log2_strict(n)
+    need = max(3 * (num_routed_wires // 3), 2 * (num_routed_wires // 2))
+    if wires.shape[0] < need:
+        raise N.ShapeError("the witness must hold at least %d wires" % need)
+    P_ = -(-(num_routed_wires // 2) // (max_quotient_degree_factor - 1))
+    out = np.empty((P_ + 1, n), dtype=np.uint64)
+    d = np.array([int(x) for x in deltas], dtype=np.uint64)
+    lr = np.array(lookup_rows, dtype=np.uint32).reshape(-1)
+    N.check(N.lib().gl_lookup_polys(ctx.h, N.np_ptr(np.ascontiguousarray(wires[:need])), log_n, num_routed_wires,
+                                    max_quotient_degree_factor, N.np_ptr(d), lr.ctypes.data_as(N.u32p), len(lr) // 3,
+                                    N.np_ptr(out), N.MEM_HOST), ctx.h)
+    return out
+
+
+def compute_all_lookup_polys(wires, num_routed_wires, max_quotient_degree_factor, deltas, lookup_rows, num_challenges,
+                             ctx=None):
+    """compute_all_lookup_polys (prover.rs:579-607): one compute_lookup_polys per challenge (4 deltas each), concatenated."""
+    parts = [compute_lookup_polys(wires, num_routed_wires, max_quotient_degree_factor, deltas[4 * c:4 * c + 4], lookup_rows,
+                                  ctx) for c in range(num_challenges)]
+    return np.concatenate(parts) if parts else np.zeros((0, wires.shape[1]), dtype=np.uint64)

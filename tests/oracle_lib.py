@@ -121,6 +121,8 @@ def lib():
                                        C.c_size_t, C.POINTER(FriBatch), C.c_size_t, u64p, C.c_uint32,
                                        C.c_void_p, C.POINTER(FriParams), C.POINTER(C.c_uint8), C.c_size_t]
     L.glo_eval_poly_base_at_ext.argtypes = [u64p, C.c_size_t, u64p, u64p]
+    L.glo_lookup_polys.restype = C.c_int
+    L.glo_lookup_polys.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u32p, C.c_uint32, u64p]
     L.glo_stark_quotient_fibonacci.restype = C.c_int
     L.glo_stark_quotient_fibonacci.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t, u64p]
     L.glo_partial_products_and_zs.restype = C.c_int
@@ -443,4 +445,19 @@ def stark_quotient_fibonacci(trace_commit, public_inputs, alphas):
     rc = lib().glo_stark_quotient_fibonacci(trace_commit.h, ptr(pi), ptr(al), len(al), ptr(out))
     if rc != 0:
         raise RuntimeError("oracle stark quotient rc=%d" % rc)
+    return out
+
+
+def lookup_polys(wires, num_routed_wires, max_quotient_degree_factor, deltas, lookup_rows):
+    """compute_lookup_polys: wires (num_wires, n); lookup_rows [(last_lu, last_lut, first_lut)]. -> (P + 1, n)."""
+    wires = np.ascontiguousarray(wires, dtype=np.uint64)
+    n = wires.shape[1]
+    P_ = -(-(num_routed_wires // 2) // (max_quotient_degree_factor - 1))
+    out = np.zeros((P_ + 1, n), dtype=np.uint64)
+    d = np.array([int(x) for x in deltas], dtype=np.uint64)
+    lr = np.array(lookup_rows, dtype=np.uint32).reshape(-1)
+    rc = lib().glo_lookup_polys(ptr(wires), int(np.log2(n)), num_routed_wires, max_quotient_degree_factor, ptr(d),
+                                lr.ctypes.data_as(u32p), len(lr) // 3, ptr(out))
+    if rc != 0:
+        raise ZeroDivisionError("Tried to invert zero")
     return out

@@ -938,3 +938,27 @@ def test_stark_prove_pipeline_on_device(pb, oracle):
         assert acc == E.ext_mul(zh, qv[j])
     tc.close()
     qc.close()
+
+
+@pytest.mark.parametrize("routed,qdf,log_n,rows", [(12, 4, 8, [(10, 40, 60)]), (80, 8, 10, [(3, 300, 500), (600, 700, 900)]),
+                                                   (6, 2, 6, [(5, 5, 5)])])
+def test_lookup_polys_match_oracle(pb, oracle, routed, qdf, log_n, rows):
+    """compute_lookup_polys (plonk/prover.rs:458-577): RE + partial Sum/LDC columns vs the oracle's literal restatement,
+    one and two LookupWires, degenerate ranges; a zero denominator is reported like the reference's panic."""
+    from plonky2_b200.prover import compute_all_lookup_polys, compute_lookup_polys
+
+    n = 1 << log_n
+    wires = synth(0xF8 + log_n, (routed, n))
+    deltas = [int(x) for x in synth(0xF9, (8,))]
+    got = compute_lookup_polys(wires, routed, qdf, deltas[:4], rows)
+    want = oracle.lookup_polys(wires, routed, qdf, deltas[:4], rows)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    both = compute_all_lookup_polys(wires, routed, qdf, deltas, rows, 2)
+    assert np.array_equal(both[:len(want)], want)
+    assert np.array_equal(both[len(want):], oracle.lookup_polys(wires, routed, qdf, deltas[4:], rows))
+    # alpha = inp + A*out on one looked slot -> "Tried to invert zero"
+    row = rows[0][2]
+    bad = list(deltas[:4])
+    bad[2] = (int(wires[0, row]) + bad[0] * int(wires[1, row])) % int(P)
+    with pytest.raises(ZeroDivisionError):
+        compute_lookup_polys(wires, routed, qdf, bad, rows)
