@@ -324,18 +324,26 @@ def gpu_arm(args, rank, local_rank, world):
                 def __init__(self, h):
                     self.h, self.ctx = h, ctx
 
+            def gather_words(local):  # all-gather of the ranks' cap entries of one FRI round (NCCL)
+                t_loc = torch.from_numpy(local.view(np.int64)).to(dev)
+                t_all = torch.empty(t_loc.numel() * world, dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(t_all, t_loc)
+                return t_all.cpu().numpy().view(np.uint64)
+
             def fri_commit_phase(hnd, cap_np):
                 ch = pb.Challenger()
                 ch.observe_cap(pb.MerkleCap(np.ascontiguousarray(cap_np).view(np.uint64).reshape(-1, 4)))
                 st = F._begin(inst, [_Oracle(hnd)], ch.get_extension_challenge(), params)
                 try:
-                    caps, final = F.fri_committed_trees(st, ch, params)
+                    caps, final = F.fri_committed_trees(st, ch, params, shard=(rank, world) if world > 1 else None,
+                                                        gather=gather_words)
                 finally:
                     st.close()
                 return caps, final
 
             fri_ctx = fri_commit_phase
         fri_out = [None]
+        fri_spans = []
 
         def step_device():
             if committer is not None:
@@ -351,7 +359,11 @@ def gpu_arm(args, rank, local_rank, world):
             else:
                 cap_full.copy_(cap_local)
             if fri_ctx is not None:
+                fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                fa.record(stream)
                 fri_out[0] = fri_ctx(hnd, cap_full.cpu().numpy())
+                fb.record(stream)
+                fri_spans.append((fa, fb))
             L.gl_commit_destroy(hnd)
 
         def sync_all():
@@ -364,6 +376,7 @@ def gpu_arm(args, rank, local_rank, world):
             step_device()
         sync_all()
         ctx.reset_phases()
+        del fri_spans[:]
         if committer is not None:
             committer.timing = True
             committer.transfer_ms()
@@ -371,11 +384,16 @@ def gpu_arm(args, rank, local_rank, world):
         sampler = ClockSampler(local_rank) if rank == 0 else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        marks = []
         for _ in range(args.steps):
             step_device()
+            m = torch.cuda.Event(enable_timing=True)
+            m.record(stream)
+            marks.append(m)
         e1.record(stream)
         sync_all()
         ms = e0.elapsed_time(e1)
+        step_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
         launches = ctx.launch_count - launches0
         side = committer.transfer_ms() if committer is not None else None
         if committer is not None:
@@ -517,12 +535,14 @@ def gpu_arm(args, rank, local_rank, world):
                          "achieved": lde_bytes / (lde_ms * 1e-3) / 1e9 if lde_ms else None, "peak": peak,
                          "unit": "GB/s", "frac": lde_bytes / (lde_ms * 1e-3) / 1e9 / peak if lde_ms else None},
         "roofline_ntt": ntt,
-        "fri_commit_phase": ({"rounds": len(fri_out[0][0]), "final_poly_len": int(len(fri_out[0][1])),
+        "fri_commit_phase": ({"ms_per_step": sum(a.elapsed_time(b) for a, b in fri_spans[:steps]) / max(1, min(steps, len(fri_spans))),
+                              "rounds": len(fri_out[0][0]), "final_poly_len": int(len(fri_out[0][1])),
                               "last_round_cap0": [int(x) for x in fri_out[0][0][-1].hashes[0]],
                               "note": "inside the timed step: alpha/betas from the host transcript, caps to the host"}
                              if fri_out[0] is not None else None),
         "cap0": [int(x) for x in cap_dev[0]],
         "cap_matches_fixture": cap_ok,
+        "step_ms_rank0": step_ms,
         "coefficient_transport": (committer.transport + (" (%s)" % committer.transport_note if committer.transport_note else ""))
         if committer is not None else None,
         "input": "splitmix64 counter generator, seed 0x%02x (tests/conftest.py synth; SURVEY 8d)" % args.seed,
@@ -656,6 +676,7 @@ def main():
                     help="N > 1: how the coefficients reach the other ranks (auto = fused NVLink stores, NCCL fallback)")
     ap.add_argument("--fri-commit", action="store_true", default=None,
                     help="include the FRI commit phase of the opening proof in every step (default: on for cfg5)")
+    ap.add_argument("--no-fri-commit", dest="fri_commit", action="store_false")
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--ntt-group", type=int, default=0, help="columns per NTT group (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true")

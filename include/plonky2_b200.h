@@ -274,6 +274,10 @@ int gl_fri_coeffs(gl_fri* f, uint64_t* out);
 /* One round of fri_committed_trees (prover.rs:96-120), split at the transcript:
  *   commit: leaves = arity consecutive (bit-reversed) values flattened; MerkleTree::new; cap -> host. */
 int gl_fri_commit_round(gl_fri* f, uint32_t arity_bits, uint64_t* cap_out /* 4 * 2^cap_height */);
+/*   the same with the round's Merkle tree row-block sharded over num_shards GPUs (each hashes its own block of leaves and
+ *   returns its 2^cap_height / num_shards cap entries; the caller all-gathers them). Values stay replicated. */
+int gl_fri_commit_round_sharded(gl_fri* f, uint32_t arity_bits, uint32_t shard_index, uint32_t num_shards,
+                                uint64_t* cap_out);
 /*   fold:   with beta from the transcript, values' = fold(values, beta) on the coset shift^arity. */
 int gl_fri_fold(gl_fri* f, const uint64_t beta[2]);
 /* Final polynomial after the last fold, truncated by 2^rate_bits (prover.rs:134-139):

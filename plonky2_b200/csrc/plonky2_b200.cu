@@ -357,6 +357,7 @@ __global__ void k_tree_open(TreeView t, const u64* indices, u64* out_leaves, u64
 
 struct Tree {
     u64* leaves = nullptr;  // device
+    u64* base = nullptr;    // allocation `leaves` points into when the tree covers a row block of a larger buffer
     bool own_leaves = false;
     u64* digests = nullptr;
     u64* cap = nullptr;
@@ -415,7 +416,7 @@ static int tree_build(gl_ctx* ctx, Tree& t) {
     return GL_OK;
 }
 static void tree_free(gl_ctx* ctx, Tree& t) {
-    if (t.own_leaves) dfree(ctx, t.leaves);
+    if (t.own_leaves) dfree(ctx, t.base ? t.base : t.leaves);
     dfree(ctx, t.digests);
     dfree(ctx, t.cap);
     t.leaves = t.digests = t.cap = nullptr;
@@ -1227,6 +1228,8 @@ struct gl_fri {
     u64 shift = 0;              // current coset shift
     uint32_t pending_arity_bits = 0;
     bool committed = false;     // commit_round done, fold pending
+    u64* round_values = nullptr;  // the committed round's whole values buffer (owned by its tree) and leaf count
+    size_t round_leaves = 0;
     std::vector<Tree> trees;
 };
 
@@ -1405,8 +1408,20 @@ struct BcastDests {
     int n;
 };
 __global__ void __launch_bounds__(256) k_bcast_copy(const ulonglong2* __restrict__ src, size_t n16, BcastDests d) {
+    // 8 independent 16-byte loads per thread before the first store: with few CTAs (the copy shares the GPU with the
+    // transforms) the bytes in flight, not the link, bounded the first version at ~120-190 GB/s
+    constexpr int U = 8;
     const size_t step = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += step) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (U - 1) * step < n16; i += U * step) {
+        ulonglong2 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) v[u] = src[i + u * step];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            for (int k = 0; k < d.n; k++) d.p[k][i + u * step] = v[u];
+    }
+    for (; i < n16; i += step) {
         const ulonglong2 v = src[i];
         for (int k = 0; k < d.n; k++) d.p[k][i] = v;
     }
@@ -2203,20 +2218,30 @@ int gl_fri_coeffs(gl_fri* f, uint64_t* out) {
 }
 uint32_t gl_fri_num_rounds(const gl_fri* f) { return (uint32_t)f->trees.size(); }
 
-int gl_fri_commit_round(gl_fri* f, uint32_t arity_bits, uint64_t* cap_out) {
+// One round's Merkle commitment; with num_shards = G > 1 only the row block [g*L/G, (g+1)*L/G) of the L leaves is hashed
+// (FRI leaves are consecutive bit-reversed values, so a row block is a set of whole cap subtrees, like the initial
+// commitment): cap_out receives this shard's C/G cap entries, the values stay replicated for the (cheap) fold.
+static int fri_commit_round(gl_fri* f, uint32_t arity_bits, uint32_t shard_index, uint32_t num_shards, uint64_t* cap_out) {
     gl_ctx* ctx = f->ctx;
     CK(ctx, cudaSetDevice(ctx->device));
     if (f->committed) return set_err(ctx, GL_ERR_BAD_ARG, "fold the previous round first");
     if (arity_bits < 1 || arity_bits > 5) return set_err(ctx, GL_ERR_UNSUPPORTED, "arity_bits %u not in 1..5", arity_bits);
     if (arity_bits > f->log_cur) return set_err(ctx, GL_ERR_BAD_SHAPE, "arity exceeds the codeword length");
-    Tree t;
-    t.N = (size_t)1 << (f->log_cur - arity_bits);
-    t.W = 2u << arity_bits;
-    t.cap_height = f->cap_height;
-    t.leaves = f->values;  // chunks(arity).map(flatten) of the bit-reversed values == this buffer
-    if (t.cap_height > f->log_cur - arity_bits)
-        return set_err(ctx, GL_ERR_BAD_SHAPE, "cap_height=%u should be at most log2(leaves.len())=%u", t.cap_height,
+    uint32_t sl = 0;
+    if (log2_exact(num_shards, &sl) || shard_index >= num_shards)
+        return set_err(ctx, GL_ERR_BAD_ARG, "bad shard %u of %u (power of two required)", shard_index, num_shards);
+    if (f->cap_height > f->log_cur - arity_bits)
+        return set_err(ctx, GL_ERR_BAD_SHAPE, "cap_height=%u should be at most log2(leaves.len())=%u", f->cap_height,
                        f->log_cur - arity_bits);
+    if (sl > f->cap_height)
+        return set_err(ctx, GL_ERR_BAD_SHAPE, "num_shards=%u exceeds the cap size 2^%u", num_shards, f->cap_height);
+    const size_t L = (size_t)1 << (f->log_cur - arity_bits);
+    Tree t;
+    t.N = L >> sl;
+    t.W = 2u << arity_bits;
+    t.cap_height = f->cap_height - sl;
+    t.base = f->values;
+    t.leaves = f->values + (size_t)shard_index * t.N * t.W;  // chunks(arity).map(flatten) of the bit-reversed values == this buffer
     t.own_leaves = false;
     int rc = tree_build(ctx, t);
     if (rc != GL_OK) {
@@ -2224,11 +2249,17 @@ int gl_fri_commit_round(gl_fri* f, uint32_t arity_bits, uint64_t* cap_out) {
         return rc;
     }
     t.own_leaves = true;  // ownership of the values buffer moves to the tree
+    f->round_values = f->values;
+    f->round_leaves = L;
     f->values = nullptr;
     f->trees.push_back(t);
     f->pending_arity_bits = arity_bits;
     f->committed = true;
     return d2h(ctx, cap_out, t.cap, t.cap_words());
+}
+int gl_fri_commit_round(gl_fri* f, uint32_t arity_bits, uint64_t* cap_out) { return fri_commit_round(f, arity_bits, 0, 1, cap_out); }
+int gl_fri_commit_round_sharded(gl_fri* f, uint32_t arity_bits, uint32_t shard_index, uint32_t num_shards, uint64_t* cap_out) {
+    return fri_commit_round(f, arity_bits, shard_index, num_shards, cap_out);
 }
 
 int gl_fri_fold(gl_fri* f, const uint64_t beta[2]) {
@@ -2236,12 +2267,11 @@ int gl_fri_fold(gl_fri* f, const uint64_t beta[2]) {
     CK(ctx, cudaSetDevice(ctx->device));
     if (!f->committed) return set_err(ctx, GL_ERR_BAD_ARG, "commit the round first");
     const uint32_t ab = f->pending_arity_bits;
-    const Tree& t = f->trees.back();
-    const size_t leaves = t.N;
+    const size_t leaves = f->round_leaves;
     u64* out;
     TRY(dmalloc(ctx, &out, 2 * leaves));
     FoldParams fp{};
-    fp.values = t.leaves;
+    fp.values = f->round_values;
     fp.out = out;
     fp.n_leaves = leaves;
     fp.log_leaves = f->log_cur - ab;

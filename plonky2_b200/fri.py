@@ -200,14 +200,24 @@ def _begin(instance, oracles, alpha, fri_params):
     return _FriState(h, ctx)
 
 
-def fri_committed_trees(state, challenger, fri_params, final_poly_coeff_len=None, max_num_query_steps=None):
-    """fri_committed_trees (prover.rs:84-150): returns (caps, final_poly coefficients (len, 2))."""
+def fri_committed_trees(state, challenger, fri_params, final_poly_coeff_len=None, max_num_query_steps=None,
+                        shard=None, gather=None):
+    """fri_committed_trees (prover.rs:84-150): returns (caps, final_poly coefficients (len, 2)).
+    shard=(g, G), gather=fn(local cap words) -> full cap words: every round's tree is row-block sharded over the G
+    ranks (this rank hashes only its block of leaves; the values and the fold stay replicated) and the ranks
+    all-gather their cap entries -- rounds too small to shard are built whole on every rank."""
     L, ctx = N.lib(), state.ctx
     cap_words = NUM_HASH_OUT_ELTS << fri_params.config.cap_height
     caps = []
     for arity_bits in fri_params.reduction_arity_bits:
         cap = np.empty(cap_words, dtype=np.uint64)
-        N.check(L.gl_fri_commit_round(state.h, arity_bits, N.np_ptr(cap)), ctx.h)
+        if shard is not None and shard[1] > 1 and (shard[1] - 1).bit_length() <= fri_params.config.cap_height:
+            local = np.empty(cap_words // shard[1], dtype=np.uint64)
+            N.check(L.gl_fri_commit_round_sharded(state.h, arity_bits, shard[0], shard[1], N.np_ptr(local)), ctx.h)
+            cap = np.ascontiguousarray(gather(local), dtype=np.uint64).reshape(-1)
+            assert cap.size == cap_words
+        else:
+            N.check(L.gl_fri_commit_round(state.h, arity_bits, N.np_ptr(cap)), ctx.h)
         cap = MerkleCap(cap)
         challenger.observe_cap(cap)
         caps.append(cap)

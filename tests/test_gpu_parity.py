@@ -962,3 +962,48 @@ def test_lookup_polys_match_oracle(pb, oracle, routed, qdf, log_n, rows):
     bad[2] = (int(wires[0, row]) + bad[0] * int(wires[1, row])) % int(P)
     with pytest.raises(ZeroDivisionError):
         compute_lookup_polys(wires, routed, qdf, bad, rows)
+
+
+@pytest.mark.parametrize("shards", [2, 8])
+def test_fri_round_trees_row_block_sharded(pb, shards):
+    """gl_fri_commit_round_sharded: every shard hashes its own block of a round's leaves; the shards' cap entries in
+    shard order are the unsharded cap, round after round (values and folds are replicated)."""
+    import ctypes as C
+
+    from plonky2_b200 import _native as N
+
+    log_n, r, h = 10, 2, 4
+    n = 1 << log_n
+    coeffs = synth(0xFA, (n, 2))
+    betas = synth(0xFB, (3, 2))
+    ctx = pb.default_context()
+    L = N.lib()
+
+    def begin():
+        f = N.vp()
+        N.check(L.gl_fri_begin_from_coeffs(ctx.h, N.np_ptr(coeffs.reshape(-1)), log_n, r, h, C.byref(f)), ctx.h)
+        return f
+
+    ref = begin()
+    states = [begin() for _ in range(shards)]
+    try:
+        for rnd, arity_bits in enumerate([3, 2, 2]):   # 4096 -> 512 -> 128 -> 32 values: leaves 512, 128, 32
+            want = np.empty(4 << h, dtype=np.uint64)
+            N.check(L.gl_fri_commit_round(ref, arity_bits, N.np_ptr(want)), ctx.h)
+            got = []
+            for g, f in enumerate(states):
+                loc = np.empty((4 << h) // shards, dtype=np.uint64)
+                N.check(L.gl_fri_commit_round_sharded(f, arity_bits, g, shards, N.np_ptr(loc)), ctx.h)
+                got.append(loc)
+            assert np.array_equal(np.concatenate(got), want), rnd
+            for f in [ref] + states:
+                N.check(L.gl_fri_fold(f, N.np_ptr(np.ascontiguousarray(betas[rnd]))), ctx.h)
+        out = [np.empty(2 * 16, dtype=np.uint64) for _ in range(1 + shards)]
+        for f, o in zip([ref] + states, out):
+            ln = C.c_size_t()
+            N.check(L.gl_fri_final_poly(f, N.np_ptr(o), o.size, C.byref(ln)), ctx.h)
+            assert ln.value == 32 >> r
+        assert all(np.array_equal(o[:16], out[0][:16]) for o in out)
+    finally:
+        for f in [ref] + states:
+            L.gl_fri_destroy(f)
