@@ -280,6 +280,9 @@ int gl_fri_commit_round_sharded(gl_fri* f, uint32_t arity_bits, uint32_t shard_i
                                 uint64_t* cap_out);
 /*   fold:   with beta from the transcript, values' = fold(values, beta) on the coset shift^arity. */
 int gl_fri_fold(gl_fri* f, const uint64_t beta[2]);
+/* batch-FRI mixing step (plonky2/src/batch_fri/prover.rs:118-132): when `f`'s codeword has been folded down to the
+ * length of `other`'s (the next, lower-degree instance from its own gl_fri_begin), values <- values * beta + other's. */
+int gl_fri_mix(gl_fri* f, const gl_fri* other, const uint64_t beta[2]);
 /* Final polynomial after the last fold, truncated by 2^rate_bits (prover.rs:134-139):
  * *len_out coefficients (2 words each) written to out (capacity `cap_words` words). */
 int gl_fri_final_poly(gl_fri* f, uint64_t* out, size_t cap_words, size_t* len_out);

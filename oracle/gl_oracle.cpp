@@ -855,7 +855,39 @@ void ext_coset_fft(std::vector<E2>& v, u64 shift) {
     coset_fft_with_options(b.data(), n, shift, 0, nullptr);
     for (size_t i = 0; i < n; i++) v[i] = E2{canon(a[i]), canon(b[i])};
 }
+void ext_coset_ifft(std::vector<E2>& v, u64 shift) {
+    size_t n = v.size();
+    std::vector<u64> a(n), b(n);
+    for (size_t i = 0; i < n; i++) {
+        a[i] = v[i].a;
+        b[i] = v[i].b;
+    }
+    coset_ifft(a.data(), n, shift);
+    coset_ifft(b.data(), n, shift);
+    for (size_t i = 0; i < n; i++) v[i] = E2{canon(a[i]), canon(b[i])};
+}
 }  // namespace
+
+// ------------------------------------------------------------------ batch FRI
+// BatchFriOracle::from_coeffs (batch_fri/oracle.rs:71-131) + BatchMerkleTree::new (hash/batch_merkle_tree.rs:34-128)
+struct glo_batch_commit {
+    struct Group {
+        uint32_t degree_bits;
+        size_t B, n, N;
+        std::vector<u64> coeffs;  // B x n
+        std::vector<u64> leaves;  // N x B row-major, leaf j = LDE row bitrev(j)
+    };
+    struct Stage {
+        size_t N, W;
+        uint32_t cap_height;
+        std::vector<u64> rows;    // N x W (stage 0: the group's leaves; later: previous cap digest || group row)
+        std::vector<Hash> digests, cap;
+    };
+    uint32_t rate_bits, cap_height;
+    std::vector<Group> groups;
+    std::vector<Stage> stages;
+    std::vector<std::pair<size_t, size_t>> where;  // polynomial index -> (group, index in group)
+};
 
 extern "C" {
 
@@ -1350,6 +1382,255 @@ int glo_prove_openings(const glo_commit* const* oracles, size_t n_oracles, const
     for (auto& c : coeffs) {
         put_u64(buf, c.a);
         put_u64(buf, c.b);
+    }
+    put_u64(buf, pow_witness);
+    *out = (uint8_t*)malloc(buf.size());
+    memcpy(*out, buf.data(), buf.size());
+    *out_len = buf.size();
+    return 0;
+}
+
+glo_batch_commit* glo_batch_commit_new(const uint64_t* const* polys, const uint32_t* log_lens, size_t num_polys,
+                                       uint32_t rate_bits, uint32_t cap_height, int is_coeffs) {
+    for (size_t i = 0; i + 1 < num_polys; i++)
+        if (log_lens[i] < log_lens[i + 1]) return nullptr;  // assert!(degree_bits.windows(2).all(|p| p[0] >= p[1]))
+    glo_batch_commit* c = new glo_batch_commit();
+    c->rate_bits = rate_bits;
+    c->cap_height = cap_height;
+    size_t group_start = 0;
+    for (size_t i = 0; i < num_polys; i++) {
+        if (i == num_polys - 1 || log_lens[i] > log_lens[i + 1]) {
+            glo_batch_commit::Group g;
+            g.degree_bits = log_lens[i];
+            g.B = i + 1 - group_start;
+            g.n = (size_t)1 << g.degree_bits;
+            g.N = g.n << rate_bits;
+            g.coeffs.resize(g.B * g.n);
+            std::vector<u64> lde(g.N);
+            g.leaves.resize(g.N * g.B);
+            const uint32_t lgN = g.degree_bits + rate_bits;
+            for (size_t b = 0; b < g.B; b++) {
+                u64* co = g.coeffs.data() + b * g.n;
+                memcpy(co, polys[group_start + b], g.n * 8);
+                if (!is_coeffs) ifft_with_options(co, g.n, nullptr);  // values.map(|v| v.ifft())
+                for (size_t k = 0; k < g.n; k++) co[k] = canon(co[k]);
+                // PolynomialBatch::lde_values (oracle.rs:114-139): lde + coset_fft
+                memcpy(lde.data(), co, g.n * 8);
+                memset(lde.data() + g.n, 0, (g.N - g.n) * 8);
+                coset_fft_with_options(lde.data(), g.N, MULTIPLICATIVE_GROUP_GENERATOR, rate_bits, nullptr);
+                // transpose + reverse_index_bits_in_place (oracle.rs:104-106)
+                for (size_t j = 0; j < g.N; j++) g.leaves[(size_t)reverse_bits(j, lgN) * g.B + b] = canon(lde[j]);
+                c->where.emplace_back(c->groups.size(), b);
+            }
+            c->groups.push_back(std::move(g));
+            group_start = i + 1;
+        }
+    }
+    // BatchMerkleTree::new: a chain of fill_digests_buf calls, cap of stage k = number of leaves of stage k+1
+    std::vector<Hash> cap;
+    for (size_t k = 0; k < c->groups.size(); k++) {
+        const glo_batch_commit::Group& g = c->groups[k];
+        glo_batch_commit::Stage st;
+        st.N = g.N;
+        st.cap_height = k + 1 < c->groups.size() ? c->groups[k + 1].degree_bits + rate_bits : cap_height;
+        if (st.cap_height > log2_strict(st.N) || (k + 1 < c->groups.size() && st.cap_height >= log2_strict(st.N))) {
+            delete c;
+            return nullptr;
+        }
+        if (k == 0) {
+            st.W = g.B;
+            st.rows = g.leaves;
+        } else {  // new_leaves = cap_hash.to_vec() ++ cur[i]   (batch_merkle_tree.rs:85-96)
+            st.W = 4 + g.B;
+            st.rows.resize(st.N * st.W);
+            for (size_t i = 0; i < st.N; i++) {
+                memcpy(st.rows.data() + i * st.W, cap[i].e, 32);
+                memcpy(st.rows.data() + i * st.W + 4, g.leaves.data() + i * g.B, g.B * 8);
+            }
+        }
+        const size_t C = (size_t)1 << st.cap_height;
+        st.digests.resize(2 * (st.N - C));
+        st.cap.resize(C);
+        merkle_build(st.rows.data(), st.N, st.W, st.cap_height, st.digests.data(), st.cap.data(), 8);
+        cap = st.cap;
+        c->stages.push_back(std::move(st));
+    }
+    return c;
+}
+void glo_batch_commit_free(glo_batch_commit* c) { delete c; }
+size_t glo_batch_commit_cap(const glo_batch_commit* c, uint64_t* out) {
+    const std::vector<Hash>& cap = c->stages.back().cap;
+    if (out) memcpy(out, cap.data(), cap.size() * 32);
+    return cap.size();
+}
+
+// BatchFriOracle::prove_openings + batch_fri_proof (batch_fri/oracle.rs:124-183, batch_fri/prover.rs:30-215), serialised
+// like write_fri_proof. instances[i] = the opening batches of the polynomials of degree 2^degree_bits[i].
+int glo_batch_prove_openings(const glo_batch_commit* const* oracles, size_t n_oracles, const uint32_t* degree_bits,
+                             const glo_fri_instance* instances, size_t n_instances, glo_challenger* ch,
+                             const glo_fri_params* params, uint8_t** out, size_t* out_len) {
+    if (n_oracles == 0 || n_instances == 0) return 1;
+    const uint32_t rate_bits = params->rate_bits;
+    E2 alpha = get_extension_challenge(ch);
+    std::vector<std::vector<E2>> lde_coeffs, lde_values;
+    for (size_t ii = 0; ii < n_instances; ii++) {
+        const size_t n = (size_t)1 << degree_bits[ii];
+        u64 alpha_count = 0;
+        std::vector<E2> final_poly;
+        for (size_t bi = 0; bi < instances[ii].n_batches; bi++) {
+            const glo_fri_batch& batch = instances[ii].batches[bi];
+            E2 point{batch.point[0], batch.point[1]};
+            std::vector<E2> comp(n, e2(0));
+            E2 base_power = e2(1);
+            for (size_t j = 0; j < batch.num_polys; j++) {
+                const glo_batch_commit* oc = oracles[batch.oracle_index[j]];
+                const auto wh = oc->where[batch.poly_index[j]];
+                const glo_batch_commit::Group& g = oc->groups[wh.first];
+                if (g.n != n) return 2;
+                const u64* poly = g.coeffs.data() + wh.second * n;
+                alpha_count++;
+                for (size_t k = 0; k < n; k++) comp[k] = eadd(comp[k], escale(base_power, poly[k]));
+                base_power = emul(base_power, alpha);
+            }
+            std::vector<E2> bs(n);
+            E2 acc = e2(0);
+            for (size_t k = n; k-- > 0;) {
+                acc = eadd(emul(acc, point), comp[k]);
+                bs[n - 1 - k] = acc;
+            }
+            bs.pop_back();
+            std::reverse(bs.begin(), bs.end());
+            bs.push_back(e2(0));
+            E2 sh = eexp(alpha, alpha_count);
+            alpha_count = 0;
+            if (final_poly.empty()) final_poly = bs;
+            else
+                for (size_t k = 0; k < n; k++) final_poly[k] = eadd(emul(final_poly[k], sh), bs[k]);
+        }
+        if (final_poly.size() != n) return 3;  // assert_eq!(final_poly.len(), 1 << degree_bits[i])
+        std::vector<E2> co(n << rate_bits, e2(0));
+        for (size_t k = 0; k < n; k++) co[k] = final_poly[k];
+        std::vector<E2> va = co;
+        ext_coset_fft(va, MULTIPLICATIVE_GROUP_GENERATOR);
+        lde_coeffs.push_back(std::move(co));
+        lde_values.push_back(std::move(va));
+    }
+    // batch_fri_proof's shape checks (prover.rs:38-57)
+    const size_t N = lde_coeffs[0].size();
+    for (size_t i = 0; i + 1 < lde_values.size(); i++)
+        if (lde_values[i].size() <= lde_values[i + 1].size()) return 4;
+    // batch_fri_committed_trees (prover.rs:88-147)
+    std::vector<Tree> trees;
+    std::vector<E2> final_coeffs = lde_coeffs[0], final_values = lde_values[0];
+    u64 shift = MULTIPLICATIVE_GROUP_GENERATOR;
+    size_t polynomial_index = 1;
+    for (uint32_t round = 0; round < params->num_reductions; round++) {
+        const uint32_t arity_bits = params->reduction_arity_bits[round];
+        const size_t arity = (size_t)1 << arity_bits;
+        std::vector<u64> flat(final_values.size() * 2);
+        for (size_t i = 0; i < final_values.size(); i++) {
+            flat[2 * i] = canon(final_values[i].a);
+            flat[2 * i + 1] = canon(final_values[i].b);
+        }
+        reverse_index_bits_in_place(flat.data(), final_values.size(), 2);
+        Tree t;
+        t.N = final_values.size() / arity;
+        t.W = 2 * arity;
+        t.cap_height = params->cap_height;
+        if (t.cap_height > log2_strict(t.N)) return 5;
+        const size_t C = (size_t)1 << t.cap_height;
+        t.leaves = std::move(flat);
+        t.digests.resize(2 * (t.N - C));
+        t.cap.resize(C);
+        merkle_build(t.leaves.data(), t.N, t.W, t.cap_height, t.digests.data(), t.cap.data(), 8);
+        observe_cap(ch, t.cap);
+        trees.push_back(std::move(t));
+        const E2 beta = get_extension_challenge(ch);
+        std::vector<E2> folded(final_coeffs.size() / arity);
+        for (size_t j = 0; j < folded.size(); j++) {
+            E2 sum = e2(0);
+            for (size_t i = arity; i-- > 0;) sum = eadd(emul(sum, beta), final_coeffs[arity * j + i]);
+            folded[j] = sum;
+        }
+        final_coeffs = std::move(folded);
+        shift = fexp(shift, arity);
+        final_values = final_coeffs;
+        ext_coset_fft(final_values, shift);
+        if (polynomial_index != lde_values.size() && final_values.size() == lde_values[polynomial_index].size()) {
+            for (size_t i = 0; i < final_values.size(); i++)
+                final_values[i] = eadd(emul(final_values[i], beta), lde_values[polynomial_index][i]);
+            polynomial_index++;
+        }
+        final_coeffs = final_values;
+        ext_coset_ifft(final_coeffs, shift);
+    }
+    if (polynomial_index != lde_values.size()) return 6;
+    final_coeffs.resize(final_coeffs.size() >> rate_bits);
+    for (auto& cf : final_coeffs) observe_ext(ch, cf);
+    // fri_proof_of_work (smallest qualifying nonce)
+    const uint32_t min_leading_zeros = params->proof_of_work_bits;
+    u64 inter[12];
+    memcpy(inter, ch->sponge_state, sizeof(inter));
+    const size_t witness_input_pos = ch->input_buffer.size();
+    for (size_t i = 0; i < witness_input_pos; i++) inter[i] = ch->input_buffer[i];
+    u64 pow_witness = 0;
+    for (u64 cand = 0;; cand++) {
+        u64 st[12];
+        memcpy(st, inter, sizeof(st));
+        st[witness_input_pos] = cand;
+        poseidon(st);
+        const u64 resp = canon(st[7]);
+        const uint32_t lz = resp == 0 ? 64 : (uint32_t)__builtin_clzll(resp);
+        if (lz >= min_leading_zeros) {
+            pow_witness = cand;
+            break;
+        }
+    }
+    observe_element(ch, pow_witness);
+    (void)get_challenge(ch);
+    // serialise (write_fri_proof); batch_fri_prover_query_round (prover.rs:171-215)
+    std::vector<uint8_t> buf;
+    for (auto& t : trees)
+        for (auto& h : t.cap) put_hash(buf, h);
+    for (uint32_t q = 0; q < params->num_query_rounds; q++) {
+        size_t x_index = (size_t)(get_challenge(ch) % N);
+        for (size_t o = 0; o < n_oracles; o++) {
+            const glo_batch_commit* oc = oracles[o];
+            const uint32_t h0 = oc->groups[0].degree_bits + rate_bits;
+            // t.values(x_index).flatten()
+            for (const auto& g : oc->groups) {
+                const size_t idx = x_index >> (h0 - (g.degree_bits + rate_bits));
+                for (size_t i = 0; i < g.B; i++) put_u64(buf, g.leaves[idx * g.B + i]);
+            }
+            // t.open_batch(x_index): the stages' sibling paths back to back
+            std::vector<Hash> sib;
+            for (const auto& st : oc->stages) {
+                const uint32_t hk = log2_strict(st.N);
+                const size_t len = hk - st.cap_height;
+                std::vector<Hash> part(len);
+                merkle_prove(x_index >> (h0 - hk), st.N, st.cap_height, st.digests.data(), part.data());
+                sib.insert(sib.end(), part.begin(), part.end());
+            }
+            buf.push_back((uint8_t)sib.size());
+            for (auto& h : sib) put_hash(buf, h);
+        }
+        for (size_t i = 0; i < trees.size(); i++) {
+            const uint32_t arity_bits = params->reduction_arity_bits[i];
+            const Tree& t = trees[i];
+            const size_t idx = x_index >> arity_bits;
+            const u64* leaf = t.leaves.data() + idx * t.W;
+            for (size_t k = 0; k < t.W; k++) put_u64(buf, leaf[k]);
+            const size_t len = log2_strict(t.N) - t.cap_height;
+            std::vector<Hash> sib(len);
+            merkle_prove(idx, t.N, t.cap_height, t.digests.data(), sib.data());
+            buf.push_back((uint8_t)len);
+            for (auto& h : sib) put_hash(buf, h);
+            x_index >>= arity_bits;
+        }
+    }
+    for (auto& cf : final_coeffs) {
+        put_u64(buf, cf.a);
+        put_u64(buf, cf.b);
     }
     put_u64(buf, pow_witness);
     *out = (uint8_t*)malloc(buf.size());

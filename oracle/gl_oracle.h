@@ -142,6 +142,23 @@ int glo_prove_openings(const glo_commit* const* oracles, size_t n_oracles,
                        uint64_t* tap_pow_witness, uint64_t* tap_query_indices);
 void glo_free(void*);
 
+/* ---- batch FRI: BatchFriOracle::from_values / from_coeffs (plonky2/src/batch_fri/oracle.rs:45-131) over
+ *      polynomials of non-increasing lengths 2^log_lens[i] with its BatchMerkleTree (hash/batch_merkle_tree.rs:34-128),
+ *      and BatchFriOracle::prove_openings + batch_fri_proof (batch_fri/oracle.rs:124-183, batch_fri/prover.rs:30-215)
+ *      serialised like write_fri_proof. Polynomial indices index each oracle's full polynomial list. */
+typedef struct glo_batch_commit glo_batch_commit;
+glo_batch_commit* glo_batch_commit_new(const uint64_t* const* polys, const uint32_t* log_lens, size_t num_polys,
+                                       uint32_t rate_bits, uint32_t cap_height, int is_coeffs);
+void glo_batch_commit_free(glo_batch_commit*);
+size_t glo_batch_commit_cap(const glo_batch_commit*, uint64_t* out); /* returns the number of cap hashes */
+typedef struct {
+    const glo_fri_batch* batches;
+    size_t n_batches;
+} glo_fri_instance;
+int glo_batch_prove_openings(const glo_batch_commit* const* oracles, size_t n_oracles, const uint32_t* degree_bits,
+                             const glo_fri_instance* instances, size_t n_instances, glo_challenger* challenger,
+                             const glo_fri_params* params, uint8_t** out, size_t* out_len);
+
 /* Restated FRI verifier (plonky2/src/fri/verifier.rs:62-241, challenges.rs:28-75): checks a
  * serialised proof against the initial caps and the claimed openings. challenger must be in the
  * same state prove_openings started from. opened_values: for each batch, for each polynomial,

@@ -29,7 +29,7 @@ EXPORTS = [
     "gl_commit_open", "gl_commit_eval_ext", "gl_openings", "gl_stark_quotient", "gl_lookup_polys", "gl_commit_dev_lde", "gl_commit_dev_coeffs", "gl_partial_products_and_zs", "gl_poseidon_permute_host",
     "gl_poseidon_permute_many", "gl_poseidon_hash_many", "gl_poseidon_hash_no_pad_many", "gl_poseidon_two_to_one_many", "gl_merkle_build", "gl_merkle_destroy",
     "gl_merkle_cap", "gl_merkle_digests", "gl_merkle_open", "gl_fri_begin", "gl_fri_begin_from_coeffs",
-    "gl_fri_destroy", "gl_fri_coeffs", "gl_fri_commit_round", "gl_fri_commit_round_sharded", "gl_fri_fold", "gl_fri_final_poly",
+    "gl_fri_destroy", "gl_fri_coeffs", "gl_fri_commit_round", "gl_fri_commit_round_sharded", "gl_fri_mix", "gl_fri_fold", "gl_fri_final_poly",
     "gl_fri_open", "gl_fri_num_rounds", "gl_fri_pow",
 ]
 
@@ -127,6 +127,7 @@ def lib():
     L.gl_fri_coeffs.argtypes = [vp, vp]
     L.gl_fri_commit_round.argtypes = [vp, C.c_uint32, vp]
     L.gl_fri_commit_round_sharded.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]
+    L.gl_fri_mix.argtypes = [vp, vp, vp]
     L.gl_fri_fold.argtypes = [vp, vp]
     L.gl_fri_final_poly.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.gl_fri_open.argtypes = [vp, C.c_uint32, vp, C.c_size_t, vp, vp]

@@ -2313,6 +2313,31 @@ int gl_fri_fold(gl_fri* f, const uint64_t beta[2]) {
     return GL_OK;
 }
 
+// batch-FRI (batch_fri/prover.rs:118-132): after a fold, when the codeword has shrunk to the size of the next (smaller)
+// instance's LDE, final_values <- final_values * beta + values[next], element by element in natural order -- which is
+// element by element in the shared bit-reversed order too.
+__global__ void k_fri_mix(u64* vals, const u64* other, size_t count, E2 beta) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const E2 v = {vals[2 * i], vals[2 * i + 1]}, w = {other[2 * i], other[2 * i + 1]};
+    const E2 r = e2_add(e2_mul(v, beta), w);
+    vals[2 * i] = canon(r.a);
+    vals[2 * i + 1] = canon(r.b);
+}
+int gl_fri_mix(gl_fri* f, const gl_fri* other, const uint64_t beta[2]) {
+    if (!f || !other || !beta) return set_err(f ? f->ctx : nullptr, GL_ERR_BAD_ARG, "null argument");
+    gl_ctx* ctx = f->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (f->committed || other->committed || !f->values || !other->values)
+        return set_err(ctx, GL_ERR_BAD_ARG, "both codewords must be between rounds (folded, not committed)");
+    if (f->log_cur != other->log_cur) return set_err(ctx, GL_ERR_BAD_SHAPE, "codeword lengths differ: 2^%u vs 2^%u", f->log_cur, other->log_cur);
+    const size_t count = (size_t)1 << f->log_cur;
+    k_fri_mix<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(f->values, other->values, count,
+                                                                         E2{canon(beta[0]), canon(beta[1])});
+    CKL(ctx);
+    return GL_OK;
+}
+
 int gl_fri_final_poly(gl_fri* f, uint64_t* out, size_t cap_words, size_t* len_out) {
     gl_ctx* ctx = f->ctx;
     CK(ctx, cudaSetDevice(ctx->device));

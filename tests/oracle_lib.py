@@ -42,6 +42,10 @@ class FriParams(C.Structure):
     ]
 
 
+class FriInstance(C.Structure):
+    pass
+
+
 class FriBatch(C.Structure):
     _fields_ = [
         ("point", C.c_uint64 * 2),
@@ -50,6 +54,8 @@ class FriBatch(C.Structure):
         ("poly_index", u32p),
     ]
 
+
+FriInstance._fields_ = [("batches", C.POINTER(FriBatch)), ("n_batches", C.c_size_t)]
 
 _lib = None
 
@@ -121,6 +127,15 @@ def lib():
                                        C.c_size_t, C.POINTER(FriBatch), C.c_size_t, u64p, C.c_uint32,
                                        C.c_void_p, C.POINTER(FriParams), C.POINTER(C.c_uint8), C.c_size_t]
     L.glo_eval_poly_base_at_ext.argtypes = [u64p, C.c_size_t, u64p, u64p]
+    L.glo_batch_commit_new.restype = C.c_void_p
+    L.glo_batch_commit_new.argtypes = [C.POINTER(u64p), u32p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int]
+    L.glo_batch_commit_free.argtypes = [C.c_void_p]
+    L.glo_batch_commit_cap.restype = C.c_size_t
+    L.glo_batch_commit_cap.argtypes = [C.c_void_p, u64p]
+    L.glo_batch_prove_openings.restype = C.c_int
+    L.glo_batch_prove_openings.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, u32p, C.POINTER(FriInstance), C.c_size_t,
+                                           C.c_void_p, C.POINTER(FriParams), C.POINTER(C.POINTER(C.c_uint8)),
+                                           C.POINTER(C.c_size_t)]
     L.glo_lookup_polys.restype = C.c_int
     L.glo_lookup_polys.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u32p, C.c_uint32, u64p]
     L.glo_stark_quotient_fibonacci.restype = C.c_int
@@ -461,3 +476,51 @@ def lookup_polys(wires, num_routed_wires, max_quotient_degree_factor, deltas, lo
     if rc != 0:
         raise ZeroDivisionError("Tried to invert zero")
     return out
+
+
+class BatchCommit:
+    """Oracle BatchFriOracle (plonky2/src/batch_fri/oracle.rs:30-131): polys = list of 1-D arrays, lengths non-increasing."""
+
+    def __init__(self, polys, rate_bits, cap_height, is_coeffs=False):
+        self.polys = [np.ascontiguousarray(p, dtype=np.uint64) for p in polys]
+        ptrs = (u64p * len(self.polys))(*[ptr(p) for p in self.polys])
+        logs = np.array([int(np.log2(len(p))) for p in self.polys], dtype=np.uint32)
+        self.h = lib().glo_batch_commit_new(ptrs, logs.ctypes.data_as(u32p), len(self.polys), rate_bits, cap_height,
+                                            int(is_coeffs))
+        if not self.h:
+            raise ValueError("bad batch commitment shape")
+
+    @property
+    def cap(self):
+        n = lib().glo_batch_commit_cap(self.h, None)
+        out = np.zeros((n, 4), dtype=np.uint64)
+        lib().glo_batch_commit_cap(self.h, ptr(out))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().glo_batch_commit_free(self.h)
+            self.h = None
+
+
+def batch_prove_openings(commits, degree_bits, instances, challenger, params):
+    """instances: per degree, a list of (point, [(oracle_index, poly_index), ...]) batches. Returns the proof bytes."""
+    L = lib()
+    handles = (C.c_void_p * len(commits))(*[c.h for c in commits])
+    insts = (FriInstance * len(instances))()
+    keep = []
+    for i, batches in enumerate(instances):
+        barr, k = _make_batches(batches)
+        keep += [barr, k]
+        insts[i].batches = C.cast(barr, C.POINTER(FriBatch))
+        insts[i].n_batches = len(batches)
+    db = np.array(degree_bits, dtype=np.uint32)
+    out = C.POINTER(C.c_uint8)()
+    out_len = C.c_size_t()
+    rc = L.glo_batch_prove_openings(handles, len(commits), db.ctypes.data_as(u32p), insts, len(instances), challenger.h,
+                                    C.byref(params), C.byref(out), C.byref(out_len))
+    if rc != 0:
+        raise RuntimeError("oracle batch prove_openings failed rc=%d" % rc)
+    proof = bytes(C.string_at(out, out_len.value))
+    L.glo_free(out)
+    return proof

@@ -115,3 +115,51 @@ def test_path_compression(pb, oracle):
         assert np.array_equal(a.siblings, b.siblings)
         assert oracle.merkle_verify(vs[i], i, a.siblings, mt.cap.hashes, cap_height)
     mt.close()
+
+
+# ----------------------------------------------------------------------------- batch FRI (batch_fri/oracle.rs, batch_fri/prover.rs)
+def _batch_case(pb, oracle, lens, counts, rate_bits, cap_height, arity_bits, num_queries, pow_bits, two_points):
+    """lens: degree bits per group (decreasing), counts: polynomials per group. Byte-identical proof vs the oracle."""
+    polys, degree_of = [], []
+    for k, c in zip(lens, counts):
+        for j in range(c):
+            polys.append(synth(0x100 + 16 * k + j, (1 << k,)))
+            degree_of.append(k)
+    go = pb.BatchFriOracle.from_values(polys, rate_bits, False, cap_height)
+    oo = oracle.BatchCommit(polys, rate_bits, cap_height)
+    assert np.array_equal(go.cap.hashes, oo.cap)
+    cfg = pb.FriConfig(rate_bits, cap_height, pow_bits, ("Fixed", list(arity_bits)), num_queries)
+    params = pb.FriParams(cfg, False, lens[0], list(arity_bits))
+    ch, och = pb.Challenger(), oracle.Challenger()
+    ch.observe_cap(go.cap)
+    och.observe_cap(oo.cap)
+    zeta = ch.get_extension_challenge()
+    assert och.get_extension_challenge() == zeta
+    instances, oinstances = [], []
+    for k in lens:
+        idx = [i for i, d in enumerate(degree_of) if d == k]
+        batches = [pb.FriBatchInfo(zeta, [pb.FriPolynomialInfo(0, i) for i in idx])]
+        if two_points:
+            gz = pb.field.ext_mul(zeta, (pb.field.primitive_root_of_unity(k), 0))
+            batches.append(pb.FriBatchInfo(gz, [pb.FriPolynomialInfo(0, idx[0])]))
+        instances.append(pb.FriInstanceInfo([pb.FriOracleInfo(len(polys), False)], batches))
+        oinstances.append([(b.point, [(p.oracle_index, p.polynomial_index) for p in b.polynomials]) for b in batches])
+    proof = pb.batch_prove_openings(list(lens), instances, [go], ch, params)
+    want = oracle.batch_prove_openings([oo], list(lens), oinstances, och, oracle.make_params(rate_bits, cap_height, pow_bits, num_queries, list(arity_bits)))
+    assert proof.to_bytes() == want
+    go.close()
+
+
+def test_batch_fri_multiple_polynomials_reference_shape(pb, oracle):
+    # batch_fri/prover.rs:341-477: k = 9, 8, 6, rate 1, cap 5, arities [1, 2, 1], 10 queries, no PoW
+    _batch_case(pb, oracle, [9, 8, 6], [1, 1, 1], 1, 5, [1, 2, 1], 10, 0, False)
+
+
+def test_batch_fri_single_polynomial_reference_shape(pb, oracle):
+    # batch_fri/prover.rs:275-339
+    _batch_case(pb, oracle, [9], [1], 1, 5, [1, 2, 1], 10, 0, False)
+
+
+def test_batch_fri_groups_two_points_pow(pb, oracle):
+    # several polynomials per degree, openings at zeta and g*zeta, grinding, arity 8 then 4
+    _batch_case(pb, oracle, [11, 8, 6], [5, 3, 2], 2, 3, [3, 2, 2], 6, 7, True)

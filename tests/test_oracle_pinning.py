@@ -267,3 +267,23 @@ def test_stark_quotient_fibonacci_satisfies_the_verifier_identity(oracle):
     for c in [(l[0] - 3) * l_first, (l[1] - 5) * l_first, (l[1] - pi[2] - 1) * l_last, cons[3], cons[4]]:
         acc = (acc * alphas[0] + c) % P_
     assert acc != zh * ev(bad[0], z) % P_
+
+
+def test_batch_fri_with_one_degree_equals_plain_fri(oracle):
+    """Pin of the batch-FRI restatement (batch_fri/oracle.rs, batch_fri/prover.rs): with a single degree group the
+    BatchMerkleTree is the MerkleTree and batch_fri_proof is fri_proof, so the proof bytes must equal the plain
+    prove_openings bytes (which the restated verifier accepts, see above)."""
+    log_n, r, h = 8, 2, 3
+    cols = synth(0xD8, (3, 1 << log_n))
+    bc = oracle.BatchCommit([c for c in cols], r, h)
+    pc = oracle.Commit(cols, r, h)
+    assert np.array_equal(bc.cap, pc.cap)
+    params = oracle.make_params(r, h, 5, 6, [2, 3])
+    ch1, ch2 = oracle.Challenger(), oracle.Challenger()
+    for ch in (ch1, ch2):
+        ch.observe_cap(pc.cap)
+    z = (12345, 67890)
+    batches = [(z, [(0, 0), (0, 1), (0, 2)]), ((777, 1), [(0, 1)])]
+    a = oracle.batch_prove_openings([bc], [log_n], [batches], ch1, params)
+    b = oracle.prove_openings([pc], batches, ch2, params)
+    assert a == b
