@@ -48,6 +48,77 @@ __global__ void __launch_bounds__(PassCfg<LOG>::COL_THREADS, PassCfg<LOG>::COL_M
                           (size_t)Cf::TPT * Cf::COL_THREADS);
 }
 
+// Even LOG (E == TPT): both steps of the pass are "radix-E lazy DFT, normalise, multiply by a twiddle", so ONE copy of
+// that body serves both (a rolled 2-trip loop; only the I/O around it differs). The two-copy kernel above is ~90 KiB of
+// SASS and its largest non-ALU stall was instruction fetch (no_instruction 0.9 per issue, profiles/r02); this one is
+// about half that.
+template <int LOG, bool ASYNC_TW>
+__global__ void __launch_bounds__(PassCfg<LOG>::COL_THREADS, PassCfg<LOG>::COL_MIN_BLOCKS) k_ntt_col_shared(ColPass cp) {
+    using Cf = PassCfg<LOG>;
+    static_assert(Cf::E == Cf::TPT, "shared-body column pass needs an even LOG");
+    extern __shared__ __align__(16) u64 smem[];
+    u64* tw_s = smem;                    // 2^LOG words
+    u64* S = smem + (1 << LOG);          // exchange tile
+    u64* mbar = S + Cf::COL_S_WORDS;
+    tma_table_issue(tw_s, cp.tw, (uint32_t)((1 << LOG) * 8), mbar);
+    u64 x[Cf::E];
+    col_load<LOG>(cp, blockIdx.x, threadIdx.x, x);
+    __syncthreads();
+    tma_table_wait(mbar);
+    const int tt = threadIdx.x % Cf::T, t = threadIdx.x / Cf::T;
+    size_t in_off, out_off;
+    int tile;
+    col_unit<LOG>(cp, blockIdx.x, in_off, out_off, tile);
+    const size_t C = (size_t)1 << cp.log_c;
+    if (cp.has_uq) {
+#pragma unroll
+        for (int q = 1; q < Cf::E; q++) x[q] = mul(x[q], cp.uq[q]);
+    }
+    const u64* twp = tw_s + t;           // step 1: tw[q*TPT + t]
+    size_t tws = Cf::TPT;
+    bool skip0 = cp.tw_full == 0;        // step 1, q = 0: the twiddle is 1 unless a scale / coset base is folded in
+#pragma unroll 1
+    for (int s = 0; s < 2; s++) {
+        L3 r[Cf::E];
+#pragma unroll
+        for (int q = 0; q < Cf::E; q++) r[q] = l3_from(x[q]);
+        dft_lazy<Cf::R1>(r);
+        if (ASYNC_TW && s == 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < Cf::E; q++) {
+            u64 y = l3_norm(r[q]);
+            if (!(q == 0 && skip0)) y = mul(y, twp[(size_t)q * tws]);
+            x[q] = y;
+        }
+        if (s == 0) {
+#pragma unroll
+            for (int q = 0; q < Cf::E; q++) S[q * Cf::COL_QPITCH + t * Cf::T + tt] = x[q];
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < Cf::TPT; j++) x[j] = S[t * Cf::COL_QPITCH + j * Cf::T + tt];  // step 2 works on row q = t
+            skip0 = false;
+            const u64* tw2 = cp.twa + (((size_t)t * Cf::TPT) << cp.log_c) + (size_t)tile * Cf::T + tt;  // output p = t*TPT + j
+            if (ASYNC_TW) {
+                __syncthreads();         // every thread holds its part of the tile: S is free
+#pragma unroll
+                for (int j = 0; j < Cf::TPT; j++)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(S + col_twiddle_slot<LOG>(threadIdx.x, j))),
+                                 "l"(tw2 + (size_t)j * C)
+                                 : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                twp = S + col_twiddle_slot<LOG>(threadIdx.x, 0);
+                tws = Cf::COL_THREADS;
+            } else {
+                twp = tw2;
+                tws = C;
+            }
+        }
+    }
+    u64* dst = cp.out + out_off + (size_t)tile * Cf::T + tt;
+#pragma unroll
+    for (int j = 0; j < Cf::TPT; j++) dst[((size_t)t * Cf::TPT + j) * C] = x[j];
+}
+
 template <int LOG, int MODE>
 __global__ void __launch_bounds__(PassCfg<LOG>::ROW_THREADS, PassCfg<LOG>::ROW_MIN_BLOCKS) k_ntt_row(RowPass rp) {
     using Cf = PassCfg<LOG>;
@@ -101,6 +172,62 @@ __global__ void __launch_bounds__(PassCfg<LOG>::ROW_THREADS, PassCfg<LOG>::ROW_M
     }
 }
 
+// Row pass with ONE copy of the radix-E lazy DFT for both steps (even LOG, E == TPT); see k_ntt_col_shared.
+template <int LOG, int MODE>
+__global__ void __launch_bounds__(PassCfg<LOG>::ROW_THREADS, PassCfg<LOG>::ROW_MIN_BLOCKS) k_ntt_row_shared(RowPass rp) {
+    using Cf = PassCfg<LOG>;
+    static_assert(Cf::E == Cf::TPT && Cf::R2 > 0 && LOG >= 4, "shared-body row pass needs an even LOG >= 4");
+    extern __shared__ __align__(16) u64 smem[];
+    u64* tw_s = smem;
+    u64* S = smem + (1 << LOG);
+    u64* mbar = S + ntt_row_smem_bytes(LOG, MODE == RM_NATURAL) / 8;
+    u64 x[Cf::E];
+    tma_table_issue(tw_s, rp.tw, (uint32_t)((1 << LOG) * 8), mbar);
+    row_load<LOG, MODE>(rp, blockIdx.x, threadIdx.x, x);
+    __syncthreads();
+    tma_table_wait(mbar);
+    const int l = threadIdx.x / Cf::TPT, t = threadIdx.x % Cf::TPT;
+    u64* Sl = S + (size_t)l * Cf::ROW_S_WORDS;
+    if (rp.has_uq) {
+#pragma unroll
+        for (int q = 1; q < Cf::E; q++) x[q] = mul(x[q], rp.uq[q]);
+    }
+    const bool skip0 = rp.tw_full == 0;
+    // `phase` starts from a value the compiler cannot see (always 0: log_r >= 0), so that it neither peels the first
+    // trip nor unswitches the loop -- either would put back the second copy of the DFT this kernel exists to avoid
+    int phase = rp.log_r < 0;
+#pragma unroll 1
+    for (int s = 0; s < 2; s++) {
+        L3 r[Cf::E];
+#pragma unroll
+        for (int q = 0; q < Cf::E; q++) r[q] = l3_from(x[q]);
+        dft_lazy<Cf::R1>(r);
+        if (phase == 0) {
+            phase = 1;
+#pragma unroll
+            for (int q = 0; q < Cf::E; q++) {
+                u64 y = l3_norm(r[q]);
+                if (!(q == 0 && skip0)) y = mul(y, tw_s[q * Cf::TPT + t]);
+                Sl[q * Cf::ROW_PITCH + t] = y;
+            }
+            __syncwarp();  // a line's TPT <= 32 threads sit in one warp
+#pragma unroll
+            for (int j = 0; j < Cf::TPT; j++) x[j] = Sl[t * Cf::ROW_PITCH + j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < Cf::TPT; j++) x[j] = l3_norm(r[j]);
+        }
+    }
+    if (MODE == RM_BITREV) {
+        row_store_bitrev<LOG>(rp, blockIdx.x, threadIdx.x, 0, x);
+    } else {
+        __syncthreads();  // the gather tile aliases the exchange buffers
+        row_gather_write<LOG>(S, threadIdx.x, 0, x);
+        __syncthreads();
+        row_store_natural<LOG>(rp, S, blockIdx.x, threadIdx.x, blockDim.x);
+    }
+}
+
 __global__ void k_fill_step(int log, u64 scale, u64 base, u64* out) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < (1u << log)) out[j] = table_step_entry(log, j, scale, base);
@@ -140,21 +267,29 @@ static int launch_col(gl_ctx* ctx, const ColPass& cp, size_t ncols) {
         CKL(ctx);
         return GL_OK;
     };
+    if constexpr (PassCfg<LOG>::E == PassCfg<LOG>::TPT) {
+        if (ctx->ntt_variant == 0) return cp.has_uq ? go(k_ntt_col_shared<LOG, true>) : go(k_ntt_col_shared<LOG, false>);
+    }
     return cp.has_uq ? go(k_ntt_col<LOG, true>) : go(k_ntt_col<LOG, false>);
 }
 template <int LOG, int MODE>
 static int launch_row(gl_ctx* ctx, const RowPass& rp) {
     const size_t smem = (size_t)(1 << LOG) * 8 + ntt_row_smem_bytes(LOG, MODE == RM_NATURAL) + 16;
-    const void* fn = (const void*)k_ntt_row<LOG, MODE>;
-    if (!ctx->smem_attr_done.count(fn)) {
-        CK(ctx, cudaFuncSetAttribute(k_ntt_row<LOG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(ctx, cudaFuncSetAttribute(k_ntt_row<LOG, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared));
-        ctx->smem_attr_done.insert(fn);
+    auto go = [&](auto kern) -> int {
+        const void* fn = (const void*)kern;
+        if (!ctx->smem_attr_done.count(fn)) {
+            CK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            ctx->smem_attr_done.insert(fn);
+        }
+        kern<<<row_blocks<LOG>(rp), PassCfg<LOG>::ROW_THREADS, smem, ctx->stream>>>(rp);
+        CKL(ctx);
+        return GL_OK;
+    };
+    if constexpr (PassCfg<LOG>::E == PassCfg<LOG>::TPT && LOG >= 4) {
+        if (ctx->ntt_variant == 0) return go(k_ntt_row_shared<LOG, MODE>);
     }
-    k_ntt_row<LOG, MODE><<<row_blocks<LOG>(rp), PassCfg<LOG>::ROW_THREADS, smem, ctx->stream>>>(rp);
-    CKL(ctx);
-    return GL_OK;
+    return go(k_ntt_row<LOG, MODE>);
 }
 static int dispatch_col(gl_ctx* ctx, int a, const ColPass& cp, size_t ncols) {
     switch (a) {

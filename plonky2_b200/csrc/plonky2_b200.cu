@@ -50,6 +50,7 @@ struct gl_ctx {
     u64* dstage = nullptr;                      // device staging for openings
     size_t dstage_words = 0;
     uint32_t ntt_group = 0;                     // 0 = auto
+    int ntt_variant = 0;                        // 0 = shared-body column pass for even LOG, 1 = two-copy kernels (A/B switch)
     int sm_count = 0;                           // queried once for ctx->device in gl_ctx_create
     int coop_ok = 0;                            // cooperative launch supported on this device
     int coop_blocks_per_sm = 0;                 // resident CTAs/SM of k_merkle_upper on this device
@@ -591,7 +592,9 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
     TRY(commit_alloc(ctx, c, cap_height, nullptr));
     // Column chunks flow through  H2D copy -> iNTT -> LDE; the copy of chunk k+1 (separate stream) overlaps the
     // transforms of chunk k.
-    const uint32_t CH = 32;  // 32 columns: launches big enough for full waves, first-chunk H2D exposure ~5 ms at n = 2^20
+    // 32-column chunks: launches big enough for full waves; the FIRST chunk is 8 columns so that only ~1.2 ms of H2D
+    // (n = 2^20) is exposed before the first transform starts instead of ~5 ms.
+    const uint32_t CH = 32, CH0 = 8;
     const bool overlap = (mem == GL_MEM_HOST) && B > CH;
     struct EventList {  // destroyed on every exit path
         std::vector<cudaEvent_t> v;
@@ -600,15 +603,21 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
         }
     } evl;
     std::vector<cudaEvent_t>& evs = evl.v;
+    std::vector<std::pair<uint32_t, uint32_t>> chunks;  // (first column, count)
     if (overlap) {
+        for (uint32_t g0 = 0; g0 < B;) {
+            const uint32_t want = g0 == 0 ? CH0 : CH, gc = (B - g0 < want) ? B - g0 : want;
+            chunks.emplace_back(g0, gc);
+            g0 += gc;
+        }
         if (!ctx->copy_stream) CK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         cudaEvent_t ready;
         CK(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
         CK(ctx, cudaEventRecord(ready, ctx->stream));  // the stream-ordered allocations above
         CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
         cudaEventDestroy(ready);
-        for (uint32_t g0 = 0; g0 < B; g0 += CH) {
-            const uint32_t gc = (B - g0 < CH) ? B - g0 : CH;
+        for (auto& ch : chunks) {
+            const uint32_t g0 = ch.first, gc = ch.second;
             if (col_stride == n) {
                 CK(ctx, cudaMemcpyAsync(c->coeffs + (size_t)g0 * n, cols + (size_t)g0 * n, (size_t)gc * n * 8,
                                         cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -621,17 +630,14 @@ static int commit_build(gl_ctx* ctx, gl_commit* c, const u64* cols, size_t col_s
             CK(ctx, cudaEventRecord(e, ctx->copy_stream));
             evs.push_back(e);
         }
-    } else if (mem == GL_MEM_HOST) {
-        CK(ctx, cudaMemcpy2DAsync(c->coeffs, n * 8, cols, col_stride * 8, n * 8, B, cudaMemcpyHostToDevice, ctx->stream));
     } else {
-        CK(ctx, cudaMemcpy2DAsync(c->coeffs, n * 8, cols, col_stride * 8, n * 8, B, cudaMemcpyDeviceToDevice,
-                                  ctx->stream));
+        chunks.emplace_back(0u, B);
+        CK(ctx, cudaMemcpy2DAsync(c->coeffs, n * 8, cols, col_stride * 8, n * 8, B,
+                                  mem == GL_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    const uint32_t step = overlap ? CH : B;
-    for (uint32_t g0 = 0, k = 0; g0 < B; g0 += step, k++) {
-        const uint32_t gc = (B - g0 < step) ? B - g0 : step;
+    for (size_t k = 0; k < chunks.size(); k++) {
         if (overlap) CK(ctx, cudaStreamWaitEvent(ctx->stream, evs[k], 0));
-        TRY(commit_chunk(ctx, c, g0, gc, is_coeffs ? 1 : 0));
+        TRY(commit_chunk(ctx, c, chunks[k].first, chunks[k].second, is_coeffs ? 1 : 0));
     }
     return commit_finish(ctx, c, salt, mem);
 }
@@ -1321,7 +1327,9 @@ int gl_ctx_synchronize(gl_ctx* ctx) {
 }
 uint64_t gl_ctx_launch_count(const gl_ctx* ctx) { return ctx->launches; }
 int gl_ctx_set_ntt_group(gl_ctx* ctx, uint32_t columns) {
-    ctx->ntt_group = columns;
+    // bit 31 selects the kernel variant of the column pass (a measurement switch, see gl_ntt_host.cuh)
+    ctx->ntt_variant = (columns >> 31) & 1;
+    ctx->ntt_group = columns & 0x7FFFFFFFu;
     return GL_OK;
 }
 int gl_ctx_set_profiling(gl_ctx* ctx, int on) {

@@ -160,6 +160,136 @@ class FriProof:
         put(np.array([self.pow_witness], dtype=np.uint64))
         return bytes(out)
 
+    def compress(self, indices, params):
+        """FriProof::compress (fri/proof.rs:137-238): per Merkle tree, drop the siblings the verifier can recompute from
+        the other queries (compress_merkle_proofs), drop from every step the evaluation it can infer, and keep one entry
+        per distinct index."""
+        from .batch_merkle_tree import compress_merkle_proofs
+        from .hash import MerkleProof
+
+        cap_height = params.config.cap_height
+        arity_bits = params.reduction_arity_bits
+        nred = len(arity_bits)
+        ntrees = len(self.query_round_proofs[0].initial_trees_proof.evals_proofs)
+        it_idx = [[] for _ in range(ntrees)]
+        it_leaves = [[] for _ in range(ntrees)]
+        it_proofs = [[] for _ in range(ntrees)]
+        st_idx = [[] for _ in range(nred)]
+        st_evals = [[] for _ in range(nred)]
+        st_proofs = [[] for _ in range(nred)]
+        for index, qrp in zip(indices, self.query_round_proofs):
+            for i, (leaf, sib) in enumerate(qrp.initial_trees_proof.evals_proofs):
+                it_idx[i].append(index)
+                it_leaves[i].append(leaf)
+                it_proofs[i].append(MerkleProof(sib))
+            for i, st in enumerate(qrp.steps):
+                within = index & ((1 << arity_bits[i]) - 1)
+                index >>= arity_bits[i]
+                st_idx[i].append(index)
+                st_evals[i].append(np.delete(np.asarray(st.evals), within, axis=0))  # remove the inferable element
+                st_proofs[i].append(MerkleProof(st.merkle_proof))
+        it_proofs = [compress_merkle_proofs(cap_height, i, p) for i, p in zip(it_idx, it_proofs)]
+        st_proofs = [compress_merkle_proofs(cap_height, i, p) for i, p in zip(st_idx, st_proofs)]
+        initial, steps = {}, [dict() for _ in range(nred)]
+        for i, index in enumerate(indices):
+            initial.setdefault(index, FriInitialTreeProof([(it_leaves[j][i], it_proofs[j][i].siblings) for j in range(ntrees)]))
+            for j in range(nred):
+                index >>= arity_bits[j]
+                steps[j].setdefault(index, FriQueryStep(st_evals[j][i], st_proofs[j][i].siblings))
+        return CompressedFriProof(self.commit_phase_merkle_caps, list(indices), initial, steps, self.final_poly,
+                                  self.pow_witness)
+
+
+@dataclass
+class CompressedFriProof:
+    """CompressedFriProof / CompressedFriQueryRounds (fri/proof.rs:92-112,124-135)."""
+    commit_phase_merkle_caps: List[MerkleCap]
+    indices: List[int]
+    initial_trees_proofs: dict      # index -> FriInitialTreeProof
+    steps: List[dict]               # per reduction: index -> FriQueryStep
+    final_poly: np.ndarray
+    pow_witness: int
+
+    def to_bytes(self):
+        """write_compressed_fri_proof (util/serialization/mod.rs:2034-2076): caps, u32 indices, the initial proofs and
+        every reduction's steps in increasing index order, final poly, pow witness."""
+        out = bytearray()
+
+        def put(arr):
+            out.extend(np.ascontiguousarray(arr, dtype="<u8").tobytes())
+
+        for cap in self.commit_phase_merkle_caps:
+            put(cap.hashes)
+        out.extend(np.array(self.indices, dtype="<u4").tobytes())
+        for _, itp in sorted(self.initial_trees_proofs.items()):
+            for leaf, sib in itp.evals_proofs:
+                put(leaf)
+                out.append(len(sib))
+                put(sib)
+        for h in self.steps:
+            for _, st in sorted(h.items()):
+                put(st.evals)
+                out.append(len(st.merkle_proof))
+                put(st.merkle_proof)
+        put(self.final_poly)
+        put(np.array([self.pow_witness], dtype=np.uint64))
+        return bytes(out)
+
+    def decompress_with(self, inferred_evals, params, lde_bits, ctx=None):
+        """CompressedFriProof::decompress (fri/proof.rs:240-360) given the elements the verifier infers
+        (`inferred_evals[q][j]` = the evaluation removed from query q's step j; plonk/proof.rs get_inferred_elements
+        computes them from the openings): re-insert them, decompress every tree's Merkle proofs and re-expand
+        duplicate indices."""
+        from .batch_merkle_tree import decompress_merkle_proofs
+        from .hash import MerkleProof
+
+        cap_height = params.config.cap_height
+        arity_bits = params.reduction_arity_bits
+        nred = len(arity_bits)
+        ntrees = len(next(iter(self.initial_trees_proofs.values())).evals_proofs)
+        # distinct indices in first-seen order, like the reference's `seen` bookkeeping
+        it_idx = [[] for _ in range(ntrees)]
+        it_leaves = [[] for _ in range(ntrees)]
+        it_proofs = [[] for _ in range(ntrees)]
+        st_idx = [[] for _ in range(nred)]
+        st_evals = [[] for _ in range(nred)]
+        st_proofs = [[] for _ in range(nred)]
+        seen_init, seen_step = set(), [set() for _ in range(nred)]
+        for q, index in enumerate(self.indices):
+            if index not in seen_init:
+                seen_init.add(index)
+                for i, (leaf, sib) in enumerate(self.initial_trees_proofs[index].evals_proofs):
+                    it_idx[i].append(index)
+                    it_leaves[i].append(leaf)
+                    it_proofs[i].append(MerkleProof(sib))
+            for j in range(nred):
+                within = index & ((1 << arity_bits[j]) - 1)
+                index >>= arity_bits[j]
+                if index not in seen_step[j]:
+                    seen_step[j].add(index)
+                    st = self.steps[j][index]
+                    ev = np.insert(np.asarray(st.evals), within, np.asarray(inferred_evals[q][j], dtype=np.uint64), axis=0)
+                    st_idx[j].append(index)
+                    st_evals[j].append(ev)
+                    st_proofs[j].append(MerkleProof(st.merkle_proof))
+        heights = [lde_bits]
+        for a in arity_bits:
+            heights.append(heights[-1] - a)
+        it_full = [decompress_merkle_proofs(lv, ix, pr, lde_bits, cap_height, ctx) for lv, ix, pr in zip(it_leaves, it_idx, it_proofs)]
+        st_full = [decompress_merkle_proofs([e.reshape(-1) for e in ev], ix, pr, heights[j + 1], cap_height, ctx)
+                   for j, (ev, ix, pr) in enumerate(zip(st_evals, st_idx, st_proofs))]
+        rounds = []
+        for index in self.indices:
+            init = FriInitialTreeProof([(it_leaves[i][it_idx[i].index(index)], it_full[i][it_idx[i].index(index)].siblings)
+                                        for i in range(ntrees)])
+            steps = []
+            for j in range(nred):
+                index >>= arity_bits[j]
+                k = st_idx[j].index(index)
+                steps.append(FriQueryStep(st_evals[j][k], st_full[j][k].siblings))
+            rounds.append(FriQueryRound(init, steps))
+        return FriProof(self.commit_phase_merkle_caps, rounds, self.final_poly, self.pow_witness)
+
 
 # ------------------------------------------------------------------ prover
 class _FriState:

@@ -1,8 +1,14 @@
 #!/bin/bash
-# Round-2 evidence in one gpurun call: ncu --set full of the NTT passes (iNTT col/row-natural, LDE col/row-bitrev)
-# and of the leaf hash, plus the launch list of one bench step.
+# Round-2 evidence in one gpurun call (1 GPU): parity tests, the bench line (with the CPU leg and the recursion-shaped
+# proof), the CPU reference arm, ncu --set full of the NTT passes and of the leaf hash, the launch list of one bench step.
 mkdir -p gpurun_out
 TAG=${1:-r02}
+export GL_REQUIRE_GPU=1
+(time timeout 500 python -m pytest tests -m gpu -x -q) > gpurun_out/pytest_$TAG.log 2>&1
+tail -3 gpurun_out/pytest_$TAG.log
+timeout 400 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+cut -c1-200 gpurun_out/bench_$TAG.json
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err
 ncu --set full --clock-control none --import-source on -k regex:"k_ntt" -c 4 \
     -o gpurun_out/prof_ntt_$TAG -f python bench.py --steps 1 --warmup 1 --cols 64 --no-cpu --no-extra --no-ntt > gpurun_out/prof_ntt_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_leaf_hash" -s 1 -c 1 \
