@@ -193,29 +193,28 @@ __global__ void __launch_bounds__(PassCfg<LOG>::ROW_THREADS, PassCfg<LOG>::ROW_M
         for (int q = 1; q < Cf::E; q++) x[q] = mul(x[q], rp.uq[q]);
     }
     const bool skip0 = rp.tw_full == 0;
-    // `phase` starts from a value the compiler cannot see (always 0: log_r >= 0), so that it neither peels the first
-    // trip nor unswitches the loop -- either would put back the second copy of the DFT this kernel exists to avoid
-    int phase = rp.log_r < 0;
+    // step 2 has no twiddle: `do_mul` (a uniform, loop-carried flag) skips the multiplies there, so that the DFT AND the
+    // normalise/multiply code exist once and only the exchange differs between the trips
+    bool do_mul = true;
 #pragma unroll 1
     for (int s = 0; s < 2; s++) {
         L3 r[Cf::E];
 #pragma unroll
         for (int q = 0; q < Cf::E; q++) r[q] = l3_from(x[q]);
         dft_lazy<Cf::R1>(r);
-        if (phase == 0) {
-            phase = 1;
 #pragma unroll
-            for (int q = 0; q < Cf::E; q++) {
-                u64 y = l3_norm(r[q]);
-                if (!(q == 0 && skip0)) y = mul(y, tw_s[q * Cf::TPT + t]);
-                Sl[q * Cf::ROW_PITCH + t] = y;
-            }
+        for (int q = 0; q < Cf::E; q++) {
+            u64 y = l3_norm(r[q]);
+            if (do_mul && !(q == 0 && skip0)) y = mul(y, tw_s[q * Cf::TPT + t]);
+            x[q] = y;
+        }
+        if (s == 0) {
+#pragma unroll
+            for (int q = 0; q < Cf::E; q++) Sl[q * Cf::ROW_PITCH + t] = x[q];
             __syncwarp();  // a line's TPT <= 32 threads sit in one warp
 #pragma unroll
             for (int j = 0; j < Cf::TPT; j++) x[j] = Sl[t * Cf::ROW_PITCH + j];
-        } else {
-#pragma unroll
-            for (int j = 0; j < Cf::TPT; j++) x[j] = l3_norm(r[j]);
+            do_mul = false;
         }
     }
     if (MODE == RM_BITREV) {

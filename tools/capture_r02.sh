@@ -8,6 +8,7 @@ export GL_REQUIRE_GPU=1
 tail -3 gpurun_out/pytest_$TAG.log
 timeout 400 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 cut -c1-200 gpurun_out/bench_$TAG.json
+timeout 200 python bench.py --no-cpu --no-extra --steps 3 --ntt-group 2147483648 > gpurun_out/bench_twocopy_$TAG.json 2> gpurun_out/bench_twocopy_$TAG.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err
 ncu --set full --clock-control none --import-source on -k regex:"k_ntt" -c 4 \
     -o gpurun_out/prof_ntt_$TAG -f python bench.py --steps 1 --warmup 1 --cols 64 --no-cpu --no-extra --no-ntt > gpurun_out/prof_ntt_$TAG.log 2>&1
