@@ -113,7 +113,7 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------
 # reference arm: the CPU path (oracle port; the Rust reference cannot be built in this image)
 # ------------------------------------------------------------------------------------------------
-CPU_STEP_SECONDS = 8.0  # one CPU step of the bounded sample (both the --impl reference arm and the cpu_baseline leg)
+CPU_STEP_SECONDS = 4.5  # one CPU step of the bounded sample: the SAME sample in the --impl reference arm (K steps) and the cpu_baseline leg
 
 
 def cpu_sample(args, cores, target_seconds=CPU_STEP_SECONDS):
