@@ -320,9 +320,10 @@ def gpu_arm(args, rank, local_rank, world):
                                       [pb.FriBatchInfo(zeta, [pb.FriPolynomialInfo(0, i) for i in range(B)]),
                                        pb.FriBatchInfo(gz, [pb.FriPolynomialInfo(0, 0), pb.FriPolynomialInfo(0, 1)])])
 
-            class _Oracle:  # what fri._begin needs of a PolynomialBatch
+            class _Oracle:  # what fri._begin / _begin_values / eval_commitments need of a PolynomialBatch
                 def __init__(self, h):
                     self.h, self.ctx = h, ctx
+                    self.num_polys, self.shard_index, self.num_shards = B, rank, world
 
             def gather_words(local):  # all-gather of the ranks' cap entries of one FRI round (NCCL)
                 t_loc = torch.from_numpy(local.view(np.int64)).to(dev)
@@ -333,7 +334,17 @@ def gpu_arm(args, rank, local_rank, world):
             def fri_commit_phase(hnd, cap_np):
                 ch = pb.Challenger()
                 ch.observe_cap(pb.MerkleCap(np.ascontiguousarray(cap_np).view(np.uint64).reshape(-1, 4)))
-                st = F._begin(inst, [_Oracle(hnd)], ch.get_extension_challenge(), params)
+                if world > 1 and args.fri_values:
+                    # N > 1: the codeword is composed in the VALUE domain from this rank's own LDE rows (and the openings,
+                    # which a prover holds at this point: proof.rs:313-351), so every FRI round is rank-local
+                    orc = _Oracle(hnd)
+                    ev_z, ev_gz = pb.eval_commitments([(orc, zeta), (orc, gz)])
+                    opened = [ev_z, ev_gz[:2]]
+                    for o in opened:
+                        ch.observe_elements(o.reshape(-1))
+                    st = F._begin_values(inst, [orc], ch.get_extension_challenge(), opened, params)
+                else:
+                    st = F._begin(inst, [_Oracle(hnd)], ch.get_extension_challenge(), params)
                 try:
                     caps, final = F.fri_committed_trees(st, ch, params, shard=(rank, world) if world > 1 else None,
                                                         gather=gather_words)
@@ -677,6 +688,11 @@ def main():
     ap.add_argument("--fri-commit", action="store_true", default=None,
                     help="include the FRI commit phase of the opening proof in every step (default: on for cfg5)")
     ap.add_argument("--no-fri-commit", dest="fri_commit", action="store_false")
+    ap.add_argument("--fri-values", dest="fri_values", action="store_true", default=False,
+                    help="N > 1: compose the FRI codeword in the value domain from each rank's own LDE rows (rank-local "
+                         "rounds) instead of the replicated coefficient-domain begin. Measured SLOWER for cfg5 on 2 GPUs "
+                         "(221 vs 158 ms/step): the openings it needs come from gl_openings, whose one-CTA-per-polynomial "
+                         "evaluation is built for many short polynomials, not 64 of length 2^24")
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--ntt-group", type=int, default=0, help="columns per NTT group (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true")

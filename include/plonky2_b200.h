@@ -265,6 +265,19 @@ typedef struct {
 int gl_fri_begin(gl_ctx* ctx, gl_commit* const* oracles, size_t n_oracles, const gl_fri_batch* batches,
                  size_t n_batches, const uint64_t alpha[2], uint32_t rate_bits, uint32_t cap_height,
                  gl_fri** out);
+/* The same codeword computed in the VALUE domain, straight from the commitments' LDE rows:
+ *   value(x) = sum_b alpha^{k_b} (F_b(x) - F_b(z_b)) / (x - z_b),  F_b(x) = sum_j alpha^j f_{b,j}(x)
+ * -- exactly the field elements gl_fri_begin's LDE holds (the quotients are exact), with no pass over the coefficients
+ * and no LDE. `opened` = the openings f_{b,j}(z_b) in batch order (2 words each; OpeningSet / gl_openings), as the
+ * prover has them at this point (oracle.rs:176-184). If the commitments are row-block shards (gl_commit_create_sharded,
+ * all with the same shard), the state holds THIS shard's rows only: every later round is rank-local
+ * (gl_fri_commit_round returns the shard's 2^cap_height / G cap entries, gl_fri_fold folds the local leaves), the final
+ * polynomial is interpolated by the caller from the gathered gl_fri_values_local. rate_bits comes from the commitments. */
+int gl_fri_begin_values(gl_ctx* ctx, gl_commit* const* oracles, size_t n_oracles, const gl_fri_batch* batches,
+                        size_t n_batches, const uint64_t* opened, const uint64_t alpha[2], uint32_t cap_height,
+                        gl_fri** out);
+/* the local block of the current codeword between rounds: *len_out F_{p^2} values (2 words each), bit-reversed order */
+int gl_fri_values_local(gl_fri* f, uint64_t* out, size_t cap_words, size_t* len_out);
 /* Same, from explicit final-polynomial coefficients (n = 2^log_n F_{p^2} elements, 2n words, host). */
 int gl_fri_begin_from_coeffs(gl_ctx* ctx, const uint64_t* coeffs_ext, uint32_t log_n, uint32_t rate_bits,
                              uint32_t cap_height, gl_fri** out);

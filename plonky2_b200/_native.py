@@ -28,7 +28,7 @@ EXPORTS = [
     "gl_commit_cap", "gl_commit_coeffs", "gl_commit_leaves", "gl_commit_digests", "gl_commit_get_lde_values",
     "gl_commit_open", "gl_commit_eval_ext", "gl_openings", "gl_stark_quotient", "gl_lookup_polys", "gl_commit_dev_lde", "gl_commit_dev_coeffs", "gl_partial_products_and_zs", "gl_poseidon_permute_host",
     "gl_poseidon_permute_many", "gl_poseidon_hash_many", "gl_poseidon_hash_no_pad_many", "gl_poseidon_two_to_one_many", "gl_merkle_build", "gl_merkle_destroy",
-    "gl_merkle_cap", "gl_merkle_digests", "gl_merkle_open", "gl_fri_begin", "gl_fri_begin_from_coeffs",
+    "gl_merkle_cap", "gl_merkle_digests", "gl_merkle_open", "gl_fri_begin", "gl_fri_begin_values", "gl_fri_values_local", "gl_fri_begin_from_coeffs",
     "gl_fri_destroy", "gl_fri_coeffs", "gl_fri_commit_round", "gl_fri_commit_round_sharded", "gl_fri_mix", "gl_fri_fold", "gl_fri_final_poly",
     "gl_fri_open", "gl_fri_num_rounds", "gl_fri_pow",
 ]
@@ -121,6 +121,9 @@ def lib():
     L.gl_merkle_open.argtypes = [vp, vp, C.c_size_t, vp, vp]
     L.gl_fri_begin.argtypes = [vp, C.POINTER(vp), C.c_size_t, C.POINTER(FriBatch), C.c_size_t, vp, C.c_uint32,
                                C.c_uint32, C.POINTER(vp)]
+    L.gl_fri_begin_values.argtypes = [vp, C.POINTER(vp), C.c_size_t, C.POINTER(FriBatch), C.c_size_t, vp, vp, C.c_uint32,
+                                      C.POINTER(vp)]
+    L.gl_fri_values_local.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.gl_fri_begin_from_coeffs.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
     L.gl_fri_destroy.argtypes = [vp]
     L.gl_fri_destroy.restype = None

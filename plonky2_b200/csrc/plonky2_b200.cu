@@ -830,6 +830,7 @@ struct FoldParams {
     u64 beta0, beta1;
     u64 arity_inv;
     u64 root_inv[32];    // w_arity^-j
+    size_t leaf0;        // global index of local leaf 0 (row-block sharded codewords)
 };
 template <int AB>
 __global__ void __launch_bounds__(128) k_fri_fold(FoldParams fp) {
@@ -856,7 +857,7 @@ __global__ void __launch_bounds__(128) k_fri_fold(FoldParams fp) {
         }
     }
     // gamma = beta / x0 ; x0^-1 = shift^-1 * w_N^{-bitrev(l)}
-    const size_t r = fp.log_leaves ? (size_t)(__brevll(l) >> (64 - fp.log_leaves)) : 0;
+    const size_t r = fp.log_leaves ? (size_t)(__brevll(l + fp.leaf0) >> (64 - fp.log_leaves)) : 0;
     const u64 x0inv = mul(fp.shift_inv, mul(fp.winv_hi[r >> 12], fp.winv_lo[r & 4095]));
     const E2 gamma = E2{mul(fp.beta0, x0inv), mul(fp.beta1, x0inv)};
     E2 acc = e[A - 1];
@@ -1236,6 +1237,9 @@ struct gl_fri {
     bool committed = false;     // commit_round done, fold pending
     u64* round_values = nullptr;  // the committed round's whole values buffer (owned by its tree) and leaf count
     size_t round_leaves = 0;
+    // value-domain, row-block sharded state (gl_fri_begin_values): `values` holds only rows
+    // [vshard_index * 2^(log_cur - vshard_log), ...) of the codeword; log_cur stays the GLOBAL length
+    uint32_t vshard_index = 0, vshard_log = 0;
     std::vector<Tree> trees;
 };
 
@@ -2168,6 +2172,156 @@ int gl_fri_begin(gl_ctx* ctx, gl_commit* const* oracles, size_t n_oracles, const
     return GL_OK;
 }
 
+// ---- value-domain composition (the pre-FRI part of prove_openings, oracle.rs:186-220, evaluated point by point) ----
+// final_poly(x) = sum_b alpha^{k_b} (F_b(x) - F_b(z_b)) / (x - z_b) with F_b(x) = sum_j alpha^j f_{b,j}(x): the same field
+// elements as the LDE of the coefficient-domain final polynomial (the quotients are exact), but computed from the
+// commitments' LDE rows in place -- rank-local when the commitments are row-block sharded.
+struct ValRef {
+    const u64* col;  // the polynomial's LDE column (leaf order), local rows
+};
+struct ValBatch {
+    uint32_t first, count;  // slice of the ValRef array
+    E2 z, y, shiftmul;      // point, F_b(z_b) = sum_j alpha^j y_{b,j}, alpha^count
+};
+constexpr int FRI_MAX_BATCHES = 8;
+struct ComposeValuesParams {
+    const ValRef* refs;
+    ValBatch batch[FRI_MAX_BATCHES];
+    uint32_t n_batches;
+    size_t rows, row0;      // local rows, global index of local row 0
+    uint32_t log_N;
+    const u64 *xhi, *xlo;   // w_N^i = xhi[i >> 12] * xlo[i & 4095]
+    u64 shift;
+    E2 alpha;
+    u64* out;               // rows x 2
+    unsigned int* flag;
+};
+__global__ void __launch_bounds__(128) k_fri_compose_values(ComposeValuesParams p) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.rows) return;
+    const size_t i = (size_t)(__brevll((unsigned long long)(j + p.row0)) >> (64 - p.log_N));  // LDE point of leaf j
+    const u64 x = mul(p.shift, mul(p.xhi[i >> 12], p.xlo[i & 4095]));
+    E2 acc = {0, 0};
+    for (uint32_t b = 0; b < p.n_batches; b++) {
+        const ValBatch vb = p.batch[b];
+        E2 s = {0, 0};
+        for (uint32_t k = vb.count; k-- > 0;) {  // Horner in alpha over the batch's polynomials
+            const u64 v = p.refs[vb.first + k].col[j];
+            s = e2_mul(s, p.alpha);
+            s.a = add(s.a, v);
+        }
+        const E2 d = {sub(x, vb.z.a), neg(vb.z.b)};  // x - z_b
+        if (canon(d.a) == 0 && canon(d.b) == 0) atomicOr(p.flag, 1u);
+        const E2 q = e2_mul(e2_sub(s, vb.y), e2_inv(d));
+        acc = e2_add(e2_mul(acc, vb.shiftmul), q);  // alpha.shift_poly(&mut final_poly); final_poly += quotient
+    }
+    p.out[2 * j] = canon(acc.a);
+    p.out[2 * j + 1] = canon(acc.b);
+}
+
+int gl_fri_begin_values(gl_ctx* ctx, gl_commit* const* oracles, size_t n_oracles, const gl_fri_batch* batches,
+                        size_t n_batches, const uint64_t* opened, const uint64_t alpha_in[2], uint32_t cap_height,
+                        gl_fri** out) {
+    if (!ctx || !oracles || !batches || !opened || !alpha_in || !out || n_oracles == 0 || n_batches == 0)
+        return set_err(ctx, GL_ERR_BAD_ARG, "null/empty argument");
+    if (n_batches > (size_t)FRI_MAX_BATCHES) return set_err(ctx, GL_ERR_UNSUPPORTED, "more than %d opening batches", FRI_MAX_BATCHES);
+    *out = nullptr;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const gl_commit* c0 = oracles[0];
+    for (size_t o = 0; o < n_oracles; o++) {
+        const gl_commit* c = oracles[o];
+        if (!c->finished) return set_err(ctx, GL_ERR_BAD_ARG, "gl_commit_finish has not been called");
+        if (c->degree_log != c0->degree_log || c->rate_bits != c0->rate_bits)
+            return set_err(ctx, GL_ERR_BAD_SHAPE, "Polynomial degrees inconsistent");
+        if (c->shard_index != c0->shard_index || c->shard_log != c0->shard_log)
+            return set_err(ctx, GL_ERR_BAD_SHAPE, "commitments are sharded differently");
+    }
+    if (c0->shard_log > cap_height) return set_err(ctx, GL_ERR_BAD_SHAPE, "more shards than cap entries");
+    gl_fri* f = new gl_fri();
+    f->ctx = ctx;
+    f->log_n = c0->degree_log;
+    f->rate_bits = c0->rate_bits;
+    f->cap_height = cap_height;
+    f->vshard_index = c0->shard_index;
+    f->vshard_log = c0->shard_log;
+    f->log_cur = c0->degree_log + c0->rate_bits;
+    f->shift = MULTIPLICATIVE_GROUP_GENERATOR;
+    const size_t rows = c0->tree.N;
+    const E2 alpha = {canon(alpha_in[0]), canon(alpha_in[1])};
+    u64 *drefs = nullptr, *xtab = nullptr, *dflag = nullptr;
+    auto body = [&]() -> int {
+        size_t total = 0;
+        for (size_t b = 0; b < n_batches; b++) total += batches[b].num_polys;
+        std::vector<ValRef> refs(total);
+        ComposeValuesParams p;
+        p.n_batches = (uint32_t)n_batches;
+        for (size_t b = 0, at = 0; b < n_batches; b++) {
+            const gl_fri_batch& batch = batches[b];
+            E2 ap = {1, 0}, y = {0, 0};
+            p.batch[b].first = (uint32_t)at;
+            p.batch[b].count = (uint32_t)batch.num_polys;
+            for (size_t k = 0; k < batch.num_polys; k++, at++) {
+                const uint32_t oi = batch.oracle_index[k], pi = batch.poly_index[k];
+                if (oi >= n_oracles || pi >= oracles[oi]->B) return set_err(ctx, GL_ERR_BAD_ARG, "bad polynomial reference");
+                refs[at].col = oracles[oi]->tree.leaves + (size_t)pi * oracles[oi]->tree.es;
+                const E2 yv = {canon(opened[2 * at]), canon(opened[2 * at + 1])};
+                y = e2_add(y, e2_mul(ap, yv));
+                ap = e2_mul(ap, alpha);
+            }
+            p.batch[b].z = E2{canon(batch.point[0]), canon(batch.point[1])};
+            p.batch[b].y = E2{canon(y.a), canon(y.b)};
+            p.batch[b].shiftmul = E2{canon(ap.a), canon(ap.b)};
+        }
+        const size_t ref_words = total * sizeof(ValRef) / 8;
+        TRY(dmalloc(ctx, &drefs, ref_words ? ref_words : 1));
+        if (ref_words) TRY(h2d(ctx, drefs, (const u64*)refs.data(), ref_words));
+        const uint32_t log_N = f->log_cur;
+        const size_t N = (size_t)1 << log_N;
+        const u64 wN = root_of_unity(log_N);
+        const size_t tcnt = 4096 > (N >> 12) + 1 ? 4096 : (N >> 12) + 1;
+        TRY(build_pow_tables(ctx, std::vector<u64>{gl::pow(wN, 4096), wN}, tcnt, &xtab));
+        TRY(dmalloc(ctx, &dflag, 1));
+        CK(ctx, cudaMemsetAsync(dflag, 0, 8, ctx->stream));
+        TRY(dmalloc(ctx, &f->values, 2 * rows));
+        p.refs = (const ValRef*)drefs;
+        p.rows = rows;
+        p.row0 = (size_t)c0->shard_index * rows;
+        p.log_N = log_N;
+        p.xhi = xtab;
+        p.xlo = xtab + tcnt;
+        p.shift = MULTIPLICATIVE_GROUP_GENERATOR;
+        p.alpha = alpha;
+        p.out = f->values;
+        p.flag = (unsigned int*)dflag;
+        k_fri_compose_values<<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(p);
+        CKL(ctx);
+        u64 flag = 0;
+        TRY(d2h(ctx, &flag, dflag, 1));
+        if (flag & 1u) return set_err(ctx, GL_ERR_DIV_ZERO, "Opening point is in the LDE domain");
+        return GL_OK;
+    };
+    int rc = body();
+    dfree(ctx, drefs);
+    dfree(ctx, xtab);
+    dfree(ctx, dflag);
+    if (rc != GL_OK) {
+        gl_fri_destroy(f);
+        return rc;
+    }
+    *out = f;
+    return GL_OK;
+}
+// the local block of the current codeword (between rounds): 2^(log_cur - shard_log) F_{p^2} values, bit-reversed order
+int gl_fri_values_local(gl_fri* f, uint64_t* out, size_t cap_words, size_t* len_out) {
+    gl_ctx* ctx = f->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (f->committed || !f->values) return set_err(ctx, GL_ERR_BAD_ARG, "fold the last round first");
+    const size_t len = (size_t)1 << (f->log_cur - f->vshard_log);
+    if (cap_words < 2 * len) return set_err(ctx, GL_ERR_BAD_ARG, "output buffer too small");
+    if (len_out) *len_out = len;
+    return d2h(ctx, out, f->values, 2 * len);
+}
+
 __global__ void k_split_ext(const u64* inter, size_t n, u64* cols) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -2215,6 +2369,7 @@ void gl_fri_destroy(gl_fri* f) {
 }
 int gl_fri_coeffs(gl_fri* f, uint64_t* out) {
     gl_ctx* ctx = f->ctx;
+    if (!f->coeff_cols) return set_err(ctx, GL_ERR_BAD_ARG, "this FRI state was built in the value domain: no coefficients");
     const size_t n = (size_t)1 << f->log_n;
     u64* tmp;
     TRY(dmalloc(ctx, &tmp, 2 * n));
@@ -2243,6 +2398,14 @@ static int fri_commit_round(gl_fri* f, uint32_t arity_bits, uint32_t shard_index
                        f->log_cur - arity_bits);
     if (sl > f->cap_height)
         return set_err(ctx, GL_ERR_BAD_SHAPE, "num_shards=%u exceeds the cap size 2^%u", num_shards, f->cap_height);
+    if (f->vshard_log) {  // the codeword itself is sharded: the local buffer is this shard's block of leaves
+        if (num_shards != 1 && (sl != f->vshard_log || shard_index != f->vshard_index))
+            return set_err(ctx, GL_ERR_BAD_ARG, "this FRI state is row-block sharded %u of %u", f->vshard_index, 1u << f->vshard_log);
+        sl = f->vshard_log;
+        shard_index = 0;  // no offset inside the local buffer
+        if (f->log_cur < arity_bits + sl || sl > f->cap_height)
+            return set_err(ctx, GL_ERR_BAD_SHAPE, "round too small for %u shards", 1u << sl);
+    }
     const size_t L = (size_t)1 << (f->log_cur - arity_bits);
     Tree t;
     t.N = L >> sl;
@@ -2258,7 +2421,7 @@ static int fri_commit_round(gl_fri* f, uint32_t arity_bits, uint32_t shard_index
     }
     t.own_leaves = true;  // ownership of the values buffer moves to the tree
     f->round_values = f->values;
-    f->round_leaves = L;
+    f->round_leaves = f->vshard_log ? t.N : L;
     f->values = nullptr;
     f->trees.push_back(t);
     f->pending_arity_bits = arity_bits;
@@ -2282,6 +2445,7 @@ int gl_fri_fold(gl_fri* f, const uint64_t beta[2]) {
     fp.values = f->round_values;
     fp.out = out;
     fp.n_leaves = leaves;
+    fp.leaf0 = (size_t)f->vshard_index * leaves;
     fp.log_leaves = f->log_cur - ab;
     const u64 wN = root_of_unity(f->log_cur);
     const u64 winv = gl::inv(wN);
@@ -2350,6 +2514,7 @@ int gl_fri_final_poly(gl_fri* f, uint64_t* out, size_t cap_words, size_t* len_ou
     gl_ctx* ctx = f->ctx;
     CK(ctx, cudaSetDevice(ctx->device));
     if (f->committed) return set_err(ctx, GL_ERR_BAD_ARG, "fold the last round first");
+    if (f->vshard_log) return set_err(ctx, GL_ERR_BAD_ARG, "sharded codeword: gather gl_fri_values_local and interpolate");
     const size_t Nf = (size_t)1 << f->log_cur;
     if (f->log_cur < f->rate_bits) return set_err(ctx, GL_ERR_BAD_SHAPE, "codeword shorter than the blowup");
     const size_t len = Nf >> f->rate_bits;

@@ -330,6 +330,48 @@ def _begin(instance, oracles, alpha, fri_params):
     return _FriState(h, ctx)
 
 
+def _begin_values(instance, oracles, alpha, opened, fri_params):
+    """The pre-FRI part of prove_openings (oracle.rs:186-220) in the value domain (gl_fri_begin_values): `opened` =
+    [(num_polys_b, 2) array per batch], the openings f_{b,j}(z_b) the prover already holds (OpeningSet). With row-block
+    sharded oracles the state holds this rank's rows only."""
+    ctx = oracles[0].ctx
+    handles = (N.vp * len(oracles))(*[o.h for o in oracles])
+    barr = (N.FriBatch * len(instance.batches))()
+    keep = []
+    for i, b in enumerate(instance.batches):
+        oi = np.array([p.oracle_index for p in b.polynomials], dtype=np.uint32)
+        pi = np.array([p.polynomial_index for p in b.polynomials], dtype=np.uint32)
+        keep += [oi, pi]
+        barr[i].point[0], barr[i].point[1] = int(b.point[0]) % ORDER, int(b.point[1]) % ORDER
+        barr[i].num_polys = len(b.polynomials)
+        barr[i].oracle_index = oi.ctypes.data_as(N.u32p)
+        barr[i].poly_index = pi.ctypes.data_as(N.u32p)
+    op = np.ascontiguousarray(np.concatenate([np.asarray(o, dtype=np.uint64).reshape(-1, 2) for o in opened]), dtype=np.uint64)
+    assert len(op) == sum(len(b.polynomials) for b in instance.batches)
+    al = np.array([alpha[0], alpha[1]], dtype=np.uint64)
+    h = N.vp()
+    N.check(N.lib().gl_fri_begin_values(ctx.h, handles, len(oracles), barr, len(instance.batches), N.np_ptr(op.reshape(-1)),
+                                        N.np_ptr(al), fri_params.config.cap_height, C.byref(h)), ctx.h)
+    st = _FriState(h, ctx)
+    st.value_sharded = (oracles[0].shard_index, oracles[0].num_shards)
+    return st
+
+
+def _final_poly_from_values(values, log_len, shift, rate_bits, ctx):
+    """Coefficients of the last codeword (prover.rs:134-139) from its values in bit-reversed order: un-reverse,
+    coset_ifft on the final coset (both F_{p^2} components), drop the top 1 - 2^-rate_bits (zero) coefficients."""
+    from .fft import coset_ifft
+    from .field import reverse_bits
+
+    n = 1 << log_len
+    nat = np.empty((n, 2), dtype=np.uint64)
+    for j in range(n):
+        nat[reverse_bits(j, log_len)] = values[j]
+    cols = np.ascontiguousarray(nat.T)
+    co = coset_ifft(cols, shift, ctx=ctx) if log_len else cols
+    return np.ascontiguousarray(co.T[:n >> rate_bits])
+
+
 def fri_committed_trees(state, challenger, fri_params, final_poly_coeff_len=None, max_num_query_steps=None,
                         shard=None, gather=None):
     """fri_committed_trees (prover.rs:84-150): returns (caps, final_poly coefficients (len, 2)).
@@ -339,9 +381,15 @@ def fri_committed_trees(state, challenger, fri_params, final_poly_coeff_len=None
     L, ctx = N.lib(), state.ctx
     cap_words = NUM_HASH_OUT_ELTS << fri_params.config.cap_height
     caps = []
+    vs = getattr(state, "value_sharded", None)
     for arity_bits in fri_params.reduction_arity_bits:
         cap = np.empty(cap_words, dtype=np.uint64)
-        if shard is not None and shard[1] > 1 and (shard[1] - 1).bit_length() <= fri_params.config.cap_height:
+        if vs is not None and vs[1] > 1:  # the codeword itself is row-block sharded: everything is rank-local
+            local = np.empty(cap_words // vs[1], dtype=np.uint64)
+            N.check(L.gl_fri_commit_round(state.h, arity_bits, N.np_ptr(local)), ctx.h)
+            cap = np.ascontiguousarray(gather(local), dtype=np.uint64).reshape(-1)
+            assert cap.size == cap_words
+        elif shard is not None and shard[1] > 1 and (shard[1] - 1).bit_length() <= fri_params.config.cap_height:
             local = np.empty(cap_words // shard[1], dtype=np.uint64)
             N.check(L.gl_fri_commit_round_sharded(state.h, arity_bits, shard[0], shard[1], N.np_ptr(local)), ctx.h)
             cap = np.ascontiguousarray(gather(local), dtype=np.uint64).reshape(-1)
@@ -360,10 +408,20 @@ def fri_committed_trees(state, challenger, fri_params, final_poly_coeff_len=None
             challenger.observe_elements(zero_cap)
             challenger.get_extension_challenge()
     n_final = fri_params.final_poly_len()
-    buf = np.empty(2 * max(n_final, 1), dtype=np.uint64)
-    ln = C.c_size_t()
-    N.check(L.gl_fri_final_poly(state.h, N.np_ptr(buf), buf.size, C.byref(ln)), ctx.h)
-    coeffs = buf[:2 * ln.value].reshape(-1, 2).copy()
+    if vs is not None and vs[1] > 1:
+        log_last = fri_params.lde_bits() - fri_params.total_arities()
+        loc = np.empty(2 * ((1 << log_last) // vs[1]), dtype=np.uint64)
+        ln = C.c_size_t()
+        N.check(L.gl_fri_values_local(state.h, N.np_ptr(loc), loc.size, C.byref(ln)), ctx.h)
+        vals = np.ascontiguousarray(gather(loc), dtype=np.uint64).reshape(-1, 2)
+        from .field import coset_shift
+        shift = pow(coset_shift(), 1 << fri_params.total_arities(), ORDER)
+        coeffs = _final_poly_from_values(vals, log_last, shift, fri_params.config.rate_bits, ctx)
+    else:
+        buf = np.empty(2 * max(n_final, 1), dtype=np.uint64)
+        ln = C.c_size_t()
+        N.check(L.gl_fri_final_poly(state.h, N.np_ptr(buf), buf.size, C.byref(ln)), ctx.h)
+        coeffs = buf[:2 * ln.value].reshape(-1, 2).copy()
     challenger.observe_extension_elements([(int(c[0]), int(c[1])) for c in coeffs])
     if final_poly_coeff_len is not None:
         for _ in range(len(coeffs), final_poly_coeff_len):

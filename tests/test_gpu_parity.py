@@ -1007,3 +1007,109 @@ def test_fri_round_trees_row_block_sharded(pb, shards):
     finally:
         for f in [ref] + states:
             L.gl_fri_destroy(f)
+
+
+def _fri_setup(pb, log_n=9, r=2, h=3, Bs=(5, 3)):
+    n = 1 << log_n
+    data = [synth(0x1A0 + i, (B, n)) for i, B in enumerate(Bs)]
+    zeta = (int(synth(0x1A8, (1,))[0]), int(synth(0x1A9, (1,))[0]))
+    gz = pb.field.ext_mul(zeta, (pb.field.primitive_root_of_unity(log_n), 0))
+    inst = pb.FriInstanceInfo([pb.FriOracleInfo(B, False) for B in Bs],
+                              [pb.FriBatchInfo(zeta, [pb.FriPolynomialInfo(o, i) for o, B in enumerate(Bs) for i in range(B)]),
+                               pb.FriBatchInfo(gz, [pb.FriPolynomialInfo(0, 1), pb.FriPolynomialInfo(1, 0)])])
+    cfg = pb.FriConfig(r, h, 4, ("Fixed", [3, 2]), 9)
+    params = pb.FriParams(cfg, False, log_n, [3, 2])
+    return data, inst, params, zeta, gz
+
+
+def _openings_for(pb, inst, batches):
+    req = []
+    for b in inst.batches:
+        for p in b.polynomials:
+            req.append((batches[p.oracle_index], b.point))
+    ev = pb.eval_commitments(req)
+    out, k = [], 0
+    for b in inst.batches:
+        vals = []
+        for p in b.polynomials:
+            vals.append(ev[k][p.polynomial_index])
+            k += 1
+        out.append(np.array(vals, dtype=np.uint64))
+    return out
+
+
+def test_fri_value_domain_begin_gives_the_same_proof(pb):
+    """gl_fri_begin_values (composition from the LDE rows + the openings) yields the codeword of gl_fri_begin: the
+    whole FRI proof is byte-identical."""
+    from plonky2_b200 import fri as F
+
+    data, inst, params, zeta, gz = _fri_setup(pb)
+    batches = [pb.PolynomialBatch.from_values(d, params.config.rate_bits, False, params.config.cap_height) for d in data]
+    opened = _openings_for(pb, inst, batches)
+    ch1, ch2 = pb.Challenger(), pb.Challenger()
+    for ch in (ch1, ch2):
+        for b in batches:
+            ch.observe_cap(b.merkle_tree.cap)
+    want = pb.prove_openings(inst, batches, ch1, params).to_bytes()
+    st = F._begin_values(inst, batches, ch2.get_extension_challenge(), opened, params)
+    try:
+        caps, final = F.fri_committed_trees(st, ch2, params)
+        poww = F.fri_proof_of_work(ch2, params.config, st.ctx)
+        rounds, _ = F.fri_prover_query_rounds(batches, st, ch2, params.lde_size(), params)
+        assert F.FriProof(caps, rounds, final, poww).to_bytes() == want
+    finally:
+        st.close()
+    for b in batches:
+        b.close()
+
+
+@pytest.mark.parametrize("shards", [2, 8])
+def test_fri_value_domain_row_block_sharded_rounds(pb, shards):
+    """With row-block sharded commitments the value-domain state is rank-local: per round the shards' cap entries in
+    shard order equal the unsharded cap, the gathered last codeword interpolates to the same final polynomial."""
+    import ctypes as C
+
+    from plonky2_b200 import _native as N
+    from plonky2_b200 import fri as F
+
+    data, inst, params, zeta, gz = _fri_setup(pb)
+    r, h = params.config.rate_bits, params.config.cap_height
+    whole = [pb.PolynomialBatch.from_values(d, r, False, h) for d in data]
+    opened = _openings_for(pb, inst, whole)
+    alpha = (int(synth(0x1AA, (1,))[0]), int(synth(0x1AB, (1,))[0]))
+    ref = F._begin_values(inst, whole, alpha, opened, params)
+    parts = [[pb.PolynomialBatch.from_values(d, r, False, h, shard=(g, shards)) for d in data] for g in range(shards)]
+    states = [F._begin_values(inst, parts[g], alpha, opened, params) for g in range(shards)]
+    L, ctx = N.lib(), ref.ctx
+    betas = synth(0x1AC, (2, 2))
+    try:
+        for rnd, ab in enumerate(params.reduction_arity_bits):
+            want = np.empty(4 << h, dtype=np.uint64)
+            N.check(L.gl_fri_commit_round(ref.h, ab, N.np_ptr(want)), ctx.h)
+            got = []
+            for st in states:
+                loc = np.empty((4 << h) // shards, dtype=np.uint64)
+                N.check(L.gl_fri_commit_round(st.h, ab, N.np_ptr(loc)), ctx.h)
+                got.append(loc)
+            assert np.array_equal(np.concatenate(got), want), rnd
+            for st in [ref] + states:
+                N.check(L.gl_fri_fold(st.h, N.np_ptr(np.ascontiguousarray(betas[rnd]))), ctx.h)
+        log_last = params.lde_bits() - params.total_arities()
+        vals = []
+        for st in states:
+            loc = np.empty(2 * ((1 << log_last) // shards), dtype=np.uint64)
+            ln = C.c_size_t()
+            N.check(L.gl_fri_values_local(st.h, N.np_ptr(loc), loc.size, C.byref(ln)), ctx.h)
+            assert ln.value == (1 << log_last) // shards
+            vals.append(loc)
+        shift = pow(pb.field.coset_shift(), 1 << params.total_arities(), int(P))
+        coeffs = F._final_poly_from_values(np.concatenate(vals).reshape(-1, 2), log_last, shift, r, ctx)
+        buf = np.empty(2 * (1 << log_last), dtype=np.uint64)
+        ln = C.c_size_t()
+        N.check(L.gl_fri_final_poly(ref.h, N.np_ptr(buf), buf.size, C.byref(ln)), ctx.h)
+        assert np.array_equal(coeffs.reshape(-1), buf[:2 * ln.value])
+    finally:
+        for st in [ref] + states:
+            st.close()
+        for b in whole + [x for p in parts for x in p]:
+            b.close()
