@@ -360,6 +360,54 @@ class PolynomialBatch {
         return out;
     }
 
+    // OpeningSet::new / StarkOpeningSet::new (plonk/proof.rs:313-351, starky/src/proof.rs:221-260): every polynomial of
+    // requests[i].first at requests[i].second, all in ONE native call (gl_openings); one vector of values per request.
+    static std::vector<std::vector<Ext>> eval_commitments(const std::vector<std::pair<const PolynomialBatch*, Ext>>& requests) {
+        std::vector<std::vector<Ext>> out(requests.size());
+        if (requests.empty()) return out;
+        Context& ctx = requests[0].first->context();
+        std::vector<gl_commit*> handles;
+        std::vector<uint32_t> pidx;
+        std::vector<F> points;
+        size_t total = 0;
+        for (auto& rq : requests) {
+            handles.push_back(rq.first->handle());
+            size_t k = 0;
+            for (; k < points.size() / 2; k++)
+                if (points[2 * k] == rq.second.c0 && points[2 * k + 1] == rq.second.c1) break;
+            if (k == points.size() / 2) {
+                points.push_back(rq.second.c0);
+                points.push_back(rq.second.c1);
+            }
+            pidx.push_back(uint32_t(k));
+            total += rq.first->num_polys();
+        }
+        std::vector<Ext> flat(total);
+        check(gl_openings(ctx.get(), handles.data(), pidx.data(), requests.size(), points.data(), points.size() / 2,
+                          &flat[0].c0, GL_MEM_HOST), ctx.get());
+        size_t off = 0;
+        for (size_t i = 0; i < requests.size(); i++) {
+            const size_t b = requests[i].first->num_polys();
+            out[i].assign(flat.begin() + off, flat.begin() + off + b);
+            off += b;
+        }
+        return out;
+    }
+    // The same commitment assembled from column groups that arrive over time (gl_commit_begin / add_columns / finish):
+    // `kind` = GL_COLS_VALUES / GL_COLS_COEFFS / GL_COLS_COEFFS_CANONICAL, `mem` = GL_MEM_HOST / GL_MEM_DEVICE.
+    static PolynomialBatch begin(Context& ctx, uint32_t num_polys, uint32_t degree_log, uint32_t rate_bits, uint32_t cap_height,
+                                 uint32_t shard_index = 0, uint32_t num_shards = 1, F* coeff_storage = nullptr) {
+        PolynomialBatch pb;
+        pb.ctx_ = &ctx;
+        check(gl_commit_begin(ctx.get(), num_polys, degree_log, rate_bits, cap_height, 0, shard_index, num_shards,
+                              coeff_storage, &pb.h_), ctx.get());
+        return pb;
+    }
+    void add_columns(uint32_t first_col, uint32_t count, const F* cols, size_t col_stride, int kind, int mem) {
+        check(gl_commit_add_columns(h_, first_col, count, cols, col_stride, kind, mem), ctx_->get());
+    }
+    void finish() { check(gl_commit_finish(h_, nullptr, GL_MEM_HOST), ctx_->get()); }
+
     // prove_openings (oracle.rs:176-237) -> fri_proof (prover.rs:24-70): host transcript in the loop.
     static FriProof prove_openings(const FriInstanceInfo& instance, const std::vector<const PolynomialBatch*>& oracles,
                                    Challenger& challenger, const FriParams& fri_params) {
