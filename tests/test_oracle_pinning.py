@@ -287,3 +287,43 @@ def test_batch_fri_with_one_degree_equals_plain_fri(oracle):
     a = oracle.batch_prove_openings([bc], [log_n], [batches], ch1, params)
     b = oracle.prove_openings([pc], batches, ch2, params)
     assert a == b
+
+
+def test_lookup_polys_restatement_satisfies_the_lookup_argument(oracle):
+    """Pin of the compute_lookup_polys restatement (plonk/prover.rs:458-577) by the argument's own invariant: with
+    multiplicities that count the looked-up pairs, the running Sum - LDC ends at 0 in the last partial polynomial at the
+    last lookup row ("If the lookup argument is valid, then it must be equal to 0", prover.rs:456-457), and does not when
+    one looking pair is not in the table. RE is checked against its definition (Horner in delta over the table rows)."""
+    P_ = int(P)
+    routed, qdf, log_n = 6, 3, 5          # 3 looking slots, 2 table slots per row; P = 2 partial polynomials
+    n = 1 << log_n
+    last_lu, last_lut, first_lut = 4, 8, 10   # LU rows 4..7, LUT rows 8..10
+    wires = np.zeros((routed, n), dtype=np.uint64)
+    table = [(int(a), int(b)) for a, b in synth(0xD9, (6, 2))]
+    rng = [int(x) for x in synth(0xDA, (12,), canonical=False)]
+    counts = [0] * 6
+    k = 0
+    for row in range(last_lu, last_lut):
+        for s in range(3):
+            e = rng[k] % 6
+            k += 1
+            counts[e] += 1
+            wires[2 * s, row], wires[2 * s + 1, row] = table[e]
+    for i, (a, b) in enumerate(table):
+        row, s = last_lut + i // 2, i % 2
+        wires[3 * s, row], wires[3 * s + 1, row], wires[3 * s + 2, row] = a, b, counts[i]
+    deltas = [int(x) for x in synth(0xDB, (4,))]
+    out = oracle.lookup_polys(wires, routed, qdf, deltas, [(last_lu, last_lut, first_lut)])
+    assert out.shape == (3, n)
+    assert int(out[2, last_lu]) == 0                      # Sum(end) - LDC(end)
+    assert not out[:, :last_lu].any() and not out[:, first_lut + 1:].any()
+    # RE by its definition
+    re = 0
+    for row in range(first_lut, last_lut - 1, -1):
+        for s in range(2):
+            re = (re * deltas[3] + int(wires[3 * s, row]) + deltas[1] * int(wires[3 * s + 1, row])) % P_
+        assert int(out[0, row]) == re
+    bad = wires.copy()
+    bad[0, last_lu] = (int(bad[0, last_lu]) + 1) % P_     # a looking pair that is not in the table
+    out2 = oracle.lookup_polys(bad, routed, qdf, deltas, [(last_lu, last_lut, first_lut)])
+    assert int(out2[2, last_lu]) != 0
