@@ -327,3 +327,45 @@ def test_lookup_polys_restatement_satisfies_the_lookup_argument(oracle):
     bad[0, last_lu] = (int(bad[0, last_lu]) + 1) % P_     # a looking pair that is not in the table
     out2 = oracle.lookup_polys(bad, routed, qdf, deltas, [(last_lu, last_lut, first_lut)])
     assert int(out2[2, last_lu]) != 0
+
+
+def test_partial_products_restatement_satisfies_the_permutation_argument(oracle):
+    """Pin of the wires_permutation_partial_products_and_zs restatement (plonk/prover.rs:387-449) by the permutation
+    argument itself: for wire values that respect the copy constraints encoded in sigma, the grand product telescopes,
+    Z(g^n) = Z(1) = 1 -- and every partial product obeys pp_m(x) = pp_{m-1}(x) * q_m(x) (util/partial_products.rs:13-37)."""
+    P_ = int(P)
+    import plonky2_b200.field as F
+
+    R, log_n, deg = 4, 3, 2
+    n = 1 << log_n
+    w = F.primitive_root_of_unity(log_n)
+    k_is = [1, 7, 49, 343]
+    wires = synth(0xDC, (R, n)).copy()
+    ids = np.array([[k_is[j] * pow(w, i, P_) % P_ for i in range(n)] for j in range(R)], dtype=np.uint64)
+    sigmas = ids.copy()
+    # copy constraints: (row 1, wire 0) == (row 5, wire 2) and (row 2, wire 1) == (row 2, wire 3): swap their ids in sigma
+    sigmas[0, 1], sigmas[2, 5] = ids[2, 5], ids[0, 1]
+    sigmas[1, 2], sigmas[3, 2] = ids[3, 2], ids[1, 2]
+    wires[2, 5] = wires[0, 1]
+    wires[3, 2] = wires[1, 2]
+    beta, gamma = [int(x) for x in synth(0xDD, (2,))]
+    out = oracle.partial_products_and_zs(wires, sigmas, np.array(k_is, dtype=np.uint64), beta, gamma, deg)
+    assert out.shape == (2, n)          # one partial product column, then Z
+    pp, Z = out[0], out[1]
+
+    def q(i, m):
+        num = den = 1
+        for j in range(m * deg, min((m + 1) * deg, R)):
+            num = num * (int(wires[j, i]) + beta * int(ids[j, i]) + gamma) % P_
+            den = den * (int(wires[j, i]) + beta * int(sigmas[j, i]) + gamma) % P_
+        return num * pow(den, P_ - 2, P_) % P_
+
+    assert int(Z[0]) == 1
+    for i in range(n):
+        assert int(pp[i]) == int(Z[i]) * q(i, 0) % P_
+        nxt = int(pp[i]) * q(i, 1) % P_
+        assert nxt == (int(Z[i + 1]) if i + 1 < n else 1)     # the product wraps around to Z(1) = 1
+    wires[2, 5] = (int(wires[2, 5]) + 1) % P_                   # break one copy constraint: the product no longer closes
+    out2 = oracle.partial_products_and_zs(wires, sigmas, np.array(k_is, dtype=np.uint64), beta, gamma, deg)
+    last = int(out2[0][n - 1]) * (lambda i: q(i, 1))(n - 1) % P_
+    assert last != 1
