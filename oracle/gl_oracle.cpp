@@ -1639,6 +1639,240 @@ int glo_batch_prove_openings(const glo_batch_commit* const* oracles, size_t n_or
     return 0;
 }
 
+// verify_batch_fri_proof, batch_fri/verifier.rs:22-251 (+ verify_batch_merkle_proof_to_cap, hash/merkle_proofs.rs:72-107;
+// challenges as in fri_challenges, fri/challenges.rs:28-75). group_num_polys[o * n_instances + i] = polynomials of oracle o
+// in degree group i (FriInstanceInfo.oracles[o].num_polys of instance i). opened_values: per instance, per batch, per
+// polynomial (2 words). Returns 0 if the proof verifies.
+int glo_verify_batch_fri_proof(const uint64_t* const* initial_caps, const size_t* group_num_polys, size_t n_oracles,
+                               const uint32_t* degree_bits, const glo_fri_instance* instances, size_t n_instances,
+                               const uint64_t* opened_values, glo_challenger* ch, const glo_fri_params* params,
+                               const uint8_t* proof, size_t proof_len) {
+    size_t pos = 0;
+    bool overrun = false;
+    auto get_u64 = [&]() -> u64 {
+        if (pos + 8 > proof_len) {
+            overrun = true;
+            return 0;
+        }
+        u64 v = 0;
+        for (int i = 0; i < 8; i++) v |= (u64)proof[pos + i] << (8 * i);
+        pos += 8;
+        return v;
+    };
+    auto get_hash = [&]() {
+        Hash h;
+        for (int i = 0; i < 4; i++) h.e[i] = get_u64();
+        return h;
+    };
+    const uint32_t rate_bits = params->rate_bits;
+    std::vector<uint32_t> heights(n_instances);  // degree_bits + rate_bits
+    for (size_t i = 0; i < n_instances; i++) heights[i] = degree_bits[i] + rate_bits;
+    const uint32_t log_N = heights[0];
+    const size_t N = (size_t)1 << log_N;
+    const size_t C = (size_t)1 << params->cap_height;
+    const uint32_t R = params->num_reductions;
+    std::vector<std::vector<Hash>> caps(R, std::vector<Hash>(C));
+    for (uint32_t r = 0; r < R; r++)
+        for (size_t c = 0; c < C; c++) caps[r][c] = get_hash();
+    struct Query {
+        std::vector<std::vector<u64>> init_leaf;
+        std::vector<std::vector<Hash>> init_sib;
+        std::vector<std::vector<E2>> evals;
+        std::vector<std::vector<Hash>> step_sib;
+    };
+    std::vector<Query> queries(params->num_query_rounds);
+    for (auto& q : queries) {
+        for (size_t o = 0; o < n_oracles; o++) {
+            size_t width = 0;
+            for (size_t i = 0; i < n_instances; i++) width += group_num_polys[o * n_instances + i];
+            std::vector<u64> leaf(width);
+            for (auto& x : leaf) x = get_u64();
+            if (pos >= proof_len) return 10;
+            size_t len = proof[pos++];
+            std::vector<Hash> sib(len);
+            for (auto& h : sib) h = get_hash();
+            q.init_leaf.push_back(leaf);
+            q.init_sib.push_back(sib);
+        }
+        for (uint32_t r = 0; r < R; r++) {
+            size_t arity = (size_t)1 << params->reduction_arity_bits[r];
+            std::vector<E2> ev(arity);
+            for (auto& e : ev) {
+                e.a = get_u64();
+                e.b = get_u64();
+            }
+            if (pos >= proof_len) return 10;
+            size_t len = proof[pos++];
+            std::vector<Hash> sib(len);
+            for (auto& h : sib) h = get_hash();
+            q.evals.push_back(ev);
+            q.step_sib.push_back(sib);
+        }
+    }
+    uint32_t final_bits = degree_bits[0];
+    for (uint32_t r = 0; r < R; r++) final_bits -= params->reduction_arity_bits[r];
+    std::vector<E2> final_poly((size_t)1 << final_bits);
+    for (auto& c : final_poly) {
+        c.a = get_u64();
+        c.b = get_u64();
+    }
+    const u64 pow_witness = get_u64();
+    if (overrun || pos != proof_len) return 10;
+    // fri_challenges
+    const E2 fri_alpha = get_extension_challenge(ch);
+    std::vector<E2> betas;
+    for (uint32_t r = 0; r < R; r++) {
+        observe_cap(ch, caps[r]);
+        betas.push_back(get_extension_challenge(ch));
+    }
+    for (auto& c : final_poly) observe_ext(ch, c);
+    observe_element(ch, pow_witness);
+    const u64 pow_response = get_challenge(ch);
+    std::vector<size_t> indices;
+    for (uint32_t q = 0; q < params->num_query_rounds; q++) indices.push_back((size_t)(get_challenge(ch) % N));
+    {
+        const uint32_t lz = pow_response == 0 ? 64 : (uint32_t)__builtin_clzll(pow_response);
+        if (lz < params->proof_of_work_bits) return 11;
+    }
+    // PrecomputedReducedOpenings per instance
+    std::vector<std::vector<E2>> reduced(n_instances);
+    {
+        size_t off = 0;
+        for (size_t i = 0; i < n_instances; i++)
+            for (size_t b = 0; b < instances[i].n_batches; b++) {
+                const glo_fri_batch& batch = instances[i].batches[b];
+                E2 acc = e2(0);
+                for (size_t j = batch.num_polys; j-- > 0;)
+                    acc = eadd(emul(acc, fri_alpha), E2{opened_values[2 * (off + j)], opened_values[2 * (off + j) + 1]});
+                off += batch.num_polys;
+                reduced[i].push_back(acc);
+            }
+    }
+    // batch_fri_combine_initial (verifier.rs:105-144)
+    auto combine_initial = [&](const Query& q, size_t inst, u64 subgroup_x) {
+        E2 sum = e2(0);
+        u64 count = 0;
+        for (size_t b = 0; b < instances[inst].n_batches; b++) {
+            const glo_fri_batch& batch = instances[inst].batches[b];
+            const E2 point{batch.point[0], batch.point[1]};
+            E2 red = e2(0);
+            for (size_t j = batch.num_polys; j-- > 0;) {
+                const u64 ev = q.init_leaf[batch.oracle_index[j]][batch.poly_index[j]];  // unsalted_eval
+                red = eadd(emul(red, fri_alpha), e2(ev));
+                count++;
+            }
+            const E2 numerator = esub(red, reduced[inst][b]);
+            const E2 denominator = esub(e2(subgroup_x), point);
+            sum = emul(eexp(fri_alpha, count), sum);
+            count = 0;
+            sum = eadd(sum, emul(numerator, einv(denominator)));
+        }
+        return sum;
+    };
+    for (size_t qi = 0; qi < queries.size(); qi++) {
+        const Query& q = queries[qi];
+        size_t x_index = indices[qi];
+        // batch_fri_verify_initial_proof (verifier.rs:75-103) + verify_batch_merkle_proof_to_cap
+        for (size_t o = 0; o < n_oracles; o++) {
+            size_t leaf_off = 0, leaf_index = x_index;
+            Hash cur = hash_or_noop(q.init_leaf[o].data(), group_num_polys[o * n_instances + 0]);
+            leaf_off += group_num_polys[o * n_instances + 0];
+            uint32_t current_height = heights[0];
+            size_t leaf_data_index = 1;
+            for (const Hash& sib : q.init_sib[o]) {
+                const size_t bit = leaf_index & 1;
+                leaf_index >>= 1;
+                cur = bit ? two_to_one(sib, cur) : two_to_one(cur, sib);
+                current_height -= 1;
+                if (leaf_data_index < n_instances && current_height == heights[leaf_data_index]) {
+                    const size_t w = group_num_polys[o * n_instances + leaf_data_index];
+                    std::vector<u64> nl(cur.e, cur.e + 4);
+                    nl.insert(nl.end(), q.init_leaf[o].begin() + leaf_off, q.init_leaf[o].begin() + leaf_off + w);
+                    cur = hash_or_noop(nl.data(), nl.size());
+                    leaf_off += w;
+                    leaf_data_index++;
+                }
+            }
+            if (leaf_data_index != n_instances) return 12;
+            if (!heq(cur, ((const Hash*)initial_caps[o])[leaf_index])) return 13;
+        }
+        uint32_t n = heights[0];
+        u64 subgroup_x = fmul(MULTIPLICATIVE_GROUP_GENERATOR, fexp(primitive_root_of_unity(n), reverse_bits(x_index, n)));
+        size_t batch_index = 0;
+        E2 old_eval = combine_initial(q, batch_index, subgroup_x);
+        batch_index++;
+        for (uint32_t r = 0; r < R; r++) {
+            const uint32_t arity_bits = params->reduction_arity_bits[r];
+            const size_t arity = (size_t)1 << arity_bits;
+            const std::vector<E2>& evals = q.evals[r];
+            const size_t coset_index = x_index >> arity_bits, within = x_index & (arity - 1);
+            if (!eeq(evals[within], old_eval)) return 14;
+            {  // compute_evaluation, fri/verifier.rs:22-47
+                const u64 g = primitive_root_of_unity(arity_bits);
+                std::vector<E2> ev = evals;
+                std::vector<u64> flat(2 * arity);
+                for (size_t i = 0; i < arity; i++) {
+                    flat[2 * i] = ev[i].a;
+                    flat[2 * i + 1] = ev[i].b;
+                }
+                reverse_index_bits_in_place(flat.data(), arity, 2);
+                for (size_t i = 0; i < arity; i++) ev[i] = E2{flat[2 * i], flat[2 * i + 1]};
+                const size_t rev_within = reverse_bits(within, arity_bits);
+                const u64 coset_start = fmul(subgroup_x, fexp(g, arity - rev_within));
+                std::vector<E2> xs(arity);
+                u64 y = 1;
+                for (size_t i = 0; i < arity; i++) {
+                    xs[i] = e2(fmul(coset_start, y));
+                    y = fmul(y, g);
+                }
+                const E2 beta = betas[r];
+                E2 result = e2(0);
+                bool hit = false;
+                for (size_t i = 0; i < arity; i++)
+                    if (eeq(xs[i], beta)) {
+                        result = ev[i];
+                        hit = true;
+                    }
+                if (!hit) {
+                    E2 l_x = e2(1);
+                    for (size_t i = 0; i < arity; i++) l_x = emul(l_x, esub(beta, xs[i]));
+                    E2 sacc = e2(0);
+                    for (size_t i = 0; i < arity; i++) {
+                        E2 w = e2(1);
+                        for (size_t j = 0; j < arity; j++)
+                            if (j != i) w = emul(w, esub(xs[i], xs[j]));
+                        sacc = eadd(sacc, emul(emul(einv(w), einv(esub(beta, xs[i]))), ev[i]));
+                    }
+                    result = emul(l_x, sacc);
+                }
+                old_eval = result;
+            }
+            std::vector<u64> flat(2 * arity);
+            for (size_t i = 0; i < arity; i++) {
+                flat[2 * i] = evals[i].a;
+                flat[2 * i + 1] = evals[i].b;
+            }
+            if (!merkle_verify(flat.data(), flat.size(), coset_index, q.step_sib[r].data(), q.step_sib[r].size(), caps[r].data()))
+                return 15;
+            for (uint32_t k = 0; k < arity_bits; k++) subgroup_x = fsqr(subgroup_x);
+            x_index = coset_index;
+            n -= arity_bits;
+            if (batch_index < n_instances && n == heights[batch_index]) {
+                const u64 subgroup_x_init =
+                    fmul(MULTIPLICATIVE_GROUP_GENERATOR, fexp(primitive_root_of_unity(n), reverse_bits(x_index, n)));
+                const E2 eval = combine_initial(q, batch_index, subgroup_x_init);
+                old_eval = eadd(emul(old_eval, betas[r]), eval);
+                batch_index++;
+            }
+        }
+        if (batch_index != n_instances) return 17;  // "Wrong number of folded instances."
+        E2 acc = e2(0);
+        for (size_t k = final_poly.size(); k-- > 0;) acc = eadd(escale(acc, subgroup_x), final_poly[k]);
+        if (!eeq(acc, old_eval)) return 16;
+    }
+    return 0;
+}
+
 // verify_fri_proof, fri/verifier.rs:62-241 with challenges from challenges.rs:28-75
 int glo_verify_fri_proof(const uint64_t* const* initial_caps, const size_t* oracle_num_polys,
                          const size_t* oracle_leaf_width, size_t n_oracles, const glo_fri_batch* batches,

@@ -159,6 +159,14 @@ int glo_batch_prove_openings(const glo_batch_commit* const* oracles, size_t n_or
                              const glo_fri_instance* instances, size_t n_instances, glo_challenger* challenger,
                              const glo_fri_params* params, uint8_t** out, size_t* out_len);
 
+/* Restated batch-FRI verifier (plonky2/src/batch_fri/verifier.rs:22-251): group_num_polys[o * n_instances + i] =
+ * polynomials of oracle o in degree group i; opened_values per instance, per batch, per polynomial (2 words each).
+ * challenger in the state batch_prove_openings started from. Returns 0 if the proof verifies. */
+int glo_verify_batch_fri_proof(const uint64_t* const* initial_caps, const size_t* group_num_polys, size_t n_oracles,
+                               const uint32_t* degree_bits, const glo_fri_instance* instances, size_t n_instances,
+                               const uint64_t* opened_values, glo_challenger* challenger, const glo_fri_params* params,
+                               const uint8_t* proof, size_t proof_len);
+
 /* Restated FRI verifier (plonky2/src/fri/verifier.rs:62-241, challenges.rs:28-75): checks a
  * serialised proof against the initial caps and the claimed openings. challenger must be in the
  * same state prove_openings started from. opened_values: for each batch, for each polynomial,

@@ -136,6 +136,9 @@ def lib():
     L.glo_batch_prove_openings.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, u32p, C.POINTER(FriInstance), C.c_size_t,
                                            C.c_void_p, C.POINTER(FriParams), C.POINTER(C.POINTER(C.c_uint8)),
                                            C.POINTER(C.c_size_t)]
+    L.glo_verify_batch_fri_proof.restype = C.c_int
+    L.glo_verify_batch_fri_proof.argtypes = [C.POINTER(u64p), C.POINTER(C.c_size_t), C.c_size_t, u32p, C.POINTER(FriInstance),
+                                             C.c_size_t, u64p, C.c_void_p, C.POINTER(FriParams), C.POINTER(C.c_uint8), C.c_size_t]
     L.glo_lookup_polys.restype = C.c_int
     L.glo_lookup_polys.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u32p, C.c_uint32, u64p]
     L.glo_stark_quotient_fibonacci.restype = C.c_int
@@ -524,3 +527,25 @@ def batch_prove_openings(commits, degree_bits, instances, challenger, params):
     proof = bytes(C.string_at(out, out_len.value))
     L.glo_free(out)
     return proof
+
+
+def verify_batch_fri_proof(caps, group_num_polys, degree_bits, instances, opened_values, challenger, params, proof):
+    """caps: per oracle (C, 4); group_num_polys: per oracle, per degree group; instances as in batch_prove_openings;
+    opened_values: flat sequence of F_{p^2} values (per instance, per batch, per polynomial)."""
+    L = lib()
+    caps = [np.ascontiguousarray(c, dtype=np.uint64) for c in caps]
+    cap_ptrs = (u64p * len(caps))(*[ptr(c) for c in caps])
+    flat = [int(x) for row in group_num_polys for x in row]
+    gnp = (C.c_size_t * len(flat))(*flat)
+    insts = (FriInstance * len(instances))()
+    keep = []
+    for i, batches in enumerate(instances):
+        barr, k = _make_batches(batches)
+        keep += [barr, k]
+        insts[i].batches = C.cast(barr, C.POINTER(FriBatch))
+        insts[i].n_batches = len(batches)
+    db = np.array(degree_bits, dtype=np.uint32)
+    ov = np.ascontiguousarray(opened_values, dtype=np.uint64).ravel()
+    buf = (C.c_uint8 * len(proof)).from_buffer_copy(proof)
+    return L.glo_verify_batch_fri_proof(cap_ptrs, gnp, len(caps), db.ctypes.data_as(u32p), insts, len(instances), ptr(ov),
+                                        challenger.h, C.byref(params), buf, len(proof))

@@ -369,3 +369,36 @@ def test_partial_products_restatement_satisfies_the_permutation_argument(oracle)
     out2 = oracle.partial_products_and_zs(wires, sigmas, np.array(k_is, dtype=np.uint64), beta, gamma, deg)
     last = int(out2[0][n - 1]) * (lambda i: q(i, 1))(n - 1) % P_
     assert last != 1
+
+
+def test_batch_fri_proof_passes_the_restated_batch_verifier(oracle):
+    """Pin of the multi-degree batch-FRI restatement: its proof (the reference test's shape, batch_fri/prover.rs:341-477,
+    plus a richer one) is accepted by the restated verify_batch_fri_proof (batch_fri/verifier.rs:22-251) with the
+    polynomials' true openings, and rejected with a wrong opening or a flipped byte."""
+    for lens, counts, r, h, arities, nq, pow_bits in ([9, 8, 6], [1, 1, 1], 1, 5, [1, 2, 1], 10, 0), ([10, 8, 6], [3, 2, 2], 2, 3, [2, 2, 2], 5, 4):
+        polys, degree_of = [], []
+        for k, c in zip(lens, counts):
+            for j in range(c):
+                polys.append(synth(0x200 + 16 * k + j, (1 << k,)))
+                degree_of.append(k)
+        oo = oracle.BatchCommit(polys, r, h)
+        coeffs = [oracle.ifft(p) for p in polys]
+        och = oracle.Challenger()
+        och.observe_cap(oo.cap)
+        zeta = och.get_extension_challenge()
+        instances, opened = [], []
+        for k in lens:
+            idx = [i for i, d in enumerate(degree_of) if d == k]
+            instances.append([(zeta, [(0, i) for i in idx])])
+            opened += [oracle.eval_poly_base_at_ext(coeffs[i], zeta) for i in idx]
+        vch = och.clone()
+        params = oracle.make_params(r, h, pow_bits, nq, arities)
+        proof = oracle.batch_prove_openings([oo], lens, instances, och, params)
+        ov = np.array(opened, dtype=np.uint64)
+        assert oracle.verify_batch_fri_proof([oo.cap], [counts], lens, instances, ov, vch.clone(), params, proof) == 0
+        bad = ov.copy()
+        bad[0, 0] ^= np.uint64(1)
+        assert oracle.verify_batch_fri_proof([oo.cap], [counts], lens, instances, bad, vch.clone(), params, proof) != 0
+        flipped = bytearray(proof)
+        flipped[len(flipped) // 2] ^= 8
+        assert oracle.verify_batch_fri_proof([oo.cap], [counts], lens, instances, ov, vch.clone(), params, bytes(flipped)) != 0
