@@ -225,6 +225,38 @@ int gl_stark_quotient(gl_ctx* ctx, gl_commit* trace, const gl_stark_instr* progr
                       const uint64_t* consts, uint32_t n_consts, const uint64_t* alphas, uint32_t n_alphas,
                       uint32_t quotient_degree_factor, uint64_t* out_coeffs);
 
+/* compute_quotient_polys of a plonky2 circuit (plonky2/src/plonk/prover.rs:609-815): for every challenge alpha_k the
+ * values eval_vanishing_poly_base_batch(x) / Z_H(x) (plonky2/src/plonk/vanishing_poly.rs:167-340) on the coset g<w_size>,
+ * size = n << log2_ceil(quotient_degree_factor), then coset_ifft: n_alphas polynomials of `size` coefficients at
+ * out_coeffs + k*size (DEVICE memory); coefficients beyond n * quotient_degree_factor are checked to vanish ("Quotient
+ * has failed ...", prover.rs:327-331 -> GL_ERR_BAD_ARG). The LDEs of the commitments (constants_sigmas, wires,
+ * zs_partial_products[_lookup], ...: all of one degree and rate, whole on this device) are read IN PLACE with
+ * get_lde_values addressing (fri/oracle.rs:142-147).
+ * The vanishing polynomial -- every gate's eval_unfiltered_base with its selector filter (gates/gate.rs:159-185,326-333),
+ * L_0(x)(Z(x) - 1) and check_partial_products (util/partial_products.rs:52-76) -- is a register program: each
+ * instruction writes register dst; GL_VP_TERM contributes vanishing term number b, and the result for challenge k is
+ * sum_t alpha_k^t term_t (reduce_with_powers_multi, plonk_common.rs:99-116; the order of the sum does not matter).
+ * plonky2_b200/plonk.py builds the program from a gate list the way eval_vanishing_poly_base_batch walks it. */
+#define GL_VP_LOCAL 0 /* r[dst] = column b of commitment a at this point's row: get_lde_values(i, step) */
+#define GL_VP_NEXT 1  /* ... at the row of point i + next_step (the Z(g x) operand) */
+#define GL_VP_CONST 2 /* r[dst] = consts[a | b << 16] */
+#define GL_VP_X 3     /* r[dst] = x = coset_shift * w_size^i (shifted_x) */
+#define GL_VP_L0 4    /* r[dst] = L_0(x) = Z_H(x) / (n (x - 1)) (ZeroPolyOnCoset::eval_l_0) */
+#define GL_VP_ADD 5   /* r[dst] = r[a] + r[b] */
+#define GL_VP_SUB 6
+#define GL_VP_MUL 7
+#define GL_VP_TERM 8  /* vanishing term number b = r[a] */
+#define GL_VP_MAX_REGS 256
+#define GL_VP_MAX_COMMITS 4
+#define GL_VP_MAX_ALPHAS 4
+#define GL_VP_MAX_QD 8
+typedef struct {
+    uint16_t op, dst, a, b;
+} gl_vp_instr;
+int gl_plonk_quotient(gl_ctx* ctx, gl_commit* const* commits, uint32_t n_commits, const gl_vp_instr* program,
+                      uint32_t n_instr, const uint64_t* consts, uint32_t n_consts, const uint64_t* alphas,
+                      uint32_t n_alphas, uint32_t n_terms, uint32_t quotient_degree_factor, uint64_t* out_coeffs);
+
 /* ---- Hasher / MerkleTree  (plonky2/src/plonk/config.rs:36-77, plonky2/src/hash/merkle_tree.rs:193-237) */
 /* PoseidonPermutation::permute on the HOST for the sequential Fiat-Shamir transcript
  * (plonky2/src/iop/challenger.rs:129-144); the same source as the device permutation. */

@@ -1208,6 +1208,150 @@ int glo_stark_quotient_fibonacci(const glo_commit* trace, const uint64_t pi[3], 
     return 0;
 }
 
+// compute_quotient_polys (plonky2/src/plonk/prover.rs:609-815) with eval_vanishing_poly_base_batch
+// (plonk/vanishing_poly.rs:167-340, no lookups) for circuits made of NoopGate, ConstantGate, PublicInputGate and
+// ArithmeticGate (gates/{noop,constant,public_input,arithmetic_base}.rs), restated with the reference's own steps:
+// evaluate_gate_constraints_base_batch (vanishing_poly.rs:702-728) with compute_filter (gates/gate.rs:326-333),
+// L_0(x)(Z(x) - 1), check_partial_products (util/partial_products.rs:52-76), reduce_with_powers_multi
+// (plonk_common.rs:99-116), ZeroPolyOnCoset (field/src/zero_poly_coset.rs), transpose, coset_ifft. BATCH_SIZE = 1.
+static const u64 UNUSED_SELECTOR = 0xFFFFFFFFull;  // gates/selectors.rs:14
+static void gate_eval_unfiltered(const glo_gate& g, const u64* local_constants, const u64* local_wires,
+                                 const uint64_t public_inputs_hash[4], std::vector<u64>& res) {
+    res.clear();
+    switch (g.kind) {
+        case GLO_GATE_NOOP: break;
+        case GLO_GATE_CONSTANT:  // constant.rs:121-129
+            for (uint32_t i = 0; i < g.param; i++) res.push_back(fsub(local_constants[i], local_wires[i]));
+            break;
+        case GLO_GATE_PUBLIC_INPUT:  // public_input.rs:103-113
+            for (uint32_t i = 0; i < 4; i++) res.push_back(fsub(local_wires[i], public_inputs_hash[i]));
+            break;
+        case GLO_GATE_ARITHMETIC: {  // arithmetic_base.rs:168-185
+            const u64 const_0 = local_constants[0], const_1 = local_constants[1];
+            for (uint32_t i = 0; i < g.param; i++) {
+                const u64 multiplicand_0 = local_wires[4 * i], multiplicand_1 = local_wires[4 * i + 1];
+                const u64 addend = local_wires[4 * i + 2], output = local_wires[4 * i + 3];
+                const u64 computed_output = fadd(fmul(fmul(multiplicand_0, multiplicand_1), const_0), fmul(addend, const_1));
+                res.push_back(fsub(output, computed_output));
+            }
+            break;
+        }
+    }
+}
+
+int glo_plonk_quotient(const glo_circuit* cd, const glo_commit* constants_sigmas, const glo_commit* wires,
+                       const glo_commit* zs_partial_products, const uint64_t public_inputs_hash[4], const uint64_t* betas,
+                       const uint64_t* gammas, const uint64_t* alphas, uint64_t* out) {
+    const uint32_t degree_bits = wires->degree_log, rate_bits = wires->rate_bits;
+    if (constants_sigmas->degree_log != degree_bits || zs_partial_products->degree_log != degree_bits) return 1;
+    if (constants_sigmas->rate_bits != rate_bits || zs_partial_products->rate_bits != rate_bits) return 1;
+    const size_t num_challenges = cd->num_challenges, num_routed_wires = cd->num_routed_wires;
+    const size_t num_prods = cd->num_partial_products, max_degree = cd->quotient_degree_factor;
+    if (constants_sigmas->B != cd->num_constants + num_routed_wires || wires->B != cd->num_wires ||
+        zs_partial_products->B != num_challenges * (1 + num_prods))
+        return 3;
+    if (num_prods + 1 != (num_routed_wires + max_degree - 1) / max_degree) return 4;  // num_partial_products, partial_products.rs:40-46
+    uint32_t quotient_degree_bits = 0;
+    while (((size_t)1 << quotient_degree_bits) < cd->quotient_degree_factor) quotient_degree_bits++;
+    if (quotient_degree_bits > rate_bits) return 2;
+    const size_t degree = (size_t)1 << degree_bits;
+    const size_t step = (size_t)1 << (rate_bits - quotient_degree_bits);
+    const size_t next_step = (size_t)1 << quotient_degree_bits;
+    const size_t lde_size = degree << quotient_degree_bits;
+    // ZeroPolyOnCoset::new(degree_bits, quotient_degree_bits)
+    u64 g_pow_n = MULTIPLICATIVE_GROUP_GENERATOR;
+    for (uint32_t k = 0; k < degree_bits; k++) g_pow_n = fsqr(g_pow_n);
+    const size_t rate = (size_t)1 << quotient_degree_bits;
+    std::vector<u64> zh_evals(rate), zh_inverses(rate);
+    {
+        u64 w = primitive_root_of_unity(quotient_degree_bits), x = 1;
+        for (size_t j = 0; j < rate; j++) {
+            zh_evals[j] = fsub(fmul(g_pow_n, x), 1);
+            zh_inverses[j] = finv(zh_evals[j]);
+            x = fmul(x, w);
+        }
+    }
+    const u64 n_field = canon((u64)degree);
+    const u64 w_lde = primitive_root_of_unity(degree_bits + quotient_degree_bits);
+    std::vector<u64> points(lde_size);  // two_adic_subgroup
+    {
+        u64 x = 1;
+        for (size_t i = 0; i < lde_size; i++) {
+            points[i] = x;
+            x = fmul(x, w_lde);
+        }
+    }
+    std::vector<u64> quotient_values(lde_size * num_challenges);
+    std::vector<u64> local_constants_sigmas(constants_sigmas->B), local_wires(wires->B), local_zs(zs_partial_products->B),
+        next_zs(zs_partial_products->B), gate_res, constraint_terms(cd->num_gate_constraints), vanishing_terms;
+    for (size_t i = 0; i < lde_size; i++) {
+        const u64 shifted_x = fmul(MULTIPLICATIVE_GROUP_GENERATOR, points[i]);
+        const size_t i_next = (i + next_step) % lde_size;
+        glo_commit_get_lde_values(constants_sigmas, i, step, local_constants_sigmas.data());
+        glo_commit_get_lde_values(wires, i, step, local_wires.data());
+        glo_commit_get_lde_values(zs_partial_products, i, step, local_zs.data());
+        glo_commit_get_lde_values(zs_partial_products, i_next, step, next_zs.data());
+        const u64* local_constants = local_constants_sigmas.data();              // constants_range
+        const u64* s_sigmas = local_constants_sigmas.data() + cd->num_constants;  // sigmas_range
+        const u64* partial_products = local_zs.data() + num_challenges;           // partial_products_range
+        // evaluate_gate_constraints_base_batch
+        std::fill(constraint_terms.begin(), constraint_terms.end(), 0);
+        for (size_t gi = 0; gi < cd->n_gates; gi++) {
+            const glo_gate& g = cd->gates[gi];
+            const u64 s = local_constants[g.selector_index];
+            u64 filter = 1;  // compute_filter
+            for (size_t j = g.group_start; j < g.group_end; j++)
+                if (j != gi) filter = fmul(filter, fsub(canon((u64)j), s));
+            if (cd->num_selectors > 1) filter = fmul(filter, fsub(UNUSED_SELECTOR, s));
+            gate_eval_unfiltered(g, local_constants + cd->num_selectors, local_wires.data(), public_inputs_hash, gate_res);
+            if (gate_res.size() > constraint_terms.size()) return 5;  // "num_constraints() gave too low of a number"
+            for (size_t j = 0; j < gate_res.size(); j++) constraint_terms[j] = fadd(constraint_terms[j], fmul(gate_res[j], filter));
+        }
+        vanishing_terms.clear();
+        const u64 l_0_x = fmul(zh_evals[i % rate], finv(fmul(n_field, fsub(shifted_x, 1))));  // eval_l_0
+        std::vector<u64> vanishing_partial_products_terms;
+        for (size_t c = 0; c < num_challenges; c++) {
+            const u64 z_x = local_zs[c], z_gx = next_zs[c];
+            vanishing_terms.push_back(fmul(l_0_x, fsub(z_x, 1)));  // vanishing_z_1_terms
+            std::vector<u64> numerator_values(num_routed_wires), denominator_values(num_routed_wires);
+            for (size_t j = 0; j < num_routed_wires; j++) {
+                const u64 wire_value = local_wires[j];
+                const u64 s_id = fmul(cd->k_is[j], shifted_x);
+                numerator_values[j] = fadd(fadd(wire_value, fmul(betas[c], s_id)), gammas[c]);
+                denominator_values[j] = fadd(fadd(wire_value, fmul(betas[c], s_sigmas[j])), gammas[c]);
+            }
+            // check_partial_products
+            const u64* current_partial_products = partial_products + c * num_prods;
+            for (size_t k = 0; k * max_degree < num_routed_wires; k++) {
+                const size_t lo = k * max_degree, hi = std::min(lo + max_degree, num_routed_wires);
+                u64 num_chunk_product = 1, den_chunk_product = 1;
+                for (size_t j = lo; j < hi; j++) {
+                    num_chunk_product = fmul(num_chunk_product, numerator_values[j]);
+                    den_chunk_product = fmul(den_chunk_product, denominator_values[j]);
+                }
+                const u64 prev_acc = k == 0 ? z_x : current_partial_products[k - 1];
+                const u64 next_acc = k == num_prods ? z_gx : current_partial_products[k];
+                vanishing_partial_products_terms.push_back(fsub(fmul(prev_acc, num_chunk_product), fmul(next_acc, den_chunk_product)));
+            }
+        }
+        vanishing_terms.insert(vanishing_terms.end(), vanishing_partial_products_terms.begin(), vanishing_partial_products_terms.end());
+        vanishing_terms.insert(vanishing_terms.end(), constraint_terms.begin(), constraint_terms.end());
+        const u64 denominator_inv = zh_inverses[i % rate];
+        for (size_t c = 0; c < num_challenges; c++) {  // reduce_with_powers_multi
+            u64 cumul = 0;
+            for (size_t t = vanishing_terms.size(); t-- > 0;) cumul = fadd(fmul(cumul, alphas[c]), vanishing_terms[t]);
+            quotient_values[i * num_challenges + c] = fmul(cumul, denominator_inv);
+        }
+    }
+    for (size_t c = 0; c < num_challenges; c++) {  // transpose + coset_ifft
+        u64* col = out + c * lde_size;
+        for (size_t i = 0; i < lde_size; i++) col[i] = quotient_values[i * num_challenges + c];
+        coset_ifft(col, lde_size, MULTIPLICATIVE_GROUP_GENERATOR);
+        for (size_t i = 0; i < lde_size; i++) col[i] = canon(col[i]);
+    }
+    return 0;
+}
+
 void glo_eval_poly_base_at_ext(const uint64_t* coeffs, size_t n, const uint64_t z[2], uint64_t out[2]) {
     E2 zz{z[0], z[1]}, acc = e2(0);
     for (size_t k = n; k-- > 0;) acc = eadd(emul(acc, zz), e2(coeffs[k]));

@@ -159,6 +159,29 @@ int glo_batch_prove_openings(const glo_batch_commit* const* oracles, size_t n_or
                              const glo_fri_instance* instances, size_t n_instances, glo_challenger* challenger,
                              const glo_fri_params* params, uint8_t** out, size_t* out_len);
 
+/* compute_quotient_polys (plonky2/src/plonk/prover.rs:609-815) + eval_vanishing_poly_base_batch
+ * (plonk/vanishing_poly.rs:167-340, circuits without lookups) for the gates below. out: num_challenges polynomials of
+ * n << log2_ceil(quotient_degree_factor) coefficients. */
+#define GLO_GATE_NOOP 0         /* gates/noop.rs */
+#define GLO_GATE_CONSTANT 1     /* gates/constant.rs, param = num_consts */
+#define GLO_GATE_PUBLIC_INPUT 2 /* gates/public_input.rs */
+#define GLO_GATE_ARITHMETIC 3   /* gates/arithmetic_base.rs, param = num_ops */
+typedef struct {
+    uint32_t kind, param;
+    uint32_t selector_index;          /* SelectorsInfo.selector_indices[gate] (gates/selectors.rs:17-20) */
+    uint32_t group_start, group_end;  /* SelectorsInfo.groups[selector_index] */
+} glo_gate;
+typedef struct {
+    uint32_t num_wires, num_routed_wires, num_constants /* selectors included */, num_challenges;
+    uint32_t quotient_degree_factor, num_selectors, num_partial_products, num_gate_constraints;
+    const glo_gate* gates; /* sorted the way CommonCircuitData.gates is */
+    size_t n_gates;
+    const uint64_t* k_is;
+} glo_circuit;
+int glo_plonk_quotient(const glo_circuit* cd, const glo_commit* constants_sigmas, const glo_commit* wires,
+                       const glo_commit* zs_partial_products, const uint64_t public_inputs_hash[4], const uint64_t* betas,
+                       const uint64_t* gammas, const uint64_t* alphas, uint64_t* out);
+
 /* Restated batch-FRI verifier (plonky2/src/batch_fri/verifier.rs:22-251): group_num_polys[o * n_instances + i] =
  * polynomials of oracle o in degree group i; opened_values per instance, per batch, per polynomial (2 words each).
  * challenger in the state batch_prove_openings started from. Returns 0 if the proof verifies. */

@@ -15,6 +15,7 @@ from .hash import (MerkleCap, MerkleProof, MerkleTree, PoseidonHash, PoseidonPer
 from .polynomial_batch import SALT_SIZE, PolynomialBatch  # noqa: F401
 from .proof import OpeningSet, StarkOpeningSet, eval_commitments  # noqa: F401
 from .stark import FibonacciStark, Stark, commit_quotient_polys, compute_quotient_polys  # noqa: F401
+from . import plonk  # noqa: F401  (plonk.compute_quotient_polys: the plonky2 circuit quotient)
 from .batch_merkle_tree import (BatchMerkleTree, compress_merkle_proofs, decompress_merkle_proofs,  # noqa: F401
                                 verify_batch_merkle_proof_to_cap)
 from .batch_fri import BatchFriOracle, batch_prove_openings  # noqa: F401

@@ -22,6 +22,7 @@
 #include "gl_field.cuh"
 #include "gl_ntt.cuh"
 #include "gl_poseidon.cuh"
+#include "gl_vanishing.cuh"
 
 using namespace gl;
 typedef uint64_t u64;
@@ -1205,6 +1206,16 @@ __global__ void k_any_nonzero(const u64* data, size_t stride, size_t begin, size
     if (canon(data[(size_t)blockIdx.y * stride + begin + i]) != 0) atomicOr(flag, 2u);
 }
 
+// ---- plonky2 quotient evaluation (compute_quotient_polys, plonk/prover.rs:609-815) ----
+// one thread per point of the quotient coset; the point's evaluation is gl_vanishing.cuh
+__global__ void __launch_bounds__(128) k_plonk_quotient(VanishingParams p) {
+    const size_t size = (size_t)1 << (p.degree_bits + p.qd_bits);
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= size) return;
+    u64 regs[GL_VP_MAX_REGS];
+    if (!vp_eval_point(p, i, regs)) atomicOr(p.flag, 1u);
+}
+
 // proof-of-work grind (prover.rs:183-194): smallest qualifying nonce via atomicMin
 struct PowParams {
     u64 state[12];
@@ -1958,6 +1969,120 @@ int gl_stark_quotient(gl_ctx* ctx, gl_commit* trace, const gl_stark_instr* progr
     int rc = body();
     dfree(ctx, dprog);
     dfree(ctx, dconst);
+    dfree(ctx, xtab);
+    dfree(ctx, dflag);
+    return rc;
+}
+
+int gl_plonk_quotient(gl_ctx* ctx, gl_commit* const* commits, uint32_t n_commits, const gl_vp_instr* program,
+                      uint32_t n_instr, const uint64_t* consts, uint32_t n_consts, const uint64_t* alphas,
+                      uint32_t n_alphas, uint32_t n_terms, uint32_t quotient_degree_factor, uint64_t* out_coeffs) {
+    if (!ctx || !commits || !program || !alphas || !out_coeffs) return set_err(ctx, GL_ERR_BAD_ARG, "null argument");
+    if (n_commits == 0 || n_commits > GL_VP_MAX_COMMITS) return set_err(ctx, GL_ERR_UNSUPPORTED, "1..%d commitments", GL_VP_MAX_COMMITS);
+    if (n_instr == 0) return set_err(ctx, GL_ERR_BAD_ARG, "empty program");
+    if (n_alphas == 0 || n_alphas > GL_VP_MAX_ALPHAS) return set_err(ctx, GL_ERR_UNSUPPORTED, "1..%d challenges", GL_VP_MAX_ALPHAS);
+    if (n_terms == 0 || n_terms > 65536) return set_err(ctx, GL_ERR_BAD_ARG, "1..65536 vanishing terms");
+    if (quotient_degree_factor == 0) return set_err(ctx, GL_ERR_BAD_ARG, "quotient_degree_factor is 0");
+    for (uint32_t c = 0; c < n_commits; c++) {
+        if (!commits[c]) return set_err(ctx, GL_ERR_BAD_ARG, "null commitment");
+        if (commits[c]->ctx != ctx) return set_err(ctx, GL_ERR_BAD_ARG, "commitment %u belongs to another context", c);
+        if (commits[c]->shard_log) return set_err(ctx, GL_ERR_UNSUPPORTED, "quotient evaluation needs the whole LDE on this device");
+        NEED_FINISHED(commits[c]);
+        if (commits[c]->degree_log != commits[0]->degree_log || commits[c]->rate_bits != commits[0]->rate_bits)
+            return set_err(ctx, GL_ERR_BAD_SHAPE, "commitments of different degree or rate");
+    }
+    const uint32_t db = commits[0]->degree_log, rate_bits = commits[0]->rate_bits;
+    uint32_t qd_bits = 0;
+    while ((1u << qd_bits) < quotient_degree_factor) qd_bits++;  // log2_ceil
+    if (qd_bits > rate_bits)
+        return set_err(ctx, GL_ERR_UNSUPPORTED, "Having constraints of degree higher than the rate is not supported yet.");
+    if ((1u << qd_bits) > GL_VP_MAX_QD) return set_err(ctx, GL_ERR_UNSUPPORTED, "quotient degree factor too large");
+    for (uint32_t k = 0; k < n_instr; k++) {  // validate once on the host: the kernel trusts the program
+        const gl_vp_instr in = program[k];
+        bool ok = in.dst < GL_VP_MAX_REGS;
+        switch (in.op) {
+            case GL_VP_LOCAL: case GL_VP_NEXT: ok = ok && in.a < n_commits && in.b < commits[in.a]->W; break;
+            case GL_VP_CONST: ok = ok && ((uint32_t)in.a | ((uint32_t)in.b << 16)) < n_consts; break;
+            case GL_VP_X: case GL_VP_L0: break;
+            case GL_VP_ADD: case GL_VP_SUB: case GL_VP_MUL: ok = ok && in.a < GL_VP_MAX_REGS && in.b < GL_VP_MAX_REGS; break;
+            case GL_VP_TERM: ok = in.a < GL_VP_MAX_REGS && in.b < n_terms; break;
+            default: ok = false;
+        }
+        if (!ok) return set_err(ctx, GL_ERR_BAD_ARG, "vanishing program: bad instruction %u", k);
+    }
+    CK(ctx, cudaSetDevice(ctx->device));
+    const uint32_t size_log = db + qd_bits;
+    const size_t size = (size_t)1 << size_log;
+    u64 *dprog = nullptr, *dconst = nullptr, *dapow = nullptr, *xtab = nullptr, *dflag = nullptr;
+    auto body = [&]() -> int {
+        const size_t prog_words = ((size_t)n_instr * sizeof(gl_vp_instr) + 7) / 8;
+        TRY(dmalloc(ctx, &dprog, prog_words));
+        TRY(h2d(ctx, dprog, (const u64*)program, prog_words));
+        TRY(dmalloc(ctx, &dconst, n_consts ? n_consts : 1));
+        if (n_consts) TRY(h2d(ctx, dconst, consts, n_consts));
+        std::vector<u64> apow((size_t)n_alphas * n_terms);
+        for (uint32_t a = 0; a < n_alphas; a++) {
+            u64 pw = 1;
+            for (uint32_t t = 0; t < n_terms; t++, pw = mul(pw, alphas[a])) apow[(size_t)a * n_terms + t] = canon(pw);
+        }
+        TRY(dmalloc(ctx, &dapow, apow.size()));
+        TRY(h2d(ctx, dapow, apow.data(), apow.size()));
+        TRY(dmalloc(ctx, &dflag, 1));
+        CK(ctx, cudaMemsetAsync(dflag, 0, 8, ctx->stream));
+        const u64 ws = root_of_unity(size_log);
+        const size_t tcnt = 4096 > (size >> 12) + 1 ? 4096 : (size >> 12) + 1;
+        TRY(build_pow_tables(ctx, std::vector<u64>{gl::pow(ws, 4096), ws}, tcnt, &xtab));
+        VanishingParams p;
+        for (uint32_t c = 0; c < GL_VP_MAX_COMMITS; c++) {
+            p.lde[c] = c < n_commits ? commits[c]->tree.leaves : nullptr;
+            p.lde_stride[c] = c < n_commits ? commits[c]->tree.es : 0;
+        }
+        p.log_N = db + rate_bits;
+        p.degree_bits = db;
+        p.qd_bits = qd_bits;
+        p.prog = (const gl_vp_instr*)dprog;
+        p.n_instr = n_instr;
+        p.consts = dconst;
+        p.apow = dapow;
+        p.n_alphas = n_alphas;
+        p.n_terms = n_terms;
+        p.xhi = xtab;
+        p.xlo = xtab + tcnt;
+        p.shift = MULTIPLICATIVE_GROUP_GENERATOR;
+        p.n_field = canon((u64)1 << db);
+        // ZeroPolyOnCoset::new(degree_bits, qd_bits) (field/src/zero_poly_coset.rs:20-34)
+        u64 g_pow_n = MULTIPLICATIVE_GROUP_GENERATOR;
+        for (uint32_t k = 0; k < db; k++) g_pow_n = sqr(g_pow_n);
+        const u64 wq = root_of_unity(qd_bits);
+        u64 xq = 1;
+        for (uint32_t j = 0; j < GL_VP_MAX_QD; j++) p.zh[j] = p.zh_inv[j] = 0;
+        for (uint32_t j = 0; j < (1u << qd_bits); j++, xq = mul(xq, wq)) {
+            p.zh[j] = canon(sub(mul(g_pow_n, xq), 1));
+            p.zh_inv[j] = canon(gl::inv(p.zh[j]));
+        }
+        p.out = out_coeffs;
+        p.flag = (unsigned int*)dflag;
+        k_plonk_quotient<<<(unsigned)((size + 127) / 128), 128, 0, ctx->stream>>>(p);
+        CKL(ctx);
+        // .coset_ifft(F::coset_shift()) of every challenge's values (prover.rs:811-814)
+        TRY(ntt_natural(ctx, out_coeffs, size, out_coeffs, size, (int)size_log, n_alphas, true, MULTIPLICATIVE_GROUP_GENERATOR));
+        // trim_to_len(quotient_degree) (prover.rs:327-331): the rest must vanish
+        const size_t keep = ((size_t)quotient_degree_factor) << db;
+        if (keep < size) {
+            k_any_nonzero<<<dim3((unsigned)((size - keep + 255) / 256), n_alphas), 256, 0, ctx->stream>>>(out_coeffs, size, keep,
+                                                                                                   size - keep, (unsigned int*)dflag);
+            CKL(ctx);
+        }
+        u64 flag = 0;
+        TRY(d2h(ctx, &flag, dflag, 1));  // synchronises: the host tables above outlive the copies
+        if (flag & 1u) return set_err(ctx, GL_ERR_DIV_ZERO, "Tried to invert zero");
+        if (flag & 2u) return set_err(ctx, GL_ERR_BAD_ARG, "Quotient has failed, the vanishing polynomial is not divisible by Z_H");
+        return GL_OK;
+    };
+    int rc = body();
+    dfree(ctx, dprog);
+    dfree(ctx, dconst);
+    dfree(ctx, dapow);
     dfree(ctx, xtab);
     dfree(ctx, dflag);
     return rc;

@@ -1,0 +1,577 @@
+"""plonky2's quotient polynomials on the device: compute_quotient_polys
+(plonky2/src/plonk/prover.rs:609-815) over eval_vanishing_poly_base_batch (plonky2/src/plonk/vanishing_poly.rs:167-340).
+
+The reference evaluates, for every point of the quotient coset, each gate's constraints times its selector filter, the
+terms L_0(x)(Z(x) - 1) and the partial-product checks of the permutation argument, and combines them with powers of
+alpha. Here that walk is done ONCE per circuit, symbolically: gates implement eval_unfiltered over expression handles,
+`vanishing_program` records the whole vanishing polynomial as a register program, and gl_plonk_quotient interprets it
+for all points on the GPU, reading the three commitments' LDEs in place. Circuit construction itself (CircuitBuilder,
+witness generation) stays with the caller; `CommonCircuitData.from_gate_instances` restates only what the quotient
+needs from `CircuitBuilder::build` (gate order, selector polynomials, constant columns, k_is, counts).
+No lookups yet (has_lookup = false)."""
+import ctypes as C
+import heapq
+
+import numpy as np
+
+from . import _native as N
+from . import field as F
+from .polynomial_batch import PolynomialBatch
+
+OP_LOCAL, OP_NEXT, OP_CONST, OP_X, OP_L0, OP_ADD, OP_SUB, OP_MUL, OP_TERM = range(9)
+MAX_REGS = 256
+UNUSED_SELECTOR = 0xFFFFFFFF   # gates/selectors.rs:14
+# commitment indices of the program's loads
+CONSTANTS_SIGMAS, WIRES, ZS_PARTIAL_PRODUCTS = 0, 1, 2
+
+
+class VpInstr(C.Structure):
+    _fields_ = [("op", C.c_uint16), ("dst", C.c_uint16), ("a", C.c_uint16), ("b", C.c_uint16)]
+
+
+class CircuitConfig:
+    """CircuitConfig (plonk/circuit_data.rs:60-131); defaults = standard_recursion_config."""
+
+    def __init__(self, num_wires=135, num_routed_wires=80, num_constants=2, num_challenges=2,
+                 max_quotient_degree_factor=8, rate_bits=3, cap_height=4):
+        self.num_wires, self.num_routed_wires, self.num_constants = num_wires, num_routed_wires, num_constants
+        self.num_challenges, self.max_quotient_degree_factor = num_challenges, max_quotient_degree_factor
+        self.rate_bits, self.cap_height = rate_bits, cap_height
+
+
+# ------------------------------------------------------------------ expressions
+class Expr:
+    """A base-field value of the vanishing program (the F / P of eval_unfiltered_base_*)."""
+    __slots__ = ("b", "idx")
+
+    def __init__(self, b, idx):
+        self.b, self.idx = b, idx
+
+    def _bin(self, op, other, swap=False):
+        other = other if isinstance(other, Expr) else self.b.constant(other)
+        x, y = (other, self) if swap else (self, other)
+        return self.b._push(op, x.idx, y.idx)
+
+    def __add__(self, o):
+        return self._bin(OP_ADD, o)
+
+    def __sub__(self, o):
+        return self._bin(OP_SUB, o)
+
+    def __rsub__(self, o):
+        return self._bin(OP_SUB, o, swap=True)
+
+    def __mul__(self, o):
+        return self._bin(OP_MUL, o)
+
+    __radd__, __rmul__ = __add__, __mul__
+
+
+class VanishingBuilder:
+    """Records values in SSA form (common subexpressions shared), then compiles them to the register program of
+    include/plonky2_b200.h (dead values dropped, registers reused after a value's last use)."""
+
+    def __init__(self, num_bound):
+        self.instrs = []
+        self.consts = [None] * num_bound     # consts[0:num_bound] are bound at evaluation time
+        self.num_bound = num_bound
+        self._const_index = {}
+        self._cache = {}
+        self.terms = {}                      # term number -> value index
+        self.term_order = None               # evaluation order of the terms (default: by number)
+
+    def _push(self, op, a=0, b=0):
+        if op in (OP_ADD, OP_MUL) and a > b:
+            a, b = b, a                      # commutative: one cache entry
+        key = (op, a, b)
+        e = self._cache.get(key)
+        if e is None:
+            self.instrs.append(key)
+            e = self._cache[key] = Expr(self, len(self.instrs) - 1)
+        return e
+
+    def local(self, commitment, column):
+        return self._push(OP_LOCAL, commitment, column)
+
+    def next(self, commitment, column):
+        return self._push(OP_NEXT, commitment, column)
+
+    def bound(self, k):
+        assert 0 <= k < self.num_bound
+        return self._push(OP_CONST, k)
+
+    def constant(self, v):
+        v = int(v) % F.ORDER
+        k = self._const_index.get(v)
+        if k is None:
+            k = self._const_index[v] = len(self.consts)
+            self.consts.append(v)
+        return self._push(OP_CONST, k)
+
+    def x(self):
+        return self._push(OP_X)
+
+    def l0(self):
+        return self._push(OP_L0)
+
+    def term(self, number, e):
+        assert number not in self.terms
+        self.terms[number] = e.idx
+
+    def product(self, es):
+        """Iterator::product over field values (empty product = ONE)."""
+        acc = None
+        for e in es:
+            acc = e if acc is None else acc * e
+        return acc if acc is not None else self.constant(1)
+
+    def compile(self):
+        """-> (VpInstr array, n_regs). Scheduling: the terms are taken in `term_order` and every value is emitted when a
+        term first needs it (depth first), so a product chain never has more than its running product and one factor
+        alive. Loads and constants are re-issued per term instead of being kept across terms (a register lives in
+        thread-local memory: keeping one costs what a coalesced load costs, and a small register set stays in L1);
+        arithmetic values, x and L_0(x) are shared. Registers are then assigned by a linear scan."""
+        ins = self.instrs
+        order = self.term_order if self.term_order is not None else sorted(self.terms)
+        assert sorted(order) == sorted(self.terms)
+        REMAT = (OP_LOCAL, OP_NEXT, OP_CONST)
+        seq = []                 # (op, a, b): operands are positions in seq for ADD/SUB/MUL/TERM
+        shared = {}              # SSA value -> position in seq
+
+        def emit(root, local):
+            def pos(v):
+                return local[v] if ins[v][0] in REMAT else shared[v]
+            stack = [(root, 0)]
+            while stack:
+                v, state = stack.pop()
+                op, a, b = ins[v]
+                if op in REMAT:
+                    if v not in local:
+                        local[v] = len(seq)
+                        seq.append((op, a, b))
+                elif v in shared:
+                    continue
+                elif op in (OP_X, OP_L0):
+                    shared[v] = len(seq)
+                    seq.append((op, 0, 0))
+                elif state == 0:
+                    stack += [(v, 1), (b, 0), (a, 0)]
+                else:
+                    shared[v] = len(seq)
+                    seq.append((op, pos(a), pos(b)))
+            return pos(root)
+
+        for number in order:
+            r = emit(self.terms[number], {})
+            seq.append((OP_TERM, r, number))
+        last_use = {}
+        for k, (op, a, b) in enumerate(seq):
+            if op in (OP_ADD, OP_SUB, OP_MUL):
+                last_use[a] = last_use[b] = k
+            elif op == OP_TERM:
+                last_use[a] = k
+        out, reg_of, free, n_regs = [], {}, [], 0
+        for k, (op, a, b) in enumerate(seq):
+            if op == OP_TERM:
+                out.append((OP_TERM, 0, reg_of[a], b))
+                if last_use[a] == k:
+                    heapq.heappush(free, reg_of[a])
+                continue
+            ra = rb = 0
+            if op in (OP_ADD, OP_SUB, OP_MUL):
+                ra, rb = reg_of[a], reg_of[b]
+                for v in {a, b}:
+                    if last_use[v] == k:
+                        heapq.heappush(free, reg_of[v])   # dst may reuse it: an instruction reads before it writes
+            if free:
+                dst = heapq.heappop(free)
+            else:
+                dst, n_regs = n_regs, n_regs + 1
+            reg_of[k] = dst
+            if op in (OP_ADD, OP_SUB, OP_MUL):
+                out.append((op, dst, ra, rb))
+            elif op == OP_CONST:
+                out.append((op, dst, a & 0xFFFF, a >> 16))
+            else:
+                out.append((op, dst, a, b))
+            assert k in last_use
+        if n_regs > MAX_REGS:
+            raise N.NativeError("vanishing program needs %d registers (max %d)" % (n_regs, MAX_REGS))
+        arr = (VpInstr * len(out))()
+        for i, (op, dst, a, b) in enumerate(out):
+            arr[i].op, arr[i].dst, arr[i].a, arr[i].b = op, dst, a, b
+        return arr, n_regs
+
+
+# ------------------------------------------------------------------ gates
+class EvaluationVarsBase:
+    """EvaluationVarsBase (plonk/vars.rs:22-27,94-100): local_constants / local_wires / public_inputs_hash as lazily
+    recorded loads."""
+
+    def __init__(self, b, num_wires, num_constants, prefix=0):
+        self.b, self.num_wires, self.num_constants, self.prefix = b, num_wires, num_constants, prefix
+
+    def local_constant(self, i):
+        assert 0 <= self.prefix + i < self.num_constants
+        return self.b.local(CONSTANTS_SIGMAS, self.prefix + i)
+
+    def local_wire(self, i):
+        assert 0 <= i < self.num_wires
+        return self.b.local(WIRES, i)
+
+    def public_inputs_hash(self, i):
+        assert 0 <= i < 4
+        return self.b.bound(i)
+
+    def remove_prefix(self, n):
+        return EvaluationVarsBase(self.b, self.num_wires, self.num_constants, self.prefix + n)
+
+
+class Gate:
+    """Gate<F, D> (gates/gate.rs:30-300): id, num_wires, num_constants, degree, num_constraints, eval_unfiltered."""
+
+    def id(self):
+        raise NotImplementedError
+
+    def num_wires(self):
+        raise NotImplementedError
+
+    def num_constants(self):
+        raise NotImplementedError
+
+    def degree(self):
+        raise NotImplementedError
+
+    def num_constraints(self):
+        raise NotImplementedError
+
+    def eval_unfiltered(self, vars):
+        """-> list of num_constraints() Exprs (eval_unfiltered_base_one / _packed)."""
+        raise NotImplementedError
+
+
+class NoopGate(Gate):
+    """gates/noop.rs"""
+
+    def id(self):
+        return "NoopGate"
+
+    def num_wires(self):
+        return 0
+
+    def num_constants(self):
+        return 0
+
+    def degree(self):
+        return 0
+
+    def num_constraints(self):
+        return 0
+
+    def eval_unfiltered(self, vars):
+        return []
+
+
+class ConstantGate(Gate):
+    """gates/constant.rs:20-130: wire i must equal constant i."""
+
+    def __init__(self, num_consts):
+        self.num_consts = num_consts
+
+    def id(self):
+        return "ConstantGate { num_consts: %d }" % self.num_consts
+
+    def num_wires(self):
+        return self.num_consts
+
+    def num_constants(self):
+        return self.num_consts
+
+    def degree(self):
+        return 1
+
+    def num_constraints(self):
+        return self.num_consts
+
+    def eval_unfiltered(self, vars):
+        return [vars.local_constant(i) - vars.local_wire(i) for i in range(self.num_consts)]
+
+
+class PublicInputGate(Gate):
+    """gates/public_input.rs:22-114: wires 0..4 carry the hash of the public inputs."""
+
+    def id(self):
+        return "PublicInputGate"
+
+    def num_wires(self):
+        return 4
+
+    def num_constants(self):
+        return 0
+
+    def degree(self):
+        return 1
+
+    def num_constraints(self):
+        return 4
+
+    def eval_unfiltered(self, vars):
+        return [vars.local_wire(i) - vars.public_inputs_hash(i) for i in range(4)]
+
+
+class ArithmeticGate(Gate):
+    """gates/arithmetic_base.rs:28-186: num_ops operations output = const_0 * m0 * m1 + const_1 * addend on wires
+    (4i, 4i+1, 4i+2, 4i+3)."""
+
+    def __init__(self, num_ops):
+        self.num_ops = num_ops
+
+    @classmethod
+    def new_from_config(cls, config):
+        return cls(config.num_routed_wires // 4)
+
+    def id(self):
+        return "ArithmeticGate { num_ops: %d }" % self.num_ops
+
+    def num_wires(self):
+        return 4 * self.num_ops
+
+    def num_constants(self):
+        return 2
+
+    def degree(self):
+        return 3
+
+    def num_constraints(self):
+        return self.num_ops
+
+    def eval_unfiltered(self, vars):
+        const_0, const_1 = vars.local_constant(0), vars.local_constant(1)
+        out = []
+        for i in range(self.num_ops):
+            m0, m1 = vars.local_wire(4 * i), vars.local_wire(4 * i + 1)
+            addend, output = vars.local_wire(4 * i + 2), vars.local_wire(4 * i + 3)
+            computed_output = m0 * m1 * const_0 + addend * const_1
+            out.append(output - computed_output)
+        return out
+
+
+# ------------------------------------------------------------------ circuit data
+class SelectorsInfo:
+    """gates/selectors.rs:16-26"""
+
+    def __init__(self, selector_indices, groups):
+        self.selector_indices, self.groups = selector_indices, groups
+
+    def num_selectors(self):
+        return len(self.groups)
+
+
+def selector_polynomials(gates, instance_gate_indices, max_degree):
+    """selector_polynomials (gates/selectors.rs:114-194). gates: sorted gate list; instance_gate_indices[row] = index of
+    the row's gate in `gates`. -> (list of selector value columns, SelectorsInfo)."""
+    n, num_gates = len(instance_gate_indices), len(gates)
+    max_gate_degree = gates[-1].degree()
+    idx = np.asarray(instance_gate_indices, dtype=np.uint64)
+    if max_gate_degree + num_gates - 1 <= max_degree:
+        return [idx.copy()], SelectorsInfo([0] * num_gates, [range(0, num_gates)])
+    if max_gate_degree >= max_degree:
+        raise ValueError("%s has too high degree. Consider increasing `quotient_degree_factor`." % gates[-1].id())
+    groups, start = [], 0
+    while start < num_gates:
+        size = 0
+        while start + size < num_gates and size + gates[start + size].degree() < max_degree:
+            size += 1
+        groups.append(range(start, start + size))
+        start += size
+    group_of = [next(j for j, r in enumerate(groups) if i in r) for i in range(num_gates)]
+    polys = []
+    for g in range(len(groups)):
+        col = np.full(n, UNUSED_SELECTOR, dtype=np.uint64)
+        for row, i in enumerate(instance_gate_indices):
+            if group_of[i] == g:
+                col[row] = i
+        polys.append(col)
+    return polys, SelectorsInfo(group_of, groups)
+
+
+def num_partial_products(n, max_degree):
+    """util/partial_products.rs:40-46"""
+    return -(-n // max_degree) - 1
+
+
+class CommonCircuitData:
+    """The fields of CommonCircuitData (plonk/circuit_data.rs:420-560) the quotient needs."""
+
+    def __init__(self, config, degree_bits, gates, selectors_info, num_constants, k_is):
+        self.config, self.degree_bits, self.gates, self.selectors_info = config, degree_bits, gates, selectors_info
+        self.quotient_degree_factor = config.max_quotient_degree_factor       # circuit_builder.rs:1146
+        self.num_gate_constraints = max([g.num_constraints() for g in gates] + [0])   # circuit_builder.rs:1236-1240
+        self.num_constants = num_constants
+        self.k_is = [int(k) for k in k_is]
+        self.num_partial_products = num_partial_products(config.num_routed_wires, self.quotient_degree_factor)
+        self._program = None
+
+    @classmethod
+    def from_gate_instances(cls, config, instances):
+        """The part of CircuitBuilder::build (plonk/circuit_builder.rs:1146-1171) that fixes the constants commitment:
+        instances = [(gate, constants)] per row (already padded to a power of two). Gates are sorted by (degree, id);
+        returns (common_data, constant_vecs) with constant_vecs = selector columns then the constant columns."""
+        n = len(instances)
+        degree_bits = F.log2_strict(n)
+        by_id = {}
+        for g, _ in instances:
+            by_id.setdefault(g.id(), g)
+        gates = sorted(by_id.values(), key=lambda g: (g.degree(), g.id()))
+        index = {g.id(): i for i, g in enumerate(gates)}
+        rows = [index[g.id()] for g, _ in instances]
+        constant_vecs, info = selector_polynomials(gates, rows, config.max_quotient_degree_factor + 1)
+        max_constants = max(g.num_constants() for g in gates)          # constant_polys, circuit_builder.rs:970-991
+        for k in range(max_constants):
+            constant_vecs.append(np.array([int(c[k]) % F.ORDER if k < len(c) else 0 for _, c in instances], dtype=np.uint64))
+        k_is = get_unique_coset_shifts(config.num_routed_wires)
+        return cls(config, degree_bits, gates, info, len(constant_vecs), k_is), constant_vecs
+
+    def quotient_degree(self):
+        return self.quotient_degree_factor << self.degree_bits
+
+    def constants_range(self):
+        return range(0, self.num_constants)
+
+    def sigmas_range(self):
+        return range(self.num_constants, self.num_constants + self.config.num_routed_wires)
+
+    def zs_range(self):
+        return range(0, self.config.num_challenges)
+
+    def partial_products_range(self):
+        return range(self.config.num_challenges, (self.num_partial_products + 1) * self.config.num_challenges)
+
+    def num_vanishing_terms(self):
+        nc = self.config.num_challenges
+        return nc + nc * (self.num_partial_products + 1) + self.num_gate_constraints
+
+    def vanishing_program(self):
+        if self._program is None:
+            self._program = vanishing_program(self)
+        return self._program
+
+
+def get_unique_coset_shifts(num_shifts):
+    """get_unique_coset_shifts (field/src/cosets.rs:9-24): g^0 .. g^(num_shifts-1)."""
+    out, x = [], 1
+    for _ in range(num_shifts):
+        out.append(x)
+        x = x * F.MULTIPLICATIVE_GROUP_GENERATOR % F.ORDER
+    return out
+
+
+def compute_filter(b, row, group_range, s, many_selector):
+    """compute_filter (gates/gate.rs:326-333)."""
+    idx = [i for i in group_range if i != row] + ([UNUSED_SELECTOR] if many_selector else [])
+    return b.product([b.constant(i) - s for i in idx]) if idx else None
+
+
+def vanishing_program(cd):
+    """eval_vanishing_poly_base_batch (plonk/vanishing_poly.rs:167-340) recorded for one point. Bound constants:
+    public_inputs_hash (4), betas (num_challenges), gammas (num_challenges). Term numbers follow the reference's order:
+    vanishing_z_1_terms, vanishing_partial_products_terms, gate constraint terms."""
+    cfg = cd.config
+    nc, nr = cfg.num_challenges, cfg.num_routed_wires
+    b = VanishingBuilder(4 + 2 * nc)
+    vars = EvaluationVarsBase(b, cfg.num_wires, cd.num_constants)
+    num_selectors = cd.selectors_info.num_selectors()
+    # evaluate_gate_constraints_base_batch (vanishing_poly.rs:702-728) with Gate::eval_filtered_base_batch (gate.rs:159-185)
+    constraint_terms = [None] * cd.num_gate_constraints
+    for i, gate in enumerate(cd.gates):
+        sel = cd.selectors_info.selector_indices[i]
+        filt = compute_filter(b, i, cd.selectors_info.groups[sel], vars.local_constant(sel), num_selectors > 1)
+        res = gate.eval_unfiltered(vars.remove_prefix(num_selectors))
+        assert len(res) <= cd.num_gate_constraints, "num_constraints() gave too low of a number"
+        for j, r in enumerate(res):
+            r = r if filt is None else r * filt
+            constraint_terms[j] = r if constraint_terms[j] is None else constraint_terms[j] + r
+    x, l_0_x = b.x(), b.l0()
+    num_prods, max_degree = cd.num_partial_products, cd.quotient_degree_factor
+    for i in range(nc):
+        beta, gamma = b.bound(4 + i), b.bound(4 + nc + i)
+        z_x, z_gx = b.local(ZS_PARTIAL_PRODUCTS, i), b.next(ZS_PARTIAL_PRODUCTS, i)
+        b.term(i, l_0_x * (z_x - 1))                                      # L_0(x) (Z(x) - 1)
+        numerators, denominators = [], []
+        for j in range(nr):
+            wire_value = vars.local_wire(j)
+            s_id = b.constant(cd.k_is[j]) * x
+            s_sigma = b.local(CONSTANTS_SIGMAS, cd.num_constants + j)
+            numerators.append(wire_value + beta * s_id + gamma)
+            denominators.append(wire_value + beta * s_sigma + gamma)
+        # check_partial_products (util/partial_products.rs:52-76)
+        accs = [z_x] + [b.local(ZS_PARTIAL_PRODUCTS, nc + i * num_prods + k) for k in range(num_prods)] + [z_gx]
+        for k in range(num_prods + 1):
+            num = b.product(numerators[k * max_degree:(k + 1) * max_degree])
+            den = b.product(denominators[k * max_degree:(k + 1) * max_degree])
+            b.term(nc + i * (num_prods + 1) + k, accs[k] * num - accs[k + 1] * den)
+    base = nc + nc * (num_prods + 1)
+    for j, t in enumerate(constraint_terms):
+        if t is not None:
+            b.term(base + j, t)
+    # evaluation order: the challenges' checks of one wire chunk next to each other (they share the chunk's k_i x)
+    b.term_order = (list(range(nc)) + [nc + i * (num_prods + 1) + k for k in range(num_prods + 1) for i in range(nc)]
+                    + [base + j for j, t in enumerate(constraint_terms) if t is not None])
+    return b
+
+
+def compute_quotient_polys(common_data, constants_sigmas_commitment, public_inputs_hash, wires_commitment,
+                           zs_partial_products_commitment, betas, gammas, alphas):
+    """compute_quotient_polys (plonk/prover.rs:609-815) on the device: a torch int64 CUDA tensor (num_challenges, size) of
+    quotient-polynomial coefficients, size = n << log2_ceil(quotient_degree_factor). The three PolynomialBatch handles
+    stay where they are; nothing but the program and the challenges crosses PCIe."""
+    import torch
+
+    cfg = common_data.config
+    nc = cfg.num_challenges
+    if not (len(betas) == len(gammas) == len(alphas) == nc) or len(public_inputs_hash) != 4:
+        raise N.ShapeError("expected %d betas, gammas, alphas and a 4-element public_inputs_hash" % nc)
+    commits = [constants_sigmas_commitment, wires_commitment, zs_partial_products_commitment]
+    expect = [common_data.num_constants + cfg.num_routed_wires, cfg.num_wires, nc * (1 + common_data.num_partial_products)]
+    for c, w in zip(commits, expect):
+        if c.num_polys != w or c.degree_log != common_data.degree_bits:
+            raise N.ShapeError("commitment with %d polynomials of degree 2^%d, expected %d of 2^%d"
+                               % (c.num_polys, c.degree_log, w, common_data.degree_bits))
+    b = common_data.vanishing_program()
+    prog, _ = b.compile()
+    bound = [int(v) % F.ORDER for v in list(public_inputs_hash) + list(betas) + list(gammas)]
+    consts = np.array(bound + b.consts[b.num_bound:], dtype=np.uint64)
+    al = np.array([int(a) % F.ORDER for a in alphas], dtype=np.uint64)
+    qdf = common_data.quotient_degree_factor
+    size = (1 << common_data.degree_bits) << (qdf - 1).bit_length()
+    ctx = wires_commitment.ctx
+    out = torch.empty((nc, size), dtype=torch.int64, device="cuda:%d" % ctx.device)
+    handles = (C.c_void_p * 3)(*[c.h for c in commits])
+    N.check(N.lib().gl_plonk_quotient(ctx.h, handles, 3, prog, len(prog), N.np_ptr(consts), len(consts), N.np_ptr(al), nc,
+                                      common_data.num_vanishing_terms(), qdf, N.vp(out.data_ptr())), ctx.h)
+    ctx.synchronize()
+    return out
+
+
+def commit_quotient_polys(common_data, quotient_polys, ctx=None):
+    """'split up quotient polys' + 'commit to quotient polys' (plonk/prover.rs:319-352): every polynomial is cut into
+    quotient_degree_factor chunks of n coefficients (trim_to_len(quotient_degree) was checked by the kernel call), all
+    chunks committed with from_coeffs -- straight from the device tensor compute_quotient_polys returned."""
+    ctx = ctx or N.default_context()
+    cfg = common_data.config
+    qdf, n = common_data.quotient_degree_factor, 1 << common_data.degree_bits
+    num = quotient_polys.shape[0]
+    B = num * qdf
+    L = N.lib()
+    h = N.vp()
+    N.check(L.gl_commit_begin(ctx.h, B, common_data.degree_bits, cfg.rate_bits, cfg.cap_height, 0, 0, 1, None, C.byref(h)), ctx.h)
+    try:
+        for j in range(num):
+            N.check(L.gl_commit_add_columns(h, j * qdf, qdf, N.vp(quotient_polys[j].data_ptr()), n, N.COLS_COEFFS,
+                                            N.MEM_DEVICE), ctx.h)
+        N.check(L.gl_commit_finish(h, None, N.MEM_DEVICE), ctx.h)
+        ctx.synchronize()
+    except Exception:
+        L.gl_commit_destroy(h)
+        raise
+    return PolynomialBatch(h, ctx, B, common_data.degree_bits, cfg.rate_bits, cfg.cap_height, False)

@@ -549,3 +549,46 @@ def verify_batch_fri_proof(caps, group_num_polys, degree_bits, instances, opened
     buf = (C.c_uint8 * len(proof)).from_buffer_copy(proof)
     return L.glo_verify_batch_fri_proof(cap_ptrs, gnp, len(caps), db.ctypes.data_as(u32p), insts, len(instances), ptr(ov),
                                         challenger.h, C.byref(params), buf, len(proof))
+
+
+class GloGate(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("param", C.c_uint32), ("selector_index", C.c_uint32),
+                ("group_start", C.c_uint32), ("group_end", C.c_uint32)]
+
+
+class GloCircuit(C.Structure):
+    _fields_ = [("num_wires", C.c_uint32), ("num_routed_wires", C.c_uint32), ("num_constants", C.c_uint32),
+                ("num_challenges", C.c_uint32), ("quotient_degree_factor", C.c_uint32), ("num_selectors", C.c_uint32),
+                ("num_partial_products", C.c_uint32), ("num_gate_constraints", C.c_uint32),
+                ("gates", C.POINTER(GloGate)), ("n_gates", C.c_size_t), ("k_is", u64p)]
+
+
+GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC = range(4)
+
+
+def plonk_quotient(circuit, constants_sigmas, wires, zs_partial_products, public_inputs_hash, betas, gammas, alphas):
+    """compute_quotient_polys of a plonky2 circuit. circuit: dict(num_wires, num_routed_wires, num_constants,
+    num_challenges, quotient_degree_factor, num_selectors, num_partial_products, num_gate_constraints, k_is,
+    gates=[(kind, param, selector_index, group_start, group_end)] in CommonCircuitData.gates order); the commitments
+    are oracle Commits. -> (num_challenges, n << log2_ceil(quotient_degree_factor)) coefficients."""
+    gates = (GloGate * len(circuit["gates"]))()
+    for i, g in enumerate(circuit["gates"]):
+        gates[i].kind, gates[i].param, gates[i].selector_index, gates[i].group_start, gates[i].group_end = g
+    k_is = np.array([int(k) for k in circuit["k_is"]], dtype=np.uint64)
+    cd = GloCircuit()
+    for f in ("num_wires", "num_routed_wires", "num_constants", "num_challenges", "quotient_degree_factor", "num_selectors",
+              "num_partial_products", "num_gate_constraints"):
+        setattr(cd, f, int(circuit[f]))
+    cd.gates, cd.n_gates, cd.k_is = gates, len(circuit["gates"]), ptr(k_is)
+    pih = np.array([int(x) for x in public_inputs_hash], dtype=np.uint64)
+    be, ga, al = (np.array([int(x) for x in v], dtype=np.uint64) for v in (betas, gammas, alphas))
+    qd_bits = (int(circuit["quotient_degree_factor"]) - 1).bit_length()
+    out = np.zeros((len(al), wires.n << qd_bits), dtype=np.uint64)
+    L = lib()
+    L.glo_plonk_quotient.restype = C.c_int
+    L.glo_plonk_quotient.argtypes = [C.POINTER(GloCircuit), C.c_void_p, C.c_void_p, C.c_void_p, u64p, u64p, u64p, u64p, u64p]
+    rc = L.glo_plonk_quotient(C.byref(cd), constants_sigmas.h, wires.h, zs_partial_products.h, ptr(pih), ptr(be), ptr(ga),
+                              ptr(al), ptr(out))
+    if rc != 0:
+        raise RuntimeError("oracle plonk quotient rc=%d" % rc)
+    return out

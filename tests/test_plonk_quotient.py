@@ -1,0 +1,284 @@
+"""plonky2's compute_quotient_polys.
+
+CPU (`-m "not gpu"`):
+  * the oracle's restatement is pinned by the verifier's own check (plonky2/src/plonk/verifier.rs:85-107):
+    vanishing_polys_zeta[i] == Z_H(zeta) * reduce_with_powers(quotient chunks at zeta, zeta^n), with the vanishing
+    polynomial evaluated at zeta by a third, plain-Python evaluation of eval_vanishing_poly (vanishing_poly.rs:29-164);
+    a witness that breaks a gate or a copy constraint must fail it;
+  * the product's vanishing PROGRAM (plonky2_b200/plonk.py) run by the kernel's own per-point source
+    (plonky2_b200/csrc/gl_vanishing.cuh compiled for the host) equals the oracle bit for bit.
+GPU (`-m gpu`): gl_plonk_quotient through the C ABI equals the oracle bit for bit, chained after the device-resident
+Z / partial-products commitment; the quotient commitment equals from_coeffs of the oracle's chunks."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import P, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P_ = int(P)
+
+# (num_wires, num_routed_wires, max_quotient_degree_factor, rate_bits, degree_bits)
+SHAPES = [
+    (12, 8, 4, 2, 4),     # two selector groups, partial-product chunks of 4
+    (13, 8, 3, 2, 4),     # quotient_degree_factor 3: coset of 4n points, the top n coefficients must vanish
+    (24, 16, 8, 3, 3),    # one selector for all gates (the standard config's situation), chunks of 8
+    (135, 80, 8, 3, 5),   # CircuitConfig::standard_recursion_config
+]
+
+
+def _plonk():
+    from plonky2_b200 import plonk   # importing the host layer does not need the CUDA library
+
+    return plonk
+
+
+def _circuit(shape, **kw):
+    import plonk_circuits as PC
+
+    plonk = _plonk()
+    nw, nr, qdf, rate_bits, degree_bits = shape
+    cfg = plonk.CircuitConfig(num_wires=nw, num_routed_wires=nr, max_quotient_degree_factor=qdf, rate_bits=rate_bits,
+                              cap_height=1)
+    return PC.FibonacciCircuit(plonk, cfg, degree_bits, seed=nw + qdf, **kw)
+
+
+def _challenges(seed, nc):
+    v = [int(x) for x in synth(seed, (3 * nc,))]
+    return v[:nc], v[nc:2 * nc], v[2 * nc:]
+
+
+def _oracle_commits(oracle, c, betas, gammas):
+    cfg = c.config
+    cs = oracle.Commit(c.constants_sigmas, cfg.rate_bits, cfg.cap_height)
+    w = oracle.Commit(c.wires, cfg.rate_bits, cfg.cap_height)
+    z = oracle.Commit(c.oracle_zs_partial_products(oracle, betas, gammas), cfg.rate_bits, cfg.cap_height)
+    return cs, w, z
+
+
+def _ev(coeffs, x):
+    acc = 0
+    for v in coeffs[::-1]:
+        acc = (acc * x + int(v)) % P_
+    return acc
+
+
+def _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas):
+    """eval_vanishing_poly (vanishing_poly.rs:29-164) at a base-field point, from the committed polynomials."""
+    import plonk_circuits as PC
+
+    cd, cfg = c.common, c.config
+    n = c.n
+    g = PC.root_of_unity(cd.degree_bits)
+    consts_sigmas = [_ev(p, zeta) for p in cs.coeffs]
+    wires = [_ev(p, zeta) for p in w.coeffs]
+    zs_pp = [_ev(p, zeta) for p in z.coeffs]
+    zs_pp_next = [_ev(p, zeta * g % P_) for p in z.coeffs]
+    nsel = cd.selectors_info.num_selectors()
+    circuit = c.oracle_circuit()
+    constraint_terms = [0] * cd.num_gate_constraints
+    for i, (kind, param, sel, g0, g1) in enumerate(circuit["gates"]):
+        s = consts_sigmas[sel]
+        filt = 1
+        for j in list(range(g0, g1)) + ([0xFFFFFFFF] if nsel > 1 else []):
+            if j != i:
+                filt = filt * (j - s) % P_
+        k = consts_sigmas[nsel:]
+        if kind == 1:
+            res = [k[t] - wires[t] for t in range(param)]
+        elif kind == 2:
+            res = [wires[t] - c.public_inputs_hash[t] for t in range(4)]
+        elif kind == 3:
+            res = [wires[4 * t + 3] - (wires[4 * t] * wires[4 * t + 1] * k[0] + wires[4 * t + 2] * k[1]) for t in range(param)]
+        else:
+            res = []
+        for t, r in enumerate(res):
+            constraint_terms[t] = (constraint_terms[t] + r * filt) % P_
+    zh = (pow(zeta, n, P_) - 1) % P_
+    l_0 = zh * pow(n * (zeta - 1) % P_, P_ - 2, P_) % P_     # eval_l_0(n, x), plonk_common.rs:69-79
+    nc, nr, qdf, nprod = cfg.num_challenges, cfg.num_routed_wires, cd.quotient_degree_factor, cd.num_partial_products
+    z1, pp = [], []
+    for i in range(nc):
+        z_x, z_gx = zs_pp[i], zs_pp_next[i]
+        z1.append(l_0 * (z_x - 1) % P_)
+        num = [(wires[j] + betas[i] * (cd.k_is[j] * zeta % P_) + gammas[i]) % P_ for j in range(nr)]
+        den = [(wires[j] + betas[i] * consts_sigmas[cd.num_constants + j] + gammas[i]) % P_ for j in range(nr)]
+        accs = [z_x] + zs_pp[nc + i * nprod: nc + (i + 1) * nprod] + [z_gx]
+        for k in range(nprod + 1):
+            a = b = 1
+            for j in range(k * qdf, min((k + 1) * qdf, nr)):
+                a, b = a * num[j] % P_, b * den[j] % P_
+            pp.append((accs[k] * a - accs[k + 1] * b) % P_)
+    terms = z1 + pp + constraint_terms
+    return [sum(pow(al, t, P_) * v for t, v in enumerate(terms)) % P_ for al in alphas], zh
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_oracle_quotient_passes_the_verifier_identity(oracle, shape):
+    c = _circuit(shape)
+    nc = c.config.num_challenges
+    betas, gammas, alphas = _challenges(0x510 + shape[0], nc)
+    cs, w, z = _oracle_commits(oracle, c, betas, gammas)
+    q = oracle.plonk_quotient(c.oracle_circuit(), cs, w, z, c.public_inputs_hash, betas, gammas, alphas)
+    qdf, n = c.common.quotient_degree_factor, c.n
+    assert q.shape == (nc, n << (qdf - 1).bit_length())
+    assert not q[:, qdf * n:].any()      # trim_to_len(quotient_degree) succeeds (prover.rs:327-331)
+    for zeta in (int(synth(0x520 + shape[0], (1,))[0]), 3):
+        want, zh = _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas)
+        for i in range(nc):
+            # reduce_with_powers(chunks at zeta, zeta^n) == the unsplit polynomial at zeta
+            chunks = [_ev(q[i, k * n:(k + 1) * n], zeta) for k in range(qdf)]
+            zn = pow(zeta, n, P_)
+            assert sum(ch * pow(zn, k, P_) for k, ch in enumerate(chunks)) % P_ == _ev(q[i], zeta)
+            assert want[i] == zh * _ev(q[i], zeta) % P_
+
+
+@pytest.mark.parametrize("broken", ["break_gate", "break_copy"])
+def test_oracle_quotient_of_a_bad_witness_fails_the_verifier_identity(oracle, broken):
+    for shape in SHAPES[:2]:
+        c = _circuit(shape, **{broken: True})
+        nc = c.config.num_challenges
+        betas, gammas, alphas = _challenges(0x530, nc)
+        cs, w, z = _oracle_commits(oracle, c, betas, gammas)
+        q = oracle.plonk_quotient(c.oracle_circuit(), cs, w, z, c.public_inputs_hash, betas, gammas, alphas)
+        zeta = int(synth(0x531, (1,))[0])
+        want, zh = _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas)
+        qdf, n = c.common.quotient_degree_factor, c.n
+        trimmed = [_ev(q[i, :qdf * n], zeta) for i in range(nc)]
+        assert any(want[i] != zh * trimmed[i] % P_ for i in range(nc))
+        if qdf & (qdf - 1):   # a trimmed region exists: "Quotient has failed" (prover.rs:327-331)
+            assert q[:, qdf * n:].any()
+
+
+def test_selector_groups_follow_the_reference_rule():
+    """selector_polynomials (gates/selectors.rs:114-194): one selector when max_gate_degree + num_gates - 1 <= max_degree,
+    else greedy groups with |G| + max degree in G <= max_degree; UNUSED_SELECTOR outside a row's group."""
+    plonk = _plonk()
+    c = _circuit(SHAPES[3])
+    info = c.common.selectors_info
+    assert [g.id() for g in c.common.gates] == ["NoopGate", "ConstantGate { num_consts: 2 }", "PublicInputGate",
+                                                "ArithmeticGate { num_ops: 20 }"]
+    assert info.num_selectors() == 1 and list(info.groups[0]) == [0, 1, 2, 3] and c.common.num_constants == 3
+    assert c.common.num_partial_products == 9 and c.common.num_gate_constraints == 20
+    c = _circuit(SHAPES[0])
+    info = c.common.selectors_info
+    assert [list(g) for g in info.groups] == [[0, 1, 2], [3]] and info.selector_indices == [0, 0, 0, 1]
+    s0, s1 = c.constant_vecs[0], c.constant_vecs[1]
+    assert s0[0] == 2 and s0[1] == 1 and s0[2] == plonk.UNUSED_SELECTOR and s1[2] == 3 and s1[0] == plonk.UNUSED_SELECTOR
+    assert s0[c.n - 1] == 0 and s1[c.n - 1] == plonk.UNUSED_SELECTOR     # NoopGate padding
+    with pytest.raises(ValueError, match="too high degree"):
+        _circuit((12, 8, 2, 1, 3))
+
+
+def _emu_lib():
+    out = "/tmp/libgl_vanishing_emu.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DGL_FORCE_32BIT_PATH", "-shared", "-fPIC", "-o", out,
+                           os.path.join(ROOT, "tests", "emu", "vanishing_emu.cpp")])
+    return C.CDLL(out)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_vanishing_program_through_the_kernel_source_on_host_matches_oracle(oracle, shape):
+    c = _circuit(shape)
+    cfg, cd = c.config, c.common
+    nc = cfg.num_challenges
+    betas, gammas, alphas = _challenges(0x540 + shape[0], nc)
+    cs, w, z = _oracle_commits(oracle, c, betas, gammas)
+    want = oracle.plonk_quotient(c.oracle_circuit(), cs, w, z, c.public_inputs_hash, betas, gammas, alphas)
+    b = cd.vanishing_program()
+    prog, n_regs = b.compile()
+    assert n_regs <= 64            # the schedule keeps the register set small (L1-resident on the device)
+    consts = np.array(list(c.public_inputs_hash) + betas + gammas + b.consts[b.num_bound:], dtype=np.uint64)
+    ldes = [np.ascontiguousarray(o.leaves.T) for o in (cs, w, z)]     # column-major LDE in leaf order, like the device
+    ptrs = (C.POINTER(C.c_uint64) * 3)(*[a.ctypes.data_as(C.POINTER(C.c_uint64)) for a in ldes])
+    strides = (C.c_size_t * 3)(*[a.shape[1] for a in ldes])
+    qd_bits = (cd.quotient_degree_factor - 1).bit_length()
+    size = c.n << qd_bits
+    vals = np.zeros((nc, size), dtype=np.uint64)
+    al = np.array(alphas, dtype=np.uint64)
+    L = _emu_lib()
+    L.emu_plonk_quotient_values.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                            C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    rc = L.emu_plonk_quotient_values(ptrs, strides, 3, cfg.rate_bits, cd.degree_bits, qd_bits, prog, len(prog),
+                                     consts.ctypes.data, al.ctypes.data, nc, cd.num_vanishing_terms(), vals.ctypes.data)
+    assert rc == 0
+    got = np.stack([oracle.coset_ifft(v, 14293326489335486720) for v in vals])   # .coset_ifft(F::coset_shift())
+    assert np.array_equal(got, want)
+
+
+# ----------------------------------------------------------------------------- GPU
+@pytest.fixture(scope="module")
+def pb():
+    import torch
+
+    if not torch.cuda.is_available():
+        if os.environ.get("GL_REQUIRE_GPU") == "1":
+            raise AssertionError("GPU tests need a CUDA device")
+        pytest.skip("no CUDA device (gpu-marked tests run on the B200 box)")
+    import plonky2_b200 as p
+
+    p.default_context()
+    return p
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[1], (135, 80, 8, 3, 7)])
+def test_plonk_quotient_on_device_matches_oracle(pb, oracle, shape):
+    """The prover's third phase without leaving the device (plonk/prover.rs:220-352): wires + constants_sigmas
+    commitments -> Z / partial products commitment (device) -> quotient polynomials (device, LDEs read in place) ->
+    quotient commitment; coefficients and cap bit for bit equal to the oracle's."""
+    import torch
+
+    from plonky2_b200 import plonk
+    from plonky2_b200.prover import commit_zs_partial_products
+
+    c = _circuit(shape)
+    cfg, cd = c.config, c.common
+    nc, nr = cfg.num_challenges, cfg.num_routed_wires
+    betas, gammas, alphas = _challenges(0x550 + shape[0], nc)
+    ocs, ow, oz = _oracle_commits(oracle, c, betas, gammas)
+    want = oracle.plonk_quotient(c.oracle_circuit(), ocs, ow, oz, c.public_inputs_hash, betas, gammas, alphas)
+    cs = pb.PolynomialBatch.from_values(c.constants_sigmas, cfg.rate_bits, False, cfg.cap_height)
+    w = pb.PolynomialBatch.from_values(c.wires, cfg.rate_bits, False, cfg.cap_height)
+    wires_dev = torch.from_numpy(c.wires[:nr].view(np.int64)).cuda()
+    sigmas_dev = torch.from_numpy(c.sigmas.view(np.int64)).cuda()
+    z = commit_zs_partial_products(wires_dev, sigmas_dev, cd.k_is, betas, gammas, cd.quotient_degree_factor, cfg.rate_bits,
+                                   cfg.cap_height)
+    assert np.array_equal(z.merkle_tree.cap.hashes, oz.cap)
+    q = plonk.compute_quotient_polys(cd, cs, c.public_inputs_hash, w, z, betas, gammas, alphas)
+    got = q.cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, want)
+    qc = plonk.commit_quotient_polys(cd, q)
+    qdf, n = cd.quotient_degree_factor, c.n
+    chunks = np.concatenate([want[i, :qdf * n].reshape(qdf, n) for i in range(nc)])   # quotient_poly.chunks(degree)
+    oq = oracle.Commit(chunks, cfg.rate_bits, cfg.cap_height, is_coeffs=True)
+    assert np.array_equal(qc.merkle_tree.cap.hashes, oq.cap)
+    for b in (cs, w, z, qc):
+        b.close()
+
+
+@pytest.mark.gpu
+def test_plonk_quotient_of_a_bad_witness_is_rejected(pb):
+    """quotient_degree_factor 3: the coset has 4n points and trim_to_len(3n) must find zeros; a broken gate leaves a
+    non-zero tail -> "Quotient has failed" (prover.rs:327-331)."""
+    import torch
+
+    from plonky2_b200 import NativeError, plonk
+    from plonky2_b200.prover import commit_zs_partial_products
+
+    c = _circuit(SHAPES[1], break_gate=True)
+    cfg, cd = c.config, c.common
+    betas, gammas, alphas = _challenges(0x560, cfg.num_challenges)
+    cs = pb.PolynomialBatch.from_values(c.constants_sigmas, cfg.rate_bits, False, cfg.cap_height)
+    w = pb.PolynomialBatch.from_values(c.wires, cfg.rate_bits, False, cfg.cap_height)
+    wires_dev = torch.from_numpy(c.wires[:cfg.num_routed_wires].view(np.int64)).cuda()
+    sigmas_dev = torch.from_numpy(c.sigmas.view(np.int64)).cuda()
+    z = commit_zs_partial_products(wires_dev, sigmas_dev, cd.k_is, betas, gammas, cd.quotient_degree_factor, cfg.rate_bits,
+                                   cfg.cap_height)
+    with pytest.raises((NativeError, ValueError), match="Quotient has failed"):
+        plonk.compute_quotient_polys(cd, cs, c.public_inputs_hash, w, z, betas, gammas, alphas)
+    for b in (cs, w, z):
+        b.close()
