@@ -246,6 +246,8 @@ int gl_stark_quotient(gl_ctx* ctx, gl_commit* trace, const gl_stark_instr* progr
 #define GL_VP_SUB 6
 #define GL_VP_MUL 7
 #define GL_VP_TERM 8  /* vanishing term number b = r[a] */
+#define GL_VP_ADDC 9  /* r[dst] = r[a] + consts[b] */
+#define GL_VP_MULC 10 /* r[dst] = r[a] * consts[b] */
 #define GL_VP_MAX_REGS 256
 #define GL_VP_MAX_COMMITS 4
 #define GL_VP_MAX_ALPHAS 4

@@ -1236,6 +1236,58 @@ static void gate_eval_unfiltered(const glo_gate& g, const u64* local_constants, 
             }
             break;
         }
+        case GLO_GATE_POSEIDON: {  // poseidon.rs:204-283 (wire layout :43-101), with the layers of hash/poseidon.rs
+            const int W = 12, HALF = GL_POSEIDON_HALF_FULL_ROUNDS, NP = GL_POSEIDON_PARTIAL_ROUNDS;
+            const int WIRE_SWAP = 2 * W, START_DELTA = 2 * W + 1, START_FULL_0 = START_DELTA + 4;
+            const int START_PARTIAL = START_FULL_0 + W * (HALF - 1), START_FULL_1 = START_PARTIAL + NP;
+            const u64 swap = local_wires[WIRE_SWAP];
+            res.push_back(fmul(swap, fsub(swap, 1)));
+            for (int i = 0; i < 4; i++)
+                res.push_back(fsub(fmul(swap, fsub(local_wires[i + 4], local_wires[i])), local_wires[START_DELTA + i]));
+            u64 state[12];
+            for (int i = 0; i < 4; i++) {
+                const u64 delta_i = local_wires[START_DELTA + i];
+                state[i] = fadd(local_wires[i], delta_i);
+                state[i + 4] = fsub(local_wires[i + 4], delta_i);
+            }
+            for (int i = 8; i < W; i++) state[i] = local_wires[i];
+            int round_ctr = 0;
+            for (int r = 0; r < HALF; r++) {
+                constant_layer(state, round_ctr);
+                if (r != 0)
+                    for (int i = 0; i < W; i++) {
+                        const u64 sbox_in = local_wires[START_FULL_0 + W * (r - 1) + i];
+                        res.push_back(fsub(state[i], sbox_in));
+                        state[i] = sbox_in;
+                    }
+                for (int i = 0; i < W; i++) state[i] = sbox(state[i]);
+                mds_layer(state);
+                round_ctr++;
+            }
+            for (int i = 0; i < W; i++) state[i] = fadd(state[i], GL_POSEIDON_FAST_FIRST_RC[i]);
+            mds_partial_layer_init(state);
+            for (int r = 0; r < NP; r++) {
+                const u64 sbox_in = local_wires[START_PARTIAL + r];
+                res.push_back(fsub(state[0], sbox_in));
+                state[0] = sbox(sbox_in);
+                if (r < NP - 1) state[0] = fadd(state[0], GL_POSEIDON_FAST_RC[r]);
+                mds_partial_layer_fast(state, r);
+            }
+            round_ctr += NP;
+            for (int r = 0; r < HALF; r++) {
+                constant_layer(state, round_ctr);
+                for (int i = 0; i < W; i++) {
+                    const u64 sbox_in = local_wires[START_FULL_1 + W * r + i];
+                    res.push_back(fsub(state[i], sbox_in));
+                    state[i] = sbox_in;
+                }
+                for (int i = 0; i < W; i++) state[i] = sbox(state[i]);
+                mds_layer(state);
+                round_ctr++;
+            }
+            for (int i = 0; i < W; i++) res.push_back(fsub(state[i], local_wires[W + i]));
+            break;
+        }
     }
 }
 

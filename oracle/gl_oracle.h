@@ -166,6 +166,7 @@ int glo_batch_prove_openings(const glo_batch_commit* const* oracles, size_t n_or
 #define GLO_GATE_CONSTANT 1     /* gates/constant.rs, param = num_consts */
 #define GLO_GATE_PUBLIC_INPUT 2 /* gates/public_input.rs */
 #define GLO_GATE_ARITHMETIC 3   /* gates/arithmetic_base.rs, param = num_ops */
+#define GLO_GATE_POSEIDON 4     /* gates/poseidon.rs */
 typedef struct {
     uint32_t kind, param;
     uint32_t selector_index;          /* SelectorsInfo.selector_indices[gate] (gates/selectors.rs:17-20) */

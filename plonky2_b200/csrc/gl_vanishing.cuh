@@ -80,6 +80,8 @@ GL_HD bool vp_eval_point(const VanishingParams& p, size_t j, uint64_t* regs) {
             case GL_VP_ADD: r = add(regs[in.a], regs[in.b]); break;
             case GL_VP_SUB: r = sub(regs[in.a], regs[in.b]); break;
             case GL_VP_MUL: r = mul(regs[in.a], regs[in.b]); break;
+            case GL_VP_ADDC: r = add(regs[in.a], p.consts[in.b]); break;
+            case GL_VP_MULC: r = mul(regs[in.a], p.consts[in.b]); break;
             default: {  // GL_VP_TERM: vanishing term number b
                 const uint64_t t = regs[in.a];
                 for (uint32_t a = 0; a < p.n_alphas; a++) acc[a] = add(acc[a], mul(t, p.apow[(size_t)a * p.n_terms + in.b]));

@@ -2005,6 +2005,7 @@ int gl_plonk_quotient(gl_ctx* ctx, gl_commit* const* commits, uint32_t n_commits
             case GL_VP_CONST: ok = ok && ((uint32_t)in.a | ((uint32_t)in.b << 16)) < n_consts; break;
             case GL_VP_X: case GL_VP_L0: break;
             case GL_VP_ADD: case GL_VP_SUB: case GL_VP_MUL: ok = ok && in.a < GL_VP_MAX_REGS && in.b < GL_VP_MAX_REGS; break;
+            case GL_VP_ADDC: case GL_VP_MULC: ok = ok && in.a < GL_VP_MAX_REGS && in.b < n_consts; break;
             case GL_VP_TERM: ok = in.a < GL_VP_MAX_REGS && in.b < n_terms; break;
             default: ok = false;
         }

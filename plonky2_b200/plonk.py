@@ -11,6 +11,8 @@ needs from `CircuitBuilder::build` (gate order, selector polynomials, constant c
 No lookups yet (has_lookup = false)."""
 import ctypes as C
 import heapq
+import os
+import re
 
 import numpy as np
 
@@ -18,7 +20,8 @@ from . import _native as N
 from . import field as F
 from .polynomial_batch import PolynomialBatch
 
-OP_LOCAL, OP_NEXT, OP_CONST, OP_X, OP_L0, OP_ADD, OP_SUB, OP_MUL, OP_TERM = range(9)
+OP_LOCAL, OP_NEXT, OP_CONST, OP_X, OP_L0, OP_ADD, OP_SUB, OP_MUL, OP_TERM, OP_ADDC, OP_MULC = range(11)
+_BINARY, _UNARY_CONST = (OP_ADD, OP_SUB, OP_MUL), (OP_ADDC, OP_MULC)
 MAX_REGS = 256
 UNUSED_SELECTOR = 0xFFFFFFFF   # gates/selectors.rs:14
 # commitment indices of the program's loads
@@ -48,7 +51,20 @@ class Expr:
         self.b, self.idx = b, idx
 
     def _bin(self, op, other, swap=False):
-        other = other if isinstance(other, Expr) else self.b.constant(other)
+        if isinstance(other, ConstRef):      # a bound or program constant: the immediate forms r + c, r * c
+            if op in (OP_MUL, OP_ADD):
+                return self.b._push(OP_MULC if op == OP_MUL else OP_ADDC, self.idx, other.k)
+            other = other.value()
+        elif not isinstance(other, Expr):    # a known field constant
+            c = int(other) % F.ORDER
+            if op == OP_MUL:
+                return self.b._push(OP_MULC, self.idx, self.b.const_index(c))
+            if op == OP_ADD:
+                return self.b._push(OP_ADDC, self.idx, self.b.const_index(c))
+            if not swap:                     # r - c
+                return self.b._push(OP_ADDC, self.idx, self.b.const_index(-c))
+            neg = self.b._push(OP_MULC, self.idx, self.b.const_index(-1))     # c - r
+            return self.b._push(OP_ADDC, neg.idx, self.b.const_index(c))
         x, y = (other, self) if swap else (self, other)
         return self.b._push(op, x.idx, y.idx)
 
@@ -63,6 +79,32 @@ class Expr:
 
     def __mul__(self, o):
         return self._bin(OP_MUL, o)
+
+    __radd__, __rmul__ = __add__, __mul__
+
+
+class ConstRef:
+    """Entry k of the program's constant table (a challenge, a public-input word, a literal): an operand of the
+    immediate forms; becomes a register value only when it has to."""
+    __slots__ = ("b", "k")
+
+    def __init__(self, b, k):
+        self.b, self.k = b, k
+
+    def value(self):
+        return self.b._push(OP_CONST, self.k)
+
+    def __add__(self, o):
+        return o + self if isinstance(o, Expr) else self.value() + o
+
+    def __mul__(self, o):
+        return o * self if isinstance(o, Expr) else self.value() * o
+
+    def __sub__(self, o):
+        return self.value() - o
+
+    def __rsub__(self, o):
+        return o - self.value()
 
     __radd__, __rmul__ = __add__, __mul__
 
@@ -98,15 +140,19 @@ class VanishingBuilder:
 
     def bound(self, k):
         assert 0 <= k < self.num_bound
-        return self._push(OP_CONST, k)
+        return ConstRef(self, k)
 
-    def constant(self, v):
+    def const_index(self, v):
         v = int(v) % F.ORDER
         k = self._const_index.get(v)
         if k is None:
             k = self._const_index[v] = len(self.consts)
             self.consts.append(v)
-        return self._push(OP_CONST, k)
+            assert k < 65536
+        return k
+
+    def constant(self, v):
+        return ConstRef(self, self.const_index(v))
 
     def x(self):
         return self._push(OP_X)
@@ -116,14 +162,14 @@ class VanishingBuilder:
 
     def term(self, number, e):
         assert number not in self.terms
-        self.terms[number] = e.idx
+        self.terms[number] = (e.value() if isinstance(e, ConstRef) else e).idx
 
     def product(self, es):
         """Iterator::product over field values (empty product = ONE)."""
         acc = None
         for e in es:
             acc = e if acc is None else acc * e
-        return acc if acc is not None else self.constant(1)
+        return acc if acc is not None else self.constant(1).value()
 
     def compile(self):
         """-> (VpInstr array, n_regs). Scheduling: the terms are taken in `term_order` and every value is emitted when a
@@ -155,10 +201,10 @@ class VanishingBuilder:
                     shared[v] = len(seq)
                     seq.append((op, 0, 0))
                 elif state == 0:
-                    stack += [(v, 1), (b, 0), (a, 0)]
+                    stack += [(v, 1), (b, 0), (a, 0)] if op in _BINARY else [(v, 1), (a, 0)]
                 else:
                     shared[v] = len(seq)
-                    seq.append((op, pos(a), pos(b)))
+                    seq.append((op, pos(a), pos(b) if op in _BINARY else b))
             return pos(root)
 
         for number in order:
@@ -166,9 +212,9 @@ class VanishingBuilder:
             seq.append((OP_TERM, r, number))
         last_use = {}
         for k, (op, a, b) in enumerate(seq):
-            if op in (OP_ADD, OP_SUB, OP_MUL):
+            if op in _BINARY:
                 last_use[a] = last_use[b] = k
-            elif op == OP_TERM:
+            elif op == OP_TERM or op in _UNARY_CONST:
                 last_use[a] = k
         out, reg_of, free, n_regs = [], {}, [], 0
         for k, (op, a, b) in enumerate(seq):
@@ -178,9 +224,9 @@ class VanishingBuilder:
                     heapq.heappush(free, reg_of[a])
                 continue
             ra = rb = 0
-            if op in (OP_ADD, OP_SUB, OP_MUL):
-                ra, rb = reg_of[a], reg_of[b]
-                for v in {a, b}:
+            if op in _BINARY or op in _UNARY_CONST:
+                ra, rb = reg_of[a], (reg_of[b] if op in _BINARY else b)
+                for v in ({a, b} if op in _BINARY else {a}):
                     if last_use[v] == k:
                         heapq.heappush(free, reg_of[v])   # dst may reuse it: an instruction reads before it writes
             if free:
@@ -188,7 +234,7 @@ class VanishingBuilder:
             else:
                 dst, n_regs = n_regs, n_regs + 1
             reg_of[k] = dst
-            if op in (OP_ADD, OP_SUB, OP_MUL):
+            if op in _BINARY or op in _UNARY_CONST:
                 out.append((op, dst, ra, rb))
             elif op == OP_CONST:
                 out.append((op, dst, a & 0xFFFF, a >> 16))
@@ -356,6 +402,172 @@ class ArithmeticGate(Gate):
         return out
 
 
+_POSEIDON = None
+
+
+def poseidon_tables():
+    """The Poseidon-12 parameter tables (plonky2/src/hash/poseidon.rs:59-157, poseidon_goldilocks.rs:24-215), read from
+    the same generated header the kernels compile (csrc/gl_poseidon_constants.h)."""
+    global _POSEIDON
+    if _POSEIDON is None:
+        text = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "gl_poseidon_constants.h")).read()
+        tabs = {}
+        for name, count, body in re.findall(r"GL_POSEIDON_(\w+)\[(\d+)\]\s*=\s*\{([^}]*)\}", text):
+            vals = [int(v, 16) for v in re.findall(r"0x([0-9a-fA-F]+)", body)]
+            assert len(vals) == int(count), name
+            tabs[name] = vals
+        assert len(tabs["RC"]) == 360 and len(tabs["FAST_VS"]) == 242 and len(tabs["FAST_INIT_MATRIX"]) == 121
+        _POSEIDON = tabs
+    return _POSEIDON
+
+
+SPONGE_WIDTH, HALF_N_FULL_ROUNDS, N_PARTIAL_ROUNDS = 12, 4, 22
+
+
+class PoseidonGate(Gate):
+    """gates/poseidon.rs:28-420: one Poseidon permutation of 12 wires with the swap flag for Merkle proofs; the S-box
+    inputs of every round but the first are wires, so that each constraint has degree 7."""
+    WIRE_SWAP = 2 * SPONGE_WIDTH
+    START_DELTA = 2 * SPONGE_WIDTH + 1
+    START_FULL_0 = START_DELTA + 4
+    START_PARTIAL = START_FULL_0 + SPONGE_WIDTH * (HALF_N_FULL_ROUNDS - 1)
+    START_FULL_1 = START_PARTIAL + N_PARTIAL_ROUNDS
+    END = START_FULL_1 + SPONGE_WIDTH * HALF_N_FULL_ROUNDS
+
+    @staticmethod
+    def wire_input(i):
+        return i
+
+    @staticmethod
+    def wire_output(i):
+        return SPONGE_WIDTH + i
+
+    @classmethod
+    def wire_delta(cls, i):
+        return cls.START_DELTA + i
+
+    @classmethod
+    def wire_full_sbox_0(cls, round, i):
+        assert 0 < round < HALF_N_FULL_ROUNDS
+        return cls.START_FULL_0 + SPONGE_WIDTH * (round - 1) + i
+
+    @classmethod
+    def wire_partial_sbox(cls, round):
+        return cls.START_PARTIAL + round
+
+    @classmethod
+    def wire_full_sbox_1(cls, round, i):
+        return cls.START_FULL_1 + SPONGE_WIDTH * round + i
+
+    def id(self):
+        return "PoseidonGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>"
+
+    def num_wires(self):
+        return self.END
+
+    def num_constants(self):
+        return 0
+
+    def degree(self):
+        return 7
+
+    def num_constraints(self):
+        return SPONGE_WIDTH * (2 * HALF_N_FULL_ROUNDS - 1) + N_PARTIAL_ROUNDS + SPONGE_WIDTH + 1 + 4
+
+    # the layers of hash/poseidon.rs over expression handles
+    @staticmethod
+    def _constant_layer(state, round_ctr):
+        rc = poseidon_tables()["RC"]
+        return [state[i] + rc[i + SPONGE_WIDTH * round_ctr] for i in range(SPONGE_WIDTH)]
+
+    @staticmethod
+    def _sbox_monomial(x):
+        x2 = x * x
+        x4 = x2 * x2
+        return x * x2 * x4
+
+    @staticmethod
+    def _mds_layer(state):
+        """mds_row_shf (poseidon.rs:180-200): result[r] = sum_i state[(i + r) % 12] * CIRC[i] + state[r] * DIAG[r]."""
+        t = poseidon_tables()
+        circ, diag = t["MDS_CIRC"], t["MDS_DIAG"]
+        out = []
+        for r in range(SPONGE_WIDTH):
+            acc = None
+            for i in range(SPONGE_WIDTH):
+                term = state[(i + r) % SPONGE_WIDTH] * (circ[i] + (diag[r] if i == 0 else 0))
+                acc = term if acc is None else acc + term
+            out.append(acc)
+        return out
+
+    @staticmethod
+    def _mds_partial_layer_init(state):
+        m = poseidon_tables()["FAST_INIT_MATRIX"]
+        out = [state[0]]
+        for c in range(1, SPONGE_WIDTH):
+            acc = None
+            for r in range(1, SPONGE_WIDTH):
+                term = state[r] * m[(r - 1) * 11 + (c - 1)]
+                acc = term if acc is None else acc + term
+            out.append(acc)
+        return out
+
+    @staticmethod
+    def _mds_partial_layer_fast(state, r):
+        t = poseidon_tables()
+        d = state[0] * (t["MDS_CIRC"][0] + t["MDS_DIAG"][0])
+        for i in range(1, SPONGE_WIDTH):
+            d = d + state[i] * t["FAST_W_HATS"][r * 11 + i - 1]
+        return [d] + [state[0] * t["FAST_VS"][r * 11 + i - 1] + state[i] for i in range(1, SPONGE_WIDTH)]
+
+    def eval_unfiltered(self, vars):
+        """eval_unfiltered_base_one (poseidon.rs:204-283)."""
+        t = poseidon_tables()
+        w = vars.local_wire
+        out = []
+        swap = w(self.WIRE_SWAP)
+        out.append(swap * (swap - 1))
+        for i in range(4):
+            out.append(swap * (w(self.wire_input(i + 4)) - w(self.wire_input(i))) - w(self.wire_delta(i)))
+        state = [None] * SPONGE_WIDTH
+        for i in range(4):
+            state[i] = w(self.wire_input(i)) + w(self.wire_delta(i))
+            state[i + 4] = w(self.wire_input(i + 4)) - w(self.wire_delta(i))
+        for i in range(8, SPONGE_WIDTH):
+            state[i] = w(self.wire_input(i))
+        round_ctr = 0
+        for r in range(HALF_N_FULL_ROUNDS):
+            state = self._constant_layer(state, round_ctr)
+            if r != 0:
+                for i in range(SPONGE_WIDTH):
+                    sbox_in = w(self.wire_full_sbox_0(r, i))
+                    out.append(state[i] - sbox_in)
+                    state[i] = sbox_in
+            state = self._mds_layer([self._sbox_monomial(x) for x in state])
+            round_ctr += 1
+        state = [state[i] + t["FAST_FIRST_RC"][i] for i in range(SPONGE_WIDTH)]
+        state = self._mds_partial_layer_init(state)
+        for r in range(N_PARTIAL_ROUNDS):
+            sbox_in = w(self.wire_partial_sbox(r))
+            out.append(state[0] - sbox_in)
+            state[0] = self._sbox_monomial(sbox_in)
+            if r < N_PARTIAL_ROUNDS - 1:
+                state[0] = state[0] + t["FAST_RC"][r]
+            state = self._mds_partial_layer_fast(state, r)
+        round_ctr += N_PARTIAL_ROUNDS
+        for r in range(HALF_N_FULL_ROUNDS):
+            state = self._constant_layer(state, round_ctr)
+            for i in range(SPONGE_WIDTH):
+                sbox_in = w(self.wire_full_sbox_1(r, i))
+                out.append(state[i] - sbox_in)
+                state[i] = sbox_in
+            state = self._mds_layer([self._sbox_monomial(x) for x in state])
+            round_ctr += 1
+        for i in range(SPONGE_WIDTH):
+            out.append(state[i] - w(self.wire_output(i)))
+        return out
+
+
 # ------------------------------------------------------------------ circuit data
 class SelectorsInfo:
     """gates/selectors.rs:16-26"""
@@ -469,7 +681,7 @@ def get_unique_coset_shifts(num_shifts):
 def compute_filter(b, row, group_range, s, many_selector):
     """compute_filter (gates/gate.rs:326-333)."""
     idx = [i for i in group_range if i != row] + ([UNUSED_SELECTOR] if many_selector else [])
-    return b.product([b.constant(i) - s for i in idx]) if idx else None
+    return b.product([i - s for i in idx]) if idx else None
 
 
 def vanishing_program(cd):
@@ -500,7 +712,7 @@ def vanishing_program(cd):
         numerators, denominators = [], []
         for j in range(nr):
             wire_value = vars.local_wire(j)
-            s_id = b.constant(cd.k_is[j]) * x
+            s_id = x * cd.k_is[j]
             s_sigma = b.local(CONSTANTS_SIGMAS, cd.num_constants + j)
             numerators.append(wire_value + beta * s_id + gamma)
             denominators.append(wire_value + beta * s_sigma + gamma)

@@ -563,7 +563,7 @@ class GloCircuit(C.Structure):
                 ("gates", C.POINTER(GloGate)), ("n_gates", C.c_size_t), ("k_is", u64p)]
 
 
-GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC = range(4)
+GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON = range(5)
 
 
 def plonk_quotient(circuit, constants_sigmas, wires, zs_partial_products, public_inputs_hash, betas, gammas, alphas):

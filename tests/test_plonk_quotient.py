@@ -25,8 +25,9 @@ P_ = int(P)
 SHAPES = [
     (12, 8, 4, 2, 4),     # two selector groups, partial-product chunks of 4
     (13, 8, 3, 2, 4),     # quotient_degree_factor 3: coset of 4n points, the top n coefficients must vanish
-    (24, 16, 8, 3, 3),    # one selector for all gates (the standard config's situation), chunks of 8
+    (24, 16, 8, 3, 3),    # one selector for all gates, chunks of 8
     (135, 80, 8, 3, 5),   # CircuitConfig::standard_recursion_config
+    (135, 80, 8, 3, 5, 9),  # ... with nine PoseidonGate rows (a hash chain): two selector groups, 123 gate constraints
 ]
 
 
@@ -40,10 +41,12 @@ def _circuit(shape, **kw):
     import plonk_circuits as PC
 
     plonk = _plonk()
-    nw, nr, qdf, rate_bits, degree_bits = shape
+    nw, nr, qdf, rate_bits, degree_bits = shape[:5]
+    if len(shape) > 5:
+        kw.setdefault("poseidon_rows", shape[5])
     cfg = plonk.CircuitConfig(num_wires=nw, num_routed_wires=nr, max_quotient_degree_factor=qdf, rate_bits=rate_bits,
                               cap_height=1)
-    return PC.FibonacciCircuit(plonk, cfg, degree_bits, seed=nw + qdf, **kw)
+    return PC.FibonacciCircuit(plonk, cfg, degree_bits, seed=nw + qdf + len(shape), **kw)
 
 
 def _challenges(seed, nc):
@@ -93,8 +96,11 @@ def _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas):
             res = [wires[t] - c.public_inputs_hash[t] for t in range(4)]
         elif kind == 3:
             res = [wires[4 * t + 3] - (wires[4 * t] * wires[4 * t + 1] * k[0] + wires[4 * t + 2] * k[1]) for t in range(param)]
-        else:
+        elif kind == 0:
             res = []
+        else:   # the product's own gate code, over numbers
+            pv = PC.PointVars(consts_sigmas, wires, c.public_inputs_hash).remove_prefix(nsel)
+            res = [int(v) for v in cd.gates[i].eval_unfiltered(pv)]
         for t, r in enumerate(res):
             constraint_terms[t] = (constraint_terms[t] + r * filt) % P_
     zh = (pow(zeta, n, P_) - 1) % P_
@@ -136,9 +142,21 @@ def test_oracle_quotient_passes_the_verifier_identity(oracle, shape):
             assert want[i] == zh * _ev(q[i], zeta) % P_
 
 
-@pytest.mark.parametrize("broken", ["break_gate", "break_copy"])
+def test_poseidon_gate_rows_hold_the_pinned_permutation(oracle):
+    """The PoseidonGate rows of the test circuit are true Poseidon traces: their output wires equal the KAT-pinned
+    permutation of the (swapped) inputs -- so the gate constraints that vanish on them are the reference's."""
+    c = _circuit(SHAPES[4])
+    assert len(c.poseidon_io) == 9
+    for inputs, swap, outputs in c.poseidon_io:
+        st = list(inputs)
+        if swap:
+            st[0:4], st[4:8] = st[4:8], st[0:4]
+        assert [int(v) for v in oracle.poseidon(np.array(st, dtype=np.uint64))] == outputs
+
+
+@pytest.mark.parametrize("broken", ["break_gate", "break_copy", "break_poseidon"])
 def test_oracle_quotient_of_a_bad_witness_fails_the_verifier_identity(oracle, broken):
-    for shape in SHAPES[:2]:
+    for shape in (SHAPES[4:5] if broken == "break_poseidon" else SHAPES[:2]):
         c = _circuit(shape, **{broken: True})
         nc = c.config.num_challenges
         betas, gammas, alphas = _challenges(0x530, nc)
@@ -225,7 +243,7 @@ def pb():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[1], (135, 80, 8, 3, 7)])
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[1], (135, 80, 8, 3, 7), (135, 80, 8, 3, 6, 20)])
 def test_plonk_quotient_on_device_matches_oracle(pb, oracle, shape):
     """The prover's third phase without leaving the device (plonk/prover.rs:220-352): wires + constants_sigmas
     commitments -> Z / partial products commitment (device) -> quotient polynomials (device, LDEs read in place) ->
