@@ -1236,6 +1236,58 @@ static void gate_eval_unfiltered(const glo_gate& g, const u64* local_constants, 
             }
             break;
         }
+        case GLO_GATE_ARITHMETIC_EXTENSION: {  // arithmetic_extension.rs:92-110
+            const u64 const_0 = local_constants[0], const_1 = local_constants[1];
+            auto ext = [&](size_t at) { return E2{local_wires[at], local_wires[at + 1]}; };
+            for (uint32_t i = 0; i < g.param; i++) {
+                const E2 multiplicand_0 = ext(8 * i), multiplicand_1 = ext(8 * i + 2), addend = ext(8 * i + 4), output = ext(8 * i + 6);
+                const E2 computed_output = eadd(escale(emul(multiplicand_0, multiplicand_1), const_0), escale(addend, const_1));
+                const E2 d = esub(output, computed_output);
+                res.push_back(d.a);
+                res.push_back(d.b);
+            }
+            break;
+        }
+        case GLO_GATE_MUL_EXTENSION: {  // multiplication_extension.rs:86-101
+            const u64 const_0 = local_constants[0];
+            auto ext = [&](size_t at) { return E2{local_wires[at], local_wires[at + 1]}; };
+            for (uint32_t i = 0; i < g.param; i++) {
+                const E2 d = esub(ext(6 * i + 4), escale(emul(ext(6 * i), ext(6 * i + 2)), const_0));
+                res.push_back(d.a);
+                res.push_back(d.b);
+            }
+            break;
+        }
+        case GLO_GATE_BASE_SUM: {  // base_sum.rs:153-170, BaseSumGate<B = param2> with param limbs
+            const u64 B = g.param2, sum = local_wires[0];
+            const u64* limbs = local_wires + 1;
+            u64 computed_sum = 0;  // reduce_with_powers(limbs, B), plonk_common.rs:128-135
+            for (size_t i = g.param; i-- > 0;) computed_sum = fadd(fmul(computed_sum, B), limbs[i]);
+            res.push_back(fsub(computed_sum, sum));
+            for (uint32_t l = 0; l < g.param; l++) {
+                u64 prod = 1;
+                for (u64 i = 0; i < B; i++) prod = fmul(prod, fsub(limbs[l], i));
+                res.push_back(prod);
+            }
+            break;
+        }
+        case GLO_GATE_REDUCING: case GLO_GATE_REDUCING_EXTENSION: {  // reducing.rs:107-127, reducing_extension.rs:109-128
+            const bool ext_coeffs = g.kind == GLO_GATE_REDUCING_EXTENSION;
+            const size_t num_coeffs = g.param, start_coeffs = 6;
+            const size_t start_accs = start_coeffs + num_coeffs * (ext_coeffs ? 2 : 1);
+            auto ext = [&](size_t at) { return E2{local_wires[at], local_wires[at + 1]}; };
+            const E2 alpha = ext(2), old_acc = ext(4);
+            E2 acc = old_acc;
+            for (size_t i = 0; i < num_coeffs; i++) {
+                const E2 coeff = ext_coeffs ? ext(start_coeffs + 2 * i) : e2(local_wires[start_coeffs + i]);
+                const E2 acc_i = ext(i == num_coeffs - 1 ? 0 : start_accs + 2 * i);  // the last accumulator is the output
+                const E2 d = esub(eadd(emul(acc, alpha), coeff), acc_i);
+                res.push_back(d.a);
+                res.push_back(d.b);
+                acc = acc_i;
+            }
+            break;
+        }
         case GLO_GATE_POSEIDON: {  // poseidon.rs:204-283 (wire layout :43-101), with the layers of hash/poseidon.rs
             const int W = 12, HALF = GL_POSEIDON_HALF_FULL_ROUNDS, NP = GL_POSEIDON_PARTIAL_ROUNDS;
             const int WIRE_SWAP = 2 * W, START_DELTA = 2 * W + 1, START_FULL_0 = START_DELTA + 4;

@@ -167,10 +167,16 @@ int glo_batch_prove_openings(const glo_batch_commit* const* oracles, size_t n_or
 #define GLO_GATE_PUBLIC_INPUT 2 /* gates/public_input.rs */
 #define GLO_GATE_ARITHMETIC 3   /* gates/arithmetic_base.rs, param = num_ops */
 #define GLO_GATE_POSEIDON 4     /* gates/poseidon.rs */
+#define GLO_GATE_ARITHMETIC_EXTENSION 5 /* gates/arithmetic_extension.rs, param = num_ops */
+#define GLO_GATE_MUL_EXTENSION 6        /* gates/multiplication_extension.rs, param = num_ops */
+#define GLO_GATE_BASE_SUM 7             /* gates/base_sum.rs, param = num_limbs, param2 = B */
+#define GLO_GATE_REDUCING 8             /* gates/reducing.rs, param = num_coeffs */
+#define GLO_GATE_REDUCING_EXTENSION 9   /* gates/reducing_extension.rs, param = num_coeffs */
 typedef struct {
     uint32_t kind, param;
     uint32_t selector_index;          /* SelectorsInfo.selector_indices[gate] (gates/selectors.rs:17-20) */
     uint32_t group_start, group_end;  /* SelectorsInfo.groups[selector_index] */
+    uint32_t param2;
 } glo_gate;
 typedef struct {
     uint32_t num_wires, num_routed_wires, num_constants /* selectors included */, num_challenges;

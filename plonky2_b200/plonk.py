@@ -121,14 +121,17 @@ class VanishingBuilder:
         self._cache = {}
         self.terms = {}                      # term number -> value index
         self.term_order = None               # evaluation order of the terms (default: by number)
+        self.scope = None
 
     def _push(self, op, a=0, b=0):
         if op in (OP_ADD, OP_MUL) and a > b:
             a, b = b, a                      # commutative: one cache entry
-        key = (op, a, b)
+        # arithmetic is shared within one scope (a gate, the permutation argument) only: an accidental match between
+        # two gates would keep a value alive from one gate's use to the other's
+        key = (op, a, b, self.scope if (op in _BINARY or op in _UNARY_CONST) else None)
         e = self._cache.get(key)
         if e is None:
-            self.instrs.append(key)
+            self.instrs.append((op, a, b))
             e = self._cache[key] = Expr(self, len(self.instrs) - 1)
         return e
 
@@ -183,6 +186,12 @@ class VanishingBuilder:
         REMAT = (OP_LOCAL, OP_NEXT, OP_CONST)
         seq = []                 # (op, a, b): operands are positions in seq for ADD/SUB/MUL/TERM
         shared = {}              # SSA value -> position in seq
+        height = [0] * len(ins)  # the deeper operand of an instruction is evaluated first (Sethi-Ullman): a leaf
+        for k, (op, a, b) in enumerate(ins):     # loaded before descending into a long chain would wait in a register
+            if op in _BINARY:
+                height[k] = 1 + max(height[a], height[b])
+            elif op in _UNARY_CONST:
+                height[k] = 1 + height[a]
 
         def emit(root, local):
             def pos(v):
@@ -201,7 +210,11 @@ class VanishingBuilder:
                     shared[v] = len(seq)
                     seq.append((op, 0, 0))
                 elif state == 0:
-                    stack += [(v, 1), (b, 0), (a, 0)] if op in _BINARY else [(v, 1), (a, 0)]
+                    if op in _BINARY:
+                        first, second = (a, b) if height[a] >= height[b] else (b, a)
+                        stack += [(v, 1), (second, 0), (first, 0)]
+                    else:
+                        stack += [(v, 1), (a, 0)]
                 else:
                     shared[v] = len(seq)
                     seq.append((op, pos(a), pos(b) if op in _BINARY else b))
@@ -400,6 +413,224 @@ class ArithmeticGate(Gate):
             computed_output = m0 * m1 * const_0 + addend * const_1
             out.append(output - computed_output)
         return out
+
+
+class Ext2:
+    """F_{p^2} = F_p[X]/(X^2 - 7) (field/src/extension/quadratic.rs:14-120) over any value type with + - * (expression
+    handles on the host program path, plain numbers in the tests): what vars.get_local_ext returns."""
+    __slots__ = ("a", "b")
+    W = 7
+
+    def __init__(self, a, b):
+        self.a, self.b = a, b
+
+    def __add__(self, o):
+        return Ext2(self.a + o.a, self.b + o.b) if isinstance(o, Ext2) else Ext2(self.a + o, self.b)
+
+    def __sub__(self, o):
+        return Ext2(self.a - o.a, self.b - o.b) if isinstance(o, Ext2) else Ext2(self.a - o, self.b)
+
+    def __mul__(self, o):
+        if isinstance(o, Ext2):
+            return Ext2(self.a * o.a + self.b * o.b * self.W, self.a * o.b + self.b * o.a)
+        return Ext2(self.a * o, self.b * o)          # scalar_mul
+
+    scalar_mul = __mul__
+
+    def to_basefield_array(self):
+        return [self.a, self.b]
+
+
+def get_local_ext(vars, start):
+    """EvaluationVarsBase::get_local_ext (plonk/vars.rs:101-110) for D = 2."""
+    return Ext2(vars.local_wire(start), vars.local_wire(start + 1))
+
+
+D = 2
+
+
+class ArithmeticExtensionGate(Gate):
+    """gates/arithmetic_extension.rs:24-170: num_ops operations output = const_0 * m0 * m1 + const_1 * addend in F_{p^2}."""
+
+    def __init__(self, num_ops):
+        self.num_ops = num_ops
+
+    @classmethod
+    def new_from_config(cls, config):
+        return cls(config.num_routed_wires // (4 * D))
+
+    def id(self):
+        return "ArithmeticExtensionGate { num_ops: %d }" % self.num_ops
+
+    def num_wires(self):
+        return self.num_ops * 4 * D
+
+    def num_constants(self):
+        return 2
+
+    def degree(self):
+        return 3
+
+    def num_constraints(self):
+        return self.num_ops * D
+
+    def eval_unfiltered(self, vars):
+        const_0, const_1 = vars.local_constant(0), vars.local_constant(1)
+        out = []
+        for i in range(self.num_ops):
+            m0, m1 = get_local_ext(vars, 4 * D * i), get_local_ext(vars, 4 * D * i + D)
+            addend, output = get_local_ext(vars, 4 * D * i + 2 * D), get_local_ext(vars, 4 * D * i + 3 * D)
+            computed_output = (m0 * m1).scalar_mul(const_0) + addend.scalar_mul(const_1)
+            out += (output - computed_output).to_basefield_array()
+        return out
+
+
+class MulExtensionGate(Gate):
+    """gates/multiplication_extension.rs:24-157: num_ops operations output = const_0 * m0 * m1 in F_{p^2}."""
+
+    def __init__(self, num_ops):
+        self.num_ops = num_ops
+
+    @classmethod
+    def new_from_config(cls, config):
+        return cls(config.num_routed_wires // (3 * D))
+
+    def id(self):
+        return "MulExtensionGate { num_ops: %d }" % self.num_ops
+
+    def num_wires(self):
+        return self.num_ops * 3 * D
+
+    def num_constants(self):
+        return 1
+
+    def degree(self):
+        return 3
+
+    def num_constraints(self):
+        return self.num_ops * D
+
+    def eval_unfiltered(self, vars):
+        const_0 = vars.local_constant(0)
+        out = []
+        for i in range(self.num_ops):
+            m0, m1 = get_local_ext(vars, 3 * D * i), get_local_ext(vars, 3 * D * i + D)
+            output = get_local_ext(vars, 3 * D * i + 2 * D)
+            out += (output - (m0 * m1).scalar_mul(const_0)).to_basefield_array()
+        return out
+
+
+class BaseSumGate(Gate):
+    """gates/base_sum.rs:27-171 (BaseSumGate<B>): wire 0 = sum of the limbs (wires 1..) in base B, little endian; every
+    limb range-checked by prod_{i<B} (limb - i)."""
+    WIRE_SUM, START_LIMBS = 0, 1
+
+    def __init__(self, num_limbs, base=2):
+        self.num_limbs, self.base = num_limbs, base
+
+    @classmethod
+    def new_from_config(cls, config, base=2):
+        log_floor, x = 0, F.ORDER - 1                       # log_floor(F::ORDER - 1, B)
+        while x >= base:
+            x //= base
+            log_floor += 1
+        return cls(min(log_floor, config.num_routed_wires - cls.START_LIMBS), base)
+
+    def id(self):
+        return "BaseSumGate { num_limbs: %d } + Base: %d" % (self.num_limbs, self.base)
+
+    def num_wires(self):
+        return 1 + self.num_limbs
+
+    def num_constants(self):
+        return 0
+
+    def degree(self):
+        return self.base
+
+    def num_constraints(self):
+        return 1 + self.num_limbs
+
+    def eval_unfiltered(self, vars):
+        total = vars.local_wire(self.WIRE_SUM)
+        limbs = [vars.local_wire(self.START_LIMBS + i) for i in range(self.num_limbs)]
+        computed = None                                     # reduce_with_powers(limbs, B): Horner from the top limb
+        for limb in reversed(limbs):
+            computed = limb if computed is None else computed * self.base + limb
+        out = [computed - total]
+        for limb in limbs:
+            acc = limb                                      # (limb - 0)
+            for i in range(1, self.base):
+                acc = acc * (limb - i)
+            out.append(acc)
+        return out
+
+
+class ReducingGate(Gate):
+    """gates/reducing.rs:25-185: acc_{i} = acc_{i-1} * alpha + coeff_i over F_{p^2} with base-field coefficients; the last
+    accumulator is the output (wires 0..D)."""
+
+    def __init__(self, num_coeffs):
+        self.num_coeffs = num_coeffs
+
+    @staticmethod
+    def max_coeffs_len(num_wires, num_routed_wires):
+        return min(num_routed_wires - 3 * D, (num_wires - 2 * D) // (D + 1))
+
+    START_COEFFS = 3 * D
+
+    def start_accs(self):
+        return self.START_COEFFS + self.num_coeffs
+
+    def wires_accs(self, i):
+        return 0 if i == self.num_coeffs - 1 else self.start_accs() + D * i
+
+    def id(self):
+        return "ReducingGate { num_coeffs: %d }" % self.num_coeffs
+
+    def num_wires(self):
+        return 2 * D + self.num_coeffs * (D + 1)
+
+    def num_constants(self):
+        return 0
+
+    def degree(self):
+        return 2
+
+    def num_constraints(self):
+        return D * self.num_coeffs
+
+    def coeff(self, vars, i):
+        return vars.local_wire(self.START_COEFFS + i)
+
+    def eval_unfiltered(self, vars):
+        alpha, acc = get_local_ext(vars, D), get_local_ext(vars, 2 * D)
+        out = []
+        for i in range(self.num_coeffs):
+            acc_i = get_local_ext(vars, self.wires_accs(i))
+            out += (acc * alpha + self.coeff(vars, i) - acc_i).to_basefield_array()
+            acc = acc_i
+        return out
+
+
+class ReducingExtensionGate(ReducingGate):
+    """gates/reducing_extension.rs:24-185: the same with coefficients in F_{p^2}."""
+
+    @staticmethod
+    def max_coeffs_len(num_wires, num_routed_wires):
+        return min((num_routed_wires - 3 * D) // D, (num_wires - 2 * D) // (D * 2))
+
+    def start_accs(self):
+        return self.START_COEFFS + self.num_coeffs * D
+
+    def id(self):
+        return "ReducingExtensionGate { num_coeffs: %d }" % self.num_coeffs
+
+    def num_wires(self):
+        return 2 * D + 2 * D * self.num_coeffs
+
+    def coeff(self, vars, i):
+        return get_local_ext(vars, self.START_COEFFS + i * D)
 
 
 _POSEIDON = None
@@ -696,6 +927,7 @@ def vanishing_program(cd):
     # evaluate_gate_constraints_base_batch (vanishing_poly.rs:702-728) with Gate::eval_filtered_base_batch (gate.rs:159-185)
     constraint_terms = [None] * cd.num_gate_constraints
     for i, gate in enumerate(cd.gates):
+        b.scope = ("gate", i)
         sel = cd.selectors_info.selector_indices[i]
         filt = compute_filter(b, i, cd.selectors_info.groups[sel], vars.local_constant(sel), num_selectors > 1)
         res = gate.eval_unfiltered(vars.remove_prefix(num_selectors))
@@ -703,6 +935,7 @@ def vanishing_program(cd):
         for j, r in enumerate(res):
             r = r if filt is None else r * filt
             constraint_terms[j] = r if constraint_terms[j] is None else constraint_terms[j] + r
+    b.scope = "permutation"
     x, l_0_x = b.x(), b.l0()
     num_prods, max_degree = cd.num_partial_products, cd.quotient_degree_factor
     for i in range(nc):

@@ -553,7 +553,7 @@ def verify_batch_fri_proof(caps, group_num_polys, degree_bits, instances, opened
 
 class GloGate(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("param", C.c_uint32), ("selector_index", C.c_uint32),
-                ("group_start", C.c_uint32), ("group_end", C.c_uint32)]
+                ("group_start", C.c_uint32), ("group_end", C.c_uint32), ("param2", C.c_uint32)]
 
 
 class GloCircuit(C.Structure):
@@ -563,7 +563,8 @@ class GloCircuit(C.Structure):
                 ("gates", C.POINTER(GloGate)), ("n_gates", C.c_size_t), ("k_is", u64p)]
 
 
-GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON = range(5)
+(GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON, GATE_ARITHMETIC_EXTENSION, GATE_MUL_EXTENSION,
+ GATE_BASE_SUM, GATE_REDUCING, GATE_REDUCING_EXTENSION) = range(10)
 
 
 def plonk_quotient(circuit, constants_sigmas, wires, zs_partial_products, public_inputs_hash, betas, gammas, alphas):
@@ -573,7 +574,8 @@ def plonk_quotient(circuit, constants_sigmas, wires, zs_partial_products, public
     are oracle Commits. -> (num_challenges, n << log2_ceil(quotient_degree_factor)) coefficients."""
     gates = (GloGate * len(circuit["gates"]))()
     for i, g in enumerate(circuit["gates"]):
-        gates[i].kind, gates[i].param, gates[i].selector_index, gates[i].group_start, gates[i].group_end = g
+        gates[i].kind, gates[i].param, gates[i].selector_index, gates[i].group_start, gates[i].group_end = g[:5]
+        gates[i].param2 = g[5] if len(g) > 5 else 0
     k_is = np.array([int(k) for k in circuit["k_is"]], dtype=np.uint64)
     cd = GloCircuit()
     for f in ("num_wires", "num_routed_wires", "num_constants", "num_challenges", "quotient_degree_factor", "num_selectors",

@@ -4,7 +4,7 @@ instances, a witness that satisfies every gate, copy constraints and the sigma p
 parity test of the plonky2 quotient."""
 import numpy as np
 
-from oracle_lib import GATE_ARITHMETIC, GATE_CONSTANT, GATE_NOOP, GATE_POSEIDON, GATE_PUBLIC_INPUT
+import oracle_lib as OL
 
 P = 0xFFFFFFFF00000001
 G = 14293326489335486720   # MULTIPLICATIVE_GROUP_GENERATOR
@@ -109,24 +109,99 @@ def poseidon_gate_witness(plonk, inputs, swap):
     return wires
 
 
+def _ext(rng):
+    return [int(v) for v in rnd(rng, 2)]
+
+
+def _emul(plonk, x, y):
+    r = plonk.Ext2(Fp(x[0]), Fp(x[1])) * plonk.Ext2(Fp(y[0]), Fp(y[1]))
+    return [int(r.a), int(r.b)]
+
+
+def extra_gate_row(plonk, config, name, rng):
+    """(gate, constants, {wire: value}) of one row holding a satisfied instance of the named gate, the way the gate's
+    generator fills it (gates/<gate>.rs: *Generator::run_once)."""
+    wires = {}
+    if name in ("ArithmeticExtensionGate", "MulExtensionGate"):
+        arith = name == "ArithmeticExtensionGate"
+        gate = getattr(plonk, name).new_from_config(config)
+        consts = [int(v) for v in rnd(rng, 2 if arith else 1)]
+        stride = 8 if arith else 6
+        for i in range(gate.num_ops):
+            m0, m1, addend = _ext(rng), _ext(rng), _ext(rng)
+            prod = _emul(plonk, m0, m1)
+            out = [(prod[k] * consts[0] + (addend[k] * consts[1] if arith else 0)) % P for k in range(2)]
+            vals = m0 + m1 + (addend if arith else []) + out
+            for k, v in enumerate(vals):
+                wires[stride * i + k] = v
+        return gate, consts, wires
+    if name == "BaseSumGate":
+        gate = plonk.BaseSumGate.new_from_config(config, 2)
+        limbs = [int(v) & 1 for v in rnd(rng, gate.num_limbs)]
+        wires[0] = sum(b << i for i, b in enumerate(limbs)) % P
+        for i, b in enumerate(limbs):
+            wires[1 + i] = b
+        return gate, [], wires
+    if name == "BaseSumGate4":
+        gate = plonk.BaseSumGate(31, 4)
+        limbs = [int(v) & 3 for v in rnd(rng, gate.num_limbs)]
+        wires[0] = sum(b * 4 ** i for i, b in enumerate(limbs)) % P
+        for i, b in enumerate(limbs):
+            wires[1 + i] = b
+        return gate, [], wires
+    if name in ("ReducingGate", "ReducingExtensionGate"):
+        cls = getattr(plonk, name)
+        gate = cls(cls.max_coeffs_len(config.num_wires, config.num_routed_wires))
+        ext = name == "ReducingExtensionGate"
+        alpha, acc = _ext(rng), _ext(rng)
+        wires[2], wires[3], wires[4], wires[5] = alpha + acc
+        for i in range(gate.num_coeffs):
+            coeff = _ext(rng) if ext else [int(rnd(rng)), 0]
+            if ext:
+                wires[6 + 2 * i], wires[7 + 2 * i] = coeff
+            else:
+                wires[6 + i] = coeff[0]
+            prod = _emul(plonk, acc, alpha)
+            acc = [(prod[0] + coeff[0]) % P, (prod[1] + coeff[1]) % P]
+            at = gate.wires_accs(i)
+            wires[at], wires[at + 1] = acc
+        return gate, [], wires
+    raise KeyError(name)
+
+
+def oracle_gate_kind(g):
+    """(kind, param, param2) of tests/oracle_lib.plonk_quotient for a product gate object."""
+    name = type(g).__name__
+    return {"NoopGate": (OL.GATE_NOOP, 0, 0), "ConstantGate": (OL.GATE_CONSTANT, getattr(g, "num_consts", 0), 0),
+            "PublicInputGate": (OL.GATE_PUBLIC_INPUT, 0, 0), "ArithmeticGate": (OL.GATE_ARITHMETIC, getattr(g, "num_ops", 0), 0),
+            "PoseidonGate": (OL.GATE_POSEIDON, 0, 0),
+            "ArithmeticExtensionGate": (OL.GATE_ARITHMETIC_EXTENSION, getattr(g, "num_ops", 0), 0),
+            "MulExtensionGate": (OL.GATE_MUL_EXTENSION, getattr(g, "num_ops", 0), 0),
+            "BaseSumGate": (OL.GATE_BASE_SUM, getattr(g, "num_limbs", 0), getattr(g, "base", 0)),
+            "ReducingGate": (OL.GATE_REDUCING, getattr(g, "num_coeffs", 0), 0),
+            "ReducingExtensionGate": (OL.GATE_REDUCING_EXTENSION, getattr(g, "num_coeffs", 0), 0)}[name]
+
+
 class FibonacciCircuit:
     """Row 0: PublicInputGate; row 1: ConstantGate(2) holding (F_0, 1); then ArithmeticGate rows whose operations compute
     out = m0 * m1 + addend with m0 = previous out, m1 = the constant 1, addend = the out before that (copy
     constraints); NoopGate rows pad to 2^degree_bits. Unconstrained wires carry random values."""
 
     def __init__(self, plonk, config, degree_bits, seed=1, arithmetic_rows=None, break_gate=False, break_copy=False,
-                 poseidon_rows=0, break_poseidon=False):
+                 poseidon_rows=0, break_poseidon=False, extra=(), break_extra=None):
         rng = np.random.default_rng(seed)
         n = 1 << degree_bits
         self.config, self.n = config, n
         arith = plonk.ArithmeticGate.new_from_config(config)
         num_ops = arith.num_ops
-        arithmetic_rows = arithmetic_rows if arithmetic_rows is not None else n - 5 - poseidon_rows
-        assert 2 + arithmetic_rows + poseidon_rows <= n
+        arithmetic_rows = arithmetic_rows if arithmetic_rows is not None else n - 5 - poseidon_rows - len(extra)
+        assert 2 + arithmetic_rows + poseidon_rows + len(extra) <= n
+        extra_rows = [extra_gate_row(plonk, config, name, rng) for name in extra]
         f0 = int(rnd(rng))
         instances = [(plonk.PublicInputGate(), []), (plonk.ConstantGate(2), [f0, 1])]
         instances += [(arith, [1, 1])] * arithmetic_rows
         instances += [(plonk.PoseidonGate(), [])] * poseidon_rows
+        instances += [(g, consts) for g, consts, _ in extra_rows]
         instances += [(plonk.NoopGate(), [])] * (n - len(instances))
         self.common, self.constant_vecs = plonk.CommonCircuitData.from_gate_instances(config, instances)
         self.public_inputs_hash = [int(v) for v in rnd(rng, 4)]
@@ -166,6 +241,13 @@ class FibonacciCircuit:
                     sets["p%d_%d" % (q, i)] = [(r - 1, plonk.PoseidonGate.wire_output(i)), (r, plonk.PoseidonGate.wire_input(i))]
             prev_out = [pw[plonk.PoseidonGate.wire_output(i)] for i in range(12)]
             self.poseidon_io.append((inputs, q & 1, prev_out))
+        for q, (_, _, ew) in enumerate(extra_rows):      # rows of the other gate types, each with a satisfying witness
+            r = 2 + arithmetic_rows + poseidon_rows + q
+            for k, v in ew.items():
+                wires[k, r] = v
+            if break_extra == q:
+                k = max(ew)
+                wires[k, r] = (int(wires[k, r]) + 1) % P
         if break_poseidon:  # one partial-round S-box input off by one
             r = 2 + arithmetic_rows
             k = plonk.PoseidonGate.wire_partial_sbox(7)
@@ -197,14 +279,12 @@ class FibonacciCircuit:
     def oracle_circuit(self):
         """The dict tests/oracle_lib.plonk_quotient takes, from the product's CommonCircuitData."""
         cd = self.common
-        kinds = {"NoopGate": GATE_NOOP, "ConstantGate": GATE_CONSTANT, "PublicInputGate": GATE_PUBLIC_INPUT,
-                 "ArithmeticGate": GATE_ARITHMETIC, "PoseidonGate": GATE_POSEIDON}
         gates = []
         for i, g in enumerate(cd.gates):
             sel = cd.selectors_info.selector_indices[i]
             grp = cd.selectors_info.groups[sel]
-            param = getattr(g, "num_consts", getattr(g, "num_ops", 0))
-            gates.append((kinds[g.id().split(" ")[0].split("(")[0]], param, sel, grp.start, grp.stop))
+            kind, param, param2 = oracle_gate_kind(g)
+            gates.append((kind, param, sel, grp.start, grp.stop, param2))
         cfg = cd.config
         return dict(num_wires=cfg.num_wires, num_routed_wires=cfg.num_routed_wires, num_constants=cd.num_constants,
                     num_challenges=cfg.num_challenges, quotient_degree_factor=cd.quotient_degree_factor,

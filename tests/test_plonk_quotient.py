@@ -28,6 +28,9 @@ SHAPES = [
     (24, 16, 8, 3, 3),    # one selector for all gates, chunks of 8
     (135, 80, 8, 3, 5),   # CircuitConfig::standard_recursion_config
     (135, 80, 8, 3, 5, 9),  # ... with nine PoseidonGate rows (a hash chain): two selector groups, 123 gate constraints
+    # ... and a row of every other gate type built so far: three selector groups
+    (135, 80, 8, 3, 5, 4, ("ArithmeticExtensionGate", "MulExtensionGate", "BaseSumGate", "BaseSumGate4", "ReducingGate",
+                           "ReducingExtensionGate")),
 ]
 
 
@@ -44,6 +47,8 @@ def _circuit(shape, **kw):
     nw, nr, qdf, rate_bits, degree_bits = shape[:5]
     if len(shape) > 5:
         kw.setdefault("poseidon_rows", shape[5])
+    if len(shape) > 6:
+        kw.setdefault("extra", shape[6])
     cfg = plonk.CircuitConfig(num_wires=nw, num_routed_wires=nr, max_quotient_degree_factor=qdf, rate_bits=rate_bits,
                               cap_height=1)
     return PC.FibonacciCircuit(plonk, cfg, degree_bits, seed=nw + qdf + len(shape), **kw)
@@ -83,7 +88,7 @@ def _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas):
     nsel = cd.selectors_info.num_selectors()
     circuit = c.oracle_circuit()
     constraint_terms = [0] * cd.num_gate_constraints
-    for i, (kind, param, sel, g0, g1) in enumerate(circuit["gates"]):
+    for i, (kind, param, sel, g0, g1, _) in enumerate(circuit["gates"]):
         s = consts_sigmas[sel]
         filt = 1
         for j in list(range(g0, g1)) + ([0xFFFFFFFF] if nsel > 1 else []):
@@ -98,7 +103,7 @@ def _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas):
             res = [wires[4 * t + 3] - (wires[4 * t] * wires[4 * t + 1] * k[0] + wires[4 * t + 2] * k[1]) for t in range(param)]
         elif kind == 0:
             res = []
-        else:   # the product's own gate code, over numbers
+        else:   # the product's own gate code, over numbers (the oracle restates these gates independently in C++)
             pv = PC.PointVars(consts_sigmas, wires, c.public_inputs_hash).remove_prefix(nsel)
             res = [int(v) for v in cd.gates[i].eval_unfiltered(pv)]
         for t, r in enumerate(res):
@@ -227,6 +232,21 @@ def test_vanishing_program_through_the_kernel_source_on_host_matches_oracle(orac
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("which", range(6))
+def test_each_gate_type_rejects_a_wrong_witness(oracle, which):
+    """One wire of the `which`-th extra gate row off by one: the oracle's quotient no longer satisfies the verifier
+    identity (the gate's constraints are not vacuous)."""
+    shape = SHAPES[5]
+    c = _circuit(shape, break_extra=which)
+    nc = c.config.num_challenges
+    betas, gammas, alphas = _challenges(0x570 + which, nc)
+    cs, w, z = _oracle_commits(oracle, c, betas, gammas)
+    q = oracle.plonk_quotient(c.oracle_circuit(), cs, w, z, c.public_inputs_hash, betas, gammas, alphas)
+    zeta = int(synth(0x571, (1,))[0])
+    want, zh = _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas)
+    assert any(want[i] != zh * _ev(q[i], zeta) % P_ for i in range(nc))
+
+
 # ----------------------------------------------------------------------------- GPU
 @pytest.fixture(scope="module")
 def pb():
@@ -243,7 +263,7 @@ def pb():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[1], (135, 80, 8, 3, 7), (135, 80, 8, 3, 6, 20)])
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[1], (135, 80, 8, 3, 7), (135, 80, 8, 3, 6, 20), SHAPES[5]])
 def test_plonk_quotient_on_device_matches_oracle(pb, oracle, shape):
     """The prover's third phase without leaving the device (plonk/prover.rs:220-352): wires + constants_sigmas
     commitments -> Z / partial products commitment (device) -> quotient polynomials (device, LDEs read in place) ->
