@@ -1288,6 +1288,116 @@ static void gate_eval_unfiltered(const glo_gate& g, const u64* local_constants, 
             }
             break;
         }
+        case GLO_GATE_POSEIDON_MDS: {  // poseidon_mds.rs:156-175, mds_layer_field (hash/poseidon.rs:292-306) per component
+            u64 in_a[12], in_b[12];
+            for (int i = 0; i < 12; i++) {
+                in_a[i] = local_wires[2 * i];
+                in_b[i] = local_wires[2 * i + 1];
+            }
+            mds_layer(in_a);
+            mds_layer(in_b);
+            for (int i = 0; i < 12; i++) {
+                res.push_back(fsub(local_wires[2 * (12 + i)], in_a[i]));
+                res.push_back(fsub(local_wires[2 * (12 + i) + 1], in_b[i]));
+            }
+            break;
+        }
+        case GLO_GATE_RANDOM_ACCESS: {  // random_access.rs:302-343; param = bits, param2 = num_copies, param3 = extra constants
+            const size_t bits = g.param, num_copies = g.param2, num_extra = g.param3, vec_size = (size_t)1 << bits;
+            const size_t num_routed = (2 + vec_size) * num_copies + num_extra;
+            for (size_t copy = 0; copy < num_copies; copy++) {
+                const u64 access_index = local_wires[(2 + vec_size) * copy];
+                const u64 claimed_element = local_wires[(2 + vec_size) * copy + 1];
+                std::vector<u64> list_items(local_wires + (2 + vec_size) * copy + 2, local_wires + (2 + vec_size) * (copy + 1));
+                const u64* b = local_wires + num_routed + copy * bits;
+                for (size_t i = 0; i < bits; i++) res.push_back(fmul(b[i], fsub(b[i], 1)));
+                u64 reconstructed_index = 0;
+                for (size_t i = bits; i-- > 0;) reconstructed_index = fadd(fadd(reconstructed_index, reconstructed_index), b[i]);
+                res.push_back(fsub(reconstructed_index, access_index));
+                for (size_t i = 0; i < bits; i++) {
+                    std::vector<u64> next(list_items.size() / 2);
+                    for (size_t k = 0; k < next.size(); k++) {
+                        const u64 x = list_items[2 * k], y = list_items[2 * k + 1];
+                        next[k] = fadd(x, fmul(b[i], fsub(y, x)));
+                    }
+                    list_items.swap(next);
+                }
+                res.push_back(fsub(list_items[0], claimed_element));
+            }
+            for (size_t i = 0; i < num_extra; i++) res.push_back(fsub(local_constants[i], local_wires[(2 + vec_size) * num_copies + i]));
+            break;
+        }
+        case GLO_GATE_EXPONENTIATION: {  // exponentiation.rs:210-243; param = num_power_bits
+            const size_t n = g.param;
+            const u64 base = local_wires[0], output = local_wires[1 + n];
+            const u64* power_bits = local_wires + 1;
+            const u64* intermediate_values = local_wires + 2 + n;
+            for (size_t i = 0; i < n; i++) {
+                const u64 prev_intermediate_value = i == 0 ? 1 : fsqr(intermediate_values[i - 1]);
+                const u64 cur_bit = power_bits[n - i - 1];
+                const u64 not_cur_bit = fsub(1, cur_bit);
+                const u64 computed_intermediate_value = fmul(prev_intermediate_value, fadd(fmul(cur_bit, base), not_cur_bit));
+                res.push_back(fsub(computed_intermediate_value, intermediate_values[i]));
+            }
+            res.push_back(fsub(output, intermediate_values[n - 1]));
+            break;
+        }
+        case GLO_GATE_COSET_INTERPOLATION: {  // coset_interpolation.rs:251-298,553-580; param = subgroup_bits, param2 = degree
+            const size_t num_points = (size_t)1 << g.param, degree = g.param2;
+            const size_t num_intermediates = (num_points - 2) / (degree - 1);
+            const size_t start_evaluation_point = 1 + 2 * num_points, start_evaluation_value = start_evaluation_point + 2;
+            const size_t start_intermediates = start_evaluation_value + 2;
+            auto ext = [&](size_t at) { return E2{local_wires[at], local_wires[at + 1]}; };
+            std::vector<u64> domain(num_points), weights(num_points);  // two_adic_subgroup, barycentric_weights (interpolation.rs:53-65)
+            {
+                const u64 w = primitive_root_of_unity((uint32_t)g.param);
+                u64 x = 1;
+                for (size_t i = 0; i < num_points; i++, x = fmul(x, w)) domain[i] = x;
+                for (size_t i = 0; i < num_points; i++) {
+                    u64 d = 1;
+                    for (size_t j = 0; j < num_points; j++)
+                        if (j != i) d = fmul(d, fsub(domain[i], domain[j]));
+                    weights[i] = finv(d);
+                }
+            }
+            const u64 shift = local_wires[0];
+            const E2 evaluation_point = ext(start_evaluation_point);
+            const E2 shifted_evaluation_point = ext(start_intermediates + 2 * 2 * num_intermediates);
+            {
+                const E2 d = esub(evaluation_point, escale(shifted_evaluation_point, shift));
+                res.push_back(d.a);
+                res.push_back(d.b);
+            }
+            auto partial_interpolate = [&](size_t lo, size_t hi, E2& eval, E2& terms_partial_prod) {
+                for (size_t i = lo; i < hi; i++) {
+                    const E2 val = escale(ext(1 + 2 * i), weights[i]);
+                    const E2 term = esub(shifted_evaluation_point, e2(domain[i]));
+                    const E2 next_eval = eadd(emul(eval, term), emul(val, terms_partial_prod));
+                    terms_partial_prod = emul(terms_partial_prod, term);
+                    eval = next_eval;
+                }
+            };
+            E2 computed_eval = e2(0), computed_prod = e2(1);
+            partial_interpolate(0, degree, computed_eval, computed_prod);
+            for (size_t i = 0; i < num_intermediates; i++) {
+                const E2 intermediate_eval = ext(start_intermediates + 2 * i);
+                const E2 intermediate_prod = ext(start_intermediates + 2 * (num_intermediates + i));
+                const E2 d0 = esub(intermediate_eval, computed_eval), d1 = esub(intermediate_prod, computed_prod);
+                res.push_back(d0.a);
+                res.push_back(d0.b);
+                res.push_back(d1.a);
+                res.push_back(d1.b);
+                const size_t start_index = 1 + (degree - 1) * (i + 1);
+                const size_t end_index = std::min(start_index + degree - 1, num_points);
+                computed_eval = intermediate_eval;
+                computed_prod = intermediate_prod;
+                partial_interpolate(start_index, end_index, computed_eval, computed_prod);
+            }
+            const E2 d = esub(ext(start_evaluation_value), computed_eval);
+            res.push_back(d.a);
+            res.push_back(d.b);
+            break;
+        }
         case GLO_GATE_POSEIDON: {  // poseidon.rs:204-283 (wire layout :43-101), with the layers of hash/poseidon.rs
             const int W = 12, HALF = GL_POSEIDON_HALF_FULL_ROUNDS, NP = GL_POSEIDON_PARTIAL_ROUNDS;
             const int WIRE_SWAP = 2 * W, START_DELTA = 2 * W + 1, START_FULL_0 = START_DELTA + 4;

@@ -172,11 +172,15 @@ int glo_batch_prove_openings(const glo_batch_commit* const* oracles, size_t n_or
 #define GLO_GATE_BASE_SUM 7             /* gates/base_sum.rs, param = num_limbs, param2 = B */
 #define GLO_GATE_REDUCING 8             /* gates/reducing.rs, param = num_coeffs */
 #define GLO_GATE_REDUCING_EXTENSION 9   /* gates/reducing_extension.rs, param = num_coeffs */
+#define GLO_GATE_POSEIDON_MDS 10        /* gates/poseidon_mds.rs */
+#define GLO_GATE_RANDOM_ACCESS 11       /* gates/random_access.rs, param = bits, param2 = num_copies, param3 = num_extra_constants */
+#define GLO_GATE_EXPONENTIATION 12      /* gates/exponentiation.rs, param = num_power_bits */
+#define GLO_GATE_COSET_INTERPOLATION 13 /* gates/coset_interpolation.rs, param = subgroup_bits, param2 = degree */
 typedef struct {
     uint32_t kind, param;
     uint32_t selector_index;          /* SelectorsInfo.selector_indices[gate] (gates/selectors.rs:17-20) */
     uint32_t group_start, group_end;  /* SelectorsInfo.groups[selector_index] */
-    uint32_t param2;
+    uint32_t param2, param3;
 } glo_gate;
 typedef struct {
     uint32_t num_wires, num_routed_wires, num_constants /* selectors included */, num_challenges;

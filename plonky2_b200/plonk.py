@@ -799,6 +799,262 @@ class PoseidonGate(Gate):
         return out
 
 
+class PoseidonMdsGate(Gate):
+    """gates/poseidon_mds.rs:28-221: outputs = MDS * inputs for 12 elements of F_{p^2} (the MDS layer acts on both
+    components)."""
+
+    def id(self):
+        return "PoseidonMdsGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>"
+
+    def num_wires(self):
+        return 2 * D * SPONGE_WIDTH
+
+    def num_constants(self):
+        return 0
+
+    def degree(self):
+        return 1
+
+    def num_constraints(self):
+        return SPONGE_WIDTH * D
+
+    def eval_unfiltered(self, vars):
+        inputs = [get_local_ext(vars, i * D) for i in range(SPONGE_WIDTH)]
+        computed = PoseidonGate._mds_layer(inputs)                 # mds_layer_field
+        out = []
+        for i in range(SPONGE_WIDTH):
+            out += (get_local_ext(vars, (SPONGE_WIDTH + i) * D) - computed[i]).to_basefield_array()
+        return out
+
+
+class RandomAccessGate(Gate):
+    """gates/random_access.rs:33-343: num_copies lookups claimed_element = list[access_index] in lists of 2^bits wires,
+    through the bit decomposition of the index; leftover routed wires pinned to constants."""
+
+    def __init__(self, num_copies, bits, num_extra_constants):
+        self.num_copies, self.bits, self.num_extra_constants = num_copies, bits, num_extra_constants
+
+    @classmethod
+    def new_from_config(cls, config, bits):
+        vec_size = 1 << bits
+        max_copies = min(config.num_routed_wires // (2 + vec_size), config.num_wires // (2 + vec_size + bits))
+        max_extra_constants = config.num_routed_wires - (2 + vec_size) * max_copies
+        return cls(max_copies, bits, min(max_extra_constants, config.num_constants))
+
+    def vec_size(self):
+        return 1 << self.bits
+
+    def wire_access_index(self, copy):
+        return (2 + self.vec_size()) * copy
+
+    def wire_claimed_element(self, copy):
+        return (2 + self.vec_size()) * copy + 1
+
+    def wire_list_item(self, i, copy):
+        return (2 + self.vec_size()) * copy + 2 + i
+
+    def wire_extra_constant(self, i):
+        return (2 + self.vec_size()) * self.num_copies + i
+
+    def num_routed_wires(self):
+        return (2 + self.vec_size()) * self.num_copies + self.num_extra_constants
+
+    def wire_bit(self, i, copy):
+        return self.num_routed_wires() + copy * self.bits + i
+
+    def id(self):
+        return ("RandomAccessGate { bits: %d, num_copies: %d, num_extra_constants: %d, _phantom: PhantomData<plonky2_field::"
+                "goldilocks_field::GoldilocksField> }<D=2>" % (self.bits, self.num_copies, self.num_extra_constants))
+
+    def num_wires(self):
+        return self.wire_bit(self.bits - 1, self.num_copies - 1) + 1
+
+    def num_constants(self):
+        return self.num_extra_constants
+
+    def degree(self):
+        return self.bits + 1
+
+    def num_constraints(self):
+        return self.num_copies * (self.bits + 2) + self.num_extra_constants
+
+    def eval_unfiltered(self, vars):
+        w = vars.local_wire
+        out = []
+        for copy in range(self.num_copies):
+            bits = [w(self.wire_bit(i, copy)) for i in range(self.bits)]
+            for b in bits:
+                out.append(b * (b - 1))
+            acc = None                                  # bits.rev().fold(0, |acc, b| acc + acc + b)
+            for b in reversed(bits):
+                acc = b if acc is None else acc + acc + b
+            out.append(acc - w(self.wire_access_index(copy)))
+            items = [w(self.wire_list_item(i, copy)) for i in range(self.vec_size())]
+            for b in bits:
+                items = [x + b * (y - x) for x, y in zip(items[0::2], items[1::2])]
+            out.append(items[0] - w(self.wire_claimed_element(copy)))
+        for i in range(self.num_extra_constants):
+            out.append(vars.local_constant(i) - w(self.wire_extra_constant(i)))
+        return out
+
+
+class ExponentiationGate(Gate):
+    """gates/exponentiation.rs:33-243: output = base^power from the power's bits (wires 1.., little endian) by square and
+    multiply with one intermediate wire per bit."""
+
+    def __init__(self, num_power_bits):
+        self.num_power_bits = num_power_bits
+
+    @classmethod
+    def new_from_config(cls, config):
+        return cls(min(config.num_routed_wires - 2, (config.num_wires - 2) // 2))
+
+    def wire_power_bit(self, i):
+        return 1 + i
+
+    def wire_output(self):
+        return 1 + self.num_power_bits
+
+    def wire_intermediate_value(self, i):
+        return 2 + self.num_power_bits + i
+
+    def id(self):
+        return ("ExponentiationGate { num_power_bits: %d, _phantom: PhantomData<plonky2_field::goldilocks_field::"
+                "GoldilocksField> }<D=2>" % self.num_power_bits)
+
+    def num_wires(self):
+        return self.wire_intermediate_value(self.num_power_bits - 1) + 1
+
+    def num_constants(self):
+        return 0
+
+    def degree(self):
+        return 4
+
+    def num_constraints(self):
+        return self.num_power_bits + 1
+
+    def eval_unfiltered(self, vars):
+        w = vars.local_wire
+        base = w(0)
+        n = self.num_power_bits
+        inter = [w(self.wire_intermediate_value(i)) for i in range(n)]
+        out = []
+        for i in range(n):
+            cur_bit = w(self.wire_power_bit(n - i - 1))          # little-endian bits, accumulated big-endian
+            factor = cur_bit * base + (1 - cur_bit)
+            computed = factor if i == 0 else inter[i - 1] * inter[i - 1] * factor
+            out.append(computed - inter[i])
+        out.append(w(self.wire_output()) - inter[n - 1])
+        return out
+
+
+def two_adic_subgroup(bits):
+    """Field::two_adic_subgroup (field/src/types.rs:283-287)."""
+    g, out, x = F.primitive_root_of_unity(bits), [], 1
+    for _ in range(1 << bits):
+        out.append(x)
+        x = x * g % F.ORDER
+    return out
+
+
+def barycentric_weights(points):
+    """barycentric_weights (field/src/interpolation.rs:53-65) for base-field abscissae."""
+    out = []
+    for i, xi in enumerate(points):
+        d = 1
+        for j, xj in enumerate(points):
+            if j != i:
+                d = d * (xi - xj) % F.ORDER
+        out.append(pow(d, F.ORDER - 2, F.ORDER))
+    return out
+
+
+class CosetInterpolationGate(Gate):
+    """gates/coset_interpolation.rs:30-397: evaluates at an F_{p^2} point the interpolant of 2^subgroup_bits F_{p^2}
+    values given on a coset shift*H, as barycentric partial sums with every (degree-1)-th intermediate on a wire."""
+
+    def __init__(self, subgroup_bits, max_degree=None):
+        n_points = 1 << subgroup_bits
+        max_degree = n_points if max_degree is None else max_degree
+        assert max_degree > 1, "need at least quadratic constraints"
+        n_intermediates = (n_points - 2) // (max_degree - 1)
+        self.subgroup_bits = subgroup_bits
+        self._degree = (n_points - 2) // (n_intermediates + 1) + 2
+        self.domain = two_adic_subgroup(subgroup_bits)
+        self.barycentric_weights = barycentric_weights(self.domain)
+
+    def num_points(self):
+        return 1 << self.subgroup_bits
+
+    def wires_value(self, i):
+        return 1 + i * D
+
+    def start_evaluation_point(self):
+        return 1 + self.num_points() * D
+
+    def start_evaluation_value(self):
+        return self.start_evaluation_point() + D
+
+    def start_intermediates(self):
+        return self.start_evaluation_value() + D
+
+    def num_intermediates(self):
+        return (self.num_points() - 2) // (self._degree - 1)
+
+    def wires_intermediate_eval(self, i):
+        return self.start_intermediates() + D * i
+
+    def wires_intermediate_prod(self, i):
+        return self.start_intermediates() + D * (self.num_intermediates() + i)
+
+    def wires_shifted_evaluation_point(self):
+        return self.start_intermediates() + D * 2 * self.num_intermediates()
+
+    def id(self):
+        return "CosetInterpolationGate { subgroup_bits: %d, degree: %d, barycentric_weights: %r }<D=2>" % (
+            self.subgroup_bits, self._degree, self.barycentric_weights)
+
+    def num_wires(self):
+        return self.start_intermediates() + D * (2 * self.num_intermediates() + 1)
+
+    def num_constants(self):
+        return 0
+
+    def degree(self):
+        return self._degree
+
+    def num_constraints(self):
+        return D + D + 2 * D * self.num_intermediates()
+
+    def partial_interpolate(self, lo, hi, values, x, acc):
+        """partial_interpolate (coset_interpolation.rs:553-580) over domain[lo:hi]; acc = (eval, partial product) or None
+        for the initial (0, 1)."""
+        for i in range(lo, hi):
+            val = values[i].scalar_mul(self.barycentric_weights[i])
+            term = x - self.domain[i]
+            acc = (val, term) if acc is None else (acc[0] * term + val * acc[1], acc[1] * term)
+        return acc
+
+    def eval_unfiltered(self, vars):
+        shift = vars.local_wire(0)
+        point = get_local_ext(vars, self.start_evaluation_point())
+        shifted = get_local_ext(vars, self.wires_shifted_evaluation_point())
+        out = (point - shifted.scalar_mul(shift)).to_basefield_array()
+        values = [get_local_ext(vars, self.wires_value(i)) for i in range(self.num_points())]
+        d = self._degree
+        acc = self.partial_interpolate(0, d, values, shifted, None)
+        for i in range(self.num_intermediates()):
+            ie = get_local_ext(vars, self.wires_intermediate_eval(i))
+            ip = get_local_ext(vars, self.wires_intermediate_prod(i))
+            out += (ie - acc[0]).to_basefield_array()
+            out += (ip - acc[1]).to_basefield_array()
+            start = 1 + (d - 1) * (i + 1)
+            acc = self.partial_interpolate(start, min(start + d - 1, self.num_points()), values, shifted, (ie, ip))
+        out += (get_local_ext(vars, self.start_evaluation_value()) - acc[0]).to_basefield_array()
+        return out
+
+
 # ------------------------------------------------------------------ circuit data
 class SelectorsInfo:
     """gates/selectors.rs:16-26"""

@@ -553,7 +553,8 @@ def verify_batch_fri_proof(caps, group_num_polys, degree_bits, instances, opened
 
 class GloGate(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("param", C.c_uint32), ("selector_index", C.c_uint32),
-                ("group_start", C.c_uint32), ("group_end", C.c_uint32), ("param2", C.c_uint32)]
+                ("group_start", C.c_uint32), ("group_end", C.c_uint32), ("param2", C.c_uint32),
+                ("param3", C.c_uint32)]
 
 
 class GloCircuit(C.Structure):
@@ -564,7 +565,8 @@ class GloCircuit(C.Structure):
 
 
 (GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON, GATE_ARITHMETIC_EXTENSION, GATE_MUL_EXTENSION,
- GATE_BASE_SUM, GATE_REDUCING, GATE_REDUCING_EXTENSION) = range(10)
+ GATE_BASE_SUM, GATE_REDUCING, GATE_REDUCING_EXTENSION, GATE_POSEIDON_MDS, GATE_RANDOM_ACCESS, GATE_EXPONENTIATION,
+ GATE_COSET_INTERPOLATION) = range(14)
 
 
 def plonk_quotient(circuit, constants_sigmas, wires, zs_partial_products, public_inputs_hash, betas, gammas, alphas):
@@ -576,6 +578,7 @@ def plonk_quotient(circuit, constants_sigmas, wires, zs_partial_products, public
     for i, g in enumerate(circuit["gates"]):
         gates[i].kind, gates[i].param, gates[i].selector_index, gates[i].group_start, gates[i].group_end = g[:5]
         gates[i].param2 = g[5] if len(g) > 5 else 0
+        gates[i].param3 = g[6] if len(g) > 6 else 0
     k_is = np.array([int(k) for k in circuit["k_is"]], dtype=np.uint64)
     cd = GloCircuit()
     for f in ("num_wires", "num_routed_wires", "num_constants", "num_challenges", "quotient_degree_factor", "num_selectors",

@@ -166,6 +166,71 @@ def extra_gate_row(plonk, config, name, rng):
             at = gate.wires_accs(i)
             wires[at], wires[at + 1] = acc
         return gate, [], wires
+    if name == "PoseidonMdsGate":
+        gate = plonk.PoseidonMdsGate()
+        ins = [_ext(rng) for _ in range(12)]
+        outs = plonk.PoseidonGate._mds_layer([plonk.Ext2(Fp(a), Fp(b)) for a, b in ins])
+        for i in range(12):
+            wires[2 * i], wires[2 * i + 1] = ins[i]
+            wires[2 * (12 + i)], wires[2 * (12 + i) + 1] = int(outs[i].a), int(outs[i].b)
+        return gate, [], wires
+    if name == "RandomAccessGate":
+        gate = plonk.RandomAccessGate.new_from_config(config, 4)
+        consts = [int(v) for v in rnd(rng, gate.num_extra_constants)]
+        for copy in range(gate.num_copies):
+            index = int(rnd(rng)) % gate.vec_size()
+            items = [int(v) for v in rnd(rng, gate.vec_size())]
+            wires[gate.wire_access_index(copy)] = index
+            wires[gate.wire_claimed_element(copy)] = items[index]
+            for i, v in enumerate(items):
+                wires[gate.wire_list_item(i, copy)] = v
+            for i in range(gate.bits):
+                wires[gate.wire_bit(i, copy)] = (index >> i) & 1
+        for i, v in enumerate(consts):
+            wires[gate.wire_extra_constant(i)] = v
+        return gate, consts, wires
+    if name == "ExponentiationGate":
+        gate = plonk.ExponentiationGate.new_from_config(config)
+        n = gate.num_power_bits
+        base = int(rnd(rng))
+        bits = [int(v) & 1 for v in rnd(rng, n)]
+        wires[0] = base
+        cur = 1
+        for i in range(n):
+            wires[gate.wire_power_bit(i)] = bits[i]
+        for i in range(n):                       # ExponentiationGenerator::run_once (exponentiation.rs:272-300)
+            cur = cur * cur % P if i else 1
+            cur = cur * (base if bits[n - 1 - i] else 1) % P
+            wires[gate.wire_intermediate_value(i)] = cur
+        wires[gate.wire_output()] = cur
+        assert cur == pow(base, sum(b << i for i, b in enumerate(bits)), P)
+        return gate, [], wires
+    if name == "CosetInterpolationGate":
+        gate = plonk.CosetInterpolationGate(4, config.max_quotient_degree_factor)
+        E = lambda v: plonk.Ext2(Fp(v[0]), Fp(v[1]))
+        shift = int(rnd(rng)) | 1
+        values = [_ext(rng) for _ in range(gate.num_points())]
+        point = _ext(rng)
+        shift_inv = pow(shift, P - 2, P)
+        shifted = [point[0] * shift_inv % P, point[1] * shift_inv % P]
+        wires[0] = shift
+        for i, v in enumerate(values):
+            wires[gate.wires_value(i)], wires[gate.wires_value(i) + 1] = v
+        at = gate.start_evaluation_point()
+        wires[at], wires[at + 1] = point
+        at = gate.wires_shifted_evaluation_point()
+        wires[at], wires[at + 1] = shifted
+        d = gate.degree()
+        vals = [E(v) for v in values]
+        acc = gate.partial_interpolate(0, d, vals, E(shifted), None)      # InterpolationGenerator::run_once
+        for i in range(gate.num_intermediates()):
+            for at, e in ((gate.wires_intermediate_eval(i), acc[0]), (gate.wires_intermediate_prod(i), acc[1])):
+                wires[at], wires[at + 1] = int(e.a), int(e.b)
+            start = 1 + (d - 1) * (i + 1)
+            acc = gate.partial_interpolate(start, min(start + d - 1, gate.num_points()), vals, E(shifted), acc)
+        at = gate.start_evaluation_value()
+        wires[at], wires[at + 1] = int(acc[0].a), int(acc[0].b)
+        return gate, [], wires, dict(shift=shift, values=values, point=point, value=[int(acc[0].a), int(acc[0].b)])
     raise KeyError(name)
 
 
@@ -179,7 +244,13 @@ def oracle_gate_kind(g):
             "MulExtensionGate": (OL.GATE_MUL_EXTENSION, getattr(g, "num_ops", 0), 0),
             "BaseSumGate": (OL.GATE_BASE_SUM, getattr(g, "num_limbs", 0), getattr(g, "base", 0)),
             "ReducingGate": (OL.GATE_REDUCING, getattr(g, "num_coeffs", 0), 0),
-            "ReducingExtensionGate": (OL.GATE_REDUCING_EXTENSION, getattr(g, "num_coeffs", 0), 0)}[name]
+            "ReducingExtensionGate": (OL.GATE_REDUCING_EXTENSION, getattr(g, "num_coeffs", 0), 0),
+            "PoseidonMdsGate": (OL.GATE_POSEIDON_MDS, 0, 0),
+            "RandomAccessGate": (OL.GATE_RANDOM_ACCESS, getattr(g, "bits", 0), getattr(g, "num_copies", 0),
+                                 getattr(g, "num_extra_constants", 0)),
+            "ExponentiationGate": (OL.GATE_EXPONENTIATION, getattr(g, "num_power_bits", 0), 0),
+            "CosetInterpolationGate": (OL.GATE_COSET_INTERPOLATION, getattr(g, "subgroup_bits", 0), getattr(g, "_degree", 0)),
+            }[name]
 
 
 class FibonacciCircuit:
@@ -197,6 +268,8 @@ class FibonacciCircuit:
         arithmetic_rows = arithmetic_rows if arithmetic_rows is not None else n - 5 - poseidon_rows - len(extra)
         assert 2 + arithmetic_rows + poseidon_rows + len(extra) <= n
         extra_rows = [extra_gate_row(plonk, config, name, rng) for name in extra]
+        self.extra_info = [r[3] if len(r) > 3 else None for r in extra_rows]
+        extra_rows = [r[:3] for r in extra_rows]
         f0 = int(rnd(rng))
         instances = [(plonk.PublicInputGate(), []), (plonk.ConstantGate(2), [f0, 1])]
         instances += [(arith, [1, 1])] * arithmetic_rows
@@ -283,8 +356,8 @@ class FibonacciCircuit:
         for i, g in enumerate(cd.gates):
             sel = cd.selectors_info.selector_indices[i]
             grp = cd.selectors_info.groups[sel]
-            kind, param, param2 = oracle_gate_kind(g)
-            gates.append((kind, param, sel, grp.start, grp.stop, param2))
+            kind, param, param2, *rest = oracle_gate_kind(g)
+            gates.append((kind, param, sel, grp.start, grp.stop, param2, rest[0] if rest else 0))
         cfg = cd.config
         return dict(num_wires=cfg.num_wires, num_routed_wires=cfg.num_routed_wires, num_constants=cd.num_constants,
                     num_challenges=cfg.num_challenges, quotient_degree_factor=cd.quotient_degree_factor,

@@ -30,8 +30,10 @@ SHAPES = [
     (135, 80, 8, 3, 5, 9),  # ... with nine PoseidonGate rows (a hash chain): two selector groups, 123 gate constraints
     # ... and a row of every other gate type built so far: three selector groups
     (135, 80, 8, 3, 5, 4, ("ArithmeticExtensionGate", "MulExtensionGate", "BaseSumGate", "BaseSumGate4", "ReducingGate",
-                           "ReducingExtensionGate")),
+                           "ReducingExtensionGate", "PoseidonMdsGate", "RandomAccessGate", "ExponentiationGate",
+                           "CosetInterpolationGate")),
 ]
+NUM_EXTRA = len(SHAPES[5][6])
 
 
 def _plonk():
@@ -88,7 +90,7 @@ def _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas):
     nsel = cd.selectors_info.num_selectors()
     circuit = c.oracle_circuit()
     constraint_terms = [0] * cd.num_gate_constraints
-    for i, (kind, param, sel, g0, g1, _) in enumerate(circuit["gates"]):
+    for i, (kind, param, sel, g0, g1, *_) in enumerate(circuit["gates"]):
         s = consts_sigmas[sel]
         filt = 1
         for j in list(range(g0, g1)) + ([0xFFFFFFFF] if nsel > 1 else []):
@@ -232,7 +234,30 @@ def test_vanishing_program_through_the_kernel_source_on_host_matches_oracle(orac
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("which", range(6))
+def test_coset_interpolation_row_holds_the_true_interpolant():
+    """The CosetInterpolationGate row's evaluation_value is the Lagrange interpolant of its 16 F_{p^2} values on the coset
+    shift*H at the evaluation point (computed here directly from the definition) -- so the barycentric recurrences the
+    gate constrains (and the oracle restates) compute what the reference's gate is documented to compute."""
+    import plonk_circuits as PC
+
+    plonk = _plonk()
+    c = _circuit(SHAPES[5])
+    info = [i for i in c.extra_info if i][0]
+    xs = [info["shift"] * x % P_ for x in plonk.two_adic_subgroup(4)]
+    z = plonk.Ext2(PC.Fp(info["point"][0]), PC.Fp(info["point"][1]))
+    total = plonk.Ext2(PC.Fp(0), PC.Fp(0))
+    for i, v in enumerate(info["values"]):
+        term = plonk.Ext2(PC.Fp(v[0]), PC.Fp(v[1]))
+        den = 1
+        for j, xj in enumerate(xs):
+            if j != i:
+                term = term * (z - xj)
+                den = den * (xs[i] - xj) % P_
+        total = total + term.scalar_mul(pow(den, P_ - 2, P_))
+    assert [int(total.a), int(total.b)] == info["value"]
+
+
+@pytest.mark.parametrize("which", range(NUM_EXTRA))
 def test_each_gate_type_rejects_a_wrong_witness(oracle, which):
     """One wire of the `which`-th extra gate row off by one: the oracle's quotient no longer satisfies the verifier
     identity (the gate's constraints are not vacuous)."""
