@@ -1453,17 +1453,96 @@ static void gate_eval_unfiltered(const glo_gate& g, const u64* local_constants, 
     }
 }
 
+// check_lookup_constraints_batch (plonk/vanishing_poly.rs:521-689) for one challenge
+static void check_lookup_constraints_batch(const glo_circuit* cd, const u64* local_wires, const u64* local_lookup_zs,
+                                           const u64* next_lookup_zs, const u64* lookup_selectors, const uint64_t deltas[4],
+                                           const std::vector<u64>& lut_re_poly_evals, std::vector<u64>& constraints) {
+    const size_t num_lu_slots = cd->num_routed_wires / 2, num_lut_slots = cd->num_routed_wires / 3;
+    const size_t lu_degree = cd->quotient_degree_factor - 1;
+    const size_t num_sldc_polys = cd->num_lookup_polys - 1;
+    const size_t lut_degree = (num_lut_slots + num_sldc_polys - 1) / num_sldc_polys;
+    const u64 z_re = local_lookup_zs[0], next_z_re = next_lookup_zs[0];
+    const u64* z_x_lookup_sldcs = local_lookup_zs + 1;
+    const u64* z_gx_lookup_sldcs = next_lookup_zs + 1;
+    const u64 delta_a = deltas[0], delta_b = deltas[1], delta_alpha = deltas[2], delta_delta = deltas[3];
+    std::vector<u64> current_looked_combos(num_lut_slots), current_looking_combos(num_lu_slots), current_lookup_combos(num_lut_slots);
+    for (size_t s = 0; s < num_lut_slots; s++) {
+        current_looked_combos[s] = fadd(local_wires[3 * s], fmul(delta_a, local_wires[3 * s + 1]));
+        current_lookup_combos[s] = fadd(local_wires[3 * s], fmul(delta_b, local_wires[3 * s + 1]));
+    }
+    for (size_t s = 0; s < num_lu_slots; s++) current_looking_combos[s] = fadd(local_wires[2 * s], fmul(delta_a, local_wires[2 * s + 1]));
+    const size_t TransSre = 0, TransLdc = 1, InitSre = 2, LastLdc = 3, StartEnd = 4;  // LookupSelectors, gates/selectors.rs:33-40
+    constraints.push_back(fmul(lookup_selectors[LastLdc], z_x_lookup_sldcs[num_sldc_polys - 1]));
+    constraints.push_back(fmul(lookup_selectors[InitSre], z_x_lookup_sldcs[0]));
+    constraints.push_back(fmul(lookup_selectors[InitSre], z_re));
+    for (size_t r = StartEnd; r < cd->num_lookup_selectors; r++)
+        constraints.push_back(fmul(lookup_selectors[r], fsub(z_re, lut_re_poly_evals[r - StartEnd])));
+    u64 cur_sum = next_z_re;
+    for (u64 elt : current_lookup_combos) cur_sum = fadd(fmul(cur_sum, delta_delta), elt);
+    constraints.push_back(fmul(lookup_selectors[TransSre], fsub(z_re, cur_sum)));
+    for (size_t poly = 0; poly < num_sldc_polys; poly++) {
+        const size_t lut_lo = poly * lut_degree, lut_hi = std::min((poly + 1) * lut_degree, num_lut_slots);
+        const size_t lu_lo = poly * lu_degree, lu_hi = std::min((poly + 1) * lu_degree, num_lu_slots);
+        u64 lut_prod = 1, lu_prod = 1;
+        for (size_t i = lut_lo; i < lut_hi; i++) lut_prod = fmul(lut_prod, fsub(delta_alpha, current_looked_combos[i]));
+        for (size_t i = lu_lo; i < lu_hi; i++) lu_prod = fmul(lu_prod, fsub(delta_alpha, current_looking_combos[i]));
+        auto lut_prod_i = [&](size_t i) {
+            u64 p = 1;
+            for (size_t j = lut_lo; j < lut_hi; j++)
+                if (j != i) p = fmul(p, fsub(delta_alpha, current_looked_combos[j]));
+            return p;
+        };
+        auto lu_prod_i = [&](size_t i) {
+            u64 p = 1;
+            for (size_t j = lu_lo; j < lu_hi; j++)
+                if (j != i) p = fmul(p, fsub(delta_alpha, current_looking_combos[j]));
+            return p;
+        };
+        u64 lu_sum_prods = 0, lut_sum_prods_with_mul = 0;
+        for (size_t i = lu_lo; i < lu_hi; i++) lu_sum_prods = fadd(lu_sum_prods, lu_prod_i(i));
+        for (size_t i = lut_lo; i < lut_hi; i++)
+            lut_sum_prods_with_mul = fadd(lut_sum_prods_with_mul, fmul(local_wires[3 * i + 2], lut_prod_i(i)));
+        const u64 prev = poly == 0 ? z_gx_lookup_sldcs[num_sldc_polys - 1] : z_x_lookup_sldcs[poly - 1];
+        const u64 unfiltered_sum_transition = fsub(fmul(lut_prod, fsub(z_x_lookup_sldcs[poly], prev)), lut_sum_prods_with_mul);
+        constraints.push_back(fmul(lookup_selectors[TransSre], unfiltered_sum_transition));
+        const u64 unfiltered_ldc_transition = fadd(fmul(lu_prod, fsub(z_x_lookup_sldcs[poly], prev)), lu_sum_prods);
+        constraints.push_back(fmul(lookup_selectors[TransLdc], unfiltered_ldc_transition));
+    }
+}
+
 int glo_plonk_quotient(const glo_circuit* cd, const glo_commit* constants_sigmas, const glo_commit* wires,
                        const glo_commit* zs_partial_products, const uint64_t public_inputs_hash[4], const uint64_t* betas,
-                       const uint64_t* gammas, const uint64_t* alphas, uint64_t* out) {
+                       const uint64_t* gammas, const uint64_t* deltas, const uint64_t* alphas, uint64_t* out) {
+    const bool has_lookup = cd->num_lookup_polys != 0;
     const uint32_t degree_bits = wires->degree_log, rate_bits = wires->rate_bits;
     if (constants_sigmas->degree_log != degree_bits || zs_partial_products->degree_log != degree_bits) return 1;
     if (constants_sigmas->rate_bits != rate_bits || zs_partial_products->rate_bits != rate_bits) return 1;
     const size_t num_challenges = cd->num_challenges, num_routed_wires = cd->num_routed_wires;
     const size_t num_prods = cd->num_partial_products, max_degree = cd->quotient_degree_factor;
     if (constants_sigmas->B != cd->num_constants + num_routed_wires || wires->B != cd->num_wires ||
-        zs_partial_products->B != num_challenges * (1 + num_prods))
+        zs_partial_products->B != num_challenges * (1 + num_prods + cd->num_lookup_polys))
         return 3;
+    // lut_re_poly_evals (prover.rs:653-681): get_lut_poly(..).eval(delta) (vanishing_poly.rs:30-52) per challenge and table
+    std::vector<std::vector<u64>> lut_re_poly_evals(num_challenges);
+    if (has_lookup) {
+        const size_t nb_slots = num_routed_wires / 3;
+        for (size_t c = 0; c < num_challenges; c++) {
+            const u64 b = deltas[4 * c + 1], delta = deltas[4 * c + 3];
+            size_t at = 0;
+            for (size_t t = 0; t < cd->n_luts; t++) {
+                const size_t n = cd->lut_len[t];
+                const size_t nb_padded_elts = (nb_slots - n % nb_slots) % nb_slots;
+                std::vector<u64> coeffs;
+                for (size_t k = 0; k < n; k++) coeffs.push_back(fadd(cd->lut_inp[at + k], fmul(b, cd->lut_out[at + k])));
+                for (size_t k = 0; k < nb_padded_elts; k++) coeffs.push_back(fadd(cd->lut_inp[at], fmul(b, cd->lut_out[at])));
+                std::reverse(coeffs.begin(), coeffs.end());  // degree = n + padding: no zero coefficients to append
+                u64 acc = 0;                                 // PolynomialCoeffs::eval: Horner from the top coefficient
+                for (size_t k = coeffs.size(); k-- > 0;) acc = fadd(fmul(acc, delta), coeffs[k]);
+                lut_re_poly_evals[c].push_back(acc);
+                at += n;
+            }
+        }
+    }
     if (num_prods + 1 != (num_routed_wires + max_degree - 1) / max_degree) return 4;  // num_partial_products, partial_products.rs:40-46
     uint32_t quotient_degree_bits = 0;
     while (((size_t)1 << quotient_degree_bits) < cd->quotient_degree_factor) quotient_degree_bits++;
@@ -1517,16 +1596,23 @@ int glo_plonk_quotient(const glo_circuit* cd, const glo_commit* constants_sigmas
             for (size_t j = g.group_start; j < g.group_end; j++)
                 if (j != gi) filter = fmul(filter, fsub(canon((u64)j), s));
             if (cd->num_selectors > 1) filter = fmul(filter, fsub(UNUSED_SELECTOR, s));
-            gate_eval_unfiltered(g, local_constants + cd->num_selectors, local_wires.data(), public_inputs_hash, gate_res);
+            gate_eval_unfiltered(g, local_constants + cd->num_selectors + cd->num_lookup_selectors, local_wires.data(),
+                                 public_inputs_hash, gate_res);
             if (gate_res.size() > constraint_terms.size()) return 5;  // "num_constraints() gave too low of a number"
             for (size_t j = 0; j < gate_res.size(); j++) constraint_terms[j] = fadd(constraint_terms[j], fmul(gate_res[j], filter));
         }
         vanishing_terms.clear();
         const u64 l_0_x = fmul(zh_evals[i % rate], finv(fmul(n_field, fsub(shifted_x, 1))));  // eval_l_0
-        std::vector<u64> vanishing_partial_products_terms;
+        std::vector<u64> vanishing_partial_products_terms, vanishing_all_lookup_terms;
         for (size_t c = 0; c < num_challenges; c++) {
             const u64 z_x = local_zs[c], z_gx = next_zs[c];
             vanishing_terms.push_back(fmul(l_0_x, fsub(z_x, 1)));  // vanishing_z_1_terms
+            if (has_lookup) {
+                const size_t at = num_challenges * (1 + num_prods) + cd->num_lookup_polys * c;  // lookup_range
+                check_lookup_constraints_batch(cd, local_wires.data(), local_zs.data() + at, next_zs.data() + at,
+                                               local_constants + cd->num_selectors, deltas + 4 * c, lut_re_poly_evals[c],
+                                               vanishing_all_lookup_terms);
+            }
             std::vector<u64> numerator_values(num_routed_wires), denominator_values(num_routed_wires);
             for (size_t j = 0; j < num_routed_wires; j++) {
                 const u64 wire_value = local_wires[j];
@@ -1549,6 +1635,7 @@ int glo_plonk_quotient(const glo_circuit* cd, const glo_commit* constants_sigmas
             }
         }
         vanishing_terms.insert(vanishing_terms.end(), vanishing_partial_products_terms.begin(), vanishing_partial_products_terms.end());
+        vanishing_terms.insert(vanishing_terms.end(), vanishing_all_lookup_terms.begin(), vanishing_all_lookup_terms.end());
         vanishing_terms.insert(vanishing_terms.end(), constraint_terms.begin(), constraint_terms.end());
         const u64 denominator_inv = zh_inverses[i % rate];
         for (size_t c = 0; c < num_challenges; c++) {  // reduce_with_powers_multi

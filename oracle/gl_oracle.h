@@ -188,10 +188,19 @@ typedef struct {
     const glo_gate* gates; /* sorted the way CommonCircuitData.gates is */
     size_t n_gates;
     const uint64_t* k_is;
+    /* lookups (all 0 / NULL without): the lookup selectors follow the gate selectors in the constants; luts = the tables'
+     * (input, output) pairs, concatenated, lut_len[t] pairs each; one LookupWire per table */
+    uint32_t num_lookup_selectors, num_lookup_polys;
+    size_t n_luts;
+    const uint32_t* lut_len;
+    const uint64_t *lut_inp, *lut_out;
 } glo_circuit;
+/* deltas: NUM_COINS_LOOKUP = 4 per challenge (A, B, alpha, delta), NULL without lookups; with lookups zs_partial_products
+ * also holds num_lookup_polys polynomials per challenge after the partial products (check_lookup_constraints_batch,
+ * vanishing_poly.rs:521-689). */
 int glo_plonk_quotient(const glo_circuit* cd, const glo_commit* constants_sigmas, const glo_commit* wires,
                        const glo_commit* zs_partial_products, const uint64_t public_inputs_hash[4], const uint64_t* betas,
-                       const uint64_t* gammas, const uint64_t* alphas, uint64_t* out);
+                       const uint64_t* gammas, const uint64_t* deltas, const uint64_t* alphas, uint64_t* out);
 
 /* Restated batch-FRI verifier (plonky2/src/batch_fri/verifier.rs:22-251): group_num_polys[o * n_instances + i] =
  * polynomials of oracle o in degree group i; opened_values per instance, per batch, per polynomial (2 words each).

@@ -8,7 +8,7 @@ alpha. Here that walk is done ONCE per circuit, symbolically: gates implement ev
 for all points on the GPU, reading the three commitments' LDEs in place. Circuit construction itself (CircuitBuilder,
 witness generation) stays with the caller; `CommonCircuitData.from_gate_instances` restates only what the quotient
 needs from `CircuitBuilder::build` (gate order, selector polynomials, constant columns, k_is, counts).
-No lookups yet (has_lookup = false)."""
+Lookup circuits carry the extra terms of `check_lookup_constraints` (the RE / Sum / LDC checks over the lookup selectors)."""
 import ctypes as C
 import heapq
 import os
@@ -24,6 +24,10 @@ OP_LOCAL, OP_NEXT, OP_CONST, OP_X, OP_L0, OP_ADD, OP_SUB, OP_MUL, OP_TERM, OP_AD
 _BINARY, _UNARY_CONST = (OP_ADD, OP_SUB, OP_MUL), (OP_ADDC, OP_MULC)
 MAX_REGS = 256
 UNUSED_SELECTOR = 0xFFFFFFFF   # gates/selectors.rs:14
+# LookupSelectors (gates/selectors.rs:33-40), LookupChallenges and NUM_COINS_LOOKUP (plonk/circuit_builder.rs:60-73)
+LOOKUP_TRANS_SRE, LOOKUP_TRANS_LDC, LOOKUP_INIT_SRE, LOOKUP_LAST_LDC, LOOKUP_START_END = range(5)
+LOOKUP_CHALLENGE_A, LOOKUP_CHALLENGE_B, LOOKUP_CHALLENGE_ALPHA, LOOKUP_CHALLENGE_DELTA = range(4)
+NUM_COINS_LOOKUP = 4
 # commitment indices of the program's loads
 CONSTANTS_SIGMAS, WIRES, ZS_PARTIAL_PRODUCTS = 0, 1, 2
 
@@ -1055,6 +1059,50 @@ class CosetInterpolationGate(Gate):
         return out
 
 
+class LookupGate(Gate):
+    """gates/lookup.rs:34-170: stores num_slots (input, output) pairs looked up in a table; no constraints of its own
+    (the lookup argument's terms are in `check_lookup_constraints`)."""
+
+    def __init__(self, num_slots, lut_index=0):
+        self.num_slots, self.lut_index = num_slots, lut_index
+
+    @classmethod
+    def new_from_config(cls, config, lut_index=0):
+        return cls(config.num_routed_wires // 2, lut_index)
+
+    def id(self):
+        return "LookupGate {num_slots: %d, lut_hash: %d}" % (self.num_slots, self.lut_index)
+
+    def num_wires(self):
+        return self.num_slots * 2
+
+    def num_constants(self):
+        return 0
+
+    def degree(self):
+        return 0
+
+    def num_constraints(self):
+        return 0
+
+    def eval_unfiltered(self, vars):
+        return []
+
+
+class LookupTableGate(LookupGate):
+    """gates/lookup_table.rs:36-188: num_slots table entries (input, output, multiplicity); no constraints of its own."""
+
+    @classmethod
+    def new_from_config(cls, config, lut_index=0):
+        return cls(config.num_routed_wires // 3, lut_index)
+
+    def id(self):
+        return "LookupTableGate {num_slots: %d, lut_hash: %d}" % (self.num_slots, self.lut_index)
+
+    def num_wires(self):
+        return self.num_slots * 3
+
+
 # ------------------------------------------------------------------ circuit data
 class SelectorsInfo:
     """gates/selectors.rs:16-26"""
@@ -1102,8 +1150,14 @@ def num_partial_products(n, max_degree):
 class CommonCircuitData:
     """The fields of CommonCircuitData (plonk/circuit_data.rs:420-560) the quotient needs."""
 
-    def __init__(self, config, degree_bits, gates, selectors_info, num_constants, k_is):
+    def __init__(self, config, degree_bits, gates, selectors_info, num_constants, k_is, luts=(), lookup_rows=()):
         self.config, self.degree_bits, self.gates, self.selectors_info = config, degree_bits, gates, selectors_info
+        self.luts = [list(t) for t in luts]                                   # LookupTable = [(input, output)] of u16
+        self.lookup_rows = [tuple(r) for r in lookup_rows]                    # LookupWire triples, one per table
+        self.num_lookup_selectors = (LOOKUP_START_END + len(self.lookup_rows)) if self.luts else 0
+        # 1 RE polynomial and ceil(num_lu_slots / (max_quotient_degree_factor - 1)) partial Sum/LDC polynomials
+        self.num_lookup_polys = (-(-(config.num_routed_wires // 2) // (config.max_quotient_degree_factor - 1)) + 1
+                                 if self.luts else 0)                        # circuit_builder.rs:1245-1251
         self.quotient_degree_factor = config.max_quotient_degree_factor       # circuit_builder.rs:1146
         self.num_gate_constraints = max([g.num_constraints() for g in gates] + [0])   # circuit_builder.rs:1236-1240
         self.num_constants = num_constants
@@ -1112,10 +1166,12 @@ class CommonCircuitData:
         self._program = None
 
     @classmethod
-    def from_gate_instances(cls, config, instances):
+    def from_gate_instances(cls, config, instances, luts=(), lookup_rows=()):
         """The part of CircuitBuilder::build (plonk/circuit_builder.rs:1146-1171) that fixes the constants commitment:
         instances = [(gate, constants)] per row (already padded to a power of two). Gates are sorted by (degree, id);
-        returns (common_data, constant_vecs) with constant_vecs = selector columns then the constant columns."""
+        returns (common_data, constant_vecs) with constant_vecs = selector columns, the lookup selectors
+        (selectors_lookup + selector_ends_lookups, gates/selectors.rs:50-108; lookup_rows = one LookupWire triple
+        (last_lu_gate, last_lut_gate, first_lut_gate) per table of `luts`), then the constant columns."""
         n = len(instances)
         degree_bits = F.log2_strict(n)
         by_id = {}
@@ -1125,11 +1181,24 @@ class CommonCircuitData:
         index = {g.id(): i for i, g in enumerate(gates)}
         rows = [index[g.id()] for g, _ in instances]
         constant_vecs, info = selector_polynomials(gates, rows, config.max_quotient_degree_factor + 1)
+        if luts:
+            assert len(luts) == len(lookup_rows)
+            sel = [np.zeros(n, dtype=np.uint64) for _ in range(LOOKUP_START_END)]
+            for last_lu_row, last_lut_row, first_lut_row in lookup_rows:
+                sel[LOOKUP_TRANS_SRE][last_lut_row:first_lut_row + 1] = 1
+                sel[LOOKUP_TRANS_LDC][last_lu_row:last_lut_row] = 1
+                sel[LOOKUP_INIT_SRE][first_lut_row + 1] = 1
+                sel[LOOKUP_LAST_LDC][last_lu_row] = 1
+            for _, last_lut_row, _ in lookup_rows:
+                ends = np.zeros(n, dtype=np.uint64)
+                ends[last_lut_row] = 1
+                sel.append(ends)
+            constant_vecs += sel
         max_constants = max(g.num_constants() for g in gates)          # constant_polys, circuit_builder.rs:970-991
         for k in range(max_constants):
             constant_vecs.append(np.array([int(c[k]) % F.ORDER if k < len(c) else 0 for _, c in instances], dtype=np.uint64))
         k_is = get_unique_coset_shifts(config.num_routed_wires)
-        return cls(config, degree_bits, gates, info, len(constant_vecs), k_is), constant_vecs
+        return cls(config, degree_bits, gates, info, len(constant_vecs), k_is, luts, lookup_rows), constant_vecs
 
     def quotient_degree(self):
         return self.quotient_degree_factor << self.degree_bits
@@ -1146,9 +1215,36 @@ class CommonCircuitData:
     def partial_products_range(self):
         return range(self.config.num_challenges, (self.num_partial_products + 1) * self.config.num_challenges)
 
+    def num_zs_partial_products_polys(self):
+        return self.config.num_challenges * (1 + self.num_partial_products)
+
+    def lookup_range(self, i):
+        """The lookup polynomials of challenge i in the zs_partial_products_lookup commitment."""
+        start = self.num_zs_partial_products_polys() + i * self.num_lookup_polys
+        return range(start, start + self.num_lookup_polys)
+
+    def num_lookup_terms(self):
+        """Constraints check_lookup_constraints yields per challenge (vanishing_poly.rs:231-236)."""
+        return (4 + len(self.luts) + 2 * (self.num_lookup_polys - 1)) if self.luts else 0
+
     def num_vanishing_terms(self):
         nc = self.config.num_challenges
-        return nc + nc * (self.num_partial_products + 1) + self.num_gate_constraints
+        return nc + nc * (self.num_partial_products + 1) + nc * self.num_lookup_terms() + self.num_gate_constraints
+
+    def lut_re_poly_evals(self, deltas):
+        """get_lut_poly(..).eval(delta) per table (vanishing_poly.rs:30-52, prover.rs:653-681) for ONE challenge's
+        deltas = (A, B, alpha, delta): sum_k (input_k + B output_k) delta^(len - 1 - k) over the table padded with its
+        first entry to whole LookupTableGate rows."""
+        b, delta = int(deltas[LOOKUP_CHALLENGE_B]), int(deltas[LOOKUP_CHALLENGE_DELTA])
+        nb_slots = self.config.num_routed_wires // 3
+        out = []
+        for lut in self.luts:
+            padded = list(lut) + [lut[0]] * ((nb_slots - len(lut) % nb_slots) % nb_slots)
+            acc = 0
+            for inp, outp in padded:
+                acc = (acc * delta + inp + b * outp) % F.ORDER
+            out.append(acc)
+        return out
 
     def vanishing_program(self):
         if self._program is None:
@@ -1171,13 +1267,68 @@ def compute_filter(b, row, group_range, s, many_selector):
     return b.product([i - s for i in idx]) if idx else None
 
 
+def check_lookup_constraints(cd, vars, local_lookup_zs, next_lookup_zs, lookup_selectors, deltas, lut_re_poly_evals,
+                             product):
+    """check_lookup_constraints_batch (plonk/vanishing_poly.rs:521-689) for one challenge, over any value type.
+    deltas = (A, B, alpha, delta); product = the value type's product-of-a-list (ONE for an empty list)."""
+    cfg = cd.config
+    num_lu_slots, num_lut_slots = cfg.num_routed_wires // 2, cfg.num_routed_wires // 3
+    lu_degree = cd.quotient_degree_factor - 1
+    num_sldc_polys = len(local_lookup_zs) - 1
+    lut_degree = -(-num_lut_slots // num_sldc_polys)
+    w = vars.local_wire
+    z_re, next_z_re = local_lookup_zs[0], next_lookup_zs[0]
+    z_x, z_gx = local_lookup_zs[1:], next_lookup_zs[1:]
+    d_a, d_b, d_alpha, d_delta = deltas
+    looked = [w(3 * s) + w(3 * s + 1) * d_a for s in range(num_lut_slots)]        # Sum / LDC combos
+    looking = [w(2 * s) + w(2 * s + 1) * d_a for s in range(num_lu_slots)]
+    lookup = [w(3 * s) + w(3 * s + 1) * d_b for s in range(num_lut_slots)]        # RE combos
+    out = [lookup_selectors[LOOKUP_LAST_LDC] * z_x[num_sldc_polys - 1],           # last LDC
+           lookup_selectors[LOOKUP_INIT_SRE] * z_x[0],                            # initial Sum
+           lookup_selectors[LOOKUP_INIT_SRE] * z_re]                              # initial RE
+    for r in range(LOOKUP_START_END, cd.num_lookup_selectors):                    # final RE, one per table
+        out.append(lookup_selectors[r] * (z_re - lut_re_poly_evals[r - LOOKUP_START_END]))
+    cur_sum = next_z_re                                                           # RE row transition
+    for elt in lookup:
+        cur_sum = cur_sum * d_delta + elt
+    out.append(lookup_selectors[LOOKUP_TRANS_SRE] * (z_re - cur_sum))
+    for poly in range(num_sldc_polys):
+        lut_rng = range(poly * lut_degree, min((poly + 1) * lut_degree, num_lut_slots))
+        lu_rng = range(poly * lu_degree, min((poly + 1) * lu_degree, num_lu_slots))
+        lut_f = {i: d_alpha - looked[i] for i in lut_rng}
+        lu_f = {i: d_alpha - looking[i] for i in lu_rng}
+        lut_prod = product([lut_f[i] for i in lut_rng])
+        lu_prod = product([lu_f[i] for i in lu_rng])
+        lu_sum_prods = None                                                        # sum_i prod_{j != i} (alpha - combo_j)
+        for i in lu_rng:
+            t = product([lu_f[j] for j in lu_rng if j != i])
+            lu_sum_prods = t if lu_sum_prods is None else lu_sum_prods + t
+        lut_sum_prods_with_mul = None                                              # sum_i mult_i prod_{j != i} (...)
+        for i in lut_rng:
+            t = w(3 * i + 2) * product([lut_f[j] for j in lut_rng if j != i])
+            lut_sum_prods_with_mul = t if lut_sum_prods_with_mul is None else lut_sum_prods_with_mul + t
+        prev = z_gx[num_sldc_polys - 1] if poly == 0 else z_x[poly - 1]
+        diff = z_x[poly] - prev
+        sum_transition = lut_prod * diff
+        if lut_sum_prods_with_mul is not None:
+            sum_transition = sum_transition - lut_sum_prods_with_mul
+        ldc_transition = lu_prod * diff
+        if lu_sum_prods is not None:
+            ldc_transition = ldc_transition + lu_sum_prods
+        out.append(lookup_selectors[LOOKUP_TRANS_SRE] * sum_transition)
+        out.append(lookup_selectors[LOOKUP_TRANS_LDC] * ldc_transition)
+    return out
+
+
 def vanishing_program(cd):
     """eval_vanishing_poly_base_batch (plonk/vanishing_poly.rs:167-340) recorded for one point. Bound constants:
-    public_inputs_hash (4), betas (num_challenges), gammas (num_challenges). Term numbers follow the reference's order:
-    vanishing_z_1_terms, vanishing_partial_products_terms, gate constraint terms."""
+    public_inputs_hash (4), betas (num_challenges), gammas (num_challenges), then with lookups the deltas
+    (NUM_COINS_LOOKUP per challenge) and the tables' RE evaluations (per challenge, per table). Term numbers follow the
+    reference's order: vanishing_z_1_terms, vanishing_partial_products_terms, vanishing_all_lookup_terms, gate constraints."""
     cfg = cd.config
     nc, nr = cfg.num_challenges, cfg.num_routed_wires
-    b = VanishingBuilder(4 + 2 * nc)
+    n_luts = len(cd.luts)
+    b = VanishingBuilder(4 + 2 * nc + (nc * (NUM_COINS_LOOKUP + n_luts) if n_luts else 0))
     vars = EvaluationVarsBase(b, cfg.num_wires, cd.num_constants)
     num_selectors = cd.selectors_info.num_selectors()
     # evaluate_gate_constraints_base_batch (vanishing_poly.rs:702-728) with Gate::eval_filtered_base_batch (gate.rs:159-185)
@@ -1186,7 +1337,7 @@ def vanishing_program(cd):
         b.scope = ("gate", i)
         sel = cd.selectors_info.selector_indices[i]
         filt = compute_filter(b, i, cd.selectors_info.groups[sel], vars.local_constant(sel), num_selectors > 1)
-        res = gate.eval_unfiltered(vars.remove_prefix(num_selectors))
+        res = gate.eval_unfiltered(vars.remove_prefix(num_selectors + cd.num_lookup_selectors))
         assert len(res) <= cd.num_gate_constraints, "num_constraints() gave too low of a number"
         for j, r in enumerate(res):
             r = r if filt is None else r * filt
@@ -1211,18 +1362,44 @@ def vanishing_program(cd):
             num = b.product(numerators[k * max_degree:(k + 1) * max_degree])
             den = b.product(denominators[k * max_degree:(k + 1) * max_degree])
             b.term(nc + i * (num_prods + 1) + k, accs[k] * num - accs[k + 1] * den)
-    base = nc + nc * (num_prods + 1)
+    lookup_base = nc + nc * (num_prods + 1)
+    n_lookup = cd.num_lookup_terms()
+    for i in range(nc if n_luts else 0):                                  # vanishing_poly.rs:266-285
+        b.scope = ("lookup", i)
+        at = 4 + 2 * nc + i * NUM_COINS_LOOKUP
+        deltas = [b.bound(at + k) for k in range(NUM_COINS_LOOKUP)]
+        re_evals = [b.bound(4 + 2 * nc + nc * NUM_COINS_LOOKUP + i * n_luts + t) for t in range(n_luts)]
+        rng = cd.lookup_range(i)
+        terms = check_lookup_constraints(cd, vars, [b.local(ZS_PARTIAL_PRODUCTS, c) for c in rng],
+                                         [b.next(ZS_PARTIAL_PRODUCTS, c) for c in rng],
+                                         [vars.local_constant(num_selectors + r) for r in range(cd.num_lookup_selectors)],
+                                         deltas, re_evals, b.product)
+        assert len(terms) == n_lookup
+        for k, t in enumerate(terms):
+            b.term(lookup_base + i * n_lookup + k, t)
+    base = lookup_base + nc * n_lookup
     for j, t in enumerate(constraint_terms):
         if t is not None:
             b.term(base + j, t)
     # evaluation order: the challenges' checks of one wire chunk next to each other (they share the chunk's k_i x)
     b.term_order = (list(range(nc)) + [nc + i * (num_prods + 1) + k for k in range(num_prods + 1) for i in range(nc)]
-                    + [base + j for j, t in enumerate(constraint_terms) if t is not None])
+                    + list(range(lookup_base, base)) + [base + j for j, t in enumerate(constraint_terms) if t is not None])
     return b
 
 
+def program_constants(common_data, b, public_inputs_hash, betas, gammas, deltas=()):
+    """The constant table of one evaluation of the vanishing program `b`: the values bound per proof
+    (public_inputs_hash, betas, gammas, deltas, lut_re_poly_evals) followed by the program's literals."""
+    nc = common_data.config.num_challenges
+    bound = [int(v) % F.ORDER for v in list(public_inputs_hash) + list(betas) + list(gammas) + list(deltas)]
+    for i in range(nc if common_data.luts else 0):   # lut_re_poly_evals (prover.rs:653-681): per challenge and table
+        bound += common_data.lut_re_poly_evals(deltas[NUM_COINS_LOOKUP * i:NUM_COINS_LOOKUP * (i + 1)])
+    assert len(bound) == b.num_bound
+    return np.array(bound + b.consts[b.num_bound:], dtype=np.uint64)
+
+
 def compute_quotient_polys(common_data, constants_sigmas_commitment, public_inputs_hash, wires_commitment,
-                           zs_partial_products_commitment, betas, gammas, alphas):
+                           zs_partial_products_commitment, betas, gammas, alphas, deltas=()):
     """compute_quotient_polys (plonk/prover.rs:609-815) on the device: a torch int64 CUDA tensor (num_challenges, size) of
     quotient-polynomial coefficients, size = n << log2_ceil(quotient_degree_factor). The three PolynomialBatch handles
     stay where they are; nothing but the program and the challenges crosses PCIe."""
@@ -1233,15 +1410,18 @@ def compute_quotient_polys(common_data, constants_sigmas_commitment, public_inpu
     if not (len(betas) == len(gammas) == len(alphas) == nc) or len(public_inputs_hash) != 4:
         raise N.ShapeError("expected %d betas, gammas, alphas and a 4-element public_inputs_hash" % nc)
     commits = [constants_sigmas_commitment, wires_commitment, zs_partial_products_commitment]
-    expect = [common_data.num_constants + cfg.num_routed_wires, cfg.num_wires, nc * (1 + common_data.num_partial_products)]
+    n_luts = len(common_data.luts)
+    if len(deltas) != (NUM_COINS_LOOKUP * nc if n_luts else 0):
+        raise N.ShapeError("expected %d lookup challenges (deltas)" % (NUM_COINS_LOOKUP * nc if n_luts else 0))
+    expect = [common_data.num_constants + cfg.num_routed_wires, cfg.num_wires,
+              nc * (1 + common_data.num_partial_products + common_data.num_lookup_polys)]
     for c, w in zip(commits, expect):
         if c.num_polys != w or c.degree_log != common_data.degree_bits:
             raise N.ShapeError("commitment with %d polynomials of degree 2^%d, expected %d of 2^%d"
                                % (c.num_polys, c.degree_log, w, common_data.degree_bits))
     b = common_data.vanishing_program()
     prog, _ = b.compile()
-    bound = [int(v) % F.ORDER for v in list(public_inputs_hash) + list(betas) + list(gammas)]
-    consts = np.array(bound + b.consts[b.num_bound:], dtype=np.uint64)
+    consts = program_constants(common_data, b, public_inputs_hash, betas, gammas, deltas)
     al = np.array([int(a) % F.ORDER for a in alphas], dtype=np.uint64)
     qdf = common_data.quotient_degree_factor
     size = (1 << common_data.degree_bits) << (qdf - 1).bit_length()

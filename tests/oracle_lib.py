@@ -561,7 +561,9 @@ class GloCircuit(C.Structure):
     _fields_ = [("num_wires", C.c_uint32), ("num_routed_wires", C.c_uint32), ("num_constants", C.c_uint32),
                 ("num_challenges", C.c_uint32), ("quotient_degree_factor", C.c_uint32), ("num_selectors", C.c_uint32),
                 ("num_partial_products", C.c_uint32), ("num_gate_constraints", C.c_uint32),
-                ("gates", C.POINTER(GloGate)), ("n_gates", C.c_size_t), ("k_is", u64p)]
+                ("gates", C.POINTER(GloGate)), ("n_gates", C.c_size_t), ("k_is", u64p),
+                ("num_lookup_selectors", C.c_uint32), ("num_lookup_polys", C.c_uint32), ("n_luts", C.c_size_t),
+                ("lut_len", u32p), ("lut_inp", u64p), ("lut_out", u64p)]
 
 
 (GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON, GATE_ARITHMETIC_EXTENSION, GATE_MUL_EXTENSION,
@@ -569,7 +571,8 @@ class GloCircuit(C.Structure):
  GATE_COSET_INTERPOLATION) = range(14)
 
 
-def plonk_quotient(circuit, constants_sigmas, wires, zs_partial_products, public_inputs_hash, betas, gammas, alphas):
+def plonk_quotient(circuit, constants_sigmas, wires, zs_partial_products, public_inputs_hash, betas, gammas, alphas,
+                   deltas=()):
     """compute_quotient_polys of a plonky2 circuit. circuit: dict(num_wires, num_routed_wires, num_constants,
     num_challenges, quotient_degree_factor, num_selectors, num_partial_products, num_gate_constraints, k_is,
     gates=[(kind, param, selector_index, group_start, group_end)] in CommonCircuitData.gates order); the commitments
@@ -585,15 +588,23 @@ def plonk_quotient(circuit, constants_sigmas, wires, zs_partial_products, public
               "num_partial_products", "num_gate_constraints"):
         setattr(cd, f, int(circuit[f]))
     cd.gates, cd.n_gates, cd.k_is = gates, len(circuit["gates"]), ptr(k_is)
+    luts = circuit.get("luts", [])
+    lut_len = np.array([len(t) for t in luts] + [0], dtype=np.uint32)
+    lut_inp = np.array([p[0] for t in luts for p in t] + [0], dtype=np.uint64)
+    lut_out = np.array([p[1] for t in luts for p in t] + [0], dtype=np.uint64)
+    cd.num_lookup_selectors, cd.num_lookup_polys = circuit.get("num_lookup_selectors", 0), circuit.get("num_lookup_polys", 0)
+    cd.n_luts, cd.lut_len, cd.lut_inp, cd.lut_out = len(luts), lut_len.ctypes.data_as(u32p), ptr(lut_inp), ptr(lut_out)
+    de = np.array([int(x) for x in deltas] + [0], dtype=np.uint64)
     pih = np.array([int(x) for x in public_inputs_hash], dtype=np.uint64)
     be, ga, al = (np.array([int(x) for x in v], dtype=np.uint64) for v in (betas, gammas, alphas))
     qd_bits = (int(circuit["quotient_degree_factor"]) - 1).bit_length()
     out = np.zeros((len(al), wires.n << qd_bits), dtype=np.uint64)
     L = lib()
     L.glo_plonk_quotient.restype = C.c_int
-    L.glo_plonk_quotient.argtypes = [C.POINTER(GloCircuit), C.c_void_p, C.c_void_p, C.c_void_p, u64p, u64p, u64p, u64p, u64p]
+    L.glo_plonk_quotient.argtypes = [C.POINTER(GloCircuit), C.c_void_p, C.c_void_p, C.c_void_p, u64p, u64p, u64p, u64p, u64p,
+                                     u64p]
     rc = L.glo_plonk_quotient(C.byref(cd), constants_sigmas.h, wires.h, zs_partial_products.h, ptr(pih), ptr(be), ptr(ga),
-                              ptr(al), ptr(out))
+                              ptr(de), ptr(al), ptr(out))
     if rc != 0:
         raise RuntimeError("oracle plonk quotient rc=%d" % rc)
     return out

@@ -250,6 +250,7 @@ def oracle_gate_kind(g):
                                  getattr(g, "num_extra_constants", 0)),
             "ExponentiationGate": (OL.GATE_EXPONENTIATION, getattr(g, "num_power_bits", 0), 0),
             "CosetInterpolationGate": (OL.GATE_COSET_INTERPOLATION, getattr(g, "subgroup_bits", 0), getattr(g, "_degree", 0)),
+            "LookupGate": (OL.GATE_NOOP, 0, 0), "LookupTableGate": (OL.GATE_NOOP, 0, 0),   # no constraints of their own
             }[name]
 
 
@@ -259,14 +260,16 @@ class FibonacciCircuit:
     constraints); NoopGate rows pad to 2^degree_bits. Unconstrained wires carry random values."""
 
     def __init__(self, plonk, config, degree_bits, seed=1, arithmetic_rows=None, break_gate=False, break_copy=False,
-                 poseidon_rows=0, break_poseidon=False, extra=(), break_extra=None):
+                 poseidon_rows=0, break_poseidon=False, extra=(), break_extra=None, lookups=False, break_lookup=None):
         rng = np.random.default_rng(seed)
         n = 1 << degree_bits
         self.config, self.n = config, n
         arith = plonk.ArithmeticGate.new_from_config(config)
         num_ops = arith.num_ops
-        arithmetic_rows = arithmetic_rows if arithmetic_rows is not None else n - 5 - poseidon_rows - len(extra)
-        assert 2 + arithmetic_rows + poseidon_rows + len(extra) <= n
+        n_lookup_rows = 4 if lookups else 0      # two LookupGate rows, then two LookupTableGate rows
+        arithmetic_rows = (arithmetic_rows if arithmetic_rows is not None
+                           else n - 5 - poseidon_rows - len(extra) - n_lookup_rows)
+        assert 2 + arithmetic_rows + poseidon_rows + len(extra) + n_lookup_rows < n
         extra_rows = [extra_gate_row(plonk, config, name, rng) for name in extra]
         self.extra_info = [r[3] if len(r) > 3 else None for r in extra_rows]
         extra_rows = [r[:3] for r in extra_rows]
@@ -275,8 +278,19 @@ class FibonacciCircuit:
         instances += [(arith, [1, 1])] * arithmetic_rows
         instances += [(plonk.PoseidonGate(), [])] * poseidon_rows
         instances += [(g, consts) for g, consts, _ in extra_rows]
+        luts, lookup_rows = [], []
+        if lookups:
+            # rows are "upside down" (circuit_builder.rs:75-87): LookupGate rows [last_lu, last_lut), table rows
+            # [last_lut, first_lut], table entry e at row first_lut - e / slots, slot e % slots, padded with entry 0
+            last_lu = len(instances)
+            last_lut, first_lut = last_lu + 2, last_lu + 3
+            instances += [(plonk.LookupGate.new_from_config(config), [])] * 2
+            instances += [(plonk.LookupTableGate.new_from_config(config), [])] * 2
+            luts = [[(3 * e + 1, (e * e + 7) & 0xFFFF) for e in range(30)]]
+            lookup_rows = [(last_lu, last_lut, first_lut)]
         instances += [(plonk.NoopGate(), [])] * (n - len(instances))
-        self.common, self.constant_vecs = plonk.CommonCircuitData.from_gate_instances(config, instances)
+        self.common, self.constant_vecs = plonk.CommonCircuitData.from_gate_instances(config, instances, luts, lookup_rows)
+        self.lookup_rows = lookup_rows
         self.public_inputs_hash = [int(v) for v in rnd(rng, 4)]
         wires = rnd(rng, (config.num_wires, n))
         wires[0:4, 0] = self.public_inputs_hash
@@ -321,6 +335,23 @@ class FibonacciCircuit:
             if break_extra == q:
                 k = max(ew)
                 wires[k, r] = (int(wires[k, r]) + 1) % P
+        if lookups:
+            lut = luts[0]
+            lu_slots, lut_slots = config.num_routed_wires // 2, config.num_routed_wires // 3
+            padded = lut + [lut[0]] * ((lut_slots - len(lut) % lut_slots) % lut_slots)
+            counts = [0] * len(padded)
+            for r in range(last_lu, last_lut):
+                for s_ in range(lu_slots):
+                    e = int(rnd(rng)) % len(lut) if (r + s_) % 5 else 0       # unused slots look up entry 0
+                    counts[e] += 1
+                    wires[2 * s_, r], wires[2 * s_ + 1, r] = lut[e]
+            for e, (a, b_) in enumerate(padded):
+                r, s_ = first_lut - e // lut_slots, e % lut_slots
+                wires[3 * s_, r], wires[3 * s_ + 1, r], wires[3 * s_ + 2, r] = a, b_, counts[e]
+            if break_lookup == "pair":       # a looking pair that is not in the table
+                wires[1, last_lu] = (int(wires[1, last_lu]) + 1) % P
+            if break_lookup == "table":      # a table row that differs from the committed table
+                wires[4, last_lut] = (int(wires[4, last_lut]) + 1) % P
         if break_poseidon:  # one partial-round S-box input off by one
             r = 2 + arithmetic_rows
             k = plonk.PoseidonGate.wire_partial_sbox(7)
@@ -362,10 +393,11 @@ class FibonacciCircuit:
         return dict(num_wires=cfg.num_wires, num_routed_wires=cfg.num_routed_wires, num_constants=cd.num_constants,
                     num_challenges=cfg.num_challenges, quotient_degree_factor=cd.quotient_degree_factor,
                     num_selectors=cd.selectors_info.num_selectors(), num_partial_products=cd.num_partial_products,
-                    num_gate_constraints=cd.num_gate_constraints, k_is=cd.k_is, gates=gates)
+                    num_gate_constraints=cd.num_gate_constraints, k_is=cd.k_is, gates=gates, luts=cd.luts,
+                    num_lookup_selectors=cd.num_lookup_selectors, num_lookup_polys=cd.num_lookup_polys)
 
-    def oracle_zs_partial_products(self, oracle, betas, gammas):
-        """[plonk_z_vecs, partial_products.concat()] (plonk/prover.rs:227-232) from the oracle's restatement."""
+    def oracle_zs_partial_products(self, oracle, betas, gammas, deltas=()):
+        """[plonk_z_vecs, partial_products.concat(), lookup polys] (plonk/prover.rs:227-245) from the oracle's restatements."""
         cfg = self.config
         zs, pps = [], []
         for beta, gamma in zip(betas, gammas):
@@ -373,4 +405,8 @@ class FibonacciCircuit:
                                                  self.common.quotient_degree_factor)
             zs.append(out[-1])
             pps += list(out[:-1])
-        return np.stack(zs + pps)
+        lk = []
+        for c in range(len(betas) if self.common.luts else 0):   # compute_all_lookup_polys (prover.rs:579-607)
+            lk += list(oracle.lookup_polys(self.wires, cfg.num_routed_wires, cfg.max_quotient_degree_factor,
+                                           deltas[4 * c:4 * c + 4], self.lookup_rows))
+        return np.stack(zs + pps + lk)

@@ -34,6 +34,8 @@ SHAPES = [
                            "CosetInterpolationGate")),
 ]
 NUM_EXTRA = len(SHAPES[5][6])
+# ... plus a lookup table of 30 entries on two LookupTableGate rows and 80 lookups on two LookupGate rows
+SHAPES.append(SHAPES[5] + (True,))
 
 
 def _plonk():
@@ -51,6 +53,8 @@ def _circuit(shape, **kw):
         kw.setdefault("poseidon_rows", shape[5])
     if len(shape) > 6:
         kw.setdefault("extra", shape[6])
+    if len(shape) > 7:
+        kw.setdefault("lookups", shape[7])
     cfg = plonk.CircuitConfig(num_wires=nw, num_routed_wires=nr, max_quotient_degree_factor=qdf, rate_bits=rate_bits,
                               cap_height=1)
     return PC.FibonacciCircuit(plonk, cfg, degree_bits, seed=nw + qdf + len(shape), **kw)
@@ -61,11 +65,16 @@ def _challenges(seed, nc):
     return v[:nc], v[nc:2 * nc], v[2 * nc:]
 
 
-def _oracle_commits(oracle, c, betas, gammas):
+def _deltas(c, seed):
+    """NUM_COINS_LOOKUP lookup challenges per challenge round, none for circuits without lookups."""
+    return [int(x) for x in synth(seed ^ 0xD17A, (4 * c.config.num_challenges,))] if c.common.luts else []
+
+
+def _oracle_commits(oracle, c, betas, gammas, deltas=()):
     cfg = c.config
     cs = oracle.Commit(c.constants_sigmas, cfg.rate_bits, cfg.cap_height)
     w = oracle.Commit(c.wires, cfg.rate_bits, cfg.cap_height)
-    z = oracle.Commit(c.oracle_zs_partial_products(oracle, betas, gammas), cfg.rate_bits, cfg.cap_height)
+    z = oracle.Commit(c.oracle_zs_partial_products(oracle, betas, gammas, deltas), cfg.rate_bits, cfg.cap_height)
     return cs, w, z
 
 
@@ -76,7 +85,7 @@ def _ev(coeffs, x):
     return acc
 
 
-def _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas):
+def _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas, deltas=()):
     """eval_vanishing_poly (vanishing_poly.rs:29-164) at a base-field point, from the committed polynomials."""
     import plonk_circuits as PC
 
@@ -96,7 +105,7 @@ def _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas):
         for j in list(range(g0, g1)) + ([0xFFFFFFFF] if nsel > 1 else []):
             if j != i:
                 filt = filt * (j - s) % P_
-        k = consts_sigmas[nsel:]
+        k = consts_sigmas[nsel + cd.num_lookup_selectors:]
         if kind == 1:
             res = [k[t] - wires[t] for t in range(param)]
         elif kind == 2:
@@ -106,7 +115,7 @@ def _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas):
         elif kind == 0:
             res = []
         else:   # the product's own gate code, over numbers (the oracle restates these gates independently in C++)
-            pv = PC.PointVars(consts_sigmas, wires, c.public_inputs_hash).remove_prefix(nsel)
+            pv = PC.PointVars(consts_sigmas, wires, c.public_inputs_hash).remove_prefix(nsel + cd.num_lookup_selectors)
             res = [int(v) for v in cd.gates[i].eval_unfiltered(pv)]
         for t, r in enumerate(res):
             constraint_terms[t] = (constraint_terms[t] + r * filt) % P_
@@ -125,7 +134,21 @@ def _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas):
             for j in range(k * qdf, min((k + 1) * qdf, nr)):
                 a, b = a * num[j] % P_, b * den[j] % P_
             pp.append((accs[k] * a - accs[k + 1] * b) % P_)
-    terms = z1 + pp + constraint_terms
+    lk = []
+    for i in range(nc if cd.luts else 0):   # the product's check_lookup_constraints over numbers (the oracle restates it in C++)
+        def product(vs):
+            acc = PC.Fp(1)
+            for v in vs:
+                acc = acc * v
+            return acc
+        plonk = _plonk()
+        rng = cd.lookup_range(i)
+        d = deltas[4 * i:4 * i + 4]
+        lk += [int(v) for v in plonk.check_lookup_constraints(
+            cd, PC.PointVars(consts_sigmas, wires, c.public_inputs_hash), [PC.Fp(zs_pp[k]) for k in rng],
+            [PC.Fp(zs_pp_next[k]) for k in rng], [PC.Fp(consts_sigmas[nsel + r]) for r in range(cd.num_lookup_selectors)],
+            d, cd.lut_re_poly_evals(d), product)]
+    terms = z1 + pp + lk + constraint_terms
     return [sum(pow(al, t, P_) * v for t, v in enumerate(terms)) % P_ for al in alphas], zh
 
 
@@ -134,13 +157,14 @@ def test_oracle_quotient_passes_the_verifier_identity(oracle, shape):
     c = _circuit(shape)
     nc = c.config.num_challenges
     betas, gammas, alphas = _challenges(0x510 + shape[0], nc)
-    cs, w, z = _oracle_commits(oracle, c, betas, gammas)
-    q = oracle.plonk_quotient(c.oracle_circuit(), cs, w, z, c.public_inputs_hash, betas, gammas, alphas)
+    deltas = _deltas(c, 0x511)
+    cs, w, z = _oracle_commits(oracle, c, betas, gammas, deltas)
+    q = oracle.plonk_quotient(c.oracle_circuit(), cs, w, z, c.public_inputs_hash, betas, gammas, alphas, deltas)
     qdf, n = c.common.quotient_degree_factor, c.n
     assert q.shape == (nc, n << (qdf - 1).bit_length())
     assert not q[:, qdf * n:].any()      # trim_to_len(quotient_degree) succeeds (prover.rs:327-331)
     for zeta in (int(synth(0x520 + shape[0], (1,))[0]), 3):
-        want, zh = _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas)
+        want, zh = _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas, deltas)
         for i in range(nc):
             # reduce_with_powers(chunks at zeta, zeta^n) == the unsplit polynomial at zeta
             chunks = [_ev(q[i, k * n:(k + 1) * n], zeta) for k in range(qdf)]
@@ -211,12 +235,13 @@ def test_vanishing_program_through_the_kernel_source_on_host_matches_oracle(orac
     cfg, cd = c.config, c.common
     nc = cfg.num_challenges
     betas, gammas, alphas = _challenges(0x540 + shape[0], nc)
-    cs, w, z = _oracle_commits(oracle, c, betas, gammas)
-    want = oracle.plonk_quotient(c.oracle_circuit(), cs, w, z, c.public_inputs_hash, betas, gammas, alphas)
+    deltas = _deltas(c, 0x541)
+    cs, w, z = _oracle_commits(oracle, c, betas, gammas, deltas)
+    want = oracle.plonk_quotient(c.oracle_circuit(), cs, w, z, c.public_inputs_hash, betas, gammas, alphas, deltas)
     b = cd.vanishing_program()
     prog, n_regs = b.compile()
     assert n_regs <= 64            # the schedule keeps the register set small (L1-resident on the device)
-    consts = np.array(list(c.public_inputs_hash) + betas + gammas + b.consts[b.num_bound:], dtype=np.uint64)
+    consts = _plonk().program_constants(cd, b, c.public_inputs_hash, betas, gammas, deltas)
     ldes = [np.ascontiguousarray(o.leaves.T) for o in (cs, w, z)]     # column-major LDE in leaf order, like the device
     ptrs = (C.POINTER(C.c_uint64) * 3)(*[a.ctypes.data_as(C.POINTER(C.c_uint64)) for a in ldes])
     strides = (C.c_size_t * 3)(*[a.shape[1] for a in ldes])
@@ -232,6 +257,21 @@ def test_vanishing_program_through_the_kernel_source_on_host_matches_oracle(orac
     assert rc == 0
     got = np.stack([oracle.coset_ifft(v, 14293326489335486720) for v in vals])   # .coset_ifft(F::coset_shift())
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("broken", ["pair", "table"])
+def test_lookup_argument_rejects_a_wrong_witness(oracle, broken):
+    """A looking pair that is not in the table, or a table row that differs from the committed table (get_lut_poly): the
+    oracle's quotient no longer satisfies the verifier identity."""
+    c = _circuit(SHAPES[6], break_lookup=broken)
+    nc = c.config.num_challenges
+    betas, gammas, alphas = _challenges(0x580, nc)
+    deltas = _deltas(c, 0x581)
+    cs, w, z = _oracle_commits(oracle, c, betas, gammas, deltas)
+    q = oracle.plonk_quotient(c.oracle_circuit(), cs, w, z, c.public_inputs_hash, betas, gammas, alphas, deltas)
+    zeta = int(synth(0x582, (1,))[0])
+    want, zh = _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas, deltas)
+    assert any(want[i] != zh * _ev(q[i], zeta) % P_ for i in range(nc))
 
 
 def test_coset_interpolation_row_holds_the_true_interpolant():
@@ -288,7 +328,7 @@ def pb():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[1], (135, 80, 8, 3, 7), (135, 80, 8, 3, 6, 20), SHAPES[5]])
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[1], (135, 80, 8, 3, 7), (135, 80, 8, 3, 6, 20), SHAPES[5], SHAPES[6]])
 def test_plonk_quotient_on_device_matches_oracle(pb, oracle, shape):
     """The prover's third phase without leaving the device (plonk/prover.rs:220-352): wires + constants_sigmas
     commitments -> Z / partial products commitment (device) -> quotient polynomials (device, LDEs read in place) ->
@@ -302,16 +342,30 @@ def test_plonk_quotient_on_device_matches_oracle(pb, oracle, shape):
     cfg, cd = c.config, c.common
     nc, nr = cfg.num_challenges, cfg.num_routed_wires
     betas, gammas, alphas = _challenges(0x550 + shape[0], nc)
-    ocs, ow, oz = _oracle_commits(oracle, c, betas, gammas)
-    want = oracle.plonk_quotient(c.oracle_circuit(), ocs, ow, oz, c.public_inputs_hash, betas, gammas, alphas)
+    deltas = _deltas(c, 0x551)
+    ocs, ow, oz = _oracle_commits(oracle, c, betas, gammas, deltas)
+    want = oracle.plonk_quotient(c.oracle_circuit(), ocs, ow, oz, c.public_inputs_hash, betas, gammas, alphas, deltas)
     cs = pb.PolynomialBatch.from_values(c.constants_sigmas, cfg.rate_bits, False, cfg.cap_height)
     w = pb.PolynomialBatch.from_values(c.wires, cfg.rate_bits, False, cfg.cap_height)
     wires_dev = torch.from_numpy(c.wires[:nr].view(np.int64)).cuda()
     sigmas_dev = torch.from_numpy(c.sigmas.view(np.int64)).cuda()
-    z = commit_zs_partial_products(wires_dev, sigmas_dev, cd.k_is, betas, gammas, cd.quotient_degree_factor, cfg.rate_bits,
-                                   cfg.cap_height)
+    if cd.luts:
+        # with lookups the second commitment also holds the RE / Sum / LDC columns (prover.rs:227-245): Z and partial
+        # products from gl_partial_products_and_zs, the lookup columns from gl_lookup_polys, committed together
+        from plonky2_b200.prover import compute_all_lookup_polys, wires_permutation_partial_products_and_zs
+
+        zs, pps = [], []
+        for beta, gamma in zip(betas, gammas):
+            out = wires_permutation_partial_products_and_zs(c.wires[:nr], c.sigmas, cd.k_is, beta, gamma, cd.quotient_degree_factor)
+            zs.append(out[-1])
+            pps += list(out[:-1])
+        lk = compute_all_lookup_polys(c.wires, nr, cfg.max_quotient_degree_factor, deltas, c.lookup_rows, nc)
+        z = pb.PolynomialBatch.from_values(np.concatenate([np.stack(zs + pps), lk]), cfg.rate_bits, False, cfg.cap_height)
+    else:
+        z = commit_zs_partial_products(wires_dev, sigmas_dev, cd.k_is, betas, gammas, cd.quotient_degree_factor, cfg.rate_bits,
+                                       cfg.cap_height)
     assert np.array_equal(z.merkle_tree.cap.hashes, oz.cap)
-    q = plonk.compute_quotient_polys(cd, cs, c.public_inputs_hash, w, z, betas, gammas, alphas)
+    q = plonk.compute_quotient_polys(cd, cs, c.public_inputs_hash, w, z, betas, gammas, alphas, deltas)
     got = q.cpu().numpy().view(np.uint64)
     assert np.array_equal(got, want)
     qc = plonk.commit_quotient_polys(cd, q)
