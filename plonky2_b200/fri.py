@@ -27,6 +27,21 @@ class FriConfig:
     def rate(self):
         return 1.0 / (1 << self.rate_bits)
 
+    def observe(self, challenger):
+        """FriConfig::observe (fri/mod.rs:73-79); the strategy as FriReductionStrategy::serialize
+        (reduction_strategies.rs:59-80)."""
+        challenger.observe_element(self.rate_bits)
+        challenger.observe_element(self.cap_height)
+        challenger.observe_element(self.proof_of_work_bits)
+        kind = self.reduction_strategy[0]
+        if kind == "Fixed":
+            challenger.observe_elements([0] + list(self.reduction_strategy[1]))
+        elif kind == "ConstantArityBits":
+            challenger.observe_elements([1, self.reduction_strategy[1], self.reduction_strategy[2]])
+        else:
+            raise ValueError("unsupported reduction strategy %r" % (kind,))
+        challenger.observe_element(self.num_query_rounds)
+
     def fri_params(self, degree_bits, hiding):
         arity = reduction_arity_bits(self.reduction_strategy, degree_bits, self.rate_bits, self.cap_height,
                                      self.num_query_rounds)
@@ -55,6 +70,13 @@ class FriParams:
     hiding: bool
     degree_bits: int
     reduction_arity_bits: List[int]
+
+    def observe(self, challenger):
+        """FriParams::observe (fri/mod.rs:145-157)."""
+        self.config.observe(challenger)
+        challenger.observe_element(int(self.hiding))
+        challenger.observe_element(self.degree_bits)
+        challenger.observe_elements(self.reduction_arity_bits)
 
     def total_arities(self):
         return sum(self.reduction_arity_bits)

@@ -1456,3 +1456,152 @@ def commit_quotient_polys(common_data, quotient_polys, ctx=None):
         L.gl_commit_destroy(h)
         raise
     return PolynomialBatch(h, ctx, B, common_data.degree_bits, cfg.rate_bits, cfg.cap_height, False)
+
+
+# ------------------------------------------------------------------ prove (plonk/prover.rs:113-360)
+class ProverOnlyCircuitData:
+    """The fields of ProverOnlyCircuitData (plonk/circuit_data.rs:330-370) prove() reads: the constants/sigmas commitment
+    (resident on the device since circuit build), the sigma value columns, the circuit digest, the FRI parameters."""
+
+    def __init__(self, constants_sigmas_commitment, sigmas, circuit_digest, fri_params):
+        self.constants_sigmas_commitment, self.sigmas = constants_sigmas_commitment, sigmas
+        self.circuit_digest, self.fri_params = [int(x) for x in circuit_digest], fri_params
+
+
+def _le_words(arr):
+    return np.ascontiguousarray(arr, dtype="<u8").tobytes()
+
+
+class Proof:
+    """Proof<F, C, D> (plonk/proof.rs:26-40)."""
+
+    def __init__(self, wires_cap, plonk_zs_partial_products_cap, quotient_polys_cap, openings, opening_proof):
+        self.wires_cap, self.plonk_zs_partial_products_cap = wires_cap, plonk_zs_partial_products_cap
+        self.quotient_polys_cap, self.openings, self.opening_proof = quotient_polys_cap, openings, opening_proof
+
+    def to_bytes(self):
+        """write_proof (util/serialization/mod.rs:1977-1987) with write_opening_set (:1436-1449)."""
+        o = self.openings
+        out = _le_words(self.wires_cap.hashes) + _le_words(self.plonk_zs_partial_products_cap.hashes)
+        out += _le_words(self.quotient_polys_cap.hashes)
+        for part in (o.constants, o.plonk_sigmas, o.wires, o.plonk_zs, o.plonk_zs_next, o.lookup_zs, o.lookup_zs_next,
+                     o.partial_products, o.quotient_polys):
+            out += _le_words(part)
+        return out + self.opening_proof.to_bytes()
+
+
+class ProofWithPublicInputs:
+    """ProofWithPublicInputs (plonk/proof.rs:82-88)."""
+
+    def __init__(self, proof, public_inputs):
+        self.proof, self.public_inputs = proof, [int(x) % F.ORDER for x in public_inputs]
+
+    def to_bytes(self):
+        """write_proof_with_public_inputs (util/serialization/mod.rs:2001-2015)."""
+        pis = np.array(self.public_inputs, dtype=np.uint64)
+        return self.proof.to_bytes() + _le_words(np.array([len(pis)], dtype=np.uint64)) + _le_words(pis)
+
+
+def get_fri_instance(cd, zeta):
+    """CommonCircuitData::get_fri_instance (plonk/circuit_data.rs:530-660): every polynomial at zeta, the Z's and the
+    lookup polynomials also at g * zeta."""
+    from .fri import FriBatchInfo, FriInstanceInfo, FriOracleInfo, FriPolynomialInfo
+
+    cfg = cd.config
+    nc = cfg.num_challenges
+    n_pre = cd.num_constants + cfg.num_routed_wires                                   # num_preprocessed_polys
+    n_zs_pp, n_lookup = cd.num_zs_partial_products_polys(), nc * cd.num_lookup_polys
+    n_quot = nc * cd.quotient_degree_factor
+    lookup = FriPolynomialInfo.from_range(2, range(n_zs_pp, n_zs_pp + n_lookup))
+    all_polys = (FriPolynomialInfo.from_range(0, range(n_pre)) + FriPolynomialInfo.from_range(1, range(cfg.num_wires))
+                 + FriPolynomialInfo.from_range(2, range(n_zs_pp)) + FriPolynomialInfo.from_range(3, range(n_quot)) + lookup)
+    g = F.primitive_root_of_unity(cd.degree_bits)
+    zeta_next = F.ext_mul((g, 0), zeta)
+    oracles = [FriOracleInfo(n_pre, False), FriOracleInfo(cfg.num_wires, False), FriOracleInfo(n_zs_pp + n_lookup, False),
+               FriOracleInfo(n_quot, False)]
+    return FriInstanceInfo(oracles, [FriBatchInfo(zeta, all_polys),
+                                     FriBatchInfo(zeta_next, FriPolynomialInfo.from_range(2, range(nc)) + lookup)])
+
+
+def prove_with_witness(prover_data, common_data, wires, public_inputs, ctx=None):
+    """prove_with_partition_witness (plonk/prover.rs:132-360) from the full witness matrix `wires` (num_wires, n) -- the
+    generators' output -- to ProofWithPublicInputs, every array-sized step on the device: wires commitment, Z / partial
+    products (+ lookup) commitment, quotient polynomials from the LDEs in place and their commitment, the openings at
+    zeta and g zeta, the FRI opening proof. The transcript runs on the host exactly as in the reference.
+    zero_knowledge = false (no blinding)."""
+    import torch
+
+    from .challenger import Challenger
+    from .fri import prove_openings
+    from .hash import PoseidonHash
+    from .proof import OpeningSet
+    from .prover import commit_zs_partial_products, compute_all_lookup_polys, wires_permutation_partial_products_and_zs
+
+    ctx = ctx or N.default_context()
+    cd, cfg = common_data, common_data.config
+    nc, nr = cfg.num_challenges, cfg.num_routed_wires
+    has_lookup = bool(cd.luts)
+    wires = np.ascontiguousarray(wires, dtype=np.uint64)
+    if wires.shape != (cfg.num_wires, 1 << cd.degree_bits):
+        raise N.ShapeError("the witness must be (num_wires, n)")
+    public_inputs_hash = [int(x) for x in PoseidonHash.hash_no_pad(np.array(public_inputs, dtype=np.uint64), ctx)]
+    wires_commitment = PolynomialBatch.from_values(wires, cfg.rate_bits, False, cfg.cap_height, ctx=ctx)
+    commitments = [wires_commitment]
+    try:
+        challenger = Challenger()
+        prover_data.fri_params.observe(challenger)                     # observe the FRI config
+        challenger.observe_hash(prover_data.circuit_digest)            # observe the instance
+        challenger.observe_hash(public_inputs_hash)
+        challenger.observe_cap(wires_commitment.merkle_tree.cap)
+        betas = challenger.get_n_challenges(nc)
+        gammas = challenger.get_n_challenges(nc)
+        deltas = (betas + gammas + challenger.get_n_challenges(NUM_COINS_LOOKUP * nc - 2 * nc)) if has_lookup else []
+        if cd.quotient_degree_factor >= nr:
+            raise N.ShapeError("When the number of routed wires is smaller that the degree, we should change the logic to "
+                               "avoid computing partial products.")
+        if has_lookup:
+            # Z's, partial products and the RE / Sum / LDC columns are committed together (prover.rs:227-262)
+            zs, pps = [], []
+            for beta, gamma in zip(betas, gammas):
+                out = wires_permutation_partial_products_and_zs(wires[:nr], prover_data.sigmas, cd.k_is, beta, gamma,
+                                                                cd.quotient_degree_factor, ctx)
+                zs.append(out[-1])
+                pps += list(out[:-1])
+            lookup_polys = compute_all_lookup_polys(wires, nr, cfg.max_quotient_degree_factor, deltas, cd.lookup_rows, nc, ctx)
+            zs_commitment = PolynomialBatch.from_values(np.concatenate([np.stack(zs + pps), lookup_polys]), cfg.rate_bits,
+                                                        False, cfg.cap_height, ctx=ctx)
+        else:
+            dev = "cuda:%d" % ctx.device
+            wires_dev = torch.from_numpy(wires[:nr].view(np.int64)).to(dev)
+            sigmas_dev = torch.from_numpy(np.ascontiguousarray(prover_data.sigmas, dtype=np.uint64).view(np.int64)).to(dev)
+            torch.cuda.synchronize(dev)
+            zs_commitment = commit_zs_partial_products(wires_dev, sigmas_dev, cd.k_is, betas, gammas,
+                                                       cd.quotient_degree_factor, cfg.rate_bits, cfg.cap_height, ctx)
+        commitments.append(zs_commitment)
+        challenger.observe_cap(zs_commitment.merkle_tree.cap)
+        alphas = challenger.get_n_challenges(nc)
+        cs = prover_data.constants_sigmas_commitment
+        quotient_polys = compute_quotient_polys(cd, cs, public_inputs_hash, wires_commitment, zs_commitment, betas, gammas,
+                                                alphas, deltas)
+        quotient_commitment = commit_quotient_polys(cd, quotient_polys, ctx)
+        commitments.append(quotient_commitment)
+        challenger.observe_cap(quotient_commitment.merkle_tree.cap)
+        zeta = challenger.get_extension_challenge()
+        g = F.primitive_root_of_unity(cd.degree_bits)
+        if F.ext_pow(zeta, 1 << cd.degree_bits) == (1, 0):
+            raise N.NativeError("Opening point is in the subgroup.")
+        n_zs_pp = cd.num_zs_partial_products_polys()
+        openings = OpeningSet.new(zeta, g, cs, wires_commitment, zs_commitment, quotient_commitment,
+                                  constants_range=cd.constants_range(), sigmas_range=cd.sigmas_range(), zs_range=cd.zs_range(),
+                                  partial_products_range=cd.partial_products_range(),
+                                  lookup_range=range(n_zs_pp, n_zs_pp + nc * cd.num_lookup_polys))
+        for batch in openings.to_fri_openings():                       # Challenger::observe_openings
+            challenger.observe_elements(batch.reshape(-1))
+        opening_proof = prove_openings(get_fri_instance(cd, zeta), [cs, wires_commitment, zs_commitment, quotient_commitment],
+                                       challenger, prover_data.fri_params)
+        proof = Proof(wires_commitment.merkle_tree.cap, zs_commitment.merkle_tree.cap, quotient_commitment.merkle_tree.cap,
+                      openings, opening_proof)
+        return ProofWithPublicInputs(proof, public_inputs)
+    finally:
+        for c in commitments:
+            c.close()

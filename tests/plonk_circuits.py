@@ -260,7 +260,8 @@ class FibonacciCircuit:
     constraints); NoopGate rows pad to 2^degree_bits. Unconstrained wires carry random values."""
 
     def __init__(self, plonk, config, degree_bits, seed=1, arithmetic_rows=None, break_gate=False, break_copy=False,
-                 poseidon_rows=0, break_poseidon=False, extra=(), break_extra=None, lookups=False, break_lookup=None):
+                 poseidon_rows=0, break_poseidon=False, extra=(), break_extra=None, lookups=False, break_lookup=None,
+                 public_inputs=None):
         rng = np.random.default_rng(seed)
         n = 1 << degree_bits
         self.config, self.n = config, n
@@ -291,7 +292,11 @@ class FibonacciCircuit:
         instances += [(plonk.NoopGate(), [])] * (n - len(instances))
         self.common, self.constant_vecs = plonk.CommonCircuitData.from_gate_instances(config, instances, luts, lookup_rows)
         self.lookup_rows = lookup_rows
-        self.public_inputs_hash = [int(v) for v in rnd(rng, 4)]
+        self.public_inputs = public_inputs
+        if public_inputs is None:
+            self.public_inputs_hash = [int(v) for v in rnd(rng, 4)]
+        else:   # C::InnerHasher::hash_no_pad(&public_inputs), prover.rs:155
+            self.public_inputs_hash = [int(v) for v in OL.hash_no_pad(np.array(public_inputs, dtype=np.uint64))]
         wires = rnd(rng, (config.num_wires, n))
         wires[0:4, 0] = self.public_inputs_hash
         wires[0, 1], wires[1, 1] = f0, 1
@@ -410,3 +415,244 @@ class FibonacciCircuit:
             lk += list(oracle.lookup_polys(self.wires, cfg.num_routed_wires, cfg.max_quotient_degree_factor,
                                            deltas[4 * c:4 * c + 4], self.lookup_rows))
         return np.stack(zs + pps + lk)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The whole prover and verifier of plonky2 for these circuits, on the CPU, from the oracle's restatements:
+# prove_with_partition_witness (plonk/prover.rs:132-360) and verify_with_challenges (plonk/verifier.rs:40-120).
+class Fp2:
+    """F_{p^2} = F_p[X]/(X^2 - 7) as numbers, with base-field scalars accepted on either side (ints)."""
+    __slots__ = ("a", "b")
+
+    def __init__(self, a, b=0):
+        self.a, self.b = int(a) % P, int(b) % P
+
+    @staticmethod
+    def of(o):
+        return o if isinstance(o, Fp2) else Fp2(int(o))
+
+    def __add__(self, o):
+        o = Fp2.of(o)
+        return Fp2(self.a + o.a, self.b + o.b)
+
+    def __sub__(self, o):
+        o = Fp2.of(o)
+        return Fp2(self.a - o.a, self.b - o.b)
+
+    def __rsub__(self, o):
+        return Fp2.of(o) - self
+
+    def __mul__(self, o):
+        o = Fp2.of(o)
+        return Fp2(self.a * o.a + 7 * self.b * o.b, self.a * o.b + self.b * o.a)
+
+    __radd__, __rmul__ = __add__, __mul__
+
+    def inverse(self):
+        d = pow((self.a * self.a - 7 * self.b * self.b) % P, P - 2, P)
+        return Fp2(self.a * d, -self.b * d)
+
+    def __eq__(self, o):
+        o = Fp2.of(o)
+        return self.a == o.a and self.b == o.b
+
+    def __int__(self):
+        assert self.b == 0
+        return self.a
+
+    def tup(self):
+        return (self.a, self.b)
+
+
+class ExtPointVars:
+    """EvaluationVars over F_{p^2} numbers (plonk/vars.rs:14-20)."""
+
+    def __init__(self, constants, wires, public_inputs_hash, prefix=0):
+        self.c, self.w, self.pih, self.prefix = constants, wires, public_inputs_hash, prefix
+
+    def local_constant(self, i):
+        return self.c[self.prefix + i]
+
+    def local_wire(self, i):
+        return self.w[i]
+
+    def public_inputs_hash(self, i):
+        return Fp2(self.pih[i])
+
+    def remove_prefix(self, n):
+        return ExtPointVars(self.c, self.w, self.pih, self.prefix + n)
+
+
+def fri_batches(cd, zeta):
+    """get_fri_instance (plonk/circuit_data.rs:530-660) as the oracle's (point, [(oracle, polynomial)]) lists."""
+    import plonky2_b200.field as F
+
+    cfg = cd.config
+    nc = cfg.num_challenges
+    n_pre, n_zs_pp = cd.num_constants + cfg.num_routed_wires, cd.num_zs_partial_products_polys()
+    n_lookup, n_quot = nc * cd.num_lookup_polys, nc * cd.quotient_degree_factor
+    lookup = [(2, i) for i in range(n_zs_pp, n_zs_pp + n_lookup)]
+    all_polys = ([(0, i) for i in range(n_pre)] + [(1, i) for i in range(cfg.num_wires)] + [(2, i) for i in range(n_zs_pp)]
+                 + [(3, i) for i in range(n_quot)] + lookup)
+    g = F.primitive_root_of_unity(cd.degree_bits)
+    zeta_next = F.ext_mul((g, 0), zeta)
+    return [(zeta, all_polys), (zeta_next, [(2, i) for i in range(nc)] + lookup)], [n_pre, cfg.num_wires, n_zs_pp + n_lookup, n_quot]
+
+
+def observe_fri_params(ch, fri_cfg, degree_bits, arity_bits):
+    """FriParams::observe (fri/mod.rs:73-79,145-157) for a ConstantArityBits strategy, hiding = false."""
+    ch.observe_elements([fri_cfg.rate_bits, fri_cfg.cap_height, fri_cfg.proof_of_work_bits])
+    ch.observe_elements([1, fri_cfg.reduction_strategy[1], fri_cfg.reduction_strategy[2]])
+    ch.observe_element(fri_cfg.num_query_rounds)
+    ch.observe_elements([0, degree_bits] + list(arity_bits))
+
+
+def oracle_prove(oracle, c, circuit_digest, fri_cfg, public_inputs):
+    """prove_with_partition_witness with the oracle's pieces. Returns (proof bytes = write_proof_with_public_inputs,
+    parts) where parts carries what the verifier reads from the proof."""
+    cd, cfg = c.common, c.config
+    nc, nr, n = cfg.num_challenges, cfg.num_routed_wires, c.n
+    arity_bits = fri_cfg.fri_params(cd.degree_bits, False).reduction_arity_bits
+    public_inputs_hash = [int(x) for x in oracle.hash_no_pad(np.array(public_inputs, dtype=np.uint64))]
+    assert public_inputs_hash == c.public_inputs_hash
+    cs = oracle.Commit(c.constants_sigmas, cfg.rate_bits, cfg.cap_height)
+    wc = oracle.Commit(c.wires, cfg.rate_bits, cfg.cap_height)
+    ch = oracle.Challenger()
+    observe_fri_params(ch, fri_cfg, cd.degree_bits, arity_bits)
+    ch.observe_elements(circuit_digest)
+    ch.observe_elements(public_inputs_hash)
+    ch.observe_cap(wc.cap)
+    betas, gammas = ch.get_n_challenges(nc), ch.get_n_challenges(nc)
+    deltas = (betas + gammas + ch.get_n_challenges(2 * nc)) if cd.luts else []
+    zc = oracle.Commit(c.oracle_zs_partial_products(oracle, betas, gammas, deltas), cfg.rate_bits, cfg.cap_height)
+    ch.observe_cap(zc.cap)
+    alphas = ch.get_n_challenges(nc)
+    q = oracle.plonk_quotient(c.oracle_circuit(), cs, wc, zc, public_inputs_hash, betas, gammas, alphas, deltas)
+    qdf = cd.quotient_degree_factor
+    assert not q[:, qdf * n:].any(), "Quotient has failed, the vanishing polynomial is not divisible by Z_H"
+    chunks = np.concatenate([q[i, :qdf * n].reshape(qdf, n) for i in range(nc)])
+    qc = oracle.Commit(chunks, cfg.rate_bits, cfg.cap_height, is_coeffs=True)
+    ch.observe_cap(qc.cap)
+    zeta = ch.get_extension_challenge()
+    batches, num_polys = fri_batches(cd, zeta)
+    commits = [cs, wc, zc, qc]
+
+    def ev(commit, z):
+        return np.array([oracle.eval_poly_base_at_ext(p, z) for p in commit.coeffs], dtype=np.uint64).reshape(-1, 2)
+
+    zeta_next = batches[1][0]
+    cs_e, w_e, z_e, z_next, q_e = ev(cs, zeta), ev(wc, zeta), ev(zc, zeta), ev(zc, zeta_next), ev(qc, zeta)
+    n_zs_pp = cd.num_zs_partial_products_polys()
+    o = dict(constants=cs_e[:cd.num_constants], plonk_sigmas=cs_e[cd.num_constants:], wires=w_e, plonk_zs=z_e[:nc],
+             plonk_zs_next=z_next[:nc], partial_products=z_e[nc:n_zs_pp], quotient_polys=q_e, lookup_zs=z_e[n_zs_pp:],
+             lookup_zs_next=z_next[n_zs_pp:])
+    zeta_batch = np.concatenate([o["constants"], o["plonk_sigmas"], o["wires"], o["plonk_zs"], o["partial_products"],
+                                 o["quotient_polys"], o["lookup_zs"]])
+    next_batch = np.concatenate([o["plonk_zs_next"], o["lookup_zs_next"]])
+    ch.observe_elements(zeta_batch.reshape(-1))
+    ch.observe_elements(next_batch.reshape(-1))
+    params = oracle.make_params(cfg.rate_bits, cfg.cap_height, fri_cfg.proof_of_work_bits, fri_cfg.num_query_rounds, arity_bits)
+    fri_bytes = oracle.prove_openings(commits, batches, ch, params)
+
+    def le(a):
+        return np.ascontiguousarray(a, dtype="<u8").tobytes()
+
+    out = le(wc.cap) + le(zc.cap) + le(qc.cap)
+    for k in ("constants", "plonk_sigmas", "wires", "plonk_zs", "plonk_zs_next", "lookup_zs", "lookup_zs_next",
+              "partial_products", "quotient_polys"):
+        out += le(o[k])
+    out += fri_bytes + le(np.array([len(public_inputs)], dtype=np.uint64)) + le(np.array(public_inputs, dtype=np.uint64))
+    parts = dict(constants_sigmas_cap=cs.cap, wires_cap=wc.cap, zs_cap=zc.cap, quotient_cap=qc.cap, openings=o,
+                 fri_bytes=fri_bytes, public_inputs=list(public_inputs))
+    return out, parts
+
+
+def oracle_verify(oracle, plonk, c, circuit_digest, fri_cfg, parts):
+    """verify (plonk/verifier.rs:20-120): get_challenges (plonk/get_challenges.rs:26-90) replayed on a fresh transcript,
+    eval_vanishing_poly at zeta in F_{p^2} (vanishing_poly.rs:57-164; the gates' and the lookup argument's formulas are
+    the product's value-generic ones, here over F_{p^2} numbers), the quotient identity, then verify_fri_proof (the
+    oracle's). Returns None or the reason of the rejection."""
+    cd, cfg = c.common, c.config
+    nc, n = cfg.num_challenges, c.n
+    o = parts["openings"]
+    arity_bits = fri_cfg.fri_params(cd.degree_bits, False).reduction_arity_bits
+    public_inputs_hash = [int(x) for x in oracle.hash_no_pad(np.array(parts["public_inputs"], dtype=np.uint64))]
+    ch = oracle.Challenger()
+    observe_fri_params(ch, fri_cfg, cd.degree_bits, arity_bits)
+    ch.observe_elements(circuit_digest)
+    ch.observe_elements(public_inputs_hash)
+    ch.observe_cap(parts["wires_cap"])
+    betas, gammas = ch.get_n_challenges(nc), ch.get_n_challenges(nc)
+    deltas = (betas + gammas + ch.get_n_challenges(2 * nc)) if cd.luts else []
+    ch.observe_cap(parts["zs_cap"])
+    alphas = ch.get_n_challenges(nc)
+    ch.observe_cap(parts["quotient_cap"])
+    zeta = ch.get_extension_challenge()
+    zeta_batch = np.concatenate([o["constants"], o["plonk_sigmas"], o["wires"], o["plonk_zs"], o["partial_products"],
+                                 o["quotient_polys"], o["lookup_zs"]])
+    next_batch = np.concatenate([o["plonk_zs_next"], o["lookup_zs_next"]])
+    ch.observe_elements(zeta_batch.reshape(-1))
+    ch.observe_elements(next_batch.reshape(-1))
+
+    def E(arr):
+        return [Fp2(int(v[0]), int(v[1])) for v in arr]
+
+    x = Fp2(*zeta)
+    constants, sigmas, wires = E(o["constants"]), E(o["plonk_sigmas"]), E(o["wires"])
+    zs, zs_next, pps, quot = E(o["plonk_zs"]), E(o["plonk_zs_next"]), E(o["partial_products"]), E(o["quotient_polys"])
+    lk, lk_next = E(o["lookup_zs"]), E(o["lookup_zs_next"])
+    nsel = cd.selectors_info.num_selectors()
+    vars_ = ExtPointVars(constants, wires, public_inputs_hash)
+    constraint_terms = [Fp2(0)] * cd.num_gate_constraints                     # evaluate_gate_constraints
+    for i, gate in enumerate(cd.gates):
+        sel = cd.selectors_info.selector_indices[i]
+        s = constants[sel]
+        filt = Fp2(1)
+        for j in list(cd.selectors_info.groups[sel]) + ([plonk.UNUSED_SELECTOR] if nsel > 1 else []):
+            if j != i:
+                filt = filt * (j - s)
+        for t, r in enumerate(gate.eval_unfiltered(vars_.remove_prefix(nsel + cd.num_lookup_selectors))):
+            constraint_terms[t] = constraint_terms[t] + Fp2.of(r) * filt
+    xn = x
+    for _ in range(cd.degree_bits):
+        xn = xn * xn
+    z_h_zeta = xn - 1
+    l_0_x = z_h_zeta * ((x - 1) * n).inverse()                                 # eval_l_0, plonk_common.rs:69-79
+    nr, qdf, nprod = cfg.num_routed_wires, cd.quotient_degree_factor, cd.num_partial_products
+    z1, pp_terms, lookup_terms = [], [], []
+
+    def product(vs):
+        acc = Fp2(1)
+        for v in vs:
+            acc = acc * v
+        return acc
+
+    for i in range(nc):
+        z1.append(l_0_x * (zs[i] - 1))
+        if cd.luts:
+            npoly = cd.num_lookup_polys
+            d = deltas[4 * i:4 * i + 4]
+            lookup_terms += [Fp2.of(v) for v in plonk.check_lookup_constraints(
+                cd, vars_, lk[npoly * i:npoly * (i + 1)], lk_next[npoly * i:npoly * (i + 1)],
+                constants[nsel:nsel + cd.num_lookup_selectors], d, cd.lut_re_poly_evals(d), product)]
+        num = [wires[j] + x * (betas[i] * cd.k_is[j] % P) + gammas[i] for j in range(nr)]
+        den = [wires[j] + sigmas[j] * betas[i] + gammas[i] for j in range(nr)]
+        accs = [zs[i]] + pps[i * nprod:(i + 1) * nprod] + [zs_next[i]]
+        for k in range(nprod + 1):
+            pp_terms.append(accs[k] * product(num[k * qdf:(k + 1) * qdf]) - accs[k + 1] * product(den[k * qdf:(k + 1) * qdf]))
+    terms = z1 + pp_terms + lookup_terms + constraint_terms
+    for i in range(nc):
+        vanishing = Fp2(0)
+        for t in reversed(terms):                                              # reduce_with_powers_multi
+            vanishing = vanishing * alphas[i] + t
+        chunk = Fp2(0)
+        for t in reversed(quot[i * qdf:(i + 1) * qdf]):                        # reduce_with_powers(chunk, zeta^n)
+            chunk = chunk * xn + t
+        if not vanishing == z_h_zeta * chunk:
+            return "vanishing polynomial identity fails for challenge %d" % i
+    batches, num_polys = fri_batches(cd, zeta)
+    params = oracle.make_params(cfg.rate_bits, cfg.cap_height, fri_cfg.proof_of_work_bits, fri_cfg.num_query_rounds, arity_bits)
+    rc = oracle.verify_fri_proof([parts["constants_sigmas_cap"], parts["wires_cap"], parts["zs_cap"], parts["quotient_cap"]],
+                                 num_polys, num_polys, batches, np.concatenate([zeta_batch.reshape(-1), next_batch.reshape(-1)]),
+                                 cd.degree_bits, ch, params, parts["fri_bytes"])
+    return None if rc == 0 else "FRI proof rejected (rc=%d)" % rc

@@ -399,3 +399,61 @@ def test_plonk_quotient_of_a_bad_witness_is_rejected(pb):
         plonk.compute_quotient_polys(cd, cs, c.public_inputs_hash, w, z, betas, gammas, alphas)
     for b in (cs, w, z):
         b.close()
+
+
+# ----------------------------------------------------------------------------- the whole proof
+def _fri_cfg(c):
+    from plonky2_b200.fri import FriConfig
+
+    # standard_recursion_config's FRI shape with fewer queries / grinding bits so that the CPU twin stays quick
+    return FriConfig(rate_bits=c.config.rate_bits, cap_height=c.config.cap_height, proof_of_work_bits=6,
+                     reduction_strategy=("ConstantArityBits", 2, 2), num_query_rounds=6)
+
+
+PROOF_SHAPES = [SHAPES[0], SHAPES[3], SHAPES[6]]
+
+
+@pytest.mark.parametrize("shape", PROOF_SHAPES)
+def test_whole_proof_is_accepted_by_the_restated_verifier(oracle, shape):
+    """prove (plonk/prover.rs:132-360) assembled from the oracle's restatements produces a ProofWithPublicInputs that
+    verify (plonk/verifier.rs:20-120) accepts: transcript replay, the vanishing-polynomial identity at zeta in F_{p^2},
+    the FRI opening proof; and rejects after tampering with an opening or with the public inputs."""
+    import plonk_circuits as PC
+
+    plonk = _plonk()
+    c = _circuit(shape, public_inputs=[3, 1, 4, 1, 5])
+    digest = [int(x) for x in synth(0x590, (4,))]
+    fri_cfg = _fri_cfg(c)
+    proof_bytes, parts = PC.oracle_prove(oracle, c, digest, fri_cfg, c.public_inputs)
+    assert PC.oracle_verify(oracle, plonk, c, digest, fri_cfg, parts) is None
+    bad = dict(parts, openings=dict(parts["openings"]))
+    w = bad["openings"]["wires"].copy()
+    w[0, 0] ^= np.uint64(1)
+    bad["openings"]["wires"] = w
+    assert PC.oracle_verify(oracle, plonk, c, digest, fri_cfg, bad) is not None
+    bad = dict(parts, public_inputs=[3, 1, 4, 1, 6])
+    assert PC.oracle_verify(oracle, plonk, c, digest, fri_cfg, bad) is not None
+    assert PC.oracle_verify(oracle, plonk, c, [digest[0] ^ 1] + digest[1:], fri_cfg, parts) is not None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", PROOF_SHAPES)
+def test_prove_on_device_is_byte_identical_to_the_cpu_prover(pb, oracle, shape):
+    """plonk.prove_with_witness: wires commitment, Z / partial products (+ lookups), quotient, openings and FRI on the
+    device, the transcript on the host -- write_proof_with_public_inputs equals the CPU twin's bytes, which the restated
+    verifier accepts."""
+    import plonk_circuits as PC
+
+    from plonky2_b200 import plonk
+
+    c = _circuit(shape, public_inputs=[3, 1, 4, 1, 5])
+    cfg, cd = c.config, c.common
+    digest = [int(x) for x in synth(0x590, (4,))]
+    fri_cfg = _fri_cfg(c)
+    want, parts = PC.oracle_prove(oracle, c, digest, fri_cfg, c.public_inputs)
+    assert PC.oracle_verify(oracle, plonk, c, digest, fri_cfg, parts) is None
+    cs = pb.PolynomialBatch.from_values(c.constants_sigmas, cfg.rate_bits, False, cfg.cap_height)
+    prover_data = plonk.ProverOnlyCircuitData(cs, c.sigmas, digest, fri_cfg.fri_params(cd.degree_bits, False))
+    proof = plonk.prove_with_witness(prover_data, cd, c.wires, c.public_inputs)
+    assert proof.to_bytes() == want
+    cs.close()
