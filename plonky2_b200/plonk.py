@@ -1523,14 +1523,22 @@ def get_fri_instance(cd, zeta):
                                      FriBatchInfo(zeta_next, FriPolynomialInfo.from_range(2, range(nc)) + lookup)])
 
 
+def _to_device(columns, ctx):
+    """Host value columns -> torch int64 tensor on the context's GPU (the layout gl_partial_products_and_zs reads)."""
+    import torch
+
+    dev = "cuda:%d" % ctx.device
+    t = torch.from_numpy(np.ascontiguousarray(columns, dtype=np.uint64).view(np.int64)).to(dev)
+    torch.cuda.synchronize(dev)
+    return t
+
+
 def prove_with_witness(prover_data, common_data, wires, public_inputs, ctx=None):
     """prove_with_partition_witness (plonk/prover.rs:132-360) from the full witness matrix `wires` (num_wires, n) -- the
     generators' output -- to ProofWithPublicInputs, every array-sized step on the device: wires commitment, Z / partial
     products (+ lookup) commitment, quotient polynomials from the LDEs in place and their commitment, the openings at
     zeta and g zeta, the FRI opening proof. The transcript runs on the host exactly as in the reference.
     zero_knowledge = false (no blinding)."""
-    import torch
-
     from .challenger import Challenger
     from .fri import prove_openings
     from .hash import PoseidonHash
@@ -1571,10 +1579,7 @@ def prove_with_witness(prover_data, common_data, wires, public_inputs, ctx=None)
             zs_commitment = PolynomialBatch.from_values(np.concatenate([np.stack(zs + pps), lookup_polys]), cfg.rate_bits,
                                                         False, cfg.cap_height, ctx=ctx)
         else:
-            dev = "cuda:%d" % ctx.device
-            wires_dev = torch.from_numpy(wires[:nr].view(np.int64)).to(dev)
-            sigmas_dev = torch.from_numpy(np.ascontiguousarray(prover_data.sigmas, dtype=np.uint64).view(np.int64)).to(dev)
-            torch.cuda.synchronize(dev)
+            wires_dev, sigmas_dev = _to_device(wires[:nr], ctx), _to_device(prover_data.sigmas, ctx)
             zs_commitment = commit_zs_partial_products(wires_dev, sigmas_dev, cd.k_is, betas, gammas,
                                                        cd.quotient_degree_factor, cfg.rate_bits, cfg.cap_height, ctx)
         commitments.append(zs_commitment)

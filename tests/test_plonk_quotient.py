@@ -436,6 +436,124 @@ def test_whole_proof_is_accepted_by_the_restated_verifier(oracle, shape):
     assert PC.oracle_verify(oracle, plonk, c, [digest[0] ^ 1] + digest[1:], fri_cfg, parts) is not None
 
 
+@pytest.mark.parametrize("shape", PROOF_SHAPES)
+def test_prove_host_logic_with_cpu_backends(oracle, shape, monkeypatch):
+    """The HOST side of plonk.prove_with_witness -- transcript order, challenge bookkeeping, ranges, FRI instance, proof
+    serialisation -- run on the CPU by standing the oracle's pieces in for the device calls (commitments, Z / partial
+    products, lookup columns, quotient, evaluations, prove_openings): the bytes must equal the CPU twin's. The device calls
+    themselves are compared with the same oracle pieces one by one in the `-m gpu` tests."""
+    import plonk_circuits as PC
+
+    import plonky2_b200.fri as fri_mod
+    import plonky2_b200.hash as hash_mod
+    import plonky2_b200.proof as proof_mod
+    import plonky2_b200.prover as prover_mod
+    from plonky2_b200 import plonk
+
+    c = _circuit(shape, public_inputs=[3, 1, 4, 1, 5])
+    cfg, cd = c.config, c.common
+    digest = [int(x) for x in synth(0x590, (4,))]
+    fri_cfg = _fri_cfg(c)
+    want, _ = PC.oracle_prove(oracle, c, digest, fri_cfg, c.public_inputs)
+
+    class Cap:
+        def __init__(self, hashes):
+            self.hashes = hashes
+
+    class Tree:
+        def __init__(self, commit):
+            self.cap = Cap(commit.cap)
+
+    class Batch:   # a PolynomialBatch whose device work is done by the oracle
+        def __init__(self, commit):
+            self.o, self.merkle_tree, self.num_polys, self.degree_log = commit, Tree(commit), commit.B, commit.log_n
+            self.ctx = ctx
+
+        @classmethod
+        def from_values(cls, values, rate_bits, blinding, cap_height, ctx=None):
+            assert not blinding
+            return cls(oracle.Commit(values, rate_bits, cap_height))
+
+        def close(self):
+            pass
+
+    class Ctx:
+        device, h = 0, None
+
+    ctx = Ctx()
+
+    def commit_zs(wires_dev, sigmas_dev, k_is, betas, gammas, degree, rate_bits, cap_height, ctx=None):
+        assert np.array_equal(wires_dev, c.wires[:cfg.num_routed_wires]) and np.array_equal(sigmas_dev, c.sigmas)
+        return Batch(oracle.Commit(c.oracle_zs_partial_products(oracle, betas, gammas), rate_bits, cap_height))
+
+    def quotient(cd_, cs, pih, w, z, betas, gammas, alphas, deltas=()):
+        return oracle.plonk_quotient(c.oracle_circuit(), cs.o, w.o, z.o, pih, betas, gammas, alphas, deltas)
+
+    def commit_quotient(cd_, q, ctx=None):
+        qdf, n = cd.quotient_degree_factor, c.n
+        chunks = np.concatenate([q[i, :qdf * n].reshape(qdf, n) for i in range(q.shape[0])])
+        return Batch(oracle.Commit(chunks, cfg.rate_bits, cfg.cap_height, is_coeffs=True))
+
+    def evals(requests):
+        return [np.array([oracle.eval_poly_base_at_ext(p, z) for p in b.o.coeffs], dtype=np.uint64).reshape(-1, 2)
+                for b, z in requests]
+
+    class FriBytes:
+        def __init__(self, b):
+            self.b = b
+
+        def to_bytes(self):
+            return self.b
+
+    import plonky2_b200.challenger as challenger_mod
+
+    class LoggingChallenger(challenger_mod.Challenger):   # the product's host transcript, with a log to replay
+        def __init__(self):
+            super().__init__()
+            self.log = []
+
+        def observe_element(self, element):
+            self.log.append(("observe", int(element)))
+            super().observe_element(element)
+
+        def get_challenge(self):
+            v = super().get_challenge()
+            self.log.append(("challenge", v))
+            return v
+
+    def prove_openings(instance, oracles, challenger, fri_params):
+        och = oracle.Challenger()     # continue the product transcript inside the oracle's prover: replay it
+        for kind, v in challenger.log:
+            if kind == "observe":
+                och.observe_element(v)
+            else:
+                assert och.get_challenge() == v
+        batches = [(b.point, [(p.oracle_index, p.polynomial_index) for p in b.polynomials]) for b in instance.batches]
+        assert [o.num_polys for o in instance.oracles] == [b.num_polys for b in oracles]
+        params = oracle.make_params(cfg.rate_bits, cfg.cap_height, fri_cfg.proof_of_work_bits, fri_cfg.num_query_rounds,
+                                    fri_params.reduction_arity_bits)
+        return FriBytes(oracle.prove_openings([b.o for b in oracles], batches, och, params))
+
+    monkeypatch.setattr(challenger_mod, "Challenger", LoggingChallenger)
+    monkeypatch.setattr(plonk, "PolynomialBatch", Batch)
+    monkeypatch.setattr(plonk, "_to_device", lambda columns, ctx: np.ascontiguousarray(columns, dtype=np.uint64))
+    monkeypatch.setattr(plonk, "compute_quotient_polys", quotient)
+    monkeypatch.setattr(plonk, "commit_quotient_polys", commit_quotient)
+    monkeypatch.setattr(prover_mod, "commit_zs_partial_products", commit_zs)
+    monkeypatch.setattr(prover_mod, "wires_permutation_partial_products_and_zs",
+                        lambda w, s, k, beta, gamma, degree, ctx=None: oracle.partial_products_and_zs(w, s, k, beta, gamma, degree))
+    monkeypatch.setattr(prover_mod, "compute_all_lookup_polys",
+                        lambda w, nr, qdf, deltas, rows, nc, ctx=None: np.concatenate(
+                            [oracle.lookup_polys(w, nr, qdf, deltas[4 * k:4 * k + 4], rows) for k in range(nc)]))
+    monkeypatch.setattr(proof_mod, "eval_commitments", evals)
+    monkeypatch.setattr(fri_mod, "prove_openings", prove_openings)
+    monkeypatch.setattr(hash_mod.PoseidonHash, "hash_no_pad", staticmethod(lambda x, ctx=None: oracle.hash_no_pad(x)))
+    cs = Batch(oracle.Commit(c.constants_sigmas, cfg.rate_bits, cfg.cap_height))
+    prover_data = plonk.ProverOnlyCircuitData(cs, c.sigmas, digest, fri_cfg.fri_params(cd.degree_bits, False))
+    proof = plonk.prove_with_witness(prover_data, cd, c.wires, c.public_inputs, ctx=ctx)
+    assert proof.to_bytes() == want
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", PROOF_SHAPES)
 def test_prove_on_device_is_byte_identical_to_the_cpu_prover(pb, oracle, shape):
