@@ -56,7 +56,7 @@ def _circuit(shape, **kw):
     if len(shape) > 7:
         kw.setdefault("lookups", shape[7])
     cfg = plonk.CircuitConfig(num_wires=nw, num_routed_wires=nr, max_quotient_degree_factor=qdf, rate_bits=rate_bits,
-                              cap_height=1)
+                              cap_height=1, num_challenges=kw.pop("num_challenges", 2))
     return PC.FibonacciCircuit(plonk, cfg, degree_bits, seed=nw + qdf + len(shape), **kw)
 
 
@@ -222,6 +222,21 @@ def test_selector_groups_follow_the_reference_rule():
         _circuit((12, 8, 2, 1, 3))
 
 
+@pytest.mark.parametrize("nc", [1, 3, 4])
+def test_other_challenge_counts_through_the_kernel_source(oracle, nc):
+    """num_challenges = 1, 3, 4 (the kernel's accumulator bound): identity for the oracle, bit-exactness for the program."""
+    for shape in (SHAPES[1], SHAPES[6]):
+        c = _circuit(shape, num_challenges=nc)
+        betas, gammas, alphas = _challenges(0x5A0 + nc, nc)
+        deltas = _deltas(c, 0x5A1)
+        cs, w, z = _oracle_commits(oracle, c, betas, gammas, deltas)
+        q = oracle.plonk_quotient(c.oracle_circuit(), cs, w, z, c.public_inputs_hash, betas, gammas, alphas, deltas)
+        zeta = int(synth(0x5A2, (1,))[0])
+        want, zh = _vanishing_at(c, cs, w, z, zeta, betas, gammas, alphas, deltas)
+        assert all(want[i] == zh * _ev(q[i], zeta) % P_ for i in range(nc))
+        assert np.array_equal(_emu_quotient(oracle, c, cs, w, z, betas, gammas, alphas, deltas), q)
+
+
 def _emu_lib():
     out = "/tmp/libgl_vanishing_emu.so"
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-DGL_FORCE_32BIT_PATH", "-shared", "-fPIC", "-o", out,
@@ -229,15 +244,10 @@ def _emu_lib():
     return C.CDLL(out)
 
 
-@pytest.mark.parametrize("shape", SHAPES)
-def test_vanishing_program_through_the_kernel_source_on_host_matches_oracle(oracle, shape):
-    c = _circuit(shape)
+def _emu_quotient(oracle, c, cs, w, z, betas, gammas, alphas, deltas):
+    """The product's program interpreted by the kernel's per-point source on the host, then coset_ifft."""
     cfg, cd = c.config, c.common
     nc = cfg.num_challenges
-    betas, gammas, alphas = _challenges(0x540 + shape[0], nc)
-    deltas = _deltas(c, 0x541)
-    cs, w, z = _oracle_commits(oracle, c, betas, gammas, deltas)
-    want = oracle.plonk_quotient(c.oracle_circuit(), cs, w, z, c.public_inputs_hash, betas, gammas, alphas, deltas)
     b = cd.vanishing_program()
     prog, n_regs = b.compile()
     assert n_regs <= 64            # the schedule keeps the register set small (L1-resident on the device)
@@ -255,8 +265,18 @@ def test_vanishing_program_through_the_kernel_source_on_host_matches_oracle(orac
     rc = L.emu_plonk_quotient_values(ptrs, strides, 3, cfg.rate_bits, cd.degree_bits, qd_bits, prog, len(prog),
                                      consts.ctypes.data, al.ctypes.data, nc, cd.num_vanishing_terms(), vals.ctypes.data)
     assert rc == 0
-    got = np.stack([oracle.coset_ifft(v, 14293326489335486720) for v in vals])   # .coset_ifft(F::coset_shift())
-    assert np.array_equal(got, want)
+    return np.stack([oracle.coset_ifft(v, 14293326489335486720) for v in vals])   # .coset_ifft(F::coset_shift())
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_vanishing_program_through_the_kernel_source_on_host_matches_oracle(oracle, shape):
+    c = _circuit(shape)
+    nc = c.config.num_challenges
+    betas, gammas, alphas = _challenges(0x540 + shape[0], nc)
+    deltas = _deltas(c, 0x541)
+    cs, w, z = _oracle_commits(oracle, c, betas, gammas, deltas)
+    want = oracle.plonk_quotient(c.oracle_circuit(), cs, w, z, c.public_inputs_hash, betas, gammas, alphas, deltas)
+    assert np.array_equal(_emu_quotient(oracle, c, cs, w, z, betas, gammas, alphas, deltas), want)
 
 
 @pytest.mark.parametrize("broken", ["pair", "table"])
