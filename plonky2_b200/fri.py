@@ -182,6 +182,41 @@ class FriProof:
         put(np.array([self.pow_witness], dtype=np.uint64))
         return bytes(out)
 
+    @classmethod
+    def from_bytes(cls, buf, leaf_widths, params, offset=0):
+        """read_fri_proof (util/serialization/mod.rs:564-587): leaf_widths = the oracles' leaf widths (polynomials + salt),
+        the rest of the shape comes from the FriParams. Returns (FriProof, next offset)."""
+        cap_len = 1 << params.config.cap_height
+        pos = offset
+
+        def words(count, shape):
+            nonlocal pos
+            a = np.frombuffer(buf, dtype="<u8", count=count, offset=pos).astype(np.uint64).reshape(shape)
+            pos += 8 * count
+            return a
+
+        def merkle_proof():
+            nonlocal pos
+            length = buf[pos]
+            pos += 1
+            return words(4 * length, (length, NUM_HASH_OUT_ELTS))
+
+        caps = [MerkleCap(words(4 * cap_len, (cap_len, NUM_HASH_OUT_ELTS))) for _ in params.reduction_arity_bits]
+        rounds = []
+        for _ in range(params.config.num_query_rounds):
+            evals_proofs = []
+            for w in leaf_widths:
+                leaf = words(w, (w,))
+                evals_proofs.append((leaf, merkle_proof()))
+            steps = []
+            for ab in params.reduction_arity_bits:
+                evals = words(2 << ab, (1 << ab, 2))
+                steps.append(FriQueryStep(evals, merkle_proof()))
+            rounds.append(FriQueryRound(FriInitialTreeProof(evals_proofs), steps))
+        final_poly = words(2 * params.final_poly_len(), (params.final_poly_len(), 2))
+        pow_witness = int(words(1, (1,))[0])
+        return cls(caps, rounds, final_poly, pow_witness), pos
+
     def compress(self, indices, params):
         """FriProof::compress (fri/proof.rs:137-238): per Merkle tree, drop the siblings the verifier can recompute from
         the other queries (compress_merkle_proofs), drop from every step the evaluation it can infer, and keep one entry
@@ -311,6 +346,22 @@ class CompressedFriProof:
                 steps.append(FriQueryStep(st_evals[j][k], st_full[j][k].siblings))
             rounds.append(FriQueryRound(init, steps))
         return FriProof(self.commit_phase_merkle_caps, rounds, self.final_poly, self.pow_witness)
+
+
+def fri_challenges(challenger, commit_phase_merkle_caps, final_poly, pow_witness, degree_bits, config):
+    """Challenger::fri_challenges (fri/challenges.rs:28-75): what the verifier (and ProofWithPublicInputs::compress)
+    re-derives from a proof. Returns (fri_alpha, fri_betas, fri_pow_response, fri_query_indices)."""
+    lde_size = 1 << (degree_bits + config.rate_bits)
+    fri_alpha = challenger.get_extension_challenge()
+    fri_betas = []
+    for cap in commit_phase_merkle_caps:
+        challenger.observe_cap(cap)
+        fri_betas.append(challenger.get_extension_challenge())
+    challenger.observe_elements(np.asarray(final_poly, dtype=np.uint64).reshape(-1))
+    challenger.observe_element(pow_witness)
+    fri_pow_response = challenger.get_challenge()
+    fri_query_indices = [challenger.get_challenge() % lde_size for _ in range(config.num_query_rounds)]
+    return fri_alpha, fri_betas, fri_pow_response, fri_query_indices
 
 
 # ------------------------------------------------------------------ prover

@@ -95,6 +95,17 @@ class PoseidonHash:
         return PoseidonHash.hash_no_pad_many(np.asarray(inputs, dtype=np.uint64).reshape(1, -1), ctx)[0]
 
     @staticmethod
+    def hash_no_pad_host(inputs):
+        """hash_n_to_hash_no_pad (hash/hashing.rs:96-123) on the HOST permutation: for the verifier-side replays of a
+        transcript (a handful of elements), where a device round trip buys nothing."""
+        perm = PoseidonPermutation()
+        inputs = [int(x) for x in inputs]
+        for at in range(0, len(inputs), SPONGE_RATE):
+            perm.set_from_slice(inputs[at:at + SPONGE_RATE], 0)
+            perm.permute()
+        return np.array(perm.squeeze()[:NUM_HASH_OUT_ELTS], dtype=np.uint64)
+
+    @staticmethod
     def hash_pad(inputs, ctx=None):
         """pad10*1 then hash_no_pad (config.rs:50-59)."""
         padded = [int(x) for x in inputs] + [1]

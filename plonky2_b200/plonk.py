@@ -1490,6 +1490,52 @@ class Proof:
         return out + self.opening_proof.to_bytes()
 
 
+    def compress(self, indices, params):
+        """Proof::compress (plonk/proof.rs:56-76)."""
+        return CompressedProof(self.wires_cap, self.plonk_zs_partial_products_cap, self.quotient_polys_cap, self.openings,
+                               self.opening_proof.compress(indices, params))
+
+    @classmethod
+    def from_bytes(cls, buf, common_data, fri_params, offset=0):
+        """read_proof (util/serialization/mod.rs: read_merkle_cap x3, read_opening_set, read_fri_proof). Returns
+        (Proof, next offset)."""
+        from .fri import FriProof
+        from .hash import MerkleCap
+        from .proof import OpeningSet
+
+        cd, cfg = common_data, common_data.config
+        nc = cfg.num_challenges
+        pos = offset
+
+        def words(count, shape):
+            nonlocal pos
+            a = np.frombuffer(buf, dtype="<u8", count=count, offset=pos).astype(np.uint64).reshape(shape)
+            pos += 8 * count
+            return a
+
+        cap_len = 1 << cfg.cap_height
+        caps = [MerkleCap(words(4 * cap_len, (cap_len, 4))) for _ in range(3)]
+
+        def ext_vec(k):
+            return words(2 * k, (k, 2))
+
+        n_lookup = nc * cd.num_lookup_polys
+        constants, sigmas, wires = ext_vec(cd.num_constants), ext_vec(cfg.num_routed_wires), ext_vec(cfg.num_wires)
+        zs, zs_next, lk, lk_next = ext_vec(nc), ext_vec(nc), ext_vec(n_lookup), ext_vec(n_lookup)
+        pps, quot = ext_vec(nc * cd.num_partial_products), ext_vec(nc * cd.quotient_degree_factor)
+        openings = OpeningSet(constants=constants, plonk_sigmas=sigmas, wires=wires, plonk_zs=zs, plonk_zs_next=zs_next,
+                              partial_products=pps, quotient_polys=quot, lookup_zs=lk, lookup_zs_next=lk_next)
+        widths = [cd.num_constants + cfg.num_routed_wires, cfg.num_wires,
+                  nc * (1 + cd.num_partial_products + cd.num_lookup_polys), nc * cd.quotient_degree_factor]
+        fri, pos = FriProof.from_bytes(buf, widths, fri_params, pos)
+        return cls(caps[0], caps[1], caps[2], openings, fri), pos
+
+
+class CompressedProof(Proof):
+    """CompressedProof (plonk/proof.rs:128-141): a Proof whose opening_proof is a CompressedFriProof; to_bytes =
+    write_compressed_proof (util/serialization/mod.rs:2080-2093)."""
+
+
 class ProofWithPublicInputs:
     """ProofWithPublicInputs (plonk/proof.rs:82-88)."""
 
@@ -1500,6 +1546,64 @@ class ProofWithPublicInputs:
         """write_proof_with_public_inputs (util/serialization/mod.rs:2001-2015)."""
         pis = np.array(self.public_inputs, dtype=np.uint64)
         return self.proof.to_bytes() + _le_words(np.array([len(pis)], dtype=np.uint64)) + _le_words(pis)
+
+    @classmethod
+    def from_bytes(cls, buf, common_data, fri_params):
+        """read_proof_with_public_inputs (util/serialization/mod.rs)."""
+        proof, pos = Proof.from_bytes(buf, common_data, fri_params)
+        n = int(np.frombuffer(buf, dtype="<u8", count=1, offset=pos)[0])
+        pis = np.frombuffer(buf, dtype="<u8", count=n, offset=pos + 8)
+        if pos + 8 + 8 * n != len(buf):
+            raise N.ShapeError("trailing bytes after the proof")
+        return cls(proof, [int(x) for x in pis])
+
+    def get_public_inputs_hash(self):
+        from .hash import PoseidonHash
+
+        return [int(x) for x in PoseidonHash.hash_no_pad_host(self.public_inputs)]
+
+    def get_challenges(self, circuit_digest, common_data, fri_params):
+        """get_challenges (plonk/get_challenges.rs:26-90): the transcript replayed on the host from the proof alone."""
+        from .challenger import Challenger
+        from .fri import fri_challenges
+
+        cd, p = common_data, self.proof
+        nc = cd.config.num_challenges
+        ch = Challenger()
+        fri_params.observe(ch)
+        ch.observe_hash(circuit_digest)
+        ch.observe_hash(self.get_public_inputs_hash())
+        ch.observe_cap(p.wires_cap)
+        betas, gammas = ch.get_n_challenges(nc), ch.get_n_challenges(nc)
+        deltas = (betas + gammas + ch.get_n_challenges(NUM_COINS_LOOKUP * nc - 2 * nc)) if cd.num_lookup_polys else []
+        ch.observe_cap(p.plonk_zs_partial_products_cap)
+        alphas = ch.get_n_challenges(nc)
+        ch.observe_cap(p.quotient_polys_cap)
+        zeta = ch.get_extension_challenge()
+        for batch in p.openings.to_fri_openings():
+            ch.observe_elements(batch.reshape(-1))
+        fp = p.opening_proof
+        fri_alpha, fri_betas, fri_pow_response, indices = fri_challenges(ch, fp.commit_phase_merkle_caps, fp.final_poly,
+                                                                         fp.pow_witness, cd.degree_bits, fri_params.config)
+        return dict(plonk_betas=betas, plonk_gammas=gammas, plonk_deltas=deltas, plonk_alphas=alphas, plonk_zeta=zeta,
+                    fri_alpha=fri_alpha, fri_betas=fri_betas, fri_pow_response=fri_pow_response, fri_query_indices=indices)
+
+    def fri_query_indices(self, circuit_digest, common_data, fri_params):
+        return self.get_challenges(circuit_digest, common_data, fri_params)["fri_query_indices"]
+
+    def compress(self, circuit_digest, common_data, fri_params):
+        """ProofWithPublicInputs::compress (plonk/proof.rs:93-104)."""
+        indices = self.fri_query_indices(circuit_digest, common_data, fri_params)
+        return CompressedProofWithPublicInputs(self.proof.compress(indices, fri_params), self.public_inputs)
+
+
+class CompressedProofWithPublicInputs(ProofWithPublicInputs):
+    """CompressedProofWithPublicInputs (plonk/proof.rs:163-170)."""
+
+    def to_bytes(self):
+        """write_compressed_proof_with_public_inputs (util/serialization/mod.rs:2097-2111): the public inputs follow
+        without a length."""
+        return self.proof.to_bytes() + _le_words(np.array(self.public_inputs, dtype=np.uint64))
 
 
 def get_fri_instance(cd, zeta):

@@ -507,7 +507,7 @@ def observe_fri_params(ch, fri_cfg, degree_bits, arity_bits):
     ch.observe_elements([0, degree_bits] + list(arity_bits))
 
 
-def oracle_prove(oracle, c, circuit_digest, fri_cfg, public_inputs):
+def oracle_prove(oracle, c, circuit_digest, fri_cfg, public_inputs, taps=False):
     """prove_with_partition_witness with the oracle's pieces. Returns (proof bytes = write_proof_with_public_inputs,
     parts) where parts carries what the verifier reads from the proof."""
     cd, cfg = c.common, c.config
@@ -552,7 +552,11 @@ def oracle_prove(oracle, c, circuit_digest, fri_cfg, public_inputs):
     ch.observe_elements(zeta_batch.reshape(-1))
     ch.observe_elements(next_batch.reshape(-1))
     params = oracle.make_params(cfg.rate_bits, cfg.cap_height, fri_cfg.proof_of_work_bits, fri_cfg.num_query_rounds, arity_bits)
-    fri_bytes = oracle.prove_openings(commits, batches, ch, params)
+    fri_taps = None
+    if taps:
+        fri_bytes, fri_taps = oracle.prove_openings(commits, batches, ch, params, taps=True)
+    else:
+        fri_bytes = oracle.prove_openings(commits, batches, ch, params)
 
     def le(a):
         return np.ascontiguousarray(a, dtype="<u8").tobytes()
@@ -563,7 +567,7 @@ def oracle_prove(oracle, c, circuit_digest, fri_cfg, public_inputs):
         out += le(o[k])
     out += fri_bytes + le(np.array([len(public_inputs)], dtype=np.uint64)) + le(np.array(public_inputs, dtype=np.uint64))
     parts = dict(constants_sigmas_cap=cs.cap, wires_cap=wc.cap, zs_cap=zc.cap, quotient_cap=qc.cap, openings=o,
-                 fri_bytes=fri_bytes, public_inputs=list(public_inputs))
+                 fri_bytes=fri_bytes, public_inputs=list(public_inputs), taps=fri_taps)
     return out, parts
 
 

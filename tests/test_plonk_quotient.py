@@ -595,3 +595,35 @@ def test_prove_on_device_is_byte_identical_to_the_cpu_prover(pb, oracle, shape):
     proof = plonk.prove_with_witness(prover_data, cd, c.wires, c.public_inputs)
     assert proof.to_bytes() == want
     cs.close()
+
+
+@pytest.mark.parametrize("shape", PROOF_SHAPES)
+def test_proof_bytes_round_trip_challenges_and_compression(oracle, shape):
+    """read_proof_with_public_inputs / write_... round trip on the CPU prover's bytes; get_challenges replayed by the
+    product's host code gives the prover's own query indices and grinding witness; Proof::compress shrinks the proof and
+    keeps one initial-tree proof per distinct index."""
+    import plonk_circuits as PC
+
+    plonk = _plonk()
+    c = _circuit(shape, public_inputs=[3, 1, 4, 1, 5])
+    digest = [int(x) for x in synth(0x590, (4,))]
+    fri_cfg = _fri_cfg(c)
+    fri_params = fri_cfg.fri_params(c.common.degree_bits, False)
+    data, parts = PC.oracle_prove(oracle, c, digest, fri_cfg, c.public_inputs, taps=True)
+    proof = plonk.ProofWithPublicInputs.from_bytes(data, c.common, fri_params)
+    assert proof.to_bytes() == data and proof.public_inputs == [3, 1, 4, 1, 5]
+    assert proof.get_public_inputs_hash() == c.public_inputs_hash
+    ch = proof.get_challenges(digest, c.common, fri_params)
+    assert ch["fri_query_indices"] == [int(i) for i in parts["taps"]["query_indices"]]
+    assert proof.proof.opening_proof.pow_witness == parts["taps"]["pow_witness"]
+    assert [tuple(int(x) for x in b) for b in parts["taps"]["betas"]] == [tuple(b) for b in ch["fri_betas"]]
+    lz = 64 - int(ch["fri_pow_response"]).bit_length()
+    assert lz >= fri_cfg.proof_of_work_bits                                   # the grinding check of the verifier
+    comp = proof.compress(digest, c.common, fri_params)
+    cbytes = comp.to_bytes()
+    assert len(cbytes) < len(data)
+    distinct = sorted(set(ch["fri_query_indices"]))
+    assert sorted(comp.proof.opening_proof.initial_trees_proofs) == distinct
+    # the caps, openings, final polynomial and witness are carried over untouched
+    head = 3 * 4 * 8 * (1 << c.config.cap_height)
+    assert cbytes[:head] == data[:head]
