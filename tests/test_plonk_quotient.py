@@ -1,14 +1,18 @@
-"""plonky2's compute_quotient_polys.
+"""plonky2's compute_quotient_polys and the prover around it.
 
 CPU (`-m "not gpu"`):
-  * the oracle's restatement is pinned by the verifier's own check (plonky2/src/plonk/verifier.rs:85-107):
+  * the oracle's restatement of the quotient is pinned by the verifier's own check (plonky2/src/plonk/verifier.rs:85-107):
     vanishing_polys_zeta[i] == Z_H(zeta) * reduce_with_powers(quotient chunks at zeta, zeta^n), with the vanishing
-    polynomial evaluated at zeta by a third, plain-Python evaluation of eval_vanishing_poly (vanishing_poly.rs:29-164);
-    a witness that breaks a gate or a copy constraint must fail it;
+    polynomial re-evaluated at zeta in plain Python (vanishing_poly.rs:29-164), for circuits holding rows of every gate
+    type and a lookup table; a witness that breaks any one gate, a copy constraint, a looking pair or a table row fails it;
   * the product's vanishing PROGRAM (plonky2_b200/plonk.py) run by the kernel's own per-point source
-    (plonky2_b200/csrc/gl_vanishing.cuh compiled for the host) equals the oracle bit for bit.
+    (plonky2_b200/csrc/gl_vanishing.cuh compiled for the host) equals the oracle bit for bit;
+  * a whole ProofWithPublicInputs assembled from the oracle's pieces is accepted by a restated verify() (transcript
+    replay, vanishing identity in F_{p^2}, FRI) and rejected after tampering; the product's prover host logic, proof
+    readers, get_challenges and compression are run against it with the oracle standing in for the device calls.
 GPU (`-m gpu`): gl_plonk_quotient through the C ABI equals the oracle bit for bit, chained after the device-resident
-Z / partial-products commitment; the quotient commitment equals from_coeffs of the oracle's chunks."""
+Z / partial-products commitment; the quotient commitment equals from_coeffs of the oracle's chunks; prove_with_witness
+produces the CPU prover's bytes."""
 import ctypes as C
 import os
 import subprocess
