@@ -40,6 +40,7 @@ SHAPES = [
 NUM_EXTRA = len(SHAPES[5][6])
 # ... plus a lookup table of 30 entries on two LookupTableGate rows and 80 lookups on two LookupGate rows
 SHAPES.append(SHAPES[5] + (True,))
+LOOKUP_SHAPE_64 = SHAPES[6][:4] + (6,) + SHAPES[6][5:]     # the same circuit on 64 rows (the GPU cases use this one)
 
 
 def _plonk():
@@ -272,7 +273,7 @@ def _emu_quotient(oracle, c, cs, w, z, betas, gammas, alphas, deltas):
     return np.stack([oracle.coset_ifft(v, 14293326489335486720) for v in vals])   # .coset_ifft(F::coset_shift())
 
 
-@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("shape", SHAPES + [LOOKUP_SHAPE_64, (135, 80, 8, 3, 6, 20), (135, 80, 8, 3, 7)])
 def test_vanishing_program_through_the_kernel_source_on_host_matches_oracle(oracle, shape):
     c = _circuit(shape)
     nc = c.config.num_challenges
@@ -352,7 +353,7 @@ def pb():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[1], (135, 80, 8, 3, 7), (135, 80, 8, 3, 6, 20), SHAPES[5], SHAPES[6]])
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[1], (135, 80, 8, 3, 7), (135, 80, 8, 3, 6, 20), SHAPES[5], LOOKUP_SHAPE_64])
 def test_plonk_quotient_on_device_matches_oracle(pb, oracle, shape):
     """The prover's third phase without leaving the device (plonk/prover.rs:220-352): wires + constants_sigmas
     commitments -> Z / partial products commitment (device) -> quotient polynomials (device, LDEs read in place) ->
@@ -434,7 +435,7 @@ def _fri_cfg(c):
                      reduction_strategy=("ConstantArityBits", 2, 2), num_query_rounds=6)
 
 
-PROOF_SHAPES = [SHAPES[0], SHAPES[3], SHAPES[6]]
+PROOF_SHAPES = [SHAPES[0], SHAPES[3], LOOKUP_SHAPE_64]
 
 
 @pytest.mark.parametrize("shape", PROOF_SHAPES)
