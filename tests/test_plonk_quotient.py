@@ -632,3 +632,56 @@ def test_proof_bytes_round_trip_challenges_and_compression(oracle, shape):
     # the caps, openings, final polynomial and witness are carried over untouched
     head = 3 * 4 * 8 * (1 << c.config.cap_height)
     assert cbytes[:head] == data[:head]
+
+
+# ----------------------------------------------------------------------------- the reference's own gate test
+def _all_gates():
+    plonk = _plonk()
+    cfg = plonk.CircuitConfig()
+    return [plonk.NoopGate(), plonk.ConstantGate(2), plonk.PublicInputGate(), plonk.ArithmeticGate.new_from_config(cfg),
+            plonk.ArithmeticExtensionGate.new_from_config(cfg), plonk.MulExtensionGate.new_from_config(cfg),
+            plonk.BaseSumGate.new_from_config(cfg, 2), plonk.BaseSumGate(31, 4), plonk.ReducingGate(43),
+            plonk.ReducingExtensionGate(32), plonk.ExponentiationGate.new_from_config(cfg),
+            plonk.RandomAccessGate.new_from_config(cfg, 4), plonk.RandomAccessGate.new_from_config(cfg, 1),
+            plonk.PoseidonMdsGate(), plonk.PoseidonGate(), plonk.CosetInterpolationGate(4, 8), plonk.CosetInterpolationGate(2),
+            plonk.LookupGate.new_from_config(cfg), plonk.LookupTableGate.new_from_config(cfg)]
+
+
+@pytest.mark.parametrize("k", range(19))
+def test_low_degree_like_the_reference_gate_tests(oracle, k):
+    """test_low_degree (plonky2/src/gates/gate_testing.rs:22-68), which every gate file of the reference runs: the
+    constraints applied to random witness polynomials of degree < 32 are polynomials of degree <= 31 * gate.degree()
+    (the value the selector grouping relies on) and there are num_constraints() of them. Beyond the reference: the bound
+    is attained, so no gate over-declares its degree."""
+    import plonk_circuits as PC
+
+    gate = _all_gates()[k]
+    WITNESS_SIZE = 32
+    rate_bits = gate.degree().bit_length()            # log2_ceil(degree + 1)
+    size = WITNESS_SIZE << rate_bits
+    rng = np.random.default_rng(1000 + k)
+
+    def random_low_degree_matrix(num_polys):
+        cols = []
+        for _ in range(num_polys):
+            coeffs = np.zeros(size, dtype=np.uint64)
+            coeffs[:WITNESS_SIZE] = PC.rnd(rng, WITNESS_SIZE)
+            cols.append(oracle.fft(coeffs))            # .lde(rate_bits).fft()
+        return np.stack(cols) if cols else np.zeros((0, size), dtype=np.uint64)
+
+    wires, constants = random_low_degree_matrix(gate.num_wires()), random_low_degree_matrix(gate.num_constants())
+    pih = [int(x) for x in PC.rnd(rng, 4)]
+    evals = np.zeros((gate.num_constraints(), size), dtype=np.uint64)
+    for p in range(size):
+        res = gate.eval_unfiltered(PC.PointVars(constants[:, p], wires[:, p], pih))
+        assert len(res) == gate.num_constraints(), "eval should return num_constraints() constraints"
+        evals[:, p] = [int(v) for v in res]
+    degrees = []
+    for row in evals:
+        co = oracle.ifft(row)
+        nz = np.nonzero(co)[0]
+        degrees.append(int(nz[-1]) if len(nz) else 0)
+    expected = (WITNESS_SIZE - 1) * gate.degree()
+    assert all(d <= expected for d in degrees), (gate.id()[:40], expected, degrees)
+    if degrees:
+        assert max(degrees) == expected, (gate.id()[:40], expected, max(degrees))
