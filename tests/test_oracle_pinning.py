@@ -402,3 +402,21 @@ def test_batch_fri_proof_passes_the_restated_batch_verifier(oracle):
         flipped = bytearray(proof)
         flipped[len(flipped) // 2] ^= 8
         assert oracle.verify_batch_fri_proof([oo.cap], [counts], lens, instances, ov, vch.clone(), params, bytes(flipped)) != 0
+
+
+def test_partial_products_reference_golden_numbers(oracle):
+    """The reference's own numbers (util/partial_products.rs:118-145): v = [1..6], denominators 1, z_x = 1: chunk products
+    [2, 12, 30] -> partial products [2, 24] and z_gx = 720 at degree 2; [6, 120] -> [6] and 720 at degree 3. Realised
+    through the restated wires_permutation_partial_products_and_zs with w = 0, beta = 1, gamma = 0, k_i = v on row 0
+    (x = 1) and sigma = 1 there: numerators v, denominators 1."""
+    from plonky2_b200.plonk import num_partial_products
+
+    v = [1, 2, 3, 4, 5, 6]
+    wires = np.zeros((6, 2), dtype=np.uint64)
+    sigmas = np.ones((6, 2), dtype=np.uint64)
+    sigmas[:, 1] = synth(0xDE, (6,))      # row 1 is arbitrary
+    for degree, pps in ((2, [2, 24]), (3, [6])):
+        out = oracle.partial_products_and_zs(wires, sigmas, np.array(v, dtype=np.uint64), 1, 0, degree)
+        assert num_partial_products(len(v), degree) == len(pps) == out.shape[0] - 1
+        assert [int(x) for x in out[:-1, 0]] == pps          # the partial products of row 0
+        assert int(out[-1, 0]) == 1 and int(out[-1, 1]) == 720   # Z(1) = 1, Z(g) = z_gx
