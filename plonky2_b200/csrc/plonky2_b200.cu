@@ -1997,19 +1997,24 @@ int gl_plonk_quotient(gl_ctx* ctx, gl_commit* const* commits, uint32_t n_commits
     if (qd_bits > rate_bits)
         return set_err(ctx, GL_ERR_UNSUPPORTED, "Having constraints of degree higher than the rate is not supported yet.");
     if ((1u << qd_bits) > GL_VP_MAX_QD) return set_err(ctx, GL_ERR_UNSUPPORTED, "quotient degree factor too large");
-    for (uint32_t k = 0; k < n_instr; k++) {  // validate once on the host: the kernel trusts the program
-        const gl_vp_instr in = program[k];
-        bool ok = in.dst < GL_VP_MAX_REGS;
-        switch (in.op) {
-            case GL_VP_LOCAL: case GL_VP_NEXT: ok = ok && in.a < n_commits && in.b < commits[in.a]->W; break;
-            case GL_VP_CONST: ok = ok && ((uint32_t)in.a | ((uint32_t)in.b << 16)) < n_consts; break;
-            case GL_VP_X: case GL_VP_L0: break;
-            case GL_VP_ADD: case GL_VP_SUB: case GL_VP_MUL: ok = ok && in.a < GL_VP_MAX_REGS && in.b < GL_VP_MAX_REGS; break;
-            case GL_VP_ADDC: case GL_VP_MULC: ok = ok && in.a < GL_VP_MAX_REGS && in.b < n_consts; break;
-            case GL_VP_TERM: ok = in.a < GL_VP_MAX_REGS && in.b < n_terms; break;
-            default: ok = false;
+    {  // validate once on the host: the kernel trusts the program (operands in range, no register read before it is written)
+        bool written[GL_VP_MAX_REGS] = {false};
+        auto readable = [&](uint16_t r) { return r < GL_VP_MAX_REGS && written[r]; };
+        for (uint32_t k = 0; k < n_instr; k++) {
+            const gl_vp_instr in = program[k];
+            bool ok = in.dst < GL_VP_MAX_REGS;
+            switch (in.op) {
+                case GL_VP_LOCAL: case GL_VP_NEXT: ok = ok && in.a < n_commits && in.b < commits[in.a]->W; break;
+                case GL_VP_CONST: ok = ok && ((uint32_t)in.a | ((uint32_t)in.b << 16)) < n_consts; break;
+                case GL_VP_X: case GL_VP_L0: break;
+                case GL_VP_ADD: case GL_VP_SUB: case GL_VP_MUL: ok = ok && readable(in.a) && readable(in.b); break;
+                case GL_VP_ADDC: case GL_VP_MULC: ok = ok && readable(in.a) && in.b < n_consts; break;
+                case GL_VP_TERM: ok = readable(in.a) && in.b < n_terms; break;
+                default: ok = false;
+            }
+            if (!ok) return set_err(ctx, GL_ERR_BAD_ARG, "vanishing program: bad instruction %u", k);
+            if (in.op != GL_VP_TERM) written[in.dst] = true;
         }
-        if (!ok) return set_err(ctx, GL_ERR_BAD_ARG, "vanishing program: bad instruction %u", k);
     }
     CK(ctx, cudaSetDevice(ctx->device));
     const uint32_t size_log = db + qd_bits;
