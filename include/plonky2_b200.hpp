@@ -393,6 +393,22 @@ class PolynomialBatch {
         }
         return out;
     }
+    // compute_quotient_polys (plonk/prover.rs:609-815) from a recorded vanishing program (include/plonky2_b200.h,
+    // gl_plonk_quotient; plonky2_b200/plonk.py builds such programs from gate lists): the LDEs of `commitments`
+    // (constants_sigmas, wires, zs_partial_products[_lookup]) are read in place; returns num_challenges polynomials of
+    // n << log2_ceil(quotient_degree_factor) coefficients in DEVICE memory at `out_coeffs_device`.
+    static void compute_quotient_polys(const std::vector<const PolynomialBatch*>& commitments,
+                                       const std::vector<gl_vp_instr>& program, const std::vector<F>& consts,
+                                       const std::vector<F>& alphas, uint32_t num_vanishing_terms,
+                                       uint32_t quotient_degree_factor, F* out_coeffs_device) {
+        Context& ctx = commitments.at(0)->context();
+        std::vector<gl_commit*> handles;
+        for (auto* c : commitments) handles.push_back(c->handle());
+        check(gl_plonk_quotient(ctx.get(), handles.data(), uint32_t(handles.size()), program.data(), uint32_t(program.size()),
+                                consts.data(), uint32_t(consts.size()), alphas.data(), uint32_t(alphas.size()),
+                                num_vanishing_terms, quotient_degree_factor, out_coeffs_device), ctx.get());
+    }
+
     // The same commitment assembled from column groups that arrive over time (gl_commit_begin / add_columns / finish):
     // `kind` = GL_COLS_VALUES / GL_COLS_COEFFS / GL_COLS_COEFFS_CANONICAL, `mem` = GL_MEM_HOST / GL_MEM_DEVICE.
     static PolynomialBatch begin(Context& ctx, uint32_t num_polys, uint32_t degree_log, uint32_t rate_bits, uint32_t cap_height,
