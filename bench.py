@@ -575,8 +575,11 @@ def gpu_arm(args, rank, local_rank, world):
             line["prove_recursion_shape"] = recursion_shape(local_rank)
         except Exception as e:  # never lose the headline line to the secondary measurement
             line["prove_recursion_shape"] = {"error": repr(e)}
-        try:
-            line["prove_plonk_circuit"] = plonk_circuit_proof(local_rank)
+        try:   # in a child process with a timeout: new code, not yet run on a GPU -- it must not be able to take the line down
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank)))
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--plonk-circuit-only"], capture_output=True,
+                                 text=True, timeout=300, env=env)
+            line["prove_plonk_circuit"] = json.loads(out.stdout.strip().splitlines()[-1])
         except Exception as e:
             line["prove_plonk_circuit"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
@@ -751,7 +754,14 @@ def main():
     ap.add_argument("--ntt-group", type=int, default=0, help="columns per NTT group (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the recursion-shaped prove() timing")
+    ap.add_argument("--plonk-circuit-only", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.plonk_circuit_only:   # child mode of the secondary measurement `prove_plonk_circuit`
+        try:
+            print(json.dumps(plonk_circuit_proof(0)), flush=True)
+        except Exception as e:
+            print(json.dumps({"error": repr(e)}), flush=True)
+        return
     if args.config:
         args.cols, args.log_n, args.rate_bits, args.cap_height = PRESETS[args.config][:4]
     if args.seed is None:
