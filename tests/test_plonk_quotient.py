@@ -685,3 +685,14 @@ def test_low_degree_like_the_reference_gate_tests(oracle, k):
     assert all(d <= expected for d in degrees), (gate.id()[:40], expected, degrees)
     if degrees:
         assert max(degrees) == expected, (gate.id()[:40], expected, max(degrees))
+
+
+def test_coset_shifts_are_distinct_cosets():
+    """field/src/cosets.rs:26-55 (`distinct_cosets`): the shifts k_i = g^i of get_unique_coset_shifts give pairwise
+    different cosets of the size-2^n subgroup, i.e. (k_i / k_j)^(2^n) != 1 -- what the permutation argument's identity
+    polynomials k_i * x rely on."""
+    plonk = _plonk()
+    shifts = plonk.get_unique_coset_shifts(80)
+    for bits in (5, 12, 20):
+        powered = [pow(k, 1 << bits, P_) for k in shifts]
+        assert len(set(powered)) == len(shifts)
