@@ -1,5 +1,7 @@
 """plonky2's quotient polynomials on the device: compute_quotient_polys
-(plonky2/src/plonk/prover.rs:609-815) over eval_vanishing_poly_base_batch (plonky2/src/plonk/vanishing_poly.rs:167-340).
+(plonky2/src/plonk/prover.rs:609-815) over eval_vanishing_poly_base_batch (plonky2/src/plonk/vanishing_poly.rs:167-340),
+the gates' constraint evaluators (plonky2/src/gates/*.rs), and the prover that strings the device pieces together
+(prove_with_witness = prove_with_partition_witness, plonk/prover.rs:132-360; Proof / CompressedProof and their byte formats).
 
 The reference evaluates, for every point of the quotient coset, each gate's constraints times its selector filter, the
 terms L_0(x)(Z(x) - 1) and the partial-product checks of the permutation argument, and combines them with powers of
